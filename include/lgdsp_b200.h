@@ -1,0 +1,280 @@
+/*
+ * lgdsp_b200.h -- C ABI of the B200-native (sm_100a) implementation of the LegendDSP.jl
+ * `dsp_icpc` hot path and of the trapezoidal filter-optimisation sweeps.
+ *
+ * Every entry point replaces one reference interface; citations are relative to the
+ * reference tree (legend-exp/LegendDSP.jl v0.3.0):
+ *
+ *   lgdsp_icpc_run / lgdsp_icpc_run_device   <- dsp_icpc(data, config, tau, pars_filter)
+ *                                               src/dsp_icpc.jl:62-230
+ *   lgdsp_trap_sweep_run / _device           <- dsp_trap_rt_optimization  src/dsp_filter_optimization.jl:102-133
+ *                                               dsp_trap_ft_optimization  src/dsp_filter_optimization.jl:241-274
+ *   lgdsp_sg_coeffs / lgdsp_lsq_fit_matrix /
+ *   lgdsp_cusp_coeffs / lgdsp_zac_coeffs     <- filter-instance construction that the reference delegates to
+ *                                               RadiationDetectorDSP.jl (fltinstance(...), src/dsp_icpc.jl:157-181)
+ *   lgdsp_synth_generate_device/_host        <- make_fake_waveform  test/test_dsp_icpc.jl:11-32 (generalised,
+ *                                               SURVEY.md section 8d)
+ *
+ * The boundary is the whole chain, not the per-filter `rdfilt!` plugin API (src/derivative.jl:37-55):
+ * a per-filter boundary would force one HBM round trip per step.
+ *
+ * All time quantities are resolved by the host language into SAMPLE units (integers) or nanoseconds
+ * (doubles) with the reference's own expressions before they cross this ABI: Julia's round() is
+ * ties-to-even and several windows of the reference's example config are exact ties.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returning int returns
+ * LGDSP_OK (0) or a negative status, with a message available from lgdsp_last_error(). The library never
+ * keeps or frees caller memory. A handle is bound to one CUDA device and is not thread-safe.
+ * There is NO CPU fallback: without a usable CUDA device lgdsp_create() fails.
+ */
+#ifndef LGDSP_B200_H
+#define LGDSP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGDSP_VERSION_MAJOR 0
+#define LGDSP_VERSION_MINOR 1
+#define LGDSP_PARAMS_VERSION 3u
+
+/* status codes */
+#define LGDSP_OK 0
+#define LGDSP_ERR_INVALID_ARG (-1)
+#define LGDSP_ERR_CUDA (-2)
+#define LGDSP_ERR_UNSUPPORTED (-3)
+#define LGDSP_ERR_NO_DEVICE (-4)
+#define LGDSP_ERR_OOM (-5)
+
+/* limits of this implementation */
+#define LGDSP_MAX_SAMPLES 8192   /* samples per waveform (multiple of 8) */
+#define LGDSP_MAX_DNI 64         /* PolynomialDNI window length */
+#define LGDSP_MAX_DNI_DEG 3
+#define LGDSP_MAX_SG 33          /* Savitzky-Golay taps */
+#define LGDSP_MAX_FIR 4096       /* CUSP/ZAC taps */
+
+/* ---- output schema: computed columns of dsp_icpc, order of src/dsp_icpc.jl:210-229.
+ * The four pass-through columns (blfc, timestamp, eventID_fadc, e_fc) never touch the GPU.
+ * Device rows are double[LGDSP_NCOL]; integer columns (qc_label, inTrace_n, n_sat_*) hold exact small
+ * integers. Times t0..t50_current, t0_inv are in microseconds; drift_time, tail_tau, t_*_max and
+ * inTrace_intersect are in the unit of the time axis (nanoseconds); blslope/tailslope are per ns. */
+enum lgdsp_col {
+    LGDSP_COL_blmean = 0, LGDSP_COL_blsigma, LGDSP_COL_blslope, LGDSP_COL_bloffset,
+    LGDSP_COL_tailmean, LGDSP_COL_tailsigma, LGDSP_COL_tailslope, LGDSP_COL_tailoffset,
+    LGDSP_COL_qc_label,
+    LGDSP_COL_t0, LGDSP_COL_t10, LGDSP_COL_t50, LGDSP_COL_t80, LGDSP_COL_t90, LGDSP_COL_t99,
+    LGDSP_COL_t50_current,
+    LGDSP_COL_drift_time,
+    LGDSP_COL_tail_tau, LGDSP_COL_tail_mean, LGDSP_COL_tail_sigma,
+    LGDSP_COL_e_max, LGDSP_COL_e_min,
+    LGDSP_COL_e_10410, LGDSP_COL_e_535, LGDSP_COL_e_313,
+    LGDSP_COL_e_10410_inv, LGDSP_COL_e_313_inv,
+    LGDSP_COL_t0_inv,
+    LGDSP_COL_e_trap, LGDSP_COL_e_cusp, LGDSP_COL_e_zac,
+    LGDSP_COL_e_trap_max, LGDSP_COL_e_cusp_max, LGDSP_COL_e_zac_max,
+    LGDSP_COL_t_trap_max, LGDSP_COL_t_cusp_max, LGDSP_COL_t_zac_max,
+    LGDSP_COL_qdrift, LGDSP_COL_lq,
+    LGDSP_COL_a_sg, LGDSP_COL_a_60, LGDSP_COL_a_100, LGDSP_COL_a_raw,
+    LGDSP_COL_inTrace_intersect, LGDSP_COL_inTrace_n,
+    LGDSP_COL_n_sat_low, LGDSP_COL_n_sat_high, LGDSP_COL_n_sat_low_cons, LGDSP_COL_n_sat_high_cons,
+    LGDSP_NCOL /* = 49 */
+};
+
+/* which groups of columns to compute (bit mask). Columns of groups that are switched off are written as 0.
+ * LGDSP_GROUP_ALL is the full dsp_icpc; LGDSP_GROUP_PZTRAP is BASELINE.json config 2
+ * (blmean, t0, t50, e_trap, e_10410 and what they depend on). */
+#define LGDSP_GROUP_BASE   0x01u  /* saturation, baseline stats, e_max/e_min, tailstats, PZ, pz_stats */
+#define LGDSP_GROUP_TIMING 0x02u  /* t0, t10..t99, drift_time, t0_inv */
+#define LGDSP_GROUP_TRAPS  0x04u  /* e_10410, e_535, e_313, *_inv, e_trap, e_trap_max, t_trap_max */
+#define LGDSP_GROUP_QDRIFT 0x08u  /* qdrift, lq */
+#define LGDSP_GROUP_CUSPZAC 0x10u /* e_cusp, e_zac, e_*_max, t_*_max */
+#define LGDSP_GROUP_CURRENT 0x20u /* a_sg, a_60, a_100, a_raw, inTrace_*, t50_current */
+#define LGDSP_GROUP_ALL    0x3Fu
+#define LGDSP_GROUP_PZTRAP (LGDSP_GROUP_BASE | LGDSP_GROUP_TIMING | LGDSP_GROUP_TRAPS)
+
+/* TrapezoidalChargeFilter(avgtime, gaptime, avgtime2) in samples [RDDSP]:
+ * out[j] = mean(y[j+navg+ngap .. j+navg+ngap+navg2-1]) - mean(y[j .. j+navg-1]), j = 0 .. n-L, L = navg+ngap+navg2;
+ * trace index j carries the time of sample j+L-1 (trailing edge). */
+typedef struct lgdsp_trap {
+    int32_t navg, ngap, navg2, reserved;
+} lgdsp_trap;
+
+/* SignalEstimator(PolynomialDNI(degree, length)) [RDDSP]; A is the least-squares fit matrix
+ * (n_w x (degree+1), row-major): coef_j = sum_i A[i*(degree+1)+j] * y[from+i], value = sum_j coef_j u^j with
+ * u = p - from, p the fractional trace index, from = clamp(round_half_even(p) - n_w/2, 0, n_trace-n_w). */
+typedef struct lgdsp_dni {
+    int32_t n_w, degree;
+    double A[LGDSP_MAX_DNI * (LGDSP_MAX_DNI_DEG + 1)];
+} lgdsp_dni;
+
+/* SavitzkyGolayFilter(length, degree, 1) [RDDSP] as a valid-mode correlation:
+ * s[j] = sum_k h[k] * y[j+k], j = 0 .. n-n_taps; trace index j carries the time of sample j+offset. */
+typedef struct lgdsp_sg {
+    int32_t n_taps, offset;
+    double h[LGDSP_MAX_SG];
+} lgdsp_sg;
+
+/* CUSPChargeFilter / ZACChargeFilter(sigma, toplen, tau, length, beta) [RDDSP], in samples.
+ * The FIR is  out[j] = sum_k coeffs[k] * y[j+L-1-k]  (valid convolution), trace index j <-> sample j+L-1.
+ * `coeffs` must be what lgdsp_cusp_coeffs / lgdsp_zac_coeffs produce for the same (sigma, flat, tau, L,
+ * beta): the device path evaluates the filter through its analytic structure (sliding exponential and
+ * polynomial windows), the coefficient array is used for the pick-off window and by the direct mode. */
+typedef struct lgdsp_cuspzac {
+    int32_t n_taps;  /* L = round(length/dt) */
+    int32_t flat;    /* round(toplen/dt) */
+    double sigma;    /* sigma/dt */
+    double tau;      /* tau/dt */
+    double beta;     /* scaling factor as passed by the reference (length/dt, src/dsp_icpc.jl:88,90) */
+    double coeffs[LGDSP_MAX_FIR];
+} lgdsp_cuspzac;
+
+typedef struct lgdsp_icpc_params {
+    uint32_t struct_size;      /* sizeof(lgdsp_icpc_params), checked */
+    uint32_t version;          /* LGDSP_PARAMS_VERSION */
+    int32_t n_samples;         /* samples per waveform, <= LGDSP_MAX_SAMPLES, multiple of 8 */
+    uint32_t groups;           /* LGDSP_GROUP_* mask */
+    double t_first_ns;         /* time of sample 0 (first(wvfs[1].time)) */
+    double dt_ns;              /* step(wvfs[1].time) */
+
+    /* saturation(wvf, low, high): src/dsp_icpc.jl:93-95; compared with the raw integer samples */
+    int64_t sat_low, sat_high;
+
+    /* windows as 0-based inclusive sample index ranges (reference: 1-based, src/tailstats.jl:16-18) */
+    int32_t bl_from, bl_until;       /* config.bl_window */
+    int32_t tail_from, tail_until;   /* config.tail_window */
+
+    /* InvCRFilter(tau): y[i] = y[i-1] + x[i]/alpha - x[i-1], alpha = RC/(RC+1), RC = tau/dt;
+     * closed form y[i] = x[i] + pz_km1 * sum_{j<=i} x[j]  with pz_km1 = 1/alpha - 1 */
+    double pz_km1;
+
+    /* get_t0: src/dsp_routines.jl:9-25, called at src/dsp_icpc.jl:126 and :207 (inverted, default flt_pars) */
+    lgdsp_trap t0_trap;
+    lgdsp_trap t0inv_trap;
+    double t0_threshold;
+    int32_t t0_min_n;          /* max(1, round(t0_mintot/dt)) */
+    int32_t tx_min_n;          /* max(1, round(tx_mintot/dt)) */
+    double tx_frac[5];         /* 0.1, 0.5, 0.8, 0.9, 0.99  (src/dsp_icpc.jl:132-136) */
+
+    /* get_qdrift: src/dsp_routines.jl:51-64; first/last of the integration-length range in ns */
+    double qdrift_first_ns, qdrift_last_ns;
+    double lq_first_ns, lq_last_ns;
+    lgdsp_dni int_dni;         /* PolynomialDNI(int_interpolation_order, int_interpolation_length) */
+    lgdsp_dni sig_dni;         /* PolynomialDNI(sig_interpolation_order, sig_interpolation_length) */
+
+    /* energy filters: src/dsp_icpc.jl:147-178 */
+    lgdsp_trap trap_10410, trap_535, trap_313, trap_e;
+    double trap_pickoff_ns;    /* trap_rt + trap_ft/2 */
+    double cusp_pickoff_ns;    /* flt_length_cusp/2 */
+    double zac_pickoff_ns;     /* flt_length_zac/2 */
+
+    /* currents: src/dsp_icpc.jl:181-195; index 0: sg_wl, 1: 60 ns, 2: 100 ns */
+    lgdsp_sg sg[3];
+    /* current_window as 0-based inclusive index ranges in the index space of each trace:
+     * 0..2: the three SG traces, 3: DerivativeFilter trace (same axis as the waveform) */
+    int32_t cur_from[4], cur_until[4];
+
+    /* get_intracePileUp: src/dsp_routines.jl:72-82, on the sg[0] trace */
+    double intrace_nsigma;
+    int32_t intrace_min_n;
+    int32_t intrace_bl_from, intrace_bl_until;  /* sigma window in sg[0]-trace index space */
+
+    /* 0: evaluate CUSP/ZAC through their analytic structure (default); 1: direct FIR with `coeffs` */
+    int32_t cuspzac_direct;
+    int32_t reserved0;
+
+    lgdsp_cuspzac cusp, zac;
+} lgdsp_icpc_params;
+
+/* one point of a trapezoidal sweep: filter + pick-off.
+ * pickoff_mode 0: fixed time pickoff_ns (dsp_trap_rt_optimization: enc_pickoff_trap);
+ * pickoff_mode 1: t50 + pickoff_ns (dsp_trap_ft_optimization: t50 + rt + ft/2), t50 found on the PZ
+ * waveform at 0.5*maximum(PZ waveform) with tx_min_n (src/dsp_filter_optimization.jl:260). */
+typedef struct lgdsp_trap_variant {
+    lgdsp_trap trap;
+    double pickoff_ns;
+    int32_t pickoff_mode;
+    int32_t reserved;
+} lgdsp_trap_variant;
+
+typedef struct lgdsp_sweep_params {
+    uint32_t struct_size;
+    uint32_t version;
+    int32_t n_samples;
+    int32_t tx_min_n;
+    double t_first_ns, dt_ns;
+    int32_t bl_from, bl_until;
+    double pz_km1;
+    lgdsp_dni sig_dni;
+} lgdsp_sweep_params;
+
+/* synthetic ICPC waveform generator: counter-based Philox4x32-10, identical on host and device */
+typedef struct lgdsp_synth_params {
+    uint64_t seed;
+    int32_t n_samples;
+    int32_t mode;          /* 0: mixed population; 1: the reference's noise-free fixture
+                              (test/test_dsp_icpc.jl:11-32) for every event */
+    double noise_sigma;    /* ADC, default 3.0 */
+    double tau_samples;    /* decay constant in samples, default 31250 */
+} lgdsp_synth_params;
+
+typedef struct lgdsp_handle lgdsp_handle;
+
+/* ---- library / handle ---- */
+const char* lgdsp_version(void);
+/* last error message of the handle (or of the last failed lgdsp_create when handle == NULL) */
+const char* lgdsp_last_error(const lgdsp_handle* h);
+/* create a handle on CUDA device `device`; stream = 0 creates an own stream, otherwise a cudaStream_t
+ * to launch on (e.g. torch's current stream) */
+int lgdsp_create(int device, void* stream, lgdsp_handle** out);
+void lgdsp_destroy(lgdsp_handle* h);
+/* number of kernels this handle has launched so far (for bench bookkeeping) */
+int64_t lgdsp_launch_count(const lgdsp_handle* h);
+/* block until all work submitted by the handle has finished */
+int lgdsp_synchronize(lgdsp_handle* h);
+
+/* ---- host-side filter construction (pure CPU, no handle) ---- */
+int lgdsp_lsq_fit_matrix(int32_t n, int32_t degree, double* A /* n*(degree+1) */);
+int lgdsp_sg_coeffs(int32_t n_taps, int32_t degree, int32_t derivative, double* h /* n_taps */);
+int lgdsp_cusp_coeffs(double sigma, int32_t flat, double tau, int32_t n_taps, double beta, double* c);
+int lgdsp_zac_coeffs(double sigma, int32_t flat, double tau, int32_t n_taps, double beta, double* c);
+
+/* ---- dsp_icpc ---- */
+/* waveforms on the HOST: wf[e*ld_samples + i], i < n_samples; out_rows: host double[n_events][LGDSP_NCOL].
+ * Copies in chunks (pinned staging, overlapped with compute), blocks until the result is in out_rows. */
+int lgdsp_icpc_run(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* wf, int64_t n_events,
+                   int64_t ld_samples, double* out_rows);
+/* waveforms and output rows in DEVICE memory (wf 16-byte aligned, ld_samples multiple of 8); asynchronous
+ * on the handle's stream */
+int lgdsp_icpc_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* d_wf, int64_t n_events,
+                          int64_t ld_samples, double* d_out_rows);
+/* upload/validate params once and reuse them for many _device calls (avoids the per-call upload);
+ * pass p == NULL to lgdsp_icpc_run_device afterwards */
+int lgdsp_icpc_set_params(lgdsp_handle* h, const lgdsp_icpc_params* p);
+
+/* ---- trapezoidal sweeps ---- */
+/* out: float[n_events][n_variants], i.e. the memory layout of the reference's column-major Julia matrix
+ * (n_variants x n_events), Float32 as src/dsp_filter_optimization.jl:263 */
+int lgdsp_trap_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* wf, int64_t n_events,
+                         int64_t ld_samples, const lgdsp_trap_variant* variants, int32_t n_variants, float* out);
+int lgdsp_trap_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* d_wf,
+                                int64_t n_events, int64_t ld_samples, const lgdsp_trap_variant* variants,
+                                int32_t n_variants, float* d_out);
+
+/* ---- synthetic input ---- */
+/* events [first_event, first_event + n_events) of the stream defined by (seed, mode) */
+int lgdsp_synth_generate_device(lgdsp_handle* h, const lgdsp_synth_params* sp, int64_t first_event,
+                                int64_t n_events, int64_t ld_samples, uint16_t* d_wf);
+int lgdsp_synth_generate_host(const lgdsp_synth_params* sp, int64_t first_event, int64_t n_events,
+                              int64_t ld_samples, uint16_t* wf);
+
+/* ---- timing helper: elapsed milliseconds of the last *_device call measured with CUDA events on the
+ * handle's stream (valid after lgdsp_synchronize) ---- */
+double lgdsp_last_kernel_ms(const lgdsp_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGDSP_B200_H */

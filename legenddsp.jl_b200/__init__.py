@@ -1,0 +1,27 @@
+"""legenddsp.jl_b200 -- B200-native (sm_100a) implementation of the LegendDSP.jl `dsp_icpc` hot path.
+
+Public surface (mirrors the reference's names, /root/reference/src/LegendDSP.jl:35-58 for this path):
+    DSPConfig, get_fltpars                         src/types.jl, src/utils.jl
+    dsp_icpc(data, config, τ, pars_filter)         src/dsp_icpc.jl:62
+    dsp_trap_rt_optimization, dsp_trap_ft_optimization   src/dsp_filter_optimization.jl:102,241
+
+All compute happens in the in-tree CUDA library (csrc/ -> liblgdsp_b200.so) behind the C ABI of
+include/lgdsp_b200.h.  Importing this package does not need a GPU; calling a compute function does.
+"""
+from . import _abi
+from ._abi import COLUMNS, COL, INT_COLUMNS, NCOL, UNITS
+from .config import (DSPConfig, Q, RddspPolicy, DEFAULT_POLICY, LibBuilders, example_config, tiefree_config,
+                     get_fltpars, grid_values, ns, us, resolve_icpc_params, resolve_sweep_params, trap_variants,
+                     params_summary)
+from ._lib import Handle, LgdspError, load_library, LIB_PATH, EXPORTED_SYMBOLS
+from .dsp_icpc import RDWaveforms, TABLE_COLUMNS, dsp_icpc, dsp_icpc_rows, rows_to_table, get_handle
+from .dsp_filter_optimization import dsp_trap_rt_optimization, dsp_trap_ft_optimization, dsp_trap_rtft_grid
+from . import synth, sharding
+
+__all__ = [
+    "DSPConfig", "Q", "ns", "us", "RddspPolicy", "example_config", "tiefree_config", "get_fltpars", "grid_values",
+    "resolve_icpc_params", "resolve_sweep_params", "trap_variants", "params_summary",
+    "Handle", "LgdspError", "load_library", "RDWaveforms", "TABLE_COLUMNS", "dsp_icpc", "dsp_icpc_rows",
+    "rows_to_table", "dsp_trap_rt_optimization", "dsp_trap_ft_optimization", "dsp_trap_rtft_grid",
+    "synth", "sharding", "COLUMNS", "COL", "INT_COLUMNS", "NCOL", "UNITS",
+]

@@ -1,0 +1,135 @@
+"""ctypes mirror of include/lgdsp_b200.h (structs, constants, column names).
+
+Kept in lock-step with the header by tests/test_abi.py, which compiles a tiny C program printing
+sizeof/offsetof of every struct and compares them with these definitions.
+"""
+import ctypes as C
+
+LGDSP_PARAMS_VERSION = 3
+LGDSP_MAX_SAMPLES = 8192
+LGDSP_MAX_DNI = 64
+LGDSP_MAX_DNI_DEG = 3
+LGDSP_MAX_SG = 33
+LGDSP_MAX_FIR = 4096
+
+LGDSP_OK = 0
+LGDSP_ERR_INVALID_ARG = -1
+LGDSP_ERR_CUDA = -2
+LGDSP_ERR_UNSUPPORTED = -3
+LGDSP_ERR_NO_DEVICE = -4
+LGDSP_ERR_OOM = -5
+
+GROUP_BASE = 0x01
+GROUP_TIMING = 0x02
+GROUP_TRAPS = 0x04
+GROUP_QDRIFT = 0x08
+GROUP_CUSPZAC = 0x10
+GROUP_CURRENT = 0x20
+GROUP_ALL = 0x3F
+GROUP_PZTRAP = GROUP_BASE | GROUP_TIMING | GROUP_TRAPS
+
+# computed columns of dsp_icpc in the order of /root/reference/src/dsp_icpc.jl:210-229
+COLUMNS = (
+    "blmean", "blsigma", "blslope", "bloffset",
+    "tailmean", "tailsigma", "tailslope", "tailoffset",
+    "qc_label",
+    "t0", "t10", "t50", "t80", "t90", "t99",
+    "t50_current",
+    "drift_time",
+    "tail_tau", "tail_mean", "tail_sigma",
+    "e_max", "e_min",
+    "e_10410", "e_535", "e_313",
+    "e_10410_inv", "e_313_inv",
+    "t0_inv",
+    "e_trap", "e_cusp", "e_zac",
+    "e_trap_max", "e_cusp_max", "e_zac_max",
+    "t_trap_max", "t_cusp_max", "t_zac_max",
+    "qdrift", "lq",
+    "a_sg", "a_60", "a_100", "a_raw",
+    "inTrace_intersect", "inTrace_n",
+    "n_sat_low", "n_sat_high", "n_sat_low_cons", "n_sat_high_cons",
+)
+NCOL = len(COLUMNS)
+assert NCOL == 49
+COL = {name: i for i, name in enumerate(COLUMNS)}
+INT_COLUMNS = ("qc_label", "inTrace_n", "n_sat_low", "n_sat_high", "n_sat_low_cons", "n_sat_high_cons")
+# unit of every non-dimensionless column (documentation + Julia wrapper table)
+UNITS = {
+    "blslope": "1/ns", "tailslope": "1/ns",
+    "t0": "us", "t10": "us", "t50": "us", "t80": "us", "t90": "us", "t99": "us", "t50_current": "us",
+    "t0_inv": "us", "drift_time": "ns", "tail_tau": "ns",
+    "t_trap_max": "ns", "t_cusp_max": "ns", "t_zac_max": "ns", "inTrace_intersect": "ns",
+}
+
+
+class Trap(C.Structure):
+    _fields_ = [("navg", C.c_int32), ("ngap", C.c_int32), ("navg2", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_tuple(self):
+        return (self.navg, self.ngap, self.navg2)
+
+    @property
+    def length(self):
+        return self.navg + self.ngap + self.navg2
+
+
+class Dni(C.Structure):
+    _fields_ = [("n_w", C.c_int32), ("degree", C.c_int32),
+                ("A", C.c_double * (LGDSP_MAX_DNI * (LGDSP_MAX_DNI_DEG + 1)))]
+
+
+class Sg(C.Structure):
+    _fields_ = [("n_taps", C.c_int32), ("offset", C.c_int32), ("h", C.c_double * LGDSP_MAX_SG)]
+
+
+class CuspZac(C.Structure):
+    _fields_ = [("n_taps", C.c_int32), ("flat", C.c_int32), ("sigma", C.c_double), ("tau", C.c_double),
+                ("beta", C.c_double), ("coeffs", C.c_double * LGDSP_MAX_FIR)]
+
+
+class IcpcParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("version", C.c_uint32),
+        ("n_samples", C.c_int32), ("groups", C.c_uint32),
+        ("t_first_ns", C.c_double), ("dt_ns", C.c_double),
+        ("sat_low", C.c_int64), ("sat_high", C.c_int64),
+        ("bl_from", C.c_int32), ("bl_until", C.c_int32),
+        ("tail_from", C.c_int32), ("tail_until", C.c_int32),
+        ("pz_km1", C.c_double),
+        ("t0_trap", Trap), ("t0inv_trap", Trap),
+        ("t0_threshold", C.c_double),
+        ("t0_min_n", C.c_int32), ("tx_min_n", C.c_int32),
+        ("tx_frac", C.c_double * 5),
+        ("qdrift_first_ns", C.c_double), ("qdrift_last_ns", C.c_double),
+        ("lq_first_ns", C.c_double), ("lq_last_ns", C.c_double),
+        ("int_dni", Dni), ("sig_dni", Dni),
+        ("trap_10410", Trap), ("trap_535", Trap), ("trap_313", Trap), ("trap_e", Trap),
+        ("trap_pickoff_ns", C.c_double), ("cusp_pickoff_ns", C.c_double), ("zac_pickoff_ns", C.c_double),
+        ("sg", Sg * 3),
+        ("cur_from", C.c_int32 * 4), ("cur_until", C.c_int32 * 4),
+        ("intrace_nsigma", C.c_double),
+        ("intrace_min_n", C.c_int32),
+        ("intrace_bl_from", C.c_int32), ("intrace_bl_until", C.c_int32),
+        ("cuspzac_direct", C.c_int32), ("reserved0", C.c_int32),
+        ("cusp", CuspZac), ("zac", CuspZac),
+    ]
+
+
+class TrapVariant(C.Structure):
+    _fields_ = [("trap", Trap), ("pickoff_ns", C.c_double), ("pickoff_mode", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SweepParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("version", C.c_uint32),
+        ("n_samples", C.c_int32), ("tx_min_n", C.c_int32),
+        ("t_first_ns", C.c_double), ("dt_ns", C.c_double),
+        ("bl_from", C.c_int32), ("bl_until", C.c_int32),
+        ("pz_km1", C.c_double),
+        ("sig_dni", Dni),
+    ]
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_samples", C.c_int32), ("mode", C.c_int32),
+                ("noise_sigma", C.c_double), ("tau_samples", C.c_double)]

@@ -1,0 +1,138 @@
+"""Loader of the in-tree CUDA library liblgdsp_b200.so (built by build.py / __graft_entry__.build()).
+
+There is NO fallback: if the library is missing this raises; if no CUDA device is usable `Handle()` raises.
+"""
+import ctypes as C
+import os
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblgdsp_b200.so")
+
+_dp = C.POINTER(C.c_double)
+_lib = None
+
+
+class LgdspError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"lgdsp error {code}: {msg}")
+        self.code = code
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "legenddsp.jl_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.lgdsp_version.restype = C.c_char_p
+    L.lgdsp_last_error.restype = C.c_char_p
+    L.lgdsp_last_error.argtypes = [vp]
+    L.lgdsp_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.lgdsp_destroy.argtypes = [vp]
+    L.lgdsp_destroy.restype = None
+    L.lgdsp_launch_count.argtypes = [vp]
+    L.lgdsp_launch_count.restype = i64
+    L.lgdsp_synchronize.argtypes = [vp]
+    L.lgdsp_last_kernel_ms.argtypes = [vp]
+    L.lgdsp_last_kernel_ms.restype = C.c_double
+    L.lgdsp_lsq_fit_matrix.argtypes = [i32, i32, _dp]
+    L.lgdsp_sg_coeffs.argtypes = [i32, i32, i32, _dp]
+    L.lgdsp_cusp_coeffs.argtypes = [C.c_double, i32, C.c_double, i32, C.c_double, _dp]
+    L.lgdsp_zac_coeffs.argtypes = [C.c_double, i32, C.c_double, i32, C.c_double, _dp]
+    L.lgdsp_icpc_set_params.argtypes = [vp, C.POINTER(_abi.IcpcParams)]
+    L.lgdsp_icpc_run.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i64, i64, vp]
+    L.lgdsp_icpc_run_device.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i64, i64, vp]
+    L.lgdsp_trap_sweep_run.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64, C.POINTER(_abi.TrapVariant), i32, vp]
+    L.lgdsp_trap_sweep_run_device.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64,
+                                              C.POINTER(_abi.TrapVariant), i32, vp]
+    L.lgdsp_synth_generate_device.argtypes = [vp, C.POINTER(_abi.SynthParams), i64, i64, i64, vp]
+    L.lgdsp_synth_generate_host.argtypes = [C.POINTER(_abi.SynthParams), i64, i64, i64, vp]
+    _lib = L
+    return L
+
+
+# every symbol include/lgdsp_b200.h declares (tests/test_abi.py checks the library exports them all)
+EXPORTED_SYMBOLS = (
+    "lgdsp_version", "lgdsp_last_error", "lgdsp_create", "lgdsp_destroy", "lgdsp_launch_count", "lgdsp_synchronize",
+    "lgdsp_lsq_fit_matrix", "lgdsp_sg_coeffs", "lgdsp_cusp_coeffs", "lgdsp_zac_coeffs",
+    "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params",
+    "lgdsp_trap_sweep_run", "lgdsp_trap_sweep_run_device",
+    "lgdsp_synth_generate_device", "lgdsp_synth_generate_host", "lgdsp_last_kernel_ms",
+)
+
+
+class Handle:
+    """RAII wrapper of lgdsp_handle: one per (thread, GPU)."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.lgdsp_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.lgdsp_last_error(None).decode()
+            self._h = None
+            raise LgdspError(rc, msg)
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lgdsp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise LgdspError(rc, self._lib.lgdsp_last_error(self._h).decode())
+
+    @property
+    def launch_count(self):
+        return int(self._lib.lgdsp_launch_count(self._h))
+
+    def synchronize(self):
+        self._check(self._lib.lgdsp_synchronize(self._h))
+
+    def last_kernel_ms(self):
+        return float(self._lib.lgdsp_last_kernel_ms(self._h))
+
+    # ---- dsp_icpc ----
+    def icpc_set_params(self, params):
+        self._check(self._lib.lgdsp_icpc_set_params(self._h, C.byref(params)))
+
+    def icpc_run_host(self, params, wf_ptr, n_events, ld, out_ptr):
+        self._check(self._lib.lgdsp_icpc_run(self._h, C.byref(params) if params is not None else None,
+                                             C.c_void_p(wf_ptr), int(n_events), int(ld), C.c_void_p(out_ptr)))
+
+    def icpc_run_device(self, params, d_wf_ptr, n_events, ld, d_out_ptr):
+        self._check(self._lib.lgdsp_icpc_run_device(self._h, C.byref(params) if params is not None else None,
+                                                    C.c_void_p(d_wf_ptr), int(n_events), int(ld), C.c_void_p(d_out_ptr)))
+
+    # ---- sweeps ----
+    def sweep_run_host(self, sparams, wf_ptr, n_events, ld, variants, out_ptr):
+        self._check(self._lib.lgdsp_trap_sweep_run(self._h, C.byref(sparams), C.c_void_p(wf_ptr), int(n_events), int(ld),
+                                                   variants, len(variants), C.c_void_p(out_ptr)))
+
+    def sweep_run_device(self, sparams, d_wf_ptr, n_events, ld, variants, d_out_ptr):
+        self._check(self._lib.lgdsp_trap_sweep_run_device(self._h, C.byref(sparams), C.c_void_p(d_wf_ptr), int(n_events),
+                                                          int(ld), variants, len(variants), C.c_void_p(d_out_ptr)))
+
+    # ---- synthetic input ----
+    def synth_device(self, sp, first_event, n_events, ld, d_wf_ptr):
+        self._check(self._lib.lgdsp_synth_generate_device(self._h, C.byref(sp), int(first_event), int(n_events), int(ld),
+                                                          C.c_void_p(d_wf_ptr)))

@@ -1,0 +1,486 @@
+// C ABI of liblgdsp_b200 (include/lgdsp_b200.h): handle management, parameter validation/upload, launches.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "lgdsp_kernels.h"
+
+using namespace lgdsp;
+
+struct lgdsp_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    int icpc_bps = 0, sweep_bps = 0;
+    std::string err;
+    // device tables
+    double* d_dniA = nullptr;      // [2][LGDSP_MAX_DNI*4]
+    double* d_cusp_g = nullptr;    // [LGDSP_MAX_FIR+1]
+    double* d_zac_g = nullptr;     // [LGDSP_MAX_FIR+1]
+    double* d_sweep_dniA = nullptr;
+    SweepVar* d_vars = nullptr;
+    int vars_cap = 0;
+    IcpcDev icpc{};
+    bool have_icpc = false;
+    // host-path staging
+    uint16_t* d_in[2] = {nullptr, nullptr};
+    double* d_rows = nullptr;
+    float* d_sweep_out = nullptr;
+    size_t in_cap = 0, rows_cap = 0, sweep_out_cap = 0;
+    cudaStream_t s_copy = nullptr;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int64_t launches = 0;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(lgdsp_handle* h, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? LGDSP_ERR_OOM : LGDSP_ERR_CUDA, "%s: %s", \
+                        #call, cudaGetErrorString(e_));                                                \
+    } while (0)
+
+extern "C" {
+
+const char* lgdsp_version(void) { return "lgdsp_b200 0.1 (sm_100a)"; }
+
+const char* lgdsp_last_error(const lgdsp_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int lgdsp_create(int device, void* stream, lgdsp_handle** out)
+{
+    lgdsp_handle* h = nullptr;
+    if (!out) return fail(nullptr, LGDSP_ERR_INVALID_ARG, "lgdsp_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, LGDSP_ERR_NO_DEVICE, "lgdsp_create: no CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, LGDSP_ERR_INVALID_ARG, "lgdsp_create: device %d of %d", device, ndev);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, LGDSP_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, LGDSP_ERR_UNSUPPORTED, "lgdsp_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    h = new lgdsp_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    auto bail = [&](int code) { lgdsp_destroy(h); return code; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { fail(nullptr, LGDSP_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); return bail(LGDSP_ERR_CUDA); }
+    if (stream) {
+        h->stream = (cudaStream_t)stream;
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            fail(nullptr, LGDSP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+            return bail(LGDSP_ERR_CUDA);
+        }
+        h->own_stream = true;
+    }
+    bool ok = cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = ok && cudaEventCreateWithFlags(&h->ev_ready[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_dniA, sizeof(double) * 2 * LGDSP_MAX_DNI * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_cusp_g, sizeof(double) * (LGDSP_MAX_FIR + 1)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_zac_g, sizeof(double) * (LGDSP_MAX_FIR + 1)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_sweep_dniA, sizeof(double) * LGDSP_MAX_DNI * 4) == cudaSuccess;
+    if (!ok) { fail(nullptr, LGDSP_ERR_CUDA, "lgdsp_create: resource allocation failed: %s", cudaGetErrorString(cudaGetLastError())); return bail(LGDSP_ERR_CUDA); }
+    if ((e = icpc_configure(&h->icpc_bps)) != cudaSuccess || (e = sweep_configure(&h->sweep_bps)) != cudaSuccess) {
+        fail(nullptr, LGDSP_ERR_CUDA, "kernel configuration failed: %s (is the library built for this GPU?)", cudaGetErrorString(e));
+        return bail(LGDSP_ERR_CUDA);
+    }
+    if (h->icpc_bps < 1 || h->sweep_bps < 1) { fail(nullptr, LGDSP_ERR_CUDA, "kernels do not fit on an SM"); return bail(LGDSP_ERR_CUDA); }
+    *out = h;
+    return LGDSP_OK;
+}
+
+void lgdsp_destroy(lgdsp_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_dniA); cudaFree(h->d_cusp_g); cudaFree(h->d_zac_g); cudaFree(h->d_sweep_dniA); cudaFree(h->d_vars);
+    cudaFree(h->d_in[0]); cudaFree(h->d_in[1]); cudaFree(h->d_rows); cudaFree(h->d_sweep_out);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]);
+        if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
+    }
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int64_t lgdsp_launch_count(const lgdsp_handle* h) { return h ? h->launches : 0; }
+
+int lgdsp_synchronize(lgdsp_handle* h)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return LGDSP_OK;
+}
+
+double lgdsp_last_kernel_ms(const lgdsp_handle* h)
+{
+    if (!h || !h->timed) return -1.0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// parameter validation and conversion
+// ---------------------------------------------------------------------------------------------------
+static bool make_trap(const lgdsp_trap& t, int n, int min_out, TrapDev& d)
+{
+    if (t.navg < 1 || t.navg2 < 1 || t.ngap < 0) return false;
+    d.a = t.navg; d.g = t.ngap; d.a2 = t.navg2;
+    d.L = t.navg + t.ngap + t.navg2;
+    d.nout = n - d.L + 1;
+    d.pad_ = 0;
+    d.inv1 = 1.0 / t.navg;
+    d.inv2 = 1.0 / t.navg2;
+    return d.nout >= min_out;
+}
+
+static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
+{
+    if (!p) return fail(h, LGDSP_ERR_INVALID_ARG, "params is NULL");
+    if (p->struct_size != sizeof(lgdsp_icpc_params) || p->version != LGDSP_PARAMS_VERSION)
+        return fail(h, LGDSP_ERR_INVALID_ARG, "lgdsp_icpc_params: size/version mismatch (got %u/%u, want %zu/%u)",
+                    p->struct_size, p->version, sizeof(lgdsp_icpc_params), LGDSP_PARAMS_VERSION);
+    const int n = p->n_samples;
+    if (n < 64 || n > LGDSP_MAX_SAMPLES || n % 8 != 0)
+        return fail(h, LGDSP_ERR_UNSUPPORTED, "n_samples = %d: need a multiple of 8 in [64, %d]", n, LGDSP_MAX_SAMPLES);
+    if (!(p->dt_ns > 0) || !std::isfinite(p->t_first_ns)) return fail(h, LGDSP_ERR_INVALID_ARG, "bad time axis");
+    auto win_ok = [&](int a, int b, int len) { return 0 <= a && a <= b && b <= len - 1; };
+    // @assert firstindex(X) <= first(idxs) <= last(idxs) <= lastindex(X)   /root/reference/src/tailstats.jl:23-25
+    if (!win_ok(p->bl_from, p->bl_until, n)) return fail(h, LGDSP_ERR_INVALID_ARG, "bl_window %d:%d outside the waveform", p->bl_from, p->bl_until);
+    if (!win_ok(p->tail_from, p->tail_until, n)) return fail(h, LGDSP_ERR_INVALID_ARG, "tail_window %d:%d outside the waveform", p->tail_from, p->tail_until);
+    IcpcDev D{};
+    D.n = n;
+    D.groups = p->groups | LGDSP_GROUP_BASE;
+    D.t_first = p->t_first_ns;
+    D.dt = p->dt_ns;
+    D.sat_low = (p->sat_low >= 0 && p->sat_low <= 65535) ? (int)p->sat_low : -1;
+    D.sat_high = (p->sat_high >= 0 && p->sat_high <= 65535) ? (int)p->sat_high : -1;
+    D.bl_from = p->bl_from; D.bl_until = p->bl_until; D.tail_from = p->tail_from; D.tail_until = p->tail_until;
+    D.km1 = p->pz_km1;
+    const int nw_sig = p->sig_dni.n_w, nw_int = p->int_dni.n_w;
+    auto dni_ok = [](const lgdsp_dni& d) { return d.degree >= 0 && d.degree <= LGDSP_MAX_DNI_DEG && d.n_w > d.degree && d.n_w <= LGDSP_MAX_DNI; };
+    if (!dni_ok(p->sig_dni) || !dni_ok(p->int_dni)) return fail(h, LGDSP_ERR_UNSUPPORTED, "PolynomialDNI window/degree outside the supported range");
+    if (nw_int > n) return fail(h, LGDSP_ERR_INVALID_ARG, "int_dni window longer than the waveform");
+    D.int_dni.n_w = nw_int; D.int_dni.m = p->int_dni.degree + 1;
+    D.sig_dni.n_w = nw_sig; D.sig_dni.m = p->sig_dni.degree + 1;
+    if (!make_trap(p->t0_trap, n, 2, D.t0) || !make_trap(p->t0inv_trap, n, 2, D.t0inv))
+        return fail(h, LGDSP_ERR_INVALID_ARG, "t0 trapezoid does not fit the waveform");
+    if (!make_trap(p->trap_10410, n, 1, D.e10410) || !make_trap(p->trap_535, n, 1, D.e535) || !make_trap(p->trap_313, n, 1, D.e313))
+        return fail(h, LGDSP_ERR_INVALID_ARG, "fixed trapezoid does not fit the waveform");
+    if (!make_trap(p->trap_e, n, nw_sig, D.etrap)) return fail(h, LGDSP_ERR_INVALID_ARG, "trap(rt,ft) leaves fewer outputs than the DNI window");
+    D.t0inv_same = (D.t0.a == D.t0inv.a && D.t0.g == D.t0inv.g && D.t0.a2 == D.t0inv.a2) ? 1 : 0;
+    if (p->t0_min_n < 1 || p->tx_min_n < 1 || p->intrace_min_n < 1) return fail(h, LGDSP_ERR_INVALID_ARG, "min_n must be >= 1");
+    D.t0_min_n = p->t0_min_n; D.tx_min_n = p->tx_min_n; D.direct = p->cuspzac_direct;
+    D.t0_thr = p->t0_threshold;
+    for (int i = 0; i < 5; ++i) D.tx_frac[i] = p->tx_frac[i];
+    D.qd_first = p->qdrift_first_ns; D.qd_last = p->qdrift_last_ns; D.lq_first = p->lq_first_ns; D.lq_last = p->lq_last_ns;
+    D.trap_pick = p->trap_pickoff_ns; D.cusp_pick = p->cusp_pickoff_ns; D.zac_pick = p->zac_pickoff_ns;
+    for (int k = 0; k < 3; ++k) {
+        const lgdsp_sg& s = p->sg[k];
+        if (s.n_taps < 1 || s.n_taps > LGDSP_MAX_SG || s.n_taps > n || s.offset < 0 || s.offset >= s.n_taps)
+            return fail(h, LGDSP_ERR_INVALID_ARG, "sg[%d]: bad tap count/offset", k);
+        SgDev& d = D.sg[k];
+        d.n_taps = s.n_taps; d.offset = s.offset; d.nout = n - s.n_taps + 1; d.pad_ = 0;
+        d.gg[0] = -s.h[0];
+        for (int i = 1; i < s.n_taps; ++i) d.gg[i] = s.h[i - 1] - s.h[i];
+        d.gg[s.n_taps] = s.h[s.n_taps - 1];
+        if (!win_ok(p->cur_from[k], p->cur_until[k], d.nout))
+            return fail(h, LGDSP_ERR_INVALID_ARG, "current_window %d:%d outside sg[%d] trace", p->cur_from[k], p->cur_until[k], k);
+    }
+    if (!win_ok(p->cur_from[3], p->cur_until[3], n)) return fail(h, LGDSP_ERR_INVALID_ARG, "current_window outside the waveform");
+    for (int k = 0; k < 4; ++k) { D.cur_from[k] = p->cur_from[k]; D.cur_until[k] = p->cur_until[k]; }
+    D.nsigma = p->intrace_nsigma;
+    D.intr_min_n = p->intrace_min_n;
+    if (!win_ok(p->intrace_bl_from, p->intrace_bl_until, D.sg[0].nout)) return fail(h, LGDSP_ERR_INVALID_ARG, "in-trace sigma window outside the sg trace");
+    D.intr_from = p->intrace_bl_from; D.intr_until = p->intrace_bl_until;
+    // CUSP / ZAC
+    const lgdsp_cuspzac* cz[2] = {&p->cusp, &p->zac};
+    double* dst[2] = {h->d_cusp_g, h->d_zac_g};
+    std::vector<double> g(LGDSP_MAX_FIR + 1);
+    for (int f = 0; f < 2; ++f) {
+        const int L = cz[f]->n_taps;
+        if (L < 4 || L > LGDSP_MAX_FIR || n - L + 1 < nw_sig)
+            return fail(h, LGDSP_ERR_INVALID_ARG, "%s: %d taps do not fit (need >= %d outputs)", f ? "zac" : "cusp", L, nw_sig);
+        // differenced taps on the prefix sum TT: out[j] = sum_{k=0}^{L} g[k] TT[j+L-k]
+        const double* c = cz[f]->coeffs;
+        g[0] = c[0];
+        for (int k = 1; k < L; ++k) g[k] = c[k] - c[k - 1];
+        g[L] = -c[L - 1];
+        CK(cudaMemcpyAsync(dst[f], g.data(), sizeof(double) * (L + 1), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    D.cusp_L = p->cusp.n_taps; D.zac_L = p->zac.n_taps;
+    std::vector<double> A(2 * LGDSP_MAX_DNI * 4, 0.0);
+    memcpy(A.data(), p->int_dni.A, sizeof(double) * LGDSP_MAX_DNI * 4);
+    memcpy(A.data() + LGDSP_MAX_DNI * 4, p->sig_dni.A, sizeof(double) * LGDSP_MAX_DNI * 4);
+    CK(cudaMemcpyAsync(h->d_dniA, A.data(), sizeof(double) * A.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    D.dni_A = h->d_dniA; D.cusp_g = h->d_cusp_g; D.zac_g = h->d_zac_g;
+    h->icpc = D;
+    h->have_icpc = true;
+    return LGDSP_OK;
+}
+
+static int check_wf(lgdsp_handle* h, const void* wf, int64_t n_events, int64_t ld, int n, bool device)
+{
+    if (n_events < 0) return fail(h, LGDSP_ERR_INVALID_ARG, "n_events < 0");
+    if (n_events > 0 && !wf) return fail(h, LGDSP_ERR_INVALID_ARG, "waveform pointer is NULL");
+    if (ld < n) return fail(h, LGDSP_ERR_INVALID_ARG, "ld_samples (%lld) < n_samples (%d)", (long long)ld, n);
+    if (device && (((uintptr_t)wf & 15u) != 0 || ld % 8 != 0))
+        return fail(h, LGDSP_ERR_INVALID_ARG, "device waveforms must be 16-byte aligned with ld_samples %% 8 == 0 (TMA bulk copy)");
+    return LGDSP_OK;
+}
+
+extern "C" {
+
+int lgdsp_icpc_set_params(lgdsp_handle* h, const lgdsp_icpc_params* p)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    return icpc_prepare(h, p);
+}
+
+int lgdsp_icpc_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* d_wf, int64_t n_events,
+                          int64_t ld_samples, double* d_out_rows)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (p) { int rc = icpc_prepare(h, p); if (rc) return rc; }
+    if (!h->have_icpc) return fail(h, LGDSP_ERR_INVALID_ARG, "no parameters set (pass params or call lgdsp_icpc_set_params)");
+    int rc = check_wf(h, d_wf, n_events, ld_samples, h->icpc.n, true);
+    if (rc) return rc;
+    if (n_events == 0) return LGDSP_OK;  // empty input -> empty table
+    if (!d_out_rows) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
+    const long long cap = (long long)h->sm_count * h->icpc_bps;
+    const int grid = (int)(n_events < cap ? n_events : cap);
+    CK(cudaEventRecord(h->ev0, h->stream));
+    icpc_launch(h->icpc, d_wf, n_events, ld_samples, d_out_rows, grid, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->launches += 1;
+    return LGDSP_OK;
+}
+
+static int ensure_staging(lgdsp_handle* h, size_t in_bytes, size_t rows_bytes)
+{
+    if (in_bytes > h->in_cap) {
+        for (int i = 0; i < 2; ++i) { cudaFree(h->d_in[i]); h->d_in[i] = nullptr; }
+        h->in_cap = 0;
+        for (int i = 0; i < 2; ++i) CK(cudaMalloc(&h->d_in[i], in_bytes));
+        h->in_cap = in_bytes;
+    }
+    if (rows_bytes > h->rows_cap) {
+        cudaFree(h->d_rows); h->d_rows = nullptr; h->rows_cap = 0;
+        CK(cudaMalloc(&h->d_rows, rows_bytes));
+        h->rows_cap = rows_bytes;
+    }
+    return LGDSP_OK;
+}
+
+// host buffers in, host rows out: chunked, H2D of chunk k+1 overlaps the kernel of chunk k
+int lgdsp_icpc_run(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* wf, int64_t n_events,
+                   int64_t ld_samples, double* out_rows)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (p) { int rc = icpc_prepare(h, p); if (rc) return rc; }
+    if (!h->have_icpc) return fail(h, LGDSP_ERR_INVALID_ARG, "no parameters set");
+    const int n = h->icpc.n;
+    int rc = check_wf(h, wf, n_events, ld_samples, n, false);
+    if (rc) return rc;
+    if (n_events == 0) return LGDSP_OK;
+    if (!out_rows) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
+    const int64_t chunk = n_events < 8192 ? n_events : 8192;
+    rc = ensure_staging(h, (size_t)chunk * n * 2, (size_t)2 * chunk * LGDSP_NCOL * sizeof(double));
+    if (rc) return rc;
+    const long long cap = (long long)h->sm_count * h->icpc_bps;
+    int c = 0;
+    for (int64_t e0 = 0; e0 < n_events; e0 += chunk, ++c) {
+        const int b = c & 1;
+        const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
+        if (c >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
+        CK(cudaMemcpy2DAsync(h->d_in[b], (size_t)n * 2, wf + e0 * ld_samples, (size_t)ld_samples * 2, (size_t)n * 2,
+                             (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
+        CK(cudaEventRecord(h->ev_ready[b], h->s_copy));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
+        double* d_rows = h->d_rows + (size_t)b * chunk * LGDSP_NCOL;
+        const int grid = (int)(ne < cap ? ne : cap);
+        icpc_launch(h->icpc, h->d_in[b], ne, n, d_rows, grid, h->stream);
+        CK(cudaGetLastError());
+        h->launches += 1;
+        CK(cudaEventRecord(h->ev_free[b], h->stream));
+        CK(cudaMemcpyAsync(out_rows + e0 * LGDSP_NCOL, d_rows, (size_t)ne * LGDSP_NCOL * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->s_copy));
+    CK(cudaStreamSynchronize(h->stream));
+    return LGDSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// trapezoid sweeps
+// ---------------------------------------------------------------------------------------------------
+static int sweep_prepare(lgdsp_handle* h, const lgdsp_sweep_params* p, const lgdsp_trap_variant* variants, int32_t nvar,
+                         SweepDev& D)
+{
+    if (!p || !variants) return fail(h, LGDSP_ERR_INVALID_ARG, "sweep params/variants NULL");
+    if (p->struct_size != sizeof(lgdsp_sweep_params) || p->version != LGDSP_PARAMS_VERSION)
+        return fail(h, LGDSP_ERR_INVALID_ARG, "lgdsp_sweep_params: size/version mismatch");
+    const int n = p->n_samples;
+    if (n < 64 || n > LGDSP_MAX_SAMPLES || n % 8 != 0) return fail(h, LGDSP_ERR_UNSUPPORTED, "n_samples = %d unsupported", n);
+    if (nvar < 1 || nvar > 1024) return fail(h, LGDSP_ERR_UNSUPPORTED, "n_variants = %d: need 1..1024", nvar);
+    if (!(0 <= p->bl_from && p->bl_from <= p->bl_until && p->bl_until < n)) return fail(h, LGDSP_ERR_INVALID_ARG, "bl_window outside the waveform");
+    const lgdsp_dni& d = p->sig_dni;
+    if (!(d.degree >= 0 && d.degree <= LGDSP_MAX_DNI_DEG && d.n_w > d.degree && d.n_w <= LGDSP_MAX_DNI))
+        return fail(h, LGDSP_ERR_UNSUPPORTED, "PolynomialDNI outside the supported range");
+    if (p->tx_min_n < 1) return fail(h, LGDSP_ERR_INVALID_ARG, "tx_min_n < 1");
+    std::vector<SweepVar> sv(nvar);
+    for (int v = 0; v < nvar; ++v) {
+        if (!make_trap(variants[v].trap, n, d.n_w, sv[v].t))
+            return fail(h, LGDSP_ERR_INVALID_ARG, "variant %d: trapezoid (%d,%d,%d) leaves fewer outputs than the DNI window", v,
+                        variants[v].trap.navg, variants[v].trap.ngap, variants[v].trap.navg2);
+        sv[v].pick_ns = variants[v].pickoff_ns;
+        sv[v].mode = variants[v].pickoff_mode;
+        sv[v].pad_ = 0;
+    }
+    if (nvar > h->vars_cap) {
+        cudaFree(h->d_vars); h->d_vars = nullptr; h->vars_cap = 0;
+        CK(cudaMalloc(&h->d_vars, sizeof(SweepVar) * nvar));
+        h->vars_cap = nvar;
+    }
+    CK(cudaMemcpyAsync(h->d_vars, sv.data(), sizeof(SweepVar) * nvar, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_sweep_dniA, d.A, sizeof(double) * LGDSP_MAX_DNI * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    D.n = n; D.tx_min_n = p->tx_min_n; D.t_first = p->t_first_ns; D.dt = p->dt_ns;
+    D.bl_from = p->bl_from; D.bl_until = p->bl_until; D.km1 = p->pz_km1;
+    D.sig_dni.n_w = d.n_w; D.sig_dni.m = d.degree + 1;
+    D.dni_A = h->d_sweep_dniA; D.vars = h->d_vars; D.nvar = nvar; D.pad_ = 0;
+    return LGDSP_OK;
+}
+
+int lgdsp_trap_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* d_wf, int64_t n_events,
+                                int64_t ld_samples, const lgdsp_trap_variant* variants, int32_t n_variants, float* d_out)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    SweepDev D{};
+    int rc = sweep_prepare(h, p, variants, n_variants, D);
+    if (rc) return rc;
+    rc = check_wf(h, d_wf, n_events, ld_samples, D.n, true);
+    if (rc) return rc;
+    if (n_events == 0) return LGDSP_OK;
+    if (!d_out) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
+    const long long cap = (long long)h->sm_count * h->sweep_bps;
+    const int grid = (int)(n_events < cap ? n_events : cap);
+    CK(cudaEventRecord(h->ev0, h->stream));
+    sweep_launch(D, d_wf, n_events, ld_samples, d_out, grid, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->launches += 1;
+    return LGDSP_OK;
+}
+
+int lgdsp_trap_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* wf, int64_t n_events,
+                         int64_t ld_samples, const lgdsp_trap_variant* variants, int32_t n_variants, float* out)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    SweepDev D{};
+    int rc = sweep_prepare(h, p, variants, n_variants, D);
+    if (rc) return rc;
+    const int n = D.n;
+    rc = check_wf(h, wf, n_events, ld_samples, n, false);
+    if (rc) return rc;
+    if (n_events == 0) return LGDSP_OK;
+    if (!out) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
+    const int64_t chunk = n_events < 8192 ? n_events : 8192;
+    rc = ensure_staging(h, (size_t)chunk * n * 2, 0);
+    if (rc) return rc;
+    const size_t ob = (size_t)2 * chunk * n_variants * sizeof(float);
+    if (ob > h->sweep_out_cap) {
+        cudaFree(h->d_sweep_out); h->d_sweep_out = nullptr; h->sweep_out_cap = 0;
+        CK(cudaMalloc(&h->d_sweep_out, ob));
+        h->sweep_out_cap = ob;
+    }
+    const long long cap = (long long)h->sm_count * h->sweep_bps;
+    int c = 0;
+    for (int64_t e0 = 0; e0 < n_events; e0 += chunk, ++c) {
+        const int b = c & 1;
+        const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
+        if (c >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
+        CK(cudaMemcpy2DAsync(h->d_in[b], (size_t)n * 2, wf + e0 * ld_samples, (size_t)ld_samples * 2, (size_t)n * 2,
+                             (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
+        CK(cudaEventRecord(h->ev_ready[b], h->s_copy));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
+        float* d_o = h->d_sweep_out + (size_t)b * chunk * n_variants;
+        const int grid = (int)(ne < cap ? ne : cap);
+        sweep_launch(D, h->d_in[b], ne, n, d_o, grid, h->stream);
+        CK(cudaGetLastError());
+        h->launches += 1;
+        CK(cudaEventRecord(h->ev_free[b], h->stream));
+        CK(cudaMemcpyAsync(out + e0 * n_variants, d_o, (size_t)ne * n_variants * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->s_copy));
+    CK(cudaStreamSynchronize(h->stream));
+    return LGDSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// synthetic input
+// ---------------------------------------------------------------------------------------------------
+int lgdsp_synth_generate_device(lgdsp_handle* h, const lgdsp_synth_params* sp, int64_t first_event, int64_t n_events,
+                                int64_t ld_samples, uint16_t* d_wf)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (!sp || sp->n_samples < 8 || sp->n_samples % 8 != 0 || sp->n_samples > LGDSP_MAX_SAMPLES || !(sp->tau_samples > 0))
+        return fail(h, LGDSP_ERR_INVALID_ARG, "bad synth params");
+    int rc = check_wf(h, d_wf, n_events, ld_samples, sp->n_samples, true);
+    if (rc) return rc;
+    if (n_events == 0) return LGDSP_OK;
+    synth_launch(*sp, first_event, n_events, ld_samples, d_wf, h->stream);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return LGDSP_OK;
+}
+
+}  // extern "C"

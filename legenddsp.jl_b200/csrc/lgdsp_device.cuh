@@ -1,0 +1,138 @@
+// Device-side parameter blocks and small helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "../../include/lgdsp_b200.h"
+
+namespace lgdsp {
+
+// TrapezoidalChargeFilter in samples, with derived constants
+struct TrapDev {
+    int a, g, a2, L, nout, pad_;
+    double inv1, inv2;
+};
+
+// SG kernel folded onto the inclusive prefix sum TT of the PZ waveform (summation by parts):
+// s[j] = sum_k h[k] (TT[j+k+1]-TT[j+k]) = sum_{k=0}^{n_taps} gg[k] TT[j+k]
+struct SgDev {
+    int n_taps, offset, nout, pad_;
+    double gg[LGDSP_MAX_SG + 1];
+};
+
+struct DniDev {
+    int n_w, m;  // window, degree+1
+};
+
+// kernel-argument block of the fused dsp_icpc kernel (lives in the constant bank, ~2 KB)
+struct IcpcDev {
+    int n;
+    unsigned groups;
+    double t_first, dt;
+    int sat_low, sat_high;  // -1: can never match a uint16 sample
+    int bl_from, bl_until, tail_from, tail_until;
+    double km1;
+    TrapDev t0, t0inv, e10410, e535, e313, etrap;
+    int t0inv_same, t0_min_n, tx_min_n, direct;
+    double t0_thr;
+    double tx_frac[5];
+    double qd_first, qd_last, lq_first, lq_last;
+    DniDev int_dni, sig_dni;
+    double trap_pick, cusp_pick, zac_pick;
+    SgDev sg[3];
+    int cur_from[4], cur_until[4];
+    double nsigma;
+    int intr_min_n, intr_from, intr_until, pad0;
+    int cusp_L, zac_L;
+    // global-memory tables (owned by the handle):
+    const double* dni_A;    // [2][LGDSP_MAX_DNI*4]: int_dni, sig_dni fit matrices
+    const double* cusp_g;   // differenced CUSP taps on TT, cusp_L+1 values
+    const double* zac_g;    // differenced ZAC taps on TT, zac_L+1 values
+};
+
+__device__ __forceinline__ int padi(int i) { return i + (i >> 5); }
+
+// ---- TMA 1-D bulk copy + mbarrier (sm_90+/sm_100a): SASS UBLKCP / SYNCS ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    while (!mbar_try_wait(bar, phase)) {}
+}
+
+// ---- warp / block reductions (results broadcast to all threads) ----
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+// (value, index) maximum with FIRST index on ties
+__device__ __forceinline__ void warp_argmax(double& v, int& i)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(FULL, v, o);
+        int oi = __shfl_xor_sync(FULL, i, o);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+
+// explicit round-to-nearest ops that the compiler never contracts into FMAs (scalar statistics formulas follow
+// the reference's operation order: src/tailstats.jl:54-70)
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+}  // namespace lgdsp

@@ -1,0 +1,1086 @@
+// Fused dsp_icpc kernel for sm_100a: one CTA per waveform, persistent over the event slice.
+//
+// Data flow per waveform (reference steps in brackets, /root/reference/src/dsp_icpc.jl):
+//   TMA bulk copy (cp.async.bulk, 16 KB UInt16) HBM -> SMEM, prefetched one event ahead
+//   pass 1  raw samples: saturation [:93-95], baseline regression sums [:102], min/max [:111-112],
+//           integer prefix sums P = cumsum(x), PP = cumsum(P)            (exact integer arithmetic)
+//   pass 2  pole-zero in closed form y = w + km1*cumsum(w), w = x - blmean [:105,:119-120]; writes
+//           TT[i+1] = cumsum(y)[i] (float64, SMEM); tail log-regression [:115]; PZ tail stats [:123];
+//           threshold masks for t10..t99 [:132-136]
+//   pass 3  every trapezoid [:126,:147-164,:202-207] as 4 look-ups in TT per output; Savitzky-Golay and
+//           derivative currents [:181-186] as short FIRs on TT; CUSP/ZAC [:167-178]
+//   pass 4  masks for t50_current and the in-trace pile-up search [:189-195]; crossing resolution with
+//           bit-parallel run detection (Intersect state machine)
+//   pass 5  interpolated pick-offs (PolynomialDNI), qdrift/lq [:141-144], output row (49 doubles)
+//
+// The waveform is read from HBM exactly once (16 KB) and 392 B are written.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "lgdsp_device.cuh"
+#include "lgdsp_kernels.h"
+
+namespace lgdsp {
+
+constexpr int NT = 256;          // threads per CTA
+constexpr int NWARP = NT / 32;
+constexpr int CH = 32;           // samples per thread in the chunked passes
+constexpr int MAXN = LGDSP_MAX_SAMPLES;
+constexpr int NWORDS = MAXN / 32;  // mask words
+
+enum { M_T0 = 0, M_T0INV, M_T10, M_T50, M_T80, M_T90, M_T99, M_CUR, M_PILE, NMASK };
+
+// ---- shared memory carve-up (bytes) ----
+constexpr int SM_XS = 0;                                   // uint16 xs[8192]
+constexpr int SM_TT = SM_XS + MAXN * 2;                    // double TT[padi(8192)+2]
+constexpr int TT_LEN = MAXN + (MAXN >> 5) + 8;
+constexpr int SM_MASK = SM_TT + TT_LEN * 8;                // uint32 masks[NMASK][NWORDS]
+constexpr int SM_RED = SM_MASK + NMASK * NWORDS * 4;       // double red[NWARP][24]
+constexpr int RED_W = 24;
+constexpr int SM_STASH = SM_RED + NWARP * RED_W * 8;       // double stash[3][LGDSP_MAX_DNI]
+constexpr int SM_DNI = SM_STASH + 3 * LGDSP_MAX_DNI * 8;   // double dniA[2][LGDSP_MAX_DNI*4]
+constexpr int SM_ROW = SM_DNI + 2 * LGDSP_MAX_DNI * 4 * 8; // double row[64]
+constexpr int SM_IBUF = SM_ROW + 64 * 8;                   // int ibuf[64]
+constexpr int SM_BAR = SM_IBUF + 64 * 4;                   // uint64 mbarrier
+constexpr int SM_TOTAL = SM_BAR + 16;
+
+int icpc_smem_bytes() { return SM_TOTAL; }
+int icpc_threads() { return NT; }
+
+// indices in ibuf
+enum { IB_POS0 = 0 /* NMASK positions */, IB_MULT = 16, IB_SCAN = 32 /* 8 warp totals */ };
+
+// block-wide sum of NV doubles; every thread gets the result
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* red, int tid)
+{
+    static_assert(NV <= RED_W, "reduction scratch too small");
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[wid * RED_W + i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) s += red[w * RED_W + i];
+        v[i] = s;
+    }
+    __syncthreads();
+}
+
+template <int NV>
+__device__ __forceinline__ void block_max(double (&v)[NV], double* red, int tid)
+{
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_max(v[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[wid * RED_W + i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = red[i];
+#pragma unroll
+        for (int w = 1; w < NWARP; ++w) s = fmax(s, red[w * RED_W + i]);
+        v[i] = s;
+    }
+    __syncthreads();
+}
+
+// block-wide (max value, FIRST index) for NV candidates
+template <int NV>
+__device__ __forceinline__ void block_argmax(double (&v)[NV], int (&ix)[NV], double* red, int tid)
+{
+    static_assert(2 * NV <= RED_W, "reduction scratch too small");
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) warp_argmax(v[i], ix[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            red[wid * RED_W + 2 * i] = v[i];
+            red[wid * RED_W + 2 * i + 1] = (double)ix[i];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double bv = red[2 * i];
+        int bi = (int)red[2 * i + 1];
+#pragma unroll
+        for (int w = 1; w < NWARP; ++w) {
+            double ov = red[w * RED_W + 2 * i];
+            int oi = (int)red[w * RED_W + 2 * i + 1];
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        v[i] = bv;
+        ix[i] = bi;
+    }
+    __syncthreads();
+}
+
+// run-length monoid for the saturation counters (src/saturation.jl:28-65)
+struct Run {
+    int pre, suf, best, len;
+};
+__device__ __forceinline__ Run run_merge(const Run& A, const Run& B)
+{
+    Run r;
+    r.pre = (A.pre == A.len) ? A.len + B.pre : A.pre;
+    r.suf = (B.suf == B.len) ? B.len + A.suf : B.suf;
+    r.best = max(max(A.best, B.best), A.suf + B.pre);
+    r.len = A.len + B.len;
+    return r;
+}
+__device__ __forceinline__ Run run_shfl_down(const Run& a, int o)
+{
+    Run r;
+    r.pre = __shfl_down_sync(FULL, a.pre, o);
+    r.suf = __shfl_down_sync(FULL, a.suf, o);
+    r.best = __shfl_down_sync(FULL, a.best, o);
+    r.len = __shfl_down_sync(FULL, a.len, o);
+    return r;
+}
+
+// regression statistics from accumulated sums, operation order of the reference (src/tailstats.jl:54-70 and
+// its RDDSP original signalstats); never contracted
+struct Stats {
+    double mean, sigma, slope, offset;
+};
+__device__ __forceinline__ Stats stats_finalize(int n, double sX, double sXX, double sY, double sYY, double sXY)
+{
+    const double inv_n = div_rn(1.0, (double)n);
+    const double mean_X = mul_rn(sX, inv_n);
+    const double mean_Y = mul_rn(sY, inv_n);
+    const double var_X = sub_rn(mul_rn(sXX, inv_n), mul_rn(mean_X, mean_X));
+    double var_Y = sub_rn(mul_rn(sYY, inv_n), mul_rn(mean_Y, mean_Y));
+    const double cov = sub_rn(mul_rn(sXY, inv_n), mul_rn(mean_X, mean_Y));
+    Stats s;
+    s.slope = div_rn(cov, var_X);
+    s.offset = sub_rn(mean_Y, mul_rn(s.slope, mean_X));
+    if (var_Y < 0) var_Y = 0;
+    s.mean = mean_Y;
+    s.sigma = sqrt(var_Y);
+    return s;
+}
+
+// sum_{i=a}^{b} X_i and X_i^2 with X_i = t0 + i*dt
+__device__ __forceinline__ void xsums(int a, int b, double t0, double dt, double& sX, double& sXX)
+{
+    const double cnt = (double)(b - a + 1);
+    const double si = 0.5 * (double)(a + b) * cnt;
+    auto s2 = [](double k) { return k * (k + 1.0) * (2.0 * k + 1.0) / 6.0; };
+    const double sii = s2((double)b) - s2((double)a - 1.0);
+    sX = cnt * t0 + dt * si;
+    sXX = cnt * t0 * t0 + 2.0 * t0 * dt * si + dt * dt * sii;
+}
+
+// extrema3points  src/interpolation.jl:8-10
+__device__ __forceinline__ double extrema3(double y1, double y2, double y3)
+{
+    const double a = y3 - 4.0 * y2 + 3.0 * y1;
+    return y1 - a * a / (8.0 * (y3 - 2.0 * y2 + y1));
+}
+
+// trapezoid output j from the prefix sums TT (TT[padi(i)] = sum_{k<i} y[k])
+__device__ __forceinline__ double trap_at(const double* TT, const TrapDev& t, int j)
+{
+    const double s1 = TT[padi(j + t.a)] - TT[padi(j)];
+    const double s2 = TT[padi(j + t.L)] - TT[padi(j + t.a + t.g)];
+    return s2 * t.inv2 - s1 * t.inv1;
+}
+// PZ waveform sample i
+__device__ __forceinline__ double y_at(const double* TT, int i) { return TT[padi(i + 1)] - TT[padi(i)]; }
+// SG trace sample j
+__device__ __forceinline__ double sg_at(const double* TT, const SgDev& s, int j)
+{
+    double acc = 0;
+    for (int k = 0; k <= s.n_taps; ++k) acc = fma(s.gg[k], TT[padi(j + k)], acc);
+    return acc;
+}
+// DerivativeFilter sample i  (src/derivative.jl:47-55)
+__device__ __forceinline__ double deriv_at(const double* TT, int i)
+{
+    const int ii = i < 1 ? 1 : i;
+    return (TT[padi(ii + 1)] - TT[padi(ii)]) - (TT[padi(ii)] - TT[padi(ii - 1)]);
+}
+// direct FIR output j of a CUSP/ZAC filter with differenced taps g[0..L] on TT: out[j] = sum_k g[k] TT[j+L-k]
+__device__ __forceinline__ double fir_at(const double* TT, const double* __restrict__ g, int L, int j)
+{
+    double acc = 0;
+    for (int k = 0; k <= L; ++k) acc = fma(__ldg(g + k), TT[padi(j + L - k)], acc);
+    return acc;
+}
+
+// One warp: find runs of >= k consecutive set bits in the NWORDS-word mask M (bits beyond the trace are zero)
+// that do not start at bit 0 -- the Intersect state machine: `pos` = start of the first such
+// run (-1 if none), `mult` = number of such runs.  M is destroyed.
+__device__ void resolve_runs(uint32_t* M, int k, int lane, int& pos, int& mult)
+{
+    constexpr int Q = NWORDS / 32;
+    uint32_t m[Q], r[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) { m[q] = M[lane * Q + q]; r[q] = m[q]; }
+    int len = 1;
+    while (len < k) {
+        const int step = min(len, k - len);
+        const int ws = step >> 5, bs = step & 31;
+        __syncwarp();
+        uint32_t nr[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int w = lane * Q + q + ws;
+            const uint32_t lo = w < NWORDS ? M[w] : 0u;
+            const uint32_t hi = (w + 1) < NWORDS ? M[w + 1] : 0u;
+            const uint32_t sh = bs ? ((lo >> bs) | (hi << (32 - bs))) : lo;
+            nr[q] = r[q] & sh;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < Q; ++q) { r[q] = nr[q]; M[lane * Q + q] = nr[q]; }
+        len += step;
+    }
+    uint32_t prev_top = __shfl_up_sync(FULL, m[Q - 1], 1);
+    if (lane == 0) prev_top = 0;
+    int p = 0x7fffffff, cnt = 0;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const uint32_t carry = ((q == 0) ? prev_top : m[q - 1]) >> 31;
+        uint32_t c = r[q] & ~((m[q] << 1) | carry);
+        if (lane == 0 && q == 0) c &= ~1u;  // a run that starts at the first sample never fires
+        cnt += __popc(c);
+        if (c && p == 0x7fffffff) p = (lane * Q + q) * 32 + (__ffs(c) - 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        p = min(p, __shfl_xor_sync(FULL, p, o));
+        cnt += __shfl_xor_sync(FULL, cnt, o);
+    }
+    pos = (p == 0x7fffffff) ? -1 : p;
+    mult = cnt;
+}
+
+// linear interpolation of Intersect: x = (thr - y_l)*(x_r - x_l)/(y_r - y_l) + x_l
+__device__ __forceinline__ double cross_x(double thr, double yl, double yr, double tl, double dt)
+{
+    return (thr - yl) * dt / (yr - yl) + tl;
+}
+
+// PolynomialDNI estimate from a window already materialised in `win` (n_w values starting at trace index `from`)
+__device__ double dni_eval(const double* A, int n_w, int m, const double* win, double u)
+{
+    double coef[LGDSP_MAX_DNI_DEG + 1];
+    for (int j = 0; j < m; ++j) {
+        double c = 0;
+        for (int i = 0; i < n_w; ++i) c = fma(A[i * m + j], win[i], c);
+        coef[j] = c;
+    }
+    double v = coef[m - 1];
+    for (int j = m - 2; j >= 0; --j) v = v * u + coef[j];
+    return v;
+}
+// window placement policy (include/lgdsp_b200.h, lgdsp_dni)
+__device__ __forceinline__ void dni_window(int n_w, int n_trace, double p, double& pc, int& from)
+{
+    if (!(p >= 0)) p = 0;
+    if (p > n_trace - 1) p = n_trace - 1;
+    long long f = (long long)rint(p) - n_w / 2;
+    if (f < 0) f = 0;
+    if (f > n_trace - n_w) f = n_trace - n_w;
+    pc = p;
+    from = (int)f;
+}
+
+__global__ void __launch_bounds__(NT, 2)
+icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, long long n_events, long long ld,
+            double* __restrict__ rows)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint16_t* xs = reinterpret_cast<uint16_t*>(smem + SM_XS);
+    double* TT = reinterpret_cast<double*>(smem + SM_TT);
+    uint32_t* masks = reinterpret_cast<uint32_t*>(smem + SM_MASK);
+    double* red = reinterpret_cast<double*>(smem + SM_RED);
+    double* stash = reinterpret_cast<double*>(smem + SM_STASH);
+    double* dniA = reinterpret_cast<double*>(smem + SM_DNI);
+    double* row = reinterpret_cast<double*>(smem + SM_ROW);
+    int* ibuf = reinterpret_cast<int*>(smem + SM_IBUF);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = P.n;
+    const uint32_t wf_bytes = (uint32_t)n * 2u;
+    const double t_first = P.t_first, dt = P.dt;
+    const unsigned G = P.groups;
+
+    // one-time setup: DNI fit matrices -> SMEM, mbarrier
+    for (int i = tid; i < 2 * LGDSP_MAX_DNI * 4; i += NT) dniA[i] = P.dni_A[i];
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    long long e = blockIdx.x;
+    if (tid == 0 && e < n_events) {
+        mbar_expect_tx(bar, wf_bytes);
+        tma_load_1d(xs, wf + e * ld, wf_bytes, bar);
+    }
+    uint32_t phase = 0;
+    const double* A_int = dniA;
+    const double* A_sig = dniA + LGDSP_MAX_DNI * 4;
+
+    for (; e < n_events; e += gridDim.x) {
+        // ------------------------------------------------------------------------------------------
+        // pass 1: raw samples
+        // ------------------------------------------------------------------------------------------
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        const int i0 = tid * CH;
+        const uint4* xv = reinterpret_cast<const uint4*>(xs + i0);
+        uint32_t csum = 0, cq = 0, mn = 0xFFFFu, mx = 0;
+        double blS = 0, blSS = 0, blSX = 0;
+        int nlow = 0, nhigh = 0;
+        for (int q = 0; q < CH / 8; ++q) {
+            if (i0 + q * 8 < n) {  // n is a multiple of 8
+                const uint4 v = xv[q];
+                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t x = (wv[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                    const int i = i0 + q * 8 + k;
+                    csum += x;
+                    cq += csum;
+                    mn = min(mn, x);
+                    mx = max(mx, x);
+                    nlow += ((int)x == P.sat_low);
+                    nhigh += ((int)x == P.sat_high);
+                    if (i >= P.bl_from && i <= P.bl_until) {
+                        blS += (double)x;
+                        blSS += (double)(x * x);  // 65535^2 < 2^32
+                        blSX += (double)((unsigned long long)x * (unsigned)i);
+                    }
+                }
+            }
+        }
+        // block scan of the chunk sums -> exclusive prefix P_excl (exact, uint32)
+        uint32_t incl = csum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t* ured = reinterpret_cast<uint32_t*>(ibuf + IB_SCAN);
+        double* dscan = row + 56;  // row[] is idle until pass 5
+        if (lane == 31) ured[wid] = incl;
+        {
+            double v[5] = {blS, blSS, blSX, (double)nlow, (double)nhigh};
+            block_sum<5>(v, red, tid);
+            blS = v[0]; blSS = v[1]; blSX = v[2]; nlow = (int)v[3]; nhigh = (int)v[4];
+        }
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) woff += (w < wid) ? ured[w] : 0u;
+        const uint32_t P_excl = woff + incl - csum;
+        // second-order scan: PP_excl = sum over previous chunks of (CH*P_excl_c + cq_c)   (exact in double)
+        const int cvalid = max(0, min(CH, n - i0));
+        double v2 = (double)cvalid * (double)P_excl + (double)cq;
+        double incl2 = v2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double t = __shfl_up_sync(FULL, incl2, o);
+            if (lane >= o) incl2 += t;
+        }
+        {
+            double mm[2] = {(double)mx, -(double)mn};
+            if (lane == 31) dscan[wid] = incl2;
+            block_max<2>(mm, red, tid);
+            mx = (uint32_t)mm[0]; mn = (uint32_t)(-mm[1]);
+        }
+        // (block_max's trailing __syncthreads makes the warp totals visible)
+        double woff2 = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) woff2 += (w < wid) ? dscan[w] : 0.0;
+        const double PP_excl = woff2 + incl2 - v2;
+
+        // saturation run lengths (only when a saturated sample exists; block-uniform branch)
+        int cons_low = 0, cons_high = 0;
+        if (nlow + nhigh > 0) {
+            Run rl = {0, 0, 0, cvalid}, rh = {0, 0, 0, cvalid};
+            {
+                const uint16_t* xs_keep = xs + i0;
+                int cl = 0, chh = 0;
+                bool pl = true, ph = true;
+                for (int k = 0; k < cvalid; ++k) {
+                    const uint32_t x = xs_keep[k];
+                    const bool il = ((int)x == P.sat_low), ih = ((int)x == P.sat_high);
+                    cl = il ? cl + 1 : 0;
+                    chh = ih ? chh + 1 : 0;
+                    rl.best = max(rl.best, cl);
+                    rh.best = max(rh.best, chh);
+                    if (pl && il) rl.pre = cl; else pl = false;
+                    if (ph && ih) rh.pre = chh; else ph = false;
+                }
+                rl.suf = cl; rh.suf = chh;
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                Run bl_ = run_shfl_down(rl, o), bh_ = run_shfl_down(rh, o);
+                if ((lane & (2 * o - 1)) == 0) { rl = run_merge(rl, bl_); rh = run_merge(rh, bh_); }
+            }
+            int* ired = reinterpret_cast<int*>(red);
+            __syncthreads();
+            if (lane == 0) {
+                ired[wid * 8 + 0] = rl.pre; ired[wid * 8 + 1] = rl.suf; ired[wid * 8 + 2] = rl.best; ired[wid * 8 + 3] = rl.len;
+                ired[wid * 8 + 4] = rh.pre; ired[wid * 8 + 5] = rh.suf; ired[wid * 8 + 6] = rh.best; ired[wid * 8 + 7] = rh.len;
+            }
+            __syncthreads();
+            Run al = {ired[0], ired[1], ired[2], ired[3]}, ah = {ired[4], ired[5], ired[6], ired[7]};
+            for (int w = 1; w < NWARP; ++w) {
+                Run bl_ = {ired[w * 8], ired[w * 8 + 1], ired[w * 8 + 2], ired[w * 8 + 3]};
+                Run bh_ = {ired[w * 8 + 4], ired[w * 8 + 5], ired[w * 8 + 6], ired[w * 8 + 7]};
+                al = run_merge(al, bl_);
+                ah = run_merge(ah, bh_);
+            }
+            cons_low = al.best; cons_high = ah.best;
+            __syncthreads();
+        }
+
+        // baseline statistics (exact sums) -> blmean
+        const int bl_n = P.bl_until - P.bl_from + 1;
+        double bsX, bsXX;
+        xsums(P.bl_from, P.bl_until, t_first, dt, bsX, bsXX);
+        const Stats bl = stats_finalize(bl_n, bsX, bsXX, blS, blSS, t_first * blS + dt * blSX);
+        const double m = bl.mean;
+        const double e_max = (double)mx - m, e_min = (double)mn - m;
+        double thr[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) thr[k] = e_max * P.tx_frac[k];
+
+        // ------------------------------------------------------------------------------------------
+        // pass 2: pole-zero waveform, prefix sums, tail statistics, t10..t99 masks
+        // ------------------------------------------------------------------------------------------
+        double tl_S = 0, tl_SS = 0, tl_SX = 0, pz_S = 0, pz_SS = 0, pz_SX = 0, tl_bad = 0;
+        uint32_t mbits[5] = {0, 0, 0, 0, 0};
+        {
+            uint32_t Pr = P_excl;
+            double PPr = PP_excl;
+            const double km1 = P.km1;
+            for (int q = 0; q < CH / 8; ++q) {
+                if (i0 + q * 8 < n) {
+                    const uint4 v = xv[q];
+                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const int k = q * 8 + kk;
+                        const int i = i0 + k;
+                        const uint32_t x = (wv[kk >> 1] >> (16 * (kk & 1))) & 0xFFFFu;
+                        Pr += x;
+                        PPr += (double)Pr;
+                        const double ip1 = (double)(i + 1);
+                        const double Sd = fma(-ip1, m, (double)Pr);        // cumsum(w)[i]
+                        const double w = (double)x - m;
+                        const double y = fma(km1, Sd, w);                   // pole-zero corrected sample
+                        const double tri = ip1 * (ip1 + 1.0) * 0.5;
+                        const double SS = fma(-tri, m, PPr);                // cumsum(cumsum(w))[i]
+                        TT[padi(i + 1)] = fma(km1, SS, Sd);                 // cumsum(y)[i]
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) mbits[t] |= (y >= thr[t]) ? (1u << k) : 0u;
+                        if (i >= P.tail_from && i <= P.tail_until) {
+                            const double X = t_first + (double)i * dt;
+                            pz_S += y;
+                            pz_SS = fma(y, y, pz_SS);
+                            pz_SX = fma(X, y, pz_SX);
+                            if (w <= 0.0) {
+                                tl_bad = 1.0;
+                            } else {
+                                const double lg = log(w);
+                                tl_S += lg;
+                                tl_SS = fma(lg, lg, tl_SS);
+                                tl_SX = fma(X, lg, tl_SX);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (tid == 0) TT[0] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) masks[(M_T10 + q) * NWORDS + tid] = mbits[q];
+        masks[M_T0 * NWORDS + tid] = 0u;
+        masks[M_T0INV * NWORDS + tid] = 0u;
+        masks[M_CUR * NWORDS + tid] = 0u;
+        masks[M_PILE * NWORDS + tid] = 0u;
+        {
+            double v[7] = {tl_S, tl_SS, tl_SX, pz_S, pz_SS, pz_SX, tl_bad};
+            block_sum<7>(v, red, tid);
+            tl_S = v[0]; tl_SS = v[1]; tl_SX = v[2]; pz_S = v[3]; pz_SS = v[4]; pz_SX = v[5]; tl_bad = v[6];
+        }
+        // xs is free now: prefetch the next event (TMA, async proxy)
+        if (tid == 0) {
+            const long long en = e + gridDim.x;
+            if (en < n_events) {
+                fence_proxy_async();
+                mbar_expect_tx(bar, wf_bytes);
+                tma_load_1d(xs, wf + en * ld, wf_bytes, bar);
+            }
+        }
+
+        // resolve t10..t99 now (t50 positions the energy pick-off windows of pass 3)
+        if (wid < 5) {
+            int pos, mult;
+            resolve_runs(masks + (M_T10 + wid) * NWORDS, P.tx_min_n, lane, pos, mult);
+            if (lane == 0) ibuf[IB_POS0 + M_T10 + wid] = pos;
+        }
+        __syncthreads();
+        // t50 [us] and the DNI windows of the three energy pick-offs
+        double t50_us = 0.0;
+        {
+            const int pos = ibuf[IB_POS0 + M_T50];
+            if (pos >= 1) {
+                const double x = cross_x(thr[1], y_at(TT, pos - 1), y_at(TT, pos), t_first + (double)(pos - 1) * dt, dt);
+                t50_us = x * 0.001;
+            }
+        }
+        double pk_p[3];
+        int pk_from[3];
+        {
+            const int Ls[3] = {P.etrap.L, P.cusp_L, P.zac_L};
+            const double picks[3] = {P.trap_pick, P.cusp_pick, P.zac_pick};
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                const double tf = t_first + (double)(Ls[f] - 1) * dt;
+                dni_window(P.sig_dni.n_w, n - Ls[f] + 1, (t50_us * 1000.0 + picks[f] - tf) / dt, pk_p[f], pk_from[f]);
+            }
+        }
+
+        // ------------------------------------------------------------------------------------------
+        // pass 3: trapezoids, currents, CUSP/ZAC
+        // ------------------------------------------------------------------------------------------
+        double e10410 = -CUDART_INF, e10410n = -CUDART_INF, e535 = -CUDART_INF, e313 = -CUDART_INF, e313n = -CUDART_INF;
+        double etmax = -CUDART_INF;
+        int etarg = 0x7fffffff;
+        if (G & (LGDSP_GROUP_TIMING | LGDSP_GROUP_TRAPS)) {
+            uint32_t b0 = 0, b0i = 0;
+#pragma unroll 2
+            for (int k = 0; k < CH; ++k) {
+                const int j = i0 + k;
+                if (j < P.t0.nout) {
+                    const double o = trap_at(TT, P.t0, j);
+                    b0 |= (o >= P.t0_thr) ? (1u << k) : 0u;
+                    if (P.t0inv_same) b0i |= (-o >= P.t0_thr) ? (1u << k) : 0u;
+                }
+                if (!P.t0inv_same && j < P.t0inv.nout) {
+                    const double o = trap_at(TT, P.t0inv, j);
+                    b0i |= (-o >= P.t0_thr) ? (1u << k) : 0u;
+                }
+                if (G & LGDSP_GROUP_TRAPS) {
+                    if (j < P.e10410.nout) {
+                        const double o = trap_at(TT, P.e10410, j);
+                        e10410 = fmax(e10410, o);
+                        e10410n = fmax(e10410n, -o);
+                    }
+                    if (j < P.e535.nout) e535 = fmax(e535, trap_at(TT, P.e535, j));
+                    if (j < P.e313.nout) {
+                        const double o = trap_at(TT, P.e313, j);
+                        e313 = fmax(e313, o);
+                        e313n = fmax(e313n, -o);
+                    }
+                    if (j < P.etrap.nout) {
+                        const double o = trap_at(TT, P.etrap, j);
+                        if (o > etmax) { etmax = o; etarg = j; }
+                        const int r = j - pk_from[0];
+                        if (r >= 0 && r < P.sig_dni.n_w) stash[r] = o;
+                    }
+                }
+            }
+            masks[M_T0 * NWORDS + tid] = b0;
+            masks[M_T0INV * NWORDS + tid] = b0i;
+        }
+        // currents: windowed first-argmax of the three SG traces and of the derivative; sg[0] full-trace stats
+        double cmax[4] = {-CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF};
+        int carg[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+        double sg_max = -CUDART_INF, sg_S = 0, sg_SS = 0;
+        if (G & LGDSP_GROUP_CURRENT) {
+            for (int k = 0; k < CH; ++k) {
+                const int j = i0 + k;
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    const bool inwin = (j >= P.cur_from[f] && j <= P.cur_until[f]);
+                    if ((f == 0 && j < P.sg[0].nout) || inwin) {
+                        const double s = sg_at(TT, P.sg[f], j);
+                        if (inwin && s > cmax[f]) { cmax[f] = s; carg[f] = j; }
+                        if (f == 0) {
+                            sg_max = fmax(sg_max, s);
+                            if (j >= P.intr_from && j <= P.intr_until) { sg_S += s; sg_SS = fma(s, s, sg_SS); }
+                        }
+                    }
+                }
+                if (j >= P.cur_from[3] && j <= P.cur_until[3]) {
+                    const double d = deriv_at(TT, j);
+                    if (d > cmax[3]) { cmax[3] = d; carg[3] = j; }
+                }
+            }
+        }
+        // CUSP / ZAC, direct form (validation mode; the structured evaluation replaces it)
+        double czmax[2] = {-CUDART_INF, -CUDART_INF};
+        int czarg[2] = {0x7fffffff, 0x7fffffff};
+        if (G & LGDSP_GROUP_CUSPZAC) {
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                const int L = f ? P.zac_L : P.cusp_L;
+                const double* g = f ? P.zac_g : P.cusp_g;
+                const int nout = n - L + 1;
+                for (int j = tid; j < nout; j += NT) {
+                    const double o = fir_at(TT, g, L, j);
+                    if (o > czmax[f]) { czmax[f] = o; czarg[f] = j; }
+                    const int r = j - pk_from[1 + f];
+                    if (r >= 0 && r < P.sig_dni.n_w) stash[(1 + f) * LGDSP_MAX_DNI + r] = o;
+                }
+            }
+        }
+        // reductions of pass 3
+        {
+            double v[6] = {e10410, e10410n, e535, e313, e313n, sg_max};
+            block_max<6>(v, red, tid);
+            e10410 = v[0]; e10410n = v[1]; e535 = v[2]; e313 = v[3]; e313n = v[4]; sg_max = v[5];
+        }
+        {
+            double v[7] = {etmax, cmax[0], cmax[1], cmax[2], cmax[3], czmax[0], czmax[1]};
+            int ix[7] = {etarg, carg[0], carg[1], carg[2], carg[3], czarg[0], czarg[1]};
+            block_argmax<7>(v, ix, red, tid);
+            etmax = v[0]; etarg = ix[0];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) { cmax[f] = v[1 + f]; carg[f] = ix[1 + f]; }
+            czmax[0] = v[5]; czarg[0] = ix[5]; czmax[1] = v[6]; czarg[1] = ix[6];
+        }
+        {
+            double v[2] = {sg_S, sg_SS};
+            block_sum<2>(v, red, tid);
+            sg_S = v[0]; sg_SS = v[1];
+        }
+
+        // ------------------------------------------------------------------------------------------
+        // pass 4: masks on the sg[0] trace (t50_current, in-trace pile-up on the REVERSED trace)
+        // ------------------------------------------------------------------------------------------
+        double pile_thr = 0.0;
+        const double cur_thr = sg_max * 0.5;
+        const int nsg = P.sg[0].nout;
+        if (G & LGDSP_GROUP_CURRENT) {
+            const int cnt = P.intr_until - P.intr_from + 1;
+            double dX, dXX;
+            xsums(P.intr_from, P.intr_until, t_first + P.sg[0].offset * dt, dt, dX, dXX);
+            const Stats st = stats_finalize(cnt, dX, dXX, sg_S, sg_SS, 0.0);
+            pile_thr = st.sigma * P.nsigma;
+            if (pile_thr == 0.0) pile_thr = 1.0;  // src/dsp_routines.jl:77
+            uint32_t bc = 0, bp = 0;
+            for (int k = 0; k < CH; ++k) {
+                const int j = i0 + k;
+                if (j < nsg) {
+                    const double s = sg_at(TT, P.sg[0], j);
+                    bc |= (s >= cur_thr) ? (1u << k) : 0u;
+                    bp |= (s >= pile_thr) ? (1u << k) : 0u;
+                }
+            }
+            masks[M_CUR * NWORDS + tid] = bc;
+            if (bp) {
+                // reversed trace: forward index j <-> reversed index nsg-1-j
+                uint32_t rev = __brev(bp);
+                int base = nsg - 1 - (i0 + 31);
+                if (base < 0) { rev >>= (-base); base = 0; }
+                const int w = base >> 5, sh = base & 31;
+                atomicOr(&masks[M_PILE * NWORDS + w], rev << sh);
+                if (sh && w + 1 < NWORDS) atomicOr(&masks[M_PILE * NWORDS + w + 1], rev >> (32 - sh));
+            }
+        }
+        __syncthreads();
+        // crossing resolution: t0, t0_inv, t50_current, pile-up (one warp each)
+        if (wid < 4) {
+            const int which[4] = {M_T0, M_T0INV, M_CUR, M_PILE};
+            const int ks[4] = {P.t0_min_n, P.t0_min_n, P.tx_min_n, P.intr_min_n};
+            int pos, mult;
+            resolve_runs(masks + which[wid] * NWORDS, ks[wid], lane, pos, mult);
+            if (lane == 0) {
+                ibuf[IB_POS0 + which[wid]] = pos;
+                if (which[wid] == M_PILE) ibuf[IB_MULT] = mult;
+            }
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------------------------------------
+        // pass 5: scalar results
+        // ------------------------------------------------------------------------------------------
+        if (tid < LGDSP_NCOL) row[tid] = 0.0;
+        __syncthreads();
+        if (wid == 0) {
+            // warp 0: everything that needs t0/t80 (timing, qdrift, lq) -- lane 0 computes, it is scalar work
+            if (lane == 0) {
+                row[LGDSP_COL_blmean] = bl.mean; row[LGDSP_COL_blsigma] = bl.sigma;
+                row[LGDSP_COL_blslope] = bl.slope; row[LGDSP_COL_bloffset] = bl.offset;
+                row[LGDSP_COL_qc_label] = -1.0;
+                row[LGDSP_COL_e_max] = e_max; row[LGDSP_COL_e_min] = e_min;
+                row[LGDSP_COL_n_sat_low] = (double)nlow; row[LGDSP_COL_n_sat_high] = (double)nhigh;
+                row[LGDSP_COL_n_sat_low_cons] = (double)cons_low; row[LGDSP_COL_n_sat_high_cons] = (double)cons_high;
+                // tailstats  src/tailstats.jl:22-72
+                const int tn = P.tail_until - P.tail_from + 1;
+                double tsX, tsXX;
+                xsums(P.tail_from, P.tail_until, t_first, dt, tsX, tsXX);
+                if (tl_bad == 0.0) {
+                    const Stats ts = stats_finalize(tn, tsX, tsXX, tl_S, tl_SS, tl_SX);
+                    row[LGDSP_COL_tail_mean] = ts.mean; row[LGDSP_COL_tail_sigma] = ts.sigma;
+                    row[LGDSP_COL_tail_tau] = div_rn(-1.0, ts.slope);
+                }
+                const Stats pz = stats_finalize(tn, tsX, tsXX, pz_S, pz_SS, pz_SX);
+                row[LGDSP_COL_tailmean] = pz.mean; row[LGDSP_COL_tailsigma] = pz.sigma;
+                row[LGDSP_COL_tailslope] = pz.slope; row[LGDSP_COL_tailoffset] = pz.offset;
+
+                double tx_us[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const int pos = ibuf[IB_POS0 + M_T10 + q];
+                    double t = 0.0;
+                    if (pos >= 1)
+                        t = cross_x(thr[q], y_at(TT, pos - 1), y_at(TT, pos), t_first + (double)(pos - 1) * dt, dt) * 0.001;
+                    if (t != t) t = 0.0;
+                    tx_us[q] = t;
+                }
+                double t0_us = 0.0, t0inv_us = 0.0;
+                if (G & LGDSP_GROUP_TIMING) {
+                    row[LGDSP_COL_t10] = tx_us[0]; row[LGDSP_COL_t50] = tx_us[1]; row[LGDSP_COL_t80] = tx_us[2];
+                    row[LGDSP_COL_t90] = tx_us[3]; row[LGDSP_COL_t99] = tx_us[4];
+                    int pos = ibuf[IB_POS0 + M_T0];
+                    if (pos >= 1) {
+                        const double tl = t_first + (double)(pos - 1 + P.t0.L - 1) * dt;
+                        t0_us = cross_x(P.t0_thr, trap_at(TT, P.t0, pos - 1), trap_at(TT, P.t0, pos), tl, dt) * 0.001;
+                        if (t0_us != t0_us) t0_us = 0.0;
+                    }
+                    pos = ibuf[IB_POS0 + M_T0INV];
+                    if (pos >= 1) {
+                        const double tl = t_first + (double)(pos - 1 + P.t0inv.L - 1) * dt;
+                        t0inv_us = cross_x(P.t0_thr, -trap_at(TT, P.t0inv, pos - 1), -trap_at(TT, P.t0inv, pos), tl, dt) * 0.001;
+                        if (t0inv_us != t0inv_us) t0inv_us = 0.0;
+                    }
+                    row[LGDSP_COL_t0] = t0_us;
+                    row[LGDSP_COL_t0_inv] = t0inv_us;
+                    row[LGDSP_COL_drift_time] = (tx_us[3] - t0_us) * 1000.0;
+                }
+                if (G & LGDSP_GROUP_QDRIFT) {
+                    // get_qdrift  src/dsp_routines.jl:51-64; integrator trace I[i] = TT[i+1]
+                    const double starts[2] = {t0_us, tx_us[2]};
+                    const double firsts[2] = {P.qd_first, P.lq_first}, lasts[2] = {P.qd_last, P.lq_last};
+                    for (int q = 0; q < 2; ++q) {
+                        const double tns = starts[q] * 1000.0;
+                        const double ts3[3] = {tns, tns + firsts[q], tns + lasts[q]};
+                        double a[3];
+                        for (int s = 0; s < 3; ++s) {
+                            double pc;
+                            int from;
+                            dni_window(P.int_dni.n_w, n, (ts3[s] - t_first) / dt, pc, from);
+                            double win[LGDSP_MAX_DNI];
+                            for (int i = 0; i < P.int_dni.n_w; ++i) win[i] = TT[padi(from + i + 1)];
+                            a[s] = dni_eval(A_int, P.int_dni.n_w, P.int_dni.m, win, pc - (double)from);
+                        }
+                        const double area1 = a[1] - a[0], area2 = a[2] - a[1];
+                        row[q == 0 ? LGDSP_COL_qdrift : LGDSP_COL_lq] = area2 - area1;
+                    }
+                }
+            }
+        } else if (wid == 1) {
+            if (lane == 0 && (G & LGDSP_GROUP_TRAPS)) {
+                row[LGDSP_COL_e_10410] = e10410; row[LGDSP_COL_e_535] = e535; row[LGDSP_COL_e_313] = e313;
+                row[LGDSP_COL_e_10410_inv] = e10410n; row[LGDSP_COL_e_313_inv] = e313n;
+                row[LGDSP_COL_e_trap_max] = etmax;
+                row[LGDSP_COL_t_trap_max] = t_first + (double)(etarg + P.etrap.L - 1) * dt;
+                row[LGDSP_COL_e_trap] = dni_eval(A_sig, P.sig_dni.n_w, P.sig_dni.m, stash, pk_p[0] - (double)pk_from[0]);
+            }
+        } else if (wid == 2) {
+            if (lane == 0 && (G & LGDSP_GROUP_CUSPZAC)) {
+                row[LGDSP_COL_e_cusp_max] = czmax[0];
+                row[LGDSP_COL_t_cusp_max] = t_first + (double)(czarg[0] + P.cusp_L - 1) * dt;
+                row[LGDSP_COL_e_cusp] = dni_eval(A_sig, P.sig_dni.n_w, P.sig_dni.m, stash + LGDSP_MAX_DNI,
+                                                 pk_p[1] - (double)pk_from[1]);
+            }
+        } else if (wid == 3) {
+            if (lane == 0 && (G & LGDSP_GROUP_CUSPZAC)) {
+                row[LGDSP_COL_e_zac_max] = czmax[1];
+                row[LGDSP_COL_t_zac_max] = t_first + (double)(czarg[1] + P.zac_L - 1) * dt;
+                row[LGDSP_COL_e_zac] = dni_eval(A_sig, P.sig_dni.n_w, P.sig_dni.m, stash + 2 * LGDSP_MAX_DNI,
+                                                pk_p[2] - (double)pk_from[2]);
+            }
+        } else if (wid == 4) {
+            if (lane < 4 && (G & LGDSP_GROUP_CURRENT)) {
+                // get_wvf_maximum  src/interpolation.jl:30-46: parabola only if strictly inside the window
+                const int f = lane;
+                const int a = carg[f];
+                double v = cmax[f];
+                if (a > P.cur_from[f] && a < P.cur_until[f]) {
+                    const double y1 = (f < 3) ? sg_at(TT, P.sg[f], a - 1) : deriv_at(TT, a - 1);
+                    const double y3 = (f < 3) ? sg_at(TT, P.sg[f], a + 1) : deriv_at(TT, a + 1);
+                    v = extrema3(y1, v, y3);
+                }
+                row[LGDSP_COL_a_sg + f] = v;
+            }
+        } else if (wid == 5) {
+            if (lane == 0 && (G & LGDSP_GROUP_CURRENT)) {
+                const double tf = t_first + (double)P.sg[0].offset * dt;
+                // t50_current  src/dsp_icpc.jl:192-195
+                int pos = ibuf[IB_POS0 + M_CUR];
+                double t = 0.0;
+                if (pos >= 1) {
+                    t = cross_x(cur_thr, sg_at(TT, P.sg[0], pos - 1), sg_at(TT, P.sg[0], pos), tf + (double)(pos - 1) * dt, dt) * 0.001;
+                    if (t != t) t = 0.0;
+                }
+                row[LGDSP_COL_t50_current] = t;
+                // in-trace pile-up  src/dsp_routines.jl:72-82 (reversed trace r[j] = s[nsg-1-j], same time axis)
+                pos = ibuf[IB_POS0 + M_PILE];
+                double xi = CUDART_NAN;
+                if (pos >= 1) {
+                    const double yl = sg_at(TT, P.sg[0], nsg - 1 - (pos - 1)), yr = sg_at(TT, P.sg[0], nsg - 1 - pos);
+                    xi = cross_x(pile_thr, yl, yr, tf + (double)(pos - 1) * dt, dt);
+                }
+                const double last_t = tf + (double)(nsg - 1) * dt;
+                row[LGDSP_COL_inTrace_intersect] = last_t - xi;
+                row[LGDSP_COL_inTrace_n] = (double)ibuf[IB_MULT];
+            }
+        }
+        __syncthreads();
+        if (tid < LGDSP_NCOL) rows[e * LGDSP_NCOL + tid] = row[tid];
+        // (the next iteration's first __syncthreads-bearing reduction orders reuse of row/stash/masks)
+        __syncthreads();
+    }
+}
+
+// ==================================================================================================
+// Trapezoid sweep kernel: dsp_trap_rt_optimization / dsp_trap_ft_optimization
+// (/root/reference/src/dsp_filter_optimization.jl:102-133, 241-274).  The reference re-filters every waveform
+// once per grid point and reads ONE interpolated sample of each filtered trace; here the waveform's prefix sums
+// stay resident in SMEM and every (rt, ft) variant only evaluates the n_w trapezoid outputs of its
+// PolynomialDNI window (4 look-ups each).  One warp per variant.
+// ==================================================================================================
+constexpr int SW_XS = 0;
+constexpr int SW_TT = SW_XS + MAXN * 2;
+constexpr int SW_MASK = SW_TT + TT_LEN * 8;
+constexpr int SW_RED = SW_MASK + NWORDS * 4;
+constexpr int SW_DNI = SW_RED + NWARP * RED_W * 8;
+constexpr int SW_OUT = SW_DNI + LGDSP_MAX_DNI * 4 * 8;
+constexpr int SW_MAXVAR = 1024;
+constexpr int SW_IBUF = SW_OUT + SW_MAXVAR * 4;
+constexpr int SW_DSCAN = SW_IBUF + 64 * 4;
+constexpr int SW_BAR = SW_DSCAN + 8 * 8;
+constexpr int SW_TOTAL = SW_BAR + 16;
+
+__global__ void __launch_bounds__(NT, 2)
+sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf, long long n_events, long long ld,
+             float* __restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint16_t* xs = reinterpret_cast<uint16_t*>(smem + SW_XS);
+    double* TT = reinterpret_cast<double*>(smem + SW_TT);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(smem + SW_MASK);
+    double* red = reinterpret_cast<double*>(smem + SW_RED);
+    double* dniA = reinterpret_cast<double*>(smem + SW_DNI);
+    float* obuf = reinterpret_cast<float*>(smem + SW_OUT);
+    int* ibuf = reinterpret_cast<int*>(smem + SW_IBUF);
+    double* dscan = reinterpret_cast<double*>(smem + SW_DSCAN);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SW_BAR);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = P.n;
+    const uint32_t wf_bytes = (uint32_t)n * 2u;
+    const double t_first = P.t_first, dt = P.dt;
+    for (int i = tid; i < LGDSP_MAX_DNI * 4; i += NT) dniA[i] = P.dni_A[i];
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    long long e = blockIdx.x;
+    if (tid == 0 && e < n_events) {
+        mbar_expect_tx(bar, wf_bytes);
+        tma_load_1d(xs, wf + e * ld, wf_bytes, bar);
+    }
+    uint32_t phase = 0;
+    for (; e < n_events; e += gridDim.x) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        const int i0 = tid * CH;
+        const uint4* xv = reinterpret_cast<const uint4*>(xs + i0);
+        uint32_t csum = 0, cq = 0;
+        double blS = 0;
+        for (int q = 0; q < CH / 8; ++q) {
+            if (i0 + q * 8 < n) {
+                const uint4 v = xv[q];
+                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t x = (wv[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                    const int i = i0 + q * 8 + k;
+                    csum += x;
+                    cq += csum;
+                    if (i >= P.bl_from && i <= P.bl_until) blS += (double)x;
+                }
+            }
+        }
+        uint32_t incl = csum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t* ured = reinterpret_cast<uint32_t*>(ibuf + IB_SCAN);
+        if (lane == 31) ured[wid] = incl;
+        {
+            double v[1] = {blS};
+            block_sum<1>(v, red, tid);
+            blS = v[0];
+        }
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) woff += (w < wid) ? ured[w] : 0u;
+        const uint32_t P_excl = woff + incl - csum;
+        const int cvalid = max(0, min(CH, n - i0));
+        const double v2 = (double)cvalid * (double)P_excl + (double)cq;
+        double incl2 = v2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double t = __shfl_up_sync(FULL, incl2, o);
+            if (lane >= o) incl2 += t;
+        }
+        if (lane == 31) dscan[wid] = incl2;
+        __syncthreads();
+        double woff2 = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) woff2 += (w < wid) ? dscan[w] : 0.0;
+        const double PP_excl = woff2 + incl2 - v2;
+        // blmean exactly as signalstats: mean_Y = sum_Y * inv_n
+        const double m = mul_rn(blS, div_rn(1.0, (double)(P.bl_until - P.bl_from + 1)));
+        double ymax = -CUDART_INF;
+        {
+            uint32_t Pr = P_excl;
+            double PPr = PP_excl;
+            const double km1 = P.km1;
+            for (int q = 0; q < CH / 8; ++q) {
+                if (i0 + q * 8 < n) {
+                    const uint4 v = xv[q];
+                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const int i = i0 + q * 8 + kk;
+                        const uint32_t x = (wv[kk >> 1] >> (16 * (kk & 1))) & 0xFFFFu;
+                        Pr += x;
+                        PPr += (double)Pr;
+                        const double ip1 = (double)(i + 1);
+                        const double Sd = fma(-ip1, m, (double)Pr);
+                        const double w = (double)x - m;
+                        const double y = fma(km1, Sd, w);
+                        const double tri = ip1 * (ip1 + 1.0) * 0.5;
+                        const double SS = fma(-tri, m, PPr);
+                        TT[padi(i + 1)] = fma(km1, SS, Sd);
+                        ymax = fmax(ymax, y);
+                    }
+                }
+            }
+        }
+        if (tid == 0) TT[0] = 0.0;
+        {
+            double v[1] = {ymax};
+            block_max<1>(v, red, tid);
+            ymax = v[0];
+        }
+        if (tid == 0) {
+            const long long en = e + gridDim.x;
+            if (en < n_events) {
+                fence_proxy_async();
+                mbar_expect_tx(bar, wf_bytes);
+                tma_load_1d(xs, wf + en * ld, wf_bytes, bar);
+            }
+        }
+        // t50 on the PZ waveform at 0.5*maximum  (src/dsp_filter_optimization.jl:260)
+        const double thr = ymax * 0.5;
+        {
+            uint32_t b = 0;
+#pragma unroll 4
+            for (int k = 0; k < CH; ++k) {
+                const int i = i0 + k;
+                // same expression as in the pass above, so the comparison sees the identical value
+                if (i < n) b |= (y_at(TT, i) >= thr) ? (1u << k) : 0u;
+            }
+            mask[tid] = b;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            int pos, mult;
+            resolve_runs(mask, P.tx_min_n, lane, pos, mult);
+            if (lane == 0) ibuf[0] = pos;
+        }
+        __syncthreads();
+        double t50_us = 0.0;
+        {
+            const int pos = ibuf[0];
+            if (pos >= 1) {
+                t50_us = cross_x(thr, y_at(TT, pos - 1), y_at(TT, pos), t_first + (double)(pos - 1) * dt, dt) * 0.001;
+                if (t50_us != t50_us) t50_us = 0.0;
+            }
+        }
+        const int n_w = P.sig_dni.n_w, mdeg = P.sig_dni.m;
+        for (int v = wid; v < P.nvar; v += NWARP) {
+            const SweepVar sv = P.vars[v];
+            const int nout = n - sv.t.L + 1;
+            const double tf = t_first + (double)(sv.t.L - 1) * dt;
+            const double t_ns = sv.mode ? t50_us * 1000.0 + sv.pick_ns : sv.pick_ns;
+            double pc;
+            int from;
+            dni_window(n_w, nout, (t_ns - tf) / dt, pc, from);
+            double c[LGDSP_MAX_DNI_DEG + 1] = {0, 0, 0, 0};
+            for (int i = lane; i < n_w; i += 32) {
+                const double val = trap_at(TT, sv.t, from + i);
+#pragma unroll
+                for (int j = 0; j <= LGDSP_MAX_DNI_DEG; ++j)
+                    if (j < mdeg) c[j] = fma(dniA[i * mdeg + j], val, c[j]);
+            }
+#pragma unroll
+            for (int j = 0; j <= LGDSP_MAX_DNI_DEG; ++j) c[j] = warp_sum(c[j]);
+            if (lane == 0) {
+                const double u = pc - (double)from;
+                double r = c[mdeg - 1];
+                for (int j = mdeg - 2; j >= 0; --j) r = r * u + c[j];
+                obuf[v] = (nout >= n_w) ? (float)r : CUDART_NAN_F;
+            }
+        }
+        __syncthreads();
+        for (int v = tid; v < P.nvar; v += NT) out[e * (long long)P.nvar + v] = obuf[v];
+        __syncthreads();
+    }
+}
+
+cudaError_t sweep_configure(int* max_blocks_per_sm)
+{
+    cudaError_t err = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_TOTAL);
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, sweep_kernel, NT, SW_TOTAL);
+}
+
+void sweep_launch(const SweepDev& P, const uint16_t* d_wf, long long n_events, long long ld, float* d_out, int grid,
+                  cudaStream_t stream)
+{
+    sweep_kernel<<<grid, NT, SW_TOTAL, stream>>>(P, d_wf, n_events, ld, d_out);
+}
+
+void icpc_launch(const IcpcDev& P, const uint16_t* d_wf, long long n_events, long long ld, double* d_rows, int grid,
+                 cudaStream_t stream)
+{
+    icpc_kernel<<<grid, NT, SM_TOTAL, stream>>>(P, d_wf, n_events, ld, d_rows);
+}
+
+cudaError_t icpc_configure(int* max_blocks_per_sm)
+{
+    cudaError_t err = cudaFuncSetAttribute(icpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, icpc_kernel, NT, SM_TOTAL);
+}
+
+}  // namespace lgdsp

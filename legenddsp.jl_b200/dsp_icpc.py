@@ -1,0 +1,131 @@
+"""`dsp_icpc(data, config, τ, pars_filter)` -- host-side mirror of the reference entry point
+(/root/reference/src/dsp_icpc.jl:62-230) on top of the C ABI (include/lgdsp_b200.h).
+
+Same argument meaning, same output column names/order/units as the reference's TypedTables.Table
+(src/dsp_icpc.jl:210-229).  All arithmetic runs in the CUDA library; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Any, Dict, Mapping, Optional
+
+import numpy as np
+
+from . import _abi
+from ._lib import Handle
+from .config import DSPConfig, Q, RddspPolicy, DEFAULT_POLICY, ns, resolve_icpc_params
+
+
+@dataclass
+class RDWaveforms:
+    """Minimal stand-in for `ArrayOfRDWaveforms` with a shared, uniformly sampled time axis:
+    `signal[n_events, n_samples]` (each waveform contiguous, as `flatview(wvfs.signal)` of the LH5 column) and
+    the time axis of the first waveform (the reference only consults `wvfs[1].time`, src/dsp_icpc.jl:88,90)."""
+    signal: Any
+    t_first: Q = ns(0.0)
+    step: Q = ns(16.0)
+
+    def __len__(self):
+        return int(self.signal.shape[0])
+
+
+# reference column order, src/dsp_icpc.jl:210-229 (pass-through columns included)
+TABLE_COLUMNS = (
+    "blmean", "blsigma", "blslope", "bloffset", "tailmean", "tailsigma", "tailslope", "tailoffset", "qc_label",
+    "t0", "t10", "t50", "t80", "t90", "t99", "t50_current", "drift_time", "tail_τ", "tail_mean", "tail_sigma",
+    "e_max", "e_min", "e_10410", "e_535", "e_313", "e_10410_inv", "e_313_inv", "t0_inv", "e_trap", "e_cusp", "e_zac",
+    "e_trap_max", "e_cusp_max", "e_zac_max", "t_trap_max", "t_cusp_max", "t_zac_max", "qdrift", "lq",
+    "a_sg", "a_60", "a_100", "a_raw", "blfc", "timestamp", "eventID_fadc", "e_fc",
+    "inTrace_intersect", "inTrace_n", "n_sat_low", "n_sat_high", "n_sat_low_cons", "n_sat_high_cons",
+)
+_PASS_THROUGH = {"blfc": "baseline", "timestamp": "timestamp", "eventID_fadc": "eventnumber", "e_fc": "daqenergy"}
+_RENAME = {"tail_τ": "tail_tau"}
+
+_handles: Dict[int, Handle] = {}
+
+
+def get_handle(device: int = 0) -> Handle:
+    """process-wide handle per device (created on first use; raises without a CUDA device)"""
+    h = _handles.get(device)
+    if h is None or h._h is None:
+        h = Handle(device)
+        _handles[device] = h
+    return h
+
+
+def _as_waveforms(wvfs) -> RDWaveforms:
+    if isinstance(wvfs, RDWaveforms):
+        return wvfs
+    if hasattr(wvfs, "signal") and hasattr(wvfs, "step"):
+        return RDWaveforms(wvfs.signal, getattr(wvfs, "t_first", ns(0.0)), wvfs.step)
+    return RDWaveforms(wvfs)
+
+
+def _signal_u16(sig) -> np.ndarray:
+    a = np.asarray(sig)
+    if a.ndim != 2:
+        raise ValueError("waveform signals must be a 2-D array [n_events, n_samples]")
+    if a.dtype != np.uint16:
+        if not np.issubdtype(a.dtype, np.integer):
+            raise TypeError("this implementation processes raw ADC samples (UInt16); got dtype %s" % a.dtype)
+        if a.size and (a.min() < 0 or a.max() > 65535):
+            raise ValueError("samples outside the UInt16 range")
+        a = a.astype(np.uint16)
+    if a.strides[1] != 2:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def rows_to_table(rows: np.ndarray, data: Optional[Mapping[str, Any]] = None) -> "OrderedDict[str, np.ndarray]":
+    """double[n_events, 49] device rows -> reference-ordered table of columns"""
+    out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    n = rows.shape[0]
+    for name in TABLE_COLUMNS:
+        if name in _PASS_THROUGH:
+            src = _PASS_THROUGH[name]
+            if data is not None and src in data:
+                out[name] = np.asarray(data[src])
+            continue
+        col = rows[:, _abi.COL[_RENAME.get(name, name)]]
+        if _RENAME.get(name, name) in _abi.INT_COLUMNS:
+            out[name] = col.astype(np.int64)
+        else:
+            out[name] = np.ascontiguousarray(col)
+    assert all(len(v) == n for v in out.values())
+    return out
+
+
+def dsp_icpc(data: Mapping[str, Any], config: DSPConfig, τ: Q, pars_filter: Optional[Dict[str, Any]] = None, *,
+             f_evaluate_qc=None, device: int = 0, handle: Optional[Handle] = None,
+             policy: RddspPolicy = DEFAULT_POLICY, groups: int = _abi.GROUP_ALL,
+             cuspzac_direct: bool = False) -> "OrderedDict[str, np.ndarray]":
+    """DSP routine for ICPC detectors: the reference's `dsp_icpc(data, config, τ, pars_filter)`.
+
+    `data` needs the columns `waveform` (RDWaveforms or a UInt16 array [n_events, n_samples]) and, for the
+    pass-through columns, `baseline`, `timestamp`, `eventnumber`, `daqenergy`.
+    Returns an ordered mapping column name -> numpy array (times in µs / ns as in the reference, see _abi.UNITS).
+    """
+    if f_evaluate_qc is not None:
+        # src/dsp_icpc.jl:108: the ML quality-cut classifier (LIBSVM) is outside the hot path
+        raise NotImplementedError("f_evaluate_qc is not supported; qc_label is -1 as in the reference without a model")
+    w = _as_waveforms(data["waveform"])
+    sig = _signal_u16(w.signal)
+    n_events, n_samples = sig.shape
+    P = resolve_icpc_params(config, τ, pars_filter, n_samples=n_samples, t_first=w.t_first, step=w.step,
+                            groups=groups, policy=policy, cuspzac_direct=cuspzac_direct)
+    h = handle or get_handle(device)
+    rows = np.zeros((n_events, _abi.NCOL), dtype=np.float64)
+    h.icpc_run_host(P, sig.ctypes.data, n_events, sig.strides[0] // 2, rows.ctypes.data)
+    return rows_to_table(rows, data)
+
+
+def dsp_icpc_rows(signal_u16: np.ndarray, params: _abi.IcpcParams, *, device: int = 0,
+                  handle: Optional[Handle] = None) -> np.ndarray:
+    """lower-level entry used by the tests: resolved params in, raw rows out"""
+    sig = _signal_u16(signal_u16)
+    h = handle or get_handle(device)
+    rows = np.zeros((sig.shape[0], _abi.NCOL), dtype=np.float64)
+    h.icpc_run_host(params, sig.ctypes.data, sig.shape[0], sig.strides[0] // 2, rows.ctypes.data)
+    return rows

@@ -1,0 +1,705 @@
+/*
+ * lgdsp_oracle.c -- CPU restatement of the LegendDSP.jl `dsp_icpc` chain.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * file's library. The product (legenddsp.jl_b200) never links, imports or calls it.
+ *
+ * PARITY STATUS: "parity unpinned" for everything the reference delegates to RadiationDetectorDSP.jl
+ * (signalstats, InvCRFilter, TrapezoidalChargeFilter, CUSP/ZACChargeFilter, SavitzkyGolayFilter,
+ * IntegratorFilter, Intersect, SignalEstimator/PolynomialDNI).  That package (compat 0.2.17,
+ * /root/reference/Project.toml:35, no Manifest) is not vendored under /root/reference and no Julia
+ * toolchain exists in this image, so these functions restate the published/recalled algorithm (marked
+ * [RDDSP]) and are anchored on LegendDSP's own call sites.  The in-tree primitives (saturation, tailstats,
+ * extremestats, get_wvf_maximum, DerivativeFilter, get_t0/get_threshold/get_qdrift/get_intracePileUp and
+ * the dsp_icpc glue) are transcribed from the cited lines and pinned by the reference's own known-answer
+ * tests (tests/test_oracle_kat.py).
+ *
+ * Style: float64 throughout, one materialised intermediate per reference broadcast step, sequential
+ * loops, direct-form FIRs -- deliberately the reference's cost structure, because the same code is timed
+ * as the CPU baseline ("port").  Build: oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp).
+ *
+ * All file:line citations are relative to /root/reference.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../include/lgdsp_b200.h"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------------
+ * small linear algebra: least-squares fit matrix  [RDDSP _lsq_fit_matrix; usage src/multi_intersect.jl:80,115-119]
+ * A = V (V^T V)^-1,  V[i][j] = x_i^j, x_i = i  (n x (d+1)),  so that coef_j = sum_i A[i][j] y[i].
+ * ------------------------------------------------------------------------------------------------ */
+static int solve_spd_small(int m, double* M /* m x m */, double* B /* m x nb */, int nb)
+{
+    /* Gauss-Jordan with partial pivoting, m <= 8 */
+    for (int c = 0; c < m; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < m; ++r)
+            if (fabs(M[r * m + c]) > fabs(M[piv * m + c])) piv = r;
+        if (M[piv * m + c] == 0.0) return -1;
+        if (piv != c) {
+            for (int k = 0; k < m; ++k) { double t = M[c * m + k]; M[c * m + k] = M[piv * m + k]; M[piv * m + k] = t; }
+            for (int k = 0; k < nb; ++k) { double t = B[c * nb + k]; B[c * nb + k] = B[piv * nb + k]; B[piv * nb + k] = t; }
+        }
+        double inv = 1.0 / M[c * m + c];
+        for (int k = 0; k < m; ++k) M[c * m + k] *= inv;
+        for (int k = 0; k < nb; ++k) B[c * nb + k] *= inv;
+        for (int r = 0; r < m; ++r) {
+            if (r == c) continue;
+            double f = M[r * m + c];
+            if (f == 0.0) continue;
+            for (int k = 0; k < m; ++k) M[r * m + k] -= f * M[c * m + k];
+            for (int k = 0; k < nb; ++k) B[r * nb + k] -= f * B[c * nb + k];
+        }
+    }
+    return 0;
+}
+
+/* fit matrix for abscissae x_i = x0 + i, i = 0..n-1 */
+static int lsq_fit_matrix_x0(int n, int degree, double x0, double* A)
+{
+    int m = degree + 1;
+    if (n < m || m > 8 || n > 4096) return -1;
+    double VtV[64];
+    double* Vt = (double*)malloc(sizeof(double) * (size_t)m * n); /* m x n */
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i < n; ++i) Vt[j * n + i] = pow(x0 + i, j);
+    for (int a = 0; a < m; ++a)
+        for (int b = 0; b < m; ++b) {
+            double s = 0;
+            for (int i = 0; i < n; ++i) s += Vt[a * n + i] * Vt[b * n + i];
+            VtV[a * m + b] = s;
+        }
+    /* solve (VtV) Z = Vt  ->  Z = (VtV)^-1 Vt  (m x n);  A = Z^T */
+    if (solve_spd_small(m, VtV, Vt, n) != 0) { free(Vt); return -1; }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < m; ++j) A[i * m + j] = Vt[j * n + i];
+    free(Vt);
+    return 0;
+}
+
+ORC_API int orc_lsq_fit_matrix(int n, int degree, double* A) { return lsq_fit_matrix_x0(n, degree, 0.0, A); }
+
+/* Savitzky-Golay coefficients [RDDSP SavitzkyGolayFilter(length, degree, derivative)]: symmetric window
+ * of n_taps (odd) points centred at 0, LSQ polynomial of `degree`, `derivative`-th derivative at the centre,
+ * per-sample units.  s[j] = sum_k h[k] y[j+k]. */
+ORC_API int orc_sg_coeffs(int n_taps, int degree, int derivative, double* h)
+{
+    if (n_taps < 1 || (n_taps & 1) == 0 || derivative > degree || n_taps <= degree) return -1;
+    int m = degree + 1;
+    double* A = (double*)malloc(sizeof(double) * (size_t)n_taps * m);
+    if (lsq_fit_matrix_x0(n_taps, degree, -(double)(n_taps / 2), A) != 0) { free(A); return -1; }
+    double fact = 1.0;
+    for (int k = 2; k <= derivative; ++k) fact *= k;
+    for (int i = 0; i < n_taps; ++i) h[i] = fact * A[i * m + derivative];
+    free(A);
+    return 0;
+}
+
+/* CUSP / ZAC coefficients [RDDSP CUSPChargeFilter/ZACChargeFilter(sigma, toplen, tau, length, beta);
+ * GERDA, Eur. Phys. J. C 75 (2015) 255, eq. 1; same construction as LEGEND's dspeed cusp_filter/zac_filter]:
+ *   lt = (L - flat) / 2 (integer division)
+ *   cusp[k] = sinh(k/sigma)/sinh(lt/sigma)        k <  lt
+ *           = 1                                   lt <= k <= lt+flat
+ *           = sinh((L-k)/sigma)/sinh(lt/sigma)    k >  lt+flat
+ *   par[k]  = (k-lt/2)^2 - (lt/2)^2 (left), 0 (top), (L-k-lt/2)^2 - (lt/2)^2 (right)
+ *   zac     = cusp - par * sum(cusp)/sum(par)
+ *   fir     = conv(shape, [1, -exp(-1/tau)])[0:L]     ("same" truncation)
+ *   coeffs  = fir * beta / L          (unit flat-top gain when beta = L, the value dsp_icpc passes,
+ *                                      src/dsp_icpc.jl:88,90 -- normalisation policy, parity unpinned)
+ */
+static void cuspzac_shape(double sigma, int flat, int L, int zac, double* c)
+{
+    int lt = (L - flat) / 2;
+    double norm = sinh(lt / sigma);
+    double* par = (double*)calloc((size_t)L, sizeof(double));
+    double acusp = 0, apar = 0;
+    for (int k = 0; k < L; ++k) {
+        if (k < lt) {
+            c[k] = sinh(k / sigma) / norm;
+            par[k] = (k - lt / 2.0) * (k - lt / 2.0) - (lt / 2.0) * (lt / 2.0);
+        } else if (k <= lt + flat) {
+            c[k] = 1.0;
+        } else {
+            c[k] = sinh((L - k) / sigma) / norm;
+            par[k] = (L - k - lt / 2.0) * (L - k - lt / 2.0) - (lt / 2.0) * (lt / 2.0);
+        }
+        acusp += c[k];
+        apar += par[k];
+    }
+    if (zac && apar != 0.0)
+        for (int k = 0; k < L; ++k) c[k] -= par[k] / apar * acusp;
+    free(par);
+}
+
+static int cuspzac_coeffs(double sigma, int flat, double tau, int L, double beta, int zac, double* out)
+{
+    if (L < 4 || L > LGDSP_MAX_FIR || flat < 0 || flat >= L - 2 || !(sigma > 0) || !(tau > 0)) return -1;
+    double* c = (double*)malloc(sizeof(double) * (size_t)L);
+    cuspzac_shape(sigma, flat, L, zac, c);
+    double r = exp(-1.0 / tau);
+    for (int k = 0; k < L; ++k) {
+        double v = c[k] - (k > 0 ? r * c[k - 1] : 0.0);
+        out[k] = v * (beta / L);
+    }
+    free(c);
+    return 0;
+}
+ORC_API int orc_cusp_coeffs(double sigma, int flat, double tau, int L, double beta, double* out)
+{ return cuspzac_coeffs(sigma, flat, tau, L, beta, 0, out); }
+ORC_API int orc_zac_coeffs(double sigma, int flat, double tau, int L, double beta, double* out)
+{ return cuspzac_coeffs(sigma, flat, tau, L, beta, 1, out); }
+
+/* ------------------------------------------------------------------------------------------------
+ * per-waveform primitives
+ * ------------------------------------------------------------------------------------------------ */
+
+/* _saturation_impl  src/saturation.jl:28-65  (transcribed; raw samples, integer equality) */
+ORC_API void orc_saturation(const uint16_t* Y, int n, int64_t low, int64_t high, int64_t out[4])
+{
+    int64_t n_low = 0, n_high = 0, n_cons_low = 0, n_cons_high = 0, c_low = 0, c_high = 0;
+    for (int i = 0; i < n; ++i) {
+        if ((int64_t)Y[i] == low) {
+            n_low += 1; c_low += 1;
+            if (c_high > n_cons_high) n_cons_high = c_high;
+            c_high = 0;
+        } else if ((int64_t)Y[i] == high) {
+            n_high += 1; c_high += 1;
+            if (c_low > n_cons_low) n_cons_low = c_low;
+            c_low = 0;
+        } else {
+            if (c_low > n_cons_low) n_cons_low = c_low;
+            c_low = 0;
+            if (c_high > n_cons_high) n_cons_high = c_high;
+            c_high = 0;
+        }
+    }
+    if (c_low > n_cons_low) n_cons_low = c_low;
+    if (c_high > n_cons_high) n_cons_high = c_high;
+    out[0] = n_low; out[1] = n_high; out[2] = n_cons_low; out[3] = n_cons_high;
+}
+
+/* signalstats [RDDSP _signalstats_impl]; LegendDSP's tailstats is its line-for-line adaptation
+ * (src/tailstats.jl:36-71 incl. the commented-out offset at :64).  X[i] = t0 + i*dt.
+ * out: mean, sigma, slope, offset */
+ORC_API void orc_signalstats(const double* Y, double t0, double dt, int from, int until, double out[4])
+{
+    double sum_X = 0, sum_Y = 0, sum_X_sqr = 0, sum_Y_sqr = 0, sum_XY = 0;
+    for (int i = from; i <= until; ++i) {
+        double x = t0 + i * dt, y = Y[i];
+        sum_X = x + sum_X;
+        sum_X_sqr = fma(x, x, sum_X_sqr);
+        sum_Y = y + sum_Y;
+        sum_Y_sqr = fma(y, y, sum_Y_sqr);
+        sum_XY = fma(x, y, sum_XY);
+    }
+    int n = until - from + 1;
+    double inv_n = 1.0 / n;
+    double mean_X = sum_X * inv_n;
+    double mean_Y = sum_Y * inv_n;
+    double var_X = sum_X_sqr * inv_n - mean_X * mean_X;
+    double var_Y = sum_Y_sqr * inv_n - mean_Y * mean_Y;
+    double cov_XY = sum_XY * inv_n - mean_X * mean_Y;
+    double slope = cov_XY / var_X;
+    double offset = mean_Y - slope * mean_X;
+    if (var_Y < 0) var_Y = 0;
+    out[0] = mean_Y; out[1] = sqrt(var_Y); out[2] = slope; out[3] = offset;
+}
+
+/* _tailstats_impl  src/tailstats.jl:22-72.  out: mean, sigma, tau */
+ORC_API void orc_tailstats(const double* Y, double t0, double dt, int from, int until, double out[3])
+{
+    for (int i = from; i <= until; ++i)
+        if (Y[i] <= 0) { out[0] = 0; out[1] = 0; out[2] = 0; return; } /* :27-33 */
+    double sum_X = 0, sum_Y = 0, sum_X_sqr = 0, sum_Y_sqr = 0, sum_XY = 0;
+    for (int i = from; i <= until; ++i) {
+        double x = t0 + i * dt, y = log(Y[i]);
+        sum_X = x + sum_X;
+        sum_X_sqr = fma(x, x, sum_X_sqr);
+        sum_Y = y + sum_Y;
+        sum_Y_sqr = fma(y, y, sum_Y_sqr);
+        sum_XY = fma(x, y, sum_XY);
+    }
+    int n = until - from + 1;
+    double inv_n = 1.0 / n;
+    double mean_X = sum_X * inv_n;
+    double mean_Y = sum_Y * inv_n;
+    double var_X = sum_X_sqr * inv_n - mean_X * mean_X;
+    double var_Y = sum_Y_sqr * inv_n - mean_Y * mean_Y;
+    double cov_XY = sum_XY * inv_n - mean_X * mean_Y;
+    double slope = cov_XY / var_X;
+    if (var_Y < 0) var_Y = 0;
+    out[0] = mean_Y; out[1] = sqrt(var_Y); out[2] = -1 / slope;
+}
+
+/* _extremestats_impl  src/extremestats.jl:25-40: findmin/findmax return the FIRST extremal index.
+ * out: min, max, tmin, tmax  (times = t0 + idx*dt) */
+ORC_API void orc_extremestats(const double* Y, double t0, double dt, int from, int until, double out[4])
+{
+    int imin = from, imax = from;
+    for (int i = from + 1; i <= until; ++i) {
+        if (Y[i] < Y[imin]) imin = i;
+        if (Y[i] > Y[imax]) imax = i;
+    }
+    out[0] = Y[imin]; out[1] = Y[imax]; out[2] = t0 + imin * dt; out[3] = t0 + imax * dt;
+}
+
+/* extrema3points  src/interpolation.jl:8-10 */
+static double extrema3points(double y1, double y2, double y3)
+{
+    double a = y3 - 4 * y2 + 3 * y1;
+    return y1 - a * a / (8 * (y3 - 2 * y2 + y1));
+}
+
+/* _get_wvf_maximum_impl  src/interpolation.jl:30-46: first argmax inside the window; parabola only if the
+ * argmax is strictly inside the WINDOW (1 < ind < length(window)) */
+ORC_API double orc_get_wvf_maximum(const double* Y, int from, int until)
+{
+    int len = until - from + 1;
+    int ind = 0; /* 0-based within window */
+    for (int i = 1; i < len; ++i)
+        if (Y[from + i] > Y[from + ind]) ind = i;
+    if (ind > 0 && ind < len - 1) return extrema3points(Y[from + ind - 1], Y[from + ind], Y[from + ind + 1]);
+    return Y[from + ind];
+}
+
+/* DerivativeFilter rdfilt!  src/derivative.jl:47-55:  y[i] = gain*(x[max(i,2)] - x[max(i-1,1)])  (1-based) */
+ORC_API void orc_derivative(const double* x, int n, double gain, double* y)
+{
+    for (int i = 0; i < n; ++i) {
+        int a = i > 1 ? i : 1, b = (i - 1) > 0 ? (i - 1) : 0;
+        y[i] = gain * (x[a] - x[b]);
+    }
+}
+
+/* InvCRFilter(tau) [RDDSP]: biquad b = (1/alpha, -1, 0), a = (1, -1, 0), alpha = RC/(RC+1), zero state.
+ * km1 = 1/alpha - 1 is passed in, so 1/alpha = 1 + km1. */
+ORC_API void orc_invcr(const double* x, int n, double km1, double* y)
+{
+    double k = 1.0 + km1, x1 = 0, y1 = 0;
+    for (int i = 0; i < n; ++i) {
+        double x0 = x[i];
+        double y0 = k * x0 - x1 + y1;
+        y[i] = y0; x1 = x0; y1 = y0;
+    }
+}
+
+/* IntegratorFilter(gain) [RDDSP]: y[i] = y[i-1] + gain*x[i]   (src/dsp_routines.jl:53) */
+ORC_API void orc_integrator(const double* x, int n, double gain, double* y)
+{
+    double acc = 0;
+    for (int i = 0; i < n; ++i) { acc = acc + gain * x[i]; y[i] = acc; }
+}
+
+/* TrapezoidalChargeFilter [RDDSP], running sums; returns output length n-L+1 (trace j <-> sample j+L-1) */
+ORC_API int orc_trap(const double* y, int n, int navg, int ngap, int navg2, double* out)
+{
+    int L = navg + ngap + navg2;
+    int n_out = n - L + 1;
+    if (n_out <= 0 || navg <= 0 || navg2 <= 0 || ngap < 0) return 0;
+    double s1 = 0, s2 = 0;
+    for (int i = 0; i < navg; ++i) s1 += y[i];
+    for (int i = navg + ngap; i < L; ++i) s2 += y[i];
+    double inv1 = 1.0 / navg, inv2 = 1.0 / navg2;
+    out[0] = s2 * inv2 - s1 * inv1;
+    for (int j = 1; j < n_out; ++j) {
+        s1 += y[j + navg - 1] - y[j - 1];
+        s2 += y[j + L - 1] - y[j + navg + ngap - 1];
+        out[j] = s2 * inv2 - s1 * inv1;
+    }
+    return n_out;
+}
+
+/* brute-force trapezoid (explicit window means) -- cross-check for orc_trap in the tests */
+ORC_API int orc_trap_bruteforce(const double* y, int n, int navg, int ngap, int navg2, double* out)
+{
+    int L = navg + ngap + navg2, n_out = n - L + 1;
+    for (int j = 0; j < n_out; ++j) {
+        double s1 = 0, s2 = 0;
+        for (int i = 0; i < navg; ++i) s1 += y[j + i];
+        for (int i = 0; i < navg2; ++i) s2 += y[j + navg + ngap + i];
+        out[j] = s2 / navg2 - s1 / navg;
+    }
+    return n_out;
+}
+
+/* valid-mode convolution [RDDSP ConvolutionFilter]: out[j] = sum_k c[k] y[j+L-1-k]; returns n-L+1 */
+ORC_API int orc_fir_valid(const double* y, int n, const double* c, int L, double* out)
+{
+    int n_out = n - L + 1;
+    for (int j = 0; j < n_out; ++j) {
+        double acc = 0;
+        const double* yy = y + j + L - 1;
+        for (int k = 0; k < L; ++k) acc += c[k] * yy[-k];
+        out[j] = acc;
+    }
+    return n_out > 0 ? n_out : 0;
+}
+
+/* valid-mode correlation for the SG kernels: out[j] = sum_k h[k] y[j+k] */
+ORC_API int orc_corr_valid(const double* y, int n, const double* h, int L, double* out)
+{
+    int n_out = n - L + 1;
+    for (int j = 0; j < n_out; ++j) {
+        double acc = 0;
+        for (int k = 0; k < L; ++k) acc += h[k] * y[j + k];
+        out[j] = acc;
+    }
+    return n_out > 0 ? n_out : 0;
+}
+
+/* Intersect(mintot)(wf, thr) [RDDSP _find_intersect_impl(X, Y, threshold, min_n)]; in-tree twins:
+ * src/intersect_maximum.jl:41-56,67-73 and src/multi_intersect.jl:53-72 (first-sample rule `>=` as :55).
+ * X[i] = t0 + i*dt.  Returns x (NaN if none); *mult = multiplicity; *pos_out = 0-based crossing index or -1. */
+ORC_API double orc_intersect(const double* Y, int n, double t0, double dt, double thr, int min_n, int64_t* mult,
+                             int* pos_out)
+{
+    if (n <= 0) { if (mult) *mult = 0; if (pos_out) *pos_out = -1; return NAN; }
+    int cand_pos = 1, intersect_pos = 1;
+    int64_t counter = (Y[0] >= thr) ? (int64_t)min_n + 1 : 0;
+    int64_t n_intersects = 0;
+    for (int i = 0; i < n; ++i) {
+        double y = Y[i];
+        int y_is_high = y >= thr;
+        int first_high_y = counter == 0;
+        if (y_is_high && first_high_y) cand_pos = i;
+        counter = y_is_high ? counter + 1 : 0;
+        int new_found = counter == min_n;
+        if (new_found && n_intersects == 0) intersect_pos = cand_pos;
+        if (new_found) n_intersects += 1;
+    }
+    if (mult) *mult = n_intersects;
+    if (n_intersects == 0 || n < 2) { if (pos_out) *pos_out = -1; return NAN; }
+    if (pos_out) *pos_out = intersect_pos;
+    double x_l = t0 + (intersect_pos - 1) * dt, x_r = t0 + intersect_pos * dt;
+    double y_l = Y[intersect_pos - 1], y_r = Y[intersect_pos];
+    return (thr - y_l) * (x_r - x_l) / (y_r - y_l) + x_l;
+}
+
+/* SignalEstimator(PolynomialDNI(deg, len))(wf, t) [RDDSP]; window placement policy documented in
+ * include/lgdsp_b200.h (lgdsp_dni): p = (t - t_first_trace)/dt clamped to [0, n-1],
+ * from = clamp(rint(p) - n_w/2, 0, n - n_w), evaluate the fitted polynomial at u = p - from. */
+ORC_API double orc_dni(const lgdsp_dni* d, const double* Y, int n, double p)
+{
+    int nw = d->n_w, m = d->degree + 1;
+    if (n < nw) return NAN;
+    if (!(p >= 0)) p = 0;
+    if (p > n - 1) p = n - 1;
+    long from = (long)rint(p) - nw / 2;
+    if (from < 0) from = 0;
+    if (from > n - nw) from = n - nw;
+    double u = p - (double)from;
+    double coef[LGDSP_MAX_DNI_DEG + 1] = {0};
+    for (int j = 0; j < m; ++j) {
+        double c = 0;
+        for (int i = 0; i < nw; ++i) c = fma(d->A[i * m + j], Y[from + i], c);
+        coef[j] = c;
+    }
+    double v = coef[m - 1];
+    for (int j = m - 2; j >= 0; --j) v = v * u + coef[j];
+    return v;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * composite routines  src/dsp_routines.jl
+ * ------------------------------------------------------------------------------------------------ */
+static double nan_to_zero(double v) { return isnan(v) ? 0.0 : v; }
+
+/* get_t0  src/dsp_routines.jl:9-25; returns microseconds, NaN -> 0 */
+static double orc_get_t0(const double* y, int n, double t_first, double dt, const lgdsp_trap* tr, double thr,
+                         int min_n, double* scratch, int* pos_out)
+{
+    int L = tr->navg + tr->ngap + tr->navg2;
+    int n_out = orc_trap(y, n, tr->navg, tr->ngap, tr->navg2, scratch);
+    int64_t mult;
+    double x = orc_intersect(scratch, n_out, t_first + (L - 1) * dt, dt, thr, min_n, &mult, pos_out);
+    return nan_to_zero(x * 0.001);
+}
+
+/* get_threshold  src/dsp_routines.jl:33-42 */
+static double orc_get_threshold(const double* y, int n, double t_first, double dt, double thr, int min_n, int* pos_out)
+{
+    int64_t mult;
+    double x = orc_intersect(y, n, t_first, dt, thr, min_n, &mult, pos_out);
+    return nan_to_zero(x * 0.001);
+}
+
+/* get_qdrift  src/dsp_routines.jl:51-64 (integrated trace passed in) */
+static double orc_get_qdrift(const double* I, int n, double t_first, double dt, const lgdsp_dni* dni, double t_start_us,
+                             double first_ns, double last_ns)
+{
+    double t_ns = t_start_us * 1000.0;
+    double a0 = orc_dni(dni, I, n, (t_ns - t_first) / dt);
+    double a1 = orc_dni(dni, I, n, (t_ns + first_ns - t_first) / dt);
+    double a2 = orc_dni(dni, I, n, (t_ns + last_ns - t_first) / dt);
+    double area1 = a1 - a0;
+    double area2 = a2 - a1;
+    return area2 - area1;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * dsp_icpc  src/dsp_icpc.jl:62-230, one event.  `idx` (optional, 16 ints) receives the integer sample
+ * indices underlying the time outputs (crossing positions, argmax positions), -1 when none.
+ * ------------------------------------------------------------------------------------------------ */
+enum { IDX_t0 = 0, IDX_t10, IDX_t50, IDX_t80, IDX_t90, IDX_t99, IDX_t50_current, IDX_t0_inv,
+       IDX_trap_max, IDX_cusp_max, IDX_zac_max, IDX_intrace, ORC_NIDX = 16 };
+
+static void dsp_icpc_one(const lgdsp_icpc_params* P, const uint16_t* raw, double* row, int32_t* idx, double* ws)
+{
+    const int n = P->n_samples;
+    const double t_first = P->t_first_ns, dt = P->dt_ns;
+    double* w = ws;             /* waveform (baseline-subtracted, then PZ, then inverted) */
+    double* flt = ws + n;       /* filtered trace */
+    double* flt2 = ws + 2 * n;  /* second scratch */
+    for (int i = 0; i < LGDSP_NCOL; ++i) row[i] = 0.0;
+    if (idx) for (int i = 0; i < ORC_NIDX; ++i) idx[i] = -1;
+    int pos;
+
+    /* :93-95 saturation on the raw samples */
+    int64_t sat[4];
+    orc_saturation(raw, n, P->sat_low, P->sat_high, sat);
+    row[LGDSP_COL_n_sat_low] = (double)sat[0];
+    row[LGDSP_COL_n_sat_high] = (double)sat[1];
+    row[LGDSP_COL_n_sat_low_cons] = (double)sat[2];
+    row[LGDSP_COL_n_sat_high_cons] = (double)sat[3];
+
+    /* :102 baseline stats on the raw waveform */
+    for (int i = 0; i < n; ++i) w[i] = (double)raw[i];
+    double bl[4];
+    orc_signalstats(w, t_first, dt, P->bl_from, P->bl_until, bl);
+    row[LGDSP_COL_blmean] = bl[0]; row[LGDSP_COL_blsigma] = bl[1];
+    row[LGDSP_COL_blslope] = bl[2]; row[LGDSP_COL_bloffset] = bl[3];
+
+    /* :105 shift_waveform.(wvfs, -bl.mean) */
+    double shift = -bl[0];
+    for (int i = 0; i < n; ++i) w[i] = w[i] + shift;
+
+    /* :108 */
+    row[LGDSP_COL_qc_label] = -1.0;
+
+    /* :111-112 */
+    double wmax = w[0], wmin = w[0];
+    for (int i = 1; i < n; ++i) { if (w[i] > wmax) wmax = w[i]; if (w[i] < wmin) wmin = w[i]; }
+    row[LGDSP_COL_e_max] = wmax; row[LGDSP_COL_e_min] = wmin;
+
+    /* :115 tailstats (pre-PZ) */
+    double ts[3];
+    orc_tailstats(w, t_first, dt, P->tail_from, P->tail_until, ts);
+    row[LGDSP_COL_tail_mean] = ts[0]; row[LGDSP_COL_tail_sigma] = ts[1]; row[LGDSP_COL_tail_tau] = ts[2];
+
+    /* :119-120 pole-zero */
+    orc_invcr(w, n, P->pz_km1, flt);
+    memcpy(w, flt, sizeof(double) * (size_t)n);
+
+    /* :123 */
+    double pz[4];
+    orc_signalstats(w, t_first, dt, P->tail_from, P->tail_until, pz);
+    row[LGDSP_COL_tailmean] = pz[0]; row[LGDSP_COL_tailsigma] = pz[1];
+    row[LGDSP_COL_tailslope] = pz[2]; row[LGDSP_COL_tailoffset] = pz[3];
+
+    /* :126 t0 */
+    double t0 = orc_get_t0(w, n, t_first, dt, &P->t0_trap, P->t0_threshold, P->t0_min_n, flt, &pos);
+    row[LGDSP_COL_t0] = t0; if (idx) idx[IDX_t0] = pos;
+
+    /* :132-136 */
+    double tx[5];
+    for (int k = 0; k < 5; ++k) {
+        tx[k] = orc_get_threshold(w, n, t_first, dt, wmax * P->tx_frac[k], P->tx_min_n, &pos);
+        if (idx) idx[IDX_t10 + k] = pos;
+    }
+    row[LGDSP_COL_t10] = tx[0]; row[LGDSP_COL_t50] = tx[1]; row[LGDSP_COL_t80] = tx[2];
+    row[LGDSP_COL_t90] = tx[3]; row[LGDSP_COL_t99] = tx[4];
+    double t50 = tx[1], t80 = tx[2], t90 = tx[3];
+
+    /* :138 */
+    row[LGDSP_COL_drift_time] = (t90 - t0) * 1000.0;
+
+    /* :141,144 (the integrator is recomputed in both calls in the reference; same result) */
+    orc_integrator(w, n, 1.0, flt);
+    row[LGDSP_COL_qdrift] = orc_get_qdrift(flt, n, t_first, dt, &P->int_dni, t0, P->qdrift_first_ns, P->qdrift_last_ns);
+    orc_integrator(w, n, 1.0, flt);
+    row[LGDSP_COL_lq] = orc_get_qdrift(flt, n, t_first, dt, &P->int_dni, t80, P->lq_first_ns, P->lq_last_ns);
+
+    /* :147-154 */
+    const lgdsp_trap* fixed[3] = { &P->trap_10410, &P->trap_535, &P->trap_313 };
+    const int fixed_col[3] = { LGDSP_COL_e_10410, LGDSP_COL_e_535, LGDSP_COL_e_313 };
+    for (int f = 0; f < 3; ++f) {
+        int no = orc_trap(w, n, fixed[f]->navg, fixed[f]->ngap, fixed[f]->navg2, flt);
+        double m = flt[0];
+        for (int j = 1; j < no; ++j) if (flt[j] > m) m = flt[j];
+        row[fixed_col[f]] = m;
+    }
+
+    /* :160-164 trap(rt, ft) */
+    {
+        const lgdsp_trap* tr = &P->trap_e;
+        int L = tr->navg + tr->ngap + tr->navg2;
+        int no = orc_trap(w, n, tr->navg, tr->ngap, tr->navg2, flt);
+        double tf = t_first + (L - 1) * dt;
+        row[LGDSP_COL_e_trap] = orc_dni(&P->sig_dni, flt, no, (t50 * 1000.0 + P->trap_pickoff_ns - tf) / dt);
+        double es[4];
+        orc_extremestats(flt, tf, dt, 0, no - 1, es);
+        row[LGDSP_COL_e_trap_max] = es[1]; row[LGDSP_COL_t_trap_max] = es[3];
+        if (idx) idx[IDX_trap_max] = (int)lrint((es[3] - tf) / dt);
+    }
+    /* :167-171 cusp */
+    {
+        int L = P->cusp.n_taps;
+        int no = orc_fir_valid(w, n, P->cusp.coeffs, L, flt);
+        double tf = t_first + (L - 1) * dt;
+        row[LGDSP_COL_e_cusp] = orc_dni(&P->sig_dni, flt, no, (t50 * 1000.0 + P->cusp_pickoff_ns - tf) / dt);
+        double es[4];
+        orc_extremestats(flt, tf, dt, 0, no - 1, es);
+        row[LGDSP_COL_e_cusp_max] = es[1]; row[LGDSP_COL_t_cusp_max] = es[3];
+        if (idx) idx[IDX_cusp_max] = (int)lrint((es[3] - tf) / dt);
+    }
+    /* :174-178 zac (the reference applies the filter twice, :175 and :177; identical results) */
+    {
+        int L = P->zac.n_taps;
+        int no = orc_fir_valid(w, n, P->zac.coeffs, L, flt);
+        double tf = t_first + (L - 1) * dt;
+        row[LGDSP_COL_e_zac] = orc_dni(&P->sig_dni, flt, no, (t50 * 1000.0 + P->zac_pickoff_ns - tf) / dt);
+        double es[4];
+        orc_extremestats(flt, tf, dt, 0, no - 1, es);
+        row[LGDSP_COL_e_zac_max] = es[1]; row[LGDSP_COL_t_zac_max] = es[3];
+        if (idx) idx[IDX_zac_max] = (int)lrint((es[3] - tf) / dt);
+    }
+
+    /* :181-186 currents.  flt2 keeps the sg_wl derivative trace for :189-195 */
+    int n_sg0 = orc_corr_valid(w, n, P->sg[0].h, P->sg[0].n_taps, flt2);
+    row[LGDSP_COL_a_sg] = orc_get_wvf_maximum(flt2, P->cur_from[0], P->cur_until[0]);
+    orc_corr_valid(w, n, P->sg[1].h, P->sg[1].n_taps, flt);
+    row[LGDSP_COL_a_60] = orc_get_wvf_maximum(flt, P->cur_from[1], P->cur_until[1]);
+    orc_corr_valid(w, n, P->sg[2].h, P->sg[2].n_taps, flt);
+    row[LGDSP_COL_a_100] = orc_get_wvf_maximum(flt, P->cur_from[2], P->cur_until[2]);
+    orc_derivative(w, n, 1.0, flt);
+    row[LGDSP_COL_a_raw] = orc_get_wvf_maximum(flt, P->cur_from[3], P->cur_until[3]);
+
+    /* :189 get_intracePileUp  src/dsp_routines.jl:72-82 */
+    {
+        double tf = t_first + P->sg[0].offset * dt;
+        double st[4];
+        orc_signalstats(flt2, tf, dt, P->intrace_bl_from, P->intrace_bl_until, st);
+        double thres = st[1] * P->intrace_nsigma;
+        if (thres == 0.0) thres = 1.0;                      /* :77 */
+        for (int j = 0; j < n_sg0; ++j) flt[j] = flt2[n_sg0 - 1 - j]; /* reverse_waveform, same time axis */
+        int64_t mult;
+        double x = orc_intersect(flt, n_sg0, tf, dt, thres, P->intrace_min_n, &mult, &pos);
+        double last_t = tf + (n_sg0 - 1) * dt;
+        row[LGDSP_COL_inTrace_intersect] = last_t - x;       /* NaN propagates, :81 */
+        row[LGDSP_COL_inTrace_n] = (double)mult;
+        if (idx) idx[IDX_intrace] = pos;
+    }
+    /* :192-195 */
+    {
+        double tf = t_first + P->sg[0].offset * dt;
+        double m = flt2[0];
+        for (int j = 1; j < n_sg0; ++j) if (flt2[j] > m) m = flt2[j];
+        row[LGDSP_COL_t50_current] = orc_get_threshold(flt2, n_sg0, tf, dt, m * 0.5, P->tx_min_n, &pos);
+        if (idx) idx[IDX_t50_current] = pos;
+    }
+
+    /* :199 invert */
+    for (int i = 0; i < n; ++i) w[i] = w[i] * -1.0;
+    /* :202-204 */
+    {
+        int no = orc_trap(w, n, P->trap_10410.navg, P->trap_10410.ngap, P->trap_10410.navg2, flt);
+        double m = flt[0];
+        for (int j = 1; j < no; ++j) if (flt[j] > m) m = flt[j];
+        row[LGDSP_COL_e_10410_inv] = m;
+        no = orc_trap(w, n, P->trap_313.navg, P->trap_313.ngap, P->trap_313.navg2, flt);
+        m = flt[0];
+        for (int j = 1; j < no; ++j) if (flt[j] > m) m = flt[j];
+        row[LGDSP_COL_e_313_inv] = m;
+    }
+    /* :207 */
+    row[LGDSP_COL_t0_inv] = orc_get_t0(w, n, t_first, dt, &P->t0inv_trap, P->t0_threshold, P->t0_min_n, flt, &pos);
+    if (idx) idx[IDX_t0_inv] = pos;
+}
+
+/* batch driver: OpenMP over events (events are independent).  idx may be NULL.
+ * n_threads <= 0: all available.  Returns the number of threads used. */
+ORC_API int orc_dsp_icpc(const lgdsp_icpc_params* P, const uint16_t* wf, int64_t n_events, int64_t ld,
+                         double* out_rows, int32_t* idx, int n_threads)
+{
+    int used = 1;
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+    used = n_threads;
+#pragma omp parallel num_threads(n_threads)
+#endif
+    {
+        double* ws = (double*)malloc(sizeof(double) * 3 * (size_t)P->n_samples);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+        for (int64_t e = 0; e < n_events; ++e)
+            dsp_icpc_one(P, wf + e * ld, out_rows + e * LGDSP_NCOL, idx ? idx + e * ORC_NIDX : NULL, ws);
+        free(ws);
+    }
+    return used;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * trapezoid sweeps  src/dsp_filter_optimization.jl:102-133 (rt, fixed pick-off) and :241-274 (ft, t50-based)
+ * out: float[n_events][n_variants] (= column-major Julia matrix n_variants x n_events)
+ * ------------------------------------------------------------------------------------------------ */
+ORC_API int orc_trap_sweep(const lgdsp_sweep_params* P, const uint16_t* wf, int64_t n_events, int64_t ld,
+                           const lgdsp_trap_variant* var, int n_var, float* out, int n_threads)
+{
+    int used = 1;
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+    used = n_threads;
+#pragma omp parallel num_threads(n_threads)
+#endif
+    {
+        const int n = P->n_samples;
+        double* w = (double*)malloc(sizeof(double) * 2 * (size_t)n);
+        double* flt = w + n;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+        for (int64_t e = 0; e < n_events; ++e) {
+            const uint16_t* raw = wf + e * ld;
+            for (int i = 0; i < n; ++i) w[i] = (double)raw[i];
+            double bl[4];
+            orc_signalstats(w, P->t_first_ns, P->dt_ns, P->bl_from, P->bl_until, bl);      /* :247 */
+            double shift = -bl[0];
+            for (int i = 0; i < n; ++i) w[i] = w[i] + shift;                                /* :250 */
+            orc_invcr(w, n, P->pz_km1, flt);                                                /* :253-254 */
+            memcpy(w, flt, sizeof(double) * (size_t)n);
+            double wmax = w[0];
+            for (int i = 1; i < n; ++i) if (w[i] > wmax) wmax = w[i];
+            int pos;
+            double t50 = orc_get_threshold(w, n, P->t_first_ns, P->dt_ns, wmax * 0.5, P->tx_min_n, &pos); /* :260 */
+            for (int v = 0; v < n_var; ++v) {
+                const lgdsp_trap* tr = &var[v].trap;
+                int L = tr->navg + tr->ngap + tr->navg2;
+                int no = orc_trap(w, n, tr->navg, tr->ngap, tr->navg2, flt);
+                double tf = P->t_first_ns + (L - 1) * P->dt_ns;
+                double t_ns = var[v].pickoff_mode ? t50 * 1000.0 + var[v].pickoff_ns : var[v].pickoff_ns;
+                double val = no > 0 ? orc_dni(&P->sig_dni, flt, no, (t_ns - tf) / P->dt_ns) : NAN;
+                out[e * (int64_t)n_var + v] = (float)val;
+            }
+        }
+        free(w);
+    }
+    return used;
+}
+
+ORC_API int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

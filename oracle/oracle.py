@@ -1,0 +1,225 @@
+"""ctypes wrapper around oracle/liblgdsp_oracle.so -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this module.
+PARITY STATUS: "parity unpinned" for the RadiationDetectorDSP.jl parts (see lgdsp_oracle.c header).
+"""
+import ctypes as C
+import importlib
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liblgdsp_oracle.so")
+
+_abi = importlib.import_module("legenddsp.jl_b200._abi")
+
+ORC_NIDX = 16
+IDX_NAMES = ("t0", "t10", "t50", "t80", "t90", "t99", "t50_current", "t0_inv", "trap_max", "cusp_max",
+             "zac_max", "intrace")
+
+_dp = C.POINTER(C.c_double)
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "lgdsp_oracle.c")
+    hdr = os.path.join(_HERE, "..", "include", "lgdsp_b200.h")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.orc_lsq_fit_matrix.argtypes = [C.c_int, C.c_int, _dp]
+        L.orc_sg_coeffs.argtypes = [C.c_int, C.c_int, C.c_int, _dp]
+        L.orc_cusp_coeffs.argtypes = [C.c_double, C.c_int, C.c_double, C.c_int, C.c_double, _dp]
+        L.orc_zac_coeffs.argtypes = [C.c_double, C.c_int, C.c_double, C.c_int, C.c_double, _dp]
+        L.orc_saturation.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
+        L.orc_saturation.restype = None
+        for name in ("orc_signalstats", "orc_tailstats", "orc_extremestats"):
+            f = getattr(L, name)
+            f.argtypes = [_dp, C.c_double, C.c_double, C.c_int, C.c_int, _dp]
+            f.restype = None
+        L.orc_get_wvf_maximum.argtypes = [_dp, C.c_int, C.c_int]
+        L.orc_get_wvf_maximum.restype = C.c_double
+        L.orc_derivative.argtypes = [_dp, C.c_int, C.c_double, _dp]
+        L.orc_derivative.restype = None
+        L.orc_invcr.argtypes = [_dp, C.c_int, C.c_double, _dp]
+        L.orc_invcr.restype = None
+        L.orc_integrator.argtypes = [_dp, C.c_int, C.c_double, _dp]
+        L.orc_integrator.restype = None
+        L.orc_trap.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+        L.orc_trap_bruteforce.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+        L.orc_fir_valid.argtypes = [_dp, C.c_int, _dp, C.c_int, _dp]
+        L.orc_corr_valid.argtypes = [_dp, C.c_int, _dp, C.c_int, _dp]
+        L.orc_intersect.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.orc_intersect.restype = C.c_double
+        L.orc_dni.argtypes = [C.POINTER(_abi.Dni), _dp, C.c_int, C.c_double]
+        L.orc_dni.restype = C.c_double
+        L.orc_dsp_icpc.argtypes = [C.POINTER(_abi.IcpcParams), C.c_void_p, C.c_int64, C.c_int64, _dp,
+                                   C.POINTER(C.c_int32), C.c_int]
+        L.orc_trap_sweep.argtypes = [C.POINTER(_abi.SweepParams), C.c_void_p, C.c_int64, C.c_int64,
+                                     C.POINTER(_abi.TrapVariant), C.c_int, C.POINTER(C.c_float), C.c_int]
+        L.orc_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+class OracleBuilders:
+    """the oracle's own (independent) filter-coefficient construction, same interface as config.LibBuilders"""
+
+    def lsq_fit_matrix(self, n, degree):
+        A = np.zeros((n, degree + 1))
+        if lib().orc_lsq_fit_matrix(n, degree, A.ctypes.data_as(_dp)) != 0:
+            raise ValueError("orc_lsq_fit_matrix failed")
+        return A
+
+    def sg_coeffs(self, n_taps, degree, derivative):
+        h = np.zeros(n_taps)
+        if lib().orc_sg_coeffs(n_taps, degree, derivative, h.ctypes.data_as(_dp)) != 0:
+            raise ValueError("orc_sg_coeffs failed")
+        return h
+
+    def cusp_coeffs(self, sigma, flat, tau, L, beta):
+        c = np.zeros(L)
+        if lib().orc_cusp_coeffs(sigma, flat, tau, L, beta, c.ctypes.data_as(_dp)) != 0:
+            raise ValueError("orc_cusp_coeffs failed")
+        return c
+
+    def zac_coeffs(self, sigma, flat, tau, L, beta):
+        c = np.zeros(L)
+        if lib().orc_zac_coeffs(sigma, flat, tau, L, beta, c.ctypes.data_as(_dp)) != 0:
+            raise ValueError("orc_zac_coeffs failed")
+        return c
+
+
+def saturation(y_u16, low, high):
+    y = np.ascontiguousarray(y_u16, dtype=np.uint16)
+    out = (C.c_int64 * 4)()
+    lib().orc_saturation(y.ctypes.data, y.size, int(low), int(high), out)
+    return dict(low=out[0], high=out[1], max_cons_low=out[2], max_cons_high=out[3])
+
+
+def _stats(fn, y, t0, dt, frm, until, n):
+    y, p = _d(y)
+    out = np.zeros(n)
+    getattr(lib(), fn)(p, float(t0), float(dt), int(frm), int(until), out.ctypes.data_as(_dp))
+    return out
+
+
+def signalstats(y, t0, dt, frm, until):
+    o = _stats("orc_signalstats", y, t0, dt, frm, until, 4)
+    return dict(mean=o[0], sigma=o[1], slope=o[2], offset=o[3])
+
+
+def tailstats(y, t0, dt, frm, until):
+    o = _stats("orc_tailstats", y, t0, dt, frm, until, 3)
+    return dict(mean=o[0], sigma=o[1], tau=o[2])
+
+
+def extremestats(y, t0, dt, frm, until):
+    o = _stats("orc_extremestats", y, t0, dt, frm, until, 4)
+    return dict(min=o[0], max=o[1], tmin=o[2], tmax=o[3])
+
+
+def get_wvf_maximum(y, frm, until):
+    y, p = _d(y)
+    return lib().orc_get_wvf_maximum(p, int(frm), int(until))
+
+
+def derivative(x, gain=1.0):
+    x, p = _d(x)
+    out = np.zeros_like(x)
+    lib().orc_derivative(p, x.size, float(gain), out.ctypes.data_as(_dp))
+    return out
+
+
+def invcr(x, km1):
+    x, p = _d(x)
+    out = np.zeros_like(x)
+    lib().orc_invcr(p, x.size, float(km1), out.ctypes.data_as(_dp))
+    return out
+
+
+def integrator(x, gain=1.0):
+    x, p = _d(x)
+    out = np.zeros_like(x)
+    lib().orc_integrator(p, x.size, float(gain), out.ctypes.data_as(_dp))
+    return out
+
+
+def trap(y, navg, ngap, navg2, bruteforce=False):
+    y, p = _d(y)
+    out = np.zeros(max(y.size, 1))
+    fn = lib().orc_trap_bruteforce if bruteforce else lib().orc_trap
+    n = fn(p, y.size, navg, ngap, navg2, out.ctypes.data_as(_dp))
+    return out[:n].copy()
+
+
+def fir_valid(y, c):
+    y, p = _d(y)
+    c, pc = _d(c)
+    out = np.zeros(max(y.size, 1))
+    n = lib().orc_fir_valid(p, y.size, pc, c.size, out.ctypes.data_as(_dp))
+    return out[:n].copy()
+
+
+def corr_valid(y, h):
+    y, p = _d(y)
+    h, ph = _d(h)
+    out = np.zeros(max(y.size, 1))
+    n = lib().orc_corr_valid(p, y.size, ph, h.size, out.ctypes.data_as(_dp))
+    return out[:n].copy()
+
+
+def intersect(y, t0, dt, thr, min_n):
+    y, p = _d(y)
+    mult = C.c_int64(0)
+    pos = C.c_int(-1)
+    x = lib().orc_intersect(p, y.size, float(t0), float(dt), float(thr), int(min_n), C.byref(mult), C.byref(pos))
+    return dict(x=x, multiplicity=mult.value, pos=pos.value)
+
+
+def dni(dni_struct, y, p_frac):
+    y, p = _d(y)
+    return lib().orc_dni(C.byref(dni_struct), p, y.size, float(p_frac))
+
+
+def dsp_icpc(params, wf_u16, n_threads=0, want_idx=False):
+    """rows[n_events, NCOL] (and idx[n_events, 16]) of the oracle chain on wf_u16[n_events, ld]"""
+    wf = np.ascontiguousarray(wf_u16, dtype=np.uint16)
+    assert wf.ndim == 2 and wf.shape[1] >= params.n_samples
+    n_ev, ld = wf.shape
+    rows = np.zeros((n_ev, _abi.NCOL))
+    idx = np.full((n_ev, ORC_NIDX), -1, dtype=np.int32) if want_idx else None
+    used = lib().orc_dsp_icpc(C.byref(params), wf.ctypes.data, n_ev, ld, rows.ctypes.data_as(_dp),
+                              idx.ctypes.data_as(C.POINTER(C.c_int32)) if want_idx else None, int(n_threads))
+    return (rows, idx, used) if want_idx else (rows, used)
+
+
+def trap_sweep(sparams, wf_u16, variants, n_threads=0):
+    wf = np.ascontiguousarray(wf_u16, dtype=np.uint16)
+    n_ev, ld = wf.shape
+    nv = len(variants)
+    out = np.zeros((n_ev, nv), dtype=np.float32)  # [event][variant] = Julia (n_variants x n_events) column-major
+    lib().orc_trap_sweep(C.byref(sparams), wf.ctypes.data, n_ev, ld, variants, nv,
+                         out.ctypes.data_as(C.POINTER(C.c_float)), int(n_threads))
+    return out
+
+
+def num_threads():
+    return lib().orc_num_threads()
