@@ -171,6 +171,74 @@ static bool make_trap(const lgdsp_trap& t, int n, int min_out, TrapDev& d)
     return d.nout >= min_out;
 }
 
+
+// analytic descriptor of a CUSP/ZAC filter for the structured device evaluation (lgdsp_icpc.cu)
+static bool make_czdev(const lgdsp_cuspzac& z, const double* cusp_coeffs, const double* zac_coeffs, CzDev& D, std::string& why)
+{
+    typedef long double ld;
+    const int L = z.n_taps, F = z.flat;
+    const int lt = (L - F) / 2, Rn = L - lt - F - 1;
+    if (lt < 2 || Rn < 1 || !(z.sigma > 0) || !(z.tau > 0)) { why = "flank too short for the structured evaluation"; return false; }
+    const ld sg = z.sigma, x = (ld)lt / sg;
+    if (x > 700.0L) { why = "lt/sigma too large"; return false; }
+    const ld a = 1.0L / sinhl(x), cA = 0.5L * a, h = lt / 2.0L;
+    const ld r = expl(-1.0L / (ld)z.tau), rho = expl(-1.0L / sg);
+    memset(&D, 0, sizeof(D));
+    D.L = L; D.F = F; D.lt = lt; D.Rn = Rn;
+    auto mod = [](int v) { return ((v % CZ_CH) + CZ_CH) % CZ_CH; };
+    D.oc[0] = 0; D.oc[1] = mod(-lt); D.oc[2] = mod(-lt - F - 1); D.oc[3] = mod(-L);
+    D.oa[0] = mod(1 - lt); D.oa[1] = mod(1); D.oa[2] = mod(1 - L); D.oa[3] = mod(-lt - F);
+    D.r = (double)r; D.rho = (double)rho; D.rho_inv = (double)(1.0L / rho); D.inv_sigma = (double)(1.0L / sg);
+    D.cA = (double)cA;
+    D.cA_rho_lt = (double)(cA * expl(-(ld)lt / sg));
+    D.cA_rhoinv_lt = (double)(cA * expl((ld)lt / sg));
+    D.cA_rhoinv_Rn = (double)(cA * expl((ld)Rn / sg));
+    D.cA_rho_Rn = (double)(cA * expl(-(ld)Rn / sg));
+    D.rho_lt = (double)expl(-(ld)lt / sg);
+    D.rho_Rn = (double)expl(-(ld)Rn / sg);
+    D.cA_rhoinv_ltm1 = (double)(cA * expl((ld)(lt - 1) / sg));
+    D.cA_rho = (double)(cA * rho);
+    for (int q = 0; q < 4; ++q) {
+        D.pw_c[q] = (double)expl(-(ld)(D.oc[q] + 1) / sg);
+        D.pw_a[q] = (double)expl(-(ld)(CZ_CH - D.oa[q]) / sg);
+    }
+    for (int s2 = 0; s2 < 5; ++s2) D.rho_ch_pow[s2] = (double)expl(-(ld)(CZ_CH << s2) / sg);
+    for (int l = 0; l < 32; ++l) D.rho_lane[l] = (double)expl(-(ld)(CZ_CH * (l + 1)) / sg);
+    D.rho_warp = (double)expl(-(ld)(CZ_CH * 32) / sg);
+    D.h2 = (double)(2.0L * h);
+    D.lt_d = lt; D.lt2_d = (double)lt * lt; D.Rn_d = Rn; D.Rn2_d = (double)Rn * Rn;
+    // shape sums -> parabola amplitude of the ZAC
+    ld acusp = 0, apar = 0;
+    auto cusp_at = [&](int k) -> ld { return k < lt ? sinhl(k / sg) * a : (k <= lt + F ? 1.0L : sinhl((L - k) / sg) * a); };
+    auto par_at = [&](int k) -> ld { return k < lt ? (k - h) * (k - h) - h * h : (k <= lt + F ? 0.0L : (L - k - h) * (L - k - h) - h * h); };
+    for (int k = 0; k < L; ++k) { acusp += cusp_at(k); apar += par_at(k); }
+    const ld B = apar != 0.0L ? -(acusp / apar) : 0.0L;
+    D.B = (double)B;
+    const ld g = (ld)z.beta / L;
+    D.g = (double)g;
+    D.gclast_cusp = (double)(g * r * cusp_at(L - 1));
+    D.gclast_zac = (double)(g * r * (cusp_at(L - 1) + B * par_at(L - 1)));
+    // the coefficient arrays passed through the ABI must be the ones this structure reproduces
+    const int probe[6] = {1, lt - 1, lt, lt + F, lt + F + 1, L - 1};
+    for (int which = 0; which < 2; ++which) {
+        const double* co = which ? zac_coeffs : cusp_coeffs;
+        if (!co) continue;
+        double scale = 0;
+        for (int k = 0; k < L; ++k) scale = fmax(scale, fabs(co[k]));
+        for (int pi = 0; pi < 6; ++pi) {
+            const int k = probe[pi];
+            const ld bb = which ? B : 0.0L;
+            const ld ck = cusp_at(k) + bb * par_at(k), ckm = cusp_at(k - 1) + bb * par_at(k - 1);
+            const double expect = (double)(g * (ck - r * ckm));
+            if (fabs(expect - co[k]) > 1e-9 * scale) {
+                why = which ? "zac.coeffs do not match (sigma, flat, tau, n_taps, beta)" : "cusp.coeffs do not match (sigma, flat, tau, n_taps, beta)";
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
 static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
 {
     if (!p) return fail(h, LGDSP_ERR_INVALID_ARG, "params is NULL");
@@ -247,6 +315,19 @@ static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
         CK(cudaStreamSynchronize(h->stream));
     }
     D.cusp_L = p->cusp.n_taps; D.zac_L = p->zac.n_taps;
+    if (!D.direct && (D.groups & LGDSP_GROUP_CUSPZAC)) {
+        const lgdsp_cuspzac &c = p->cusp, &z = p->zac;
+        D.cz_shared = (c.n_taps == z.n_taps && c.flat == z.flat && c.sigma == z.sigma && c.tau == z.tau && c.beta == z.beta) ? 1 : 0;
+        std::string why;
+        bool ok;
+        if (D.cz_shared) {
+            ok = make_czdev(c, c.coeffs, z.coeffs, D.cz[0], why);
+            D.cz[1] = D.cz[0];
+        } else {
+            ok = make_czdev(c, c.coeffs, nullptr, D.cz[0], why) && make_czdev(z, nullptr, z.coeffs, D.cz[1], why);
+        }
+        if (!ok) return fail(h, LGDSP_ERR_UNSUPPORTED, "CUSP/ZAC structured evaluation: %s (set cuspzac_direct = 1)", why.c_str());
+    }
     std::vector<double> A(2 * LGDSP_MAX_DNI * 4, 0.0);
     memcpy(A.data(), p->int_dni.A, sizeof(double) * LGDSP_MAX_DNI * 4);
     memcpy(A.data() + LGDSP_MAX_DNI * 4, p->sig_dni.A, sizeof(double) * LGDSP_MAX_DNI * 4);

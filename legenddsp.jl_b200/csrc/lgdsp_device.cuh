@@ -23,6 +23,23 @@ struct DniDev {
     int n_w, m;  // window, degree+1
 };
 
+// Structured evaluation of a CUSP/ZAC filter (see lgdsp_icpc.cu, "CUSP/ZAC through their analytic structure").
+// One descriptor = one (sigma, flat, tau, L); it can emit the CUSP output (B = 0) and/or the ZAC output.
+constexpr int CZ_CH = 32;  // samples per thread chunk
+struct CzDev {
+    int L, F, lt, Rn;
+    int oc[4], oa[4];          // in-chunk offsets of the decimated prefix-table positions
+    double r, rho, rho_inv, inv_sigma;
+    double cA, cA_rho_lt, cA_rhoinv_lt, cA_rhoinv_Rn, cA_rho_Rn;   // recurrence input gains (cA = a/2)
+    double rho_lt, rho_Rn, cA_rhoinv_ltm1, cA_rho;                 // closed-form initial states
+    double pw_c[4], pw_a[4];   // rho^(oc+1), rho^(CH-oa): carry multipliers of the decayed prefixes
+    double rho_ch_pow[5];      // rho^(CH*2^s)
+    double rho_lane[32];       // rho^(CH*(lane+1))
+    double rho_warp;           // rho^(CH*32)
+    double h2, B, lt_d, lt2_d, Rn_d, Rn2_d;
+    double g, gclast_cusp, gclast_zac;  // output gain, g*r*c[L-1] of the cusp / zac shape
+};
+
 // kernel-argument block of the fused dsp_icpc kernel (lives in the constant bank, ~2 KB)
 struct IcpcDev {
     int n;
@@ -43,6 +60,8 @@ struct IcpcDev {
     double nsigma;
     int intr_min_n, intr_from, intr_until, pad0;
     int cusp_L, zac_L;
+    int cz_shared, pad1;   // 1: cusp and zac share (sigma, flat, tau, L) -> one structured pass emits both
+    CzDev cz[2];           // [0]: cusp (or shared), [1]: zac
     // global-memory tables (owned by the handle):
     const double* dni_A;    // [2][LGDSP_MAX_DNI*4]: int_dni, sig_dni fit matrices
     const double* cusp_g;   // differenced CUSP taps on TT, cusp_L+1 values

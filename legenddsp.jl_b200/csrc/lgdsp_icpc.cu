@@ -37,8 +37,9 @@ constexpr int SM_MASK = SM_TT + TT_LEN * 8;                // uint32 masks[NMASK
 constexpr int SM_RED = SM_MASK + NMASK * NWORDS * 4;       // double red[NWARP][24]
 constexpr int RED_W = 24;
 constexpr int SM_STASH = SM_RED + NWARP * RED_W * 8;       // double stash[3][LGDSP_MAX_DNI]
-constexpr int SM_DNI = SM_STASH + 3 * LGDSP_MAX_DNI * 8;   // double dniA[2][LGDSP_MAX_DNI*4]
-constexpr int SM_ROW = SM_DNI + 2 * LGDSP_MAX_DNI * 4 * 8; // double row[64]
+constexpr int SM_TAB = SM_STASH + 3 * LGDSP_MAX_DNI * 8;   // double tabB[8][256]: CUSP/ZAC prefix tables 8..15
+                                                           // (tables 0..7 alias xs, which is idle in pass 3)
+constexpr int SM_ROW = SM_TAB + 8 * NT * 8;                // double row[64]
 constexpr int SM_IBUF = SM_ROW + 64 * 8;                   // int ibuf[64]
 constexpr int SM_BAR = SM_IBUF + 64 * 4;                   // uint64 mbarrier
 constexpr int SM_TOTAL = SM_BAR + 16;
@@ -297,6 +298,229 @@ __device__ __forceinline__ void dni_window(int n_w, int n_trace, double p, doubl
     from = (int)f;
 }
 
+
+// ==================================================================================================
+// CUSP/ZAC through their analytic structure (replaces two 2375-tap FIRs = 27.6 M MAC per waveform by O(n) work).
+//
+//   coeffs[k] = g*(c[k] - r*c[k-1])  =>  out[j] = g*( sum_k c[k]*d[m-k] + r*c[L-1]*y[m-L] ),  m = j+L-1,
+//   d[i] = y[i] - r*y[i-1]  (the "current"),   c = sinh flank | flat top | mirrored sinh flank (+ parabolas for ZAC).
+//
+// Every piece of c is an exponential or a polynomial in k, so sum_k c[k]*d[m-k] splits into sliding windows
+//   E-(m) = sum rho^k d, E+(m) = sum rho^-k d, W0/W1/W2 = sum {1,k,k^2} d      (rho = exp(-1/sigma))
+// over the left flank, the flat top and the right flank.  Each window obeys a 1-step linear recurrence in m.
+// Thread t owns outputs m in [32t, 32t+32): it gets the window states at m = 32t in closed form from
+// block-wide prefix scans of d (decayed prefix P-, anti-causal decayed prefix P+, moments D1 = sum i*d,
+// D2 = sum i^2*d; D0 = sum d comes from TT directly), which are only ever needed at 4 positions per chunk
+// (fixed in-chunk offsets) -> 16 tables x 256 entries instead of 4 full-resolution arrays; then it steps the
+// recurrences 32 times.  The growing exponentials are only propagated over 32 samples, so nothing blows up.
+// (validated against the direct FIR in tools/proto_cuspzac.py and tests/test_gpu_icpc.py)
+// ==================================================================================================
+struct CzState {
+    double EmL, EpL, W0L, W1L, W2L, W0F, V0, V1, V2, EpR, EmR;
+    bool active;
+};
+
+__device__ __forceinline__ double* cz_tab(double* tabA, double* tabB, int idx)
+{
+    return idx < 8 ? tabA + idx * NT : tabB + (idx - 8) * NT;
+}
+
+// block-wide scans of d over the whole waveform; fills the 16 decimated tables and *pp0 = P+[0]
+__device__ void cz_scan(const CzDev& Z, const double* TT, int n, int tid, double* tabA, double* tabB, double* red,
+                        double* pp0)
+{
+    const int lane = tid & 31, wid = tid >> 5;
+    const int i0 = tid * CZ_CH;
+    const double r = Z.r, rho = Z.rho;
+    double pm = 0, d1 = 0, d2 = 0, pp = 0;
+    double cpm[4] = {0, 0, 0, 0}, cd1[4] = {0, 0, 0, 0}, cd2[4] = {0, 0, 0, 0}, cpp[4] = {0, 0, 0, 0};
+    if (i0 < n) {
+        // forward: P-, D1, D2
+        double tcur = TT[padi(i0)];
+        double yprev = (i0 >= 1) ? tcur - TT[padi(i0 - 1)] : 0.0;
+#pragma unroll 4
+        for (int k = 0; k < CZ_CH; ++k) {
+            const int i = i0 + k;
+            double d = 0.0;
+            if (i < n) {
+                const double tnext = TT[padi(i + 1)];
+                const double y = tnext - tcur;      // exact difference of neighbouring prefix sums
+                d = fma(-r, yprev, y);
+                yprev = y;
+                tcur = tnext;
+            }
+            const double di = (double)i;
+            pm = fma(rho, pm, d);
+            d1 = fma(di, d, d1);
+            d2 = fma(di * di, d, d2);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (k == Z.oc[q]) { cpm[q] = pm; cd1[q] = d1; cd2[q] = d2; }
+        }
+        // backward: P+
+        const int il = min(i0 + CZ_CH, n);          // one past the last valid sample of the chunk
+        double tn = TT[padi(il)], tc = TT[padi(il - 1)];
+#pragma unroll 4
+        for (int k = CZ_CH - 1; k >= 0; --k) {
+            const int i = i0 + k;
+            double d = 0.0;
+            if (i < n) {
+                const double tp = (i >= 1) ? TT[padi(i - 1)] : tc;   // i == 0: y[-1] = 0
+                d = fma(-r, tc - tp, tn - tc);
+                tn = tc;
+                tc = tp;
+            }
+            pp = fma(rho, pp, d);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (k == Z.oa[q]) cpp[q] = pp;
+        }
+    }
+    // warp-level scans (linear recurrences with constant multiplier rho^CH; plain sums for the moments)
+    double vpm = pm, vd1 = d1, vd2 = d2, vpp = pp;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int o = 1 << s;
+        const double upm = __shfl_up_sync(FULL, vpm, o), ud1 = __shfl_up_sync(FULL, vd1, o), ud2 = __shfl_up_sync(FULL, vd2, o);
+        const double upp = __shfl_down_sync(FULL, vpp, o);
+        if (lane >= o) { vpm = fma(Z.rho_ch_pow[s], upm, vpm); vd1 += ud1; vd2 += ud2; }
+        if (lane + o < 32) vpp = fma(Z.rho_ch_pow[s], upp, vpp);
+    }
+    if (lane == 31) { red[wid] = vpm; red[8 + wid] = vd1; red[16 + wid] = vd2; }
+    if (lane == 0) red[24 + wid] = vpp;
+    __syncthreads();
+    double gpm = 0, gd1 = 0, gd2 = 0, gpp = 0;   // carries of the neighbouring warps
+    for (int w = 0; w < wid; ++w) { gpm = fma(Z.rho_warp, gpm, red[w]); gd1 += red[8 + w]; gd2 += red[16 + w]; }
+    for (int w = NWARP - 1; w > wid; --w) gpp = fma(Z.rho_warp, gpp, red[24 + w]);
+    // global inclusive values of this thread, then the carry-in = inclusive value of the neighbour thread
+    const double ipm = fma(Z.rho_lane[lane], gpm, vpm);
+    const double ipp = fma(Z.rho_lane[31 - lane], gpp, vpp);
+    double c_pm = __shfl_up_sync(FULL, ipm, 1), c_pp = __shfl_down_sync(FULL, ipp, 1);
+    if (lane == 0) c_pm = gpm;
+    if (lane == 31) c_pp = gpp;
+    const double c_d1 = gd1 + (vd1 - d1), c_d2 = gd2 + (vd2 - d2);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        cz_tab(tabA, tabB, q * 3 + 0)[tid] = fma(Z.pw_c[q], c_pm, cpm[q]);
+        cz_tab(tabA, tabB, q * 3 + 1)[tid] = cd1[q] + c_d1;
+        cz_tab(tabA, tabB, q * 3 + 2)[tid] = cd2[q] + c_d2;
+        cz_tab(tabA, tabB, 12 + q)[tid] = fma(Z.pw_a[q], c_pp, cpp[q]);
+    }
+    if (tid == 0) *pp0 = ipp;
+}
+
+// window states at m = 32*tid in closed form from the tables
+__device__ void cz_init(const CzDev& Z, const double* TT, int n, int tid, double* tabA, double* tabB, double pp0,
+                        CzState& S)
+{
+    const int m = tid * CZ_CH;
+    S.active = (m < n) && (m + CZ_CH - 1 >= Z.L - 1);
+    if (!S.active) return;
+    auto lc = [&](int q, int kind, int pos) -> double {   // causal prefixes (P-, D1, D2): zero before the trace
+        return pos < 0 ? 0.0 : cz_tab(tabA, tabB, q * 3 + kind)[pos >> 5];
+    };
+    auto la = [&](int q, int pos) -> double {             // anti-causal prefix P+
+        if (pos >= n) return 0.0;
+        if (pos < 0) return exp((double)pos * Z.inv_sigma) * pp0;   // rho^(-pos) * P+[0]
+        return cz_tab(tabA, tabB, 12 + q)[pos >> 5];
+    };
+    auto d0 = [&](int j) -> double {                      // D0[j] = sum_{i<=j} d[i] = TT[j+1] - r*TT[j]
+        return j < 0 ? 0.0 : fma(-Z.r, TT[padi(j)], TT[padi(j + 1)]);
+    };
+    const int lt = Z.lt, L = Z.L, Rn = Z.Rn, F = Z.F;
+    const double dm = (double)m;
+    S.EmL = Z.cA * (lc(0, 0, m) - Z.rho_lt * lc(1, 0, m - lt));
+    S.EpL = Z.cA_rhoinv_ltm1 * (la(0, m - lt + 1) - Z.rho_lt * la(1, m + 1));
+    S.EpR = Z.cA_rhoinv_Rn * (lc(2, 0, m - L + Rn) - Z.rho_Rn * lc(3, 0, m - L));
+    S.EmR = Z.cA_rho * (la(2, m - L + 1) - Z.rho_Rn * la(3, m - L + Rn + 1));
+    const double a0 = d0(m) - d0(m - lt), a1 = lc(0, 1, m) - lc(1, 1, m - lt), a2 = lc(0, 2, m) - lc(1, 2, m - lt);
+    S.W0L = a0;
+    S.W1L = dm * a0 - a1;
+    S.W2L = dm * dm * a0 - 2.0 * dm * a1 + a2;
+    S.W0F = d0(m - lt) - d0(m - lt - F - 1);
+    const double b0 = d0(m - L + Rn) - d0(m - L);
+    const double b1 = lc(2, 1, m - L + Rn) - lc(3, 1, m - L), b2 = lc(2, 2, m - L + Rn) - lc(3, 2, m - L);
+    const double qq = (double)(m - L);
+    S.V0 = b0;
+    S.V1 = b1 - qq * b0;
+    S.V2 = b2 - 2.0 * qq * b1 + qq * qq * b0;
+}
+
+// one input stream d[j], j advancing by one per step (indices before the trace read as zero)
+struct CzStream {
+    double t, yprev;
+    int j;  // index of the NEXT d to produce
+    __device__ __forceinline__ void init(const double* TT, int j0)
+    {
+        j = j0;
+        t = TT[padi(max(j0, 0))];
+        yprev = (j0 >= 1) ? t - TT[padi(j0 - 1)] : 0.0;
+    }
+    __device__ __forceinline__ double next(const double* TT, double r, int n)
+    {
+        const int jj = min(max(j + 1, 0), n);
+        const double tn = TT[padi(jj)];
+        const double y = tn - t;
+        const double d = fma(-r, yprev, y);
+        yprev = y;
+        t = tn;
+        ++j;
+        return d;
+    }
+};
+
+// 32 recurrence steps; emits CUSP and/or ZAC outputs, tracks (max, first argmax), fills the pick-off windows
+__device__ void cz_run(const CzDev& Z, const double* TT, int n, int tid, CzState& S, bool want_cusp, bool want_zac,
+                       int from_cusp, int from_zac, int n_w, double* stash_cusp, double* stash_zac, double (&czmax)[2],
+                       int (&czarg)[2])
+{
+    if (!S.active) return;
+    const int m0 = tid * CZ_CH;
+    const int L = Z.L, lt = Z.lt, F = Z.F;
+    const double r = Z.r;
+    CzStream s0, s1, s2, s3;
+    s0.init(TT, m0 + 1);
+    s1.init(TT, m0 + 1 - lt);
+    s2.init(TT, m0 - lt - F);
+    s3.init(TT, m0 + 1 - L);
+#pragma unroll 2
+    for (int k = 0; k < CZ_CH; ++k) {
+        const int m = m0 + k;
+        if (m >= n) break;
+        if (m >= L - 1) {
+            const int j = m - L + 1;
+            const double ylast = s3.yprev;   // y[m-L]
+            const double Dc = (S.EpL - S.EmL + S.EpR - S.EmR) + S.W0F;
+            if (want_cusp) {
+                const double o = fma(Z.g, Dc, Z.gclast_cusp * ylast);
+                if (o > czmax[0]) { czmax[0] = o; czarg[0] = j; }
+                const int q = j - from_cusp;
+                if (q >= 0 && q < n_w) stash_cusp[q] = o;
+            }
+            if (want_zac) {
+                const double poly = (S.W2L - Z.h2 * S.W1L) + (S.V2 - Z.h2 * S.V1);
+                const double o = fma(Z.g, fma(Z.B, poly, Dc), Z.gclast_zac * ylast);
+                if (o > czmax[1]) { czmax[1] = o; czarg[1] = j; }
+                const int q = j - from_zac;
+                if (q >= 0 && q < n_w) stash_zac[q] = o;
+            }
+        }
+        // step m -> m+1
+        const double a = s0.next(TT, r, n), b = s1.next(TT, r, n), c = s2.next(TT, r, n), d = s3.next(TT, r, n);
+        S.EmL = fma(Z.rho, S.EmL, fma(Z.cA, a, -Z.cA_rho_lt * b));
+        S.EpL = fma(Z.rho_inv, S.EpL, fma(Z.cA, a, -Z.cA_rhoinv_lt * b));
+        S.W2L = S.W2L + 2.0 * S.W1L + S.W0L - Z.lt2_d * b;
+        S.W1L = S.W1L + S.W0L - Z.lt_d * b;
+        S.W0L = S.W0L + a - b;
+        S.W0F = S.W0F + b - c;
+        S.V2 = S.V2 - 2.0 * S.V1 + S.V0 + Z.Rn2_d * c;
+        S.V1 = S.V1 - S.V0 + Z.Rn_d * c;
+        S.V0 = S.V0 + c - d;
+        S.EpR = fma(Z.rho, S.EpR, fma(Z.cA_rhoinv_Rn, c, -Z.cA * d));
+        S.EmR = fma(Z.rho_inv, S.EmR, fma(Z.cA_rho_Rn, c, -Z.cA * d));
+    }
+}
+
 __global__ void __launch_bounds__(NT, 2)
 icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, long long n_events, long long ld,
             double* __restrict__ rows)
@@ -307,7 +531,6 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
     uint32_t* masks = reinterpret_cast<uint32_t*>(smem + SM_MASK);
     double* red = reinterpret_cast<double*>(smem + SM_RED);
     double* stash = reinterpret_cast<double*>(smem + SM_STASH);
-    double* dniA = reinterpret_cast<double*>(smem + SM_DNI);
     double* row = reinterpret_cast<double*>(smem + SM_ROW);
     int* ibuf = reinterpret_cast<int*>(smem + SM_IBUF);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM_BAR);
@@ -318,8 +541,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
     const double t_first = P.t_first, dt = P.dt;
     const unsigned G = P.groups;
 
-    // one-time setup: DNI fit matrices -> SMEM, mbarrier
-    for (int i = tid; i < 2 * LGDSP_MAX_DNI * 4; i += NT) dniA[i] = P.dni_A[i];
+    // one-time setup: mbarrier
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -331,8 +553,8 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         tma_load_1d(xs, wf + e * ld, wf_bytes, bar);
     }
     uint32_t phase = 0;
-    const double* A_int = dniA;
-    const double* A_sig = dniA + LGDSP_MAX_DNI * 4;
+    const double* A_int = P.dni_A;                       // global, L1/L2 resident (4 KB)
+    const double* A_sig = P.dni_A + LGDSP_MAX_DNI * 4;
 
     for (; e < n_events; e += gridDim.x) {
         // ------------------------------------------------------------------------------------------
@@ -520,15 +742,20 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             block_sum<7>(v, red, tid);
             tl_S = v[0]; tl_SS = v[1]; tl_SX = v[2]; pz_S = v[3]; pz_SS = v[4]; pz_SX = v[5]; tl_bad = v[6];
         }
-        // xs is free now: prefetch the next event (TMA, async proxy)
-        if (tid == 0) {
-            const long long en = e + gridDim.x;
-            if (en < n_events) {
-                fence_proxy_async();
-                mbar_expect_tx(bar, wf_bytes);
-                tma_load_1d(xs, wf + en * ld, wf_bytes, bar);
+        // xs is free now: prefetch the next event (TMA, async proxy) -- unless the structured CUSP/ZAC pass borrows
+        // xs for its prefix tables; then the prefetch is issued inside that pass
+        const bool cz_structured = (G & LGDSP_GROUP_CUSPZAC) && !P.direct;
+        auto prefetch_next = [&]() {
+            if (tid == 0) {
+                const long long en = e + gridDim.x;
+                if (en < n_events) {
+                    fence_proxy_async();
+                    mbar_expect_tx(bar, wf_bytes);
+                    tma_load_1d(xs, wf + en * ld, wf_bytes, bar);
+                }
             }
-        }
+        };
+        if (!cz_structured) prefetch_next();
 
         // resolve t10..t99 now (t50 positions the energy pick-off windows of pass 3)
         if (wid < 5) {
@@ -626,10 +853,11 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 }
             }
         }
-        // CUSP / ZAC, direct form (validation mode; the structured evaluation replaces it)
+        // CUSP / ZAC
         double czmax[2] = {-CUDART_INF, -CUDART_INF};
         int czarg[2] = {0x7fffffff, 0x7fffffff};
-        if (G & LGDSP_GROUP_CUSPZAC) {
+        if ((G & LGDSP_GROUP_CUSPZAC) && P.direct) {
+            // direct form (validation mode)
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
                 const int L = f ? P.zac_L : P.cusp_L;
@@ -641,6 +869,25 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     const int r = j - pk_from[1 + f];
                     if (r >= 0 && r < P.sig_dni.n_w) stash[(1 + f) * LGDSP_MAX_DNI + r] = o;
                 }
+            }
+        } else if (G & LGDSP_GROUP_CUSPZAC) {
+            double* tabA = reinterpret_cast<double*>(smem + SM_XS);
+            double* tabB = reinterpret_cast<double*>(smem + SM_TAB);
+            const int npass = P.cz_shared ? 1 : 2;
+            for (int ps = 0; ps < npass; ++ps) {
+                const CzDev& Z = P.cz[ps];
+                const bool want_cusp = P.cz_shared || ps == 0, want_zac = P.cz_shared || ps == 1;
+                if (ps > 0) __syncthreads();  // previous pass finished reading the tables
+                cz_scan(Z, TT, n, tid, tabA, tabB, red, row + 55);
+                __syncthreads();
+                CzState st;
+                cz_init(Z, TT, n, tid, tabA, tabB, row[55], st);
+                if (ps == npass - 1) {
+                    __syncthreads();       // every thread has read its table entries: xs may be overwritten
+                    prefetch_next();
+                }
+                cz_run(Z, TT, n, tid, st, want_cusp, want_zac, pk_from[1], pk_from[2], P.sig_dni.n_w,
+                       stash + LGDSP_MAX_DNI, stash + 2 * LGDSP_MAX_DNI, czmax, czarg);
             }
         }
         // reductions of pass 3

@@ -334,13 +334,20 @@ ORC_API int orc_trap_bruteforce(const double* y, int n, int navg, int ngap, int 
 ORC_API int orc_fir_valid(const double* y, int n, const double* c, int L, double* out)
 {
     int n_out = n - L + 1;
+    if (n_out <= 0) return 0;
+    /* reversed taps so that the inner loop runs forward over contiguous memory (SIMD-friendly, like the
+     * reference's @simd loops; the summation order is the compiler's, as in Julia) */
+    double* cr = (double*)malloc(sizeof(double) * (size_t)L);
+    for (int k = 0; k < L; ++k) cr[k] = c[L - 1 - k];
     for (int j = 0; j < n_out; ++j) {
         double acc = 0;
-        const double* yy = y + j + L - 1;
-        for (int k = 0; k < L; ++k) acc += c[k] * yy[-k];
+        const double* yy = y + j;
+#pragma omp simd reduction(+ : acc)
+        for (int k = 0; k < L; ++k) acc += cr[k] * yy[k];
         out[j] = acc;
     }
-    return n_out > 0 ? n_out : 0;
+    free(cr);
+    return n_out;
 }
 
 /* valid-mode correlation for the SG kernels: out[j] = sum_k h[k] y[j+k] */
