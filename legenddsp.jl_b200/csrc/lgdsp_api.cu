@@ -219,18 +219,18 @@ static bool make_czdev(const lgdsp_cuspzac& z, const double* cusp_coeffs, const 
     D.gclast_cusp = (double)(g * r * cusp_at(L - 1));
     D.gclast_zac = (double)(g * r * (cusp_at(L - 1) + B * par_at(L - 1)));
     // the coefficient arrays passed through the ABI must be the ones this structure reproduces
-    const int probe[6] = {1, lt - 1, lt, lt + F, lt + F + 1, L - 1};
     for (int which = 0; which < 2; ++which) {
         const double* co = which ? zac_coeffs : cusp_coeffs;
         if (!co) continue;
         double scale = 0;
         for (int k = 0; k < L; ++k) scale = fmax(scale, fabs(co[k]));
-        for (int pi = 0; pi < 6; ++pi) {
-            const int k = probe[pi];
-            const ld bb = which ? B : 0.0L;
-            const ld ck = cusp_at(k) + bb * par_at(k), ckm = cusp_at(k - 1) + bb * par_at(k - 1);
-            const double expect = (double)(g * (ck - r * ckm));
-            if (fabs(expect - co[k]) > 1e-9 * scale) {
+        const ld bb = which ? B : 0.0L;
+        ld prev = 0.0L;
+        for (int k = 0; k < L; ++k) {
+            const ld ck = cusp_at(k) + bb * par_at(k);
+            const double expect = (double)(g * (ck - r * prev));
+            prev = ck;
+            if (!(fabs(expect - co[k]) <= 1e-9 * scale)) {
                 why = which ? "zac.coeffs do not match (sigma, flat, tau, n_taps, beta)" : "cusp.coeffs do not match (sigma, flat, tau, n_taps, beta)";
                 return false;
             }
@@ -342,6 +342,7 @@ static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
 static int check_wf(lgdsp_handle* h, const void* wf, int64_t n_events, int64_t ld, int n, bool device)
 {
     if (n_events < 0) return fail(h, LGDSP_ERR_INVALID_ARG, "n_events < 0");
+    if (n_events == 0) return LGDSP_OK;  // empty table in, empty table out
     if (n_events > 0 && !wf) return fail(h, LGDSP_ERR_INVALID_ARG, "waveform pointer is NULL");
     if (ld < n) return fail(h, LGDSP_ERR_INVALID_ARG, "ld_samples (%lld) < n_samples (%d)", (long long)ld, n);
     if (device && (((uintptr_t)wf & 15u) != 0 || ld % 8 != 0))

@@ -1,0 +1,46 @@
+"""Filter-instance construction: the product library's host builders against the oracle's independent ones and
+against textbook values."""
+import numpy as np
+import pytest
+
+
+def test_sg_textbook_values(L, O):
+    for B in (L.LibBuilders(), O.OracleBuilders()):
+        assert np.allclose(B.sg_coeffs(5, 3, 1), np.array([1, -8, 0, 8, -1]) / 12.0, atol=1e-14)
+        assert np.allclose(B.sg_coeffs(7, 3, 1), np.array([22, -67, -58, 0, 58, 67, -22]) / 252.0, atol=1e-14)
+        assert np.allclose(B.sg_coeffs(5, 2, 0), np.array([-3, 12, 17, 12, -3]) / 35.0, atol=1e-14)
+
+
+@pytest.mark.parametrize("n,deg", [(6, 3), (44, 3), (5, 1), (64, 3), (9, 2)])
+def test_lsq_fit_matrix_reproduces_polynomials(L, O, n, deg):
+    x = np.arange(n, dtype=float)
+    rng = np.random.default_rng(n)
+    c = rng.normal(size=deg + 1)
+    y = sum(c[j] * x ** j for j in range(deg + 1))
+    Al, Ao = L.LibBuilders().lsq_fit_matrix(n, deg), O.OracleBuilders().lsq_fit_matrix(n, deg)
+    assert np.allclose(y @ Al, c, rtol=1e-8, atol=1e-8)
+    assert np.allclose(Al, Ao, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("sigma,flat,L_,zac", [(312.5, 156, 2375, 0), (312.5, 156, 2375, 1), (62.5, 62, 2375, 1),
+                                               (80.5, 40, 601, 1), (1000.0, 250, 2375, 0)])
+def test_cuspzac_coeffs_agree_and_have_the_expected_shape(L, O, sigma, flat, L_, zac):
+    tau = 6.25e8
+    fl = (L.LibBuilders().zac_coeffs if zac else L.LibBuilders().cusp_coeffs)(sigma, flat, tau, L_, float(L_))
+    fo = (O.OracleBuilders().zac_coeffs if zac else O.OracleBuilders().cusp_coeffs)(sigma, flat, tau, L_, float(L_))
+    assert np.allclose(fl, fo, rtol=1e-10, atol=1e-15)
+    shape = np.cumsum(fl)            # tau -> inf: coeffs = first difference of the shape
+    lt = (L_ - flat) // 2
+    assert np.allclose(shape[lt:lt + flat + 1], 1.0, atol=1e-5)   # unit flat top for beta = L
+    if zac:
+        assert abs(shape.sum()) < 1e-6 * np.abs(shape).sum()      # zero area
+
+
+def test_builder_argument_errors(L):
+    lib = L.load_library()
+    import ctypes as C
+    buf = (C.c_double * 16)()
+    assert lib.lgdsp_sg_coeffs(4, 3, 1, buf) != 0      # even length
+    assert lib.lgdsp_sg_coeffs(3, 3, 1, buf) != 0      # degree too high for the window
+    assert lib.lgdsp_lsq_fit_matrix(3, 3, buf) != 0
+    assert lib.lgdsp_cusp_coeffs(-1.0, 2, 1.0, 16, 1.0, buf) != 0
