@@ -198,9 +198,19 @@ static bool make_czdev(const lgdsp_cuspzac& z, const double* cusp_coeffs, const 
     D.rho_Rn = (double)expl(-(ld)Rn / sg);
     D.cA_rhoinv_ltm1 = (double)(cA * expl((ld)(lt - 1) / sg));
     D.cA_rho = (double)(cA * rho);
-    for (int q = 0; q < 4; ++q) {
-        D.pw_c[q] = (double)expl(-(ld)(D.oc[q] + 1) / sg);
-        D.pw_a[q] = (double)expl(-(ld)(CZ_CH - D.oa[q]) / sg);
+    {
+        int oc_idx[4] = {0, 1, 2, 3}, oa_idx[4] = {0, 1, 2, 3};
+        for (int a_ = 0; a_ < 4; ++a_)
+            for (int b_ = a_ + 1; b_ < 4; ++b_) {
+                if (D.oc[oc_idx[b_]] < D.oc[oc_idx[a_]]) { int t_ = oc_idx[a_]; oc_idx[a_] = oc_idx[b_]; oc_idx[b_] = t_; }
+                if (D.oa[oa_idx[b_]] > D.oa[oa_idx[a_]]) { int t_ = oa_idx[a_]; oa_idx[a_] = oa_idx[b_]; oa_idx[b_] = t_; }
+            }
+        for (int q = 0; q < 4; ++q) {
+            D.oc_sorted[q] = D.oc[oc_idx[q]]; D.tab_c[q] = oc_idx[q];
+            D.oa_sorted[q] = D.oa[oa_idx[q]]; D.tab_a[q] = oa_idx[q];
+            D.pw_c[q] = (double)expl(-(ld)(D.oc_sorted[q] + 1) / sg);
+            D.pw_a[q] = (double)expl(-(ld)(CZ_CH - D.oa_sorted[q]) / sg);
+        }
     }
     for (int s2 = 0; s2 < 5; ++s2) D.rho_ch_pow[s2] = (double)expl(-(ld)(CZ_CH << s2) / sg);
     for (int l = 0; l < 32; ++l) D.rho_lane[l] = (double)expl(-(ld)(CZ_CH * (l + 1)) / sg);
@@ -293,7 +303,12 @@ static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
             return fail(h, LGDSP_ERR_INVALID_ARG, "current_window %d:%d outside sg[%d] trace", p->cur_from[k], p->cur_until[k], k);
     }
     if (!win_ok(p->cur_from[3], p->cur_until[3], n)) return fail(h, LGDSP_ERR_INVALID_ARG, "current_window outside the waveform");
-    for (int k = 0; k < 4; ++k) { D.cur_from[k] = p->cur_from[k]; D.cur_until[k] = p->cur_until[k]; }
+    for (int k = 0; k < 4; ++k) { D.cur_from[k] = p->cur_from[k]; D.cur_until[k] = p->cur_until[k]; D.sg_alias[k] = -1; }
+    for (int k = 1; k < 3; ++k)
+        for (int q = 0; q < k && D.sg_alias[k] < 0; ++q)
+            if (p->sg[k].n_taps == p->sg[q].n_taps && p->cur_from[k] == p->cur_from[q] && p->cur_until[k] == p->cur_until[q] &&
+                memcmp(p->sg[k].h, p->sg[q].h, sizeof(double) * p->sg[k].n_taps) == 0)
+                D.sg_alias[k] = q;
     D.nsigma = p->intrace_nsigma;
     D.intr_min_n = p->intrace_min_n;
     if (!win_ok(p->intrace_bl_from, p->intrace_bl_until, D.sg[0].nout)) return fail(h, LGDSP_ERR_INVALID_ARG, "in-trace sigma window outside the sg trace");

@@ -25,14 +25,16 @@ struct DniDev {
 
 // Structured evaluation of a CUSP/ZAC filter (see lgdsp_icpc.cu, "CUSP/ZAC through their analytic structure").
 // One descriptor = one (sigma, flat, tau, L); it can emit the CUSP output (B = 0) and/or the ZAC output.
-constexpr int CZ_CH = 32;  // samples per thread chunk
+constexpr int CZ_CH = 33;  // samples per thread chunk (odd: conflict-free linear SMEM layout)
 struct CzDev {
     int L, F, lt, Rn;
-    int oc[4], oa[4];          // in-chunk offsets of the decimated prefix-table positions
+    int oc[4], oa[4];          // in-chunk offsets of the decimated prefix-table positions (logical order)
+    int oc_sorted[4], tab_c[4];   // causal capture offsets ascending + logical table index of each rank
+    int oa_sorted[4], tab_a[4];   // anti-causal capture offsets DESCENDING + logical table index of each rank
     double r, rho, rho_inv, inv_sigma;
     double cA, cA_rho_lt, cA_rhoinv_lt, cA_rhoinv_Rn, cA_rho_Rn;   // recurrence input gains (cA = a/2)
     double rho_lt, rho_Rn, cA_rhoinv_ltm1, cA_rho;                 // closed-form initial states
-    double pw_c[4], pw_a[4];   // rho^(oc+1), rho^(CH-oa): carry multipliers of the decayed prefixes
+    double pw_c[4], pw_a[4];   // rho^(oc_sorted+1), rho^(CH-oa_sorted): carry multipliers (indexed by rank)
     double rho_ch_pow[5];      // rho^(CH*2^s)
     double rho_lane[32];       // rho^(CH*(lane+1))
     double rho_warp;           // rho^(CH*32)
@@ -57,6 +59,7 @@ struct IcpcDev {
     double trap_pick, cusp_pick, zac_pick;
     SgDev sg[3];
     int cur_from[4], cur_until[4];
+    int sg_alias[4];           // sg_alias[f] >= 0: filter f (taps and window) is identical to that earlier filter
     double nsigma;
     int intr_min_n, intr_from, intr_until, pad0;
     int cusp_L, zac_L;
@@ -68,7 +71,6 @@ struct IcpcDev {
     const double* zac_g;    // differenced ZAC taps on TT, zac_L+1 values
 };
 
-__device__ __forceinline__ int padi(int i) { return i + (i >> 5); }
 
 // ---- TMA 1-D bulk copy + mbarrier (sm_90+/sm_100a): SASS UBLKCP / SYNCS ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
