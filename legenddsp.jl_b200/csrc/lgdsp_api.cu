@@ -199,17 +199,24 @@ static bool make_czdev(const lgdsp_cuspzac& z, const double* cusp_coeffs, const 
     D.cA_rhoinv_ltm1 = (double)(cA * expl((ld)(lt - 1) / sg));
     D.cA_rho = (double)(cA * rho);
     {
-        int oc_idx[4] = {0, 1, 2, 3}, oa_idx[4] = {0, 1, 2, 3};
-        for (int a_ = 0; a_ < 4; ++a_)
-            for (int b_ = a_ + 1; b_ < 4; ++b_) {
-                if (D.oc[oc_idx[b_]] < D.oc[oc_idx[a_]]) { int t_ = oc_idx[a_]; oc_idx[a_] = oc_idx[b_]; oc_idx[b_] = t_; }
-                if (D.oa[oa_idx[b_]] > D.oa[oa_idx[a_]]) { int t_ = oa_idx[a_]; oa_idx[a_] = oa_idx[b_]; oa_idx[b_] = t_; }
+        // capture events: causal table q after sample oc[q]; anti-causal table q after sample oa[q]-1
+        struct Ev { int k, kind, tab; };
+        Ev ev[8];
+        for (int q = 0; q < 4; ++q) { ev[q] = {D.oc[q], 0, q}; ev[4 + q] = {D.oa[q] - 1, 1, q}; }
+        for (int a_ = 0; a_ < 8; ++a_)
+            for (int b_ = a_ + 1; b_ < 8; ++b_)
+                if (ev[b_].k < ev[a_].k) { Ev t_ = ev[a_]; ev[a_] = ev[b_]; ev[b_] = t_; }
+        D.n_ev = 8;
+        for (int i = 0; i < 8; ++i) {
+            D.ev_k[i] = ev[i].k; D.ev_kind[i] = ev[i].kind; D.ev_tab[i] = ev[i].tab;
+            if (ev[i].kind == 0) {
+                D.ev_pw[i] = (double)expl(-(ld)(ev[i].k + 1) / sg);
+                D.ev_rinv[i] = 0.0;
+            } else {
+                const int o = ev[i].k + 1;
+                D.ev_pw[i] = (double)expl(-(ld)(CZ_CH - o) / sg);
+                D.ev_rinv[i] = (double)expl((ld)o / sg);
             }
-        for (int q = 0; q < 4; ++q) {
-            D.oc_sorted[q] = D.oc[oc_idx[q]]; D.tab_c[q] = oc_idx[q];
-            D.oa_sorted[q] = D.oa[oa_idx[q]]; D.tab_a[q] = oa_idx[q];
-            D.pw_c[q] = (double)expl(-(ld)(D.oc_sorted[q] + 1) / sg);
-            D.pw_a[q] = (double)expl(-(ld)(CZ_CH - D.oa_sorted[q]) / sg);
         }
     }
     for (int s2 = 0; s2 < 5; ++s2) D.rho_ch_pow[s2] = (double)expl(-(ld)(CZ_CH << s2) / sg);
@@ -228,6 +235,21 @@ static bool make_czdev(const lgdsp_cuspzac& z, const double* cusp_coeffs, const 
     D.g = (double)g;
     D.gclast_cusp = (double)(g * r * cusp_at(L - 1));
     D.gclast_zac = (double)(g * r * (cusp_at(L - 1) + B * par_at(L - 1)));
+    // Lipschitz constants of the two output traces (coarse-to-fine pruning in the kernel): total variation of the
+    // zero-extended taps h[k] = g*(c[k] - r*c[k-1])
+    for (int which = 0; which < 2; ++which) {
+        const ld bb = which ? B : 0.0L;
+        ld prev_c = 0.0L, prev_h = 0.0L, tv = 0.0L;
+        for (int k = 0; k < L; ++k) {
+            const ld ck = cusp_at(k) + bb * par_at(k);
+            const ld hk = g * (ck - r * prev_c);
+            tv += fabsl(hk - prev_h);
+            prev_c = ck;
+            prev_h = hk;
+        }
+        tv += fabsl(prev_h);
+        (which ? D.lip_zac : D.lip_cusp) = (double)(tv * (1.0L + 1e-9L));
+    }
     // the coefficient arrays passed through the ABI must be the ones this structure reproduces
     for (int which = 0; which < 2; ++which) {
         const double* co = which ? zac_coeffs : cusp_coeffs;

@@ -29,17 +29,21 @@ constexpr int CZ_CH = 33;  // samples per thread chunk (odd: conflict-free linea
 struct CzDev {
     int L, F, lt, Rn;
     int oc[4], oa[4];          // in-chunk offsets of the decimated prefix-table positions (logical order)
-    int oc_sorted[4], tab_c[4];   // causal capture offsets ascending + logical table index of each rank
-    int oa_sorted[4], tab_a[4];   // anti-causal capture offsets DESCENDING + logical table index of each rank
+    // capture events of the single forward scan, sorted by sample index: after sample ev_k (-1: before the first)
+    // the running causal values (kind 0: P-, D1, D2 -> tables 3*ev_tab..) or the running anti-causal partial sum
+    // (kind 1 -> table 12+ev_tab) are stored
+    int n_ev, ev_k[8], ev_kind[8], ev_tab[8];
+    double ev_pw[8];           // carry multiplier: rho^(oc+1) (causal) / rho^(CH-oa) (anti-causal)
+    double ev_rinv[8];         // anti-causal: rho^(-oa)
     double r, rho, rho_inv, inv_sigma;
     double cA, cA_rho_lt, cA_rhoinv_lt, cA_rhoinv_Rn, cA_rho_Rn;   // recurrence input gains (cA = a/2)
     double rho_lt, rho_Rn, cA_rhoinv_ltm1, cA_rho;                 // closed-form initial states
-    double pw_c[4], pw_a[4];   // rho^(oc_sorted+1), rho^(CH-oa_sorted): carry multipliers (indexed by rank)
     double rho_ch_pow[5];      // rho^(CH*2^s)
     double rho_lane[32];       // rho^(CH*(lane+1))
     double rho_warp;           // rho^(CH*32)
     double h2, B, lt_d, lt2_d, Rn_d, Rn2_d;
     double g, gclast_cusp, gclast_zac;  // output gain, g*r*c[L-1] of the cusp / zac shape
+    double lip_cusp, lip_zac;           // sum_k |h[k]-h[k-1]| of the zero-extended FIR taps: |out[j+1]-out[j]| <= lip * max|y|
 };
 
 // kernel-argument block of the fused dsp_icpc kernel (lives in the constant bank, ~2 KB)

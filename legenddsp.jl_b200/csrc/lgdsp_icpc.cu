@@ -2,21 +2,30 @@
 //
 // Data flow per waveform (reference steps in brackets, /root/reference/src/dsp_icpc.jl):
 //   TMA bulk copy (cp.async.bulk, 16 KB UInt16) HBM -> SMEM, prefetched one event ahead
-//   pass 1  raw samples: saturation [:93-95], baseline regression sums [:102], min/max [:111-112],
-//           integer prefix sums P = cumsum(x), PP = cumsum(P)            (exact integer arithmetic)
-//   pass 2  pole-zero in closed form y = w + km1*cumsum(w), w = x - blmean [:105,:119-120]; writes
-//           TT[i+1] = cumsum(y)[i] (float64, SMEM); tail log-regression [:115]; PZ tail stats [:123];
-//           threshold masks for t10..t99 [:132-136]
-//   pass 3  every trapezoid [:126,:147-164,:202-207] as 4 look-ups in TT per output; Savitzky-Golay and
-//           derivative currents [:181-186] as sliding-window FIRs on TT
-//   pass 4  masks for t50_current and the in-trace pile-up search [:189-195]; crossing resolution with
-//           bit-parallel run detection (Intersect state machine)
-//   cz      CUSP/ZAC [:167-178] through their analytic structure (sliding exponential/polynomial windows)
-//   pass 5  interpolated pick-offs (PolynomialDNI), qdrift/lq [:141-144], output row (49 doubles)
+//   P1  raw samples: saturation [:93-95], baseline regression sums [:102], min/max [:111-112], block scan of the
+//       chunk sums (exact integers) -> P = cumsum(x), PP = cumsum(P) at every chunk start
+//   P2  pole-zero in closed form y = w + km1*cumsum(w), w = x - blmean [:105,:119-120]; writes
+//       TT[i+1] = cumsum(y)[i] (float64, SMEM); t10..t99 threshold masks [:132-136] only for chunks whose
+//       [ymin, ymax] straddles a threshold; tail log-regression [:115] spread evenly over all threads
+//   P3  everything that only needs TT: PZ tail stats [:123]; the two trapezoids whose minimum is needed
+//       (e_10410, e_313 and their *_inv, [:147-154,:202-204]) in full; the other trapezoids [:126,:150,:160,:207]
+//       on a COARSE grid (every 33rd output); Savitzky-Golay / derivative currents [:181-186]; prefix tables of the
+//       CUSP/ZAC evaluation
+//   P4  coarse-to-fine: an interval between two coarse points is only evaluated when it can matter --
+//         maxima (e_535, e_trap_max, e_cusp_max, e_zac_max): |out[j+1]-out[j]| <= max|y| * sum_k |h[k]-h[k-1]| for any FIR
+//           h (Lipschitz bound), so an interval whose bound stays below the best coarse value is skipped;
+//         t0 / t0_inv (Intersect with mintot >= 34 samples): a qualifying run overlapping an interval must contain
+//           one of its end points, so intervals whose end points are both below threshold are skipped;
+//         t50_current / in-trace pile-up masks: only chunks whose maximum reaches the smaller threshold.
+//       Both rules are exact (never change a result); how much they save is data dependent.
+//       CUSP/ZAC [:167-178] through their analytic structure (sliding exponential/polynomial windows): closed-form
+//       states at every chunk start give the coarse values; the 33-step recurrences run on candidate chunks only.
+//   P5  crossing resolution with bit-parallel run detection (Intersect state machine),
+//       interpolated pick-offs (PolynomialDNI), qdrift/lq [:141-144], output row (49 doubles)
 //
-// Work mapping: thread t owns the CH = 33 consecutive samples/outputs [33t, 33t+33).  33 is odd, so with the plain
-// linear layout of TT the 32 lanes of a warp hit 32 different banks for EVERY window offset, and all SMEM
-// addresses inside the unrolled loops are "per-stream base register + immediate": no padding, no index math.
+// Work mapping: scans use chunks of CH = 33 consecutive samples per thread (33 is odd: with the plain linear layout
+// of TT the 32 lanes of a warp hit different banks for every window offset); all other passes are strided over the
+// threads (consecutive lanes <-> consecutive samples), so windowed work is spread evenly.
 // The waveform is read from HBM exactly once (16 KB) and 392 B are written.
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -27,112 +36,114 @@ namespace lgdsp {
 
 constexpr int NT = 256;          // threads per CTA
 constexpr int NWARP = NT / 32;
-constexpr int CH = CZ_CH;        // samples per thread (33)
+constexpr int CH = CZ_CH;        // samples per thread in the scan passes (33)
 constexpr int MAXN = LGDSP_MAX_SAMPLES;
 constexpr int NWORDS = MAXN / 32;  // mask words
 static_assert(NT * CH >= MAXN + 1, "chunks must cover the waveform");
 static_assert(NWORDS == NT, "one mask word per thread");
 
-enum { M_T0 = 0, M_T0INV, M_T10, M_T50, M_T80, M_T90, M_T99, M_CUR, M_PILE, NMASK };
+// T10..T99 last: their 5 KB are reused for the coarse CUSP/ZAC values once they are resolved
+enum { M_T0 = 0, M_T0INV, M_CUR, M_PILE, M_T10, M_T50, M_T80, M_T90, M_T99, NMASK };
+
+// reduction slots: red[slot][warp]
+enum {
+    // stage A (after P1)
+    R_BLS = 0, R_BLSS, R_BLSX, R_NLOW, R_NHIGH, R_MX, R_MN, R_SLEN, R_SS, R_SQ,
+    // stage C (after P2/P3)
+    R_TLS, R_TLSS, R_TLSX, R_TLBAD, R_PZS, R_PZSS, R_PZSX, R_YMIN, R_YMAX,
+    R_E104, R_E104N, R_E313, R_E313N, R_C535, R_CET, R_SGMAX, R_SGS, R_SGSS,
+    R_CMAX0, R_CMAX1, R_CMAX2, R_CMAX3, R_CARG0, R_CARG1, R_CARG2, R_CARG3,
+    // stage D
+    R_CZC0, R_CZC1,
+    // stage E
+    R_E535, R_ETMAX, R_ETARG, R_CZMAX0, R_CZARG0, R_CZMAX1, R_CZARG1,
+    // scratch of cz_scan (4 slots = 32 doubles)
+    R_CZSCR, R_CZSCR1, R_CZSCR2, R_CZSCR3,
+    NSLOT
+};
 
 // ---- shared memory carve-up (bytes) ----
 constexpr int SM_XS = 0;                                   // uint16 xs[8192]  (aliased by CUSP/ZAC tables 0..7)
 constexpr int TT_LEN = MAXN + 8;
 constexpr int SM_TT = SM_XS + MAXN * 2;                    // double TT[8193+]
 constexpr int SM_MASK = SM_TT + TT_LEN * 8;                // uint32 masks[NMASK][NWORDS]
-constexpr int RED_W = 24;
-constexpr int SM_RED = SM_MASK + NMASK * NWORDS * 4;       // double red[NWARP][24]
-constexpr int SM_STASH = SM_RED + NWARP * RED_W * 8;       // double stash[3][LGDSP_MAX_DNI]
+constexpr int SM_RED = SM_MASK + NMASK * NWORDS * 4;       // double red[NSLOT][NWARP]
+constexpr int SM_STASH = SM_RED + NSLOT * NWARP * 8;       // double stash[3][LGDSP_MAX_DNI]
 constexpr int SM_TAB = SM_STASH + 3 * LGDSP_MAX_DNI * 8;   // double tabB[8][256]: CUSP/ZAC prefix tables 8..15
 constexpr int SM_ROW = SM_TAB + 8 * NT * 8;                // double row[64]
 constexpr int SM_SCR = SM_ROW + 64 * 8;                    // double scr[32]: scalars passed between warps
 constexpr int SM_IBUF = SM_SCR + 32 * 8;                   // int ibuf[64]
 constexpr int SM_BAR = SM_IBUF + 64 * 4;                   // uint64 mbarrier
 constexpr int SM_TOTAL = SM_BAR + 16;
+static_assert(2 * (SM_TOTAL + 1024) <= 233472, "two CTAs per SM");
+static_assert(2 * NT * 8 <= 5 * NWORDS * 4, "coarse CUSP/ZAC values fit into the T10..T99 mask area");
 
 int icpc_smem_bytes() { return SM_TOTAL; }
 int icpc_threads() { return NT; }
 
-enum { IB_POS0 = 0 /* NMASK positions */, IB_MULT = 16, IB_SCAN = 32 /* 8 warp totals */ };
-enum { SC_TX = 0 /* 5 */, SC_T0 = 5, SC_T0INV = 6, SC_DSCAN = 8 /* 8 */, SC_PP0 = 16 };
+enum { IB_POS0 = 0 /* NMASK positions */, IB_MULT = 16 };
+enum { SC_TX = 0 /* 5 */, SC_T0 = 5, SC_T0INV = 6, SC_PP0 = 16 };
 
 // ---------------------------------------------------------------------------------------------------
-// block-wide reductions; every thread gets the result
+// reductions.  Maxima/minima of doubles go through an order-preserving 64-bit integer key and two 32-bit
+// REDUX instructions instead of 5 shuffle rounds; every warp publishes its partial in red[slot][warp]; after the
+// next barrier a warp combines the 8 partials with its lanes (lane l reads partial l & 7).
 // ---------------------------------------------------------------------------------------------------
-template <int NV>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double* red, int tid)
+__device__ __forceinline__ long long d2key(double v)
 {
-    static_assert(NV <= RED_W, "reduction scratch too small");
-    const int lane = tid & 31, wid = tid >> 5;
+    const long long b = __double_as_longlong(v);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double key2d(long long k) { return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL)); }
+// maximum over the warp (no NaNs), result in every lane
+__device__ __noinline__ double wmax_d(double v)
+{
+    const long long k = d2key(v);
+    const int hi = (int)(k >> 32);
+    const unsigned lo = (unsigned)k;
+    const int mh = __reduce_max_sync(FULL, hi);
+    const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+    return key2d(((long long)mh << 32) | (long long)ml);
+}
+__device__ __forceinline__ double wmin_d(double v) { return -wmax_d(-v); }
+// (maximum, FIRST index) over the warp
+__device__ __forceinline__ double wargmax_d(double v, int& ix)
+{
+    const double m = wmax_d(v);
+    ix = __reduce_min_sync(FULL, v == m ? ix : 0x7fffffff);
+    return m;
+}
+__device__ __noinline__ double wsum_d(double v)
+{
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) red[wid * RED_W + i] = v[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double s = 0;
-#pragma unroll
-        for (int w = 0; w < NWARP; ++w) s += red[w * RED_W + i];
-        v[i] = s;
-    }
-    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ void red_put(double* red, int slot, int wid, int lane, double v)
+{
+    if (lane == 0) red[slot * NWARP + wid] = v;
+}
+__device__ __noinline__ double red_sum(const double* red, int slot)
+{
+    double v = red[slot * NWARP + (threadIdx.x & 7)];
+    v += __shfl_xor_sync(FULL, v, 4);
+    v += __shfl_xor_sync(FULL, v, 2);
+    v += __shfl_xor_sync(FULL, v, 1);
+    return v;
+}
+__device__ __noinline__ double red_max(const double* red, int slot) { return wmax_d(red[slot * NWARP + (threadIdx.x & 7)]); }
+__device__ __forceinline__ double red_min(const double* red, int slot) { return -wmax_d(-red[slot * NWARP + (threadIdx.x & 7)]); }
+// (max value, FIRST index)
+__device__ __forceinline__ void red_argmax(const double* red, int slot_v, int slot_i, double& v, int& ix)
+{
+    const double pv = red[slot_v * NWARP + (threadIdx.x & 7)];
+    int pi = (int)red[slot_i * NWARP + (threadIdx.x & 7)];
+    v = wargmax_d(pv, pi);
+    ix = pi;
 }
 
-template <int NV>
-__device__ __forceinline__ void block_max(double (&v)[NV], double* red, int tid)
-{
-    const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = warp_max(v[i]);
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) red[wid * RED_W + i] = v[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double s = red[i];
-#pragma unroll
-        for (int w = 1; w < NWARP; ++w) s = fmax(s, red[w * RED_W + i]);
-        v[i] = s;
-    }
-    __syncthreads();
-}
-
-// block-wide (max value, FIRST index) for NV candidates
-template <int NV>
-__device__ __forceinline__ void block_argmax(double (&v)[NV], int (&ix)[NV], double* red, int tid)
-{
-    static_assert(2 * NV <= RED_W, "reduction scratch too small");
-    const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) warp_argmax(v[i], ix[i]);
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            red[wid * RED_W + 2 * i] = v[i];
-            red[wid * RED_W + 2 * i + 1] = (double)ix[i];
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double bv = red[2 * i];
-        int bi = (int)red[2 * i + 1];
-#pragma unroll
-        for (int w = 1; w < NWARP; ++w) {
-            double ov = red[w * RED_W + 2 * i];
-            int oi = (int)red[w * RED_W + 2 * i + 1];
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        v[i] = bv;
-        ix[i] = bi;
-    }
-    __syncthreads();
-}
+// exact uint32 -> double without the conversion pipe: 2^52 + v has v in its low mantissa word
+__device__ __forceinline__ double u2d(uint32_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
 
 // run-length monoid for the saturation counters (src/saturation.jl:28-65)
 struct Run {
@@ -198,11 +209,15 @@ __device__ __forceinline__ double extrema3(double y1, double y2, double y3)
 }
 
 // ---- single-sample evaluations on the prefix sums TT (TT[i] = sum_{k<i} y[k]); used by the scalar tail ----
+__device__ __noinline__ double trap_eval(const double* TT, int a, int ag, int L, double inv1, double inv2, int j)
+{
+    const double s1 = TT[j + a] - TT[j];
+    const double s2 = TT[j + L] - TT[j + ag];
+    return s2 * inv2 - s1 * inv1;
+}
 __device__ __forceinline__ double trap_at(const double* TT, const TrapDev& t, int j)
 {
-    const double s1 = TT[j + t.a] - TT[j];
-    const double s2 = TT[j + t.L] - TT[j + t.a + t.g];
-    return s2 * t.inv2 - s1 * t.inv1;
+    return trap_eval(TT, t.a, t.a + t.g, t.L, t.inv1, t.inv2, j);
 }
 __device__ __forceinline__ double y_at(const double* TT, int i) { return TT[i + 1] - TT[i]; }
 __device__ __noinline__ double sg_at(const double* TT, const SgDev& s, int j)
@@ -340,44 +355,6 @@ __device__ __noinline__ double dni_eval_warp(const double* __restrict__ A, int n
 // ---------------------------------------------------------------------------------------------------
 // chunk passes over the prefix sums
 // ---------------------------------------------------------------------------------------------------
-// one trapezoid over the thread's chunk of outputs j in [j0, j0+CH): max, optional min (as max of -o), optional
-// first argmax, optional threshold masks for o >= thr and -o >= thr
-template <bool WANT_NEG, bool WANT_ARG, bool WANT_MASK>
-__device__ __forceinline__ void trap_chunk(const double* TT, const TrapDev& t, int j0, double thr, double& vmax, double& vneg,
-                                           int& arg, unsigned long long& bpos, unsigned long long& bneg)
-{
-    const int cnt = min(CH, t.nout - j0);
-    if (cnt <= 0) return;
-    const double* p0 = TT + j0;
-    const double* p1 = p0 + t.a;
-    const double* p2 = p1 + t.g;
-    const double* p3 = p0 + t.L;
-    const double inv1 = t.inv1, inv2 = t.inv2;
-    auto body = [&](int k) {
-        const double o = (p3[k] - p2[k]) * inv2 - (p1[k] - p0[k]) * inv1;
-        if (WANT_ARG) {
-            if (o > vmax) { vmax = o; arg = j0 + k; }
-        } else {
-            vmax = fmax(vmax, o);
-        }
-        if (WANT_NEG) vneg = fmax(vneg, -o);
-        if (WANT_MASK) {
-            bpos |= (o >= thr) ? (1ull << k) : 0ull;
-            bneg |= (-o >= thr) ? (1ull << k) : 0ull;
-        }
-    };
-    // modest unrolling only: the kernel must stay small enough for the instruction cache
-    int k = 0;
-#pragma unroll 1
-    for (; k + 3 <= cnt; k += 3) {
-        body(k);
-        body(k + 1);
-        body(k + 2);
-    }
-#pragma unroll 1
-    for (; k < cnt; ++k) body(k);
-}
-
 // sliding-window FIR on TT (the SG kernels folded onto the prefix sums): s[j] = sum_{q<NW} gg[q]*TT[j+q].
 // f(k, s) is called for every output j0+k of the chunk, k < cnt.
 template <int NW, typename F>
@@ -420,11 +397,11 @@ template <typename F>
 __device__ __forceinline__ void sg_chunk(const double* TT, const SgDev& S, int j0, int cnt, F&& f)
 {
     if (cnt <= 0) return;
-    switch (S.n_taps + 1) {
-        case 6: sg_chunk_t<6>(TT, S, j0, cnt, f); break;    // 5 taps
-        case 8: sg_chunk_t<8>(TT, S, j0, cnt, f); break;    // 7 taps
-        default:
-            for (int k = 0; k < cnt; ++k) f(k, sg_at(TT, S, j0 + k));
+    if (S.n_taps + 1 <= 8) {
+        // one 8-wide instantiation for every short kernel: gg is zero-padded and TT is finite (zero) beyond the trace
+        sg_chunk_t<8>(TT, S, j0, cnt, f);
+    } else {
+        for (int k = 0; k < cnt; ++k) f(k, sg_at(TT, S, j0 + k));
     }
 }
 
@@ -454,87 +431,76 @@ __device__ __forceinline__ double* cz_tab(double* tabA, double* tabB, int idx)
     return idx < 8 ? tabA + idx * NT : tabB + (idx - 8) * NT;
 }
 
-// block-wide scans of d over the whole waveform; fills the 16 decimated tables and *pp0 = P+[0]
+// block-wide scans of d over the whole waveform; fills the 16 decimated tables and *pp0 = P+[0].
+// One forward loop per chunk: P- (decayed prefix), D1, D2 (moments) and the partial sums acc = sum_{k'<=k} rho^k' d
+// of the anti-causal prefix (P+ at in-chunk offset o is (total - acc[o-1]) * rho^-o; the weights only span one
+// chunk, so nothing cancels).  The running values are stored at the capture events the host sorted by sample index.
 __device__ __noinline__ void cz_scan(const CzDev& Z, const double* TT, int n, int tid, double* tabA, double* tabB, double* red,
                         double* pp0)
 {
     const int lane = tid & 31, wid = tid >> 5;
     const int i0 = tid * CH;
     const double r = Z.r, rho = Z.rho;
-    double pm = 0, d1 = 0, d2 = 0, pp = 0;
-    double cpm[4] = {0, 0, 0, 0}, cd1[4] = {0, 0, 0, 0}, cd2[4] = {0, 0, 0, 0}, cpp[4] = {0, 0, 0, 0};
-    if (i0 < n) {
+    double pm = 0, d1 = 0, d2 = 0, acc = 0;
+    const bool live = i0 < n;
+    if (live) {
         const int cnt = min(CH, n - i0);
-        // forward: P-, D1, D2; captured at the 4 in-chunk offsets (sorted ascending on the host: segments, no
-        // per-sample compare); samples beyond the trace contribute d = 0
-        {
-            const double* p = TT + i0;
-            double tcur = p[0];
-            double yprev = (i0 >= 1) ? tcur - p[-1] : 0.0;
-            double di = (double)i0;
-            int k = 0;
+        const double* p = TT + i0 + 1;
+        double tcur = p[-1];
+        double yprev = (i0 >= 1) ? tcur - p[-2] : 0.0;
+        double di = (double)i0, w = 1.0;
+        auto step = [&](double d) {
+            pm = fma(rho, pm, d);
+            const double kd = di * d;
+            d1 += kd;
+            d2 = fma(di, kd, d2);
+            di += 1.0;
+            acc = fma(w, d, acc);
+            w *= rho;
+        };
+        int k = 0;
+        auto run_to = [&](int kend) {
+            if (cnt == CH) {
 #pragma unroll 1
-            for (int sgm = 0; sgm < 4; ++sgm) {
-                const int kend = Z.oc_sorted[sgm];
+                for (; k <= kend; ++k) {
+                    const double tnext = p[k];
+                    const double y = tnext - tcur;      // exact difference of neighbouring prefix sums
+                    const double d = fma(-r, yprev, y);
+                    yprev = y;
+                    tcur = tnext;
+                    step(d);
+                }
+            } else {
+                // last chunk of the trace: samples beyond the trace contribute d = 0
 #pragma unroll 1
                 for (; k <= kend; ++k) {
                     double d = 0.0;
                     if (k < cnt) {
-                        const double tnext = p[k + 1];
-                        const double y = tnext - tcur;      // exact difference of neighbouring prefix sums
+                        const double tnext = p[k];
+                        const double y = tnext - tcur;
                         d = fma(-r, yprev, y);
                         yprev = y;
                         tcur = tnext;
                     }
-                    pm = fma(rho, pm, d);
-                    d1 = fma(di, d, d1);
-                    d2 = fma(di * di, d, d2);
-                    di += 1.0;
+                    step(d);
                 }
-                cpm[sgm] = pm; cd1[sgm] = d1; cd2[sgm] = d2;
             }
+        };
 #pragma unroll 1
-            for (; k < CH; ++k) {
-                double d = 0.0;
-                if (k < cnt) {
-                    const double tnext = p[k + 1];
-                    const double y = tnext - tcur;
-                    d = fma(-r, yprev, y);
-                    yprev = y;
-                    tcur = tnext;
-                }
-                pm = fma(rho, pm, d);
-                d1 = fma(di, d, d1);
-                d2 = fma(di * di, d, d2);
-                di += 1.0;
+        for (int ev = 0; ev < Z.n_ev; ++ev) {
+            run_to(Z.ev_k[ev]);
+            const int tb = Z.ev_tab[ev];
+            if (Z.ev_kind[ev] == 0) {
+                cz_tab(tabA, tabB, tb * 3 + 0)[tid] = pm;
+                cz_tab(tabA, tabB, tb * 3 + 1)[tid] = d1;
+                cz_tab(tabA, tabB, tb * 3 + 2)[tid] = d2;
+            } else {
+                cz_tab(tabA, tabB, 12 + tb)[tid] = acc;
             }
         }
-        // backward: P+, captured at the 4 offsets sorted DESCENDING
-        {
-            const double* p = TT + i0;
-            double tn = p[cnt], tc = p[cnt - 1];
-            int k = CH - 1;
-            auto step = [&](int kk) {
-                double d = 0.0;
-                if (kk < cnt) {
-                    const double tp = (i0 + kk >= 1) ? p[kk - 1] : tc;   // sample 0: y[-1] = 0
-                    d = fma(-r, tc - tp, tn - tc);
-                    tn = tc;
-                    tc = tp;
-                }
-                pp = fma(rho, pp, d);
-            };
-#pragma unroll 1
-            for (int sgm = 0; sgm < 4; ++sgm) {
-                const int kend = Z.oa_sorted[sgm];
-#pragma unroll 1
-                for (; k >= kend; --k) step(k);
-                cpp[sgm] = pp;
-            }
-#pragma unroll 1
-            for (; k >= 0; --k) step(k);
-        }
+        run_to(CH - 1);
     }
+    const double pp = acc;   // P+ of the chunk alone at its first sample
     // warp-level scans (linear recurrences with constant multiplier rho^CH; plain sums for the moments)
     double vpm = pm, vd1 = d1, vd2 = d2, vpp = pp;
 #pragma unroll
@@ -558,19 +524,30 @@ __device__ __noinline__ void cz_scan(const CzDev& Z, const double* TT, int n, in
     if (lane == 0) c_pm = gpm;
     if (lane == 31) c_pp = gpp;
     const double c_d1 = gd1 + (vd1 - d1), c_d2 = gd2 + (vd2 - d2);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        // q = rank in the sorted order; the logical table index comes from the host (tab_c/tab_a)
-        cz_tab(tabA, tabB, Z.tab_c[q] * 3 + 0)[tid] = fma(Z.pw_c[q], c_pm, cpm[q]);
-        cz_tab(tabA, tabB, Z.tab_c[q] * 3 + 1)[tid] = cd1[q] + c_d1;
-        cz_tab(tabA, tabB, Z.tab_c[q] * 3 + 2)[tid] = cd2[q] + c_d2;
-        cz_tab(tabA, tabB, 12 + Z.tab_a[q])[tid] = fma(Z.pw_a[q], c_pp, cpp[q]);
+    // fix-up of this thread's own table entries: add the carried-in prefixes
+    if (live) {
+#pragma unroll 1
+        for (int ev = 0; ev < Z.n_ev; ++ev) {
+            const int tb = Z.ev_tab[ev];
+            const double pw = Z.ev_pw[ev];
+            if (Z.ev_kind[ev] == 0) {
+                double* t0 = cz_tab(tabA, tabB, tb * 3 + 0) + tid;
+                double* t1 = cz_tab(tabA, tabB, tb * 3 + 1) + tid;
+                double* t2 = cz_tab(tabA, tabB, tb * 3 + 2) + tid;
+                *t0 = fma(pw, c_pm, *t0);
+                *t1 += c_d1;
+                *t2 += c_d2;
+            } else {
+                double* t = cz_tab(tabA, tabB, 12 + tb) + tid;
+                *t = fma(pw, c_pp, (pp - *t) * Z.ev_rinv[ev]);
+            }
+        }
     }
     if (tid == 0) *pp0 = ipp;
 }
 
 // window states at m = CH*tid in closed form from the tables
-__device__ __noinline__ void cz_init(const CzDev& Z, const double* TT, int n, int tid, double* tabA, double* tabB, double pp0,
+__device__ __forceinline__ void cz_init(const CzDev& Z, const double* TT, int n, int tid, double* tabA, double* tabB, double pp0,
                         CzState& S)
 {
     const int m = tid * CH;
@@ -643,7 +620,7 @@ struct CzStream {
 };
 
 // CH recurrence steps; emits CUSP and/or ZAC outputs, tracks (max, first argmax), fills the pick-off windows
-__device__ __noinline__ void cz_run(const CzDev& Z, const double* TT, int n, int tid, CzState& S, bool want_cusp, bool want_zac,
+__device__ __forceinline__ void cz_run(const CzDev& Z, const double* TT, int n, int tid, CzState& S, bool want_cusp, bool want_zac,
                        int from_cusp, int from_zac, int n_w, double* stash_cusp, double* stash_zac, double (&czmax)[2],
                        int (&czarg)[2])
 {
@@ -693,13 +670,10 @@ __device__ __noinline__ void cz_run(const CzDev& Z, const double* TT, int n, int
     };
     // interior chunk: every stream index is inside the trace, every m is a valid output
     const bool interior = (m0 - L >= 1) && (m0 + CH + 1 <= n);
-    const int jlo = m0 - L + 1, jhi = jlo + CH - 1;
-    const bool touches_window = (want_cusp && jhi >= from_cusp && jlo < from_cusp + n_w) ||
-                                (want_zac && jhi >= from_zac && jlo < from_zac + n_w);
-    if (interior && !touches_window) {
+    if (interior) {
 #pragma unroll 3
         for (int k = 0; k < CH; ++k) {
-            emit(m0 + k, false);
+            emit(m0 + k, true);
             const double a = s0.next_fast(r, k), b = s1.next_fast(r, k), c = s2.next_fast(r, k), d = s3.next_fast(r, k);
             update(a, b, c, d);
         }
@@ -716,9 +690,71 @@ __device__ __noinline__ void cz_run(const CzDev& Z, const double* TT, int n, int
     }
 }
 
+// CUSP / ZAC outputs at the chunk start m0 = CH*tid from the closed-form state (the coarse grid of the pruning);
+// -inf where m0 is not a valid output
+__device__ __forceinline__ void cz_coarse(const CzDev& Z, const double* TT, int n, int tid, const CzState& S, double& oc, double& oz)
+{
+    const int m0 = tid * CH;
+    oc = -CUDART_INF;
+    oz = -CUDART_INF;
+    if (!S.active || m0 < Z.L - 1 || m0 >= n) return;
+    const double ylast = (m0 - Z.L >= 0) ? TT[m0 - Z.L + 1] - TT[m0 - Z.L] : 0.0;   // y[m0-L]
+    const double Dc = (S.EpL - S.EmL + S.EpR - S.EmR) + S.W0F;
+    oc = fma(Z.g, Dc, Z.gclast_cusp * ylast);
+    const double poly = (S.W2L - Z.h2 * S.W1L) + (S.V2 - Z.h2 * S.V1);
+    oz = fma(Z.g, fma(Z.B, poly, Dc), Z.gclast_zac * ylast);
+}
+
 // ==================================================================================================
 // the fused kernel
 // ==================================================================================================
+// the two full trapezoid traces (e_10410-like A, e_313-like B), outputs strided over the block: maximum and maximum
+// of the negated trace of each; the TT[j] stream is shared
+__device__ __noinline__ void trap_full2_minmax(const double* TT, const TrapDev& A, const TrapDev& B, int tid, double (&out)[4])
+{
+    double mxa = -CUDART_INF, mna = CUDART_INF, mxb = -CUDART_INF, mnb = CUDART_INF;
+    const double* p0 = TT + tid;
+    {
+        const double* a1 = p0 + A.a; const double* a2 = a1 + A.g; const double* a3 = p0 + A.L;
+        const double* b1 = p0 + B.a; const double* b2 = b1 + B.g; const double* b3 = p0 + B.L;
+        const double ai1 = A.inv1, ai2 = A.inv2, bi1 = B.inv1, bi2 = B.inv2;
+        const int cnt = min(A.nout, B.nout) - tid;
+        int off = 0;
+#pragma unroll 2
+        for (; off < cnt; off += NT) {
+            const double t0 = p0[off];
+            const double oa = (a3[off] - a2[off]) * ai2 - (a1[off] - t0) * ai1;
+            const double ob = (b3[off] - b2[off]) * bi2 - (b1[off] - t0) * bi1;
+            mxa = oa > mxa ? oa : mxa; mna = oa < mna ? oa : mna;
+            mxb = ob > mxb ? ob : mxb; mnb = ob < mnb ? ob : mnb;
+        }
+        // remainder of the longer trace
+        const bool a_longer = A.nout > B.nout;
+        const TrapDev& R = a_longer ? A : B;
+        const double* r1 = p0 + R.a; const double* r2 = r1 + R.g; const double* r3 = p0 + R.L;
+        const double ri1 = R.inv1, ri2 = R.inv2;
+        double mx = -CUDART_INF, mn = CUDART_INF;
+        const int cntr = R.nout - tid;
+#pragma unroll 1
+        for (; off < cntr; off += NT) {
+            const double o = (r3[off] - r2[off]) * ri2 - (r1[off] - p0[off]) * ri1;
+            mx = o > mx ? o : mx; mn = o < mn ? o : mn;
+        }
+        if (a_longer) { mxa = mx > mxa ? mx : mxa; mna = mn < mna ? mn : mna; }
+        else { mxb = mx > mxb ? mx : mxb; mnb = mn < mnb ? mn : mnb; }
+    }
+    out[0] = mxa; out[1] = -mna; out[2] = mxb; out[3] = -mnb;
+}
+
+// upper bound of a trace on the open interval between two coarse points 33 samples apart, from the Lipschitz
+// constant kap of the trace: a = value at the left point (always valid), b = value at the right point
+__device__ __forceinline__ double interval_bound(double a, double b, bool b_valid, double kap)
+{
+    return b_valid ? fma(0.5 * (double)CH, kap, 0.5 * (a + b)) : fma((double)(CH - 1), kap, a);
+}
+
+__device__ __noinline__ double log_d(double x) { return log(x); }
+
 __global__ void __launch_bounds__(NT, 2)
 icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, long long n_events, long long ld,
             double* __restrict__ rows)
@@ -733,6 +769,9 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
     double* scr = reinterpret_cast<double*>(smem + SM_SCR);
     int* ibuf = reinterpret_cast<int*>(smem + SM_IBUF);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+    double* czco = reinterpret_cast<double*>(masks + M_T10 * NWORDS);   // coarse CUSP/ZAC values [2][NT]
+    double* tabA = reinterpret_cast<double*>(smem + SM_XS);
+    double* tabB = reinterpret_cast<double*>(smem + SM_TAB);
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = P.n;
@@ -746,6 +785,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         mbar_init(bar, 1);
         fence_mbar_init();
     }
+    if (tid < TT_LEN - 1 - n) TT[n + 1 + tid] = 0.0;   // finite padding behind the trace (zero-padded SG kernels read it)
     __syncthreads();
     long long e = blockIdx.x;
     if (tid == 0 && e < n_events) {
@@ -755,27 +795,31 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
     uint32_t phase = 0;
     const int i0 = tid * CH;
     const int cvalid = max(0, min(CH, n - i0));
+    const unsigned long long chunk_all = (1ull << cvalid) - 1ull;   // cvalid <= 33
+    const bool cz_on = (G & LGDSP_GROUP_CUSPZAC) != 0;
+    const bool cz_structured = cz_on && !P.direct;
+    const int npass = cz_structured ? (P.cz_shared ? 1 : 2) : 0;
 
     for (; e < n_events; e += gridDim.x) {
-        // ------------------------------------------------------------------------------------------
-        // pass 1: raw samples
-        // ------------------------------------------------------------------------------------------
+        // ==========================================================================================
+        // P1: raw samples
+        // ==========================================================================================
         mbar_wait(bar, phase);
         phase ^= 1;
         const uint16_t* xp = xs + i0;
-        uint32_t csum = 0, cq = 0, mn = 0xFFFFu, mx = 0;
+        uint32_t csum = 0, cq = 0, cmn = 0xFFFFu, cmx = 0;
 #pragma unroll 3
         for (int k = 0; k < cvalid; ++k) {
             const uint32_t x = xp[k];
             csum += x;
             cq += csum;
-            mn = min(mn, x);
-            mx = max(mx, x);
+            cmn = min(cmn, x);
+            cmx = max(cmx, x);
         }
         // baseline regression sums (exact integers): only chunks that intersect the window
-        unsigned long long blSS = 0;
-        uint32_t blS = 0, blSK = 0;
         {
+            unsigned long long blSS = 0;
+            uint32_t blS = 0, blSK = 0;
             const int ka = max(0, P.bl_from - i0), kb = min(cvalid - 1, P.bl_until - i0);
 #pragma unroll 3
             for (int k = ka; k <= kb; ++k) {
@@ -784,59 +828,85 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 blSK += x * (uint32_t)k;
                 blSS += (unsigned long long)(x * x);   // 65535^2 < 2^32
             }
+            double a = 0.0, b = 0.0, c = 0.0;
+            if (__any_sync(FULL, ka <= kb)) {
+                // sum_i i*x = i0*sum x + sum k*x   (all exact in double)
+                a = wsum_d((double)blS);
+                b = wsum_d((double)blSS);
+                c = wsum_d((double)i0 * (double)blS + (double)blSK);
+            }
+            if (lane == 0) { red[R_BLS * NWARP + wid] = a; red[R_BLSS * NWARP + wid] = b; red[R_BLSX * NWARP + wid] = c; }
         }
         // saturation counts: a sample can only equal low/high if the chunk's min/max says so
         int nlow = 0, nhigh = 0;
-        if ((int)mn == P.sat_low || (int)mx == P.sat_high) {
+        if ((int)cmn == P.sat_low || (int)cmx == P.sat_high) {
             for (int k = 0; k < cvalid; ++k) {
                 const int x = xp[k];
                 nlow += (x == P.sat_low);
                 nhigh += (x == P.sat_high);
             }
         }
-        // block scan of the chunk sums -> exclusive prefix P_excl (exact, uint32)
-        uint32_t incl = csum;
+        {
+            const uint32_t wmn = __reduce_min_sync(FULL, cmn), wmx = __reduce_max_sync(FULL, cmx);
+            const uint32_t wl = __reduce_add_sync(FULL, (uint32_t)nlow), wh = __reduce_add_sync(FULL, (uint32_t)nhigh);
+            if (lane == 0) {
+                uint32_t* ured = reinterpret_cast<uint32_t*>(red + R_MX * NWARP);   // 4 x NWARP uint32 in the R_MX/R_MN slots
+                ured[wid] = wmx; ured[NWARP + wid] = wmn; ured[2 * NWARP + wid] = wl; ured[3 * NWARP + wid] = wh;
+            }
+        }
+        // one scan for P = cumsum(x) and PP = cumsum(P): segments (len, s = sum x, q = sum of the inclusive
+        // prefix sums inside the segment) combine as (lenA+lenB, sA+sB, qA+qB+lenB*sA); all values exact
+        int sl = cvalid;
+        uint32_t ss = csum;
+        double sq = (double)cq;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += t;
+            const int l2 = __shfl_up_sync(FULL, sl, o);
+            const uint32_t s2 = __shfl_up_sync(FULL, ss, o);
+            const double q2 = __shfl_up_sync(FULL, sq, o);
+            if (lane >= o) {
+                sq = q2 + sq + (double)sl * (double)s2;
+                ss += s2;
+                sl += l2;
+            }
         }
-        uint32_t* ured = reinterpret_cast<uint32_t*>(ibuf + IB_SCAN);
-        double* dscan = scr + SC_DSCAN;
-        if (lane == 31) ured[wid] = incl;
-        // zero the masks of this event while we are at it (committed with atomicOr later)
+        if (lane == 31) {
+            red[R_SLEN * NWARP + wid] = (double)sl;
+            red[R_SS * NWARP + wid] = (double)ss;
+            red[R_SQ * NWARP + wid] = sq;
+        }
+        int el = __shfl_up_sync(FULL, sl, 1);
+        uint32_t es = __shfl_up_sync(FULL, ss, 1);
+        double eq = __shfl_up_sync(FULL, sq, 1);
+        if (lane == 0) { el = 0; es = 0; eq = 0.0; }
+        // zero the masks of this event (committed with atomicOr later)
 #pragma unroll
         for (int q = 0; q < NMASK; ++q) masks[q * NWORDS + tid] = 0u;
-        double blSd, blSSd, blSXd;
+        __syncthreads();   // ---- B1 ----
+
+        // exclusive prefixes of this thread's chunk
+        uint32_t P_excl;
+        double PP_excl;
         {
-            // sum_i i*x = i0*sum x + sum k*x
-            double v[5] = {(double)blS, (double)blSS, (double)i0 * (double)blS + (double)blSK, (double)nlow, (double)nhigh};
-            block_sum<5>(v, red, tid);
-            blSd = v[0]; blSSd = v[1]; blSXd = v[2]; nlow = (int)v[3]; nhigh = (int)v[4];
+            double cs = 0.0, cqd = 0.0;
+#pragma unroll 1
+            for (int w = 0; w < wid; ++w) {
+                const double lw = red[R_SLEN * NWARP + w], sw = red[R_SS * NWARP + w], qw = red[R_SQ * NWARP + w];
+                cqd = cqd + qw + lw * cs;
+                cs += sw;
+            }
+            P_excl = (uint32_t)cs + es;
+            PP_excl = cqd + eq + (double)el * cs;
         }
-        uint32_t woff = 0;
-#pragma unroll
-        for (int w = 0; w < NWARP; ++w) woff += (w < wid) ? ured[w] : 0u;
-        const uint32_t P_excl = woff + incl - csum;
-        // second-order scan: PP_excl = sum over previous chunks of (cvalid*P_excl_c + cq_c)   (exact in double)
-        const double v2 = (double)cvalid * (double)P_excl + (double)cq;
-        double incl2 = v2;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            double t = __shfl_up_sync(FULL, incl2, o);
-            if (lane >= o) incl2 += t;
-        }
+        uint32_t mx, mn;
         {
-            double mm[2] = {(double)mx, -(double)mn};
-            if (lane == 31) dscan[wid] = incl2;
-            block_max<2>(mm, red, tid);
-            mx = (uint32_t)mm[0]; mn = (uint32_t)(-mm[1]);
+            const uint32_t* ured = reinterpret_cast<const uint32_t*>(red + R_MX * NWARP);
+            const int l8 = lane & 7;
+            mx = __reduce_max_sync(FULL, ured[l8]);
+            mn = __reduce_min_sync(FULL, ured[NWARP + l8]);
+            nlow = (int)__reduce_add_sync(FULL, lane < 8 ? ured[2 * NWARP + l8] : 0u);
+            nhigh = (int)__reduce_add_sync(FULL, lane < 8 ? ured[3 * NWARP + l8] : 0u);
         }
-        // (block_max's trailing __syncthreads makes the warp totals visible)
-        double woff2 = 0;
-#pragma unroll
-        for (int w = 0; w < NWARP; ++w) woff2 += (w < wid) ? dscan[w] : 0.0;
-        const double PP_excl = woff2 + incl2 - v2;
 
         // saturation run lengths (only when a saturated sample exists; block-uniform branch)
         int cons_low = 0, cons_high = 0;
@@ -862,8 +932,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 Run bl_ = run_shfl_down(rl, o), bh_ = run_shfl_down(rh, o);
                 if ((lane & (2 * o - 1)) == 0) { rl = run_merge(rl, bl_); rh = run_merge(rh, bh_); }
             }
-            int* ired = reinterpret_cast<int*>(red);
-            __syncthreads();
+            int* ired = reinterpret_cast<int*>(stash);   // stash is idle here
             if (lane == 0) {
                 ired[wid * 8 + 0] = rl.pre; ired[wid * 8 + 1] = rl.suf; ired[wid * 8 + 2] = rl.best; ired[wid * 8 + 3] = rl.len;
                 ired[wid * 8 + 4] = rh.pre; ired[wid * 8 + 5] = rh.suf; ired[wid * 8 + 6] = rh.best; ired[wid * 8 + 7] = rh.len;
@@ -882,90 +951,114 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
 
         // baseline statistics (exact sums) -> blmean
         const int bl_n = P.bl_until - P.bl_from + 1;
-        double bsX, bsXX;
-        xsums(P.bl_from, P.bl_until, t_first, dt, bsX, bsXX);
-        const Stats bl = stats_finalize(bl_n, bsX, bsXX, blSd, blSSd, t_first * blSd + dt * blSXd);
+        Stats bl;
+        {
+            double bsX, bsXX;
+            xsums(P.bl_from, P.bl_until, t_first, dt, bsX, bsXX);
+            const double blSd = red_sum(red, R_BLS), blSSd = red_sum(red, R_BLSS), blSXd = red_sum(red, R_BLSX);
+            bl = stats_finalize(bl_n, bsX, bsXX, blSd, blSSd, t_first * blSd + dt * blSXd);
+        }
         const double m = bl.mean;
         const double e_max = (double)mx - m, e_min = (double)mn - m;
         double thr[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) thr[k] = e_max * P.tx_frac[k];
 
-        // ------------------------------------------------------------------------------------------
-        // pass 2: pole-zero waveform, prefix sums, tail statistics, t10..t99 masks
-        // ------------------------------------------------------------------------------------------
-        double tl_S = 0, tl_SS = 0, tl_SX = 0, pz_S = 0, pz_SS = 0, pz_SX = 0, tl_bad = 0;
+        // ==========================================================================================
+        // P2: prefix sums of the pole-zero waveform; t10..t99 masks; tail log-regression
+        // ==========================================================================================
         {
-            unsigned long long mb[5] = {0, 0, 0, 0, 0};
-            uint32_t Pr = P_excl;
-            double PPr = PP_excl;
             const double km1 = P.km1;
-            double ip1 = (double)i0;                                  // becomes i+1 inside the loop
-            double tri = 0.5 * (double)i0 * ((double)i0 + 1.0);       // (i+1)(i+2)/2 after the update
-            double* tp = TT + i0 + 1;
-            const int ta = max(0, P.tail_from - i0), tb = min(cvalid - 1, P.tail_until - i0);
-            const bool has_tail = ta <= tb;
-            auto body = [&](int k, bool tail) {
-                const uint32_t x = xp[k];
-                Pr += x;
-                const double Pd = (double)Pr;
-                PPr += Pd;
-                ip1 += 1.0;
-                tri += ip1;
-                const double Sd = fma(-ip1, m, Pd);                // cumsum(w)[i]
-                const double w = (double)x - m;
-                const double y = fma(km1, Sd, w);                   // pole-zero corrected sample
-                const double SS = fma(-tri, m, PPr);                // cumsum(cumsum(w))[i]
-                tp[k] = fma(km1, SS, Sd);                           // cumsum(y)[i]
-#pragma unroll
-                for (int t = 0; t < 5; ++t) mb[t] |= (y >= thr[t]) ? (1ull << k) : 0ull;
-                if (tail && k >= ta && k <= tb) {
-                    const double X = t_first + (ip1 - 1.0) * dt;
-                    pz_S += y;
-                    pz_SS = fma(y, y, pz_SS);
-                    pz_SX = fma(X, y, pz_SX);
-                }
-            };
-            if (!has_tail) {
+            const double Sd0 = fma(-(double)i0, m, u2d(P_excl));                      // cumsum(w)[i0-1]
+            const double tri0 = 0.5 * (double)i0 * ((double)i0 + 1.0);
+            const double TT0 = fma(km1, fma(-tri0, m, PP_excl), Sd0);                 // TT[i0] (bit-identical to the neighbour's)
+            {
+                uint32_t Pr = P_excl;
+                double PPr = PP_excl;
+                double ip1 = (double)i0;                                  // becomes i+1 inside the loop
+                double tri = tri0;                                        // (i+1)(i+2)/2 after the update
+                double* tp = TT + i0 + 1;
+                auto body = [&](int k) {
+                    Pr += xp[k];
+                    const double Pd = u2d(Pr);
+                    PPr += Pd;
+                    ip1 += 1.0;
+                    tri += ip1;
+                    const double Sd = fma(-ip1, m, Pd);                // cumsum(w)[i]
+                    const double SS = fma(-tri, m, PPr);                // cumsum(cumsum(w))[i]
+                    tp[k] = fma(km1, SS, Sd);                           // cumsum(y)[i]
+                };
                 int k = 0;
 #pragma unroll 1
-                for (; k + 3 <= cvalid; k += 3) { body(k, false); body(k + 1, false); body(k + 2, false); }
+                for (; k + 3 <= cvalid; k += 3) { body(k); body(k + 1); body(k + 2); }
 #pragma unroll 1
-                for (; k < cvalid; ++k) body(k, false);
-            } else {
-#pragma unroll 1
-                for (int k = 0; k < cvalid; ++k) body(k, true);
+                for (; k < cvalid; ++k) body(k);
+                if (tid == 0) TT[0] = 0.0;
             }
-            if (tid == 0) TT[0] = 0.0;
-            if (G & LGDSP_GROUP_TIMING) {
+            // Conservative bounds of y = w + km1*cumsum(w) on the chunk from the integer min/max of the raw samples:
+            // cumsum(w)[i0+k] lies between S0 + (k+1)*wmin and S0 + (k+1)*wmax.
+            const double wmin = (double)cmn - m, wmax = (double)cmx - m;
+            const double ak = fabs(km1);
+            const double srange = (double)CH * fmax(fabs(wmin), fabs(wmax));
+            const double ylo = wmin + km1 * Sd0 - ak * srange, yhi = wmax + km1 * Sd0 + ak * srange;
+            const double guard = 1e-9 * (fabs(ylo) + fabs(yhi)) + 1e-6;   // >> rounding of the TT differences
+            // t10..t99: a chunk entirely below (above) a threshold contributes zeros (ones) without a compare
+            if ((G & LGDSP_GROUP_TIMING) && cvalid > 0) {
+                unsigned long long mb[5] = {0, 0, 0, 0, 0};
+                bool straddle = false;
 #pragma unroll
-                for (int q = 0; q < 5; ++q) mask_commit(masks + (M_T10 + q) * NWORDS, tid, mb[q]);
-            }
-            // tailstats: log-regression on the PRE-PZ waveform (src/tailstats.jl:22-72)
-            if (has_tail) {
+                for (int t = 0; t < 5; ++t) straddle |= !(ylo - guard >= thr[t]) && !(yhi + guard < thr[t]);
+                if (straddle) {
+                    const double* tp = TT + i0;
+                    double tprev = TT0;
 #pragma unroll 1
-                for (int k = ta; k <= tb; ++k) {
-                    const double w = (double)xp[k] - m;
-                    if (w <= 0.0) {
-                        tl_bad = 1.0;
-                    } else {
-                        const double X = t_first + (double)(i0 + k) * dt;
-                        const double lg = log(w);
-                        tl_S += lg;
-                        tl_SS = fma(lg, lg, tl_SS);
-                        tl_SX = fma(X, lg, tl_SX);
+                    for (int k = 0; k < cvalid; ++k) {
+                        const double tn = tp[k + 1];
+                        const double y = tn - tprev;
+                        tprev = tn;
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) mb[t] |= (y >= thr[t]) ? (1ull << k) : 0ull;
                     }
                 }
+#pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    if (ylo - guard >= thr[t]) mb[t] = chunk_all;
+                    else if (yhi + guard < thr[t]) mb[t] = 0ull;
+                    mask_commit(masks + (M_T10 + t) * NWORDS, tid, mb[t]);
+                }
+            }
+            // bound of max |y| over the block (Lipschitz constants of the pruning)
+            const double ya = wmax_d(cvalid > 0 ? fmax(fabs(ylo), fabs(yhi)) : 0.0);
+            red_put(red, R_YMAX, wid, lane, ya);
+        }
+        // tailstats: log-regression on the PRE-PZ waveform (src/tailstats.jl:22-72), samples strided over the block
+        {
+            double tl_S = 0, tl_SS = 0, tl_SX = 0;
+            bool bad = false;
+#pragma unroll 1
+            for (int idx = P.tail_from + tid; idx <= P.tail_until; idx += NT) {
+                const double w = u2d(xs[idx]) - m;
+                if (w <= 0.0) {
+                    bad = true;
+                } else {
+                    const double X = t_first + (double)idx * dt;
+                    const double lg = log_d(w);
+                    tl_S += lg;
+                    tl_SS = fma(lg, lg, tl_SS);
+                    tl_SX = fma(X, lg, tl_SX);
+                }
+            }
+            tl_S = wsum_d(tl_S); tl_SS = wsum_d(tl_SS); tl_SX = wsum_d(tl_SX);
+            const bool anybad = __any_sync(FULL, bad);
+            if (lane == 0) {
+                red[R_TLS * NWARP + wid] = tl_S; red[R_TLSS * NWARP + wid] = tl_SS;
+                red[R_TLSX * NWARP + wid] = tl_SX; red[R_TLBAD * NWARP + wid] = anybad ? 1.0 : 0.0;
             }
         }
-        {
-            double v[7] = {tl_S, tl_SS, tl_SX, pz_S, pz_SS, pz_SX, tl_bad};
-            block_sum<7>(v, red, tid);
-            tl_S = v[0]; tl_SS = v[1]; tl_SX = v[2]; pz_S = v[3]; pz_SS = v[4]; pz_SX = v[5]; tl_bad = v[6];
-        }
+        __syncthreads();   // ---- B2: TT and the t10..t99 masks are complete; xs is dead ----
+
         // xs is free now: prefetch the next event (TMA, async proxy) -- unless the structured CUSP/ZAC pass borrows
-        // xs for its prefix tables; then the prefetch is issued inside that pass
-        const bool cz_structured = (G & LGDSP_GROUP_CUSPZAC) && !P.direct;
+        // xs for its prefix tables; then the prefetch is issued when the tables are dead
         auto prefetch_next = [&]() {
             if (tid == 0) {
                 const long long en = e + gridDim.x;
@@ -978,13 +1071,124 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         };
         if (!cz_structured) prefetch_next();
 
-        // resolve t10..t99 now (t50 positions the energy pick-off windows)
+        // ==========================================================================================
+        // P3: work that only needs TT
+        // ==========================================================================================
+        // resolve t10..t99 (t50 positions the energy pick-off windows)
         if (wid < 5) {
             int pos, mult;
             resolve_runs(masks + (M_T10 + wid) * NWORDS, P.tx_min_n, lane, pos, mult);
             if (lane == 0) ibuf[IB_POS0 + M_T10 + wid] = pos;
         }
-        __syncthreads();
+        // PZ tail statistics (signalstats on the tail window, src/dsp_icpc.jl:123)
+        {
+            double pz_S = 0, pz_SS = 0, pz_SX = 0;
+#pragma unroll 2
+            for (int idx = P.tail_from + tid; idx <= P.tail_until; idx += NT) {
+                const double y = TT[idx + 1] - TT[idx];
+                const double X = t_first + (double)idx * dt;
+                pz_S += y;
+                pz_SS = fma(y, y, pz_SS);
+                pz_SX = fma(X, y, pz_SX);
+            }
+            pz_S = wsum_d(pz_S); pz_SS = wsum_d(pz_SS); pz_SX = wsum_d(pz_SX);
+            if (lane == 0) {
+                red[R_PZS * NWARP + wid] = pz_S; red[R_PZSS * NWARP + wid] = pz_SS; red[R_PZSX * NWARP + wid] = pz_SX;
+            }
+        }
+        // trapezoids whose minimum is needed as well: full traces
+        if (G & LGDSP_GROUP_TRAPS) {
+            double o4[4];
+            trap_full2_minmax(TT, P.e10410, P.e313, tid, o4);
+            const double a = wmax_d(o4[0]), b = wmax_d(o4[1]), c = wmax_d(o4[2]), d = wmax_d(o4[3]);
+            if (lane == 0) {
+                red[R_E104 * NWARP + wid] = a; red[R_E104N * NWARP + wid] = b;
+                red[R_E313 * NWARP + wid] = c; red[R_E313N * NWARP + wid] = d;
+            }
+        }
+        // coarse grid (outputs 33*tid and 33*(tid+1)) of the other trapezoids
+        double c0a = 0, c0b = 0, cia = 0, cib = 0, c5a = -CUDART_INF, c5b = -CUDART_INF, cea = -CUDART_INF, ceb = -CUDART_INF;
+        {
+            const int ja = i0, jb = i0 + CH;
+            if (G & LGDSP_GROUP_TIMING) {
+                if (ja < P.t0.nout) c0a = trap_at(TT, P.t0, ja);
+                if (jb < P.t0.nout) c0b = trap_at(TT, P.t0, jb);
+                if (!P.t0inv_same) {
+                    if (ja < P.t0inv.nout) cia = trap_at(TT, P.t0inv, ja);
+                    if (jb < P.t0inv.nout) cib = trap_at(TT, P.t0inv, jb);
+                }
+            }
+            if (G & LGDSP_GROUP_TRAPS) {
+                if (ja < P.e535.nout) c5a = trap_at(TT, P.e535, ja);
+                if (jb < P.e535.nout) c5b = trap_at(TT, P.e535, jb);
+                if (ja < P.etrap.nout) cea = trap_at(TT, P.etrap, ja);
+                if (jb < P.etrap.nout) ceb = trap_at(TT, P.etrap, jb);
+                const double w5 = wmax_d(c5a), we = wmax_d(cea);
+                red_put(red, R_C535, wid, lane, w5);
+                red_put(red, R_CET, wid, lane, we);
+            }
+        }
+        // currents: sg[0] over the whole trace (chunked, sliding window in registers): trace maximum, windowed first
+        // argmax, baseline-window sums; the chunk maximum is kept for the mask pass
+        double sgcmax = -CUDART_INF;
+        const int nsg = P.sg[0].nout;
+        if (G & LGDSP_GROUP_CURRENT) {
+            double cmax[4] = {-CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF};
+            int carg[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+            double sg_S = 0, sg_SS = 0;
+            {
+                const int cnt = min(CH, nsg - i0);
+                const int wa = P.cur_from[0] - i0, wb = P.cur_until[0] - i0;
+                const int sa = P.intr_from - i0, sb = P.intr_until - i0;
+                const bool plain = (wb < 0 || wa >= CH) && (sb < 0 || sa >= CH);   // no window touches this chunk
+                if (plain) {
+                    sg_chunk(TT, P.sg[0], i0, cnt, [&](int k, double s) { sgcmax = s > sgcmax ? s : sgcmax; });
+                } else {
+                    sg_chunk(TT, P.sg[0], i0, cnt, [&](int k, double s) {
+                        sgcmax = s > sgcmax ? s : sgcmax;
+                        if (k >= wa && k <= wb && s > cmax[0]) { cmax[0] = s; carg[0] = i0 + k; }
+                        if (k >= sa && k <= sb) { sg_S += s; sg_SS = fma(s, s, sg_SS); }
+                    });
+                }
+            }
+            // sg[1], sg[2] and the plain derivative are only needed inside the current window: strided
+#pragma unroll 1
+            for (int f = 1; f < 3; ++f) {
+                if (P.sg_alias[f] >= 0) continue;   // identical to an earlier filter: copied after the reduction
+                double bm = -CUDART_INF;
+                int ba = 0x7fffffff;
+#pragma unroll 1
+                for (int j = P.cur_from[f] + tid; j <= P.cur_until[f]; j += NT) {
+                    const double s = sg_at(TT, P.sg[f], j);
+                    if (s > bm) { bm = s; ba = j; }
+                }
+                cmax[f] = bm; carg[f] = ba;
+            }
+#pragma unroll 1
+            for (int j = P.cur_from[3] + tid; j <= P.cur_until[3]; j += NT) {
+                const double d = deriv_at(TT, j);
+                if (d > cmax[3]) { cmax[3] = d; carg[3] = j; }
+            }
+            const double wsm = wmax_d(sgcmax);
+            sg_S = wsum_d(sg_S); sg_SS = wsum_d(sg_SS);
+#pragma unroll
+            for (int f = 0; f < 4; ++f) cmax[f] = wargmax_d(cmax[f], carg[f]);
+            if (lane == 0) {
+                red[R_SGMAX * NWARP + wid] = wsm; red[R_SGS * NWARP + wid] = sg_S; red[R_SGSS * NWARP + wid] = sg_SS;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    red[(R_CMAX0 + f) * NWARP + wid] = cmax[f];
+                    red[(R_CARG0 + f) * NWARP + wid] = (double)carg[f];
+                }
+            }
+        }
+        // CUSP/ZAC prefix tables (first descriptor)
+        if (cz_structured) cz_scan(P.cz[0], TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
+        __syncthreads();   // ---- B3 ----
+
+        // ==========================================================================================
+        // P4a: decisions that need block-wide values; fine evaluation of the flagged intervals
+        // ==========================================================================================
         // t50 [us] and the DNI windows of the three energy pick-offs
         double t50_us = 0.0;
         {
@@ -1005,179 +1209,259 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 dni_window(P.sig_dni.n_w, n - Ls[f] + 1, (t50_us * 1000.0 + picks[f] - tf) / dt, pk_p[f], pk_from[f]);
             }
         }
+        const double Ymax = red_max(red, R_YMAX);     // bound of max |y| of the PZ waveform
+        const double kslack = 1e-7 * Ymax;            // >> float64 rounding of any trace
+        // the 44 trap(rt,ft) outputs of the e_trap pick-off window
+        if ((G & LGDSP_GROUP_TRAPS) && tid < P.sig_dni.n_w) stash[tid] = trap_at(TT, P.etrap, pk_from[0] + tid);
 
-        // ------------------------------------------------------------------------------------------
-        // pass 3: trapezoids and currents
-        // ------------------------------------------------------------------------------------------
-        double e10410 = -CUDART_INF, e10410n = -CUDART_INF, e535 = -CUDART_INF, e313 = -CUDART_INF, e313n = -CUDART_INF;
-        double etmax = -CUDART_INF;
-        int etarg = 0x7fffffff;
+        // ---- coarse-to-fine trapezoids: lane i of warp w owns the interval (33q, 33q+33), q = 32w + i ----
+        double e535 = c5a, etmax = cea;
+        int etarg = (cea > -CUDART_INF) ? i0 : 0x7fffffff;
         {
-            double dummy = 0;
-            int idummy = 0;
-            unsigned long long b0 = 0, b0i = 0, bd = 0;
+            bool f0 = false, fi = false, f5 = false, fe = false;
             if (G & LGDSP_GROUP_TIMING) {
-                double v = -CUDART_INF;
-                trap_chunk<false, false, true>(TT, P.t0, i0, P.t0_thr, v, dummy, idummy, b0, b0i);
-                if (!P.t0inv_same) {
-                    b0i = 0;
-                    trap_chunk<false, false, true>(TT, P.t0inv, i0, P.t0_thr, v, dummy, idummy, bd, b0i);
+                const double th = P.t0_thr;
+                const bool va = i0 < P.t0.nout, vb = i0 + CH < P.t0.nout;
+                // a run of >= min_n > 33 samples that overlaps the open interval contains one of its end points
+                const bool all = P.t0_min_n <= CH;
+                if (va) {
+                    const bool pa = c0a >= th, na = -c0a >= th;
+                    const bool pb = vb && (c0b >= th), nb = vb && (-c0b >= th);
+                    if (P.t0inv_same) {
+                        f0 = all || pa || pb || na || nb;
+                        mask_commit(masks + M_T0 * NWORDS, tid, pa ? 1ull : 0ull);
+                        mask_commit(masks + M_T0INV * NWORDS, tid, na ? 1ull : 0ull);
+                    } else {
+                        f0 = all || pa || pb;
+                        mask_commit(masks + M_T0 * NWORDS, tid, pa ? 1ull : 0ull);
+                    }
                 }
-                mask_commit(masks + M_T0 * NWORDS, tid, b0);
-                mask_commit(masks + M_T0INV * NWORDS, tid, b0i);
+                if (!P.t0inv_same) {
+                    const bool wa = i0 < P.t0inv.nout, wb = i0 + CH < P.t0inv.nout;
+                    if (wa) {
+                        const bool na = -cia >= th, nb = wb && (-cib >= th);
+                        fi = all || na || nb;
+                        mask_commit(masks + M_T0INV * NWORDS, tid, na ? 1ull : 0ull);
+                    }
+                }
             }
             if (G & LGDSP_GROUP_TRAPS) {
-                trap_chunk<true, false, false>(TT, P.e10410, i0, 0.0, e10410, e10410n, idummy, bd, bd);
-                trap_chunk<false, false, false>(TT, P.e535, i0, 0.0, e535, dummy, idummy, bd, bd);
-                trap_chunk<true, false, false>(TT, P.e313, i0, 0.0, e313, e313n, idummy, bd, bd);
-                trap_chunk<false, true, false>(TT, P.etrap, i0, 0.0, etmax, dummy, etarg, bd, bd);
+                const double M5 = red_max(red, R_C535), Me = red_max(red, R_CET);
+                const double k5 = Ymax * 2.0 * (P.e535.inv1 + P.e535.inv2) * 1.000001;
+                const double ke = Ymax * 2.0 * (P.etrap.inv1 + P.etrap.inv2) * 1.000001;
+                if (i0 + 1 < P.e535.nout) f5 = interval_bound(c5a, c5b, i0 + CH < P.e535.nout, k5) + kslack >= M5;
+                if (i0 + 1 < P.etrap.nout) fe = interval_bound(cea, ceb, i0 + CH < P.etrap.nout, ke) + kslack >= Me;
+            }
+            // every warp evaluates its own flagged intervals, 32 interior outputs = one per lane
+            unsigned b0 = __ballot_sync(FULL, f0), bi = __ballot_sync(FULL, fi);
+            unsigned b5 = __ballot_sync(FULL, f5), be = __ballot_sync(FULL, fe);
+            const double th = P.t0_thr;
+#pragma unroll 1
+            while (b0) {
+                const int i = __ffs(b0) - 1;
+                b0 &= b0 - 1;
+                const int j = (wid * 32 + i) * CH + 1 + lane;
+                const bool v = j < P.t0.nout;
+                const double o = v ? trap_at(TT, P.t0, j) : 0.0;
+                const unsigned mp = __ballot_sync(FULL, v && (o >= th));
+                const unsigned mn_ = __ballot_sync(FULL, v && (-o >= th));
+                if (lane == 0) {
+                    mask_commit(masks + M_T0 * NWORDS, wid * 32 + i, (unsigned long long)mp << 1);
+                    if (P.t0inv_same) mask_commit(masks + M_T0INV * NWORDS, wid * 32 + i, (unsigned long long)mn_ << 1);
+                }
+            }
+#pragma unroll 1
+            while (bi) {
+                const int i = __ffs(bi) - 1;
+                bi &= bi - 1;
+                const int j = (wid * 32 + i) * CH + 1 + lane;
+                const bool v = j < P.t0inv.nout;
+                const double o = v ? trap_at(TT, P.t0inv, j) : 0.0;
+                const unsigned mn_ = __ballot_sync(FULL, v && (-o >= th));
+                if (lane == 0) mask_commit(masks + M_T0INV * NWORDS, wid * 32 + i, (unsigned long long)mn_ << 1);
+            }
+#pragma unroll 1
+            while (b5) {
+                const int i = __ffs(b5) - 1;
+                b5 &= b5 - 1;
+                const int j = (wid * 32 + i) * CH + 1 + lane;
+                if (j < P.e535.nout) {
+                    const double o = trap_at(TT, P.e535, j);
+                    e535 = o > e535 ? o : e535;
+                }
+            }
+#pragma unroll 1
+            while (be) {
+                const int i = __ffs(be) - 1;
+                be &= be - 1;
+                const int j = (wid * 32 + i) * CH + 1 + lane;
+                if (j < P.etrap.nout) {
+                    const double o = trap_at(TT, P.etrap, j);
+                    if (o > etmax || (o == etmax && j < etarg)) { etmax = o; etarg = j; }
+                }
             }
         }
-        // currents: windowed first-argmax of the three SG traces and of the derivative; sg[0] full-trace stats
-        double cmax[4] = {-CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF};
-        int carg[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
-        double sg_max = -CUDART_INF, sg_S = 0, sg_SS = 0;
-        const int nsg = P.sg[0].nout;
+
+        // ---- masks on the sg[0] trace (t50_current, in-trace pile-up on the REVERSED trace): only chunks whose
+        //      maximum reaches the smaller threshold can contribute a bit; a warp evaluates its flagged chunks
+        //      with one output per lane (same operation order as the chunk pass: bit-identical values) ----
+        double pile_thr = 0.0, cur_thr = 0.0;
         if (G & LGDSP_GROUP_CURRENT) {
-            {
-                const int cnt = min(CH, nsg - i0);
-                const int wa = P.cur_from[0] - i0, wb = P.cur_until[0] - i0;
-                const int sa = P.intr_from - i0, sb = P.intr_until - i0;
-                const bool plain = (wb < 0 || wa >= CH) && (sb < 0 || sa >= CH);   // no window touches this chunk
-                if (plain) {
-                    sg_chunk(TT, P.sg[0], i0, cnt, [&](int k, double s) { sg_max = fmax(sg_max, s); });
-                } else {
-                    sg_chunk(TT, P.sg[0], i0, cnt, [&](int k, double s) {
-                        sg_max = fmax(sg_max, s);
-                        if (k >= wa && k <= wb && s > cmax[0]) { cmax[0] = s; carg[0] = i0 + k; }
-                        if (k >= sa && k <= sb) { sg_S += s; sg_SS = fma(s, s, sg_SS); }
-                    });
-                }
-            }
-#pragma unroll
-            for (int f = 1; f < 3; ++f) {
-                if (P.sg_alias[f] >= 0) continue;   // identical to an earlier filter: copied after the reduction
-                const int wa = P.cur_from[f] - i0, wb = P.cur_until[f] - i0;
-                if (wb >= 0 && wa < CH) {
-                    const int cnt = min(CH, P.sg[f].nout - i0);
-                    sg_chunk(TT, P.sg[f], i0, cnt, [&](int k, double s) {
-                        if (k >= wa && k <= wb && s > cmax[f]) { cmax[f] = s; carg[f] = i0 + k; }
-                    });
-                }
-            }
-            {
-                const int ka = max(0, P.cur_from[3] - i0), kb = min(cvalid - 1, P.cur_until[3] - i0);
-                for (int k = ka; k <= kb; ++k) {
-                    const double d = deriv_at(TT, i0 + k);
-                    if (d > cmax[3]) { cmax[3] = d; carg[3] = i0 + k; }
+            cur_thr = red_max(red, R_SGMAX) * 0.5;
+            const int cnt = P.intr_until - P.intr_from + 1;
+            double dX, dXX;
+            xsums(P.intr_from, P.intr_until, t_first + P.sg[0].offset * dt, dt, dX, dXX);
+            const double sS = red_sum(red, R_SGS), sSS = red_sum(red, R_SGSS);
+            const Stats st = stats_finalize(cnt, dX, dXX, sS, sSS, 0.0);
+            pile_thr = st.sigma * P.nsigma;
+            if (pile_thr == 0.0) pile_thr = 1.0;  // src/dsp_routines.jl:77
+            unsigned bf = __ballot_sync(FULL, sgcmax >= fmin(cur_thr, pile_thr));
+#pragma unroll 1
+            while (bf) {
+                const int i = __ffs(bf) - 1;
+                bf &= bf - 1;
+                const int q = wid * 32 + i;
+                const int j = q * CH + lane;
+                const bool v = j < nsg;
+                const double s = v ? sg_at(TT, P.sg[0], j) : 0.0;
+                unsigned long long bc = __ballot_sync(FULL, v && (s >= cur_thr));
+                unsigned long long bp = __ballot_sync(FULL, v && (s >= pile_thr));
+                if (lane == 0) {
+                    const int j2 = q * CH + 32;
+                    if (j2 < nsg) {
+                        const double s2 = sg_at(TT, P.sg[0], j2);
+                        bc |= (s2 >= cur_thr) ? (1ull << 32) : 0ull;
+                        bp |= (s2 >= pile_thr) ? (1ull << 32) : 0ull;
+                    }
+                    mask_commit(masks + M_CUR * NWORDS, q, bc);
+                    mask_commit_reversed(masks + M_PILE * NWORDS, q, bp, nsg);
                 }
             }
         }
-        // CUSP / ZAC, direct form (validation mode only)
+
+        // ---- CUSP / ZAC ----
         double czmax[2] = {-CUDART_INF, -CUDART_INF};
         int czarg[2] = {0x7fffffff, 0x7fffffff};
-        if ((G & LGDSP_GROUP_CUSPZAC) && P.direct) {
-#pragma unroll
+        if (cz_on && P.direct) {
+            // direct form (validation mode only)
+#pragma unroll 1
             for (int f = 0; f < 2; ++f) {
                 const int L = f ? P.zac_L : P.cusp_L;
                 const double* g = f ? P.zac_g : P.cusp_g;
                 const int nout = n - L + 1;
+                double bm = -CUDART_INF;
+                int ba = 0x7fffffff;
+#pragma unroll 1
                 for (int j = tid; j < nout; j += NT) {
                     const double o = fir_at(TT, g, L, j);
-                    if (o > czmax[f]) { czmax[f] = o; czarg[f] = j; }
+                    if (o > bm) { bm = o; ba = j; }
                     const int r = j - pk_from[1 + f];
                     if (r >= 0 && r < P.sig_dni.n_w) stash[(1 + f) * LGDSP_MAX_DNI + r] = o;
                 }
+                czmax[f] = bm; czarg[f] = ba;
             }
         }
-        // reductions of pass 3
-        {
-            double v[6] = {e10410, e10410n, e535, e313, e313n, sg_max};
-            block_max<6>(v, red, tid);
-            e10410 = v[0]; e10410n = v[1]; e535 = v[2]; e313 = v[3]; e313n = v[4]; sg_max = v[5];
-        }
-        {
-            double v[2] = {sg_S, sg_SS};
-            block_sum<2>(v, red, tid);
-            sg_S = v[0]; sg_SS = v[1];
-        }
-
-        // ------------------------------------------------------------------------------------------
-        // pass 4: masks on the sg[0] trace (t50_current, in-trace pile-up on the REVERSED trace)
-        // ------------------------------------------------------------------------------------------
-        double pile_thr = 0.0;
-        const double cur_thr = sg_max * 0.5;
-        if (G & LGDSP_GROUP_CURRENT) {
-            const int cnt = P.intr_until - P.intr_from + 1;
-            double dX, dXX;
-            xsums(P.intr_from, P.intr_until, t_first + P.sg[0].offset * dt, dt, dX, dXX);
-            const Stats st = stats_finalize(cnt, dX, dXX, sg_S, sg_SS, 0.0);
-            pile_thr = st.sigma * P.nsigma;
-            if (pile_thr == 0.0) pile_thr = 1.0;  // src/dsp_routines.jl:77
-            unsigned long long bc = 0, bp = 0;
-            sg_chunk(TT, P.sg[0], i0, min(CH, nsg - i0), [&](int k, double s) {
-                bc |= (s >= cur_thr) ? (1ull << k) : 0ull;
-                bp |= (s >= pile_thr) ? (1ull << k) : 0ull;
-            });
-            mask_commit(masks + M_CUR * NWORDS, tid, bc);
-            mask_commit_reversed(masks + M_PILE * NWORDS, tid, bp, nsg);
-        }
-        // the 44 trap(rt,ft) outputs of the e_trap pick-off window
-        if ((G & LGDSP_GROUP_TRAPS) && tid < P.sig_dni.n_w) stash[tid] = trap_at(TT, P.etrap, pk_from[0] + tid);
-
-        // ------------------------------------------------------------------------------------------
-        // CUSP / ZAC through their analytic structure
-        // ------------------------------------------------------------------------------------------
-        if (cz_structured) {
-            double* tabA = reinterpret_cast<double*>(smem + SM_XS);
-            double* tabB = reinterpret_cast<double*>(smem + SM_TAB);
-            const int npass = P.cz_shared ? 1 : 2;
-            for (int ps = 0; ps < npass; ++ps) {
-                const CzDev& Z = P.cz[ps];
-                const bool want_cusp = P.cz_shared || ps == 0, want_zac = P.cz_shared || ps == 1;
-                if (ps > 0) __syncthreads();  // previous pass finished reading the tables
-                cz_scan(Z, TT, n, tid, tabA, tabB, red, scr + SC_PP0);
+#pragma unroll 1
+        for (int ps = 0; ps < npass; ++ps) {
+            const CzDev& Z = P.cz[ps];
+            const bool want_cusp = P.cz_shared || ps == 0, want_zac = P.cz_shared || ps == 1;
+            if (ps > 0) {
+                __syncthreads();   // the previous pass is done with the tables and the coarse values
+                cz_scan(Z, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
                 __syncthreads();
-                CzState st;
-                cz_init(Z, TT, n, tid, tabA, tabB, scr[SC_PP0], st);
-                if (ps == npass - 1) {
-                    __syncthreads();       // every thread has read its table entries: xs may be overwritten
-                    prefetch_next();
+            }
+            CzState st;
+            cz_init(Z, TT, n, tid, tabA, tabB, scr[SC_PP0], st);
+            double oc, oz;
+            cz_coarse(Z, TT, n, tid, st, oc, oz);
+            if (!want_cusp) oc = -CUDART_INF;
+            if (!want_zac) oz = -CUDART_INF;
+            // the coarse points are outputs themselves
+            const int j0 = i0 - Z.L + 1;
+            if (oc > czmax[0]) { czmax[0] = oc; czarg[0] = j0; }
+            if (oz > czmax[1]) { czmax[1] = oz; czarg[1] = j0; }
+            czco[tid] = oc;
+            czco[NT + tid] = oz;
+            {
+                const double wc = wmax_d(oc), wz = wmax_d(oz);
+                red_put(red, R_CZC0, wid, lane, wc);
+                red_put(red, R_CZC1, wid, lane, wz);
+            }
+            __syncthreads();   // ---- B4 ----
+            if (ps == npass - 1) prefetch_next();   // every thread has read its table entries: xs may be overwritten
+            // candidate chunks: Lipschitz bound on (33 tid, 33 tid + 33) against the best coarse value; chunks that
+            // hold part of a pick-off window are always evaluated
+            const double Mc = red_max(red, R_CZC0), Mz = red_max(red, R_CZC1);
+            bool cand = false;
+            if (st.active) {
+                const int t1 = min(tid + 1, NT - 1);
+                const double kap = Ymax * 1.000001;
+                const int jlo = i0 - Z.L + 1, jhi = jlo + CH - 1;
+                if (want_cusp) {
+                    const double a = oc, b = (tid + 1 < NT) ? czco[t1] : -CUDART_INF;
+                    const double kc = kap * Z.lip_cusp;
+                    double bound;
+                    if (a > -CUDART_INF) bound = interval_bound(a, b, b > -CUDART_INF, kc);
+                    else if (b > -CUDART_INF) bound = fma((double)CH, kc, b);
+                    else bound = CUDART_INF;
+                    cand |= bound + 1e-6 * (fabs(Mc) + Ymax * fabs(Z.g)) >= Mc;
+                    cand |= (jhi >= pk_from[1] && jlo < pk_from[1] + P.sig_dni.n_w);
                 }
+                if (want_zac) {
+                    const double a = oz, b = (tid + 1 < NT) ? czco[NT + t1] : -CUDART_INF;
+                    const double kz = kap * Z.lip_zac;
+                    double bound;
+                    if (a > -CUDART_INF) bound = interval_bound(a, b, b > -CUDART_INF, kz);
+                    else if (b > -CUDART_INF) bound = fma((double)CH, kz, b);
+                    else bound = CUDART_INF;
+                    cand |= bound + 1e-6 * (fabs(Mz) + Ymax * fabs(Z.g)) >= Mz;
+                    cand |= (jhi >= pk_from[2] && jlo < pk_from[2] + P.sig_dni.n_w);
+                }
+            }
+            if (cand)
                 cz_run(Z, TT, n, tid, st, want_cusp, want_zac, pk_from[1], pk_from[2], P.sig_dni.n_w,
                        stash + LGDSP_MAX_DNI, stash + 2 * LGDSP_MAX_DNI, czmax, czarg);
+        }
+        if (npass == 0) __syncthreads();   // ---- B4 (no structured CUSP/ZAC) ----
+
+        // final partials
+        {
+            e535 = wmax_d(e535);
+            etmax = wargmax_d(etmax, etarg);
+            czmax[0] = wargmax_d(czmax[0], czarg[0]);
+            czmax[1] = wargmax_d(czmax[1], czarg[1]);
+            if (lane == 0) {
+                red[R_E535 * NWARP + wid] = e535;
+                red[R_ETMAX * NWARP + wid] = etmax; red[R_ETARG * NWARP + wid] = (double)etarg;
+                red[R_CZMAX0 * NWARP + wid] = czmax[0]; red[R_CZARG0 * NWARP + wid] = (double)czarg[0];
+                red[R_CZMAX1 * NWARP + wid] = czmax[1]; red[R_CZARG1 * NWARP + wid] = (double)czarg[1];
             }
         }
+        // crossing resolution: t0, t0_inv, t50_current, pile-up (one warp each; the masks were complete at B4)
         {
-            double v[7] = {etmax, cmax[0], cmax[1], cmax[2], cmax[3], czmax[0], czmax[1]};
-            int ix[7] = {etarg, carg[0], carg[1], carg[2], carg[3], czarg[0], czarg[1]};
-            block_argmax<7>(v, ix, red, tid);   // (its barriers also publish the masks and the stash)
-            etmax = v[0]; etarg = ix[0];
-#pragma unroll
-            for (int f = 0; f < 4; ++f) { cmax[f] = v[1 + f]; carg[f] = ix[1 + f]; }
-            czmax[0] = v[5]; czarg[0] = ix[5]; czmax[1] = v[6]; czarg[1] = ix[6];
-#pragma unroll
-            for (int f = 1; f < 3; ++f)
-                if (P.sg_alias[f] >= 0) { cmax[f] = cmax[P.sg_alias[f]]; carg[f] = carg[P.sg_alias[f]]; }
-        }
-        // crossing resolution: t0, t0_inv, t50_current, pile-up (one warp each)
-        if (wid < 4) {
-            const int which[4] = {M_T0, M_T0INV, M_CUR, M_PILE};
-            const int ks[4] = {P.t0_min_n, P.t0_min_n, P.tx_min_n, P.intr_min_n};
-            int pos, mult;
-            resolve_runs(masks + which[wid] * NWORDS, ks[wid], lane, pos, mult);
-            if (lane == 0) {
-                ibuf[IB_POS0 + which[wid]] = pos;
-                if (which[wid] == M_PILE) ibuf[IB_MULT] = mult;
+            const int slot = (wid == 0) ? 0 : (wid == 1) ? 1 : (wid == 6) ? 2 : (wid == 7) ? 3 : -1;
+            if (slot >= 0) {
+                const int which = (slot == 0) ? M_T0 : (slot == 1) ? M_T0INV : (slot == 2) ? M_CUR : M_PILE;
+                const int ks = (slot < 2) ? P.t0_min_n : (slot == 2) ? P.tx_min_n : P.intr_min_n;
+                int pos, mult;
+                resolve_runs(masks + which * NWORDS, ks, lane, pos, mult);
+                if (lane == 0) {
+                    ibuf[IB_POS0 + which] = pos;
+                    if (which == M_PILE) ibuf[IB_MULT] = mult;
+                }
             }
         }
         if (tid < 64) row[tid] = 0.0;
-        __syncthreads();
+        __syncthreads();   // ---- B6 ----
 
-        // ------------------------------------------------------------------------------------------
-        // pass 5: scalar results, spread over the warps; stage A
-        // ------------------------------------------------------------------------------------------
+        // ==========================================================================================
+        // P5: scalar results, spread over the warps; stage A
+        // ==========================================================================================
         if (wid == 0) {
+            // block-wide sums first (warp-collective), then lanes 0..2 finish the three statistics blocks
+            const double tlS = red_sum(red, R_TLS), tlSS = red_sum(red, R_TLSS), tlSX = red_sum(red, R_TLSX);
+            const double tlbad = red_sum(red, R_TLBAD);
+            const double pzS = red_sum(red, R_PZS), pzSS = red_sum(red, R_PZSS), pzSX = red_sum(red, R_PZSX);
             if (lane == 0) {
                 row[LGDSP_COL_blmean] = bl.mean; row[LGDSP_COL_blsigma] = bl.sigma;
                 row[LGDSP_COL_blslope] = bl.slope; row[LGDSP_COL_bloffset] = bl.offset;
@@ -1191,13 +1475,13 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 xsums(P.tail_from, P.tail_until, t_first, dt, tsX, tsXX);
                 if (lane == 1) {
                     // tailstats  src/tailstats.jl:22-72
-                    if (tl_bad == 0.0) {
-                        const Stats ts = stats_finalize(tn, tsX, tsXX, tl_S, tl_SS, tl_SX);
+                    if (tlbad == 0.0) {
+                        const Stats ts = stats_finalize(tn, tsX, tsXX, tlS, tlSS, tlSX);
                         row[LGDSP_COL_tail_mean] = ts.mean; row[LGDSP_COL_tail_sigma] = ts.sigma;
                         row[LGDSP_COL_tail_tau] = div_rn(-1.0, ts.slope);
                     }
                 } else {
-                    const Stats pz = stats_finalize(tn, tsX, tsXX, pz_S, pz_SS, pz_SX);
+                    const Stats pz = stats_finalize(tn, tsX, tsXX, pzS, pzSS, pzSX);
                     row[LGDSP_COL_tailmean] = pz.mean; row[LGDSP_COL_tailsigma] = pz.sigma;
                     row[LGDSP_COL_tailslope] = pz.slope; row[LGDSP_COL_tailoffset] = pz.offset;
                 }
@@ -1230,38 +1514,55 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         } else if (wid == 2) {
             if (G & LGDSP_GROUP_TRAPS) {
                 const double v = dni_eval_warp(A_sig, P.sig_dni.n_w, P.sig_dni.m, stash, pk_p[0] - (double)pk_from[0], lane);
+                double em;
+                int ea;
+                red_argmax(red, R_ETMAX, R_ETARG, em, ea);
+                const double a = red_max(red, R_E104), b = red_max(red, R_E535), c = red_max(red, R_E313);
+                const double d = red_max(red, R_E104N), f = red_max(red, R_E313N);
                 if (lane == 0) {
-                    row[LGDSP_COL_e_10410] = e10410; row[LGDSP_COL_e_535] = e535; row[LGDSP_COL_e_313] = e313;
-                    row[LGDSP_COL_e_10410_inv] = e10410n; row[LGDSP_COL_e_313_inv] = e313n;
-                    row[LGDSP_COL_e_trap_max] = etmax;
-                    row[LGDSP_COL_t_trap_max] = t_first + (double)(etarg + P.etrap.L - 1) * dt;
+                    row[LGDSP_COL_e_10410] = a; row[LGDSP_COL_e_535] = b; row[LGDSP_COL_e_313] = c;
+                    row[LGDSP_COL_e_10410_inv] = d; row[LGDSP_COL_e_313_inv] = f;
+                    row[LGDSP_COL_e_trap_max] = em;
+                    row[LGDSP_COL_t_trap_max] = t_first + (double)(ea + P.etrap.L - 1) * dt;
                     row[LGDSP_COL_e_trap] = v;
                 }
             }
         } else if (wid == 3 || wid == 4) {
-            if (G & LGDSP_GROUP_CUSPZAC) {
+            if (cz_on) {
                 const int f = wid - 3;
                 const double v = dni_eval_warp(A_sig, P.sig_dni.n_w, P.sig_dni.m, stash + (1 + f) * LGDSP_MAX_DNI,
                                                pk_p[1 + f] - (double)pk_from[1 + f], lane);
+                double cm;
+                int ca;
+                red_argmax(red, f ? R_CZMAX1 : R_CZMAX0, f ? R_CZARG1 : R_CZARG0, cm, ca);
                 if (lane == 0) {
                     const int L = f ? P.zac_L : P.cusp_L;
-                    row[f ? LGDSP_COL_e_zac_max : LGDSP_COL_e_cusp_max] = czmax[f];
-                    row[f ? LGDSP_COL_t_zac_max : LGDSP_COL_t_cusp_max] = t_first + (double)(czarg[f] + L - 1) * dt;
+                    row[f ? LGDSP_COL_e_zac_max : LGDSP_COL_e_cusp_max] = cm;
+                    row[f ? LGDSP_COL_t_zac_max : LGDSP_COL_t_cusp_max] = t_first + (double)(ca + L - 1) * dt;
                     row[f ? LGDSP_COL_e_zac : LGDSP_COL_e_cusp] = v;
                 }
             }
         } else if (wid == 5) {
-            if (lane < 4 && (G & LGDSP_GROUP_CURRENT)) {
+            if (G & LGDSP_GROUP_CURRENT) {
                 // get_wvf_maximum  src/interpolation.jl:30-46: parabola only if strictly inside the window
-                const int f = lane;
-                const int a = carg[f];
-                double v = cmax[f];
-                if (a > P.cur_from[f] && a < P.cur_until[f]) {
-                    const double y1 = (f < 3) ? sg_at(TT, P.sg[f], a - 1) : deriv_at(TT, a - 1);
-                    const double y3 = (f < 3) ? sg_at(TT, P.sg[f], a + 1) : deriv_at(TT, a + 1);
-                    v = extrema3(y1, v, y3);
+                double vv[4];
+                int aa[4];
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const int fs = (f < 3 && P.sg_alias[f] >= 0) ? P.sg_alias[f] : f;   // aliased filter: same trace and window
+                    red_argmax(red, R_CMAX0 + fs, R_CARG0 + fs, vv[f], aa[f]);
                 }
-                row[LGDSP_COL_a_sg + f] = v;
+                if (lane < 4) {
+                    const int f = lane;
+                    double v = f == 0 ? vv[0] : f == 1 ? vv[1] : f == 2 ? vv[2] : vv[3];
+                    const int a = f == 0 ? aa[0] : f == 1 ? aa[1] : f == 2 ? aa[2] : aa[3];
+                    if (a > P.cur_from[f] && a < P.cur_until[f]) {
+                        const double y1 = (f < 3) ? sg_at(TT, P.sg[f], a - 1) : deriv_at(TT, a - 1);
+                        const double y3 = (f < 3) ? sg_at(TT, P.sg[f], a + 1) : deriv_at(TT, a + 1);
+                        v = extrema3(y1, v, y3);
+                    }
+                    row[LGDSP_COL_a_sg + f] = v;
+                }
             }
         } else if (wid == 6) {
             if (lane < 2 && (G & LGDSP_GROUP_CURRENT)) {
@@ -1289,7 +1590,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();   // ---- B7 ----
         // stage B: what needs t0 / t80 / t90
         if (wid < 2) {
             if (G & LGDSP_GROUP_QDRIFT) {
@@ -1297,7 +1598,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 const double tns = (wid == 0 ? scr[SC_T0] : scr[SC_TX + 2]) * 1000.0;
                 const double first = wid == 0 ? P.qd_first : P.lq_first, last = wid == 0 ? P.qd_last : P.lq_last;
                 double a[3];
-#pragma unroll
+#pragma unroll 1
                 for (int s = 0; s < 3; ++s) {
                     const double ts = s == 0 ? tns : (s == 1 ? tns + first : tns + last);
                     double pc;
@@ -1313,9 +1614,9 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         } else if (wid == 2) {
             if (lane == 0 && (G & LGDSP_GROUP_TIMING)) row[LGDSP_COL_drift_time] = (scr[SC_TX + 3] - scr[SC_T0]) * 1000.0;
         }
-        __syncthreads();
+        __syncthreads();   // ---- B8 ----
         if (tid < LGDSP_NCOL) rows[e * LGDSP_NCOL + tid] = row[tid];
-        // (the next iteration's first barrier orders the reuse of row/stash/masks/scr)
+        // (the next iteration's first barrier orders the reuse of row/stash/masks/scr/red)
     }
 }
 
@@ -1326,6 +1627,32 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
 // stay resident in SMEM and every (rt, ft) variant only evaluates the n_w trapezoid outputs of its
 // PolynomialDNI window (4 look-ups each).  One warp per variant.
 // ==================================================================================================
+constexpr int RED_W = 24;
+// block-wide sum / max of one double (two barriers); every thread gets the result
+__device__ __forceinline__ double block_sum1(double v, double* red, int tid)
+{
+    const int lane = tid & 31, wid = tid >> 5;
+    v = warp_sum(v);
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) s += red[w];
+    __syncthreads();
+    return s;
+}
+__device__ __forceinline__ double block_max1(double v, double* red, int tid)
+{
+    const int lane = tid & 31, wid = tid >> 5;
+    v = warp_max(v);
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double s = red[0];
+#pragma unroll
+    for (int w = 1; w < NWARP; ++w) s = fmax(s, red[w]);
+    __syncthreads();
+    return s;
+}
 constexpr int SW_XS = 0;
 constexpr int SW_TT = SW_XS + MAXN * 2;
 constexpr int SW_MASK = SW_TT + TT_LEN * 8;
@@ -1391,14 +1718,12 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
             uint32_t t = __shfl_up_sync(FULL, incl, o);
             if (lane >= o) incl += t;
         }
-        uint32_t* ured = reinterpret_cast<uint32_t*>(ibuf + IB_SCAN);
+        uint32_t* ured = reinterpret_cast<uint32_t*>(ibuf + 32);
         if (lane == 31) ured[wid] = incl;
         mask[tid] = 0u;
         double blSd;
         {
-            double v[1] = {(double)blS};
-            block_sum<1>(v, red, tid);
-            blSd = v[0];
+            blSd = block_sum1((double)blS, red, tid);
         }
         uint32_t woff = 0;
 #pragma unroll
@@ -1451,9 +1776,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
         }
         if (tid == 0) TT[0] = 0.0;
         {
-            double v[1] = {ymax};
-            block_max<1>(v, red, tid);
-            ymax = v[0];
+            ymax = block_max1(ymax, red, tid);
         }
         if (tid == 0) {
             const long long en = e + gridDim.x;
