@@ -21,11 +21,13 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, profile=False):
+    """profile=True adds -DLGDSP_PROFILE_SECTIONS (per-section cycle counters, tools/phase_cycles.py); not for benchmarks"""
     if not force and not needs_build():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + list(SOURCES)
+    cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DLGDSP_PROFILE_SECTIONS"] if profile else [])
+           + ["-o", OUT] + list(SOURCES))
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -36,4 +38,4 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_library(force="--force" in sys.argv or "--profile" in sys.argv, verbose=True, profile="--profile" in sys.argv))

@@ -23,6 +23,9 @@ struct lgdsp_handle {
     double* d_cusp_g = nullptr;    // [LGDSP_MAX_FIR+1]
     double* d_zac_g = nullptr;     // [LGDSP_MAX_FIR+1]
     double* d_sweep_dniA = nullptr;
+    unsigned long long* d_phase = nullptr;   // [grid][8] phase cycle counters (debug)
+    int phase_grid = 0;
+    bool phase_on = false;
     SweepVar* d_vars = nullptr;
     int vars_cap = 0;
     IcpcDev icpc{};
@@ -123,6 +126,7 @@ void lgdsp_destroy(lgdsp_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_phase);
     cudaFree(h->d_dniA); cudaFree(h->d_cusp_g); cudaFree(h->d_zac_g); cudaFree(h->d_sweep_dniA); cudaFree(h->d_vars);
     cudaFree(h->d_in[0]); cudaFree(h->d_in[1]); cudaFree(h->d_rows); cudaFree(h->d_sweep_out);
     for (int i = 0; i < 2; ++i) {
@@ -409,8 +413,16 @@ int lgdsp_icpc_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const uin
     if (!d_out_rows) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
     const long long cap = (long long)h->sm_count * h->icpc_bps;
     const int grid = (int)(n_events < cap ? n_events : cap);
+    IcpcDev D = h->icpc;
+    D.phase_cycles = nullptr;
+    if (h->phase_on) {
+        if (!h->d_phase) CK(cudaMalloc(&h->d_phase, sizeof(unsigned long long) * (8 * (size_t)cap + 32 * 8)));
+        CK(cudaMemsetAsync(h->d_phase, 0, sizeof(unsigned long long) * (8 * (size_t)cap + 32 * 8), h->stream));
+        D.phase_cycles = h->d_phase;
+        h->phase_grid = grid;
+    }
     CK(cudaEventRecord(h->ev0, h->stream));
-    icpc_launch(h->icpc, d_wf, n_events, ld_samples, d_out_rows, grid, h->stream);
+    icpc_launch(D, d_wf, n_events, ld_samples, d_out_rows, grid, h->stream);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
@@ -471,6 +483,40 @@ int lgdsp_icpc_run(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* 
     }
     CK(cudaStreamSynchronize(h->s_copy));
     CK(cudaStreamSynchronize(h->stream));
+    return LGDSP_OK;
+}
+
+// debug: per-phase cycle counters of the last lgdsp_icpc_run_device call (sum over CTAs; index 0: TMA wait,
+// 1..6: P1, P2, P3, P4a, P4b, P5, see lgdsp_icpc.cu).  enable != 0 switches the counters on for later calls.
+int lgdsp_debug_phase_cycles(lgdsp_handle* h, int enable, double* out8)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (out8) {
+        for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+        if (h->d_phase && h->phase_grid > 0) {
+            CK(cudaStreamSynchronize(h->stream));
+            std::vector<unsigned long long> v((size_t)h->phase_grid * 8);
+            CK(cudaMemcpy(v.data(), h->d_phase, v.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            for (int b = 0; b < h->phase_grid; ++b)
+                for (int i = 0; i < 8; ++i) out8[i] += (double)v[(size_t)b * 8 + i];
+        }
+    }
+    h->phase_on = enable != 0;
+    return LGDSP_OK;
+}
+
+// debug (library built with -DLGDSP_PROFILE_SECTIONS only): cycles per (section, warp) of the last run, out[32*8]
+int lgdsp_debug_section_cycles(lgdsp_handle* h, double* out256)
+{
+    if (!h || !out256) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    for (int i = 0; i < 256; ++i) out256[i] = 0.0;
+    if (!h->d_phase || h->phase_grid <= 0) return LGDSP_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned long long v[256];
+    CK(cudaMemcpy(v, h->d_phase + (size_t)h->phase_grid * 8, sizeof(v), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 256; ++i) out256[i] = (double)v[i];
     return LGDSP_OK;
 }
 

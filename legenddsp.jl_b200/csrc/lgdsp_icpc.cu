@@ -74,7 +74,12 @@ constexpr int SM_ROW = SM_TAB + 8 * NT * 8;                // double row[64]
 constexpr int SM_SCR = SM_ROW + 64 * 8;                    // double scr[32]: scalars passed between warps
 constexpr int SM_IBUF = SM_SCR + 32 * 8;                   // int ibuf[64]
 constexpr int SM_BAR = SM_IBUF + 64 * 4;                   // uint64 mbarrier
-constexpr int SM_TOTAL = SM_BAR + 16;
+constexpr int SM_PAR = SM_BAR + 16;                        // SmemPar: parameter tables read by the noinline helpers
+struct SmemPar {
+    CzDev cz[2];
+    double sgg[3][8];      // zero-padded SG taps folded on TT (filters with <= 7 taps)
+};
+constexpr int SM_TOTAL = SM_PAR + (int)sizeof(SmemPar);
 static_assert(2 * (SM_TOTAL + 1024) <= 233472, "two CTAs per SM");
 static_assert(2 * NT * 8 <= 5 * NWORDS * 4, "coarse CUSP/ZAC values fit into the T10..T99 mask area");
 
@@ -220,14 +225,24 @@ __device__ __forceinline__ double trap_at(const double* TT, const TrapDev& t, in
     return trap_eval(TT, t.a, t.a + t.g, t.L, t.inv1, t.inv2, j);
 }
 __device__ __forceinline__ double y_at(const double* TT, int i) { return TT[i + 1] - TT[i]; }
-__device__ __noinline__ double sg_at(const double* TT, const SgDev& s, int j)
+__device__ __noinline__ double sg_eval(const double* TT, const double* gg, int n_taps, int j)
 {
     double a0 = 0, a1 = 0;   // same association as sg_chunk_t
 #pragma unroll 1
-    for (int k = 0; k <= s.n_taps; k += 2) {
-        a0 = fma(s.gg[k], TT[j + k], a0);
-        if (k + 1 <= s.n_taps) a1 = fma(s.gg[k + 1], TT[j + k + 1], a1);
+    for (int k = 0; k <= n_taps; k += 2) {
+        a0 = fma(gg[k], TT[j + k], a0);
+        if (k + 1 <= n_taps) a1 = fma(gg[k + 1], TT[j + k + 1], a1);
     }
+    return a0 + a1;
+}
+// 8-tap version for the zero-padded SMEM copy of a short kernel (bit-identical to sg_eval / sg_chunk_t<8>)
+__device__ __noinline__ double sg_eval8(const double* TT, const double* gg, int j)
+{
+    const double* p = TT + j;
+    double a0 = gg[0] * p[0], a1 = gg[1] * p[1];
+    a0 = fma(gg[2], p[2], a0); a1 = fma(gg[3], p[3], a1);
+    a0 = fma(gg[4], p[4], a0); a1 = fma(gg[5], p[5], a1);
+    a0 = fma(gg[6], p[6], a0); a1 = fma(gg[7], p[7], a1);
     return a0 + a1;
 }
 // DerivativeFilter sample i  (src/derivative.jl:47-55)
@@ -401,7 +416,7 @@ __device__ __forceinline__ void sg_chunk(const double* TT, const SgDev& S, int j
         // one 8-wide instantiation for every short kernel: gg is zero-padded and TT is finite (zero) beyond the trace
         sg_chunk_t<8>(TT, S, j0, cnt, f);
     } else {
-        for (int k = 0; k < cnt; ++k) f(k, sg_at(TT, S, j0 + k));
+        for (int k = 0; k < cnt; ++k) f(k, sg_eval(TT, S.gg, S.n_taps, j0 + k));
     }
 }
 
@@ -435,9 +450,10 @@ __device__ __forceinline__ double* cz_tab(double* tabA, double* tabB, int idx)
 // One forward loop per chunk: P- (decayed prefix), D1, D2 (moments) and the partial sums acc = sum_{k'<=k} rho^k' d
 // of the anti-causal prefix (P+ at in-chunk offset o is (total - acc[o-1]) * rho^-o; the weights only span one
 // chunk, so nothing cancels).  The running values are stored at the capture events the host sorted by sample index.
-__device__ __noinline__ void cz_scan(const CzDev& Z, const double* TT, int n, int tid, double* tabA, double* tabB, double* red,
+__device__ __noinline__ void cz_scan(const CzDev* Zp, const double* TT, int n, int tid, double* tabA, double* tabB, double* red,
                         double* pp0)
 {
+    const CzDev& Z = *Zp;   // SMEM copy of the descriptor (a reference to the kernel parameter would force generic loads)
     const int lane = tid & 31, wid = tid >> 5;
     const int i0 = tid * CH;
     const double r = Z.r, rho = Z.rho;
@@ -710,7 +726,7 @@ __device__ __forceinline__ void cz_coarse(const CzDev& Z, const double* TT, int 
 // ==================================================================================================
 // the two full trapezoid traces (e_10410-like A, e_313-like B), outputs strided over the block: maximum and maximum
 // of the negated trace of each; the TT[j] stream is shared
-__device__ __noinline__ void trap_full2_minmax(const double* TT, const TrapDev& A, const TrapDev& B, int tid, double (&out)[4])
+__device__ __forceinline__ void trap_full2_minmax(const double* TT, const TrapDev& A, const TrapDev& B, int tid, double (&out)[4])
 {
     double mxa = -CUDART_INF, mna = CUDART_INF, mxb = -CUDART_INF, mnb = CUDART_INF;
     const double* p0 = TT + tid;
@@ -754,6 +770,32 @@ __device__ __forceinline__ double interval_bound(double a, double b, bool b_vali
 }
 
 __device__ __noinline__ double log_d(double x) { return log(x); }
+// log1p(u) for |u| <= 1/8: Taylor series to u^17 (truncation < 3e-17 relative), Horner
+__device__ __noinline__ double log1p_small(double u)
+{
+    double p = 1.0 / 17.0;
+    p = fma(p, u, -1.0 / 16.0); p = fma(p, u, 1.0 / 15.0); p = fma(p, u, -1.0 / 14.0); p = fma(p, u, 1.0 / 13.0);
+    p = fma(p, u, -1.0 / 12.0); p = fma(p, u, 1.0 / 11.0); p = fma(p, u, -1.0 / 10.0); p = fma(p, u, 1.0 / 9.0);
+    p = fma(p, u, -1.0 / 8.0); p = fma(p, u, 1.0 / 7.0); p = fma(p, u, -1.0 / 6.0); p = fma(p, u, 1.0 / 5.0);
+    p = fma(p, u, -1.0 / 4.0); p = fma(p, u, 1.0 / 3.0); p = fma(p, u, -0.5); p = fma(p, u, 1.0);
+    return p * u;
+}
+// threshold mask of one chunk of the PZ waveform: bit k = (y[i0+k] >= th), y from the prefix sums (tt0 = TT[i0])
+__device__ __noinline__ unsigned long long mask_chunk(const double* tp, double tt0, int cvalid, double th)
+{
+    uint32_t lo = 0;
+    double tprev = tt0;
+    const int c32 = min(cvalid, 32);
+#pragma unroll 1
+    for (int k = 0; k < c32; ++k) {
+        const double tn = tp[k + 1];
+        lo |= ((tn - tprev) >= th) ? (1u << k) : 0u;
+        tprev = tn;
+    }
+    unsigned long long m = lo;
+    if (cvalid > 32 && (tp[33] - tprev) >= th) m |= 1ull << 32;
+    return m;
+}
 
 __global__ void __launch_bounds__(NT, 2)
 icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, long long n_events, long long ld,
@@ -786,7 +828,20 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         fence_mbar_init();
     }
     if (tid < TT_LEN - 1 - n) TT[n + 1 + tid] = 0.0;   // finite padding behind the trace (zero-padded SG kernels read it)
+    SmemPar* spar = reinterpret_cast<SmemPar*>(smem + SM_PAR);
+    {
+        // parameter tables used by noinline helpers: SMEM copies (once per CTA; the kernel is persistent)
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.cz[0]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&spar->cz[0]);
+        for (int i = tid; i < (int)(2 * sizeof(CzDev) / 4); i += NT) dst[i] = src[i];
+        if (tid < 24) spar->sgg[tid >> 3][tid & 7] = P.sg[tid >> 3].gg[tid & 7];
+    }
     __syncthreads();
+    const bool sg_short0 = P.sg[0].n_taps + 1 <= 8;
+    // SG trace sample j of filter f
+    auto sg_at = [&](int f, int j) -> double {
+        return (P.sg[f].n_taps + 1 <= 8) ? sg_eval8(TT, spar->sgg[f], j) : sg_eval(TT, P.sg[f].gg, P.sg[f].n_taps, j);
+    };
     long long e = blockIdx.x;
     if (tid == 0 && e < n_events) {
         mbar_expect_tx(bar, wf_bytes);
@@ -800,12 +855,31 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
     const bool cz_structured = cz_on && !P.direct;
     const int npass = cz_structured ? (P.cz_shared ? 1 : 2) : 0;
 
+    // optional phase timing (debug): thread 0 accumulates barrier-to-barrier cycles
+    unsigned long long* pc_acc = reinterpret_cast<unsigned long long*>(scr + 20);   // [9]: 8 counters + last clock (SMEM)
+    const bool pc_on = (P.phase_cycles != nullptr) && tid == 0;
+#define LGDSP_PHASE(i) do { if (pc_on) { const unsigned long long now_ = (unsigned long long)clock64(); pc_acc[i] += now_ - pc_acc[8]; pc_acc[8] = now_; } } while (0)
+    if (pc_on) {
+        for (int i = 0; i < 8; ++i) pc_acc[i] = 0ull;
+        pc_acc[8] = (unsigned long long)clock64();
+    }
+#ifdef LGDSP_PROFILE_SECTIONS
+    // per-(section, warp) cycle sums (debug build only): lane 0 of every warp, global atomics behind the phase counters
+    unsigned long long sect_last = (unsigned long long)clock64();
+#define SECT(i) do { if (P.phase_cycles != nullptr && lane == 0) { const unsigned long long now_ = (unsigned long long)clock64(); \
+        atomicAdd(&P.phase_cycles[(size_t)gridDim.x * 8 + (i) * 8 + wid], now_ - sect_last); sect_last = now_; } } while (0)
+#else
+#define SECT(i) do { } while (0)
+#endif
+
     for (; e < n_events; e += gridDim.x) {
         // ==========================================================================================
         // P1: raw samples
         // ==========================================================================================
         mbar_wait(bar, phase);
         phase ^= 1;
+        LGDSP_PHASE(0);   // wait for the TMA load
+        SECT(31);
         const uint16_t* xp = xs + i0;
         uint32_t csum = 0, cq = 0, cmn = 0xFFFFu, cmx = 0;
 #pragma unroll 3
@@ -816,6 +890,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             cmn = min(cmn, x);
             cmx = max(cmx, x);
         }
+        SECT(0);
         // baseline regression sums (exact integers): only chunks that intersect the window
         {
             unsigned long long blSS = 0;
@@ -882,7 +957,10 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         // zero the masks of this event (committed with atomicOr later)
 #pragma unroll
         for (int q = 0; q < NMASK; ++q) masks[q * NWORDS + tid] = 0u;
+        SECT(1);
         __syncthreads();   // ---- B1 ----
+        LGDSP_PHASE(1);
+        SECT(2);
 
         // exclusive prefixes of this thread's chunk
         uint32_t P_excl;
@@ -964,6 +1042,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
 #pragma unroll
         for (int k = 0; k < 5; ++k) thr[k] = e_max * P.tx_frac[k];
 
+        SECT(3);
         // ==========================================================================================
         // P2: prefix sums of the pole-zero waveform; t10..t99 masks; tail log-regression
         // ==========================================================================================
@@ -995,6 +1074,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 for (; k < cvalid; ++k) body(k);
                 if (tid == 0) TT[0] = 0.0;
             }
+            SECT(4);
             // Conservative bounds of y = w + km1*cumsum(w) on the chunk from the integer min/max of the raw samples:
             // cumsum(w)[i0+k] lies between S0 + (k+1)*wmin and S0 + (k+1)*wmax.
             const double wmin = (double)cmn - m, wmax = (double)cmx - m;
@@ -1004,37 +1084,28 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             const double guard = 1e-9 * (fabs(ylo) + fabs(yhi)) + 1e-6;   // >> rounding of the TT differences
             // t10..t99: a chunk entirely below (above) a threshold contributes zeros (ones) without a compare
             if ((G & LGDSP_GROUP_TIMING) && cvalid > 0) {
-                unsigned long long mb[5] = {0, 0, 0, 0, 0};
-                bool straddle = false;
-#pragma unroll
-                for (int t = 0; t < 5; ++t) straddle |= !(ylo - guard >= thr[t]) && !(yhi + guard < thr[t]);
-                if (straddle) {
-                    const double* tp = TT + i0;
-                    double tprev = TT0;
 #pragma unroll 1
-                    for (int k = 0; k < cvalid; ++k) {
-                        const double tn = tp[k + 1];
-                        const double y = tn - tprev;
-                        tprev = tn;
-#pragma unroll
-                        for (int t = 0; t < 5; ++t) mb[t] |= (y >= thr[t]) ? (1ull << k) : 0ull;
-                    }
-                }
-#pragma unroll
                 for (int t = 0; t < 5; ++t) {
-                    if (ylo - guard >= thr[t]) mb[t] = chunk_all;
-                    else if (yhi + guard < thr[t]) mb[t] = 0ull;
-                    mask_commit(masks + (M_T10 + t) * NWORDS, tid, mb[t]);
+                    const double th = e_max * P.tx_frac[t];   // = thr[t]
+                    unsigned long long mbt;
+                    if (ylo - guard >= th) mbt = chunk_all;
+                    else if (yhi + guard < th) mbt = 0ull;
+                    else mbt = mask_chunk(TT + i0, TT0, cvalid, th);
+                    mask_commit(masks + (M_T10 + t) * NWORDS, tid, mbt);
                 }
             }
             // bound of max |y| over the block (Lipschitz constants of the pruning)
             const double ya = wmax_d(cvalid > 0 ? fmax(fabs(ylo), fabs(yhi)) : 0.0);
             red_put(red, R_YMAX, wid, lane, ya);
         }
+        SECT(5);
         // tailstats: log-regression on the PRE-PZ waveform (src/tailstats.jl:22-72), samples strided over the block
         {
             double tl_S = 0, tl_SS = 0, tl_SX = 0;
             bool bad = false;
+            // log(w) = log(c) + log1p((w - c)/c) around the thread's first sample c: one full log per thread, the
+            // others are short polynomials unless the tail moves by more than 1/8 (then the full log again)
+            double cref = 0.0, cinv = 0.0, clog = 0.0;
 #pragma unroll 1
             for (int idx = P.tail_from + tid; idx <= P.tail_until; idx += NT) {
                 const double w = u2d(xs[idx]) - m;
@@ -1042,7 +1113,14 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     bad = true;
                 } else {
                     const double X = t_first + (double)idx * dt;
-                    const double lg = log_d(w);
+                    double lg;
+                    const double u = (w - cref) * cinv;
+                    if (cref > 0.0 && fabs(u) <= 0.125) {
+                        lg = clog + log1p_small(u);
+                    } else {
+                        lg = log_d(w);
+                        cref = w; cinv = 1.0 / w; clog = lg;
+                    }
                     tl_S += lg;
                     tl_SS = fma(lg, lg, tl_SS);
                     tl_SX = fma(X, lg, tl_SX);
@@ -1055,7 +1133,10 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 red[R_TLSX * NWARP + wid] = tl_SX; red[R_TLBAD * NWARP + wid] = anybad ? 1.0 : 0.0;
             }
         }
+        SECT(6);
         __syncthreads();   // ---- B2: TT and the t10..t99 masks are complete; xs is dead ----
+        LGDSP_PHASE(2);
+        SECT(7);
 
         // xs is free now: prefetch the next event (TMA, async proxy) -- unless the structured CUSP/ZAC pass borrows
         // xs for its prefix tables; then the prefetch is issued when the tables are dead
@@ -1080,6 +1161,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             resolve_runs(masks + (M_T10 + wid) * NWORDS, P.tx_min_n, lane, pos, mult);
             if (lane == 0) ibuf[IB_POS0 + M_T10 + wid] = pos;
         }
+        SECT(8);
         // PZ tail statistics (signalstats on the tail window, src/dsp_icpc.jl:123)
         {
             double pz_S = 0, pz_SS = 0, pz_SX = 0;
@@ -1096,6 +1178,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 red[R_PZS * NWARP + wid] = pz_S; red[R_PZSS * NWARP + wid] = pz_SS; red[R_PZSX * NWARP + wid] = pz_SX;
             }
         }
+        SECT(9);
         // trapezoids whose minimum is needed as well: full traces
         if (G & LGDSP_GROUP_TRAPS) {
             double o4[4];
@@ -1106,6 +1189,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 red[R_E313 * NWARP + wid] = c; red[R_E313N * NWARP + wid] = d;
             }
         }
+        SECT(10);
         // coarse grid (outputs 33*tid and 33*(tid+1)) of the other trapezoids
         double c0a = 0, c0b = 0, cia = 0, cib = 0, c5a = -CUDART_INF, c5b = -CUDART_INF, cea = -CUDART_INF, ceb = -CUDART_INF;
         {
@@ -1128,6 +1212,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 red_put(red, R_CET, wid, lane, we);
             }
         }
+        SECT(11);
         // currents: sg[0] over the whole trace (chunked, sliding window in registers): trace maximum, windowed first
         // argmax, baseline-window sums; the chunk maximum is kept for the mask pass
         double sgcmax = -CUDART_INF;
@@ -1151,6 +1236,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     });
                 }
             }
+            SECT(12);
             // sg[1], sg[2] and the plain derivative are only needed inside the current window: strided
 #pragma unroll 1
             for (int f = 1; f < 3; ++f) {
@@ -1159,7 +1245,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 int ba = 0x7fffffff;
 #pragma unroll 1
                 for (int j = P.cur_from[f] + tid; j <= P.cur_until[f]; j += NT) {
-                    const double s = sg_at(TT, P.sg[f], j);
+                    const double s = sg_at(f, j);
                     if (s > bm) { bm = s; ba = j; }
                 }
                 cmax[f] = bm; carg[f] = ba;
@@ -1169,6 +1255,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 const double d = deriv_at(TT, j);
                 if (d > cmax[3]) { cmax[3] = d; carg[3] = j; }
             }
+            SECT(13);
             const double wsm = wmax_d(sgcmax);
             sg_S = wsum_d(sg_S); sg_SS = wsum_d(sg_SS);
 #pragma unroll
@@ -1182,9 +1269,13 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 }
             }
         }
+        SECT(14);
         // CUSP/ZAC prefix tables (first descriptor)
-        if (cz_structured) cz_scan(P.cz[0], TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
+        if (cz_structured) cz_scan(&spar->cz[0], TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
+        SECT(15);
         __syncthreads();   // ---- B3 ----
+        LGDSP_PHASE(3);
+        SECT(16);
 
         // ==========================================================================================
         // P4a: decisions that need block-wide values; fine evaluation of the flagged intervals
@@ -1214,6 +1305,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         // the 44 trap(rt,ft) outputs of the e_trap pick-off window
         if ((G & LGDSP_GROUP_TRAPS) && tid < P.sig_dni.n_w) stash[tid] = trap_at(TT, P.etrap, pk_from[0] + tid);
 
+        SECT(17);
         // ---- coarse-to-fine trapezoids: lane i of warp w owns the interval (33q, 33q+33), q = 32w + i ----
         double e535 = c5a, etmax = cea;
         int etarg = (cea > -CUDART_INF) ? i0 : 0x7fffffff;
@@ -1302,6 +1394,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             }
         }
 
+        SECT(18);
         // ---- masks on the sg[0] trace (t50_current, in-trace pile-up on the REVERSED trace): only chunks whose
         //      maximum reaches the smaller threshold can contribute a bit; a warp evaluates its flagged chunks
         //      with one output per lane (same operation order as the chunk pass: bit-identical values) ----
@@ -1315,30 +1408,46 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             const Stats st = stats_finalize(cnt, dX, dXX, sS, sSS, 0.0);
             pile_thr = st.sigma * P.nsigma;
             if (pile_thr == 0.0) pile_thr = 1.0;  // src/dsp_routines.jl:77
-            unsigned bf = __ballot_sync(FULL, sgcmax >= fmin(cur_thr, pile_thr));
+            const bool flag = sgcmax >= fmin(cur_thr, pile_thr);
+            unsigned bf = __ballot_sync(FULL, flag);
+            if (__popc(bf) > 10) {
+                // many flagged chunks in this warp (low threshold): every flagged lane redoes its own chunk
+                if (flag) {
+                    unsigned long long bc = 0, bp = 0;
+                    sg_chunk(TT, P.sg[0], i0, min(CH, nsg - i0), [&](int k, double s) {
+                        bc |= (s >= cur_thr) ? (1ull << k) : 0ull;
+                        bp |= (s >= pile_thr) ? (1ull << k) : 0ull;
+                    });
+                    mask_commit(masks + M_CUR * NWORDS, tid, bc);
+                    mask_commit_reversed(masks + M_PILE * NWORDS, tid, bp, nsg);
+                }
+            } else {
+                // few: the warp evaluates them together, one output per lane (same operation order: identical values)
 #pragma unroll 1
-            while (bf) {
-                const int i = __ffs(bf) - 1;
-                bf &= bf - 1;
-                const int q = wid * 32 + i;
-                const int j = q * CH + lane;
-                const bool v = j < nsg;
-                const double s = v ? sg_at(TT, P.sg[0], j) : 0.0;
-                unsigned long long bc = __ballot_sync(FULL, v && (s >= cur_thr));
-                unsigned long long bp = __ballot_sync(FULL, v && (s >= pile_thr));
-                if (lane == 0) {
-                    const int j2 = q * CH + 32;
-                    if (j2 < nsg) {
-                        const double s2 = sg_at(TT, P.sg[0], j2);
-                        bc |= (s2 >= cur_thr) ? (1ull << 32) : 0ull;
-                        bp |= (s2 >= pile_thr) ? (1ull << 32) : 0ull;
+                while (bf) {
+                    const int i = __ffs(bf) - 1;
+                    bf &= bf - 1;
+                    const int q = wid * 32 + i;
+                    const int j = q * CH + lane;
+                    const bool v = j < nsg;
+                    const double s = v ? sg_at(0, j) : 0.0;
+                    unsigned long long bc = __ballot_sync(FULL, v && (s >= cur_thr));
+                    unsigned long long bp = __ballot_sync(FULL, v && (s >= pile_thr));
+                    if (lane == 0) {
+                        const int j2 = q * CH + 32;
+                        if (j2 < nsg) {
+                            const double s2 = sg_at(0, j2);
+                            bc |= (s2 >= cur_thr) ? (1ull << 32) : 0ull;
+                            bp |= (s2 >= pile_thr) ? (1ull << 32) : 0ull;
+                        }
+                        mask_commit(masks + M_CUR * NWORDS, q, bc);
+                        mask_commit_reversed(masks + M_PILE * NWORDS, q, bp, nsg);
                     }
-                    mask_commit(masks + M_CUR * NWORDS, q, bc);
-                    mask_commit_reversed(masks + M_PILE * NWORDS, q, bp, nsg);
                 }
             }
         }
 
+        SECT(19);
         // ---- CUSP / ZAC ----
         double czmax[2] = {-CUDART_INF, -CUDART_INF};
         int czarg[2] = {0x7fffffff, 0x7fffffff};
@@ -1367,7 +1476,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             const bool want_cusp = P.cz_shared || ps == 0, want_zac = P.cz_shared || ps == 1;
             if (ps > 0) {
                 __syncthreads();   // the previous pass is done with the tables and the coarse values
-                cz_scan(Z, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
+                cz_scan(&spar->cz[ps], TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
                 __syncthreads();
             }
             CzState st;
@@ -1387,7 +1496,10 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 red_put(red, R_CZC0, wid, lane, wc);
                 red_put(red, R_CZC1, wid, lane, wz);
             }
+            SECT(20);
             __syncthreads();   // ---- B4 ----
+            LGDSP_PHASE(4);
+            SECT(21);
             if (ps == npass - 1) prefetch_next();   // every thread has read its table entries: xs may be overwritten
             // candidate chunks: Lipschitz bound on (33 tid, 33 tid + 33) against the best coarse value; chunks that
             // hold part of a pick-off window are always evaluated
@@ -1418,11 +1530,13 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     cand |= (jhi >= pk_from[2] && jlo < pk_from[2] + P.sig_dni.n_w);
                 }
             }
+            SECT(22);
             if (cand)
                 cz_run(Z, TT, n, tid, st, want_cusp, want_zac, pk_from[1], pk_from[2], P.sig_dni.n_w,
                        stash + LGDSP_MAX_DNI, stash + 2 * LGDSP_MAX_DNI, czmax, czarg);
         }
-        if (npass == 0) __syncthreads();   // ---- B4 (no structured CUSP/ZAC) ----
+        SECT(23);
+        if (npass == 0) { __syncthreads(); LGDSP_PHASE(4); }   // ---- B4 (no structured CUSP/ZAC) ----
 
         // final partials
         {
@@ -1437,6 +1551,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 red[R_CZMAX1 * NWARP + wid] = czmax[1]; red[R_CZARG1 * NWARP + wid] = (double)czarg[1];
             }
         }
+        SECT(24);
         // crossing resolution: t0, t0_inv, t50_current, pile-up (one warp each; the masks were complete at B4)
         {
             const int slot = (wid == 0) ? 0 : (wid == 1) ? 1 : (wid == 6) ? 2 : (wid == 7) ? 3 : -1;
@@ -1451,12 +1566,49 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 }
             }
         }
+        SECT(25);
         if (tid < 64) row[tid] = 0.0;
         __syncthreads();   // ---- B6 ----
+        LGDSP_PHASE(5);
+        SECT(26);
 
         // ==========================================================================================
-        // P5: scalar results, spread over the warps; stage A
+        // P5: scalar results, spread over the warps (every warp is self-contained: no barrier in between)
         // ==========================================================================================
+        // t10..t99 [us] (k = 0..4) and t0 / t0_inv [us] from the resolved positions; NaN -> 0
+        auto tx_us = [&](int k) -> double {
+            const int pos = ibuf[IB_POS0 + M_T10 + k];
+            const double th = k == 0 ? thr[0] : k == 1 ? thr[1] : k == 2 ? thr[2] : k == 3 ? thr[3] : thr[4];
+            double t = 0.0;
+            if (pos >= 1) t = cross_x(th, y_at(TT, pos - 1), y_at(TT, pos), t_first + (double)(pos - 1) * dt, dt) * 0.001;
+            return t != t ? 0.0 : t;
+        };
+        auto t0_us = [&](bool inv) -> double {
+            const TrapDev& tr = inv ? P.t0inv : P.t0;
+            const int pos = ibuf[IB_POS0 + (inv ? M_T0INV : M_T0)];
+            double t = 0.0;
+            if (pos >= 1) {
+                const double tl = t_first + (double)(pos - 1 + tr.L - 1) * dt;
+                const double sgn = inv ? -1.0 : 1.0;
+                t = cross_x(P.t0_thr, sgn * trap_at(TT, tr, pos - 1), sgn * trap_at(TT, tr, pos), tl, dt) * 0.001;
+            }
+            return t != t ? 0.0 : t;
+        };
+        // get_qdrift  src/dsp_routines.jl:51-64 on the integrator trace I[i] = TT[i+1], one warp
+        auto qdrift_warp = [&](double t_us, double first, double last) -> double {
+            const double tns = t_us * 1000.0;
+            double a[3];
+#pragma unroll 1
+            for (int q = 0; q < 3; ++q) {
+                const double ts = q == 0 ? tns : (q == 1 ? tns + first : tns + last);
+                double pc;
+                int from;
+                dni_window(P.int_dni.n_w, n, (ts - t_first) / dt, pc, from);
+                a[q] = dni_eval_warp(A_int, P.int_dni.n_w, P.int_dni.m, TT + from + 1, pc - (double)from, lane);
+            }
+            const double area1 = a[1] - a[0], area2 = a[2] - a[1];
+            return area2 - area1;
+        };
         if (wid == 0) {
             // block-wide sums first (warp-collective), then lanes 0..2 finish the three statistics blocks
             const double tlS = red_sum(red, R_TLS), tlSS = red_sum(red, R_TLSS), tlSX = red_sum(red, R_TLSX);
@@ -1487,30 +1639,17 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 }
             }
         } else if (wid == 1) {
-            // interpolated crossings: lanes 0..4 t10..t99, lane 5 t0, lane 6 t0_inv
+            // interpolated crossings: lanes 0..4 t10..t99, lane 5 t0, lane 6 t0_inv; then drift_time = t90 - t0
+            double t = 0.0;
             if (lane < 5) {
-                const int pos = ibuf[IB_POS0 + M_T10 + lane];
-                const double th = lane == 0 ? thr[0] : lane == 1 ? thr[1] : lane == 2 ? thr[2] : lane == 3 ? thr[3] : thr[4];
-                double t = 0.0;
-                if (pos >= 1)
-                    t = cross_x(th, y_at(TT, pos - 1), y_at(TT, pos), t_first + (double)(pos - 1) * dt, dt) * 0.001;
-                if (t != t) t = 0.0;
-                scr[SC_TX + lane] = t;
+                t = tx_us(lane);
                 if (G & LGDSP_GROUP_TIMING) row[LGDSP_COL_t10 + lane] = t;
             } else if (lane == 5 || lane == 6) {
-                const bool inv = lane == 6;
-                const TrapDev& tr = inv ? P.t0inv : P.t0;
-                const int pos = ibuf[IB_POS0 + (inv ? M_T0INV : M_T0)];
-                double t = 0.0;
-                if (pos >= 1) {
-                    const double tl = t_first + (double)(pos - 1 + tr.L - 1) * dt;
-                    const double sgn = inv ? -1.0 : 1.0;
-                    t = cross_x(P.t0_thr, sgn * trap_at(TT, tr, pos - 1), sgn * trap_at(TT, tr, pos), tl, dt) * 0.001;
-                    if (t != t) t = 0.0;
-                }
-                scr[inv ? SC_T0INV : SC_T0] = t;
-                if (G & LGDSP_GROUP_TIMING) row[inv ? LGDSP_COL_t0_inv : LGDSP_COL_t0] = t;
+                t = t0_us(lane == 6);
+                if (G & LGDSP_GROUP_TIMING) row[lane == 6 ? LGDSP_COL_t0_inv : LGDSP_COL_t0] = t;
             }
+            const double t90 = __shfl_sync(FULL, t, 3), t0v = __shfl_sync(FULL, t, 5);
+            if (lane == 0 && (G & LGDSP_GROUP_TIMING)) row[LGDSP_COL_drift_time] = (t90 - t0v) * 1000.0;
         } else if (wid == 2) {
             if (G & LGDSP_GROUP_TRAPS) {
                 const double v = dni_eval_warp(A_sig, P.sig_dni.n_w, P.sig_dni.m, stash, pk_p[0] - (double)pk_from[0], lane);
@@ -1557,14 +1696,23 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     double v = f == 0 ? vv[0] : f == 1 ? vv[1] : f == 2 ? vv[2] : vv[3];
                     const int a = f == 0 ? aa[0] : f == 1 ? aa[1] : f == 2 ? aa[2] : aa[3];
                     if (a > P.cur_from[f] && a < P.cur_until[f]) {
-                        const double y1 = (f < 3) ? sg_at(TT, P.sg[f], a - 1) : deriv_at(TT, a - 1);
-                        const double y3 = (f < 3) ? sg_at(TT, P.sg[f], a + 1) : deriv_at(TT, a + 1);
+                        const double y1 = (f < 3) ? sg_at(f, a - 1) : deriv_at(TT, a - 1);
+                        const double y3 = (f < 3) ? sg_at(f, a + 1) : deriv_at(TT, a + 1);
                         v = extrema3(y1, v, y3);
                     }
                     row[LGDSP_COL_a_sg + f] = v;
                 }
             }
+        } else if (wid == 7) {
+            if (G & LGDSP_GROUP_QDRIFT) {
+                const double v = qdrift_warp(t0_us(false), P.qd_first, P.qd_last);   // qdrift @ t0
+                if (lane == 0) row[LGDSP_COL_qdrift] = v;
+            }
         } else if (wid == 6) {
+            if (G & LGDSP_GROUP_QDRIFT) {
+                const double v = qdrift_warp(tx_us(2), P.lq_first, P.lq_last);       // lq @ t80
+                if (lane == 0) row[LGDSP_COL_lq] = v;
+            }
             if (lane < 2 && (G & LGDSP_GROUP_CURRENT)) {
                 const double tf = t_first + (double)P.sg[0].offset * dt;
                 if (lane == 0) {
@@ -1572,7 +1720,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     const int pos = ibuf[IB_POS0 + M_CUR];
                     double t = 0.0;
                     if (pos >= 1) {
-                        t = cross_x(cur_thr, sg_at(TT, P.sg[0], pos - 1), sg_at(TT, P.sg[0], pos), tf + (double)(pos - 1) * dt, dt) * 0.001;
+                        t = cross_x(cur_thr, sg_at(0, pos - 1), sg_at(0, pos), tf + (double)(pos - 1) * dt, dt) * 0.001;
                         if (t != t) t = 0.0;
                     }
                     row[LGDSP_COL_t50_current] = t;
@@ -1581,7 +1729,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     const int pos = ibuf[IB_POS0 + M_PILE];
                     double xi = CUDART_NAN;
                     if (pos >= 1) {
-                        const double yl = sg_at(TT, P.sg[0], nsg - 1 - (pos - 1)), yr = sg_at(TT, P.sg[0], nsg - 1 - pos);
+                        const double yl = sg_at(0, nsg - 1 - (pos - 1)), yr = sg_at(0, nsg - 1 - pos);
                         xi = cross_x(pile_thr, yl, yr, tf + (double)(pos - 1) * dt, dt);
                     }
                     const double last_t = tf + (double)(nsg - 1) * dt;
@@ -1590,34 +1738,19 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 }
             }
         }
-        __syncthreads();   // ---- B7 ----
-        // stage B: what needs t0 / t80 / t90
-        if (wid < 2) {
-            if (G & LGDSP_GROUP_QDRIFT) {
-                // get_qdrift  src/dsp_routines.jl:51-64; integrator trace I[i] = TT[i+1]; warp 0: qdrift @t0, warp 1: lq @t80
-                const double tns = (wid == 0 ? scr[SC_T0] : scr[SC_TX + 2]) * 1000.0;
-                const double first = wid == 0 ? P.qd_first : P.lq_first, last = wid == 0 ? P.qd_last : P.lq_last;
-                double a[3];
-#pragma unroll 1
-                for (int s = 0; s < 3; ++s) {
-                    const double ts = s == 0 ? tns : (s == 1 ? tns + first : tns + last);
-                    double pc;
-                    int from;
-                    dni_window(P.int_dni.n_w, n, (ts - t_first) / dt, pc, from);
-                    a[s] = dni_eval_warp(A_int, P.int_dni.n_w, P.int_dni.m, TT + from + 1, pc - (double)from, lane);
-                }
-                if (lane == 0) {
-                    const double area1 = a[1] - a[0], area2 = a[2] - a[1];
-                    row[wid == 0 ? LGDSP_COL_qdrift : LGDSP_COL_lq] = area2 - area1;
-                }
-            }
-        } else if (wid == 2) {
-            if (lane == 0 && (G & LGDSP_GROUP_TIMING)) row[LGDSP_COL_drift_time] = (scr[SC_TX + 3] - scr[SC_T0]) * 1000.0;
-        }
+        SECT(27);
         __syncthreads();   // ---- B8 ----
+        LGDSP_PHASE(6);
+        SECT(28);
         if (tid < LGDSP_NCOL) rows[e * LGDSP_NCOL + tid] = row[tid];
         // (the next iteration's first barrier orders the reuse of row/stash/masks/scr/red)
     }
+    if (pc_on) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) P.phase_cycles[blockIdx.x * 8 + i] = pc_acc[i];
+    }
+#undef LGDSP_PHASE
+#undef SECT
 }
 
 // ==================================================================================================
