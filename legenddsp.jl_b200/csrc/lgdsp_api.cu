@@ -298,6 +298,7 @@ static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
     D.sat_high = (p->sat_high >= 0 && p->sat_high <= 65535) ? (int)p->sat_high : -1;
     D.bl_from = p->bl_from; D.bl_until = p->bl_until; D.tail_from = p->tail_from; D.tail_until = p->tail_until;
     D.km1 = p->pz_km1;
+    D.bl_inv_n = 1.0 / (double)(p->bl_until - p->bl_from + 1);
     const int nw_sig = p->sig_dni.n_w, nw_int = p->int_dni.n_w;
     auto dni_ok = [](const lgdsp_dni& d) { return d.degree >= 0 && d.degree <= LGDSP_MAX_DNI_DEG && d.n_w > d.degree && d.n_w <= LGDSP_MAX_DNI; };
     if (!dni_ok(p->sig_dni) || !dni_ok(p->int_dni)) return fail(h, LGDSP_ERR_UNSUPPORTED, "PolynomialDNI window/degree outside the supported range");
@@ -339,6 +340,7 @@ static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
     D.intr_min_n = p->intrace_min_n;
     if (!win_ok(p->intrace_bl_from, p->intrace_bl_until, D.sg[0].nout)) return fail(h, LGDSP_ERR_INVALID_ARG, "in-trace sigma window outside the sg trace");
     D.intr_from = p->intrace_bl_from; D.intr_until = p->intrace_bl_until;
+    D.intr_inv_n = 1.0 / (double)(p->intrace_bl_until - p->intrace_bl_from + 1);
     // CUSP / ZAC
     const lgdsp_cuspzac* cz[2] = {&p->cusp, &p->zac};
     double* dst[2] = {h->d_cusp_g, h->d_zac_g};

@@ -54,6 +54,7 @@ struct IcpcDev {
     int sat_low, sat_high;  // -1: can never match a uint16 sample
     int bl_from, bl_until, tail_from, tail_until;
     double km1;
+    double bl_inv_n;        // 1/(number of baseline-window samples), as the reference's inv_n
     TrapDev t0, t0inv, e10410, e535, e313, etrap;
     int t0inv_same, t0_min_n, tx_min_n, direct;
     double t0_thr;
@@ -65,6 +66,7 @@ struct IcpcDev {
     int cur_from[4], cur_until[4];
     int sg_alias[4];           // sg_alias[f] >= 0: filter f (taps and window) is identical to that earlier filter
     double nsigma;
+    double intr_inv_n;      // 1/(samples of the in-trace sigma window)
     int intr_min_n, intr_from, intr_until, pad0;
     int cusp_L, zac_L;
     int cz_shared, pad1;   // 1: cusp and zac share (sigma, flat, tau, L) -> one structured pass emits both

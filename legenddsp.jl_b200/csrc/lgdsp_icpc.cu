@@ -86,8 +86,12 @@ static_assert(2 * NT * 8 <= 5 * NWORDS * 4, "coarse CUSP/ZAC values fit into the
 int icpc_smem_bytes() { return SM_TOTAL; }
 int icpc_threads() { return NT; }
 
-enum { IB_POS0 = 0 /* NMASK positions */, IB_MULT = 16 };
-enum { SC_TX = 0 /* 5 */, SC_T0 = 5, SC_T0INV = 6, SC_PP0 = 16 };
+enum { IB_POS0 = 0 /* NMASK positions */, IB_MULT = 16, IB_PKFROM = 20 /* 3 */, IB_QN = 24, IB_CZN = 25, IB_CZT = 32 /* 31 chunk ids */ };
+constexpr int QCAP = 480;    // work queue of flagged intervals (uint16 codes behind the coarse CUSP/ZAC values)
+constexpr int CZCAP = 31;    // candidate chunks per round of the CUSP/ZAC output buffer (31 * 33 * 2 doubles <= 16 KB)
+static_assert(2 * NT * 8 + QCAP * 2 <= 5 * NWORDS * 4, "coarse values + queue fit into the T10..T99 mask area");
+static_assert(CZCAP * CH * 2 * 8 <= 8 * NT * 8, "output buffer fits into the tables 8..15 area");
+enum { SC_TX = 0 /* 5 */, SC_T0 = 5, SC_T0INV = 6, SC_PKP = 8 /* 3 */, SC_PP0 = 16 };
 
 // ---------------------------------------------------------------------------------------------------
 // reductions.  Maxima/minima of doubles go through an order-preserving 64-bit integer key and two 32-bit
@@ -286,48 +290,44 @@ __device__ __forceinline__ void mask_commit_reversed(uint32_t* M, int tid, unsig
 
 // One warp: find runs of >= k consecutive set bits in the NWORDS-word mask M (bits beyond the trace are zero)
 // that do not start at bit 0 -- the Intersect state machine: `pos` = start of the first such
-// run (-1 if none), `mult` = number of such runs.  M is destroyed.
-__device__ __noinline__ void resolve_runs(uint32_t* M, int k, int lane, int& pos, int& mult)
+// run (-1 if none), `mult` = number of such runs.  Every lane looks for run STARTS (set bit after a clear bit) in its
+// 8 words and measures each run forward, word by word; M is left intact.
+__device__ __noinline__ void resolve_runs(const uint32_t* M, int k, int lane, int& pos, int& mult)
 {
     constexpr int Q = NWORDS / 32;
-    uint32_t m[Q], r[Q];
+    uint32_t m[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) { m[q] = M[lane * Q + q]; r[q] = m[q]; }
-    int len = 1;
-    while (len < k) {
-        const int step = min(len, k - len);
-        const int ws = step >> 5, bs = step & 31;
-        __syncwarp();
-        uint32_t nr[Q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const int w = lane * Q + q + ws;
-            const uint32_t lo = w < NWORDS ? M[w] : 0u;
-            const uint32_t hi = (w + 1) < NWORDS ? M[w + 1] : 0u;
-            const uint32_t sh = bs ? ((lo >> bs) | (hi << (32 - bs))) : lo;
-            nr[q] = r[q] & sh;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < Q; ++q) { r[q] = nr[q]; M[lane * Q + q] = nr[q]; }
-        len += step;
-    }
+    for (int q = 0; q < Q; ++q) m[q] = M[lane * Q + q];
     uint32_t prev_top = __shfl_up_sync(FULL, m[Q - 1], 1);
     if (lane == 0) prev_top = 0;
     int p = 0x7fffffff, cnt = 0;
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
         const uint32_t carry = ((q == 0) ? prev_top : m[q - 1]) >> 31;
-        uint32_t c = r[q] & ~((m[q] << 1) | carry);
-        if (lane == 0 && q == 0) c &= ~1u;  // a run that starts at the first sample never fires
-        cnt += __popc(c);
-        if (c && p == 0x7fffffff) p = (lane * Q + q) * 32 + (__ffs(c) - 1);
+        uint32_t starts = m[q] & ~((m[q] << 1) | carry);
+        if (lane == 0 && q == 0) starts &= ~1u;  // a run that starts at the first sample never fires
+        while (starts) {
+            const int b = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const uint32_t rest = ~(m[q] >> b);            // first clear bit above b (the shifted-in zeros stop it at the word end)
+            int len = rest ? __ffs(rest) - 1 : 32;
+            if (len == 32 - b) {
+                // the run reaches the top of its word: follow it through the next words
+                for (int w = lane * Q + q + 1; w < NWORDS && len < k; ++w) {
+                    const uint32_t x = M[w];
+                    if (x == 0xffffffffu) { len += 32; continue; }
+                    len += __ffs(~x) - 1;
+                    break;
+                }
+            }
+            if (len >= k) {
+                ++cnt;
+                p = min(p, (lane * Q + q) * 32 + b);
+            }
+        }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        p = min(p, __shfl_xor_sync(FULL, p, o));
-        cnt += __shfl_xor_sync(FULL, cnt, o);
-    }
+    p = __reduce_min_sync(FULL, p);
+    cnt = __reduce_add_sync(FULL, cnt);
     pos = (p == 0x7fffffff) ? -1 : p;
     mult = cnt;
 }
@@ -450,10 +450,13 @@ __device__ __forceinline__ double* cz_tab(double* tabA, double* tabB, int idx)
 // One forward loop per chunk: P- (decayed prefix), D1, D2 (moments) and the partial sums acc = sum_{k'<=k} rho^k' d
 // of the anti-causal prefix (P+ at in-chunk offset o is (total - acc[o-1]) * rho^-o; the weights only span one
 // chunk, so nothing cancels).  The running values are stored at the capture events the host sorted by sample index.
-__device__ __noinline__ void cz_scan(const CzDev* Zp, const double* TT, int n, int tid, double* tabA, double* tabB, double* red,
+__device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, double* tabA, double* tabB, double* red,
                         double* pp0)
 {
-    const CzDev& Z = *Zp;   // SMEM copy of the descriptor (a reference to the kernel parameter would force generic loads)
+    // SMEM copy of the descriptor, addressed through the dynamic shared memory base so that the loads are LDS
+    // (a reference to the kernel parameter or a generic pointer would force generic loads)
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    const CzDev& Z = reinterpret_cast<const SmemPar*>(smem_dyn + SM_PAR)->cz[ps];
     const int lane = tid & 31, wid = tid >> 5;
     const int i0 = tid * CH;
     const double r = Z.r, rho = Z.rho;
@@ -465,6 +468,7 @@ __device__ __noinline__ void cz_scan(const CzDev* Zp, const double* TT, int n, i
         double tcur = p[-1];
         double yprev = (i0 >= 1) ? tcur - p[-2] : 0.0;
         double di = (double)i0, w = 1.0;
+        double tpre = p[0];   // software prefetch of the next prefix sum
         auto step = [&](double d) {
             pm = fma(rho, pm, d);
             const double kd = di * d;
@@ -479,7 +483,8 @@ __device__ __noinline__ void cz_scan(const CzDev* Zp, const double* TT, int n, i
             if (cnt == CH) {
 #pragma unroll 1
                 for (; k <= kend; ++k) {
-                    const double tnext = p[k];
+                    const double tnext = tpre;
+                    tpre = p[k + 1];                    // (<= TT[i0+34]: exists for every full chunk)
                     const double y = tnext - tcur;      // exact difference of neighbouring prefix sums
                     const double d = fma(-r, yprev, y);
                     yprev = y;
@@ -635,12 +640,11 @@ struct CzStream {
     }
 };
 
-// CH recurrence steps; emits CUSP and/or ZAC outputs, tracks (max, first argmax), fills the pick-off windows
-__device__ __forceinline__ void cz_run(const CzDev& Z, const double* TT, int n, int tid, CzState& S, bool want_cusp, bool want_zac,
-                       int from_cusp, int from_zac, int n_w, double* stash_cusp, double* stash_zac, double (&czmax)[2],
-                       int (&czarg)[2])
+// CH recurrence steps of one candidate chunk: the CUSP and ZAC outputs go to obuf[k][0..1] (-inf where m0+k is not a
+// valid output); maxima, argmaxima and the pick-off windows are taken from there by a block-parallel pass.  No
+// compares or branches in the loop: the only loop-carried dependency is the state update.
+__device__ __forceinline__ void cz_out(const CzDev& Z, const double* TT, int n, int tid, CzState& S, double* obuf)
 {
-    if (!S.active) return;
     const int m0 = tid * CH;
     const int L = Z.L, lt = Z.lt, F = Z.F;
     const double r = Z.r;
@@ -649,27 +653,12 @@ __device__ __forceinline__ void cz_run(const CzDev& Z, const double* TT, int n, 
     s1.init(TT, m0 + 1 - lt);
     s2.init(TT, m0 - lt - F);
     s3.init(TT, m0 + 1 - L);
-    auto emit = [&](int m, bool stash) {
-        const int j = m - L + 1;
+    auto emit = [&](int k) {
         const double ylast = s3.yprev;   // y[m-L]
         const double Dc = (S.EpL - S.EmL + S.EpR - S.EmR) + S.W0F;
-        if (want_cusp) {
-            const double o = fma(Z.g, Dc, Z.gclast_cusp * ylast);
-            if (o > czmax[0]) { czmax[0] = o; czarg[0] = j; }
-            if (stash) {
-                const int q = j - from_cusp;
-                if (q >= 0 && q < n_w) stash_cusp[q] = o;
-            }
-        }
-        if (want_zac) {
-            const double poly = (S.W2L - Z.h2 * S.W1L) + (S.V2 - Z.h2 * S.V1);
-            const double o = fma(Z.g, fma(Z.B, poly, Dc), Z.gclast_zac * ylast);
-            if (o > czmax[1]) { czmax[1] = o; czarg[1] = j; }
-            if (stash) {
-                const int q = j - from_zac;
-                if (q >= 0 && q < n_w) stash_zac[q] = o;
-            }
-        }
+        const double poly = (S.W2L - Z.h2 * S.W1L) + (S.V2 - Z.h2 * S.V1);
+        obuf[2 * k] = fma(Z.g, Dc, Z.gclast_cusp * ylast);
+        obuf[2 * k + 1] = fma(Z.g, fma(Z.B, poly, Dc), Z.gclast_zac * ylast);
     };
     auto update = [&](double a, double b, double c, double d) {
         S.EmL = fma(Z.rho, S.EmL, fma(Z.cA, a, -Z.cA_rho_lt * b));
@@ -684,12 +673,11 @@ __device__ __forceinline__ void cz_run(const CzDev& Z, const double* TT, int n, 
         S.EpR = fma(Z.rho, S.EpR, fma(Z.cA_rhoinv_Rn, c, -Z.cA * d));
         S.EmR = fma(Z.rho_inv, S.EmR, fma(Z.cA_rho_Rn, c, -Z.cA * d));
     };
-    // interior chunk: every stream index is inside the trace, every m is a valid output
     const bool interior = (m0 - L >= 1) && (m0 + CH + 1 <= n);
     if (interior) {
 #pragma unroll 3
         for (int k = 0; k < CH; ++k) {
-            emit(m0 + k, true);
+            emit(k);
             const double a = s0.next_fast(r, k), b = s1.next_fast(r, k), c = s2.next_fast(r, k), d = s3.next_fast(r, k);
             update(a, b, c, d);
         }
@@ -697,8 +685,8 @@ __device__ __forceinline__ void cz_run(const CzDev& Z, const double* TT, int n, 
 #pragma unroll 1
         for (int k = 0; k < CH; ++k) {
             const int m = m0 + k;
-            if (m >= n) break;
-            if (m >= L - 1) emit(m, true);
+            if (m >= L - 1 && m < n) emit(k);
+            else { obuf[2 * k] = -CUDART_INF; obuf[2 * k + 1] = -CUDART_INF; }
             const double a = s0.next_safe(TT, r, n), b = s1.next_safe(TT, r, n), c = s2.next_safe(TT, r, n),
                          d = s3.next_safe(TT, r, n);
             update(a, b, c, d);
@@ -770,15 +758,18 @@ __device__ __forceinline__ double interval_bound(double a, double b, bool b_vali
 }
 
 __device__ __noinline__ double log_d(double x) { return log(x); }
-// log1p(u) for |u| <= 1/8: Taylor series to u^17 (truncation < 3e-17 relative), Horner
-__device__ __noinline__ double log1p_small(double u)
+// log1p(u) for |u| <= 1/8: Taylor series to u^18 (truncation < 1e-17 relative), Estrin scheme (dependency depth 6)
+__device__ __forceinline__ double log1p_small(double u)
 {
-    double p = 1.0 / 17.0;
-    p = fma(p, u, -1.0 / 16.0); p = fma(p, u, 1.0 / 15.0); p = fma(p, u, -1.0 / 14.0); p = fma(p, u, 1.0 / 13.0);
-    p = fma(p, u, -1.0 / 12.0); p = fma(p, u, 1.0 / 11.0); p = fma(p, u, -1.0 / 10.0); p = fma(p, u, 1.0 / 9.0);
-    p = fma(p, u, -1.0 / 8.0); p = fma(p, u, 1.0 / 7.0); p = fma(p, u, -1.0 / 6.0); p = fma(p, u, 1.0 / 5.0);
-    p = fma(p, u, -1.0 / 4.0); p = fma(p, u, 1.0 / 3.0); p = fma(p, u, -0.5); p = fma(p, u, 1.0);
-    return p * u;
+    const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4, u16 = u8 * u8;
+    // c_k = (-1)^k / (k+1):  log1p(u) = u * sum_{k=0}^{17} c_k u^k
+    const double a0 = fma(-1.0 / 2.0, u, 1.0), a1 = fma(-1.0 / 4.0, u, 1.0 / 3.0), a2 = fma(-1.0 / 6.0, u, 1.0 / 5.0),
+                 a3 = fma(-1.0 / 8.0, u, 1.0 / 7.0), a4 = fma(-1.0 / 10.0, u, 1.0 / 9.0), a5 = fma(-1.0 / 12.0, u, 1.0 / 11.0),
+                 a6 = fma(-1.0 / 14.0, u, 1.0 / 13.0), a7 = fma(-1.0 / 16.0, u, 1.0 / 15.0), a8 = fma(-1.0 / 18.0, u, 1.0 / 17.0);
+    const double b0 = fma(a1, u2, a0), b1 = fma(a3, u2, a2), b2 = fma(a5, u2, a4), b3 = fma(a7, u2, a6);
+    const double c0 = fma(b1, u4, b0), c1 = fma(b3, u4, b2);
+    const double d0 = fma(c1, u8, c0);
+    return u * fma(a8, u16, d0);
 }
 // threshold mask of one chunk of the PZ waveform: bit k = (y[i0+k] >= th), y from the prefix sums (tt0 = TT[i0])
 __device__ __noinline__ unsigned long long mask_chunk(const double* tp, double tt0, int cvalid, double th)
@@ -954,9 +945,10 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         uint32_t es = __shfl_up_sync(FULL, ss, 1);
         double eq = __shfl_up_sync(FULL, sq, 1);
         if (lane == 0) { el = 0; es = 0; eq = 0.0; }
-        // zero the masks of this event (committed with atomicOr later)
+        // zero the masks and the queue counters of this event (committed with atomics later)
 #pragma unroll
         for (int q = 0; q < NMASK; ++q) masks[q * NWORDS + tid] = 0u;
+        if (tid == 0) { ibuf[IB_QN] = 0; ibuf[IB_CZN] = 0; }
         SECT(1);
         __syncthreads();   // ---- B1 ----
         LGDSP_PHASE(1);
@@ -1027,16 +1019,8 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             __syncthreads();
         }
 
-        // baseline statistics (exact sums) -> blmean
-        const int bl_n = P.bl_until - P.bl_from + 1;
-        Stats bl;
-        {
-            double bsX, bsXX;
-            xsums(P.bl_from, P.bl_until, t_first, dt, bsX, bsXX);
-            const double blSd = red_sum(red, R_BLS), blSSd = red_sum(red, R_BLSS), blSXd = red_sum(red, R_BLSX);
-            bl = stats_finalize(bl_n, bsX, bsXX, blSd, blSSd, t_first * blSd + dt * blSXd);
-        }
-        const double m = bl.mean;
+        // blmean = mean_Y = sum_Y * inv_n exactly as signalstats computes it (the other baseline statistics: P5)
+        const double m = mul_rn(red_sum(red, R_BLS), P.bl_inv_n);
         const double e_max = (double)mx - m, e_min = (double)mn - m;
         double thr[5];
 #pragma unroll
@@ -1084,13 +1068,37 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             const double guard = 1e-9 * (fabs(ylo) + fabs(yhi)) + 1e-6;   // >> rounding of the TT differences
             // t10..t99: a chunk entirely below (above) a threshold contributes zeros (ones) without a compare
             if ((G & LGDSP_GROUP_TIMING) && cvalid > 0) {
-#pragma unroll 1
+                uint32_t lo[5] = {0, 0, 0, 0, 0}, hi = 0;   // bits 0..31 of every threshold; bit t of hi = sample 32
+                bool straddle = false;
+#pragma unroll
+                for (int t = 0; t < 5; ++t) straddle |= !(ylo - guard >= thr[t]) && !(yhi + guard < thr[t]);
+                if (straddle) {
+                    // one pass over the chunk, the five compares are independent (y from the prefix sums)
+                    const double* tp = TT + i0;
+                    double tprev = TT0;
+                    const int c32 = min(cvalid, 32);
+                    double tnx = tp[1];                       // software prefetch: the load of sample k+1 overlaps sample k
+#pragma unroll 2
+                    for (int k = 0; k < c32; ++k) {
+                        const double tn = tnx;
+                        tnx = tp[k + 2];                      // (<= TT[i0+34]: inside the zero padding for the last chunk)
+                        const double y = tn - tprev;
+                        tprev = tn;
+                        const uint32_t bit = 1u << k;
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) lo[t] |= (y >= thr[t]) ? bit : 0u;
+                    }
+                    if (cvalid > 32) {
+                        const double y = tnx - tprev;
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) hi |= (y >= thr[t]) ? (1u << t) : 0u;
+                    }
+                }
+#pragma unroll
                 for (int t = 0; t < 5; ++t) {
-                    const double th = e_max * P.tx_frac[t];   // = thr[t]
-                    unsigned long long mbt;
-                    if (ylo - guard >= th) mbt = chunk_all;
-                    else if (yhi + guard < th) mbt = 0ull;
-                    else mbt = mask_chunk(TT + i0, TT0, cvalid, th);
+                    unsigned long long mbt = (unsigned long long)lo[t] | ((unsigned long long)((hi >> t) & 1u) << 32);
+                    if (ylo - guard >= thr[t]) mbt = chunk_all;
+                    else if (yhi + guard < thr[t]) mbt = 0ull;
                     mask_commit(masks + (M_T10 + t) * NWORDS, tid, mbt);
                 }
             }
@@ -1103,28 +1111,43 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         {
             double tl_S = 0, tl_SS = 0, tl_SX = 0;
             bool bad = false;
-            // log(w) = log(c) + log1p((w - c)/c) around the thread's first sample c: one full log per thread, the
-            // others are short polynomials unless the tail moves by more than 1/8 (then the full log again)
+            // log(w) = log(c) + log1p((w - c)/c) around a per-thread reference sample c: one full log per thread, the
+            // others are short polynomials unless the tail moves by more than 1/8 (then the full log again);
+            // two samples per iteration so that their polynomial chains overlap
             double cref = 0.0, cinv = 0.0, clog = 0.0;
-#pragma unroll 1
-            for (int idx = P.tail_from + tid; idx <= P.tail_until; idx += NT) {
-                const double w = u2d(xs[idx]) - m;
-                if (w <= 0.0) {
-                    bad = true;
+            auto one = [&](int idx, double w, double u) {
+                if (w <= 0.0) { bad = true; return; }
+                double lg;
+                if (cref > 0.0 && fabs(u) <= 0.125) {
+                    lg = clog + log1p_small(u);
                 } else {
-                    const double X = t_first + (double)idx * dt;
-                    double lg;
-                    const double u = (w - cref) * cinv;
-                    if (cref > 0.0 && fabs(u) <= 0.125) {
-                        lg = clog + log1p_small(u);
-                    } else {
-                        lg = log_d(w);
-                        cref = w; cinv = 1.0 / w; clog = lg;
-                    }
-                    tl_S += lg;
-                    tl_SS = fma(lg, lg, tl_SS);
-                    tl_SX = fma(X, lg, tl_SX);
+                    lg = log_d(w);
+                    cref = w; cinv = 1.0 / w; clog = lg;
                 }
+                const double X = t_first + (double)idx * dt;
+                tl_S += lg;
+                tl_SS = fma(lg, lg, tl_SS);
+                tl_SX = fma(X, lg, tl_SX);
+            };
+            int idx = P.tail_from + tid;
+#pragma unroll 1
+            for (; idx + NT <= P.tail_until; idx += 2 * NT) {
+                const double w0 = u2d(xs[idx]) - m, w1 = u2d(xs[idx + NT]) - m;
+                const double u0 = (w0 - cref) * cinv, u1 = (w1 - cref) * cinv;
+                if (cref > 0.0 && w0 > 0.0 && w1 > 0.0 && fabs(u0) <= 0.125 && fabs(u1) <= 0.125) {
+                    // common case: both through the polynomial, interleaved
+                    const double l0 = clog + log1p_small(u0), l1 = clog + log1p_small(u1);
+                    const double X0 = t_first + (double)idx * dt, X1 = t_first + (double)(idx + NT) * dt;
+                    tl_S += l0; tl_SS = fma(l0, l0, tl_SS); tl_SX = fma(X0, l0, tl_SX);
+                    tl_S += l1; tl_SS = fma(l1, l1, tl_SS); tl_SX = fma(X1, l1, tl_SX);
+                } else {
+                    one(idx, w0, u0);
+                    one(idx + NT, w1, (w1 - cref) * cinv);
+                }
+            }
+            if (idx <= P.tail_until) {
+                const double w0 = u2d(xs[idx]) - m;
+                one(idx, w0, (w0 - cref) * cinv);
             }
             tl_S = wsum_d(tl_S); tl_SS = wsum_d(tl_SS); tl_SX = wsum_d(tl_SX);
             const bool anybad = __any_sync(FULL, bad);
@@ -1160,6 +1183,22 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             int pos, mult;
             resolve_runs(masks + (M_T10 + wid) * NWORDS, P.tx_min_n, lane, pos, mult);
             if (lane == 0) ibuf[IB_POS0 + M_T10 + wid] = pos;
+            if (wid == M_T50 - M_T10 && lane < 3) {
+                // t50 [us] and the DNI window of energy pick-off `lane` (0 trap, 1 cusp, 2 zac): published for everyone
+                double t50_us = 0.0;
+                if (pos >= 1) {
+                    const double x = cross_x(thr[1], y_at(TT, pos - 1), y_at(TT, pos), t_first + (double)(pos - 1) * dt, dt);
+                    t50_us = x * 0.001;
+                }
+                const int Lf = lane == 0 ? P.etrap.L : lane == 1 ? P.cusp_L : P.zac_L;
+                const double pick = lane == 0 ? P.trap_pick : lane == 1 ? P.cusp_pick : P.zac_pick;
+                const double tf = t_first + (double)(Lf - 1) * dt;
+                double pp;
+                int pf;
+                dni_window(P.sig_dni.n_w, n - Lf + 1, (t50_us * 1000.0 + pick - tf) / dt, pp, pf);
+                scr[SC_PKP + lane] = pp;
+                ibuf[IB_PKFROM + lane] = pf;
+            }
         }
         SECT(8);
         // PZ tail statistics (signalstats on the tail window, src/dsp_icpc.jl:123)
@@ -1221,36 +1260,59 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             double cmax[4] = {-CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF};
             int carg[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
             double sg_S = 0, sg_SS = 0;
-            {
-                const int cnt = min(CH, nsg - i0);
-                const int wa = P.cur_from[0] - i0, wb = P.cur_until[0] - i0;
-                const int sa = P.intr_from - i0, sb = P.intr_until - i0;
-                const bool plain = (wb < 0 || wa >= CH) && (sb < 0 || sa >= CH);   // no window touches this chunk
-                if (plain) {
-                    sg_chunk(TT, P.sg[0], i0, cnt, [&](int k, double s) { sgcmax = s > sgcmax ? s : sgcmax; });
-                } else {
-                    sg_chunk(TT, P.sg[0], i0, cnt, [&](int k, double s) {
-                        sgcmax = s > sgcmax ? s : sgcmax;
-                        if (k >= wa && k <= wb && s > cmax[0]) { cmax[0] = s; carg[0] = i0 + k; }
-                        if (k >= sa && k <= sb) { sg_S += s; sg_SS = fma(s, s, sg_SS); }
-                    });
-                }
-            }
+            // (a) whole trace, one chunk per thread: only the chunk maximum (uniform cost for every thread)
+            sg_chunk(TT, P.sg[0], i0, min(CH, nsg - i0), [&](int k, double s) { sgcmax = s > sgcmax ? s : sgcmax; });
             SECT(12);
-            // sg[1], sg[2] and the plain derivative are only needed inside the current window: strided
+            // (b) windowed quantities, strided over the block (same operation order as the chunk pass: identical values):
+            //     first argmax of sg[0..2] and of the plain derivative inside the current window, baseline-window sums of sg[0]
 #pragma unroll 1
-            for (int f = 1; f < 3; ++f) {
-                if (P.sg_alias[f] >= 0) continue;   // identical to an earlier filter: copied after the reduction
+            for (int f = 0; f < 3; ++f) {
+                if (f > 0 && P.sg_alias[f] >= 0) continue;   // identical to an earlier filter: copied after the reduction
                 double bm = -CUDART_INF;
                 int ba = 0x7fffffff;
+                if (P.sg[f].n_taps + 1 <= 8) {
+                    double g[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] = spar->sgg[f][q];
+                    auto ev = [&](int j) -> double {
+                        const double* p = TT + j;
+                        double a0 = g[0] * p[0], a1 = g[1] * p[1];
+                        a0 = fma(g[2], p[2], a0); a1 = fma(g[3], p[3], a1);
+                        a0 = fma(g[4], p[4], a0); a1 = fma(g[5], p[5], a1);
+                        a0 = fma(g[6], p[6], a0); a1 = fma(g[7], p[7], a1);
+                        return a0 + a1;
+                    };
+#pragma unroll 2
+                    for (int j = P.cur_from[f] + tid; j <= P.cur_until[f]; j += NT) {
+                        const double v = ev(j);
+                        if (v > bm) { bm = v; ba = j; }
+                    }
+                    if (f == 0) {
+#pragma unroll 2
+                        for (int j = P.intr_from + tid; j <= P.intr_until; j += NT) {
+                            const double v = ev(j);
+                            sg_S += v;
+                            sg_SS = fma(v, v, sg_SS);
+                        }
+                    }
+                } else {
 #pragma unroll 1
-                for (int j = P.cur_from[f] + tid; j <= P.cur_until[f]; j += NT) {
-                    const double s = sg_at(f, j);
-                    if (s > bm) { bm = s; ba = j; }
+                    for (int j = P.cur_from[f] + tid; j <= P.cur_until[f]; j += NT) {
+                        const double v = sg_at(f, j);
+                        if (v > bm) { bm = v; ba = j; }
+                    }
+                    if (f == 0) {
+#pragma unroll 1
+                        for (int j = P.intr_from + tid; j <= P.intr_until; j += NT) {
+                            const double v = sg_at(0, j);
+                            sg_S += v;
+                            sg_SS = fma(v, v, sg_SS);
+                        }
+                    }
                 }
-                cmax[f] = bm; carg[f] = ba;
+                if (f == 0) { cmax[0] = bm; carg[0] = ba; } else if (f == 1) { cmax[1] = bm; carg[1] = ba; } else { cmax[2] = bm; carg[2] = ba; }
             }
-#pragma unroll 1
+#pragma unroll 2
             for (int j = P.cur_from[3] + tid; j <= P.cur_until[3]; j += NT) {
                 const double d = deriv_at(TT, j);
                 if (d > cmax[3]) { cmax[3] = d; carg[3] = j; }
@@ -1271,7 +1333,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         }
         SECT(14);
         // CUSP/ZAC prefix tables (first descriptor)
-        if (cz_structured) cz_scan(&spar->cz[0], TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
+        if (cz_structured) cz_scan(0, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
         SECT(15);
         __syncthreads();   // ---- B3 ----
         LGDSP_PHASE(3);
@@ -1280,61 +1342,111 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         // ==========================================================================================
         // P4a: decisions that need block-wide values; fine evaluation of the flagged intervals
         // ==========================================================================================
-        // t50 [us] and the DNI windows of the three energy pick-offs
-        double t50_us = 0.0;
-        {
-            const int pos = ibuf[IB_POS0 + M_T50];
-            if (pos >= 1) {
-                const double x = cross_x(thr[1], y_at(TT, pos - 1), y_at(TT, pos), t_first + (double)(pos - 1) * dt, dt);
-                t50_us = x * 0.001;
-            }
-        }
+        // DNI windows of the three energy pick-offs (computed by the t50 warp in P3)
         double pk_p[3];
         int pk_from[3];
-        {
-            const int Ls[3] = {P.etrap.L, P.cusp_L, P.zac_L};
-            const double picks[3] = {P.trap_pick, P.cusp_pick, P.zac_pick};
 #pragma unroll
-            for (int f = 0; f < 3; ++f) {
-                const double tf = t_first + (double)(Ls[f] - 1) * dt;
-                dni_window(P.sig_dni.n_w, n - Ls[f] + 1, (t50_us * 1000.0 + picks[f] - tf) / dt, pk_p[f], pk_from[f]);
-            }
-        }
+        for (int f = 0; f < 3; ++f) { pk_p[f] = scr[SC_PKP + f]; pk_from[f] = ibuf[IB_PKFROM + f]; }
         const double Ymax = red_max(red, R_YMAX);     // bound of max |y| of the PZ waveform
         const double kslack = 1e-7 * Ymax;            // >> float64 rounding of any trace
         // the 44 trap(rt,ft) outputs of the e_trap pick-off window
         if ((G & LGDSP_GROUP_TRAPS) && tid < P.sig_dni.n_w) stash[tid] = trap_at(TT, P.etrap, pk_from[0] + tid);
 
         SECT(17);
-        // ---- coarse-to-fine trapezoids: lane i of warp w owns the interval (33q, 33q+33), q = 32w + i ----
+        // ---- thresholds of the sg[0] masks (t50_current at half the trace maximum; pile-up at n sigma of the baseline
+        //      window, sigma exactly as signalstats computes it) ----
+        double pile_thr = 0.0, cur_thr = 0.0;
+        if (G & LGDSP_GROUP_CURRENT) {
+            cur_thr = red_max(red, R_SGMAX) * 0.5;
+            const double sS = red_sum(red, R_SGS), sSS = red_sum(red, R_SGSS);
+            const double mean_Y = mul_rn(sS, P.intr_inv_n);
+            double var_Y = sub_rn(mul_rn(sSS, P.intr_inv_n), mul_rn(mean_Y, mean_Y));
+            if (var_Y < 0) var_Y = 0;
+            pile_thr = sqrt(var_Y) * P.nsigma;
+            if (pile_thr == 0.0) pile_thr = 1.0;  // src/dsp_routines.jl:77
+        }
+        uint16_t* qitems = reinterpret_cast<uint16_t*>(czco + 2 * NT);   // work queue behind the coarse CUSP/ZAC values
         double e535 = c5a, etmax = cea;
         int etarg = (cea > -CUDART_INF) ? i0 : 0x7fffffff;
+        // one flagged interval / chunk q, evaluated by a whole warp (one output per lane):
+        //   type 0: trap(t0) on (33q, 33q+33) -> t0 mask (and t0_inv mask when both use the same filter); 1: t0_inv filter;
+        //   2: trap(5,3) maximum; 3: trap(rt,ft) maximum + first argmax; 4: sg[0] chunk q -> t50_current / pile-up masks
+        auto do_item = [&](int type, int q) {
+            if (type <= 1) {
+                const TrapDev& tr = type == 0 ? P.t0 : P.t0inv;
+                const double th = P.t0_thr;
+                const int j = q * CH + 1 + lane;
+                const bool v = j < tr.nout;
+                const double o = v ? trap_at(TT, tr, j) : 0.0;
+                const unsigned mp = __ballot_sync(FULL, v && (o >= th));
+                const unsigned mn_ = __ballot_sync(FULL, v && (-o >= th));
+                if (lane == 0) {
+                    if (type == 0) mask_commit(masks + M_T0 * NWORDS, q, (unsigned long long)mp << 1);
+                    if (type == 1 || P.t0inv_same) mask_commit(masks + M_T0INV * NWORDS, q, (unsigned long long)mn_ << 1);
+                }
+            } else if (type == 2) {
+                const int j = q * CH + 1 + lane;
+                if (j < P.e535.nout) {
+                    const double o = trap_at(TT, P.e535, j);
+                    e535 = o > e535 ? o : e535;
+                }
+            } else if (type == 3) {
+                const int j = q * CH + 1 + lane;
+                if (j < P.etrap.nout) {
+                    const double o = trap_at(TT, P.etrap, j);
+                    if (o > etmax || (o == etmax && j < etarg)) { etmax = o; etarg = j; }
+                }
+            } else {
+                const int j = q * CH + lane;
+                const bool v = j < nsg;
+                const double sv = v ? sg_at(0, j) : 0.0;
+                unsigned long long bc = __ballot_sync(FULL, v && (sv >= cur_thr));
+                unsigned long long bp = __ballot_sync(FULL, v && (sv >= pile_thr));
+                if (lane == 0) {
+                    const int j2 = q * CH + 32;
+                    if (j2 < nsg) {
+                        const double s2 = sg_at(0, j2);
+                        bc |= (s2 >= cur_thr) ? (1ull << 32) : 0ull;
+                        bp |= (s2 >= pile_thr) ? (1ull << 32) : 0ull;
+                    }
+                    mask_commit(masks + M_CUR * NWORDS, q, bc);
+                    mask_commit_reversed(masks + M_PILE * NWORDS, q, bp, nsg);
+                }
+            }
+        };
+        // ---- coarse-to-fine trapezoids: lane i of warp w owns the interval (33q, 33q+33), q = 32w + i ----
         {
             bool f0 = false, fi = false, f5 = false, fe = false;
             if (G & LGDSP_GROUP_TIMING) {
+                // Which intervals can hold part of a qualifying run (>= min_n consecutive samples above threshold)?
+                //   min_n >= 2*33: such a run contains two CONSECUTIVE coarse points, and one of them is an end point of
+                //                  every interval it overlaps -> need (a && b) || (a && prev) || (b && next);
+                //   min_n  >  33 : it contains an end point of every interval it overlaps -> need a || b;
+                //   otherwise every interval is evaluated.
+                // (prev/next = coarse points q-1 / q+2; unknown across a warp boundary -> assumed above threshold)
                 const double th = P.t0_thr;
-                const bool va = i0 < P.t0.nout, vb = i0 + CH < P.t0.nout;
-                // a run of >= min_n > 33 samples that overlaps the open interval contains one of its end points
-                const bool all = P.t0_min_n <= CH;
-                if (va) {
-                    const bool pa = c0a >= th, na = -c0a >= th;
-                    const bool pb = vb && (c0b >= th), nb = vb && (-c0b >= th);
-                    if (P.t0inv_same) {
-                        f0 = all || pa || pb || na || nb;
-                        mask_commit(masks + M_T0 * NWORDS, tid, pa ? 1ull : 0ull);
-                        mask_commit(masks + M_T0INV * NWORDS, tid, na ? 1ull : 0ull);
-                    } else {
-                        f0 = all || pa || pb;
-                        mask_commit(masks + M_T0 * NWORDS, tid, pa ? 1ull : 0ull);
-                    }
+                const int rule = P.t0_min_n >= 2 * CH ? 2 : (P.t0_min_n > CH ? 1 : 0);
+                auto need = [&](bool a, bool b, bool valid) -> bool {
+                    bool prev = __shfl_up_sync(FULL, a, 1), next = __shfl_down_sync(FULL, b, 1);
+                    if (lane == 0) prev = true;
+                    if (lane == 31) next = true;
+                    if (!valid) return false;
+                    return rule == 2 ? ((a && b) || (a && prev) || (b && next)) : (rule == 1 ? (a || b) : true);
+                };
+                {
+                    const bool va = i0 < P.t0.nout, vb = i0 + CH < P.t0.nout;
+                    const bool pa = va && (c0a >= th), pb = vb && (c0b >= th);
+                    const bool na = va && (-c0a >= th), nb = vb && (-c0b >= th);
+                    const bool fp = need(pa, pb, va), fn = need(na, nb, va);
+                    f0 = P.t0inv_same ? (fp || fn) : fp;
+                    if (pa) mask_commit(masks + M_T0 * NWORDS, tid, 1ull);
+                    if (P.t0inv_same && na) mask_commit(masks + M_T0INV * NWORDS, tid, 1ull);
                 }
                 if (!P.t0inv_same) {
                     const bool wa = i0 < P.t0inv.nout, wb = i0 + CH < P.t0inv.nout;
-                    if (wa) {
-                        const bool na = -cia >= th, nb = wb && (-cib >= th);
-                        fi = all || na || nb;
-                        mask_commit(masks + M_T0INV * NWORDS, tid, na ? 1ull : 0ull);
-                    }
+                    const bool na = wa && (-cia >= th), nb = wb && (-cib >= th);
+                    fi = need(na, nb, wa);
+                    if (na) mask_commit(masks + M_T0INV * NWORDS, tid, 1ull);
                 }
             }
             if (G & LGDSP_GROUP_TRAPS) {
@@ -1344,72 +1456,36 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 if (i0 + 1 < P.e535.nout) f5 = interval_bound(c5a, c5b, i0 + CH < P.e535.nout, k5) + kslack >= M5;
                 if (i0 + 1 < P.etrap.nout) fe = interval_bound(cea, ceb, i0 + CH < P.etrap.nout, ke) + kslack >= Me;
             }
-            // every warp evaluates its own flagged intervals, 32 interior outputs = one per lane
-            unsigned b0 = __ballot_sync(FULL, f0), bi = __ballot_sync(FULL, fi);
-            unsigned b5 = __ballot_sync(FULL, f5), be = __ballot_sync(FULL, fe);
-            const double th = P.t0_thr;
-#pragma unroll 1
-            while (b0) {
-                const int i = __ffs(b0) - 1;
-                b0 &= b0 - 1;
-                const int j = (wid * 32 + i) * CH + 1 + lane;
-                const bool v = j < P.t0.nout;
-                const double o = v ? trap_at(TT, P.t0, j) : 0.0;
-                const unsigned mp = __ballot_sync(FULL, v && (o >= th));
-                const unsigned mn_ = __ballot_sync(FULL, v && (-o >= th));
-                if (lane == 0) {
-                    mask_commit(masks + M_T0 * NWORDS, wid * 32 + i, (unsigned long long)mp << 1);
-                    if (P.t0inv_same) mask_commit(masks + M_T0INV * NWORDS, wid * 32 + i, (unsigned long long)mn_ << 1);
+            // flagged intervals go to a block-wide work queue (processed by all warps after B4, so the pulse-region
+            // warp does not evaluate all of them alone); what does not fit is evaluated right away by the owning warp
+            auto push = [&](int type, bool flag) {
+                const unsigned b = __ballot_sync(FULL, flag);
+                if (b == 0u) return;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&ibuf[IB_QN], __popc(b));
+                base = __shfl_sync(FULL, base, 0);
+                const int idx = base + __popc(b & ((1u << lane) - 1u));
+                const bool fits = idx < QCAP;
+                if (flag && fits) qitems[idx] = (uint16_t)((type << 8) | tid);
+                unsigned bo = __ballot_sync(FULL, flag && !fits);
+                while (bo) {
+                    const int i = __ffs(bo) - 1;
+                    bo &= bo - 1;
+                    do_item(type, wid * 32 + i);
                 }
-            }
-#pragma unroll 1
-            while (bi) {
-                const int i = __ffs(bi) - 1;
-                bi &= bi - 1;
-                const int j = (wid * 32 + i) * CH + 1 + lane;
-                const bool v = j < P.t0inv.nout;
-                const double o = v ? trap_at(TT, P.t0inv, j) : 0.0;
-                const unsigned mn_ = __ballot_sync(FULL, v && (-o >= th));
-                if (lane == 0) mask_commit(masks + M_T0INV * NWORDS, wid * 32 + i, (unsigned long long)mn_ << 1);
-            }
-#pragma unroll 1
-            while (b5) {
-                const int i = __ffs(b5) - 1;
-                b5 &= b5 - 1;
-                const int j = (wid * 32 + i) * CH + 1 + lane;
-                if (j < P.e535.nout) {
-                    const double o = trap_at(TT, P.e535, j);
-                    e535 = o > e535 ? o : e535;
-                }
-            }
-#pragma unroll 1
-            while (be) {
-                const int i = __ffs(be) - 1;
-                be &= be - 1;
-                const int j = (wid * 32 + i) * CH + 1 + lane;
-                if (j < P.etrap.nout) {
-                    const double o = trap_at(TT, P.etrap, j);
-                    if (o > etmax || (o == etmax && j < etarg)) { etmax = o; etarg = j; }
-                }
-            }
+            };
+            push(0, f0);
+            push(1, fi);
+            push(2, f5);
+            push(3, fe);
         }
-
         SECT(18);
+
         // ---- masks on the sg[0] trace (t50_current, in-trace pile-up on the REVERSED trace): only chunks whose
-        //      maximum reaches the smaller threshold can contribute a bit; a warp evaluates its flagged chunks
-        //      with one output per lane (same operation order as the chunk pass: bit-identical values) ----
-        double pile_thr = 0.0, cur_thr = 0.0;
+        //      maximum reaches the smaller threshold can contribute a bit ----
         if (G & LGDSP_GROUP_CURRENT) {
-            cur_thr = red_max(red, R_SGMAX) * 0.5;
-            const int cnt = P.intr_until - P.intr_from + 1;
-            double dX, dXX;
-            xsums(P.intr_from, P.intr_until, t_first + P.sg[0].offset * dt, dt, dX, dXX);
-            const double sS = red_sum(red, R_SGS), sSS = red_sum(red, R_SGSS);
-            const Stats st = stats_finalize(cnt, dX, dXX, sS, sSS, 0.0);
-            pile_thr = st.sigma * P.nsigma;
-            if (pile_thr == 0.0) pile_thr = 1.0;  // src/dsp_routines.jl:77
             const bool flag = sgcmax >= fmin(cur_thr, pile_thr);
-            unsigned bf = __ballot_sync(FULL, flag);
+            const unsigned bf = __ballot_sync(FULL, flag);
             if (__popc(bf) > 10) {
                 // many flagged chunks in this warp (low threshold): every flagged lane redoes its own chunk
                 if (flag) {
@@ -1421,33 +1497,24 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     mask_commit(masks + M_CUR * NWORDS, tid, bc);
                     mask_commit_reversed(masks + M_PILE * NWORDS, tid, bp, nsg);
                 }
-            } else {
-                // few: the warp evaluates them together, one output per lane (same operation order: identical values)
-#pragma unroll 1
-                while (bf) {
-                    const int i = __ffs(bf) - 1;
-                    bf &= bf - 1;
-                    const int q = wid * 32 + i;
-                    const int j = q * CH + lane;
-                    const bool v = j < nsg;
-                    const double s = v ? sg_at(0, j) : 0.0;
-                    unsigned long long bc = __ballot_sync(FULL, v && (s >= cur_thr));
-                    unsigned long long bp = __ballot_sync(FULL, v && (s >= pile_thr));
-                    if (lane == 0) {
-                        const int j2 = q * CH + 32;
-                        if (j2 < nsg) {
-                            const double s2 = sg_at(0, j2);
-                            bc |= (s2 >= cur_thr) ? (1ull << 32) : 0ull;
-                            bp |= (s2 >= pile_thr) ? (1ull << 32) : 0ull;
-                        }
-                        mask_commit(masks + M_CUR * NWORDS, q, bc);
-                        mask_commit_reversed(masks + M_PILE * NWORDS, q, bp, nsg);
-                    }
+            } else if (bf) {
+                // few: queued, a warp evaluates one chunk with one output per lane (same operation order: identical values)
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&ibuf[IB_QN], __popc(bf));
+                base = __shfl_sync(FULL, base, 0);
+                const int idx = base + __popc(bf & ((1u << lane) - 1u));
+                const bool fits = idx < QCAP;
+                if (flag && fits) qitems[idx] = (uint16_t)((4 << 8) | tid);
+                unsigned bo = __ballot_sync(FULL, flag && !fits);
+                while (bo) {
+                    const int i = __ffs(bo) - 1;
+                    bo &= bo - 1;
+                    do_item(4, wid * 32 + i);
                 }
             }
         }
-
         SECT(19);
+
         // ---- CUSP / ZAC ----
         double czmax[2] = {-CUDART_INF, -CUDART_INF};
         int czarg[2] = {0x7fffffff, 0x7fffffff};
@@ -1467,16 +1534,18 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     const int r = j - pk_from[1 + f];
                     if (r >= 0 && r < P.sig_dni.n_w) stash[(1 + f) * LGDSP_MAX_DNI + r] = o;
                 }
-                czmax[f] = bm; czarg[f] = ba;
+                if (f == 0) { czmax[0] = bm; czarg[0] = ba; } else { czmax[1] = bm; czarg[1] = ba; }
             }
         }
+        bool queue_done = false;
 #pragma unroll 1
         for (int ps = 0; ps < npass; ++ps) {
             const CzDev& Z = P.cz[ps];
             const bool want_cusp = P.cz_shared || ps == 0, want_zac = P.cz_shared || ps == 1;
             if (ps > 0) {
-                __syncthreads();   // the previous pass is done with the tables and the coarse values
-                cz_scan(&spar->cz[ps], TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
+                __syncthreads();   // the previous pass is done with the tables, the coarse values and the output buffer
+                if (tid == 0) ibuf[IB_CZN] = 0;
+                cz_scan(ps, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
                 __syncthreads();
             }
             CzState st;
@@ -1497,7 +1566,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 red_put(red, R_CZC1, wid, lane, wz);
             }
             SECT(20);
-            __syncthreads();   // ---- B4 ----
+            __syncthreads();   // ---- B4: tables are dead, coarse values and the work queue are complete ----
             LGDSP_PHASE(4);
             SECT(21);
             if (ps == npass - 1) prefetch_next();   // every thread has read its table entries: xs may be overwritten
@@ -1530,13 +1599,72 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     cand |= (jhi >= pk_from[2] && jlo < pk_from[2] + P.sig_dni.n_w);
                 }
             }
+            // slot of every candidate chunk in the output buffer (rounds of CZCAP chunks)
+            int slot = -1;
+            {
+                const unsigned bc = __ballot_sync(FULL, cand);
+                int base = 0;
+                if (lane == 0 && bc) base = atomicAdd(&ibuf[IB_CZN], __popc(bc));
+                base = __shfl_sync(FULL, base, 0);
+                if (cand) slot = base + __popc(bc & ((1u << lane) - 1u));
+            }
             SECT(22);
-            if (cand)
-                cz_run(Z, TT, n, tid, st, want_cusp, want_zac, pk_from[1], pk_from[2], P.sig_dni.n_w,
-                       stash + LGDSP_MAX_DNI, stash + 2 * LGDSP_MAX_DNI, czmax, czarg);
+            // the queued intervals, spread over all warps (before the long recurrences of the candidate warps)
+            if (!queue_done) {
+                const int nq = min(ibuf[IB_QN], QCAP);
+#pragma unroll 1
+                for (int it = wid; it < nq; it += NWARP) {
+                    const int code = qitems[it];
+                    do_item(code >> 8, code & 255);
+                }
+                queue_done = true;
+            }
+            SECT(29);
+            // rounds: recurrences of up to CZCAP candidate chunks write their outputs to SMEM, then the whole block
+            // takes maxima / first argmaxima / pick-off windows from there
+            double* czbuf = tabB;
+#pragma unroll 1
+            for (int r0 = 0;; r0 += CZCAP) {
+                if (cand && slot >= r0 && slot < r0 + CZCAP) {
+                    ibuf[IB_CZT + slot - r0] = tid;
+                    cz_out(Z, TT, n, tid, st, czbuf + (size_t)(slot - r0) * (CH * 2));
+                }
+                SECT(23);
+                __syncthreads();   // ---- B5 ----
+                SECT(30);
+                const int ncz = ibuf[IB_CZN];
+                const int nslot = min(ncz - r0, CZCAP);
+                const int nw = P.sig_dni.n_w;
+#pragma unroll 1
+                for (int i = tid; i < nslot * CH; i += NT) {
+                    const int sl = i / CH, k = i - sl * CH;
+                    const int j = ibuf[IB_CZT + sl] * CH + k - Z.L + 1;
+                    const double o_c = czbuf[2 * i], o_z = czbuf[2 * i + 1];
+                    if (want_cusp) {
+                        if (o_c > czmax[0] || (o_c == czmax[0] && j < czarg[0])) { czmax[0] = o_c; czarg[0] = j; }
+                        const int q = j - pk_from[1];
+                        if (q >= 0 && q < nw && o_c > -CUDART_INF) stash[LGDSP_MAX_DNI + q] = o_c;
+                    }
+                    if (want_zac) {
+                        if (o_z > czmax[1] || (o_z == czmax[1] && j < czarg[1])) { czmax[1] = o_z; czarg[1] = j; }
+                        const int q = j - pk_from[2];
+                        if (q >= 0 && q < nw && o_z > -CUDART_INF) stash[2 * LGDSP_MAX_DNI + q] = o_z;
+                    }
+                }
+                if (r0 + CZCAP >= ncz) break;
+                __syncthreads();   // the buffer is reused by the next round
+            }
         }
-        SECT(23);
-        if (npass == 0) { __syncthreads(); LGDSP_PHASE(4); }   // ---- B4 (no structured CUSP/ZAC) ----
+        if (npass == 0) {
+            __syncthreads();   // ---- B4 (no structured CUSP/ZAC) ----
+            LGDSP_PHASE(4);
+            const int nq = min(ibuf[IB_QN], QCAP);
+#pragma unroll 1
+            for (int it = wid; it < nq; it += NWARP) {
+                const int code = qitems[it];
+                do_item(code >> 8, code & 255);
+            }
+        }
 
         // final partials
         {
@@ -1552,20 +1680,6 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             }
         }
         SECT(24);
-        // crossing resolution: t0, t0_inv, t50_current, pile-up (one warp each; the masks were complete at B4)
-        {
-            const int slot = (wid == 0) ? 0 : (wid == 1) ? 1 : (wid == 6) ? 2 : (wid == 7) ? 3 : -1;
-            if (slot >= 0) {
-                const int which = (slot == 0) ? M_T0 : (slot == 1) ? M_T0INV : (slot == 2) ? M_CUR : M_PILE;
-                const int ks = (slot < 2) ? P.t0_min_n : (slot == 2) ? P.tx_min_n : P.intr_min_n;
-                int pos, mult;
-                resolve_runs(masks + which * NWORDS, ks, lane, pos, mult);
-                if (lane == 0) {
-                    ibuf[IB_POS0 + which] = pos;
-                    if (which == M_PILE) ibuf[IB_MULT] = mult;
-                }
-            }
-        }
         SECT(25);
         if (tid < 64) row[tid] = 0.0;
         __syncthreads();   // ---- B6 ----
@@ -1583,9 +1697,8 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             if (pos >= 1) t = cross_x(th, y_at(TT, pos - 1), y_at(TT, pos), t_first + (double)(pos - 1) * dt, dt) * 0.001;
             return t != t ? 0.0 : t;
         };
-        auto t0_us = [&](bool inv) -> double {
+        auto t0_us = [&](bool inv, int pos) -> double {
             const TrapDev& tr = inv ? P.t0inv : P.t0;
-            const int pos = ibuf[IB_POS0 + (inv ? M_T0INV : M_T0)];
             double t = 0.0;
             if (pos >= 1) {
                 const double tl = t_first + (double)(pos - 1 + tr.L - 1) * dt;
@@ -1610,42 +1723,49 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             return area2 - area1;
         };
         if (wid == 0) {
-            // block-wide sums first (warp-collective), then lanes 0..2 finish the three statistics blocks
+            // block-wide sums first (warp-collective), then lanes 0..2 finish one statistics block each (same code path):
+            // lane 0 baseline [:102], lane 1 tailstats [:115, src/tailstats.jl:22-72], lane 2 PZ tail stats [:123]
+            const double blS = red_sum(red, R_BLS), blSS = red_sum(red, R_BLSS), blSX = red_sum(red, R_BLSX);
             const double tlS = red_sum(red, R_TLS), tlSS = red_sum(red, R_TLSS), tlSX = red_sum(red, R_TLSX);
             const double tlbad = red_sum(red, R_TLBAD);
             const double pzS = red_sum(red, R_PZS), pzSS = red_sum(red, R_PZSS), pzSX = red_sum(red, R_PZSX);
-            if (lane == 0) {
-                row[LGDSP_COL_blmean] = bl.mean; row[LGDSP_COL_blsigma] = bl.sigma;
-                row[LGDSP_COL_blslope] = bl.slope; row[LGDSP_COL_bloffset] = bl.offset;
-                row[LGDSP_COL_qc_label] = -1.0;
-                row[LGDSP_COL_e_max] = e_max; row[LGDSP_COL_e_min] = e_min;
-                row[LGDSP_COL_n_sat_low] = (double)nlow; row[LGDSP_COL_n_sat_high] = (double)nhigh;
-                row[LGDSP_COL_n_sat_low_cons] = (double)cons_low; row[LGDSP_COL_n_sat_high_cons] = (double)cons_high;
-            } else if (lane == 1 || lane == 2) {
-                const int tn = P.tail_until - P.tail_from + 1;
-                double tsX, tsXX;
-                xsums(P.tail_from, P.tail_until, t_first, dt, tsX, tsXX);
-                if (lane == 1) {
-                    // tailstats  src/tailstats.jl:22-72
+            if (lane < 3) {
+                const int from = lane == 0 ? P.bl_from : P.tail_from, until = lane == 0 ? P.bl_until : P.tail_until;
+                const double sY = lane == 0 ? blS : lane == 1 ? tlS : pzS;
+                const double sYY = lane == 0 ? blSS : lane == 1 ? tlSS : pzSS;
+                const double sXY = lane == 0 ? t_first * blS + dt * blSX : lane == 1 ? tlSX : pzSX;
+                double sX, sXX;
+                xsums(from, until, t_first, dt, sX, sXX);
+                const Stats st = stats_finalize(until - from + 1, sX, sXX, sY, sYY, sXY);
+                if (lane == 0) {
+                    row[LGDSP_COL_blmean] = st.mean; row[LGDSP_COL_blsigma] = st.sigma;
+                    row[LGDSP_COL_blslope] = st.slope; row[LGDSP_COL_bloffset] = st.offset;
+                    row[LGDSP_COL_qc_label] = -1.0;
+                    row[LGDSP_COL_e_max] = e_max; row[LGDSP_COL_e_min] = e_min;
+                    row[LGDSP_COL_n_sat_low] = (double)nlow; row[LGDSP_COL_n_sat_high] = (double)nhigh;
+                    row[LGDSP_COL_n_sat_low_cons] = (double)cons_low; row[LGDSP_COL_n_sat_high_cons] = (double)cons_high;
+                } else if (lane == 1) {
                     if (tlbad == 0.0) {
-                        const Stats ts = stats_finalize(tn, tsX, tsXX, tlS, tlSS, tlSX);
-                        row[LGDSP_COL_tail_mean] = ts.mean; row[LGDSP_COL_tail_sigma] = ts.sigma;
-                        row[LGDSP_COL_tail_tau] = div_rn(-1.0, ts.slope);
+                        row[LGDSP_COL_tail_mean] = st.mean; row[LGDSP_COL_tail_sigma] = st.sigma;
+                        row[LGDSP_COL_tail_tau] = div_rn(-1.0, st.slope);
                     }
                 } else {
-                    const Stats pz = stats_finalize(tn, tsX, tsXX, pzS, pzSS, pzSX);
-                    row[LGDSP_COL_tailmean] = pz.mean; row[LGDSP_COL_tailsigma] = pz.sigma;
-                    row[LGDSP_COL_tailslope] = pz.slope; row[LGDSP_COL_tailoffset] = pz.offset;
+                    row[LGDSP_COL_tailmean] = st.mean; row[LGDSP_COL_tailsigma] = st.sigma;
+                    row[LGDSP_COL_tailslope] = st.slope; row[LGDSP_COL_tailoffset] = st.offset;
                 }
             }
         } else if (wid == 1) {
             // interpolated crossings: lanes 0..4 t10..t99, lane 5 t0, lane 6 t0_inv; then drift_time = t90 - t0
+            // crossing resolution of the t0 / t0_inv masks (complete since B6) by this warp
+            int pos0, pos0i, mult_;
+            resolve_runs(masks + M_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
+            resolve_runs(masks + M_T0INV * NWORDS, P.t0_min_n, lane, pos0i, mult_);
             double t = 0.0;
             if (lane < 5) {
                 t = tx_us(lane);
                 if (G & LGDSP_GROUP_TIMING) row[LGDSP_COL_t10 + lane] = t;
             } else if (lane == 5 || lane == 6) {
-                t = t0_us(lane == 6);
+                t = t0_us(lane == 6, lane == 6 ? pos0i : pos0);
                 if (G & LGDSP_GROUP_TIMING) row[lane == 6 ? LGDSP_COL_t0_inv : LGDSP_COL_t0] = t;
             }
             const double t90 = __shfl_sync(FULL, t, 3), t0v = __shfl_sync(FULL, t, 5);
@@ -1702,40 +1822,44 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     }
                     row[LGDSP_COL_a_sg + f] = v;
                 }
+                // crossing resolution of the sg[0] masks (complete since B6), then t50_current and the in-trace pile-up
+                int posc, posp, multc, multp;
+                resolve_runs(masks + M_CUR * NWORDS, P.tx_min_n, lane, posc, multc);
+                resolve_runs(masks + M_PILE * NWORDS, P.intr_min_n, lane, posp, multp);
+                if (lane >= 4 && lane < 6) {
+                    const double tf = t_first + (double)P.sg[0].offset * dt;
+                    if (lane == 4) {
+                        // t50_current  src/dsp_icpc.jl:192-195
+                        double t = 0.0;
+                        if (posc >= 1) {
+                            t = cross_x(cur_thr, sg_at(0, posc - 1), sg_at(0, posc), tf + (double)(posc - 1) * dt, dt) * 0.001;
+                            if (t != t) t = 0.0;
+                        }
+                        row[LGDSP_COL_t50_current] = t;
+                    } else {
+                        // in-trace pile-up  src/dsp_routines.jl:72-82 (reversed trace r[j] = s[nsg-1-j], same time axis)
+                        double xi = CUDART_NAN;
+                        if (posp >= 1) {
+                            const double yl = sg_at(0, nsg - 1 - (posp - 1)), yr = sg_at(0, nsg - 1 - posp);
+                            xi = cross_x(pile_thr, yl, yr, tf + (double)(posp - 1) * dt, dt);
+                        }
+                        const double last_t = tf + (double)(nsg - 1) * dt;
+                        row[LGDSP_COL_inTrace_intersect] = last_t - xi;
+                        row[LGDSP_COL_inTrace_n] = (double)multp;
+                    }
+                }
             }
         } else if (wid == 7) {
             if (G & LGDSP_GROUP_QDRIFT) {
-                const double v = qdrift_warp(t0_us(false), P.qd_first, P.qd_last);   // qdrift @ t0
+                int pos0, mult_;
+                resolve_runs(masks + M_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
+                const double v = qdrift_warp(t0_us(false, pos0), P.qd_first, P.qd_last);   // qdrift @ t0
                 if (lane == 0) row[LGDSP_COL_qdrift] = v;
             }
         } else if (wid == 6) {
             if (G & LGDSP_GROUP_QDRIFT) {
                 const double v = qdrift_warp(tx_us(2), P.lq_first, P.lq_last);       // lq @ t80
                 if (lane == 0) row[LGDSP_COL_lq] = v;
-            }
-            if (lane < 2 && (G & LGDSP_GROUP_CURRENT)) {
-                const double tf = t_first + (double)P.sg[0].offset * dt;
-                if (lane == 0) {
-                    // t50_current  src/dsp_icpc.jl:192-195
-                    const int pos = ibuf[IB_POS0 + M_CUR];
-                    double t = 0.0;
-                    if (pos >= 1) {
-                        t = cross_x(cur_thr, sg_at(0, pos - 1), sg_at(0, pos), tf + (double)(pos - 1) * dt, dt) * 0.001;
-                        if (t != t) t = 0.0;
-                    }
-                    row[LGDSP_COL_t50_current] = t;
-                } else {
-                    // in-trace pile-up  src/dsp_routines.jl:72-82 (reversed trace r[j] = s[nsg-1-j], same time axis)
-                    const int pos = ibuf[IB_POS0 + M_PILE];
-                    double xi = CUDART_NAN;
-                    if (pos >= 1) {
-                        const double yl = sg_at(0, nsg - 1 - (pos - 1)), yr = sg_at(0, nsg - 1 - pos);
-                        xi = cross_x(pile_thr, yl, yr, tf + (double)(pos - 1) * dt, dt);
-                    }
-                    const double last_t = tf + (double)(nsg - 1) * dt;
-                    row[LGDSP_COL_inTrace_intersect] = last_t - xi;
-                    row[LGDSP_COL_inTrace_n] = (double)ibuf[IB_MULT];
-                }
             }
         }
         SECT(27);
