@@ -299,6 +299,20 @@ static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
     D.bl_from = p->bl_from; D.bl_until = p->bl_until; D.tail_from = p->tail_from; D.tail_until = p->tail_until;
     D.km1 = p->pz_km1;
     D.bl_inv_n = 1.0 / (double)(p->bl_until - p->bl_from + 1);
+    D.tail_inv_n = 1.0 / (double)(p->tail_until - p->tail_from + 1);
+    {
+        // sum_{i=a}^{b} X_i and X_i^2 with X_i = t_first + i*dt (configuration constants of the two regressions)
+        auto xs = [&](int a, int b, double& sX, double& sXX) {
+            typedef long double ld;
+            const ld t0 = p->t_first_ns, dt = p->dt_ns, cnt = (ld)(b - a + 1);
+            auto s2 = [](ld k) { return k * (k + 1.0L) * (2.0L * k + 1.0L) / 6.0L; };
+            const ld si = 0.5L * (ld)(a + b) * cnt, sii = s2((ld)b) - s2((ld)a - 1.0L);
+            sX = (double)(cnt * t0 + dt * si);
+            sXX = (double)(cnt * t0 * t0 + 2.0L * t0 * dt * si + dt * dt * sii);
+        };
+        xs(p->bl_from, p->bl_until, D.bl_sX, D.bl_sXX);
+        xs(p->tail_from, p->tail_until, D.tail_sX, D.tail_sXX);
+    }
     const int nw_sig = p->sig_dni.n_w, nw_int = p->int_dni.n_w;
     auto dni_ok = [](const lgdsp_dni& d) { return d.degree >= 0 && d.degree <= LGDSP_MAX_DNI_DEG && d.n_w > d.degree && d.n_w <= LGDSP_MAX_DNI; };
     if (!dni_ok(p->sig_dni) || !dni_ok(p->int_dni)) return fail(h, LGDSP_ERR_UNSUPPORTED, "PolynomialDNI window/degree outside the supported range");

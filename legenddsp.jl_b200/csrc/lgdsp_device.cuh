@@ -55,6 +55,8 @@ struct IcpcDev {
     int bl_from, bl_until, tail_from, tail_until;
     double km1;
     double bl_inv_n;        // 1/(number of baseline-window samples), as the reference's inv_n
+    double tail_inv_n;      // same for the tail window
+    double bl_sX, bl_sXX, tail_sX, tail_sXX;   // sum of X and X^2 (X = time of the sample) over the two windows
     TrapDev t0, t0inv, e10410, e535, e313, etrap;
     int t0inv_same, t0_min_n, tx_min_n, direct;
     double t0_thr;

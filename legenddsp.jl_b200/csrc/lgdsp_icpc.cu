@@ -182,9 +182,8 @@ __device__ __forceinline__ Run run_shfl_down(const Run& a, int o)
 struct Stats {
     double mean, sigma, slope, offset;
 };
-__device__ __noinline__ Stats stats_finalize(int n, double sX, double sXX, double sY, double sYY, double sXY)
+__device__ __noinline__ Stats stats_finalize(double inv_n, double sX, double sXX, double sY, double sYY, double sXY)
 {
-    const double inv_n = div_rn(1.0, (double)n);
     const double mean_X = mul_rn(sX, inv_n);
     const double mean_Y = mul_rn(sY, inv_n);
     const double var_X = sub_rn(mul_rn(sXX, inv_n), mul_rn(mean_X, mean_X));
@@ -197,17 +196,6 @@ __device__ __noinline__ Stats stats_finalize(int n, double sX, double sXX, doubl
     s.mean = mean_Y;
     s.sigma = sqrt(var_Y);
     return s;
-}
-
-// sum_{i=a}^{b} X_i and X_i^2 with X_i = t0 + i*dt
-__device__ __noinline__ void xsums(int a, int b, double t0, double dt, double& sX, double& sXX)
-{
-    const double cnt = (double)(b - a + 1);
-    const double si = 0.5 * (double)(a + b) * cnt;
-    auto s2 = [](double k) { return k * (k + 1.0) * (2.0 * k + 1.0) / 6.0; };
-    const double sii = s2((double)b) - s2((double)a - 1.0);
-    sX = cnt * t0 + dt * si;
-    sXX = cnt * t0 * t0 + 2.0 * t0 * dt * si + dt * dt * sii;
 }
 
 // extrema3points  src/interpolation.jl:8-10
@@ -292,7 +280,7 @@ __device__ __forceinline__ void mask_commit_reversed(uint32_t* M, int tid, unsig
 // that do not start at bit 0 -- the Intersect state machine: `pos` = start of the first such
 // run (-1 if none), `mult` = number of such runs.  Every lane looks for run STARTS (set bit after a clear bit) in its
 // 8 words and measures each run forward, word by word; M is left intact.
-__device__ __noinline__ void resolve_runs(const uint32_t* M, int k, int lane, int& pos, int& mult)
+__device__ __noinline__ int resolve_runs_packed(const uint32_t* M, int k, int lane)
 {
     constexpr int Q = NWORDS / 32;
     uint32_t m[Q];
@@ -328,8 +316,13 @@ __device__ __noinline__ void resolve_runs(const uint32_t* M, int k, int lane, in
     }
     p = __reduce_min_sync(FULL, p);
     cnt = __reduce_add_sync(FULL, cnt);
-    pos = (p == 0x7fffffff) ? -1 : p;
-    mult = cnt;
+    return ((p == 0x7fffffff) ? 0 : p + 1) | (cnt << 16);   // (pos + 1) in the low half, multiplicity in the high half
+}
+__device__ __forceinline__ void resolve_runs(const uint32_t* M, int k, int lane, int& pos, int& mult)
+{
+    const int r = resolve_runs_packed(M, k, lane);
+    pos = (r & 0xffff) - 1;
+    mult = r >> 16;
 }
 
 // linear interpolation of Intersect: x = (thr - y_l)*(x_r - x_l)/(y_r - y_l) + x_l
@@ -362,6 +355,29 @@ __device__ __noinline__ double dni_eval_warp(const double* __restrict__ A, int n
     }
 #pragma unroll
     for (int j = 0; j <= LGDSP_MAX_DNI_DEG; ++j) c[j] = warp_sum(c[j]);
+    double r = c[m - 1];
+    for (int j = m - 2; j >= 0; --j) r = r * u + c[j];
+    return r;
+}
+
+// Three PolynomialDNI estimates at once for windows of <= 8 samples: lanes [8g, 8g+8) work on estimate g (its window
+// start `from` and evaluation point `u` are per lane, equal inside a group); every lane of group g gets estimate g.
+// Same products and the same xor-4,2,1 reduction order as dni_eval_warp: bit-identical results.
+__device__ __noinline__ double dni3_warp(const double* __restrict__ A, int n_w, int m, const double* trace, int from, double u,
+                                         int lane)
+{
+    const int i = lane & 7;
+    const bool on = i < n_w && lane < 24;
+    const double v = on ? trace[from + i] : 0.0;
+    double c[LGDSP_MAX_DNI_DEG + 1] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j <= LGDSP_MAX_DNI_DEG; ++j)
+        if (on && j < m) c[j] = __ldg(A + i * m + j) * v;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j <= LGDSP_MAX_DNI_DEG; ++j) c[j] += __shfl_xor_sync(FULL, c[j], o);
+    }
     double r = c[m - 1];
     for (int j = m - 2; j >= 0; --j) r = r * u + c[j];
     return r;
@@ -1129,25 +1145,24 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 tl_SS = fma(lg, lg, tl_SS);
                 tl_SX = fma(X, lg, tl_SX);
             };
-            int idx = P.tail_from + tid;
 #pragma unroll 1
-            for (; idx + NT <= P.tail_until; idx += 2 * NT) {
-                const double w0 = u2d(xs[idx]) - m, w1 = u2d(xs[idx + NT]) - m;
+            for (int idx = P.tail_from + tid; idx <= P.tail_until; idx += 2 * NT) {
+                const bool two = idx + NT <= P.tail_until;
+                const double w0 = u2d(xs[idx]) - m, w1 = two ? u2d(xs[idx + NT]) - m : cref;
                 const double u0 = (w0 - cref) * cinv, u1 = (w1 - cref) * cinv;
-                if (cref > 0.0 && w0 > 0.0 && w1 > 0.0 && fabs(u0) <= 0.125 && fabs(u1) <= 0.125) {
+                if (two && cref > 0.0 && w0 > 0.0 && w1 > 0.0 && fabs(u0) <= 0.125 && fabs(u1) <= 0.125) {
                     // common case: both through the polynomial, interleaved
                     const double l0 = clog + log1p_small(u0), l1 = clog + log1p_small(u1);
                     const double X0 = t_first + (double)idx * dt, X1 = t_first + (double)(idx + NT) * dt;
                     tl_S += l0; tl_SS = fma(l0, l0, tl_SS); tl_SX = fma(X0, l0, tl_SX);
                     tl_S += l1; tl_SS = fma(l1, l1, tl_SS); tl_SX = fma(X1, l1, tl_SX);
                 } else {
-                    one(idx, w0, u0);
-                    one(idx + NT, w1, (w1 - cref) * cinv);
+#pragma unroll 1
+                    for (int q = 0; q < (two ? 2 : 1); ++q) {
+                        const double w = q ? w1 : w0;
+                        one(idx + q * NT, w, (w - cref) * cinv);
+                    }
                 }
-            }
-            if (idx <= P.tail_until) {
-                const double w0 = u2d(xs[idx]) - m;
-                one(idx, w0, (w0 - cref) * cinv);
             }
             tl_S = wsum_d(tl_S); tl_SS = wsum_d(tl_SS); tl_SX = wsum_d(tl_SX);
             const bool anybad = __any_sync(FULL, bad);
@@ -1342,6 +1357,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         // ==========================================================================================
         // P4a: decisions that need block-wide values; fine evaluation of the flagged intervals
         // ==========================================================================================
+        if (tid < 64) row[tid] = 0.0;
         // DNI windows of the three energy pick-offs (computed by the t50 warp in P3)
         double pk_p[3];
         int pk_from[3];
@@ -1537,6 +1553,192 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 if (f == 0) { czmax[0] = bm; czarg[0] = ba; } else { czmax[1] = bm; czarg[1] = ba; }
             }
         }
+        // ---- scalar results, one self-contained job per warp.  Everything that does not need the CUSP/ZAC outputs runs
+        //      while the candidate warps step their recurrences (scalar_jobs), the two CUSP/ZAC jobs after B6 ----
+        // t10..t99 [us] (k = 0..4) and t0 / t0_inv [us] from the resolved positions; NaN -> 0
+        auto tx_us = [&](int k) -> double {
+            const int pos = ibuf[IB_POS0 + M_T10 + k];
+            const double th = k == 0 ? thr[0] : k == 1 ? thr[1] : k == 2 ? thr[2] : k == 3 ? thr[3] : thr[4];
+            double t = 0.0;
+            if (pos >= 1) t = cross_x(th, y_at(TT, pos - 1), y_at(TT, pos), t_first + (double)(pos - 1) * dt, dt) * 0.001;
+            return t != t ? 0.0 : t;
+        };
+        auto t0_us = [&](bool inv, int pos) -> double {
+            const TrapDev& tr = inv ? P.t0inv : P.t0;
+            double t = 0.0;
+            if (pos >= 1) {
+                const double tl = t_first + (double)(pos - 1 + tr.L - 1) * dt;
+                const double sgn = inv ? -1.0 : 1.0;
+                t = cross_x(P.t0_thr, sgn * trap_at(TT, tr, pos - 1), sgn * trap_at(TT, tr, pos), tl, dt) * 0.001;
+            }
+            return t != t ? 0.0 : t;
+        };
+        // get_qdrift  src/dsp_routines.jl:51-64 on the integrator trace I[i] = TT[i+1], one warp
+        auto qdrift_warp = [&](double t_us, double first, double last) -> double {
+            const double tns = t_us * 1000.0;
+            if (P.int_dni.n_w <= 8) {
+                // the three estimates in parallel, 8 lanes each
+                const int g = lane >> 3;
+                const double ts = g == 0 ? tns : (g == 1 ? tns + first : tns + last);
+                double pc;
+                int from;
+                dni_window(P.int_dni.n_w, n, (ts - t_first) / dt, pc, from);
+                const double r = dni3_warp(A_int, P.int_dni.n_w, P.int_dni.m, TT + 1, from, pc - (double)from, lane);
+                const double a0 = __shfl_sync(FULL, r, 0), a1 = __shfl_sync(FULL, r, 8), a2 = __shfl_sync(FULL, r, 16);
+                return (a2 - a1) - (a1 - a0);
+            }
+            double a[3];
+#pragma unroll 1
+            for (int q = 0; q < 3; ++q) {
+                const double ts = q == 0 ? tns : (q == 1 ? tns + first : tns + last);
+                double pc;
+                int from;
+                dni_window(P.int_dni.n_w, n, (ts - t_first) / dt, pc, from);
+                a[q] = dni_eval_warp(A_int, P.int_dni.n_w, P.int_dni.m, TT + from + 1, pc - (double)from, lane);
+            }
+            const double area1 = a[1] - a[0], area2 = a[2] - a[1];
+            return area2 - area1;
+        };
+        auto scalar_jobs = [&]() {
+        if (wid == 0) {
+            // block-wide sums first (warp-collective), then lanes 0..2 finish one statistics block each (same code path):
+            // lane 0 baseline [:102], lane 1 tailstats [:115, src/tailstats.jl:22-72], lane 2 PZ tail stats [:123]
+            const double blS = red_sum(red, R_BLS), blSS = red_sum(red, R_BLSS), blSX = red_sum(red, R_BLSX);
+            const double tlS = red_sum(red, R_TLS), tlSS = red_sum(red, R_TLSS), tlSX = red_sum(red, R_TLSX);
+            const double tlbad = red_sum(red, R_TLBAD);
+            const double pzS = red_sum(red, R_PZS), pzSS = red_sum(red, R_PZSS), pzSX = red_sum(red, R_PZSX);
+            if (lane < 3) {
+                const double sY = lane == 0 ? blS : lane == 1 ? tlS : pzS;
+                const double sYY = lane == 0 ? blSS : lane == 1 ? tlSS : pzSS;
+                const double sXY = lane == 0 ? t_first * blS + dt * blSX : lane == 1 ? tlSX : pzSX;
+                const Stats st = stats_finalize(lane == 0 ? P.bl_inv_n : P.tail_inv_n, lane == 0 ? P.bl_sX : P.tail_sX,
+                                                lane == 0 ? P.bl_sXX : P.tail_sXX, sY, sYY, sXY);
+                if (lane == 0) {
+                    row[LGDSP_COL_blmean] = st.mean; row[LGDSP_COL_blsigma] = st.sigma;
+                    row[LGDSP_COL_blslope] = st.slope; row[LGDSP_COL_bloffset] = st.offset;
+                    row[LGDSP_COL_qc_label] = -1.0;
+                    row[LGDSP_COL_e_max] = e_max; row[LGDSP_COL_e_min] = e_min;
+                    row[LGDSP_COL_n_sat_low] = (double)nlow; row[LGDSP_COL_n_sat_high] = (double)nhigh;
+                    row[LGDSP_COL_n_sat_low_cons] = (double)cons_low; row[LGDSP_COL_n_sat_high_cons] = (double)cons_high;
+                } else if (lane == 1) {
+                    if (tlbad == 0.0) {
+                        row[LGDSP_COL_tail_mean] = st.mean; row[LGDSP_COL_tail_sigma] = st.sigma;
+                        row[LGDSP_COL_tail_tau] = div_rn(-1.0, st.slope);
+                    }
+                } else {
+                    row[LGDSP_COL_tailmean] = st.mean; row[LGDSP_COL_tailsigma] = st.sigma;
+                    row[LGDSP_COL_tailslope] = st.slope; row[LGDSP_COL_tailoffset] = st.offset;
+                }
+            }
+        } else if (wid == 1) {
+            // interpolated crossings: lanes 0..4 t10..t99, lane 5 t0, lane 6 t0_inv; then drift_time = t90 - t0
+            // crossing resolution of the t0 / t0_inv masks (complete since B6) by this warp
+            int pos0, pos0i, mult_;
+            resolve_runs(masks + M_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
+            resolve_runs(masks + M_T0INV * NWORDS, P.t0_min_n, lane, pos0i, mult_);
+            double t = 0.0;
+            if (lane < 5) {
+                t = tx_us(lane);
+                if (G & LGDSP_GROUP_TIMING) row[LGDSP_COL_t10 + lane] = t;
+            } else if (lane == 5 || lane == 6) {
+                t = t0_us(lane == 6, lane == 6 ? pos0i : pos0);
+                if (G & LGDSP_GROUP_TIMING) row[lane == 6 ? LGDSP_COL_t0_inv : LGDSP_COL_t0] = t;
+            }
+            const double t90 = __shfl_sync(FULL, t, 3), t0v = __shfl_sync(FULL, t, 5);
+            if (lane == 0 && (G & LGDSP_GROUP_TIMING)) row[LGDSP_COL_drift_time] = (t90 - t0v) * 1000.0;
+        } else if (wid == 2) {
+            if (G & LGDSP_GROUP_TRAPS) {
+                const double v = dni_eval_warp(A_sig, P.sig_dni.n_w, P.sig_dni.m, stash, pk_p[0] - (double)pk_from[0], lane);
+                double em;
+                int ea;
+                red_argmax(red, R_ETMAX, R_ETARG, em, ea);
+                const double a = red_max(red, R_E104), b = red_max(red, R_E535), c = red_max(red, R_E313);
+                const double d = red_max(red, R_E104N), f = red_max(red, R_E313N);
+                if (lane == 0) {
+                    row[LGDSP_COL_e_10410] = a; row[LGDSP_COL_e_535] = b; row[LGDSP_COL_e_313] = c;
+                    row[LGDSP_COL_e_10410_inv] = d; row[LGDSP_COL_e_313_inv] = f;
+                    row[LGDSP_COL_e_trap_max] = em;
+                    row[LGDSP_COL_t_trap_max] = t_first + (double)(ea + P.etrap.L - 1) * dt;
+                    row[LGDSP_COL_e_trap] = v;
+                }
+            }
+        } else if (wid == 5) {
+            if (G & LGDSP_GROUP_CURRENT) {
+                // get_wvf_maximum  src/interpolation.jl:30-46: parabola only if strictly inside the window
+                double vv[4];
+                int aa[4];
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const int fs = (f < 3 && P.sg_alias[f] >= 0) ? P.sg_alias[f] : f;   // aliased filter: same trace and window
+                    red_argmax(red, R_CMAX0 + fs, R_CARG0 + fs, vv[f], aa[f]);
+                }
+                if (lane < 4) {
+                    const int f = lane;
+                    double v = f == 0 ? vv[0] : f == 1 ? vv[1] : f == 2 ? vv[2] : vv[3];
+                    const int a = f == 0 ? aa[0] : f == 1 ? aa[1] : f == 2 ? aa[2] : aa[3];
+                    if (a > P.cur_from[f] && a < P.cur_until[f]) {
+                        const double y1 = (f < 3) ? sg_at(f, a - 1) : deriv_at(TT, a - 1);
+                        const double y3 = (f < 3) ? sg_at(f, a + 1) : deriv_at(TT, a + 1);
+                        v = extrema3(y1, v, y3);
+                    }
+                    row[LGDSP_COL_a_sg + f] = v;
+                }
+                // crossing resolution of the sg[0] masks (complete since B6), then t50_current and the in-trace pile-up
+                int posc, posp, multc, multp;
+                resolve_runs(masks + M_CUR * NWORDS, P.tx_min_n, lane, posc, multc);
+                resolve_runs(masks + M_PILE * NWORDS, P.intr_min_n, lane, posp, multp);
+                if (lane >= 4 && lane < 6) {
+                    const double tf = t_first + (double)P.sg[0].offset * dt;
+                    if (lane == 4) {
+                        // t50_current  src/dsp_icpc.jl:192-195
+                        double t = 0.0;
+                        if (posc >= 1) {
+                            t = cross_x(cur_thr, sg_at(0, posc - 1), sg_at(0, posc), tf + (double)(posc - 1) * dt, dt) * 0.001;
+                            if (t != t) t = 0.0;
+                        }
+                        row[LGDSP_COL_t50_current] = t;
+                    } else {
+                        // in-trace pile-up  src/dsp_routines.jl:72-82 (reversed trace r[j] = s[nsg-1-j], same time axis)
+                        double xi = CUDART_NAN;
+                        if (posp >= 1) {
+                            const double yl = sg_at(0, nsg - 1 - (posp - 1)), yr = sg_at(0, nsg - 1 - posp);
+                            xi = cross_x(pile_thr, yl, yr, tf + (double)(posp - 1) * dt, dt);
+                        }
+                        const double last_t = tf + (double)(nsg - 1) * dt;
+                        row[LGDSP_COL_inTrace_intersect] = last_t - xi;
+                        row[LGDSP_COL_inTrace_n] = (double)multp;
+                    }
+                }
+            }
+        } else if (wid == 7) {
+            if (G & LGDSP_GROUP_QDRIFT) {
+                int pos0, mult_;
+                resolve_runs(masks + M_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
+                const double v = qdrift_warp(t0_us(false, pos0), P.qd_first, P.qd_last);   // qdrift @ t0
+                if (lane == 0) row[LGDSP_COL_qdrift] = v;
+            }
+        } else if (wid == 6) {
+            if (G & LGDSP_GROUP_QDRIFT) {
+                const double v = qdrift_warp(tx_us(2), P.lq_first, P.lq_last);       // lq @ t80
+                if (lane == 0) row[LGDSP_COL_lq] = v;
+            }
+        }
+        };
+        // the queued intervals, spread over all warps; then the trapezoid partials of the block-wide maxima
+        auto run_queue = [&]() {
+            const int nq = min(ibuf[IB_QN], QCAP);
+#pragma unroll 1
+            for (int it = wid; it < nq; it += NWARP) {
+                const int code = qitems[it];
+                do_item(code >> 8, code & 255);
+            }
+            e535 = wmax_d(e535);
+            etmax = wargmax_d(etmax, etarg);
+            if (lane == 0) {
+                red[R_E535 * NWARP + wid] = e535;
+                red[R_ETMAX * NWARP + wid] = etmax; red[R_ETARG * NWARP + wid] = (double)etarg;
+            }
+        };
         bool queue_done = false;
 #pragma unroll 1
         for (int ps = 0; ps < npass; ++ps) {
@@ -1610,15 +1812,12 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             }
             SECT(22);
             // the queued intervals, spread over all warps (before the long recurrences of the candidate warps)
+            const bool last_pass = ps == npass - 1;
             if (!queue_done) {
-                const int nq = min(ibuf[IB_QN], QCAP);
-#pragma unroll 1
-                for (int it = wid; it < nq; it += NWARP) {
-                    const int code = qitems[it];
-                    do_item(code >> 8, code & 255);
-                }
+                run_queue();
                 queue_done = true;
             }
+            if (last_pass) __syncthreads();   // ---- Bq: masks and trapezoid partials are complete ----
             SECT(29);
             // rounds: recurrences of up to CZCAP candidate chunks write their outputs to SMEM, then the whole block
             // takes maxima / first argmaxima / pick-off windows from there
@@ -1630,6 +1829,8 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     cz_out(Z, TT, n, tid, st, czbuf + (size_t)(slot - r0) * (CH * 2));
                 }
                 SECT(23);
+                if (last_pass && r0 == 0) scalar_jobs();   // overlaps the recurrences of the candidate warps
+                SECT(27);
                 __syncthreads();   // ---- B5 ----
                 SECT(30);
                 const int ncz = ibuf[IB_CZN];
@@ -1658,135 +1859,27 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         if (npass == 0) {
             __syncthreads();   // ---- B4 (no structured CUSP/ZAC) ----
             LGDSP_PHASE(4);
-            const int nq = min(ibuf[IB_QN], QCAP);
-#pragma unroll 1
-            for (int it = wid; it < nq; it += NWARP) {
-                const int code = qitems[it];
-                do_item(code >> 8, code & 255);
-            }
+            run_queue();
+            __syncthreads();   // ---- Bq ----
+            scalar_jobs();
         }
 
-        // final partials
+        // CUSP/ZAC partials
         {
-            e535 = wmax_d(e535);
-            etmax = wargmax_d(etmax, etarg);
             czmax[0] = wargmax_d(czmax[0], czarg[0]);
             czmax[1] = wargmax_d(czmax[1], czarg[1]);
             if (lane == 0) {
-                red[R_E535 * NWARP + wid] = e535;
-                red[R_ETMAX * NWARP + wid] = etmax; red[R_ETARG * NWARP + wid] = (double)etarg;
                 red[R_CZMAX0 * NWARP + wid] = czmax[0]; red[R_CZARG0 * NWARP + wid] = (double)czarg[0];
                 red[R_CZMAX1 * NWARP + wid] = czmax[1]; red[R_CZARG1 * NWARP + wid] = (double)czarg[1];
             }
         }
         SECT(24);
         SECT(25);
-        if (tid < 64) row[tid] = 0.0;
         __syncthreads();   // ---- B6 ----
         LGDSP_PHASE(5);
         SECT(26);
 
-        // ==========================================================================================
-        // P5: scalar results, spread over the warps (every warp is self-contained: no barrier in between)
-        // ==========================================================================================
-        // t10..t99 [us] (k = 0..4) and t0 / t0_inv [us] from the resolved positions; NaN -> 0
-        auto tx_us = [&](int k) -> double {
-            const int pos = ibuf[IB_POS0 + M_T10 + k];
-            const double th = k == 0 ? thr[0] : k == 1 ? thr[1] : k == 2 ? thr[2] : k == 3 ? thr[3] : thr[4];
-            double t = 0.0;
-            if (pos >= 1) t = cross_x(th, y_at(TT, pos - 1), y_at(TT, pos), t_first + (double)(pos - 1) * dt, dt) * 0.001;
-            return t != t ? 0.0 : t;
-        };
-        auto t0_us = [&](bool inv, int pos) -> double {
-            const TrapDev& tr = inv ? P.t0inv : P.t0;
-            double t = 0.0;
-            if (pos >= 1) {
-                const double tl = t_first + (double)(pos - 1 + tr.L - 1) * dt;
-                const double sgn = inv ? -1.0 : 1.0;
-                t = cross_x(P.t0_thr, sgn * trap_at(TT, tr, pos - 1), sgn * trap_at(TT, tr, pos), tl, dt) * 0.001;
-            }
-            return t != t ? 0.0 : t;
-        };
-        // get_qdrift  src/dsp_routines.jl:51-64 on the integrator trace I[i] = TT[i+1], one warp
-        auto qdrift_warp = [&](double t_us, double first, double last) -> double {
-            const double tns = t_us * 1000.0;
-            double a[3];
-#pragma unroll 1
-            for (int q = 0; q < 3; ++q) {
-                const double ts = q == 0 ? tns : (q == 1 ? tns + first : tns + last);
-                double pc;
-                int from;
-                dni_window(P.int_dni.n_w, n, (ts - t_first) / dt, pc, from);
-                a[q] = dni_eval_warp(A_int, P.int_dni.n_w, P.int_dni.m, TT + from + 1, pc - (double)from, lane);
-            }
-            const double area1 = a[1] - a[0], area2 = a[2] - a[1];
-            return area2 - area1;
-        };
-        if (wid == 0) {
-            // block-wide sums first (warp-collective), then lanes 0..2 finish one statistics block each (same code path):
-            // lane 0 baseline [:102], lane 1 tailstats [:115, src/tailstats.jl:22-72], lane 2 PZ tail stats [:123]
-            const double blS = red_sum(red, R_BLS), blSS = red_sum(red, R_BLSS), blSX = red_sum(red, R_BLSX);
-            const double tlS = red_sum(red, R_TLS), tlSS = red_sum(red, R_TLSS), tlSX = red_sum(red, R_TLSX);
-            const double tlbad = red_sum(red, R_TLBAD);
-            const double pzS = red_sum(red, R_PZS), pzSS = red_sum(red, R_PZSS), pzSX = red_sum(red, R_PZSX);
-            if (lane < 3) {
-                const int from = lane == 0 ? P.bl_from : P.tail_from, until = lane == 0 ? P.bl_until : P.tail_until;
-                const double sY = lane == 0 ? blS : lane == 1 ? tlS : pzS;
-                const double sYY = lane == 0 ? blSS : lane == 1 ? tlSS : pzSS;
-                const double sXY = lane == 0 ? t_first * blS + dt * blSX : lane == 1 ? tlSX : pzSX;
-                double sX, sXX;
-                xsums(from, until, t_first, dt, sX, sXX);
-                const Stats st = stats_finalize(until - from + 1, sX, sXX, sY, sYY, sXY);
-                if (lane == 0) {
-                    row[LGDSP_COL_blmean] = st.mean; row[LGDSP_COL_blsigma] = st.sigma;
-                    row[LGDSP_COL_blslope] = st.slope; row[LGDSP_COL_bloffset] = st.offset;
-                    row[LGDSP_COL_qc_label] = -1.0;
-                    row[LGDSP_COL_e_max] = e_max; row[LGDSP_COL_e_min] = e_min;
-                    row[LGDSP_COL_n_sat_low] = (double)nlow; row[LGDSP_COL_n_sat_high] = (double)nhigh;
-                    row[LGDSP_COL_n_sat_low_cons] = (double)cons_low; row[LGDSP_COL_n_sat_high_cons] = (double)cons_high;
-                } else if (lane == 1) {
-                    if (tlbad == 0.0) {
-                        row[LGDSP_COL_tail_mean] = st.mean; row[LGDSP_COL_tail_sigma] = st.sigma;
-                        row[LGDSP_COL_tail_tau] = div_rn(-1.0, st.slope);
-                    }
-                } else {
-                    row[LGDSP_COL_tailmean] = st.mean; row[LGDSP_COL_tailsigma] = st.sigma;
-                    row[LGDSP_COL_tailslope] = st.slope; row[LGDSP_COL_tailoffset] = st.offset;
-                }
-            }
-        } else if (wid == 1) {
-            // interpolated crossings: lanes 0..4 t10..t99, lane 5 t0, lane 6 t0_inv; then drift_time = t90 - t0
-            // crossing resolution of the t0 / t0_inv masks (complete since B6) by this warp
-            int pos0, pos0i, mult_;
-            resolve_runs(masks + M_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
-            resolve_runs(masks + M_T0INV * NWORDS, P.t0_min_n, lane, pos0i, mult_);
-            double t = 0.0;
-            if (lane < 5) {
-                t = tx_us(lane);
-                if (G & LGDSP_GROUP_TIMING) row[LGDSP_COL_t10 + lane] = t;
-            } else if (lane == 5 || lane == 6) {
-                t = t0_us(lane == 6, lane == 6 ? pos0i : pos0);
-                if (G & LGDSP_GROUP_TIMING) row[lane == 6 ? LGDSP_COL_t0_inv : LGDSP_COL_t0] = t;
-            }
-            const double t90 = __shfl_sync(FULL, t, 3), t0v = __shfl_sync(FULL, t, 5);
-            if (lane == 0 && (G & LGDSP_GROUP_TIMING)) row[LGDSP_COL_drift_time] = (t90 - t0v) * 1000.0;
-        } else if (wid == 2) {
-            if (G & LGDSP_GROUP_TRAPS) {
-                const double v = dni_eval_warp(A_sig, P.sig_dni.n_w, P.sig_dni.m, stash, pk_p[0] - (double)pk_from[0], lane);
-                double em;
-                int ea;
-                red_argmax(red, R_ETMAX, R_ETARG, em, ea);
-                const double a = red_max(red, R_E104), b = red_max(red, R_E535), c = red_max(red, R_E313);
-                const double d = red_max(red, R_E104N), f = red_max(red, R_E313N);
-                if (lane == 0) {
-                    row[LGDSP_COL_e_10410] = a; row[LGDSP_COL_e_535] = b; row[LGDSP_COL_e_313] = c;
-                    row[LGDSP_COL_e_10410_inv] = d; row[LGDSP_COL_e_313_inv] = f;
-                    row[LGDSP_COL_e_trap_max] = em;
-                    row[LGDSP_COL_t_trap_max] = t_first + (double)(ea + P.etrap.L - 1) * dt;
-                    row[LGDSP_COL_e_trap] = v;
-                }
-            }
-        } else if (wid == 3 || wid == 4) {
+        if (wid == 3 || wid == 4) {
             if (cz_on) {
                 const int f = wid - 3;
                 const double v = dni_eval_warp(A_sig, P.sig_dni.n_w, P.sig_dni.m, stash + (1 + f) * LGDSP_MAX_DNI,
@@ -1801,68 +1894,8 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     row[f ? LGDSP_COL_e_zac : LGDSP_COL_e_cusp] = v;
                 }
             }
-        } else if (wid == 5) {
-            if (G & LGDSP_GROUP_CURRENT) {
-                // get_wvf_maximum  src/interpolation.jl:30-46: parabola only if strictly inside the window
-                double vv[4];
-                int aa[4];
-#pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    const int fs = (f < 3 && P.sg_alias[f] >= 0) ? P.sg_alias[f] : f;   // aliased filter: same trace and window
-                    red_argmax(red, R_CMAX0 + fs, R_CARG0 + fs, vv[f], aa[f]);
-                }
-                if (lane < 4) {
-                    const int f = lane;
-                    double v = f == 0 ? vv[0] : f == 1 ? vv[1] : f == 2 ? vv[2] : vv[3];
-                    const int a = f == 0 ? aa[0] : f == 1 ? aa[1] : f == 2 ? aa[2] : aa[3];
-                    if (a > P.cur_from[f] && a < P.cur_until[f]) {
-                        const double y1 = (f < 3) ? sg_at(f, a - 1) : deriv_at(TT, a - 1);
-                        const double y3 = (f < 3) ? sg_at(f, a + 1) : deriv_at(TT, a + 1);
-                        v = extrema3(y1, v, y3);
-                    }
-                    row[LGDSP_COL_a_sg + f] = v;
-                }
-                // crossing resolution of the sg[0] masks (complete since B6), then t50_current and the in-trace pile-up
-                int posc, posp, multc, multp;
-                resolve_runs(masks + M_CUR * NWORDS, P.tx_min_n, lane, posc, multc);
-                resolve_runs(masks + M_PILE * NWORDS, P.intr_min_n, lane, posp, multp);
-                if (lane >= 4 && lane < 6) {
-                    const double tf = t_first + (double)P.sg[0].offset * dt;
-                    if (lane == 4) {
-                        // t50_current  src/dsp_icpc.jl:192-195
-                        double t = 0.0;
-                        if (posc >= 1) {
-                            t = cross_x(cur_thr, sg_at(0, posc - 1), sg_at(0, posc), tf + (double)(posc - 1) * dt, dt) * 0.001;
-                            if (t != t) t = 0.0;
-                        }
-                        row[LGDSP_COL_t50_current] = t;
-                    } else {
-                        // in-trace pile-up  src/dsp_routines.jl:72-82 (reversed trace r[j] = s[nsg-1-j], same time axis)
-                        double xi = CUDART_NAN;
-                        if (posp >= 1) {
-                            const double yl = sg_at(0, nsg - 1 - (posp - 1)), yr = sg_at(0, nsg - 1 - posp);
-                            xi = cross_x(pile_thr, yl, yr, tf + (double)(posp - 1) * dt, dt);
-                        }
-                        const double last_t = tf + (double)(nsg - 1) * dt;
-                        row[LGDSP_COL_inTrace_intersect] = last_t - xi;
-                        row[LGDSP_COL_inTrace_n] = (double)multp;
-                    }
-                }
-            }
-        } else if (wid == 7) {
-            if (G & LGDSP_GROUP_QDRIFT) {
-                int pos0, mult_;
-                resolve_runs(masks + M_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
-                const double v = qdrift_warp(t0_us(false, pos0), P.qd_first, P.qd_last);   // qdrift @ t0
-                if (lane == 0) row[LGDSP_COL_qdrift] = v;
-            }
-        } else if (wid == 6) {
-            if (G & LGDSP_GROUP_QDRIFT) {
-                const double v = qdrift_warp(tx_us(2), P.lq_first, P.lq_last);       // lq @ t80
-                if (lane == 0) row[LGDSP_COL_lq] = v;
-            }
         }
-        SECT(27);
+        SECT(28);
         __syncthreads();   // ---- B8 ----
         LGDSP_PHASE(6);
         SECT(28);
