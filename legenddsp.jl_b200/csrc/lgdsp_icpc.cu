@@ -283,25 +283,23 @@ __device__ __forceinline__ void mask_commit_reversed(uint32_t* M, int tid, unsig
 __device__ __noinline__ int resolve_runs_packed(const uint32_t* M, int k, int lane)
 {
     constexpr int Q = NWORDS / 32;
-    uint32_t m[Q];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) m[q] = M[lane * Q + q];
-    uint32_t prev_top = __shfl_up_sync(FULL, m[Q - 1], 1);
-    if (lane == 0) prev_top = 0;
     int p = 0x7fffffff, cnt = 0;
-#pragma unroll
+    uint32_t prev = lane ? M[lane * Q - 1] : 0u;
+#pragma unroll 1
     for (int q = 0; q < Q; ++q) {
-        const uint32_t carry = ((q == 0) ? prev_top : m[q - 1]) >> 31;
-        uint32_t starts = m[q] & ~((m[q] << 1) | carry);
-        if (lane == 0 && q == 0) starts &= ~1u;  // a run that starts at the first sample never fires
+        const int w0 = lane * Q + q;
+        const uint32_t mq = M[w0];
+        uint32_t starts = mq & ~((mq << 1) | (prev >> 31));
+        prev = mq;
+        if (w0 == 0) starts &= ~1u;  // a run that starts at the first sample never fires
         while (starts) {
             const int b = __ffs(starts) - 1;
             starts &= starts - 1;
-            const uint32_t rest = ~(m[q] >> b);            // first clear bit above b (the shifted-in zeros stop it at the word end)
+            const uint32_t rest = ~(mq >> b);            // first clear bit above b (the shifted-in zeros stop it at the word end)
             int len = rest ? __ffs(rest) - 1 : 32;
             if (len == 32 - b) {
                 // the run reaches the top of its word: follow it through the next words
-                for (int w = lane * Q + q + 1; w < NWORDS && len < k; ++w) {
+                for (int w = w0 + 1; w < NWORDS && len < k; ++w) {
                     const uint32_t x = M[w];
                     if (x == 0xffffffffu) { len += 32; continue; }
                     len += __ffs(~x) - 1;
@@ -310,7 +308,7 @@ __device__ __noinline__ int resolve_runs_packed(const uint32_t* M, int k, int la
             }
             if (len >= k) {
                 ++cnt;
-                p = min(p, (lane * Q + q) * 32 + b);
+                p = min(p, w0 * 32 + b);
             }
         }
     }
@@ -342,22 +340,23 @@ __device__ __noinline__ void dni_window(int n_w, int n_trace, double p, double& 
     pc = p;
     from = (int)f;
 }
-// PolynomialDNI estimate, one warp: window values win[0..n_w) (SMEM/any), fit matrix A (global); result in every lane
+// PolynomialDNI estimate, one warp: window values win[0..n_w) (SMEM/any), fit matrix A (global); result in every lane.
+// (coefficients beyond the degree are zero, so the fixed-length Horner scheme gives the same value as a shorter one)
 __device__ __noinline__ double dni_eval_warp(const double* __restrict__ A, int n_w, int m, const double* win, double u,
                                                 int lane)
 {
-    double c[LGDSP_MAX_DNI_DEG + 1] = {0, 0, 0, 0};
+    double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll 1
     for (int i = lane; i < n_w; i += 32) {
         const double v = win[i];
-#pragma unroll
-        for (int j = 0; j <= LGDSP_MAX_DNI_DEG; ++j)
-            if (j < m) c[j] = fma(__ldg(A + i * m + j), v, c[j]);
+        const double* a = A + i * m;
+        c0 = fma(__ldg(a), v, c0);
+        if (m > 1) c1 = fma(__ldg(a + 1), v, c1);
+        if (m > 2) c2 = fma(__ldg(a + 2), v, c2);
+        if (m > 3) c3 = fma(__ldg(a + 3), v, c3);
     }
-#pragma unroll
-    for (int j = 0; j <= LGDSP_MAX_DNI_DEG; ++j) c[j] = warp_sum(c[j]);
-    double r = c[m - 1];
-    for (int j = m - 2; j >= 0; --j) r = r * u + c[j];
-    return r;
+    c0 = wsum_d(c0); c1 = wsum_d(c1); c2 = wsum_d(c2); c3 = wsum_d(c3);
+    return fma(fma(fma(c3, u, c2), u, c1), u, c0);
 }
 
 // Three PolynomialDNI estimates at once for windows of <= 8 samples: lanes [8g, 8g+8) work on estimate g (its window
@@ -369,18 +368,22 @@ __device__ __noinline__ double dni3_warp(const double* __restrict__ A, int n_w, 
     const int i = lane & 7;
     const bool on = i < n_w && lane < 24;
     const double v = on ? trace[from + i] : 0.0;
-    double c[LGDSP_MAX_DNI_DEG + 1] = {0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j <= LGDSP_MAX_DNI_DEG; ++j)
-        if (on && j < m) c[j] = __ldg(A + i * m + j) * v;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-#pragma unroll
-        for (int j = 0; j <= LGDSP_MAX_DNI_DEG; ++j) c[j] += __shfl_xor_sync(FULL, c[j], o);
+    double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    if (on) {
+        const double* a = A + i * m;
+        c0 = __ldg(a) * v;
+        if (m > 1) c1 = __ldg(a + 1) * v;
+        if (m > 2) c2 = __ldg(a + 2) * v;
+        if (m > 3) c3 = __ldg(a + 3) * v;
     }
-    double r = c[m - 1];
-    for (int j = m - 2; j >= 0; --j) r = r * u + c[j];
-    return r;
+#pragma unroll 1
+    for (int o = 4; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(FULL, c0, o);
+        c1 += __shfl_xor_sync(FULL, c1, o);
+        c2 += __shfl_xor_sync(FULL, c2, o);
+        c3 += __shfl_xor_sync(FULL, c3, o);
+    }
+    return fma(fma(fma(c3, u, c2), u, c1), u, c0);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1431,6 +1434,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             }
         };
         // ---- coarse-to-fine trapezoids: lane i of warp w owns the interval (33q, 33q+33), q = 32w + i ----
+        unsigned flags = 0;
         {
             bool f0 = false, fi = false, f5 = false, fe = false;
             if (G & LGDSP_GROUP_TIMING) {
@@ -1472,28 +1476,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 if (i0 + 1 < P.e535.nout) f5 = interval_bound(c5a, c5b, i0 + CH < P.e535.nout, k5) + kslack >= M5;
                 if (i0 + 1 < P.etrap.nout) fe = interval_bound(cea, ceb, i0 + CH < P.etrap.nout, ke) + kslack >= Me;
             }
-            // flagged intervals go to a block-wide work queue (processed by all warps after B4, so the pulse-region
-            // warp does not evaluate all of them alone); what does not fit is evaluated right away by the owning warp
-            auto push = [&](int type, bool flag) {
-                const unsigned b = __ballot_sync(FULL, flag);
-                if (b == 0u) return;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&ibuf[IB_QN], __popc(b));
-                base = __shfl_sync(FULL, base, 0);
-                const int idx = base + __popc(b & ((1u << lane) - 1u));
-                const bool fits = idx < QCAP;
-                if (flag && fits) qitems[idx] = (uint16_t)((type << 8) | tid);
-                unsigned bo = __ballot_sync(FULL, flag && !fits);
-                while (bo) {
-                    const int i = __ffs(bo) - 1;
-                    bo &= bo - 1;
-                    do_item(type, wid * 32 + i);
-                }
-            };
-            push(0, f0);
-            push(1, fi);
-            push(2, f5);
-            push(3, fe);
+            flags = (f0 ? 1u : 0u) | (fi ? 2u : 0u) | (f5 ? 4u : 0u) | (fe ? 8u : 0u);
         }
         SECT(18);
 
@@ -1513,20 +1496,25 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     mask_commit(masks + M_CUR * NWORDS, tid, bc);
                     mask_commit_reversed(masks + M_PILE * NWORDS, tid, bp, nsg);
                 }
-            } else if (bf) {
-                // few: queued, a warp evaluates one chunk with one output per lane (same operation order: identical values)
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&ibuf[IB_QN], __popc(bf));
-                base = __shfl_sync(FULL, base, 0);
-                const int idx = base + __popc(bf & ((1u << lane) - 1u));
-                const bool fits = idx < QCAP;
-                if (flag && fits) qitems[idx] = (uint16_t)((4 << 8) | tid);
-                unsigned bo = __ballot_sync(FULL, flag && !fits);
-                while (bo) {
-                    const int i = __ffs(bo) - 1;
-                    bo &= bo - 1;
-                    do_item(4, wid * 32 + i);
-                }
+            } else if (flag) {
+                flags |= 16u;   // few: queued, a warp evaluates one chunk with one output per lane (identical values)
+            }
+        }
+        // flagged intervals / chunks go to a block-wide work queue (processed by all warps after B4, so the pulse-region
+        // warp does not evaluate all of them alone); what does not fit stays with the owning warp (ovf bits)
+        unsigned ovf = 0;
+#pragma unroll 1
+        for (int type = 0; type < 5; ++type) {
+            const bool flag = (flags >> type) & 1u;
+            const unsigned b = __ballot_sync(FULL, flag);
+            if (b == 0u) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&ibuf[IB_QN], __popc(b));
+            base = __shfl_sync(FULL, base, 0);
+            const int idx = base + __popc(b & ((1u << lane) - 1u));
+            if (flag) {
+                if (idx < QCAP) qitems[idx] = (uint16_t)((type << 8) | tid);
+                else ovf |= 1u << type;
             }
         }
         SECT(19);
@@ -1727,10 +1715,28 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         // the queued intervals, spread over all warps; then the trapezoid partials of the block-wide maxima
         auto run_queue = [&]() {
             const int nq = min(ibuf[IB_QN], QCAP);
+            int it = wid, otype = 0;
+            unsigned ob = __ballot_sync(FULL, ovf & 1u);
 #pragma unroll 1
-            for (int it = wid; it < nq; it += NWARP) {
-                const int code = qitems[it];
-                do_item(code >> 8, code & 255);
+            for (;;) {
+                int type, q;
+                if (it < nq) {
+                    const int code = qitems[it];
+                    it += NWARP;
+                    type = code >> 8;
+                    q = code & 255;
+                } else {
+                    while (ob == 0u && otype < 4) {
+                        ++otype;
+                        ob = __ballot_sync(FULL, (ovf >> otype) & 1u);
+                    }
+                    if (ob == 0u) break;
+                    const int i = __ffs(ob) - 1;
+                    ob &= ob - 1;
+                    type = otype;
+                    q = wid * 32 + i;
+                }
+                do_item(type, q);
             }
             e535 = wmax_d(e535);
             etmax = wargmax_d(etmax, etarg);
@@ -1740,10 +1746,12 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             }
         };
         bool queue_done = false;
+        const int np = max(npass, 1);
 #pragma unroll 1
-        for (int ps = 0; ps < npass; ++ps) {
+        for (int ps = 0; ps < np; ++ps) {
+            const bool czp = ps < npass;   // structured CUSP/ZAC pass (otherwise only the queue and the scalar jobs)
             const CzDev& Z = P.cz[ps];
-            const bool want_cusp = P.cz_shared || ps == 0, want_zac = P.cz_shared || ps == 1;
+            const bool want_cusp = czp && (P.cz_shared || ps == 0), want_zac = czp && (P.cz_shared || ps == 1);
             if (ps > 0) {
                 __syncthreads();   // the previous pass is done with the tables, the coarse values and the output buffer
                 if (tid == 0) ibuf[IB_CZN] = 0;
@@ -1751,18 +1759,19 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 __syncthreads();
             }
             CzState st;
-            cz_init(Z, TT, n, tid, tabA, tabB, scr[SC_PP0], st);
-            double oc, oz;
-            cz_coarse(Z, TT, n, tid, st, oc, oz);
-            if (!want_cusp) oc = -CUDART_INF;
-            if (!want_zac) oz = -CUDART_INF;
-            // the coarse points are outputs themselves
-            const int j0 = i0 - Z.L + 1;
-            if (oc > czmax[0]) { czmax[0] = oc; czarg[0] = j0; }
-            if (oz > czmax[1]) { czmax[1] = oz; czarg[1] = j0; }
-            czco[tid] = oc;
-            czco[NT + tid] = oz;
-            {
+            st.active = false;
+            double oc = -CUDART_INF, oz = -CUDART_INF;
+            if (czp) {
+                cz_init(Z, TT, n, tid, tabA, tabB, scr[SC_PP0], st);
+                cz_coarse(Z, TT, n, tid, st, oc, oz);
+                if (!want_cusp) oc = -CUDART_INF;
+                if (!want_zac) oz = -CUDART_INF;
+                // the coarse points are outputs themselves
+                const int j0 = i0 - Z.L + 1;
+                if (oc > czmax[0]) { czmax[0] = oc; czarg[0] = j0; }
+                if (oz > czmax[1]) { czmax[1] = oz; czarg[1] = j0; }
+                czco[tid] = oc;
+                czco[NT + tid] = oz;
                 const double wc = wmax_d(oc), wz = wmax_d(oz);
                 red_put(red, R_CZC0, wid, lane, wc);
                 red_put(red, R_CZC1, wid, lane, wz);
@@ -1771,12 +1780,13 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             __syncthreads();   // ---- B4: tables are dead, coarse values and the work queue are complete ----
             LGDSP_PHASE(4);
             SECT(21);
-            if (ps == npass - 1) prefetch_next();   // every thread has read its table entries: xs may be overwritten
+            if (czp && ps == npass - 1) prefetch_next();   // every thread has read its table entries: xs may be overwritten
             // candidate chunks: Lipschitz bound on (33 tid, 33 tid + 33) against the best coarse value; chunks that
             // hold part of a pick-off window are always evaluated
-            const double Mc = red_max(red, R_CZC0), Mz = red_max(red, R_CZC1);
+            double Mc = 0.0, Mz = 0.0;
+            if (czp) { Mc = red_max(red, R_CZC0); Mz = red_max(red, R_CZC1); }
             bool cand = false;
-            if (st.active) {
+            if (czp && st.active) {
                 const int t1 = min(tid + 1, NT - 1);
                 const double kap = Ymax * 1.000001;
                 const int jlo = i0 - Z.L + 1, jhi = jlo + CH - 1;
@@ -1812,7 +1822,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             }
             SECT(22);
             // the queued intervals, spread over all warps (before the long recurrences of the candidate warps)
-            const bool last_pass = ps == npass - 1;
+            const bool last_pass = ps == np - 1;
             if (!queue_done) {
                 run_queue();
                 queue_done = true;
@@ -1833,7 +1843,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 SECT(27);
                 __syncthreads();   // ---- B5 ----
                 SECT(30);
-                const int ncz = ibuf[IB_CZN];
+                const int ncz = czp ? ibuf[IB_CZN] : 0;
                 const int nslot = min(ncz - r0, CZCAP);
                 const int nw = P.sig_dni.n_w;
 #pragma unroll 1
@@ -1856,14 +1866,6 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 __syncthreads();   // the buffer is reused by the next round
             }
         }
-        if (npass == 0) {
-            __syncthreads();   // ---- B4 (no structured CUSP/ZAC) ----
-            LGDSP_PHASE(4);
-            run_queue();
-            __syncthreads();   // ---- Bq ----
-            scalar_jobs();
-        }
-
         // CUSP/ZAC partials
         {
             czmax[0] = wargmax_d(czmax[0], czarg[0]);
