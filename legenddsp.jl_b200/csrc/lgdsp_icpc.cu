@@ -252,7 +252,7 @@ __device__ __forceinline__ double fir_at(const double* TT, const double* __restr
 }
 
 // thread-local 33-bit mask -> block mask (bit position 33*tid + k)
-__device__ __forceinline__ void mask_commit(uint32_t* M, int tid, unsigned long long bits)
+__device__ __noinline__ void mask_commit(uint32_t* M, int tid, unsigned long long bits)
 {
     if (bits == 0ull) return;
     const int p0 = tid * CH, w0 = p0 >> 5, s0 = p0 & 31;
@@ -262,7 +262,7 @@ __device__ __forceinline__ void mask_commit(uint32_t* M, int tid, unsigned long 
     if (mid && w0 + 1 < NWORDS) atomicOr(&M[w0 + 1], mid);
 }
 // same for the time-reversed trace of length nlen: forward bit i <-> reversed bit nlen-1-i
-__device__ __forceinline__ void mask_commit_reversed(uint32_t* M, int tid, unsigned long long bits, int nlen)
+__device__ __noinline__ void mask_commit_reversed(uint32_t* M, int tid, unsigned long long bits, int nlen)
 {
     if (bits == 0ull) return;
     // reversed positions of the chunk: base = nlen-1-(33*tid+32) holds forward bit 32, base+32 holds forward bit 0
@@ -455,6 +455,8 @@ __device__ __forceinline__ void sg_chunk(const double* TT, const SgDev& S, int j
 // recurrences 33 times.  The growing exponentials are only propagated over 33 samples, so nothing blows up.
 // (validated against the direct FIR in tools/proto_cuspzac.py and tests/test_gpu_*.py)
 // ==================================================================================================
+__device__ __noinline__ double exp_d(double x) { return exp(x); }
+
 struct CzState {
     double EmL, EpL, W0L, W1L, W2L, W0F, V0, V1, V2, EpR, EmR;
     bool active;
@@ -527,8 +529,10 @@ __device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, d
             }
         };
 #pragma unroll 1
-        for (int ev = 0; ev < Z.n_ev; ++ev) {
-            run_to(Z.ev_k[ev]);
+        for (int ev = 0; ev <= Z.n_ev; ++ev) {
+            const bool last = ev == Z.n_ev;            // pseudo event: the rest of the chunk, nothing to capture
+            run_to(last ? CH - 1 : Z.ev_k[ev]);
+            if (last) break;
             const int tb = Z.ev_tab[ev];
             if (Z.ev_kind[ev] == 0) {
                 cz_tab(tabA, tabB, tb * 3 + 0)[tid] = pm;
@@ -538,12 +542,11 @@ __device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, d
                 cz_tab(tabA, tabB, 12 + tb)[tid] = acc;
             }
         }
-        run_to(CH - 1);
     }
     const double pp = acc;   // P+ of the chunk alone at its first sample
     // warp-level scans (linear recurrences with constant multiplier rho^CH; plain sums for the moments)
     double vpm = pm, vd1 = d1, vd2 = d2, vpp = pp;
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < 5; ++s) {
         const int o = 1 << s;
         const double upm = __shfl_up_sync(FULL, vpm, o), ud1 = __shfl_up_sync(FULL, vd1, o), ud2 = __shfl_up_sync(FULL, vd2, o);
@@ -598,7 +601,7 @@ __device__ __forceinline__ void cz_init(const CzDev& Z, const double* TT, int n,
     };
     auto la = [&](int q, int pos) -> double {             // anti-causal prefix P+
         if (pos >= n) return 0.0;
-        if (pos < 0) return exp((double)pos * Z.inv_sigma) * pp0;   // rho^(-pos) * P+[0]
+        if (pos < 0) return exp_d((double)pos * Z.inv_sigma) * pp0;   // rho^(-pos) * P+[0]
         return cz_tab(tabA, tabB, 12 + q)[pos / CH];
     };
     auto d0 = [&](int j) -> double {                      // D0[j] = sum_{i<=j} d[i] = TT[j+1] - r*TT[j]
