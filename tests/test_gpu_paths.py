@@ -1,0 +1,108 @@
+"""GPU parity tests aimed at the data-dependent paths of the fused kernel (coarse-to-fine pruning, work queue,
+CUSP/ZAC candidate rounds, crossing rules): every path must give the oracle's answer, whatever it skips."""
+from importlib import import_module
+
+import numpy as np
+import pytest
+
+from parity import assert_parity, compare_rows
+from test_gpu_icpc import assert_parity_with_ties
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(**kw):
+    cfgm = import_module("legenddsp.jl_b200.config")
+    d = cfgm.example_config_dict()
+    d["kwargs_pars"].update(kw)
+    return cfgm.DSPConfig.from_dict(d)
+
+
+@pytest.mark.parametrize("t0_mintot_ns", [96.0, 800.0, 1500.0, 4000.0])
+def test_t0_interval_rules(L, O, handle, t0_mintot_ns):
+    """get_t0 with mintot below one coarse interval (every interval evaluated), between one and two (end-point
+    rule) and above two (two consecutive coarse points rule): same t0 / t0_inv as the sequential Intersect"""
+    cfg = _cfg(t0_mintot=L.ns(t0_mintot_ns))
+    P = L.resolve_icpc_params(cfg, L.us(500.0), builders=O.OracleBuilders())
+    wf = L.synth.generate_host(768, first_event=4242)
+    got = L.dsp_icpc_rows(wf, P, handle=handle)
+    ref, _ = O.dsp_icpc(P, wf)
+    assert_parity_with_ties(L, O, P, wf, got, ref)
+    c = L.COL
+    assert (ref[:, c["t0"]] > 0).any()
+
+
+def test_low_thresholds_and_long_mintot(L, O, handle):
+    """low t0 threshold (noise crosses it all the time: thousands of flagged intervals -> queue overflow path) and a
+    long tx_mintot / intrace_mintot"""
+    cfgm = import_module("legenddsp.jl_b200.config")
+    d = cfgm.example_config_dict()
+    d["t0_threshold"] = 1.0
+    d["inTraceCut_std_threshold"] = 1.5
+    d["kwargs_pars"].update(tx_mintot=L.ns(160.0), intrace_mintot=L.ns(48.0))
+    cfg = cfgm.DSPConfig.from_dict(d)
+    P = L.resolve_icpc_params(cfg, L.us(500.0), builders=O.OracleBuilders())
+    wf = L.synth.generate_host(512, first_event=90000)
+    got = L.dsp_icpc_rows(wf, P, handle=handle)
+    ref, _ = O.dsp_icpc(P, wf)
+    assert_parity_with_ties(L, O, P, wf, got, ref)
+
+
+def test_column_groups(L, O, handle):
+    """BASELINE config 2 (pole-zero + trapezoid energies / t0 only): the enabled columns equal the full run's"""
+    P_all = L.resolve_icpc_params(L.example_config(), L.us(500.0), builders=O.OracleBuilders())
+    P_pz = L.resolve_icpc_params(L.example_config(), L.us(500.0), builders=O.OracleBuilders(), groups=L._abi.GROUP_PZTRAP)
+    wf = L.synth.generate_host(300, first_event=5)
+    full = L.dsp_icpc_rows(wf, P_all, handle=handle)
+    part = L.dsp_icpc_rows(wf, P_pz, handle=handle)
+    cols = ("blmean", "blsigma", "blslope", "bloffset", "tailmean", "tailsigma", "tail_tau", "e_max", "e_min", "t0", "t10",
+            "t50", "t80", "t90", "t99", "drift_time", "t0_inv", "e_10410", "e_535", "e_313", "e_10410_inv", "e_313_inv",
+            "e_trap", "e_trap_max", "t_trap_max", "n_sat_low", "n_sat_high", "n_sat_low_cons", "n_sat_high_cons")
+    for name in cols:
+        a, b = part[:, L.COL[name]], full[:, L.COL[name]]
+        assert np.array_equal(a, b, equal_nan=True), name
+    for name in ("e_cusp", "e_zac", "a_sg", "qdrift", "lq", "inTrace_n"):
+        assert (part[:, L.COL[name]] == 0).all(), name
+
+
+def test_large_population_and_determinism(L, O, handle):
+    """16 384 events of the mixed generator against the oracle (rare decision flips would show up here), and a second
+    run must be bit-identical (atomics and the work queue change the order of evaluation, never a result)"""
+    P = L.resolve_icpc_params(L.tiefree_config(), L.us(500.0), builders=O.OracleBuilders())
+    wf = L.synth.generate_host(16384, first_event=1_000_000)
+    got = L.dsp_icpc_rows(wf, P, handle=handle)
+    again = L.dsp_icpc_rows(wf, P, handle=handle)
+    assert np.array_equal(got, again, equal_nan=True)
+    ref, _ = O.dsp_icpc(P, wf)
+    res, n_ties = assert_parity_with_ties(L, O, P, wf, got, ref)
+    c = L.COL
+    # every class of the population is present
+    assert (ref[:, c["n_sat_high"]] > 0).sum() > 100 and (ref[:, c["inTrace_n"]] > 1).sum() > 100
+    assert (ref[:, c["t0"]] == 0).sum() > 100          # empty events: no t0
+
+
+def test_pathological_waveforms(L, O, handle):
+    """constant, ramp, alternating, full-scale and all-zero traces: nothing to prune with, sentinels everywhere"""
+    n = 8192
+    rows = []
+    rows.append(np.full(n, 12000, np.uint16))                                     # constant
+    rows.append((np.arange(n) * 7 % 65521).astype(np.uint16))                      # sawtooth over the full range
+    rows.append(np.where(np.arange(n) % 2 == 0, 100, 60000).astype(np.uint16))      # alternating
+    rows.append(np.full(n, 65520, np.uint16))                                     # saturated high everywhere
+    rows.append(np.zeros(n, np.uint16))                                           # saturated low everywhere
+    rows.append(np.clip(9000 + np.arange(n) * 6, 0, 65520).astype(np.uint16))       # ramp into saturation
+    step = np.full(n, 10000, np.uint16); step[4000:] = 50000
+    rows.append(step)                                                             # bare step (no decay)
+    neg = np.full(n, 30000, np.uint16); neg[3000:] = 5000
+    rows.append(neg)                                                              # negative step
+    wf = np.stack(rows)
+    P = L.resolve_icpc_params(L.example_config(), L.us(500.0), builders=O.OracleBuilders())
+    got = L.dsp_icpc_rows(wf, P, handle=handle)
+    ref, _ = O.dsp_icpc(P, wf)
+    res = compare_rows(got, ref, L.COLUMNS)
+    # exact ties are everywhere on such inputs (flat traces): compare what is well defined
+    well_defined = ("blmean", "blsigma", "e_max", "e_min", "n_sat_low", "n_sat_high", "n_sat_low_cons", "n_sat_high_cons",
+                    "tail_mean", "tail_sigma", "tailmean", "e_10410", "e_535", "e_313", "e_10410_inv", "e_313_inv",
+                    "e_trap_max", "e_cusp_max", "e_zac_max", "t10", "t50", "t90", "qc_label")
+    bad = {k: res[k] for k in well_defined if res[k][1] > 0}
+    assert not bad, bad
