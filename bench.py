@@ -25,6 +25,10 @@ sys.path.insert(0, ROOT)
 
 BYTES_IN = 8192 * 2
 NCOL = 49
+# DRAM traffic per waveform of icpc_kernel from the committed ncu --set full capture (profiles/r01_icpc_kernel_ncu_full.txt:
+# dram__bytes_read.sum + dram__bytes_write.sum = 269.97 MB + 11.56 MB for 16 384 events); roofline.traffic scales it to
+# the events of one launch.  Algorithmic bytes are 16 776 B/waveform: no re-reads.
+NCU_DRAM_BYTES_PER_WF = {"dsp_icpc": (269.97e6 + 11.56e6) / 16384.0}
 
 
 def _peaks():
@@ -85,16 +89,24 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_throughput(L, O, P, n_events, workload, variants=None, sparams=None, reps=1):
+def host_threads():
+    """host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the scheduler, not OpenMP)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_port_throughput(L, O, P, n_events, workload, variants=None, sparams=None, reps=1, threads=0):
     """the CPU port of the reference algorithm (oracle/) on all host cores: waveforms/s"""
     wf = L.synth.generate_host(n_events, first_event=10_000_000)
     best = None
     for _ in range(reps):
         t0 = time.perf_counter()
         if workload == "trap_sweep":
-            O.trap_sweep(sparams, wf, variants)
+            O.trap_sweep(sparams, wf, variants, n_threads=threads)
         else:
-            O.dsp_icpc(P, wf)
+            O.dsp_icpc(P, wf, n_threads=threads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return n_events / best
@@ -103,7 +115,7 @@ def cpu_port_throughput(L, O, P, n_events, workload, variants=None, sparams=None
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dsp_icpc", choices=["dsp_icpc", "pz_trap", "trap_sweep"])
@@ -153,15 +165,15 @@ def main():
         P = L.resolve_icpc_params(cfg, tau, groups=groups or L._abi.GROUP_ALL, builders=O.OracleBuilders())
         if args.workload == "trap_sweep":
             sparams = L.resolve_sweep_params(cfg, tau, builders=O.OracleBuilders())
-        threads = O.num_threads()
+        threads = host_threads()
         n_s = args.cpu_sample or (32 * threads if args.workload != "trap_sweep" else 16 * threads)
         wf = L.synth.generate_host(n_s, first_event=10_000_000)
 
         def step():
             if args.workload == "trap_sweep":
-                O.trap_sweep(sparams, wf, variants)
+                O.trap_sweep(sparams, wf, variants, n_threads=threads)
             else:
-                O.dsp_icpc(P, wf)
+                O.dsp_icpc(P, wf, n_threads=threads)
         for _ in range(args.warmup):
             step()
         t0 = time.perf_counter()
@@ -295,7 +307,11 @@ def main():
             "e2e": {"value": e2e_val, "unit": "waveforms/s", "h2d_bytes_per_step": Be * BYTES_IN,
                     "d2h_bytes_per_step": Be * out_bytes, "events_per_step_per_gpu": Be, "checksum": checksum},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                         "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": (NCU_DRAM_BYTES_PER_WF[args.workload] * B if args.workload in NCU_DRAM_BYTES_PER_WF
+                                     and args.groups is None else None),
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, scaled by events)",
+                         "peak_source": peak_kind,
                          "algorithmic_bytes_per_waveform": bytes_per_wf,
                          "kernel": "sweep_kernel" if args.workload == "trap_sweep" else "icpc_kernel"},
         }
@@ -303,9 +319,9 @@ def main():
             from oracle import oracle as O
             Po = L.resolve_icpc_params(cfg, tau, groups=groups or L._abi.GROUP_ALL, builders=O.OracleBuilders())
             so = L.resolve_sweep_params(cfg, tau, builders=O.OracleBuilders()) if args.workload == "trap_sweep" else None
-            threads = O.num_threads()
+            threads = host_threads()
             n_s = args.cpu_sample or 128 * threads
-            v = cpu_port_throughput(L, O, Po, n_s, args.workload, variants, so)
+            v = cpu_port_throughput(L, O, Po, n_s, args.workload, variants, so, threads=threads)
             line["cpu_baseline"] = {"value": v, "unit": "waveforms/s", "cores": threads, "kind": "port",
                                     "sample": f"{n_s} waveforms of the same synthetic stream, CPU restatement of the reference "
                                               "algorithm (oracle/, float64, direct-form CUSP/ZAC FIRs), OpenMP over events; not Julia"}
