@@ -9,6 +9,9 @@
  *                                               src/dsp_icpc.jl:62-230
  *   lgdsp_trap_sweep_run / _device           <- dsp_trap_rt_optimization  src/dsp_filter_optimization.jl:102-133
  *                                               dsp_trap_ft_optimization  src/dsp_filter_optimization.jl:241-274
+ *   lgdsp_sweep_run / _device                <- the same two plus dsp_cusp_rt/zac_rt_optimization :145-231,
+ *                                               dsp_cusp_ft/zac_ft_optimization :286-375, dsp_sg_optimization :393-441
+ *                                               (every sweep of the file except the _compressed / qc variants)
  *   lgdsp_sg_coeffs / lgdsp_lsq_fit_matrix /
  *   lgdsp_cusp_coeffs / lgdsp_zac_coeffs     <- filter-instance construction that the reference delegates to
  *                                               RadiationDetectorDSP.jl (fltinstance(...), src/dsp_icpc.jl:157-181)
@@ -39,7 +42,7 @@ extern "C" {
 
 #define LGDSP_VERSION_MAJOR 0
 #define LGDSP_VERSION_MINOR 1
-#define LGDSP_PARAMS_VERSION 3u
+#define LGDSP_PARAMS_VERSION 4u
 
 /* status codes */
 #define LGDSP_OK 0
@@ -208,7 +211,29 @@ typedef struct lgdsp_sweep_params {
     int32_t bl_from, bl_until;
     double pz_km1;
     lgdsp_dni sig_dni;
+    int32_t out_f64;       /* 0: float output (the ft sweeps' Union{Missing,Float32} matrices, :263); 1: double output
+                              (the rt sweeps' zeros(Float64, ...), :122, and dsp_sg_optimization) */
+    int32_t reserved0;
 } lgdsp_sweep_params;
+
+/* one point of a general filter sweep:
+ * kind 0  TrapezoidalChargeFilter(`trap`), value = SignalEstimator at the pick-off            (:109-127, :264-270)
+ * kind 1  FIR `coeffs[n_taps]` as produced by lgdsp_cusp_coeffs / lgdsp_zac_coeffs (valid convolution, trailing-edge
+ *         time axis), value = SignalEstimator at the pick-off                                  (:173-176, :316-318)
+ * kind 2  SavitzkyGolayFilter taps `coeffs[n_taps]` (valid correlation, trace index j <-> sample j + sg_offset),
+ *         value = get_wvf_maximum of the trace inside [win_from, win_until] (trace indices)      (:432-433)
+ * pick-off (kinds 0/1): pickoff_mode 0: fixed time pickoff_ns; 1: t50 + pickoff_ns, t50 on the PZ waveform at half its
+ * maximum with tx_min_n (:260). */
+typedef struct lgdsp_sweep_variant {
+    int32_t kind;
+    int32_t pickoff_mode;
+    double pickoff_ns;
+    lgdsp_trap trap;
+    int32_t n_taps;
+    int32_t sg_offset;
+    int32_t win_from, win_until;
+    const double* coeffs;      /* host pointer, read during the call only */
+} lgdsp_sweep_variant;
 
 /* synthetic ICPC waveform generator: counter-based Philox4x32-10, identical on host and device */
 typedef struct lgdsp_synth_params {
@@ -262,6 +287,15 @@ int lgdsp_trap_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uin
 int lgdsp_trap_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* d_wf,
                                 int64_t n_events, int64_t ld_samples, const lgdsp_trap_variant* variants,
                                 int32_t n_variants, float* d_out);
+
+/* general sweep: out is float or double [n_events][n_variants] (lgdsp_sweep_params.out_f64); aux, when not NULL,
+ * receives double[n_events][4] = (blmean, blslope [1/ns], t50 [us], 0) -- the extra columns of dsp_sg_optimization's
+ * result table (:435-439) */
+int lgdsp_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* wf, int64_t n_events, int64_t ld_samples,
+                    const lgdsp_sweep_variant* variants, int32_t n_variants, void* out, double* aux);
+int lgdsp_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* d_wf, int64_t n_events,
+                           int64_t ld_samples, const lgdsp_sweep_variant* variants, int32_t n_variants, void* d_out,
+                           double* d_aux);
 
 /* ---- synthetic input ---- */
 /* events [first_event, first_event + n_events) of the stream defined by (seed, mode) */

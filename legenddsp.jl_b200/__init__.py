@@ -12,10 +12,12 @@ from . import _abi
 from ._abi import COLUMNS, COL, INT_COLUMNS, NCOL, UNITS
 from .config import (DSPConfig, Q, RddspPolicy, DEFAULT_POLICY, LibBuilders, example_config, tiefree_config,
                      get_fltpars, grid_values, ns, us, resolve_icpc_params, resolve_sweep_params, trap_variants,
-                     params_summary)
+                     trap_sweep_variants, cuspzac_sweep_variants, sg_sweep_variants, SweepVariants, params_summary)
 from ._lib import Handle, LgdspError, load_library, LIB_PATH, EXPORTED_SYMBOLS
 from .dsp_icpc import RDWaveforms, TABLE_COLUMNS, dsp_icpc, dsp_icpc_rows, rows_to_table, get_handle
-from .dsp_filter_optimization import dsp_trap_rt_optimization, dsp_trap_ft_optimization, dsp_trap_rtft_grid
+from .dsp_filter_optimization import (dsp_trap_rt_optimization, dsp_trap_ft_optimization, dsp_trap_rtft_grid,
+                                      dsp_cusp_rt_optimization, dsp_zac_rt_optimization, dsp_cusp_ft_optimization,
+                                      dsp_zac_ft_optimization, dsp_sg_optimization)
 from . import synth, sharding
 
 __all__ = [
@@ -23,5 +25,7 @@ __all__ = [
     "resolve_icpc_params", "resolve_sweep_params", "trap_variants", "params_summary",
     "Handle", "LgdspError", "load_library", "RDWaveforms", "TABLE_COLUMNS", "dsp_icpc", "dsp_icpc_rows",
     "rows_to_table", "dsp_trap_rt_optimization", "dsp_trap_ft_optimization", "dsp_trap_rtft_grid",
+    "dsp_cusp_rt_optimization", "dsp_zac_rt_optimization", "dsp_cusp_ft_optimization", "dsp_zac_ft_optimization",
+    "dsp_sg_optimization", "trap_sweep_variants", "cuspzac_sweep_variants", "sg_sweep_variants",
     "synth", "sharding", "COLUMNS", "COL", "INT_COLUMNS", "NCOL", "UNITS",
 ]

@@ -5,7 +5,7 @@ sizeof/offsetof of every struct and compares them with these definitions.
 """
 import ctypes as C
 
-LGDSP_PARAMS_VERSION = 3
+LGDSP_PARAMS_VERSION = 4
 LGDSP_MAX_SAMPLES = 8192
 LGDSP_MAX_DNI = 64
 LGDSP_MAX_DNI_DEG = 3
@@ -127,6 +127,17 @@ class SweepParams(C.Structure):
         ("bl_from", C.c_int32), ("bl_until", C.c_int32),
         ("pz_km1", C.c_double),
         ("sig_dni", Dni),
+        ("out_f64", C.c_int32), ("reserved0", C.c_int32),
+    ]
+
+
+class SweepVariant(C.Structure):
+    """lgdsp_sweep_variant: kind 0 trapezoid, 1 FIR (CUSP/ZAC coefficient array), 2 Savitzky-Golay + windowed maximum"""
+    _fields_ = [
+        ("kind", C.c_int32), ("pickoff_mode", C.c_int32), ("pickoff_ns", C.c_double),
+        ("trap", Trap),
+        ("n_taps", C.c_int32), ("sg_offset", C.c_int32), ("win_from", C.c_int32), ("win_until", C.c_int32),
+        ("coeffs", C.POINTER(C.c_double)),
     ]
 
 

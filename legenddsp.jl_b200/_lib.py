@@ -51,6 +51,8 @@ def load_library():
     L.lgdsp_trap_sweep_run.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64, C.POINTER(_abi.TrapVariant), i32, vp]
     L.lgdsp_trap_sweep_run_device.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64,
                                               C.POINTER(_abi.TrapVariant), i32, vp]
+    L.lgdsp_sweep_run.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64, C.POINTER(_abi.SweepVariant), i32, vp, vp]
+    L.lgdsp_sweep_run_device.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64, C.POINTER(_abi.SweepVariant), i32, vp, vp]
     L.lgdsp_synth_generate_device.argtypes = [vp, C.POINTER(_abi.SynthParams), i64, i64, i64, vp]
     L.lgdsp_synth_generate_host.argtypes = [C.POINTER(_abi.SynthParams), i64, i64, i64, vp]
     L.lgdsp_debug_phase_cycles.argtypes = [vp, C.c_int, _dp]
@@ -64,7 +66,7 @@ EXPORTED_SYMBOLS = (
     "lgdsp_version", "lgdsp_last_error", "lgdsp_create", "lgdsp_destroy", "lgdsp_launch_count", "lgdsp_synchronize",
     "lgdsp_lsq_fit_matrix", "lgdsp_sg_coeffs", "lgdsp_cusp_coeffs", "lgdsp_zac_coeffs",
     "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params",
-    "lgdsp_trap_sweep_run", "lgdsp_trap_sweep_run_device",
+    "lgdsp_trap_sweep_run", "lgdsp_trap_sweep_run_device", "lgdsp_sweep_run", "lgdsp_sweep_run_device",
     "lgdsp_synth_generate_device", "lgdsp_synth_generate_host", "lgdsp_last_kernel_ms", "lgdsp_debug_phase_cycles", "lgdsp_debug_section_cycles",
 )
 
@@ -146,6 +148,17 @@ class Handle:
     def sweep_run_device(self, sparams, d_wf_ptr, n_events, ld, variants, d_out_ptr):
         self._check(self._lib.lgdsp_trap_sweep_run_device(self._h, C.byref(sparams), C.c_void_p(d_wf_ptr), int(n_events),
                                                           int(ld), variants, len(variants), C.c_void_p(d_out_ptr)))
+
+    def gsweep_run_host(self, sparams, wf_ptr, n_events, ld, variants, out_ptr, aux_ptr=None):
+        """general sweep (lgdsp_sweep_run): variants = ctypes array of _abi.SweepVariant"""
+        self._check(self._lib.lgdsp_sweep_run(self._h, C.byref(sparams), C.c_void_p(wf_ptr), int(n_events), int(ld),
+                                              variants, len(variants), C.c_void_p(out_ptr),
+                                              C.c_void_p(aux_ptr) if aux_ptr else None))
+
+    def gsweep_run_device(self, sparams, d_wf_ptr, n_events, ld, variants, d_out_ptr, d_aux_ptr=None):
+        self._check(self._lib.lgdsp_sweep_run_device(self._h, C.byref(sparams), C.c_void_p(d_wf_ptr), int(n_events), int(ld),
+                                                     variants, len(variants), C.c_void_p(d_out_ptr),
+                                                     C.c_void_p(d_aux_ptr) if d_aux_ptr else None))
 
     # ---- synthetic input ----
     def synth_device(self, sp, first_event, n_events, ld, d_wf_ptr):

@@ -464,7 +464,7 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
 
 
 def resolve_sweep_params(cfg: DSPConfig, tau: Q, *, n_samples: int = 8192, t_first: Q = ns(0.0),
-                         step: Q = ns(16.0), builders=None) -> _abi.SweepParams:
+                         step: Q = ns(16.0), builders=None, out_f64: bool = False) -> _abi.SweepParams:
     """common part of dsp_trap_rt_optimization / dsp_trap_ft_optimization
     (src/dsp_filter_optimization.jl:102-133, 241-274)"""
     if builders is None:
@@ -486,6 +486,7 @@ def resolve_sweep_params(cfg: DSPConfig, tau: Q, *, n_samples: int = 8192, t_fir
     alpha = RC / (RC + 1.0)
     S.pz_km1 = 1.0 / alpha - 1.0
     _fill_dni(S.sig_dni, int(kw["sig_interpolation_order"]), kw["sig_interpolation_length"], step, builders)
+    S.out_f64 = 1 if out_f64 else 0
     return S
 
 
@@ -504,6 +505,85 @@ def trap_variants(rts: Sequence[Q], fts: Sequence[Q], step: Q, *, mode: str, pic
                 out[i].pickoff_ns = (rt + ft / 2).ns()
                 out[i].pickoff_mode = 1
             i += 1
+    return out
+
+
+class SweepVariants:
+    """ctypes array of lgdsp_sweep_variant plus the numpy coefficient arrays its pointers refer to (kept alive here)"""
+
+    def __init__(self, n: int):
+        self.array = (_abi.SweepVariant * n)()
+        self._keep = []
+
+    def __len__(self):
+        return len(self.array)
+
+    def set_coeffs(self, i: int, c: np.ndarray):
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        self._keep.append(c)
+        self.array[i].coeffs = c.ctypes.data_as(C.POINTER(C.c_double))
+        self.array[i].n_taps = int(c.size)
+
+
+def trap_sweep_variants(rts: Sequence[Q], fts: Sequence[Q], step: Q, *, mode: str, pickoff: Optional[Q] = None) -> SweepVariants:
+    """the trapezoid sweeps as general variants (kind 0); same order and pick-offs as trap_variants"""
+    tv = trap_variants(rts, fts, step, mode=mode, pickoff=pickoff)
+    out = SweepVariants(len(tv))
+    for i in range(len(tv)):
+        out.array[i].kind = 0
+        out.array[i].trap = tv[i].trap
+        out.array[i].pickoff_ns = tv[i].pickoff_ns
+        out.array[i].pickoff_mode = tv[i].pickoff_mode
+    return out
+
+
+def cuspzac_sweep_variants(cfg: DSPConfig, kind: str, rts: Sequence[Q], fts: Sequence[Q], step: Q, *, mode: str,
+                           policy: RddspPolicy = DEFAULT_POLICY, builders=None) -> SweepVariants:
+    """CUSP / ZAC sweeps (kind 1): for rt in rts, for ft in fts the filter `CUSPChargeFilter(rt, ft, 1e7 us, length, scale)`
+    (src/dsp_filter_optimization.jl:173,221,316,366); mode "rt": fixed pick-off enc_pickoff_cusp/zac (:175,:223);
+    mode "ft": t50 + flt_length/2 (:318,:368)"""
+    if builders is None:
+        builders = LibBuilders()
+    length = cfg.flt_length_cusp if kind == "cusp" else cfg.flt_length_zac
+    pick = cfg.enc_pickoff_cusp if kind == "cusp" else cfg.enc_pickoff_zac
+    out = SweepVariants(len(rts) * len(fts))
+    i = 0
+    for rt in rts:
+        for ft in fts:
+            cz = _abi.CuspZac()
+            _fill_cuspzac(cz, kind, rt, ft, us(10000000.0), length, _ratio(length, step), step, policy, builders)
+            out.array[i].kind = 1
+            out.set_coeffs(i, np.array(cz.coeffs[:cz.n_taps]))
+            if mode == "rt":
+                out.array[i].pickoff_ns = pick.ns()
+                out.array[i].pickoff_mode = 0
+            else:
+                out.array[i].pickoff_ns = (length / 2).ns()
+                out.array[i].pickoff_mode = 1
+            i += 1
+    return out
+
+
+def sg_sweep_variants(cfg: DSPConfig, wls: Sequence[Q], *, n_samples: int, t_first: Q, step: Q,
+                      policy: RddspPolicy = DEFAULT_POLICY, builders=None) -> SweepVariants:
+    """Savitzky-Golay window-length sweep (kind 2): SavitzkyGolayFilter(wl, sg_flt_degree, 1) and get_wvf_maximum in
+    current_window (src/dsp_filter_optimization.jl:430-433); the window is resolved on every filter's own trace axis"""
+    if builders is None:
+        builders = LibBuilders()
+    out = SweepVariants(len(wls))
+    for i, wl in enumerate(wls):
+        sg = _abi.Sg()
+        _fill_sg(sg, wl, int(cfg.sg_flt_degree), step, policy, builders)
+        first_k = t_first + step * float(sg.offset)
+        n_trace = n_samples - sg.n_taps + 1
+        a = _sub_over_step(cfg.current_window[0], first_k, step)
+        b = _sub_over_step(cfg.current_window[1], first_k, step)
+        if not (0 <= a <= b <= n_trace - 1):
+            raise AssertionError(f"current_window on sg(wl={wl}): index range {a + 1}:{b + 1} outside 1:{n_trace}")
+        out.array[i].kind = 2
+        out.set_coeffs(i, np.array(sg.h[:sg.n_taps]))
+        out.array[i].sg_offset = sg.offset
+        out.array[i].win_from, out.array[i].win_until = a, b
     return out
 
 

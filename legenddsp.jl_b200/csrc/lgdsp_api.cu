@@ -28,12 +28,14 @@ struct lgdsp_handle {
     bool phase_on = false;
     SweepVar* d_vars = nullptr;
     int vars_cap = 0;
+    double* d_taps = nullptr;      // differenced FIR / SG taps of the sweep variants
+    size_t taps_cap = 0;
     IcpcDev icpc{};
     bool have_icpc = false;
     // host-path staging
     uint16_t* d_in[2] = {nullptr, nullptr};
     double* d_rows = nullptr;
-    float* d_sweep_out = nullptr;
+    void* d_sweep_out = nullptr;
     size_t in_cap = 0, rows_cap = 0, sweep_out_cap = 0;
     cudaStream_t s_copy = nullptr;
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -127,7 +129,7 @@ void lgdsp_destroy(lgdsp_handle* h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_phase);
-    cudaFree(h->d_dniA); cudaFree(h->d_cusp_g); cudaFree(h->d_zac_g); cudaFree(h->d_sweep_dniA); cudaFree(h->d_vars);
+    cudaFree(h->d_dniA); cudaFree(h->d_cusp_g); cudaFree(h->d_zac_g); cudaFree(h->d_sweep_dniA); cudaFree(h->d_vars); cudaFree(h->d_taps);
     cudaFree(h->d_in[0]); cudaFree(h->d_in[1]); cudaFree(h->d_rows); cudaFree(h->d_sweep_out);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]);
@@ -539,7 +541,8 @@ int lgdsp_debug_section_cycles(lgdsp_handle* h, double* out256)
 // ---------------------------------------------------------------------------------------------------
 // trapezoid sweeps
 // ---------------------------------------------------------------------------------------------------
-static int sweep_prepare(lgdsp_handle* h, const lgdsp_sweep_params* p, const lgdsp_trap_variant* variants, int32_t nvar,
+// variants -> device table (filter taps are differenced onto the prefix sums TT and uploaded)
+static int sweep_prepare(lgdsp_handle* h, const lgdsp_sweep_params* p, const lgdsp_sweep_variant* variants, int32_t nvar,
                          SweepDev& D)
 {
     if (!p || !variants) return fail(h, LGDSP_ERR_INVALID_ARG, "sweep params/variants NULL");
@@ -554,31 +557,82 @@ static int sweep_prepare(lgdsp_handle* h, const lgdsp_sweep_params* p, const lgd
         return fail(h, LGDSP_ERR_UNSUPPORTED, "PolynomialDNI outside the supported range");
     if (p->tx_min_n < 1) return fail(h, LGDSP_ERR_INVALID_ARG, "tx_min_n < 1");
     std::vector<SweepVar> sv(nvar);
+    std::vector<double> taps;            // all differenced tap arrays, back to back
+    std::vector<size_t> tap_off(nvar, 0);
     for (int v = 0; v < nvar; ++v) {
-        if (!make_trap(variants[v].trap, n, d.n_w, sv[v].t))
-            return fail(h, LGDSP_ERR_INVALID_ARG, "variant %d: trapezoid (%d,%d,%d) leaves fewer outputs than the DNI window", v,
-                        variants[v].trap.navg, variants[v].trap.ngap, variants[v].trap.navg2);
-        sv[v].pick_ns = variants[v].pickoff_ns;
-        sv[v].mode = variants[v].pickoff_mode;
-        sv[v].pad_ = 0;
+        const lgdsp_sweep_variant& in = variants[v];
+        SweepVar& o = sv[v];
+        memset(&o, 0, sizeof(o));
+        o.kind = in.kind;
+        o.pick_ns = in.pickoff_ns;
+        o.mode = in.pickoff_mode;
+        if (in.kind == 0) {
+            if (!make_trap(in.trap, n, d.n_w, o.t))
+                return fail(h, LGDSP_ERR_INVALID_ARG, "variant %d: trapezoid (%d,%d,%d) leaves fewer outputs than the DNI window", v,
+                            in.trap.navg, in.trap.ngap, in.trap.navg2);
+            o.L = o.t.L;
+        } else if (in.kind == 1) {
+            const int L = in.n_taps;
+            if (!in.coeffs || L < 2 || L > LGDSP_MAX_FIR || n - L + 1 < d.n_w)
+                return fail(h, LGDSP_ERR_INVALID_ARG, "variant %d: FIR with %d taps does not fit (need >= %d outputs)", v, L, d.n_w);
+            o.L = L;
+            tap_off[v] = taps.size();
+            // out[j] = sum_k c[k] y[j+L-1-k] = sum_{k=0}^{L} g[k] TT[j+L-k],  g = first difference of c
+            taps.push_back(in.coeffs[0]);
+            for (int k = 1; k < L; ++k) taps.push_back(in.coeffs[k] - in.coeffs[k - 1]);
+            taps.push_back(-in.coeffs[L - 1]);
+        } else if (in.kind == 2) {
+            const int T = in.n_taps;
+            if (!in.coeffs || T < 1 || T > LGDSP_MAX_SG || T > n || in.sg_offset < 0 || in.sg_offset >= T)
+                return fail(h, LGDSP_ERR_INVALID_ARG, "variant %d: bad Savitzky-Golay tap count/offset", v);
+            if (!(0 <= in.win_from && in.win_from <= in.win_until && in.win_until <= n - T))
+                return fail(h, LGDSP_ERR_INVALID_ARG, "variant %d: current_window %d:%d outside the SG trace", v, in.win_from, in.win_until);
+            o.L = T; o.sg_off = in.sg_offset; o.win_from = in.win_from; o.win_until = in.win_until;
+            tap_off[v] = taps.size();
+            // s[j] = sum_k h[k] y[j+k] = sum_{k=0}^{T} gg[k] TT[j+k]
+            taps.push_back(-in.coeffs[0]);
+            for (int k = 1; k < T; ++k) taps.push_back(in.coeffs[k - 1] - in.coeffs[k]);
+            taps.push_back(in.coeffs[T - 1]);
+        } else {
+            return fail(h, LGDSP_ERR_INVALID_ARG, "variant %d: unknown kind %d", v, in.kind);
+        }
     }
     if (nvar > h->vars_cap) {
         cudaFree(h->d_vars); h->d_vars = nullptr; h->vars_cap = 0;
         CK(cudaMalloc(&h->d_vars, sizeof(SweepVar) * nvar));
         h->vars_cap = nvar;
     }
+    if (taps.size() > h->taps_cap) {
+        cudaFree(h->d_taps); h->d_taps = nullptr; h->taps_cap = 0;
+        CK(cudaMalloc(&h->d_taps, sizeof(double) * taps.size()));
+        h->taps_cap = taps.size();
+    }
+    for (int v = 0; v < nvar; ++v)
+        if (sv[v].kind != 0) sv[v].g = h->d_taps + tap_off[v];
+    if (!taps.empty()) CK(cudaMemcpyAsync(h->d_taps, taps.data(), sizeof(double) * taps.size(), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_vars, sv.data(), sizeof(SweepVar) * nvar, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_sweep_dniA, d.A, sizeof(double) * LGDSP_MAX_DNI * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     D.n = n; D.tx_min_n = p->tx_min_n; D.t_first = p->t_first_ns; D.dt = p->dt_ns;
     D.bl_from = p->bl_from; D.bl_until = p->bl_until; D.km1 = p->pz_km1;
     D.sig_dni.n_w = d.n_w; D.sig_dni.m = d.degree + 1;
-    D.dni_A = h->d_sweep_dniA; D.vars = h->d_vars; D.nvar = nvar; D.pad_ = 0;
+    D.dni_A = h->d_sweep_dniA; D.vars = h->d_vars; D.nvar = nvar; D.out_f64 = p->out_f64 ? 1 : 0;
+    D.bl_inv_n = 1.0 / (double)(p->bl_until - p->bl_from + 1);
+    {
+        typedef long double ld;
+        const int a = p->bl_from, b = p->bl_until;
+        const ld t0 = p->t_first_ns, dt = p->dt_ns, cnt = (ld)(b - a + 1);
+        auto s2 = [](ld k) { return k * (k + 1.0L) * (2.0L * k + 1.0L) / 6.0L; };
+        const ld si = 0.5L * (ld)(a + b) * cnt, sii = s2((ld)b) - s2((ld)a - 1.0L);
+        D.bl_sX = (double)(cnt * t0 + dt * si);
+        D.bl_sXX = (double)(cnt * t0 * t0 + 2.0L * t0 * dt * si + dt * dt * sii);
+    }
     return LGDSP_OK;
 }
 
-int lgdsp_trap_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* d_wf, int64_t n_events,
-                                int64_t ld_samples, const lgdsp_trap_variant* variants, int32_t n_variants, float* d_out)
+int lgdsp_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* d_wf, int64_t n_events,
+                           int64_t ld_samples, const lgdsp_sweep_variant* variants, int32_t n_variants, void* d_out,
+                           double* d_aux)
 {
     if (!h) return LGDSP_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
@@ -592,7 +646,7 @@ int lgdsp_trap_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, co
     const long long cap = (long long)h->sm_count * h->sweep_bps;
     const int grid = (int)(n_events < cap ? n_events : cap);
     CK(cudaEventRecord(h->ev0, h->stream));
-    sweep_launch(D, d_wf, n_events, ld_samples, d_out, grid, h->stream);
+    sweep_launch(D, d_wf, n_events, ld_samples, d_out, d_aux, grid, h->stream);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
@@ -600,8 +654,8 @@ int lgdsp_trap_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, co
     return LGDSP_OK;
 }
 
-int lgdsp_trap_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* wf, int64_t n_events,
-                         int64_t ld_samples, const lgdsp_trap_variant* variants, int32_t n_variants, float* out)
+int lgdsp_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* wf, int64_t n_events, int64_t ld_samples,
+                    const lgdsp_sweep_variant* variants, int32_t n_variants, void* out, double* aux)
 {
     if (!h) return LGDSP_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
@@ -616,13 +670,16 @@ int lgdsp_trap_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uin
     const int64_t chunk = n_events < 8192 ? n_events : 8192;
     rc = ensure_staging(h, (size_t)chunk * n * 2, 0);
     if (rc) return rc;
-    const size_t ob = (size_t)2 * chunk * n_variants * sizeof(float);
+    const size_t esz = D.out_f64 ? sizeof(double) : sizeof(float);
+    const size_t ob = (size_t)2 * chunk * (n_variants * esz + 4 * sizeof(double));
     if (ob > h->sweep_out_cap) {
         cudaFree(h->d_sweep_out); h->d_sweep_out = nullptr; h->sweep_out_cap = 0;
         CK(cudaMalloc(&h->d_sweep_out, ob));
         h->sweep_out_cap = ob;
     }
     const long long cap = (long long)h->sm_count * h->sweep_bps;
+    char* base = reinterpret_cast<char*>(h->d_sweep_out);
+    const size_t out_bytes = (size_t)chunk * n_variants * esz;   // per buffer; the aux buffers follow the two output buffers
     int c = 0;
     for (int64_t e0 = 0; e0 < n_events; e0 += chunk, ++c) {
         const int b = c & 1;
@@ -632,17 +689,54 @@ int lgdsp_trap_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uin
                              (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
         CK(cudaEventRecord(h->ev_ready[b], h->s_copy));
         CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
-        float* d_o = h->d_sweep_out + (size_t)b * chunk * n_variants;
+        void* d_o = base + (size_t)b * out_bytes;
+        double* d_a = aux ? reinterpret_cast<double*>(base + 2 * out_bytes) + (size_t)b * chunk * 4 : nullptr;
         const int grid = (int)(ne < cap ? ne : cap);
-        sweep_launch(D, h->d_in[b], ne, n, d_o, grid, h->stream);
+        sweep_launch(D, h->d_in[b], ne, n, d_o, d_a, grid, h->stream);
         CK(cudaGetLastError());
         h->launches += 1;
         CK(cudaEventRecord(h->ev_free[b], h->stream));
-        CK(cudaMemcpyAsync(out + e0 * n_variants, d_o, (size_t)ne * n_variants * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(reinterpret_cast<char*>(out) + (size_t)e0 * n_variants * esz, d_o, (size_t)ne * n_variants * esz,
+                           cudaMemcpyDeviceToHost, h->stream));
+        if (aux) CK(cudaMemcpyAsync(aux + e0 * 4, d_a, (size_t)ne * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->s_copy));
     CK(cudaStreamSynchronize(h->stream));
     return LGDSP_OK;
+}
+
+// the trapezoid-only entry points (kept for callers of the first ABI revision): thin wrappers
+static std::vector<lgdsp_sweep_variant> trap_to_general(const lgdsp_trap_variant* variants, int32_t n)
+{
+    std::vector<lgdsp_sweep_variant> v((size_t)(n > 0 ? n : 0));
+    for (int i = 0; i < n; ++i) {
+        memset(&v[i], 0, sizeof(v[i]));
+        v[i].kind = 0;
+        v[i].pickoff_mode = variants[i].pickoff_mode;
+        v[i].pickoff_ns = variants[i].pickoff_ns;
+        v[i].trap = variants[i].trap;
+    }
+    return v;
+}
+
+int lgdsp_trap_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* d_wf, int64_t n_events,
+                                int64_t ld_samples, const lgdsp_trap_variant* variants, int32_t n_variants, float* d_out)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    if (!variants) return fail(h, LGDSP_ERR_INVALID_ARG, "sweep params/variants NULL");
+    if (p && p->out_f64) return fail(h, LGDSP_ERR_INVALID_ARG, "lgdsp_trap_sweep_run_device writes float: out_f64 must be 0");
+    std::vector<lgdsp_sweep_variant> v = trap_to_general(variants, n_variants);
+    return lgdsp_sweep_run_device(h, p, d_wf, n_events, ld_samples, v.data(), n_variants, d_out, nullptr);
+}
+
+int lgdsp_trap_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* wf, int64_t n_events,
+                         int64_t ld_samples, const lgdsp_trap_variant* variants, int32_t n_variants, float* out)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    if (!variants) return fail(h, LGDSP_ERR_INVALID_ARG, "sweep params/variants NULL");
+    if (p && p->out_f64) return fail(h, LGDSP_ERR_INVALID_ARG, "lgdsp_trap_sweep_run writes float: out_f64 must be 0");
+    std::vector<lgdsp_sweep_variant> v = trap_to_general(variants, n_variants);
+    return lgdsp_sweep_run(h, p, wf, n_events, ld_samples, v.data(), n_variants, out, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -1955,14 +1955,14 @@ constexpr int SW_RED = SW_MASK + NWORDS * 4;
 constexpr int SW_DNI = SW_RED + NWARP * RED_W * 8;
 constexpr int SW_OUT = SW_DNI + LGDSP_MAX_DNI * 4 * 8;
 constexpr int SW_MAXVAR = 1024;
-constexpr int SW_IBUF = SW_OUT + SW_MAXVAR * 4;
+constexpr int SW_IBUF = SW_OUT + SW_MAXVAR * 8;
 constexpr int SW_DSCAN = SW_IBUF + 64 * 4;
 constexpr int SW_BAR = SW_DSCAN + 8 * 8;
 constexpr int SW_TOTAL = SW_BAR + 16;
 
 __global__ void __launch_bounds__(NT, 2)
 sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf, long long n_events, long long ld,
-             float* __restrict__ out)
+             void* __restrict__ out, double* __restrict__ aux)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint16_t* xs = reinterpret_cast<uint16_t*>(smem + SW_XS);
@@ -1970,7 +1970,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
     uint32_t* mask = reinterpret_cast<uint32_t*>(smem + SW_MASK);
     double* red = reinterpret_cast<double*>(smem + SW_RED);
     double* dniA = reinterpret_cast<double*>(smem + SW_DNI);
-    float* obuf = reinterpret_cast<float*>(smem + SW_OUT);
+    double* obuf = reinterpret_cast<double*>(smem + SW_OUT);
     int* ibuf = reinterpret_cast<int*>(smem + SW_IBUF);
     double* dscan = reinterpret_cast<double*>(smem + SW_DSCAN);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SW_BAR);
@@ -1984,6 +1984,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
         mbar_init(bar, 1);
         fence_mbar_init();
     }
+    if (tid < TT_LEN - 1 - n) TT[n + 1 + tid] = 0.0;
     __syncthreads();
     long long e = blockIdx.x;
     if (tid == 0 && e < n_events) {
@@ -1997,14 +1998,16 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
         mbar_wait(bar, phase);
         phase ^= 1;
         const uint16_t* xp = xs + i0;
-        uint32_t csum = 0, cq = 0, blS = 0;
+        uint32_t csum = 0, cq = 0, blS = 0, blSK = 0;
         {
             const int ka = P.bl_from - i0, kb = P.bl_until - i0;
             for (int k = 0; k < cvalid; ++k) {
                 const uint32_t x = xp[k];
                 csum += x;
                 cq += csum;
-                blS += (k >= ka && k <= kb) ? x : 0u;
+                const bool in = (k >= ka && k <= kb);
+                blS += in ? x : 0u;
+                blSK += in ? x * (uint32_t)k : 0u;
             }
         }
         uint32_t incl = csum;
@@ -2016,10 +2019,9 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
         uint32_t* ured = reinterpret_cast<uint32_t*>(ibuf + 32);
         if (lane == 31) ured[wid] = incl;
         mask[tid] = 0u;
-        double blSd;
-        {
-            blSd = block_sum1((double)blS, red, tid);
-        }
+        const double blSd = block_sum1((double)blS, red, tid);
+        // sum_i i*x over the baseline window (for blslope of the aux outputs; exact in double)
+        const double blSXd = aux ? block_sum1((double)i0 * (double)blS + (double)blSK, red, tid) : 0.0;
         uint32_t woff = 0;
 #pragma unroll
         for (int w = 0; w < NWARP; ++w) woff += (w < wid) ? ured[w] : 0u;
@@ -2038,7 +2040,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
         for (int w = 0; w < NWARP; ++w) woff2 += (w < wid) ? dscan[w] : 0.0;
         const double PP_excl = woff2 + incl2 - v2;
         // blmean exactly as signalstats: mean_Y = sum_Y * inv_n
-        const double m = mul_rn(blSd, div_rn(1.0, (double)(P.bl_until - P.bl_from + 1)));
+        const double m = mul_rn(blSd, P.bl_inv_n);
         double ymax = -CUDART_INF;
         {
             uint32_t Pr = P_excl;
@@ -2050,16 +2052,16 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
             auto body = [&](int k) {
                 const uint32_t x = xp[k];
                 Pr += x;
-                const double Pd = (double)Pr;
+                const double Pd = u2d(Pr);
                 PPr += Pd;
                 ip1 += 1.0;
                 tri += ip1;
                 const double Sd = fma(-ip1, m, Pd);
-                const double w = (double)x - m;
+                const double w = u2d(x) - m;
                 const double y = fma(km1, Sd, w);
                 const double SS = fma(-tri, m, PPr);
                 tp[k] = fma(km1, SS, Sd);
-                ymax = fmax(ymax, y);
+                ymax = y > ymax ? y : ymax;
             };
             {
                 int k = 0;
@@ -2070,9 +2072,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
             }
         }
         if (tid == 0) TT[0] = 0.0;
-        {
-            ymax = block_max1(ymax, red, tid);
-        }
+        ymax = block_max1(ymax, red, tid);
         if (tid == 0) {
             const long long en = e + gridDim.x;
             if (en < n_events) {
@@ -2104,18 +2104,50 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
                 if (t50_us != t50_us) t50_us = 0.0;
             }
         }
+        if (aux && tid == 0) {
+            const Stats st = stats_finalize(P.bl_inv_n, P.bl_sX, P.bl_sXX, blSd, 0.0, t_first * blSd + dt * blSXd);
+            double* a = aux + e * 4;
+            a[0] = m; a[1] = st.slope; a[2] = t50_us; a[3] = 0.0;
+        }
         const int n_w = P.sig_dni.n_w, mdeg = P.sig_dni.m;
+#pragma unroll 1
         for (int v = wid; v < P.nvar; v += NWARP) {
             const SweepVar sv = P.vars[v];
-            const int nout = n - sv.t.L + 1;
-            const double tf = t_first + (double)(sv.t.L - 1) * dt;
+            if (sv.kind == 2) {
+                // SavitzkyGolay derivative trace s[j] = sum_k g[k] TT[j+k] (taps folded on the prefix sums); first argmax
+                // inside the window, parabola through its neighbours when strictly inside  (src/interpolation.jl:30-46)
+                auto sgv = [&](int j) -> double {
+                    double a0 = 0, a1 = 0;
+                    for (int k = 0; k <= sv.L; k += 2) {
+                        a0 = fma(__ldg(sv.g + k), TT[j + k], a0);
+                        if (k + 1 <= sv.L) a1 = fma(__ldg(sv.g + k + 1), TT[j + k + 1], a1);
+                    }
+                    return a0 + a1;
+                };
+                double bm = -CUDART_INF;
+                int ba = 0x7fffffff;
+                for (int j = sv.win_from + lane; j <= sv.win_until; j += 32) {
+                    const double s = sgv(j);
+                    if (s > bm) { bm = s; ba = j; }
+                }
+                bm = wargmax_d(bm, ba);
+                if (lane == 0) {
+                    double val = bm;
+                    if (ba > sv.win_from && ba < sv.win_until) val = extrema3(sgv(ba - 1), bm, sgv(ba + 1));
+                    obuf[v] = val;
+                }
+                continue;
+            }
+            const int Lf = sv.kind ? sv.L : sv.t.L;
+            const int nout = n - Lf + 1;
+            const double tf = t_first + (double)(Lf - 1) * dt;
             const double t_ns = sv.mode ? t50_us * 1000.0 + sv.pick_ns : sv.pick_ns;
             double pc;
             int from;
             dni_window(n_w, nout, (t_ns - tf) / dt, pc, from);
             double c[LGDSP_MAX_DNI_DEG + 1] = {0, 0, 0, 0};
             for (int i = lane; i < n_w; i += 32) {
-                const double val = trap_at(TT, sv.t, from + i);
+                const double val = sv.kind ? fir_at(TT, sv.g, Lf, from + i) : trap_at(TT, sv.t, from + i);
 #pragma unroll
                 for (int j = 0; j <= LGDSP_MAX_DNI_DEG; ++j)
                     if (j < mdeg) c[j] = fma(dniA[i * mdeg + j], val, c[j]);
@@ -2126,11 +2158,17 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
                 const double u = pc - (double)from;
                 double r = c[mdeg - 1];
                 for (int j = mdeg - 2; j >= 0; --j) r = r * u + c[j];
-                obuf[v] = (nout >= n_w) ? (float)r : CUDART_NAN_F;
+                obuf[v] = (nout >= n_w) ? r : CUDART_NAN;
             }
         }
         __syncthreads();
-        for (int v = tid; v < P.nvar; v += NT) out[e * (long long)P.nvar + v] = obuf[v];
+        if (P.out_f64) {
+            double* o = reinterpret_cast<double*>(out);
+            for (int v = tid; v < P.nvar; v += NT) o[e * (long long)P.nvar + v] = obuf[v];
+        } else {
+            float* o = reinterpret_cast<float*>(out);
+            for (int v = tid; v < P.nvar; v += NT) o[e * (long long)P.nvar + v] = (float)obuf[v];
+        }
         __syncthreads();
     }
 }
@@ -2142,10 +2180,10 @@ cudaError_t sweep_configure(int* max_blocks_per_sm)
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, sweep_kernel, NT, SW_TOTAL);
 }
 
-void sweep_launch(const SweepDev& P, const uint16_t* d_wf, long long n_events, long long ld, float* d_out, int grid,
-                  cudaStream_t stream)
+void sweep_launch(const SweepDev& P, const uint16_t* d_wf, long long n_events, long long ld, void* d_out, double* d_aux,
+                  int grid, cudaStream_t stream)
 {
-    sweep_kernel<<<grid, NT, SW_TOTAL, stream>>>(P, d_wf, n_events, ld, d_out);
+    sweep_kernel<<<grid, NT, SW_TOTAL, stream>>>(P, d_wf, n_events, ld, d_out, d_aux);
 }
 
 void icpc_launch(const IcpcDev& P, const uint16_t* d_wf, long long n_events, long long ld, double* d_rows, int grid,

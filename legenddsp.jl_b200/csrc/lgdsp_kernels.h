@@ -15,9 +15,12 @@ void icpc_launch(const IcpcDev& P, const uint16_t* d_wf, long long n_events, lon
 
 // trapezoid sweep kernel
 struct SweepVar {
-    TrapDev t;
+    TrapDev t;             // kind 0
     double pick_ns;
-    int mode, pad_;
+    int mode, kind;        // kind 0 trapezoid, 1 FIR on TT (differenced taps), 2 Savitzky-Golay + windowed maximum
+    int L;                 // filter length (trap L / FIR taps / SG taps)
+    int sg_off, win_from, win_until;
+    const double* g;       // device: kind 1: L+1 differenced FIR taps on TT; kind 2: L+1 differenced SG taps on TT
 };
 struct SweepDev {
     int n, tx_min_n;
@@ -27,11 +30,12 @@ struct SweepDev {
     DniDev sig_dni;
     const double* dni_A;     // [LGDSP_MAX_DNI*4]
     const SweepVar* vars;    // device array
-    int nvar, pad_;
+    int nvar, out_f64;
+    double bl_inv_n, bl_sX, bl_sXX;   // baseline regression constants (aux outputs)
 };
 cudaError_t sweep_configure(int* max_blocks_per_sm);
-void sweep_launch(const SweepDev& P, const uint16_t* d_wf, long long n_events, long long ld, float* d_out, int grid,
-                  cudaStream_t stream);
+void sweep_launch(const SweepDev& P, const uint16_t* d_wf, long long n_events, long long ld, void* d_out, double* d_aux,
+                  int grid, cudaStream_t stream);
 
 // synthetic generator
 void synth_launch(const lgdsp_synth_params& sp, long long first_event, long long n_events, long long ld, uint16_t* d_wf,

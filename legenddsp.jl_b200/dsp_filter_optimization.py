@@ -1,6 +1,8 @@
-"""Trapezoidal filter-optimisation sweeps: host-side mirror of `dsp_trap_rt_optimization`
-(/root/reference/src/dsp_filter_optimization.jl:102-133) and `dsp_trap_ft_optimization` (:241-274), plus the
-batched (rt x ft) grid that callers of the reference build by looping over the ft sweep (BASELINE.json config 4).
+"""Filter-optimisation sweeps: host-side mirror of /root/reference/src/dsp_filter_optimization.jl --
+`dsp_trap_rt_optimization` (:102-133), `dsp_cusp_rt_optimization` (:145-182), `dsp_zac_rt_optimization` (:193-231),
+`dsp_trap_ft_optimization` (:241-274), `dsp_cusp_ft_optimization` (:286-325), `dsp_zac_ft_optimization` (:336-375),
+`dsp_sg_optimization` (:393-441), plus the batched (rt x ft) grid that callers of the reference build by looping over
+the ft sweep (BASELINE.json config 4).  The `_compressed` and QC-classifier variants are out of scope.
 """
 from __future__ import annotations
 
@@ -10,7 +12,10 @@ import numpy as np
 
 from . import _abi
 from ._lib import Handle
-from .config import DSPConfig, Q, grid_values, resolve_sweep_params, trap_variants, us
+from collections import OrderedDict
+
+from .config import (DSPConfig, Q, RddspPolicy, DEFAULT_POLICY, cuspzac_sweep_variants, get_fltpars, grid_values,
+                     resolve_sweep_params, sg_sweep_variants, trap_sweep_variants, trap_variants, us)
 from .dsp_icpc import _as_waveforms, _signal_u16, get_handle
 
 
@@ -58,3 +63,90 @@ def dsp_trap_rtft_grid(wvfs, config: DSPConfig, τ: Q, rts: Optional[Sequence[Q]
     var = trap_variants(rts, fts, w.step, mode="ft")
     out = _run(w, config, τ, var, device, handle)
     return np.ascontiguousarray(out.T).reshape(len(rts), len(fts), -1)
+
+
+# ----------------------------------------------------------------------------------------------
+# general sweeps (lgdsp_sweep_run): CUSP / ZAC rise- and flat-top-time sweeps, Savitzky-Golay window-length sweep
+# ----------------------------------------------------------------------------------------------
+def _run_general(wvfs, config: DSPConfig, τ: Q, variants, *, f64: bool, want_aux: bool = False, device: int = 0,
+                 handle: Optional[Handle] = None):
+    w = _as_waveforms(wvfs)
+    sig = _signal_u16(w.signal)
+    n_events, n_samples = sig.shape
+    S = resolve_sweep_params(config, τ, n_samples=n_samples, t_first=w.t_first, step=w.step, out_f64=f64)
+    h = handle or get_handle(device)
+    out = np.zeros((n_events, len(variants)), dtype=np.float64 if f64 else np.float32)
+    aux = np.zeros((n_events, 4), dtype=np.float64) if want_aux else None
+    h.gsweep_run_host(S, sig.ctypes.data, n_events, sig.strides[0] // 2, variants.array, out.ctypes.data,
+                      aux.ctypes.data if want_aux else None)
+    return (out, aux) if want_aux else out
+
+
+def _cuspzac_rt(kind, wvfs, config, τ, ft, policy, device, handle):
+    w = _as_waveforms(wvfs)
+    rts = grid_values(config.e_grid_rt_cusp if kind == "cusp" else config.e_grid_rt_zac)
+    var = cuspzac_sweep_variants(config, kind, rts, [ft], w.step, mode="rt", policy=policy)
+    out = _run_general(w, config, τ, var, f64=True, device=device, handle=handle)
+    return np.ascontiguousarray(out.T)
+
+
+def _cuspzac_ft(kind, wvfs, config, τ, rt, policy, device, handle):
+    w = _as_waveforms(wvfs)
+    fts = grid_values(config.e_grid_ft_cusp if kind == "cusp" else config.e_grid_ft_zac)
+    var = cuspzac_sweep_variants(config, kind, [rt], fts, w.step, mode="ft", policy=policy)
+    out = _run_general(w, config, τ, var, f64=False, device=device, handle=handle)
+    return np.ascontiguousarray(out.T)
+
+
+def dsp_cusp_rt_optimization(wvfs, config: DSPConfig, τ: Q, *, ft: Q = us(2.0), policy: RddspPolicy = DEFAULT_POLICY,
+                             device: int = 0, handle: Optional[Handle] = None) -> np.ndarray:
+    """ENC noise grid for the CUSP rise-time grid at fixed flat-top `ft`, pick-off `enc_pickoff_cusp`:
+    Float64[n_rt, n_events]  (src/dsp_filter_optimization.jl:145-182)"""
+    return _cuspzac_rt("cusp", wvfs, config, τ, ft, policy, device, handle)
+
+
+def dsp_zac_rt_optimization(wvfs, config: DSPConfig, τ: Q, *, ft: Q = us(2.0), policy: RddspPolicy = DEFAULT_POLICY,
+                            device: int = 0, handle: Optional[Handle] = None) -> np.ndarray:
+    """same for the ZAC filter  (src/dsp_filter_optimization.jl:193-231)"""
+    return _cuspzac_rt("zac", wvfs, config, τ, ft, policy, device, handle)
+
+
+def dsp_cusp_ft_optimization(wvfs, config: DSPConfig, τ: Q, rt: Q, *, policy: RddspPolicy = DEFAULT_POLICY,
+                             device: int = 0, handle: Optional[Handle] = None) -> np.ndarray:
+    """energy grid for the CUSP flat-top grid at fixed rise time `rt`, pick-off t50 + flt_length_cusp/2:
+    Float32[n_ft, n_events]  (src/dsp_filter_optimization.jl:286-325)"""
+    return _cuspzac_ft("cusp", wvfs, config, τ, rt, policy, device, handle)
+
+
+def dsp_zac_ft_optimization(wvfs, config: DSPConfig, τ: Q, rt: Q, *, policy: RddspPolicy = DEFAULT_POLICY,
+                            device: int = 0, handle: Optional[Handle] = None) -> np.ndarray:
+    """same for the ZAC filter  (src/dsp_filter_optimization.jl:336-375)"""
+    return _cuspzac_ft("zac", wvfs, config, τ, rt, policy, device, handle)
+
+
+def dsp_sg_optimization(wvfs, config: DSPConfig, τ: Q, pars_filter, *, f_evaluate_qc=None,
+                        policy: RddspPolicy = DEFAULT_POLICY, device: int = 0, handle: Optional[Handle] = None):
+    """Savitzky-Golay window-length sweep  (src/dsp_filter_optimization.jl:393-441): table with the columns
+    aoe[n_events, n_wl] (current maximum / energy), energy (trap(rt, ft) at t50 + rt + ft/2), blmean, blslope [1/ns],
+    t50 [us], qc_label (-1)."""
+    if f_evaluate_qc is not None:
+        raise NotImplementedError("f_evaluate_qc is not supported; qc_label is -1 as in the reference without a model")
+    w = _as_waveforms(wvfs)
+    sig = _signal_u16(w.signal)
+    rt, ft = get_fltpars(pars_filter, "trap", config)       # pars_filter.trap.rt / .ft  (:401-402)
+    wls = grid_values(config.a_grid_wl_sg)
+    sgv = sg_sweep_variants(config, wls, n_samples=sig.shape[1], t_first=w.t_first, step=w.step, policy=policy)
+    ev = trap_sweep_variants([rt], [ft], w.step, mode="ft")
+    # one pass: variant 0 = the energy estimate, variants 1.. = the window lengths
+    from .config import SweepVariants
+    allv = SweepVariants(1 + len(wls))
+    allv.array[0] = ev.array[0]
+    for i in range(len(wls)):
+        allv.array[1 + i] = sgv.array[i]
+    allv._keep = sgv._keep
+    out, aux = _run_general(w, config, τ, allv, f64=True, want_aux=True, device=device, handle=handle)
+    energy = out[:, 0].copy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        aoe = out[:, 1:] / energy[:, None]
+    return OrderedDict(aoe=np.ascontiguousarray(aoe), energy=energy, blmean=aux[:, 0].copy(), blslope=aux[:, 1].copy(),
+                       t50=aux[:, 2].copy(), qc_label=np.full(sig.shape[0], -1, dtype=np.int64))

@@ -702,6 +702,72 @@ ORC_API int orc_trap_sweep(const lgdsp_sweep_params* P, const uint16_t* wf, int6
     return used;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * general sweeps: every dsp_*_optimization of src/dsp_filter_optimization.jl except the _compressed / qc ones.
+ * Common part :109-117 (= :151-165, :199-213, :247-260, :292-309, :342-359, :405-423): signalstats on the baseline
+ * window, shift, InvCRFilter, t50 = get_threshold(wvfs, 0.5 * maximum).  Per variant:
+ *   kind 0  TrapezoidalChargeFilter -> SignalEstimator at the pick-off                       :125-127, :266-270
+ *   kind 1  CUSP/ZACChargeFilter (coefficient array) -> SignalEstimator at the pick-off      :173-176, :221-224, :316-318, :366-368
+ *   kind 2  SavitzkyGolayFilter -> get_wvf_maximum inside current_window                     :432-433
+ * out: double[n_events][n_variants]; aux (optional): double[n_events][4] = blmean, blslope, t50 [us], 0   (:436-438)
+ * ------------------------------------------------------------------------------------------------ */
+ORC_API int orc_sweep(const lgdsp_sweep_params* P, const uint16_t* wf, int64_t n_events, int64_t ld,
+                      const lgdsp_sweep_variant* var, int n_var, double* out, double* aux, int n_threads)
+{
+    int used = 1;
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+    used = n_threads;
+#pragma omp parallel num_threads(n_threads)
+#endif
+    {
+        const int n = P->n_samples;
+        double* w = (double*)malloc(sizeof(double) * 2 * (size_t)n);
+        double* flt = w + n;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+        for (int64_t e = 0; e < n_events; ++e) {
+            const uint16_t* raw = wf + e * ld;
+            for (int i = 0; i < n; ++i) w[i] = (double)raw[i];
+            double bl[4];
+            orc_signalstats(w, P->t_first_ns, P->dt_ns, P->bl_from, P->bl_until, bl);
+            double shift = -bl[0];
+            for (int i = 0; i < n; ++i) w[i] = w[i] + shift;
+            orc_invcr(w, n, P->pz_km1, flt);
+            memcpy(w, flt, sizeof(double) * (size_t)n);
+            double wmax = w[0];
+            for (int i = 1; i < n; ++i) if (w[i] > wmax) wmax = w[i];
+            int pos;
+            double t50 = orc_get_threshold(w, n, P->t_first_ns, P->dt_ns, wmax * 0.5, P->tx_min_n, &pos);
+            if (aux) { aux[e * 4 + 0] = bl[0]; aux[e * 4 + 1] = bl[2]; aux[e * 4 + 2] = t50; aux[e * 4 + 3] = 0.0; }
+            for (int v = 0; v < n_var; ++v) {
+                const lgdsp_sweep_variant* sv = &var[v];
+                double val;
+                if (sv->kind == 2) {
+                    int no = orc_corr_valid(w, n, sv->coeffs, sv->n_taps, flt);
+                    val = (no > sv->win_until) ? orc_get_wvf_maximum(flt, sv->win_from, sv->win_until) : NAN;
+                } else {
+                    int L, no;
+                    if (sv->kind == 0) {
+                        L = sv->trap.navg + sv->trap.ngap + sv->trap.navg2;
+                        no = orc_trap(w, n, sv->trap.navg, sv->trap.ngap, sv->trap.navg2, flt);
+                    } else {
+                        L = sv->n_taps;
+                        no = orc_fir_valid(w, n, sv->coeffs, L, flt);
+                    }
+                    double tf = P->t_first_ns + (L - 1) * P->dt_ns;
+                    double t_ns = sv->pickoff_mode ? t50 * 1000.0 + sv->pickoff_ns : sv->pickoff_ns;
+                    val = no > 0 ? orc_dni(&P->sig_dni, flt, no, (t_ns - tf) / P->dt_ns) : NAN;
+                }
+                out[e * (int64_t)n_var + v] = val;
+            }
+        }
+        free(w);
+    }
+    return used;
+}
+
 ORC_API int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -221,5 +221,19 @@ def trap_sweep(sparams, wf_u16, variants, n_threads=0):
     return out
 
 
+def sweep(sparams, wf_u16, variants, n_threads=0, want_aux=False):
+    """general sweep (orc_sweep): float64 out[n_events, n_variants] (+ aux[n_events, 4] = blmean, blslope, t50_us, 0)"""
+    wf = np.ascontiguousarray(wf_u16, dtype=np.uint16)
+    n_ev, ld = wf.shape
+    nv = len(variants)
+    out = np.zeros((n_ev, nv), dtype=np.float64)
+    aux = np.zeros((n_ev, 4), dtype=np.float64) if want_aux else None
+    L = lib()
+    L.orc_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, _dp, _dp, C.c_int]
+    L.orc_sweep(C.byref(sparams), wf.ctypes.data, n_ev, ld, C.cast(variants, C.c_void_p), nv, out.ctypes.data_as(_dp),
+                aux.ctypes.data_as(_dp) if want_aux else None, int(n_threads))
+    return (out, aux) if want_aux else out
+
+
 def num_threads():
     return lib().orc_num_threads()

@@ -21,7 +21,7 @@ def _c_layout():
 #define O(t, f) printf("offsetof " #t "." #f " %zu\n", offsetof(t, f))
 int main(void) {
   S(lgdsp_trap); S(lgdsp_dni); S(lgdsp_sg); S(lgdsp_cuspzac); S(lgdsp_icpc_params); S(lgdsp_trap_variant);
-  S(lgdsp_sweep_params); S(lgdsp_synth_params);
+  S(lgdsp_sweep_params); S(lgdsp_synth_params); S(lgdsp_sweep_variant);
   O(lgdsp_icpc_params, groups); O(lgdsp_icpc_params, sat_high); O(lgdsp_icpc_params, pz_km1);
   O(lgdsp_icpc_params, t0inv_trap); O(lgdsp_icpc_params, t0_threshold); O(lgdsp_icpc_params, tx_frac);
   O(lgdsp_icpc_params, int_dni); O(lgdsp_icpc_params, sig_dni); O(lgdsp_icpc_params, trap_e);
@@ -29,6 +29,8 @@ int main(void) {
   O(lgdsp_icpc_params, intrace_nsigma); O(lgdsp_icpc_params, intrace_bl_until); O(lgdsp_icpc_params, cuspzac_direct);
   O(lgdsp_icpc_params, cusp); O(lgdsp_icpc_params, zac);
   O(lgdsp_cuspzac, coeffs); O(lgdsp_sweep_params, sig_dni); O(lgdsp_trap_variant, pickoff_mode);
+  O(lgdsp_sweep_params, out_f64); O(lgdsp_sweep_variant, trap); O(lgdsp_sweep_variant, n_taps);
+  O(lgdsp_sweep_variant, win_until); O(lgdsp_sweep_variant, coeffs);
   printf("ncol %d\n", (int)LGDSP_NCOL);
   printf("version %u\n", (unsigned)LGDSP_PARAMS_VERSION);
   return 0; }
@@ -48,7 +50,8 @@ def test_ctypes_mirror_matches_header(L):
     A = L._abi
     pairs = {"lgdsp_trap": A.Trap, "lgdsp_dni": A.Dni, "lgdsp_sg": A.Sg, "lgdsp_cuspzac": A.CuspZac,
              "lgdsp_icpc_params": A.IcpcParams, "lgdsp_trap_variant": A.TrapVariant,
-             "lgdsp_sweep_params": A.SweepParams, "lgdsp_synth_params": A.SynthParams}
+             "lgdsp_sweep_params": A.SweepParams, "lgdsp_synth_params": A.SynthParams,
+             "lgdsp_sweep_variant": A.SweepVariant}
     for name, cls in pairs.items():
         assert C.sizeof(cls) == c["sizeof " + name], name
     for key, off in c.items():
