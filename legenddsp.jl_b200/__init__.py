@@ -3,7 +3,9 @@
 Public surface (mirrors the reference's names, /root/reference/src/LegendDSP.jl:35-58 for this path):
     DSPConfig, get_fltpars                         src/types.jl, src/utils.jl
     dsp_icpc(data, config, τ, pars_filter)         src/dsp_icpc.jl:62
-    dsp_trap_rt_optimization, dsp_trap_ft_optimization   src/dsp_filter_optimization.jl:102,241
+    dsp_trap/cusp/zac_rt_optimization, dsp_trap/cusp/zac_ft_optimization, dsp_sg_optimization
+                                                   src/dsp_filter_optimization.jl:102-441
+    dsp_puls, dsp_decay_times                      src/dsp_puls.jl:29, src/dsp_decaytime.jl:11
 
 All compute happens in the in-tree CUDA library (csrc/ -> liblgdsp_b200.so) behind the C ABI of
 include/lgdsp_b200.h.  Importing this package does not need a GPU; calling a compute function does.
@@ -18,6 +20,7 @@ from .dsp_icpc import RDWaveforms, TABLE_COLUMNS, dsp_icpc, dsp_icpc_rows, rows_
 from .dsp_filter_optimization import (dsp_trap_rt_optimization, dsp_trap_ft_optimization, dsp_trap_rtft_grid,
                                       dsp_cusp_rt_optimization, dsp_zac_rt_optimization, dsp_cusp_ft_optimization,
                                       dsp_zac_ft_optimization, dsp_sg_optimization)
+from .dsp_puls import dsp_puls, dsp_decay_times, resolve_puls_params, PULS_COLUMNS
 from . import synth, sharding
 
 __all__ = [
@@ -26,6 +29,6 @@ __all__ = [
     "Handle", "LgdspError", "load_library", "RDWaveforms", "TABLE_COLUMNS", "dsp_icpc", "dsp_icpc_rows",
     "rows_to_table", "dsp_trap_rt_optimization", "dsp_trap_ft_optimization", "dsp_trap_rtft_grid",
     "dsp_cusp_rt_optimization", "dsp_zac_rt_optimization", "dsp_cusp_ft_optimization", "dsp_zac_ft_optimization",
-    "dsp_sg_optimization", "trap_sweep_variants", "cuspzac_sweep_variants", "sg_sweep_variants",
+    "dsp_sg_optimization", "dsp_puls", "dsp_decay_times", "resolve_puls_params", "PULS_COLUMNS", "trap_sweep_variants", "cuspzac_sweep_variants", "sg_sweep_variants",
     "synth", "sharding", "COLUMNS", "COL", "INT_COLUMNS", "NCOL", "UNITS",
 ]

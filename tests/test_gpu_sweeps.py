@@ -104,3 +104,38 @@ def test_general_sweep_errors_and_empty(L, O, handle):
     ok = L.trap_sweep_variants([L.us(4.0)], [L.us(2.0)], L.ns(16.0), mode="ft")
     handle.gsweep_run_host(S, wf.ctypes.data, 0, 8192, ok.array, out.ctypes.data)   # empty table in, nothing written
     assert (out == 0).all()
+
+
+def test_dsp_puls_and_decay_times(L, O, handle):
+    """dsp_puls (src/dsp_puls.jl:29-66: no pole-zero correction, t50 with the default 1000 ns mintot, e_10410) and
+    dsp_decay_times (src/dsp_decaytime.jl:11-26) are subsets of the chain served by the same kernel"""
+    n = 256
+    wf = L.synth.generate_host(n, first_event=31337)
+    data = {"waveform": L.RDWaveforms(wf, L.ns(0.0), L.ns(16.0)), "baseline": np.arange(n, dtype=np.float32),
+            "timestamp": np.arange(n, dtype=np.uint64), "eventnumber": np.arange(n, dtype=np.uint32),
+            "daqenergy": np.arange(n, dtype=np.uint16)}
+    tab = L.dsp_puls(data, L.example_config(), handle=handle)
+    assert tuple(tab.keys()) == L.PULS_COLUMNS
+    P = L.resolve_puls_params(L.example_config(), builders=O.OracleBuilders())
+    assert P.pz_km1 == 0.0 and P.tx_min_n == 62       # round(1000/16 = 62.5) ties to even
+    ref, _ = O.dsp_icpc(P, wf)
+    for name, tol in (("blmean", 0), ("blsigma", 1e-9), ("blslope", 1e-15), ("bloffset", 1e-8), ("t50", 1e-7), ("e_max", 0),
+                      ("e_10410", 1e-7)):
+        a, b = tab[name], ref[:, L.COL[name]]
+        assert np.all(np.abs(a - b) <= tol + 1e-9 * np.abs(b)), name
+    assert np.array_equal(tab["blfc"], data["baseline"]) and np.array_equal(tab["e_fc"], data["daqenergy"])
+    # without pole-zero correction e_10410 sits below the PZ-corrected one for real pulses
+    Pz = L.resolve_icpc_params(L.example_config(), L.us(500.0), builders=O.OracleBuilders())
+    full = L.dsp_icpc_rows(wf, Pz, handle=handle)
+    big = full[:, L.COL["e_max"]] > 1000
+    assert (tab["e_10410"][big] < full[big, L.COL["e_10410"]]).mean() > 0.9
+    # decay times in us, both call forms
+    tau = L.dsp_decay_times(L.RDWaveforms(wf), L.example_config(), handle=handle)
+    cfg = L.example_config()
+    tau2 = L.dsp_decay_times(L.RDWaveforms(wf), cfg.bl_window, cfg.tail_window, handle=handle)
+    assert np.array_equal(tau, tau2)
+    ref_tau = ref[:, L.COL["tail_tau"]] * 1e-3
+    inv = lambda t: np.where(t == 0, 0.0, 1.0 / np.where(t == 0, 1.0, t))
+    assert np.allclose(inv(tau), inv(ref_tau), rtol=1e-7, atol=1e-10)
+    good = (full[:, L.COL["e_max"]] > 5000) & (full[:, L.COL["n_sat_high"]] == 0) & (full[:, L.COL["inTrace_n"]] == 1)
+    assert abs(np.median(tau[good]) - 500.0) < 5.0       # the generator's decay constant
