@@ -2110,9 +2110,42 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
             a[0] = m; a[1] = st.slope; a[2] = t50_us; a[3] = 0.0;
         }
         const int n_w = P.sig_dni.n_w, mdeg = P.sig_dni.m;
+        // trapezoid variants: ONE THREAD per variant walks its pick-off window (4 look-ups in TT per output; the DNI
+        // matrix row is a broadcast read) -- a 200-variant grid is one window per thread instead of 25 per warp
+#pragma unroll 1
+        for (int v = tid; v < P.nvar; v += NT) {
+            if (P.vars[v].kind != 0) continue;
+            const TrapDev t = P.vars[v].t;
+            const double pick = P.vars[v].pick_ns;
+            const int mode = P.vars[v].mode;
+            const int nout = n - t.L + 1;
+            const double tf = t_first + (double)(t.L - 1) * dt;
+            const double t_ns = mode ? t50_us * 1000.0 + pick : pick;
+            double pc;
+            int from;
+            dni_window(n_w, nout, (t_ns - tf) / dt, pc, from);
+            const double* p0 = TT + from;
+            const double* p1 = p0 + t.a;
+            const double* p2 = p1 + t.g;
+            const double* p3 = p0 + t.L;
+            double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll 2
+            for (int i = 0; i < n_w; ++i) {
+                const double val = (p3[i] - p2[i]) * t.inv2 - (p1[i] - p0[i]) * t.inv1;
+                const double* a = dniA + i * mdeg;
+                c0 = fma(a[0], val, c0);
+                if (mdeg > 1) c1 = fma(a[1], val, c1);
+                if (mdeg > 2) c2 = fma(a[2], val, c2);
+                if (mdeg > 3) c3 = fma(a[3], val, c3);
+            }
+            const double u = pc - (double)from;
+            obuf[v] = (nout >= n_w) ? fma(fma(fma(c3, u, c2), u, c1), u, c0) : CUDART_NAN;
+        }
+        // FIR and Savitzky-Golay variants: one warp per variant
 #pragma unroll 1
         for (int v = wid; v < P.nvar; v += NWARP) {
             const SweepVar sv = P.vars[v];
+            if (sv.kind == 0) continue;
             if (sv.kind == 2) {
                 // SavitzkyGolay derivative trace s[j] = sum_k g[k] TT[j+k] (taps folded on the prefix sums); first argmax
                 // inside the window, parabola through its neighbours when strictly inside  (src/interpolation.jl:30-46)
@@ -2138,7 +2171,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
                 }
                 continue;
             }
-            const int Lf = sv.kind ? sv.L : sv.t.L;
+            const int Lf = sv.L;
             const int nout = n - Lf + 1;
             const double tf = t_first + (double)(Lf - 1) * dt;
             const double t_ns = sv.mode ? t50_us * 1000.0 + sv.pick_ns : sv.pick_ns;
@@ -2147,7 +2180,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
             dni_window(n_w, nout, (t_ns - tf) / dt, pc, from);
             double c[LGDSP_MAX_DNI_DEG + 1] = {0, 0, 0, 0};
             for (int i = lane; i < n_w; i += 32) {
-                const double val = sv.kind ? fir_at(TT, sv.g, Lf, from + i) : trap_at(TT, sv.t, from + i);
+                const double val = fir_at(TT, sv.g, Lf, from + i);
 #pragma unroll
                 for (int j = 0; j <= LGDSP_MAX_DNI_DEG; ++j)
                     if (j < mdeg) c[j] = fma(dniA[i * mdeg + j], val, c[j]);
