@@ -850,7 +850,6 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         if (tid < 24) spar->sgg[tid >> 3][tid & 7] = P.sg[tid >> 3].gg[tid & 7];
     }
     __syncthreads();
-    const bool sg_short0 = P.sg[0].n_taps + 1 <= 8;
     // SG trace sample j of filter f
     auto sg_at = [&](int f, int j) -> double {
         return (P.sg[f].n_taps + 1 <= 8) ? sg_eval8(TT, spar->sgg[f], j) : sg_eval(TT, P.sg[f].gg, P.sg[f].n_taps, j);
