@@ -29,6 +29,7 @@
 // The waveform is read from HBM exactly once (16 KB) and 392 B are written.
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <type_traits>
 #include "lgdsp_device.cuh"
 #include "lgdsp_kernels.h"
 
@@ -1353,7 +1354,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         }
         SECT(14);
         // CUSP/ZAC prefix tables (first descriptor)
-        if (cz_structured) cz_scan(0, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
+        if (cz_structured) cz_scan(npass == 2 ? 1 : 0, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
         SECT(15);
         __syncthreads();   // ---- B3 ----
         LGDSP_PHASE(3);
@@ -1748,13 +1749,15 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             }
         };
         bool queue_done = false;
-        const int np = max(npass, 1);
-#pragma unroll 1
-        for (int ps = 0; ps < np; ++ps) {
-            const bool czp = ps < npass;   // structured CUSP/ZAC pass (otherwise only the queue and the scalar jobs)
+        // One pass of the structured CUSP/ZAC evaluation.  The descriptor index is a compile-time constant so that its
+        // fields are immediate constant-bank operands inside the recurrences (a run-time index costs an indexed constant
+        // load per use).  The LAST pass always uses descriptor 0 (CUSP, or both filters when they share their parameters)
+        // and carries the work queue's scalar jobs; a separate ZAC descriptor (index 1) is evaluated in a pass before it.
+        auto cz_pass = [&](auto psc, const bool czp, const bool want_cusp, const bool want_zac, const bool rescan,
+                           const bool last_pass) {
+            constexpr int ps = decltype(psc)::value;
             const CzDev& Z = P.cz[ps];
-            const bool want_cusp = czp && (P.cz_shared || ps == 0), want_zac = czp && (P.cz_shared || ps == 1);
-            if (ps > 0) {
+            if (rescan) {
                 __syncthreads();   // the previous pass is done with the tables, the coarse values and the output buffer
                 if (tid == 0) ibuf[IB_CZN] = 0;
                 cz_scan(ps, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
@@ -1782,7 +1785,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             __syncthreads();   // ---- B4: tables are dead, coarse values and the work queue are complete ----
             LGDSP_PHASE(4);
             SECT(21);
-            if (czp && ps == npass - 1) prefetch_next();   // every thread has read its table entries: xs may be overwritten
+            if (czp && last_pass) prefetch_next();   // every thread has read its table entries: xs may be overwritten
             // candidate chunks: Lipschitz bound on (33 tid, 33 tid + 33) against the best coarse value; chunks that
             // hold part of a pick-off window are always evaluated
             double Mc = 0.0, Mz = 0.0;
@@ -1824,7 +1827,6 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
             }
             SECT(22);
             // the queued intervals, spread over all warps (before the long recurrences of the candidate warps)
-            const bool last_pass = ps == np - 1;
             if (!queue_done) {
                 run_queue();
                 queue_done = true;
@@ -1867,7 +1869,9 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 if (r0 + CZCAP >= ncz) break;
                 __syncthreads();   // the buffer is reused by the next round
             }
-        }
+        };
+        if (npass == 2) cz_pass(std::integral_constant<int, 1>{}, true, false, true, false, false);
+        cz_pass(std::integral_constant<int, 0>{}, npass >= 1, npass >= 1, npass == 1, npass == 2, true);
         // CUSP/ZAC partials
         {
             czmax[0] = wargmax_d(czmax[0], czarg[0]);
