@@ -277,6 +277,29 @@ __device__ __noinline__ void mask_commit_reversed(uint32_t* M, int tid, unsigned
     if (mid && w0 + 1 < NWORDS) atomicOr(&M[w0 + 1], mid);
 }
 
+// Warp-cooperative commit of two 33-bit chunk masks of chunk q (bit k <-> position 33q + k): lanes 0,1 write the two words
+// of mask A, lanes 2,3 those of mask B (B optionally on the time-reversed trace of length nlen) -- one atomic instruction
+// for the warp instead of four sequential ones.  Every lane passes the same arguments.
+__device__ __forceinline__ void commit_pair(uint32_t* MA, unsigned long long bits_a, uint32_t* MB, unsigned long long bits_b,
+                                            bool b_reversed, int nlen, int q, int lane)
+{
+    if (lane >= 4) return;
+    const bool isb = lane >= 2;
+    unsigned long long bits = isb ? bits_b : bits_a;
+    uint32_t* M = isb ? MB : MA;
+    if (M == nullptr || bits == 0ull) return;
+    int base = q * CH;
+    if (isb && b_reversed) {
+        bits = __brevll(bits) >> (64 - CH);            // reversed bit (32-k) = forward bit k
+        base = nlen - 1 - (q * CH + CH - 1);
+        if (base < 0) { bits >>= (-base); base = 0; }
+    }
+    const int w = (base >> 5) + (lane & 1), s0 = base & 31;
+    const unsigned long long sh = bits << s0;          // 33 bits shifted by <= 31: fits in 64
+    const uint32_t word = (lane & 1) ? (uint32_t)(sh >> 32) : (uint32_t)sh;
+    if (word && w < NWORDS) atomicOr(&M[w], word);
+}
+
 // One warp: find runs of >= k consecutive set bits in the NWORDS-word mask M (bits beyond the trace are zero)
 // that do not start at bit 0 -- the Intersect state machine: `pos` = start of the first such
 // run (-1 if none), `mult` = number of such runs.  Every lane looks for run STARTS (set bit after a clear bit) in its
@@ -1402,10 +1425,9 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 const double o = v ? trap_at(TT, tr, j) : 0.0;
                 const unsigned mp = __ballot_sync(FULL, v && (o >= th));
                 const unsigned mn_ = __ballot_sync(FULL, v && (-o >= th));
-                if (lane == 0) {
-                    if (type == 0) mask_commit(masks + M_T0 * NWORDS, q, (unsigned long long)mp << 1);
-                    if (type == 1 || P.t0inv_same) mask_commit(masks + M_T0INV * NWORDS, q, (unsigned long long)mn_ << 1);
-                }
+                commit_pair(type == 0 ? masks + M_T0 * NWORDS : nullptr, (unsigned long long)mp << 1,
+                            (type == 1 || P.t0inv_same) ? masks + M_T0INV * NWORDS : nullptr, (unsigned long long)mn_ << 1,
+                            false, 0, q, lane);
             } else if (type == 2) {
                 const int j = q * CH + 1 + lane;
                 if (j < P.e535.nout) {
@@ -1422,18 +1444,14 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 const int j = q * CH + lane;
                 const bool v = j < nsg;
                 const double sv = v ? sg_at(0, j) : 0.0;
-                unsigned long long bc = __ballot_sync(FULL, v && (sv >= cur_thr));
-                unsigned long long bp = __ballot_sync(FULL, v && (sv >= pile_thr));
-                if (lane == 0) {
-                    const int j2 = q * CH + 32;
-                    if (j2 < nsg) {
-                        const double s2 = sg_at(0, j2);
-                        bc |= (s2 >= cur_thr) ? (1ull << 32) : 0ull;
-                        bp |= (s2 >= pile_thr) ? (1ull << 32) : 0ull;
-                    }
-                    mask_commit(masks + M_CUR * NWORDS, q, bc);
-                    mask_commit_reversed(masks + M_PILE * NWORDS, q, bp, nsg);
-                }
+                // the 33rd output of the chunk: evaluated by every lane (same value), no divergence
+                const int j2 = q * CH + 32;
+                const double s2 = (j2 < nsg) ? sg_at(0, j2) : -CUDART_INF;
+                const unsigned long long bc = (unsigned long long)__ballot_sync(FULL, v && (sv >= cur_thr)) |
+                                              ((s2 >= cur_thr) ? (1ull << 32) : 0ull);
+                const unsigned long long bp = (unsigned long long)__ballot_sync(FULL, v && (sv >= pile_thr)) |
+                                              ((s2 >= pile_thr) ? (1ull << 32) : 0ull);
+                commit_pair(masks + M_CUR * NWORDS, bc, masks + M_PILE * NWORDS, bp, true, nsg, q, lane);
             }
         };
         // ---- coarse-to-fine trapezoids: lane i of warp w owns the interval (33q, 33q+33), q = 32w + i ----
@@ -1674,7 +1692,21 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                     }
                     row[LGDSP_COL_a_sg + f] = v;
                 }
-                // crossing resolution of the sg[0] masks (complete since B6), then t50_current and the in-trace pile-up
+            }
+        } else if (wid == 7) {
+            if (G & LGDSP_GROUP_QDRIFT) {
+                int pos0, mult_;
+                resolve_runs(masks + M_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
+                const double v = qdrift_warp(t0_us(false, pos0), P.qd_first, P.qd_last);   // qdrift @ t0
+                if (lane == 0) row[LGDSP_COL_qdrift] = v;
+            }
+        } else if (wid == 6) {
+            if (G & LGDSP_GROUP_QDRIFT) {
+                const double v = qdrift_warp(tx_us(2), P.lq_first, P.lq_last);       // lq @ t80
+                if (lane == 0) row[LGDSP_COL_lq] = v;
+            }
+            if (G & LGDSP_GROUP_CURRENT) {
+                // crossing resolution of the sg[0] masks (complete since Bq), then t50_current and the in-trace pile-up
                 int posc, posp, multc, multp;
                 resolve_runs(masks + M_CUR * NWORDS, P.tx_min_n, lane, posc, multc);
                 resolve_runs(masks + M_PILE * NWORDS, P.intr_min_n, lane, posp, multp);
@@ -1700,18 +1732,6 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                         row[LGDSP_COL_inTrace_n] = (double)multp;
                     }
                 }
-            }
-        } else if (wid == 7) {
-            if (G & LGDSP_GROUP_QDRIFT) {
-                int pos0, mult_;
-                resolve_runs(masks + M_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
-                const double v = qdrift_warp(t0_us(false, pos0), P.qd_first, P.qd_last);   // qdrift @ t0
-                if (lane == 0) row[LGDSP_COL_qdrift] = v;
-            }
-        } else if (wid == 6) {
-            if (G & LGDSP_GROUP_QDRIFT) {
-                const double v = qdrift_warp(tx_us(2), P.lq_first, P.lq_last);       // lq @ t80
-                if (lane == 0) row[LGDSP_COL_lq] = v;
             }
         }
         };
