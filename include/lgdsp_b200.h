@@ -275,6 +275,52 @@ int lgdsp_icpc_run(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* 
  * on the handle's stream */
 int lgdsp_icpc_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* d_wf, int64_t n_events,
                           int64_t ld_samples, double* d_out_rows);
+/* dsp_icpc_compressed building block (/root/reference/src/dsp_icpc.jl:293-499): the same chain on waveforms of
+ * 16-bit (sample_bytes = 2) or 32-bit unsigned samples (sample_bytes = 4: presummed traces, n_samples <=
+ * LGDSP_MAX_SAMPLES/2), with an optional per-event EXTERNAL baseline: when baseline != NULL the waveform is shifted by
+ * -baseline[e] instead of by its own bl_window mean -- the windowed waveform of the compressed format is shifted by the
+ * presummed waveform's baseline / presum_rate (:349-350).  blmean..bloffset still report the statistics of the
+ * waveform's own bl_window. */
+int lgdsp_icpc_run_ext(lgdsp_handle* h, const lgdsp_icpc_params* p, const void* wf, int32_t sample_bytes,
+                       const double* baseline, int64_t n_events, int64_t ld_samples, double* out_rows);
+int lgdsp_icpc_run_ext_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const void* d_wf, int32_t sample_bytes,
+                              const double* d_baseline, int64_t n_events, int64_t ld_samples, double* d_out_rows);
+
+/* signalstats.(wvfs, from, until) on several windows of every waveform: the auxiliary baseline / pole-zero windows of
+ * dsp_icpc_compressed (:338-339 on the raw waveform, :365-366 on the baseline-subtracted one: pass shift = blmean).
+ * windows: HOST int32[n_windows][2], 0-based inclusive sample ranges; shift: NULL or double[n_events], subtracted from
+ * the samples; out: double[n_events][n_windows][LGDSP_NSTAT] = (mean, sigma, slope [1/ns], offset,
+ * slope_residual_sigma).  slope_residual_sigma = population sigma of the residuals of the straight-line fit
+ * (RadiationDetectorDSP's definition is not in the reference tree: parity unpinned). */
+#define LGDSP_NSTAT 5
+#define LGDSP_MAX_STAT_WINDOWS 16
+int lgdsp_window_stats_run(lgdsp_handle* h, const void* wf, int32_t sample_bytes, int64_t n_events, int32_t n_samples,
+                           int64_t ld_samples, double t_first_ns, double dt_ns, const double* shift,
+                           const int32_t* windows, int32_t n_windows, double* out);
+int lgdsp_window_stats_run_device(lgdsp_handle* h, const void* d_wf, int32_t sample_bytes, int64_t n_events,
+                                  int32_t n_samples, int64_t ld_samples, double t_first_ns, double dt_ns,
+                                  const double* d_shift, const int32_t* windows, int32_t n_windows, double* d_out);
+
+/* ---- dsp_icpc_compressed(data, config, tau, pars_filter)  /root/reference/src/dsp_icpc.jl:293-499 ----
+ * Every event has a presummed waveform (energies, tail, saturation, in-trace pile-up; step = presum_rate x ADC step)
+ * and a windowed waveform (t0, t10..t99, Q-drift, currents).  p_pre / p_wdw: the constants of the two time axes (NULL
+ * reuses the previous call's).  The library runs the fused chain on the presummed batch, signalstats on the five
+ * windows (auxbl1, auxbl2, bl_window on the raw trace; auxpz1, auxpz2 on the baseline-subtracted trace, :338-339, :346,
+ * :365-366) and the fused chain on the windowed batch shifted by -blmean_pre / presum_rate (:350).
+ * aux_windows: HOST int32[4][2] = auxbl1, auxbl2, auxpz1, auxpz2 as 0-based inclusive sample ranges of the presummed
+ * axis.  Outputs: rows_pre, rows_wdw: double[n_events][LGDSP_NCOL] (the caller picks the columns the reference takes
+ * from each waveform, :463-499); stats: double[n_events][5][LGDSP_NSTAT] in the window order auxbl1, auxbl2, bl,
+ * auxpz1, auxpz2. */
+int lgdsp_icpc_compressed_run(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, const lgdsp_icpc_params* p_wdw,
+                              const void* wf_pre, int32_t pre_sample_bytes, int64_t ld_pre, const void* wf_wdw,
+                              int32_t wdw_sample_bytes, int64_t ld_wdw, double presum_rate, const int32_t* aux_windows,
+                              int64_t n_events, double* rows_pre, double* rows_wdw, double* stats);
+int lgdsp_icpc_compressed_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, const lgdsp_icpc_params* p_wdw,
+                                     const void* d_wf_pre, int32_t pre_sample_bytes, int64_t ld_pre, const void* d_wf_wdw,
+                                     int32_t wdw_sample_bytes, int64_t ld_wdw, double presum_rate,
+                                     const int32_t* aux_windows, int64_t n_events, double* d_rows_pre, double* d_rows_wdw,
+                                     double* d_stats);
+
 /* upload/validate params once and reuse them for many _device calls (avoids the per-call upload);
  * pass p == NULL to lgdsp_icpc_run_device afterwards */
 int lgdsp_icpc_set_params(lgdsp_handle* h, const lgdsp_icpc_params* p);

@@ -13,10 +13,12 @@ include/lgdsp_b200.h.  Importing this package does not need a GPU; calling a com
 from . import _abi
 from ._abi import COLUMNS, COL, INT_COLUMNS, NCOL, UNITS
 from .config import (DSPConfig, Q, RddspPolicy, DEFAULT_POLICY, LibBuilders, example_config, tiefree_config,
-                     get_fltpars, grid_values, ns, us, resolve_icpc_params, resolve_sweep_params, trap_variants,
+                     get_fltpars, grid_values, ns, us, resolve_icpc_params, resolve_compressed_params, resolve_sweep_params,
+                     trap_variants,
                      trap_sweep_variants, cuspzac_sweep_variants, sg_sweep_variants, SweepVariants, params_summary)
 from ._lib import Handle, LgdspError, load_library, LIB_PATH, EXPORTED_SYMBOLS
-from .dsp_icpc import RDWaveforms, TABLE_COLUMNS, dsp_icpc, dsp_icpc_rows, rows_to_table, get_handle
+from .dsp_icpc import (RDWaveforms, TABLE_COLUMNS, COMPRESSED_COLUMNS, dsp_icpc, dsp_icpc_rows, rows_to_table, get_handle,
+                       dsp_icpc_compressed, compressed_to_table)
 from .dsp_filter_optimization import (dsp_trap_rt_optimization, dsp_trap_ft_optimization, dsp_trap_rtft_grid,
                                       dsp_cusp_rt_optimization, dsp_zac_rt_optimization, dsp_cusp_ft_optimization,
                                       dsp_zac_ft_optimization, dsp_sg_optimization)
@@ -30,5 +32,6 @@ __all__ = [
     "rows_to_table", "dsp_trap_rt_optimization", "dsp_trap_ft_optimization", "dsp_trap_rtft_grid",
     "dsp_cusp_rt_optimization", "dsp_zac_rt_optimization", "dsp_cusp_ft_optimization", "dsp_zac_ft_optimization",
     "dsp_sg_optimization", "dsp_puls", "dsp_decay_times", "resolve_puls_params", "PULS_COLUMNS", "trap_sweep_variants", "cuspzac_sweep_variants", "sg_sweep_variants",
+    "dsp_icpc_compressed", "compressed_to_table", "COMPRESSED_COLUMNS", "resolve_compressed_params",
     "synth", "sharding", "COLUMNS", "COL", "INT_COLUMNS", "NCOL", "UNITS",
 ]

@@ -48,6 +48,14 @@ def load_library():
     L.lgdsp_icpc_set_params.argtypes = [vp, C.POINTER(_abi.IcpcParams)]
     L.lgdsp_icpc_run.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i64, i64, vp]
     L.lgdsp_icpc_run_device.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i64, i64, vp]
+    L.lgdsp_icpc_run_ext.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i32, vp, i64, i64, vp]
+    L.lgdsp_icpc_run_ext_device.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i32, vp, i64, i64, vp]
+    L.lgdsp_window_stats_run.argtypes = [vp, vp, i32, i64, i32, i64, C.c_double, C.c_double, vp, vp, i32, vp]
+    L.lgdsp_window_stats_run_device.argtypes = [vp, vp, i32, i64, i32, i64, C.c_double, C.c_double, vp, vp, i32, vp]
+    _comp = [vp, C.POINTER(_abi.IcpcParams), C.POINTER(_abi.IcpcParams), vp, i32, i64, vp, i32, i64, C.c_double, vp, i64,
+             vp, vp, vp]
+    L.lgdsp_icpc_compressed_run.argtypes = _comp
+    L.lgdsp_icpc_compressed_run_device.argtypes = _comp
     L.lgdsp_trap_sweep_run.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64, C.POINTER(_abi.TrapVariant), i32, vp]
     L.lgdsp_trap_sweep_run_device.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64,
                                               C.POINTER(_abi.TrapVariant), i32, vp]
@@ -65,7 +73,8 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "lgdsp_version", "lgdsp_last_error", "lgdsp_create", "lgdsp_destroy", "lgdsp_launch_count", "lgdsp_synchronize",
     "lgdsp_lsq_fit_matrix", "lgdsp_sg_coeffs", "lgdsp_cusp_coeffs", "lgdsp_zac_coeffs",
-    "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params",
+    "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params", "lgdsp_icpc_run_ext", "lgdsp_icpc_run_ext_device",
+    "lgdsp_window_stats_run", "lgdsp_window_stats_run_device", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
     "lgdsp_trap_sweep_run", "lgdsp_trap_sweep_run_device", "lgdsp_sweep_run", "lgdsp_sweep_run_device",
     "lgdsp_synth_generate_device", "lgdsp_synth_generate_host", "lgdsp_last_kernel_ms", "lgdsp_debug_phase_cycles", "lgdsp_debug_section_cycles",
 )
@@ -139,6 +148,49 @@ class Handle:
     def icpc_run_device(self, params, d_wf_ptr, n_events, ld, d_out_ptr):
         self._check(self._lib.lgdsp_icpc_run_device(self._h, C.byref(params) if params is not None else None,
                                                     C.c_void_p(d_wf_ptr), int(n_events), int(ld), C.c_void_p(d_out_ptr)))
+
+    def icpc_run_ext_host(self, params, wf_ptr, sample_bytes, baseline_ptr, n_events, ld, out_ptr):
+        """dsp_icpc chain on uint16 / uint32 samples with an optional external per-event baseline (host buffers)"""
+        self._check(self._lib.lgdsp_icpc_run_ext(self._h, C.byref(params) if params is not None else None, C.c_void_p(wf_ptr),
+                                                 int(sample_bytes), C.c_void_p(baseline_ptr) if baseline_ptr else None,
+                                                 int(n_events), int(ld), C.c_void_p(out_ptr)))
+
+    def icpc_run_ext_device(self, params, d_wf_ptr, sample_bytes, d_baseline_ptr, n_events, ld, d_out_ptr):
+        self._check(self._lib.lgdsp_icpc_run_ext_device(self._h, C.byref(params) if params is not None else None,
+                                                        C.c_void_p(d_wf_ptr), int(sample_bytes),
+                                                        C.c_void_p(d_baseline_ptr) if d_baseline_ptr else None,
+                                                        int(n_events), int(ld), C.c_void_p(d_out_ptr)))
+
+    def window_stats_host(self, wf_ptr, sample_bytes, n_events, n_samples, ld, t_first_ns, dt_ns, shift_ptr, windows, out_ptr):
+        """signalstats on `windows` ([(from, until), ...] 0-based inclusive) of every waveform; out double[n][nw][5]"""
+        w = (C.c_int32 * (2 * len(windows)))(*[int(v) for ab in windows for v in ab])
+        self._check(self._lib.lgdsp_window_stats_run(self._h, C.c_void_p(wf_ptr), int(sample_bytes), int(n_events), int(n_samples),
+                                                     int(ld), float(t_first_ns), float(dt_ns),
+                                                     C.c_void_p(shift_ptr) if shift_ptr else None, w, len(windows),
+                                                     C.c_void_p(out_ptr)))
+
+    def window_stats_device(self, d_wf_ptr, sample_bytes, n_events, n_samples, ld, t_first_ns, dt_ns, d_shift_ptr, windows,
+                            d_out_ptr):
+        w = (C.c_int32 * (2 * len(windows)))(*[int(v) for ab in windows for v in ab])
+        self._check(self._lib.lgdsp_window_stats_run_device(self._h, C.c_void_p(d_wf_ptr), int(sample_bytes), int(n_events),
+                                                            int(n_samples), int(ld), float(t_first_ns), float(dt_ns),
+                                                            C.c_void_p(d_shift_ptr) if d_shift_ptr else None, w, len(windows),
+                                                            C.c_void_p(d_out_ptr)))
+
+    def _compressed(self, fn, p_pre, p_wdw, pre_ptr, pre_bytes, ld_pre, wdw_ptr, wdw_bytes, ld_wdw, presum_rate, aux_windows,
+                    n_events, rows_pre_ptr, rows_wdw_ptr, stats_ptr):
+        w = (C.c_int32 * 8)(*[int(v) for ab in aux_windows for v in ab])
+        self._check(fn(self._h, C.byref(p_pre) if p_pre is not None else None, C.byref(p_wdw) if p_wdw is not None else None,
+                       C.c_void_p(pre_ptr), int(pre_bytes), int(ld_pre), C.c_void_p(wdw_ptr), int(wdw_bytes), int(ld_wdw),
+                       float(presum_rate), w, int(n_events), C.c_void_p(rows_pre_ptr), C.c_void_p(rows_wdw_ptr),
+                       C.c_void_p(stats_ptr)))
+
+    def icpc_compressed_run_host(self, *a):
+        """dsp_icpc_compressed on host buffers: see lgdsp_icpc_compressed_run (include/lgdsp_b200.h)"""
+        self._compressed(self._lib.lgdsp_icpc_compressed_run, *a)
+
+    def icpc_compressed_run_device(self, *a):
+        self._compressed(self._lib.lgdsp_icpc_compressed_run_device, *a)
 
     # ---- sweeps ----
     def sweep_run_host(self, sparams, wf_ptr, n_events, ld, variants, out_ptr):

@@ -328,7 +328,8 @@ def _sg_taps(length: Q, step: Q, policy: RddspPolicy) -> int:
 
 def _fill_sg(s: _abi.Sg, length: Q, degree: int, step: Q, policy: RddspPolicy, builders) -> None:
     n = _sg_taps(length, step, policy)
-    if n > _abi.LGDSP_MAX_SG or n <= degree:
+    # n <= degree (underdetermined fit) gives the minimum-norm coefficients, see lgdsp_sg_coeffs
+    if n > _abi.LGDSP_MAX_SG or n < 1:
         raise ValueError(f"SavitzkyGolayFilter with {n} taps / degree {degree} outside the supported range")
     h = builders.sg_coeffs(n, degree, 1)
     s.n_taps = n
@@ -357,11 +358,25 @@ def _fill_cuspzac(cz: _abi.CuspZac, kind: str, rt: Q, ft: Q, tau: Q, length: Q, 
 def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, Any]] = None, *,
                         n_samples: int = 8192, t_first: Q = ns(0.0), step: Q = ns(16.0),
                         groups: int = _abi.GROUP_ALL, policy: RddspPolicy = DEFAULT_POLICY,
-                        builders=None, cuspzac_direct: bool = False) -> _abi.IcpcParams:
+                        builders=None, cuspzac_direct: bool = False, role: str = "full",
+                        presum_rate: int = 1) -> _abi.IcpcParams:
     """Everything `dsp_icpc` (src/dsp_icpc.jl:62-230) derives from (config, tau, pars_filter) and the time axis
-    of the first waveform, expressed in samples / nanoseconds."""
+    of the first waveform, expressed in samples / nanoseconds.
+
+    `role` selects one of the two passes of `dsp_icpc_compressed` (src/dsp_icpc.jl:293-499): "pre" resolves what the
+    presummed waveform needs (saturation with sat_high * presum_rate :334, windows, energy filters, the in-trace filter
+    SavitzkyGolayFilter(sg_wl * presum_rate / 2) :439), "wdw" what the windowed waveform needs (t0, t10..t99, Q-drift,
+    currents).  What a pass does not use is filled with the smallest valid placeholder (its groups are switched off or
+    its columns are not read)."""
     if builders is None:
         builders = LibBuilders()
+    if role not in ("full", "pre", "wdw"):
+        raise ValueError(f"unknown role {role!r}")
+    if role == "pre":
+        groups = _abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_TRAPS | _abi.GROUP_CUSPZAC | _abi.GROUP_CURRENT
+    elif role == "wdw":
+        groups = _abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_QDRIFT | _abi.GROUP_CURRENT
+    dummy_trap = _abi.Trap(1, 0, 1, 0)
     kw = cfg.kwargs_pars
     P = _abi.IcpcParams()
     P.struct_size = C.sizeof(_abi.IcpcParams)
@@ -374,7 +389,7 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
 
     # src/dsp_icpc.jl:93-94  (sic: 2^bit_depth - bit_depth)
     bit_depth = int(kw["fc_bit_depth"])
-    P.sat_low, P.sat_high = 0, 2 ** bit_depth - bit_depth
+    P.sat_low, P.sat_high = 0, (2 ** bit_depth - bit_depth) * (int(presum_rate) if role == "pre" else 1)   # :334
 
     def window(w, first_x: Q, n_trace: int, what: str):
         a = _sub_over_step(w[0], first_x, step)
@@ -384,8 +399,13 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
             raise AssertionError(f"{what}: index range {a + 1}:{b + 1} outside 1:{n_trace}")
         return a, b
 
-    P.bl_from, P.bl_until = window(cfg.bl_window, t_first, n, "bl_window")
-    P.tail_from, P.tail_until = window(cfg.tail_window, t_first, n, "tail_window")
+    if role == "wdw":
+        # the windowed waveform is shifted by the presummed baseline (:350); its own statistics are not read
+        P.bl_from, P.bl_until = 0, min(n - 1, 15)
+        P.tail_from, P.tail_until = max(0, n - 16), n - 1
+    else:
+        P.bl_from, P.bl_until = window(cfg.bl_window, t_first, n, "bl_window")
+        P.tail_from, P.tail_until = window(cfg.tail_window, t_first, n, "tail_window")
 
     # InvCRFilter(tau) [RDDSP]: RC = tau/dt, alpha = RC/(RC+1), k = 1/alpha
     RC = _ratio(tau, step)
@@ -394,8 +414,11 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
 
     # get_t0: src/dsp_routines.jl:9-25
     fp = kw["t0_flt_pars"]
-    P.t0_trap = _trap(fp[0], fp[1], step, fp[2])
-    P.t0inv_trap = _trap(ns(40.0), ns(100.0), step, ns(2000.0))   # default flt_pars, src/dsp_icpc.jl:207
+    if role == "pre":
+        P.t0_trap = P.t0inv_trap = dummy_trap     # t0 / t0_inv come from the windowed waveform (:378, :458)
+    else:
+        P.t0_trap = _trap(fp[0], fp[1], step, fp[2])
+        P.t0inv_trap = _trap(ns(40.0), ns(100.0), step, ns(2000.0))   # default flt_pars, src/dsp_icpc.jl:207
     P.t0_threshold = float(cfg.t0_threshold)
     P.t0_min_n = _min_n(kw["t0_mintot"], step)
     P.tx_min_n = _min_n(kw["tx_mintot"], step)
@@ -407,18 +430,27 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
     P.qdrift_last_ns = cfg.qdrift_int_length[2].ns()
     P.lq_first_ns = cfg.lq_int_length[0].ns()
     P.lq_last_ns = cfg.lq_int_length[2].ns()
-    _fill_dni(P.int_dni, int(kw["int_interpolation_order"]), kw["int_interpolation_length"], step, builders)
-    _fill_dni(P.sig_dni, int(kw["sig_interpolation_order"]), kw["sig_interpolation_length"], step, builders)
+    if role == "pre":   # Q-drift is evaluated on the windowed waveform only (:391-394)
+        _fill_dni(P.int_dni, 1, step * 2.0, step, builders)
+    else:
+        _fill_dni(P.int_dni, int(kw["int_interpolation_order"]), kw["int_interpolation_length"], step, builders)
+    if role == "wdw":   # the SignalEstimator of the energies runs on the presummed waveform only (:407-428)
+        _fill_dni(P.sig_dni, 1, step * 2.0, step, builders)
+    else:
+        _fill_dni(P.sig_dni, int(kw["sig_interpolation_order"]), kw["sig_interpolation_length"], step, builders)
 
     # src/dsp_icpc.jl:147-160
-    P.trap_10410 = _trap(us(10.0), us(4.0), step)
-    P.trap_535 = _trap(us(5.0), us(3.0), step)
-    P.trap_313 = _trap(us(3.0), us(1.0), step)
     trap_rt, trap_ft = get_fltpars(pars_filter, "trap", cfg)
     cusp_rt, cusp_ft = get_fltpars(pars_filter, "cusp", cfg)
     zac_rt, zac_ft = get_fltpars(pars_filter, "zac", cfg)
     sg_wl = get_fltpars(pars_filter, "sg", cfg)
-    P.trap_e = _trap(trap_rt, trap_ft, step)
+    if role == "wdw":
+        P.trap_10410 = P.trap_535 = P.trap_313 = P.trap_e = dummy_trap
+    else:
+        P.trap_10410 = _trap(us(10.0), us(4.0), step)
+        P.trap_535 = _trap(us(5.0), us(3.0), step)
+        P.trap_313 = _trap(us(3.0), us(1.0), step)
+        P.trap_e = _trap(trap_rt, trap_ft, step)
     P.trap_pickoff_ns = (trap_rt + trap_ft / 2).ns()
     P.cusp_pickoff_ns = (cfg.flt_length_cusp / 2).ns()
     P.zac_pickoff_ns = (cfg.flt_length_zac / 2).ns()
@@ -429,38 +461,75 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
 
     # CUSP / ZAC: src/dsp_icpc.jl:87-90,98-99,167,174
     tau_off = us(10000000.0)
-    _fill_cuspzac(P.cusp, "cusp", cusp_rt, cusp_ft, tau_off, cfg.flt_length_cusp,
-                  _ratio(cfg.flt_length_cusp, step), step, policy, builders)
-    _fill_cuspzac(P.zac, "zac", zac_rt, zac_ft, tau_off, cfg.flt_length_zac,
-                  _ratio(cfg.flt_length_zac, step), step, policy, builders)
+    if role == "wdw":
+        for cz in (P.cusp, P.zac):
+            cz.n_taps, cz.flat, cz.sigma, cz.tau, cz.beta = 4, 0, 1.0, 1.0, 1.0
+    else:
+        _fill_cuspzac(P.cusp, "cusp", cusp_rt, cusp_ft, tau_off, cfg.flt_length_cusp,
+                      _ratio(cfg.flt_length_cusp, step), step, policy, builders)
+        _fill_cuspzac(P.zac, "zac", zac_rt, zac_ft, tau_off, cfg.flt_length_zac,
+                      _ratio(cfg.flt_length_zac, step), step, policy, builders)
     if P.cusp.n_taps > n or P.zac.n_taps > n:
         raise ValueError("CUSP/ZAC filter longer than the waveform")
 
     # currents: src/dsp_icpc.jl:181-186
     deg = int(cfg.sg_flt_degree)
-    _fill_sg(P.sg[0], sg_wl, deg, step, policy, builders)
-    _fill_sg(P.sg[1], ns(60.0), deg, step, policy, builders)
-    _fill_sg(P.sg[2], ns(100.0), deg, step, policy, builders)
-    for k in range(3):
-        first_k = t_first + step * float(P.sg[k].offset)
-        a, b = window(cfg.current_window, first_k, n - P.sg[k].n_taps + 1, f"current_window on sg[{k}]")
-        P.cur_from[k], P.cur_until[k] = a, b
-    a, b = window(cfg.current_window, t_first, n, "current_window")
-    P.cur_from[3], P.cur_until[3] = a, b
+    if role == "pre":
+        # :439 the in-trace / current-rise filter of the presummed waveform; the currents themselves (:431-435) are
+        # taken from the windowed waveform
+        for k in range(3):
+            _fill_sg(P.sg[k], (sg_wl * float(presum_rate)) / 2.0, deg, step, policy, builders)
+            P.cur_from[k], P.cur_until[k] = 0, n - P.sg[k].n_taps
+        P.cur_from[3], P.cur_until[3] = 0, n - 1
+    else:
+        _fill_sg(P.sg[0], sg_wl, deg, step, policy, builders)
+        _fill_sg(P.sg[1], ns(60.0), deg, step, policy, builders)
+        _fill_sg(P.sg[2], ns(100.0), deg, step, policy, builders)
+        for k in range(3):
+            first_k = t_first + step * float(P.sg[k].offset)
+            a, b = window(cfg.current_window, first_k, n - P.sg[k].n_taps + 1, f"current_window on sg[{k}]")
+            P.cur_from[k], P.cur_until[k] = a, b
+        a, b = window(cfg.current_window, t_first, n, "current_window")
+        P.cur_from[3], P.cur_until[3] = a, b
 
     # get_intracePileUp: src/dsp_routines.jl:72-82
     P.intrace_nsigma = float(cfg.inTraceCut_std_threshold)
     P.intrace_min_n = _min_n(kw["intrace_mintot"], step)
     first_sg = t_first + step * float(P.sg[0].offset)
     n_sg = n - P.sg[0].n_taps + 1
-    a = _sub_over_step(cfg.bl_window[0] + first_sg, first_sg, step)   # leftendpoint + first(time), :75
-    b = _sub_over_step(cfg.bl_window[1], first_sg, step)
+    if role == "wdw":
+        a, b = 0, min(n_sg - 1, 15)       # in-trace pile-up is evaluated on the presummed waveform (:440)
+    else:
+        a = _sub_over_step(cfg.bl_window[0] + first_sg, first_sg, step)   # leftendpoint + first(time), :75
+        b = _sub_over_step(cfg.bl_window[1], first_sg, step)
     if not (0 <= a <= b <= n_sg - 1):
         raise AssertionError(f"in-trace sigma window {a + 1}:{b + 1} outside 1:{n_sg}")
     P.intrace_bl_from, P.intrace_bl_until = a, b
 
     P.cuspzac_direct = 1 if cuspzac_direct else 0
     return P
+
+
+def resolve_compressed_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, Any]] = None, *, presum_rate: int,
+                               n_pre: int, t_first_pre: Q = ns(0.0), step_pre: Q, n_wdw: int, t_first_wdw: Q = ns(0.0),
+                               step_wdw: Q = ns(16.0), policy: RddspPolicy = DEFAULT_POLICY, builders=None):
+    """What `dsp_icpc_compressed` (src/dsp_icpc.jl:293-499) derives from (config, tau, pars_filter), the two time axes
+    and the presum rate: (params of the presummed pass, params of the windowed pass, the four auxiliary windows
+    auxbl1, auxbl2, auxpz1, auxpz2 as 0-based inclusive sample ranges of the presummed axis)."""
+    P_pre = resolve_icpc_params(cfg, tau, pars_filter, n_samples=n_pre, t_first=t_first_pre, step=step_pre, policy=policy,
+                                builders=builders, role="pre", presum_rate=presum_rate)
+    P_wdw = resolve_icpc_params(cfg, tau, pars_filter, n_samples=n_wdw, t_first=t_first_wdw, step=step_wdw, policy=policy,
+                                builders=builders, role="wdw", presum_rate=presum_rate)
+    aux = []
+    for name in ("auxbl1_window", "auxbl2_window", "auxpz1_window", "auxpz2_window"):
+        w = getattr(cfg, name)
+        a = _sub_over_step(w[0], t_first_pre, step_pre)
+        b = _sub_over_step(w[1], t_first_pre, step_pre)
+        # @assert firstindex(X) <= first(idxs) <= last(idxs) <= lastindex(X)   src/tailstats.jl:23-25
+        if not (0 <= a <= b <= n_pre - 1):
+            raise AssertionError(f"{name}: index range {a + 1}:{b + 1} outside 1:{n_pre}")
+        aux.append((a, b))
+    return P_pre, P_wdw, aux
 
 
 def resolve_sweep_params(cfg: DSPConfig, tau: Q, *, n_samples: int = 8192, t_first: Q = ns(0.0),

@@ -32,9 +32,22 @@ struct lgdsp_handle {
     size_t taps_cap = 0;
     IcpcDev icpc{};
     bool have_icpc = false;
+    // second parameter slot: the windowed-waveform pass of dsp_icpc_compressed
+    IcpcDev icpc_w{};
+    bool have_icpc_w = false;
+    double* d_dniA_w = nullptr;
+    double* d_cusp_g_w = nullptr;
+    double* d_zac_g_w = nullptr;
+    void* d_cin[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][pre, wdw] staging of the compressed host path
+    size_t cin_cap[2] = {0, 0};
+    double* d_crows = nullptr;
+    size_t crows_cap = 0;
     // host-path staging
     uint16_t* d_in[2] = {nullptr, nullptr};
     double* d_rows = nullptr;
+    double* d_aux = nullptr;   // per-event external baselines / shifts (two chunks)
+    size_t aux_cap = 0;
+    int* d_win = nullptr;      // window list of lgdsp_window_stats_run
     void* d_sweep_out = nullptr;
     size_t in_cap = 0, rows_cap = 0, sweep_out_cap = 0;
     cudaStream_t s_copy = nullptr;
@@ -131,6 +144,9 @@ void lgdsp_destroy(lgdsp_handle* h)
     cudaFree(h->d_phase);
     cudaFree(h->d_dniA); cudaFree(h->d_cusp_g); cudaFree(h->d_zac_g); cudaFree(h->d_sweep_dniA); cudaFree(h->d_vars); cudaFree(h->d_taps);
     cudaFree(h->d_in[0]); cudaFree(h->d_in[1]); cudaFree(h->d_rows); cudaFree(h->d_sweep_out);
+    cudaFree(h->d_aux); cudaFree(h->d_win);
+    cudaFree(h->d_dniA_w); cudaFree(h->d_cusp_g_w); cudaFree(h->d_zac_g_w); cudaFree(h->d_crows);
+    for (int b = 0; b < 2; ++b) for (int k = 0; k < 2; ++k) cudaFree(h->d_cin[b][k]);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]);
         if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
@@ -277,9 +293,17 @@ static bool make_czdev(const lgdsp_cuspzac& z, const double* cusp_coeffs, const 
     return true;
 }
 
-static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
+static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p, int slot = 0)
 {
     if (!p) return fail(h, LGDSP_ERR_INVALID_ARG, "params is NULL");
+    if (slot && !h->d_dniA_w) {
+        CK(cudaMalloc(&h->d_dniA_w, sizeof(double) * 2 * LGDSP_MAX_DNI * 4));
+        CK(cudaMalloc(&h->d_cusp_g_w, sizeof(double) * (LGDSP_MAX_FIR + 1)));
+        CK(cudaMalloc(&h->d_zac_g_w, sizeof(double) * (LGDSP_MAX_FIR + 1)));
+    }
+    double* const t_dniA = slot ? h->d_dniA_w : h->d_dniA;
+    double* const t_cusp = slot ? h->d_cusp_g_w : h->d_cusp_g;
+    double* const t_zac = slot ? h->d_zac_g_w : h->d_zac_g;
     if (p->struct_size != sizeof(lgdsp_icpc_params) || p->version != LGDSP_PARAMS_VERSION)
         return fail(h, LGDSP_ERR_INVALID_ARG, "lgdsp_icpc_params: size/version mismatch (got %u/%u, want %zu/%u)",
                     p->struct_size, p->version, sizeof(lgdsp_icpc_params), LGDSP_PARAMS_VERSION);
@@ -296,8 +320,8 @@ static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
     D.groups = p->groups | LGDSP_GROUP_BASE;
     D.t_first = p->t_first_ns;
     D.dt = p->dt_ns;
-    D.sat_low = (p->sat_low >= 0 && p->sat_low <= 65535) ? (int)p->sat_low : -1;
-    D.sat_high = (p->sat_high >= 0 && p->sat_high <= 65535) ? (int)p->sat_high : -1;
+    D.sat_low = (p->sat_low >= 0 && p->sat_low <= 0x7fffffffLL) ? (int)p->sat_low : -1;
+    D.sat_high = (p->sat_high >= 0 && p->sat_high <= 0x7fffffffLL) ? (int)p->sat_high : -1;
     D.bl_from = p->bl_from; D.bl_until = p->bl_until; D.tail_from = p->tail_from; D.tail_until = p->tail_until;
     D.km1 = p->pz_km1;
     D.bl_inv_n = 1.0 / (double)(p->bl_until - p->bl_from + 1);
@@ -359,7 +383,7 @@ static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
     D.intr_inv_n = 1.0 / (double)(p->intrace_bl_until - p->intrace_bl_from + 1);
     // CUSP / ZAC
     const lgdsp_cuspzac* cz[2] = {&p->cusp, &p->zac};
-    double* dst[2] = {h->d_cusp_g, h->d_zac_g};
+    double* dst[2] = {t_cusp, t_zac};
     std::vector<double> g(LGDSP_MAX_FIR + 1);
     for (int f = 0; f < 2; ++f) {
         const int L = cz[f]->n_taps;
@@ -390,22 +414,25 @@ static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p)
     std::vector<double> A(2 * LGDSP_MAX_DNI * 4, 0.0);
     memcpy(A.data(), p->int_dni.A, sizeof(double) * LGDSP_MAX_DNI * 4);
     memcpy(A.data() + LGDSP_MAX_DNI * 4, p->sig_dni.A, sizeof(double) * LGDSP_MAX_DNI * 4);
-    CK(cudaMemcpyAsync(h->d_dniA, A.data(), sizeof(double) * A.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(t_dniA, A.data(), sizeof(double) * A.size(), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    D.dni_A = h->d_dniA; D.cusp_g = h->d_cusp_g; D.zac_g = h->d_zac_g;
-    h->icpc = D;
-    h->have_icpc = true;
+    D.dni_A = t_dniA; D.cusp_g = t_cusp; D.zac_g = t_zac;
+    if (slot) { h->icpc_w = D; h->have_icpc_w = true; }
+    else { h->icpc = D; h->have_icpc = true; }
     return LGDSP_OK;
 }
 
-static int check_wf(lgdsp_handle* h, const void* wf, int64_t n_events, int64_t ld, int n, bool device)
+static int check_wf(lgdsp_handle* h, const void* wf, int64_t n_events, int64_t ld, int n, bool device, int sample_bytes = 2)
 {
+    if (sample_bytes != 2 && sample_bytes != 4) return fail(h, LGDSP_ERR_UNSUPPORTED, "sample_bytes = %d: uint16 (2) or uint32 (4) samples", sample_bytes);
+    if (sample_bytes == 4 && n > LGDSP_MAX_SAMPLES / 2)
+        return fail(h, LGDSP_ERR_UNSUPPORTED, "32-bit samples: n_samples = %d > %d", n, LGDSP_MAX_SAMPLES / 2);
     if (n_events < 0) return fail(h, LGDSP_ERR_INVALID_ARG, "n_events < 0");
     if (n_events == 0) return LGDSP_OK;  // empty table in, empty table out
     if (n_events > 0 && !wf) return fail(h, LGDSP_ERR_INVALID_ARG, "waveform pointer is NULL");
     if (ld < n) return fail(h, LGDSP_ERR_INVALID_ARG, "ld_samples (%lld) < n_samples (%d)", (long long)ld, n);
-    if (device && (((uintptr_t)wf & 15u) != 0 || ld % 8 != 0))
-        return fail(h, LGDSP_ERR_INVALID_ARG, "device waveforms must be 16-byte aligned with ld_samples %% 8 == 0 (TMA bulk copy)");
+    if (device && (((uintptr_t)wf & 15u) != 0 || (ld * sample_bytes) % 16 != 0))
+        return fail(h, LGDSP_ERR_INVALID_ARG, "device waveforms must be 16-byte aligned with rows of a multiple of 16 bytes (TMA bulk copy)");
     return LGDSP_OK;
 }
 
@@ -418,14 +445,14 @@ int lgdsp_icpc_set_params(lgdsp_handle* h, const lgdsp_icpc_params* p)
     return icpc_prepare(h, p);
 }
 
-int lgdsp_icpc_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* d_wf, int64_t n_events,
-                          int64_t ld_samples, double* d_out_rows)
+static int icpc_run_device_impl(lgdsp_handle* h, const lgdsp_icpc_params* p, const void* d_wf, int sample_bytes,
+                                const double* d_baseline, int64_t n_events, int64_t ld_samples, double* d_out_rows)
 {
     if (!h) return LGDSP_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     if (p) { int rc = icpc_prepare(h, p); if (rc) return rc; }
     if (!h->have_icpc) return fail(h, LGDSP_ERR_INVALID_ARG, "no parameters set (pass params or call lgdsp_icpc_set_params)");
-    int rc = check_wf(h, d_wf, n_events, ld_samples, h->icpc.n, true);
+    int rc = check_wf(h, d_wf, n_events, ld_samples, h->icpc.n, true, sample_bytes);
     if (rc) return rc;
     if (n_events == 0) return LGDSP_OK;  // empty input -> empty table
     if (!d_out_rows) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
@@ -440,12 +467,24 @@ int lgdsp_icpc_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const uin
         h->phase_grid = grid;
     }
     CK(cudaEventRecord(h->ev0, h->stream));
-    icpc_launch(D, d_wf, n_events, ld_samples, d_out_rows, grid, h->stream);
+    icpc_launch(D, d_wf, sample_bytes, n_events, ld_samples, d_baseline, 1, 1.0, d_out_rows, grid, h->stream);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
     h->launches += 1;
     return LGDSP_OK;
+}
+
+int lgdsp_icpc_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* d_wf, int64_t n_events,
+                          int64_t ld_samples, double* d_out_rows)
+{
+    return icpc_run_device_impl(h, p, d_wf, 2, nullptr, n_events, ld_samples, d_out_rows);
+}
+
+int lgdsp_icpc_run_ext_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const void* d_wf, int32_t sample_bytes,
+                              const double* d_baseline, int64_t n_events, int64_t ld_samples, double* d_out_rows)
+{
+    return icpc_run_device_impl(h, p, d_wf, sample_bytes, d_baseline, n_events, ld_samples, d_out_rows);
 }
 
 static int ensure_staging(lgdsp_handle* h, size_t in_bytes, size_t rows_bytes)
@@ -464,40 +503,261 @@ static int ensure_staging(lgdsp_handle* h, size_t in_bytes, size_t rows_bytes)
     return LGDSP_OK;
 }
 
+static int ensure_aux(lgdsp_handle* h, size_t bytes)
+{
+    if (bytes > h->aux_cap) {
+        cudaFree(h->d_aux); h->d_aux = nullptr; h->aux_cap = 0;
+        CK(cudaMalloc(&h->d_aux, bytes));
+        h->aux_cap = bytes;
+    }
+    return LGDSP_OK;
+}
+
 // host buffers in, host rows out: chunked, H2D of chunk k+1 overlaps the kernel of chunk k
-int lgdsp_icpc_run(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* wf, int64_t n_events,
-                   int64_t ld_samples, double* out_rows)
+static int icpc_run_host_impl(lgdsp_handle* h, const lgdsp_icpc_params* p, const void* wf, int sample_bytes,
+                              const double* baseline, int64_t n_events, int64_t ld_samples, double* out_rows)
 {
     if (!h) return LGDSP_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     if (p) { int rc = icpc_prepare(h, p); if (rc) return rc; }
     if (!h->have_icpc) return fail(h, LGDSP_ERR_INVALID_ARG, "no parameters set");
     const int n = h->icpc.n;
-    int rc = check_wf(h, wf, n_events, ld_samples, n, false);
+    int rc = check_wf(h, wf, n_events, ld_samples, n, false, sample_bytes);
     if (rc) return rc;
     if (n_events == 0) return LGDSP_OK;
     if (!out_rows) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
+    const size_t sb = (size_t)sample_bytes;
     const int64_t chunk = n_events < 8192 ? n_events : 8192;
-    rc = ensure_staging(h, (size_t)chunk * n * 2, (size_t)2 * chunk * LGDSP_NCOL * sizeof(double));
+    rc = ensure_staging(h, (size_t)chunk * n * sb, (size_t)2 * chunk * LGDSP_NCOL * sizeof(double));
     if (rc) return rc;
+    if (baseline) {
+        rc = ensure_aux(h, (size_t)2 * chunk * sizeof(double));
+        if (rc) return rc;
+    }
     const long long cap = (long long)h->sm_count * h->icpc_bps;
+    const unsigned char* src = static_cast<const unsigned char*>(wf);
     int c = 0;
     for (int64_t e0 = 0; e0 < n_events; e0 += chunk, ++c) {
         const int b = c & 1;
         const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
         if (c >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
-        CK(cudaMemcpy2DAsync(h->d_in[b], (size_t)n * 2, wf + e0 * ld_samples, (size_t)ld_samples * 2, (size_t)n * 2,
+        CK(cudaMemcpy2DAsync(h->d_in[b], (size_t)n * sb, src + (size_t)e0 * ld_samples * sb, (size_t)ld_samples * sb, (size_t)n * sb,
                              (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
+        double* d_bl = nullptr;
+        if (baseline) {
+            d_bl = h->d_aux + (size_t)b * chunk;
+            CK(cudaMemcpyAsync(d_bl, baseline + e0, (size_t)ne * sizeof(double), cudaMemcpyHostToDevice, h->s_copy));
+        }
         CK(cudaEventRecord(h->ev_ready[b], h->s_copy));
         CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
         double* d_rows = h->d_rows + (size_t)b * chunk * LGDSP_NCOL;
         const int grid = (int)(ne < cap ? ne : cap);
-        icpc_launch(h->icpc, h->d_in[b], ne, n, d_rows, grid, h->stream);
+        icpc_launch(h->icpc, h->d_in[b], sample_bytes, ne, n, d_bl, 1, 1.0, d_rows, grid, h->stream);
         CK(cudaGetLastError());
         h->launches += 1;
         CK(cudaEventRecord(h->ev_free[b], h->stream));
         CK(cudaMemcpyAsync(out_rows + e0 * LGDSP_NCOL, d_rows, (size_t)ne * LGDSP_NCOL * sizeof(double),
                            cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->s_copy));
+    CK(cudaStreamSynchronize(h->stream));
+    return LGDSP_OK;
+}
+
+int lgdsp_icpc_run(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* wf, int64_t n_events,
+                   int64_t ld_samples, double* out_rows)
+{
+    return icpc_run_host_impl(h, p, wf, 2, nullptr, n_events, ld_samples, out_rows);
+}
+
+int lgdsp_icpc_run_ext(lgdsp_handle* h, const lgdsp_icpc_params* p, const void* wf, int32_t sample_bytes,
+                       const double* baseline, int64_t n_events, int64_t ld_samples, double* out_rows)
+{
+    return icpc_run_host_impl(h, p, wf, sample_bytes, baseline, n_events, ld_samples, out_rows);
+}
+
+// signalstats on n_windows windows of every waveform (optionally shifted by -shift[e]): out double[n_events][n_windows][5]
+int lgdsp_window_stats_run_device(lgdsp_handle* h, const void* d_wf, int32_t sample_bytes, int64_t n_events, int32_t n_samples,
+                                  int64_t ld_samples, double t_first_ns, double dt_ns, const double* d_shift,
+                                  const int32_t* windows, int32_t n_windows, double* d_out)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (sample_bytes != 2 && sample_bytes != 4) return fail(h, LGDSP_ERR_UNSUPPORTED, "sample_bytes = %d", sample_bytes);
+    if (n_events < 0 || n_windows < 0 || n_windows > LGDSP_MAX_STAT_WINDOWS) return fail(h, LGDSP_ERR_INVALID_ARG, "bad n_events / n_windows");
+    if (n_events == 0 || n_windows == 0) return LGDSP_OK;
+    if (!d_wf || !windows || !d_out) return fail(h, LGDSP_ERR_INVALID_ARG, "NULL pointer");
+    if (n_samples < 1 || ld_samples < n_samples) return fail(h, LGDSP_ERR_INVALID_ARG, "bad n_samples / ld_samples");
+    if (!(dt_ns > 0) || !std::isfinite(t_first_ns)) return fail(h, LGDSP_ERR_INVALID_ARG, "bad time axis");
+    for (int w = 0; w < n_windows; ++w) {
+        const int a = windows[2 * w], b = windows[2 * w + 1];
+        // @assert firstindex(X) <= first(idxs) <= last(idxs) <= lastindex(X)   /root/reference/src/tailstats.jl:23-25
+        if (!(0 <= a && a <= b && b <= n_samples - 1)) return fail(h, LGDSP_ERR_INVALID_ARG, "window %d (%d:%d) outside the waveform", w, a, b);
+    }
+    if (!h->d_win) CK(cudaMalloc(&h->d_win, sizeof(int) * 2 * LGDSP_MAX_STAT_WINDOWS));
+    CK(cudaMemcpyAsync(h->d_win, windows, sizeof(int) * 2 * (size_t)n_windows, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    window_stats_launch(d_wf, sample_bytes, n_events, ld_samples, t_first_ns, dt_ns, d_shift, 1, 0xFFFFFFFFu, h->d_win, n_windows, d_out, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->launches += 1;
+    // the window list is read from pageable host memory by the async copy: make sure it is consumed before returning
+    CK(cudaStreamSynchronize(h->stream));
+    return LGDSP_OK;
+}
+
+int lgdsp_window_stats_run(lgdsp_handle* h, const void* wf, int32_t sample_bytes, int64_t n_events, int32_t n_samples,
+                           int64_t ld_samples, double t_first_ns, double dt_ns, const double* shift,
+                           const int32_t* windows, int32_t n_windows, double* out)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (sample_bytes != 2 && sample_bytes != 4) return fail(h, LGDSP_ERR_UNSUPPORTED, "sample_bytes = %d", sample_bytes);
+    if (n_events < 0 || n_windows < 0 || n_windows > LGDSP_MAX_STAT_WINDOWS) return fail(h, LGDSP_ERR_INVALID_ARG, "bad n_events / n_windows");
+    if (n_events == 0 || n_windows == 0) return LGDSP_OK;
+    if (!wf || !out) return fail(h, LGDSP_ERR_INVALID_ARG, "NULL pointer");
+    if (n_samples < 1 || ld_samples < n_samples) return fail(h, LGDSP_ERR_INVALID_ARG, "bad n_samples / ld_samples");
+    const size_t sb = (size_t)sample_bytes;
+    const int64_t chunk = n_events < 8192 ? n_events : 8192;
+    const size_t out_per = (size_t)n_windows * 5;
+    int rc = ensure_staging(h, (size_t)chunk * n_samples * sb, (size_t)chunk * out_per * sizeof(double));
+    if (rc) return rc;
+    if (shift) { rc = ensure_aux(h, (size_t)chunk * sizeof(double)); if (rc) return rc; }
+    const unsigned char* src = static_cast<const unsigned char*>(wf);
+    for (int64_t e0 = 0; e0 < n_events; e0 += chunk) {
+        const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
+        CK(cudaMemcpy2DAsync(h->d_in[0], (size_t)n_samples * sb, src + (size_t)e0 * ld_samples * sb, (size_t)ld_samples * sb,
+                             (size_t)n_samples * sb, (size_t)ne, cudaMemcpyHostToDevice, h->stream));
+        if (shift) CK(cudaMemcpyAsync(h->d_aux, shift + e0, (size_t)ne * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        rc = lgdsp_window_stats_run_device(h, h->d_in[0], sample_bytes, ne, n_samples, n_samples, t_first_ns, dt_ns,
+                                           shift ? h->d_aux : nullptr, windows, n_windows, h->d_rows);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out + (size_t)e0 * out_per, h->d_rows, (size_t)ne * out_per * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return LGDSP_OK;
+}
+
+// ---- dsp_icpc_compressed: presummed + windowed waveform per event (/root/reference/src/dsp_icpc.jl:293-499) ----
+static int compressed_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, const lgdsp_icpc_params* p_wdw, int pre_bytes,
+                              int wdw_bytes, double presum_rate, const int32_t* aux)
+{
+    if (p_pre) { int rc = icpc_prepare(h, p_pre, 0); if (rc) return rc; }
+    if (p_wdw) { int rc = icpc_prepare(h, p_wdw, 1); if (rc) return rc; }
+    if (!h->have_icpc || !h->have_icpc_w) return fail(h, LGDSP_ERR_INVALID_ARG, "dsp_icpc_compressed: parameters of both waveforms are needed");
+    if (!(presum_rate >= 1.0)) return fail(h, LGDSP_ERR_INVALID_ARG, "presum_rate must be >= 1");
+    if ((pre_bytes != 2 && pre_bytes != 4) || (wdw_bytes != 2 && wdw_bytes != 4))
+        return fail(h, LGDSP_ERR_UNSUPPORTED, "sample_bytes: uint16 (2) or uint32 (4) samples");
+    if (!aux) return fail(h, LGDSP_ERR_INVALID_ARG, "aux_windows is NULL");
+    const int n = h->icpc.n;
+    for (int w = 0; w < 4; ++w) {
+        const int a = aux[2 * w], b = aux[2 * w + 1];
+        if (!(0 <= a && a <= b && b <= n - 1)) return fail(h, LGDSP_ERR_INVALID_ARG, "auxiliary window %d (%d:%d) outside the presummed waveform", w, a, b);
+    }
+    if (!h->d_win) CK(cudaMalloc(&h->d_win, sizeof(int) * 2 * LGDSP_MAX_STAT_WINDOWS));
+    // window order of the statistics output: auxbl1, auxbl2, bl_window (raw), auxpz1, auxpz2 (baseline-subtracted)
+    const int win[10] = {aux[0], aux[1], aux[2], aux[3], h->icpc.bl_from, h->icpc.bl_until, aux[4], aux[5], aux[6], aux[7]};
+    CK(cudaMemcpyAsync(h->d_win, win, sizeof(win), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LGDSP_OK;
+}
+
+// the three launches of one batch, in stream order
+static void compressed_launch(lgdsp_handle* h, const void* d_pre, int pre_bytes, int64_t ld_pre, const void* d_wdw, int wdw_bytes,
+                              int64_t ld_wdw, double presum_rate, int64_t ne, double* d_rows_pre, double* d_rows_wdw, double* d_stats)
+{
+    const long long cap = (long long)h->sm_count * h->icpc_bps;
+    const int grid = (int)(ne < cap ? ne : cap);
+    // :332-346, :356-375, :383, :397-428, :439-455 on the presummed waveform
+    icpc_launch(h->icpc, d_pre, pre_bytes, ne, ld_pre, nullptr, 1, 1.0, d_rows_pre, grid, h->stream);
+    // :338-339, :346 (slope_residual_sigma), :365-366: windows 3, 4 are shifted by the baseline mean of the first launch
+    window_stats_launch(d_pre, pre_bytes, ne, ld_pre, h->icpc.t_first, h->icpc.dt, d_rows_pre + LGDSP_COL_blmean, LGDSP_NCOL, 0x18u,
+                        h->d_win, 5, d_stats, h->stream);
+    // :350 the windowed waveform is shifted by -blmean / presum_rate; :378-394, :431-435, :458
+    icpc_launch(h->icpc_w, d_wdw, wdw_bytes, ne, ld_wdw, d_rows_pre + LGDSP_COL_blmean, LGDSP_NCOL, presum_rate, d_rows_wdw, grid,
+                h->stream);
+    h->launches += 3;
+}
+
+int lgdsp_icpc_compressed_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, const lgdsp_icpc_params* p_wdw,
+                                     const void* d_wf_pre, int32_t pre_sample_bytes, int64_t ld_pre, const void* d_wf_wdw,
+                                     int32_t wdw_sample_bytes, int64_t ld_wdw, double presum_rate, const int32_t* aux_windows,
+                                     int64_t n_events, double* d_rows_pre, double* d_rows_wdw, double* d_stats)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = compressed_prepare(h, p_pre, p_wdw, pre_sample_bytes, wdw_sample_bytes, presum_rate, aux_windows);
+    if (rc) return rc;
+    rc = check_wf(h, d_wf_pre, n_events, ld_pre, h->icpc.n, true, pre_sample_bytes);
+    if (rc) return rc;
+    rc = check_wf(h, d_wf_wdw, n_events, ld_wdw, h->icpc_w.n, true, wdw_sample_bytes);
+    if (rc) return rc;
+    if (n_events == 0) return LGDSP_OK;
+    if (!d_rows_pre || !d_rows_wdw || !d_stats) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
+    CK(cudaEventRecord(h->ev0, h->stream));
+    compressed_launch(h, d_wf_pre, pre_sample_bytes, ld_pre, d_wf_wdw, wdw_sample_bytes, ld_wdw, presum_rate, n_events, d_rows_pre,
+                      d_rows_wdw, d_stats);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    return LGDSP_OK;
+}
+
+int lgdsp_icpc_compressed_run(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, const lgdsp_icpc_params* p_wdw, const void* wf_pre,
+                              int32_t pre_sample_bytes, int64_t ld_pre, const void* wf_wdw, int32_t wdw_sample_bytes,
+                              int64_t ld_wdw, double presum_rate, const int32_t* aux_windows, int64_t n_events, double* rows_pre,
+                              double* rows_wdw, double* stats)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = compressed_prepare(h, p_pre, p_wdw, pre_sample_bytes, wdw_sample_bytes, presum_rate, aux_windows);
+    if (rc) return rc;
+    const int np = h->icpc.n, nw = h->icpc_w.n;
+    rc = check_wf(h, wf_pre, n_events, ld_pre, np, false, pre_sample_bytes);
+    if (rc) return rc;
+    rc = check_wf(h, wf_wdw, n_events, ld_wdw, nw, false, wdw_sample_bytes);
+    if (rc) return rc;
+    if (n_events == 0) return LGDSP_OK;
+    if (!rows_pre || !rows_wdw || !stats) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
+    const int64_t chunk = n_events < 8192 ? n_events : 8192;
+    const size_t sbp = (size_t)pre_sample_bytes, sbw = (size_t)wdw_sample_bytes;
+    const size_t need[2] = {(size_t)chunk * np * sbp, (size_t)chunk * nw * sbw};
+    for (int k = 0; k < 2; ++k)
+        if (need[k] > h->cin_cap[k]) {
+            for (int b = 0; b < 2; ++b) { cudaFree(h->d_cin[b][k]); h->d_cin[b][k] = nullptr; }
+            h->cin_cap[k] = 0;
+            for (int b = 0; b < 2; ++b) CK(cudaMalloc(&h->d_cin[b][k], need[k]));
+            h->cin_cap[k] = need[k];
+        }
+    const size_t per_event = 2 * LGDSP_NCOL + 5 * LGDSP_NSTAT;
+    if ((size_t)2 * chunk * per_event * sizeof(double) > h->crows_cap) {
+        cudaFree(h->d_crows); h->d_crows = nullptr; h->crows_cap = 0;
+        CK(cudaMalloc(&h->d_crows, (size_t)2 * chunk * per_event * sizeof(double)));
+        h->crows_cap = (size_t)2 * chunk * per_event * sizeof(double);
+    }
+    const unsigned char* sp = static_cast<const unsigned char*>(wf_pre);
+    const unsigned char* sw = static_cast<const unsigned char*>(wf_wdw);
+    int c = 0;
+    for (int64_t e0 = 0; e0 < n_events; e0 += chunk, ++c) {
+        const int b = c & 1;
+        const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
+        if (c >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
+        CK(cudaMemcpy2DAsync(h->d_cin[b][0], (size_t)np * sbp, sp + (size_t)e0 * ld_pre * sbp, (size_t)ld_pre * sbp, (size_t)np * sbp,
+                             (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
+        CK(cudaMemcpy2DAsync(h->d_cin[b][1], (size_t)nw * sbw, sw + (size_t)e0 * ld_wdw * sbw, (size_t)ld_wdw * sbw, (size_t)nw * sbw,
+                             (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
+        CK(cudaEventRecord(h->ev_ready[b], h->s_copy));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
+        double* d_rp = h->d_crows + (size_t)b * chunk * per_event;
+        double* d_rw = d_rp + (size_t)chunk * LGDSP_NCOL;
+        double* d_st = d_rw + (size_t)chunk * LGDSP_NCOL;
+        compressed_launch(h, h->d_cin[b][0], pre_sample_bytes, np, h->d_cin[b][1], wdw_sample_bytes, nw, presum_rate, ne, d_rp, d_rw, d_st);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->ev_free[b], h->stream));
+        CK(cudaMemcpyAsync(rows_pre + e0 * LGDSP_NCOL, d_rp, (size_t)ne * LGDSP_NCOL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(rows_wdw + e0 * LGDSP_NCOL, d_rw, (size_t)ne * LGDSP_NCOL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(stats + e0 * 5 * LGDSP_NSTAT, d_st, (size_t)ne * 5 * LGDSP_NSTAT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->s_copy));
     CK(cudaStreamSynchronize(h->stream));

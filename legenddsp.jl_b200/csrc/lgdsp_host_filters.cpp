@@ -7,6 +7,7 @@
 // the oracle uses normal equations + Gauss-Jordan.  tests/test_builders.py checks they agree to 1e-12.
 #include <cmath>
 #include <cstdint>
+#include <utility>
 #include <vector>
 #include "../../include/lgdsp_b200.h"
 
@@ -140,8 +141,40 @@ int lgdsp_lsq_fit_matrix(int32_t n, int32_t degree, double* A)
 int lgdsp_sg_coeffs(int32_t n_taps, int32_t degree, int32_t derivative, double* h)
 {
     if (!h || n_taps < 1 || (n_taps & 1) == 0 || n_taps > 4095 || degree < 0 || degree > 7 || derivative < 0 ||
-        derivative > degree || n_taps <= degree)
+        derivative > degree)
         return LGDSP_ERR_INVALID_ARG;
+    if (n_taps <= degree) {
+        // fewer points than polynomial coefficients (dsp_icpc_compressed's in-trace filter with the example config:
+        // 3 taps, degree 3, /root/reference/src/dsp_icpc.jl:439): minimum-norm solution of the underdetermined fit,
+        // c = V^T (V V^T)^-1 y with V[k][p] = x_k^p, so h = derivative! * (V V^T)^-1 V[:, derivative]  (policy, unpinned)
+        const int n = n_taps, m = degree + 1;
+        long double G[8][9];
+        for (int i = 0; i < n; ++i) {
+            const long double xi = (long double)(i - n / 2);
+            for (int k = 0; k < n; ++k) {
+                const long double xk = (long double)(k - n / 2);
+                long double g = 0;
+                for (int p = 0; p < m; ++p) g += powl(xi, p) * powl(xk, p);
+                G[i][k] = g;
+            }
+            G[i][n] = powl(xi, derivative);
+        }
+        for (int c = 0; c < n; ++c) {   // Gauss-Jordan with partial pivoting
+            int piv = c;
+            for (int r = c + 1; r < n; ++r) if (fabsl(G[r][c]) > fabsl(G[piv][c])) piv = r;
+            if (G[piv][c] == 0.0L) return LGDSP_ERR_INVALID_ARG;
+            if (piv != c) for (int k = 0; k <= n; ++k) std::swap(G[piv][k], G[c][k]);
+            for (int r = 0; r < n; ++r) {
+                if (r == c) continue;
+                const long double f = G[r][c] / G[c][c];
+                for (int k = c; k <= n; ++k) G[r][k] -= f * G[c][k];
+            }
+        }
+        long double fact = 1.0L;
+        for (int k = 2; k <= derivative; ++k) fact *= k;
+        for (int i = 0; i < n; ++i) h[i] = (double)(fact * G[i][n] / G[i][i]);
+        return LGDSP_OK;
+    }
     std::vector<long double> Ac;
     fit_matrix_centered(n_taps, degree, (long double)(n_taps / 2), Ac);
     long double fact = 1.0L;

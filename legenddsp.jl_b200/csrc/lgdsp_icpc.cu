@@ -834,12 +834,16 @@ __device__ __noinline__ unsigned long long mask_chunk(const double* tp, double t
     return m;
 }
 
+// SAMPLE = uint16_t (raw FADC samples) or uint32_t (presummed waveforms of dsp_icpc_compressed, n <= 4096).
+// bl_ext != NULL: the baseline mean of event e is bl_ext[e] instead of the bl_window mean (windowed waveforms of
+// dsp_icpc_compressed are shifted by blmean_presummed / presum_rate, src/dsp_icpc.jl:350).
+template <typename SAMPLE>
 __global__ void __launch_bounds__(NT, 2)
-icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, long long n_events, long long ld,
-            double* __restrict__ rows)
+icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, long long n_events, long long ld,
+            const double* __restrict__ bl_ext, long long bl_stride, double bl_div, double* __restrict__ rows)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint16_t* xs = reinterpret_cast<uint16_t*>(smem + SM_XS);
+    SAMPLE* xs = reinterpret_cast<SAMPLE*>(smem + SM_XS);
     double* TT = reinterpret_cast<double*>(smem + SM_TT);
     uint32_t* masks = reinterpret_cast<uint32_t*>(smem + SM_MASK);
     double* red = reinterpret_cast<double*>(smem + SM_RED);
@@ -854,7 +858,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = P.n;
-    const uint32_t wf_bytes = (uint32_t)n * 2u;
+    const uint32_t wf_bytes = (uint32_t)n * (uint32_t)sizeof(SAMPLE);
     const double t_first = P.t_first, dt = P.dt;
     const unsigned G = P.groups;
     const double* A_int = P.dni_A;                       // global, L1/L2 resident (4 KB)
@@ -916,8 +920,8 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         phase ^= 1;
         LGDSP_PHASE(0);   // wait for the TMA load
         SECT(31);
-        const uint16_t* xp = xs + i0;
-        uint32_t csum = 0, cq = 0, cmn = 0xFFFFu, cmx = 0;
+        const SAMPLE* xp = xs + i0;
+        uint32_t csum = 0, cq = 0, cmn = 0xFFFFFFFFu, cmx = 0;
 #pragma unroll 3
         for (int k = 0; k < cvalid; ++k) {
             const uint32_t x = xp[k];
@@ -937,7 +941,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
                 const uint32_t x = xp[k];
                 blS += x;
                 blSK += x * (uint32_t)k;
-                blSS += (unsigned long long)(x * x);   // 65535^2 < 2^32
+                blSS += (unsigned long long)x * (unsigned long long)x;
             }
             double a = 0.0, b = 0.0, c = 0.0;
             if (__any_sync(FULL, ka <= kb)) {
@@ -1065,7 +1069,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const uint16_t* __restrict__ wf, 
         }
 
         // blmean = mean_Y = sum_Y * inv_n exactly as signalstats computes it (the other baseline statistics: P5)
-        const double m = mul_rn(red_sum(red, R_BLS), P.bl_inv_n);
+        const double m = bl_ext ? div_rn(bl_ext[e * bl_stride], bl_div) : mul_rn(red_sum(red, R_BLS), P.bl_inv_n);
         const double e_max = (double)mx - m, e_min = (double)mn - m;
         double thr[5];
 #pragma unroll
@@ -2242,17 +2246,101 @@ void sweep_launch(const SweepDev& P, const uint16_t* d_wf, long long n_events, l
     sweep_kernel<<<grid, NT, SW_TOTAL, stream>>>(P, d_wf, n_events, ld, d_out, d_aux);
 }
 
-void icpc_launch(const IcpcDev& P, const uint16_t* d_wf, long long n_events, long long ld, double* d_rows, int grid,
-                 cudaStream_t stream)
+void icpc_launch(const IcpcDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld, const double* d_bl_ext,
+                 long long bl_stride, double bl_div,
+                 double* d_rows, int grid, cudaStream_t stream)
 {
-    icpc_kernel<<<grid, NT, SM_TOTAL, stream>>>(P, d_wf, n_events, ld, d_rows);
+    if (sample_bytes == 4)
+        icpc_kernel<uint32_t><<<grid, NT, SM_TOTAL, stream>>>(P, static_cast<const uint32_t*>(d_wf), n_events, ld, d_bl_ext, bl_stride, bl_div, d_rows);
+    else
+        icpc_kernel<uint16_t><<<grid, NT, SM_TOTAL, stream>>>(P, static_cast<const uint16_t*>(d_wf), n_events, ld, d_bl_ext, bl_stride, bl_div, d_rows);
+}
+
+// ==================================================================================================
+// signalstats on arbitrary windows of raw (optionally shifted) waveforms: the auxiliary baseline / pole-zero windows
+// of dsp_icpc_compressed (/root/reference/src/dsp_icpc.jl:338-339, 365-366).  One warp per (event, window); the sums
+// over the integer samples are exact (int64), the shift enters in closed form.
+// out[(e * n_windows + w) * 5 + {0..4}] = mean, sigma, slope, offset, slope_residual_sigma
+// ==================================================================================================
+template <typename SAMPLE>
+__global__ void window_stats_kernel(const SAMPLE* __restrict__ wf, long long n_events, long long ld, double t_first, double dt,
+                                    const double* __restrict__ shift, long long shift_stride, unsigned shift_mask,
+                                    const int* __restrict__ win /* [n_windows][2] */, int n_windows, double* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= n_events * n_windows) return;
+    const long long e = item / n_windows;
+    const int w = (int)(item - e * n_windows);
+    const int from = win[2 * w], until = win[2 * w + 1];
+    const SAMPLE* x = wf + e * ld;
+    // integer part of the shift is taken out exactly (int64 sums of x - c0), the fractional rest in closed form
+    const bool shifted = shift != nullptr && ((shift_mask >> w) & 1u);
+    const double c = shifted ? shift[e * shift_stride] : 0.0;
+    const long long c0 = shifted ? __double2ll_rn(c) : 0ll;
+    // exact in int64: samples are < 2^20 after presumming (16-bit ADC x presum rate <= 16) and a window holds < 2^13
+    // samples, so sum v < 2^33, sum v^2 < 2^53, sum k v < 2^46
+    long long sY = 0, sYY = 0, sKY = 0;
+    for (int i = from + lane; i <= until; i += 32) {
+        const long long v = (long long)x[i] - c0;
+        sY += v;
+        sYY += v * v;
+        sKY += v * (long long)(i - from);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sY += __shfl_xor_sync(FULL, sY, o);
+        sYY += __shfl_xor_sync(FULL, sYY, o);
+        sKY += __shfl_xor_sync(FULL, sKY, o);
+    }
+    if (lane == 0) {
+        // statistics of y = v - d (d = c - c0, |d| <= 1/2): sum y = sY - n d, sum y^2 = sYY - 2 d sY + n d^2,
+        // sum X y with X_i = t_first + i dt
+        const double d = c - (double)c0;
+        const double nn = (double)(until - from + 1);
+        const double Sy = (double)sY - nn * d;
+        const double Syy = (double)sYY - 2.0 * d * (double)sY + nn * d * d;
+        const double Sk = 0.5 * nn * (nn - 1.0);                       // sum of (i - from)
+        const double Skk = (nn - 1.0) * nn * (2.0 * nn - 1.0) / 6.0;   // sum of (i - from)^2
+        const double Sky = (double)sKY - d * Sk;
+        const double x0 = t_first + (double)from * dt;
+        const double sX = nn * x0 + dt * Sk;
+        const double sXX = nn * x0 * x0 + 2.0 * x0 * dt * Sk + dt * dt * Skk;
+        const double sXY = x0 * Sy + dt * Sky;
+        const double inv_n = 1.0 / nn;
+        const Stats st = stats_finalize(inv_n, sX, sXX, Sy, Syy, sXY);
+        // residual sigma of the straight-line fit (population): var_res = var_Y - slope * cov_XY, clamped at 0
+        const double mX = sX * inv_n, mY = Sy * inv_n;
+        const double var_Y = Syy * inv_n - mY * mY, cov = sXY * inv_n - mX * mY;
+        const double var_r = fmax(var_Y - st.slope * cov, 0.0);
+        double* o = out + item * 5;
+        o[0] = st.mean; o[1] = st.sigma; o[2] = st.slope; o[3] = st.offset; o[4] = sqrt(var_r);
+    }
+}
+
+void window_stats_launch(const void* d_wf, int sample_bytes, long long n_events, long long ld, double t_first, double dt,
+                         const double* d_shift, long long shift_stride, unsigned shift_mask, const int* d_win, int n_windows,
+                         double* d_out, cudaStream_t stream)
+{
+    const long long items = n_events * n_windows;
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((items + wpb - 1) / wpb);
+    if (grid == 0) return;
+    if (sample_bytes == 4)
+        window_stats_kernel<uint32_t><<<grid, wpb * 32, 0, stream>>>(static_cast<const uint32_t*>(d_wf), n_events, ld, t_first, dt,
+                                                                      d_shift, shift_stride, shift_mask, d_win, n_windows, d_out);
+    else
+        window_stats_kernel<uint16_t><<<grid, wpb * 32, 0, stream>>>(static_cast<const uint16_t*>(d_wf), n_events, ld, t_first, dt,
+                                                                      d_shift, shift_stride, shift_mask, d_win, n_windows, d_out);
 }
 
 cudaError_t icpc_configure(int* max_blocks_per_sm)
 {
-    cudaError_t err = cudaFuncSetAttribute(icpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    cudaError_t err = cudaFuncSetAttribute(icpc_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     if (err != cudaSuccess) return err;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, icpc_kernel, NT, SM_TOTAL);
+    err = cudaFuncSetAttribute(icpc_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, icpc_kernel<uint16_t>, NT, SM_TOTAL);
 }
 
 }  // namespace lgdsp

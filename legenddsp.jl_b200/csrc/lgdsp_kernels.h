@@ -10,8 +10,13 @@ namespace lgdsp {
 int icpc_smem_bytes();
 int icpc_threads();
 cudaError_t icpc_configure(int* max_blocks_per_sm);
-void icpc_launch(const IcpcDev& P, const uint16_t* d_wf, long long n_events, long long ld, double* d_rows, int grid,
-                 cudaStream_t stream);
+// d_bl_ext != NULL: event e is shifted by -(d_bl_ext[e * bl_stride] / bl_div) instead of by its own baseline mean
+void icpc_launch(const IcpcDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld, const double* d_bl_ext,
+                 long long bl_stride, double bl_div, double* d_rows, int grid, cudaStream_t stream);
+// window w is shifted by -d_shift[e * shift_stride] when d_shift != NULL and bit w of shift_mask is set
+void window_stats_launch(const void* d_wf, int sample_bytes, long long n_events, long long ld, double t_first, double dt,
+                         const double* d_shift, long long shift_stride, unsigned shift_mask, const int* d_win, int n_windows,
+                         double* d_out, cudaStream_t stream);
 
 // trapezoid sweep kernel
 struct SweepVar {

@@ -15,7 +15,8 @@ import numpy as np
 
 from . import _abi
 from ._lib import Handle
-from .config import DSPConfig, Q, RddspPolicy, DEFAULT_POLICY, ns, resolve_icpc_params
+from .config import (DSPConfig, Q, RddspPolicy, DEFAULT_POLICY, ns, resolve_icpc_params,
+                     resolve_compressed_params)
 
 
 @dataclass
@@ -129,3 +130,113 @@ def dsp_icpc_rows(signal_u16: np.ndarray, params: _abi.IcpcParams, *, device: in
     rows = np.zeros((sig.shape[0], _abi.NCOL), dtype=np.float64)
     h.icpc_run_host(params, sig.ctypes.data, sig.shape[0], sig.strides[0] // 2, rows.ctypes.data)
     return rows
+
+
+# ----------------------------------------------------------------------------------------------
+# dsp_icpc_compressed   (/root/reference/src/dsp_icpc.jl:293-499)
+# ----------------------------------------------------------------------------------------------
+# reference column order :463-499; value = (source, name) with source "pass" (input column), "pre" / "wdw" (row of the
+# fused chain on the presummed / windowed waveform), "stat" ((window, field) of the statistics block)
+_ST = {"mean": 0, "sigma": 1, "slope": 2, "offset": 3, "slope_sigma": 4}
+_WIN = {"auxbl1": 0, "auxbl2": 1, "bl": 2, "auxpz1": 3, "auxpz2": 4}
+
+
+def _aux(win):
+    return [(f"{win}_mean", ("stat", (win, "mean"))), (f"{win}_sigma", ("stat", (win, "sigma"))),
+            (f"{win}_slope_sigma", ("stat", (win, "slope_sigma")))]
+
+
+COMPRESSED_COLUMNS = OrderedDict(
+    [("blfc", ("pass", "baseline")), ("timestamp", ("pass", "timestamp")), ("eventID_fadc", ("pass", "eventnumber")),
+     ("e_fc", ("pass", "daqenergy")), ("deadtime", ("pass", "deadtime")),
+     ("n_sat_low", ("pre", "n_sat_low")), ("n_sat_high", ("pre", "n_sat_high")),
+     ("n_sat_low_cons", ("pre", "n_sat_low_cons")), ("n_sat_high_cons", ("pre", "n_sat_high_cons")),
+     ("t_sat_lo", ("pass", "t_sat_lo")), ("t_sat_hi", ("pass", "t_sat_hi")),
+     ("blmean", ("pre", "blmean")), ("blsigma", ("pre", "blsigma")), ("blslope", ("pre", "blslope")),
+     ("bloffset", ("pre", "bloffset")), ("bl_slope_sigma", ("stat", ("bl", "slope_sigma")))]
+    + _aux("auxbl1") + _aux("auxbl2")
+    + [("qc_label", ("pre", "qc_label")),
+       ("e_max", ("wdw", "e_max")), ("e_min", ("wdw", "e_min")), ("e_max_pre", ("pre", "e_max")), ("e_min_pre", ("pre", "e_min")),
+       ("tailmean", ("pre", "tailmean")), ("tailsigma", ("pre", "tailsigma")), ("tailslope", ("pre", "tailslope")),
+       ("tailoffset", ("pre", "tailoffset")), ("tail_τ", ("pre", "tail_tau")), ("tail_mean", ("pre", "tail_mean")),
+       ("tail_sigma", ("pre", "tail_sigma"))]
+    + _aux("auxpz1") + _aux("auxpz2")
+    + [("t0", ("wdw", "t0")), ("t10", ("wdw", "t10")), ("t50", ("wdw", "t50")), ("t80", ("wdw", "t80")),
+       ("t90", ("wdw", "t90")), ("t99", ("wdw", "t99")), ("t50_pre", ("pre", "t50")),
+       ("drift_time", ("wdw", "drift_time")), ("t50_current", ("pre", "t50_current")),
+       ("e_10410", ("pre", "e_10410")), ("e_535", ("pre", "e_535")), ("e_313", ("pre", "e_313")),
+       ("e_trap", ("pre", "e_trap")), ("e_cusp", ("pre", "e_cusp")), ("e_zac", ("pre", "e_zac")),
+       ("e_trap_max", ("pre", "e_trap_max")), ("e_cusp_max", ("pre", "e_cusp_max")), ("e_zac_max", ("pre", "e_zac_max")),
+       ("t_trap_max", ("pre", "t_trap_max")), ("t_cusp_max", ("pre", "t_cusp_max")), ("t_zac_max", ("pre", "t_zac_max")),
+       ("qdrift", ("wdw", "qdrift")), ("lq", ("wdw", "lq")),
+       ("a_sg", ("wdw", "a_sg")), ("a_60", ("wdw", "a_60")), ("a_100", ("wdw", "a_100")), ("a_raw", ("wdw", "a_raw")),
+       ("inTrace_intersect", ("pre", "inTrace_intersect")), ("inTrace_n", ("pre", "inTrace_n")),
+       ("e_10410_inv", ("pre", "e_10410_inv")), ("e_313_inv", ("pre", "e_313_inv")), ("t0_inv", ("wdw", "t0_inv"))])
+
+
+def _signal_uint(sig) -> np.ndarray:
+    """raw samples as uint16 when they fit, else uint32 (presummed traces: 16-bit ADC x presum rate)"""
+    a = np.asarray(sig)
+    if a.ndim != 2:
+        raise ValueError("waveform signals must be a 2-D array [n_events, n_samples]")
+    if not np.issubdtype(a.dtype, np.integer):
+        raise TypeError("this implementation processes raw integer ADC samples; got dtype %s" % a.dtype)
+    if a.dtype not in (np.uint16, np.uint32):
+        if a.size and a.min() < 0:
+            raise ValueError("negative samples")
+        if a.size and a.max() > 0xFFFFFFFF:
+            raise ValueError("samples outside the UInt32 range")
+        a = a.astype(np.uint16 if (a.size == 0 or a.max() <= 65535) else np.uint32)
+    if a.strides[1] != a.dtype.itemsize:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def compressed_to_table(rows_pre: np.ndarray, rows_wdw: np.ndarray, stats: np.ndarray,
+                        data: Optional[Mapping[str, Any]] = None) -> "OrderedDict[str, np.ndarray]":
+    """assemble the reference's result table (:463-499) from the two row blocks and the statistics block"""
+    out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    for name, (src, key) in COMPRESSED_COLUMNS.items():
+        if src == "pass":
+            if data is not None and key in data:
+                out[name] = np.asarray(data[key])
+            continue
+        if src == "stat":
+            out[name] = np.ascontiguousarray(stats[:, _WIN[key[0]], _ST[key[1]]])
+            continue
+        col = (rows_pre if src == "pre" else rows_wdw)[:, _abi.COL[key]]
+        out[name] = col.astype(np.int64) if key in _abi.INT_COLUMNS else np.ascontiguousarray(col)
+    return out
+
+
+def dsp_icpc_compressed(data: Mapping[str, Any], config: DSPConfig, τ: Q, pars_filter: Optional[Dict[str, Any]] = None, *,
+                        f_evaluate_qc=None, device: int = 0, handle: Optional[Handle] = None,
+                        policy: RddspPolicy = DEFAULT_POLICY, builders=None) -> "OrderedDict[str, np.ndarray]":
+    """DSP routine for ICPC detectors on the compressed format: the reference's
+    `dsp_icpc_compressed(data, config, τ, pars_filter)` (src/dsp_icpc.jl:293-499).
+
+    `data` needs `waveform_presummed`, `waveform_windowed` (RDWaveforms of raw integer samples, each with its own time
+    axis) and `presum_rate` (one value for all events, `only(unique(presum_rate))` :324); the pass-through columns
+    `baseline, timestamp, eventnumber, daqenergy, t_sat_lo, t_sat_hi, deadtime` are copied when present."""
+    if f_evaluate_qc is not None:
+        raise NotImplementedError("f_evaluate_qc is not supported; qc_label is -1 as in the reference without a model")
+    wp, ww = _as_waveforms(data["waveform_presummed"]), _as_waveforms(data["waveform_windowed"])
+    pre, wdw = _signal_uint(wp.signal), _signal_uint(ww.signal)
+    if pre.shape[0] != wdw.shape[0]:
+        raise ValueError("waveform_presummed and waveform_windowed differ in length")
+    rates = np.unique(np.asarray(data["presum_rate"]))
+    if rates.size != 1:                                           # only(unique(presum_rate))  :324
+        raise ValueError("presum_rate must be the same for all events")
+    presum = int(rates[0])
+    n_events = pre.shape[0]
+    P_pre, P_wdw, aux = resolve_compressed_params(config, τ, pars_filter, presum_rate=presum, n_pre=pre.shape[1],
+                                                  t_first_pre=wp.t_first, step_pre=wp.step, n_wdw=wdw.shape[1],
+                                                  t_first_wdw=ww.t_first, step_wdw=ww.step, policy=policy, builders=builders)
+    h = handle or get_handle(device)
+    rows_pre = np.zeros((n_events, _abi.NCOL), dtype=np.float64)
+    rows_wdw = np.zeros((n_events, _abi.NCOL), dtype=np.float64)
+    stats = np.zeros((n_events, 5, 5), dtype=np.float64)
+    h.icpc_compressed_run_host(P_pre, P_wdw, pre.ctypes.data, pre.dtype.itemsize, pre.strides[0] // pre.dtype.itemsize,
+                               wdw.ctypes.data, wdw.dtype.itemsize, wdw.strides[0] // wdw.dtype.itemsize, float(presum), aux,
+                               n_events, rows_pre.ctypes.data, rows_wdw.ctypes.data, stats.ctypes.data)
+    return compressed_to_table(rows_pre, rows_wdw, stats, data)

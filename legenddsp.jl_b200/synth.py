@@ -28,3 +28,19 @@ def generate_device(handle, d_ptr, n_events, first_event=0, ld=None, **kw):
     sp = synth_params(**kw)
     handle.synth_device(sp, first_event, n_events, ld or sp.n_samples, d_ptr)
     return sp
+
+
+def compress(wf_u16: np.ndarray, presum_rate: int = 8, window=(2600, 1400)):
+    """the DAQ's compressed format from full-rate traces: (presummed, windowed) where presummed[e, k] is the sum of
+    `presum_rate` consecutive samples (uint32 when the sums exceed 16 bits; length n // presum_rate) and windowed is
+    the full-rate slice [from, from + length) (what dsp_icpc_compressed reads as waveform_presummed /
+    waveform_windowed, /root/reference/src/dsp_icpc.jl:313-314).  Input generation only."""
+    wf = np.asarray(wf_u16)
+    n_ev, n = wf.shape
+    r = int(presum_rate)
+    m = n // r
+    pre = wf[:, :m * r].astype(np.uint32).reshape(n_ev, m, r).sum(axis=2, dtype=np.uint64)
+    pre = pre.astype(np.uint16 if (pre.size == 0 or pre.max() <= 65535) else np.uint32)
+    a, length = int(window[0]), int(window[1])
+    wdw = np.ascontiguousarray(wf[:, a:a + length])
+    return pre, wdw

@@ -92,8 +92,28 @@ ORC_API int orc_lsq_fit_matrix(int n, int degree, double* A) { return lsq_fit_ma
  * per-sample units.  s[j] = sum_k h[k] y[j+k]. */
 ORC_API int orc_sg_coeffs(int n_taps, int degree, int derivative, double* h)
 {
-    if (n_taps < 1 || (n_taps & 1) == 0 || derivative > degree || n_taps <= degree) return -1;
+    if (n_taps < 1 || (n_taps & 1) == 0 || derivative > degree || degree > 7) return -1;
     int m = degree + 1;
+    if (n_taps <= degree) {
+        /* underdetermined fit (3 taps / degree 3: the in-trace filter of dsp_icpc_compressed with the example config,
+         * src/dsp_icpc.jl:439): minimum-norm coefficients, h = derivative! * (V V^T)^-1 V[:, derivative], V[k][p] = x_k^p
+         * (what a pseudo-inverse / QR least-squares solve returns; parity unpinned) */
+        double G[64], b[8];
+        for (int i = 0; i < n_taps; ++i) {
+            double xi = i - n_taps / 2;
+            for (int k = 0; k < n_taps; ++k) {
+                double xk = k - n_taps / 2, g = 0;
+                for (int q = 0; q < m; ++q) g += pow(xi, q) * pow(xk, q);
+                G[i * n_taps + k] = g;
+            }
+            b[i] = pow(xi, derivative);
+        }
+        if (solve_spd_small(n_taps, G, b, 1) != 0) return -1;
+        double fact = 1.0;
+        for (int k = 2; k <= derivative; ++k) fact *= k;
+        for (int i = 0; i < n_taps; ++i) h[i] = fact * b[i];
+        return 0;
+    }
     double* A = (double*)malloc(sizeof(double) * (size_t)n_taps * m);
     if (lsq_fit_matrix_x0(n_taps, degree, -(double)(n_taps / 2), A) != 0) { free(A); return -1; }
     double fact = 1.0;
@@ -649,6 +669,281 @@ ORC_API int orc_dsp_icpc(const lgdsp_icpc_params* P, const uint16_t* wf, int64_t
 #endif
         for (int64_t e = 0; e < n_events; ++e)
             dsp_icpc_one(P, wf + e * ld, out_rows + e * LGDSP_NCOL, idx ? idx + e * ORC_NIDX : NULL, ws);
+        free(ws);
+    }
+    return used;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * dsp_icpc_compressed  src/dsp_icpc.jl:293-499, one event.
+ * Two waveforms per event: the presummed one (`pre`, energy and tail quantities; step = presum_rate * ADC step) and
+ * the windowed one (`wdw`, timing, currents, Q-drift; full sampling rate).  Pp / Pw hold the sample-domain constants of
+ * the two time axes (the fields each step uses are named in the comments).  aux: the four auxiliary windows on the
+ * presummed axis (auxbl1, auxbl2 on the raw trace :338-339; auxpz1, auxpz2 on the baseline-subtracted one :365-366).
+ * signalstats' slope_residual_sigma (:468 ...) is not defined in the reference tree [RDDSP]: restated as the
+ * population sigma of the residuals of the straight-line fit -- parity unpinned.
+ * Output: the computed columns of the result table :463-499 in the order of orc_compressed_columns().
+ * ------------------------------------------------------------------------------------------------ */
+#define ORC_CCOLS \
+    X(n_sat_low) X(n_sat_high) X(n_sat_low_cons) X(n_sat_high_cons) \
+    X(blmean) X(blsigma) X(blslope) X(bloffset) X(bl_slope_sigma) \
+    X(auxbl1_mean) X(auxbl1_sigma) X(auxbl1_slope_sigma) X(auxbl2_mean) X(auxbl2_sigma) X(auxbl2_slope_sigma) \
+    X(qc_label) X(e_max) X(e_min) X(e_max_pre) X(e_min_pre) \
+    X(tailmean) X(tailsigma) X(tailslope) X(tailoffset) X(tail_tau) X(tail_mean) X(tail_sigma) \
+    X(auxpz1_mean) X(auxpz1_sigma) X(auxpz1_slope_sigma) X(auxpz2_mean) X(auxpz2_sigma) X(auxpz2_slope_sigma) \
+    X(t0) X(t10) X(t50) X(t80) X(t90) X(t99) X(t50_pre) X(drift_time) X(t50_current) \
+    X(e_10410) X(e_535) X(e_313) X(e_trap) X(e_cusp) X(e_zac) X(e_trap_max) X(e_cusp_max) X(e_zac_max) \
+    X(t_trap_max) X(t_cusp_max) X(t_zac_max) X(qdrift) X(lq) X(a_sg) X(a_60) X(a_100) X(a_raw) \
+    X(inTrace_intersect) X(inTrace_n) X(e_10410_inv) X(e_313_inv) X(t0_inv)
+enum {
+#define X(name) CC_##name,
+    ORC_CCOLS
+#undef X
+    ORC_NCCOL
+};
+ORC_API const char* orc_compressed_columns(void)
+{
+    return ""
+#define X(name) #name ","
+        ORC_CCOLS
+#undef X
+        ;
+}
+ORC_API int orc_compressed_ncol(void) { return ORC_NCCOL; }
+
+/* signalstats with the residual sigma of the fit as fifth value */
+ORC_API void orc_signalstats5(const double* Y, double t0, double dt, int from, int until, double out[5])
+{
+    orc_signalstats(Y, t0, dt, from, until, out);
+    double slope = out[2], offset = out[3], acc = 0;
+    int n = until - from + 1;
+    for (int i = from; i <= until; ++i) {
+        double r = Y[i] - (offset + slope * (t0 + i * dt));
+        acc += r * r;
+    }
+    out[4] = sqrt(acc / n);
+}
+
+static double sample_at(const void* raw, int bytes, int i)
+{
+    return bytes == 4 ? (double)((const uint32_t*)raw)[i] : (double)((const uint16_t*)raw)[i];
+}
+
+static double trace_max(const double* y, int n)
+{
+    double m = y[0];
+    for (int i = 1; i < n; ++i) if (y[i] > m) m = y[i];
+    return m;
+}
+
+static void dsp_icpc_compressed_one(const lgdsp_icpc_params* Pp, const lgdsp_icpc_params* Pw, const void* pre, int pre_bytes,
+                                    const void* wdw, int wdw_bytes, double presum_rate, const int32_t aux[8], double* row,
+                                    double* ws)
+{
+    const int np = Pp->n_samples, nw = Pw->n_samples;
+    const int nmax = np > nw ? np : nw;
+    const double tp = Pp->t_first_ns, dp = Pp->dt_ns, tw = Pw->t_first_ns, dw = Pw->dt_ns;
+    double* wp = ws;                 /* presummed waveform */
+    double* ww = ws + nmax;          /* windowed waveform */
+    double* flt = ws + 2 * nmax;
+    double* flt2 = ws + 3 * nmax;
+    int pos;
+    for (int i = 0; i < ORC_NCCOL; ++i) row[i] = 0.0;
+
+    /* :332-335 saturation on the presummed samples; sat_high = (2^bit_depth - bit_depth) * presum_rate (host) */
+    {
+        int64_t n_low = 0, n_high = 0, cons_low = 0, cons_high = 0, c_low = 0, c_high = 0;
+        for (int i = 0; i < np; ++i) {        /* src/saturation.jl:28-65 on the wide samples */
+            int64_t v = (int64_t)sample_at(pre, pre_bytes, i);
+            if (v == Pp->sat_low) {
+                n_low++; c_low++;
+                if (c_high > cons_high) cons_high = c_high;
+                c_high = 0;
+            } else if (v == Pp->sat_high) {
+                n_high++; c_high++;
+                if (c_low > cons_low) cons_low = c_low;
+                c_low = 0;
+            } else {
+                if (c_low > cons_low) cons_low = c_low;
+                c_low = 0;
+                if (c_high > cons_high) cons_high = c_high;
+                c_high = 0;
+            }
+        }
+        if (c_low > cons_low) cons_low = c_low;
+        if (c_high > cons_high) cons_high = c_high;
+        row[CC_n_sat_low] = (double)n_low; row[CC_n_sat_high] = (double)n_high;
+        row[CC_n_sat_low_cons] = (double)cons_low; row[CC_n_sat_high_cons] = (double)cons_high;
+    }
+    for (int i = 0; i < np; ++i) wp[i] = sample_at(pre, pre_bytes, i);
+    for (int i = 0; i < nw; ++i) ww[i] = sample_at(wdw, wdw_bytes, i);
+
+    /* :338-339 auxiliary baselines on the raw presummed waveform */
+    double st[5];
+    orc_signalstats5(wp, tp, dp, aux[0], aux[1], st);
+    row[CC_auxbl1_mean] = st[0]; row[CC_auxbl1_sigma] = st[1]; row[CC_auxbl1_slope_sigma] = st[4];
+    orc_signalstats5(wp, tp, dp, aux[2], aux[3], st);
+    row[CC_auxbl2_mean] = st[0]; row[CC_auxbl2_sigma] = st[1]; row[CC_auxbl2_slope_sigma] = st[4];
+
+    /* :346 baseline */
+    double bl[5];
+    orc_signalstats5(wp, tp, dp, Pp->bl_from, Pp->bl_until, bl);
+    row[CC_blmean] = bl[0]; row[CC_blsigma] = bl[1]; row[CC_blslope] = bl[2]; row[CC_bloffset] = bl[3];
+    row[CC_bl_slope_sigma] = bl[4];
+
+    /* :349-350 */
+    {
+        double s_pre = -bl[0], s_wdw = -bl[0] / presum_rate;
+        for (int i = 0; i < np; ++i) wp[i] = wp[i] + s_pre;
+        for (int i = 0; i < nw; ++i) ww[i] = ww[i] + s_wdw;
+    }
+    /* :353 */
+    row[CC_qc_label] = -1.0;
+
+    /* :356-360 */
+    double max_pre = wp[0], min_pre = wp[0], max_wdw = ww[0], min_wdw = ww[0];
+    for (int i = 1; i < np; ++i) { if (wp[i] > max_pre) max_pre = wp[i]; if (wp[i] < min_pre) min_pre = wp[i]; }
+    for (int i = 1; i < nw; ++i) { if (ww[i] > max_wdw) max_wdw = ww[i]; if (ww[i] < min_wdw) min_wdw = ww[i]; }
+    row[CC_e_max] = max_wdw; row[CC_e_min] = min_wdw; row[CC_e_max_pre] = max_pre; row[CC_e_min_pre] = min_pre;
+
+    /* :363 */
+    double ts[3];
+    orc_tailstats(wp, tp, dp, Pp->tail_from, Pp->tail_until, ts);
+    row[CC_tail_mean] = ts[0]; row[CC_tail_sigma] = ts[1]; row[CC_tail_tau] = ts[2];
+
+    /* :365-366 auxiliary pole-zero windows (baseline-subtracted, before the deconvolution) */
+    orc_signalstats5(wp, tp, dp, aux[4], aux[5], st);
+    row[CC_auxpz1_mean] = st[0]; row[CC_auxpz1_sigma] = st[1]; row[CC_auxpz1_slope_sigma] = st[4];
+    orc_signalstats5(wp, tp, dp, aux[6], aux[7], st);
+    row[CC_auxpz2_mean] = st[0]; row[CC_auxpz2_sigma] = st[1]; row[CC_auxpz2_slope_sigma] = st[4];
+
+    /* :370-372 InvCRFilter(tau) on both (RC = tau / step of each axis) */
+    orc_invcr(wp, np, Pp->pz_km1, flt); memcpy(wp, flt, sizeof(double) * (size_t)np);
+    orc_invcr(ww, nw, Pw->pz_km1, flt); memcpy(ww, flt, sizeof(double) * (size_t)nw);
+
+    /* :375 */
+    double pz[4];
+    orc_signalstats(wp, tp, dp, Pp->tail_from, Pp->tail_until, pz);
+    row[CC_tailmean] = pz[0]; row[CC_tailsigma] = pz[1]; row[CC_tailslope] = pz[2]; row[CC_tailoffset] = pz[3];
+
+    /* :378 */
+    double t0 = orc_get_t0(ww, nw, tw, dw, &Pw->t0_trap, Pw->t0_threshold, Pw->t0_min_n, flt, &pos);
+    row[CC_t0] = t0;
+
+    /* :381-386 */
+    double t10 = orc_get_threshold(ww, nw, tw, dw, max_wdw * 0.1, Pw->tx_min_n, &pos);
+    double t50 = orc_get_threshold(ww, nw, tw, dw, max_wdw * 0.5, Pw->tx_min_n, &pos);
+    double t50_pre = orc_get_threshold(wp, np, tp, dp, max_pre * 0.5, Pp->tx_min_n, &pos);
+    double t80 = orc_get_threshold(ww, nw, tw, dw, max_wdw * 0.8, Pw->tx_min_n, &pos);
+    double t90 = orc_get_threshold(ww, nw, tw, dw, max_wdw * 0.9, Pw->tx_min_n, &pos);
+    double t99 = orc_get_threshold(ww, nw, tw, dw, max_wdw * 0.99, Pw->tx_min_n, &pos);
+    row[CC_t10] = t10; row[CC_t50] = t50; row[CC_t80] = t80; row[CC_t90] = t90; row[CC_t99] = t99;
+    row[CC_t50_pre] = t50_pre;
+
+    /* :388 */
+    row[CC_drift_time] = (t90 - t0) * 1000.0;
+
+    /* :391, :394 */
+    orc_integrator(ww, nw, 1.0, flt);
+    row[CC_qdrift] = orc_get_qdrift(flt, nw, tw, dw, &Pw->int_dni, t0, Pw->qdrift_first_ns, Pw->qdrift_last_ns);
+    row[CC_lq] = orc_get_qdrift(flt, nw, tw, dw, &Pw->int_dni, t80, Pw->lq_first_ns, Pw->lq_last_ns);
+
+    /* :397-404 */
+    {
+        int no = orc_trap(wp, np, Pp->trap_10410.navg, Pp->trap_10410.ngap, Pp->trap_10410.navg2, flt);
+        row[CC_e_10410] = trace_max(flt, no);
+        no = orc_trap(wp, np, Pp->trap_535.navg, Pp->trap_535.ngap, Pp->trap_535.navg2, flt);
+        row[CC_e_535] = trace_max(flt, no);
+        no = orc_trap(wp, np, Pp->trap_313.navg, Pp->trap_313.ngap, Pp->trap_313.navg2, flt);
+        row[CC_e_313] = trace_max(flt, no);
+    }
+    /* :407-414 */
+    {
+        const lgdsp_trap* tr = &Pp->trap_e;
+        int L = tr->navg + tr->ngap + tr->navg2;
+        int no = orc_trap(wp, np, tr->navg, tr->ngap, tr->navg2, flt);
+        double tf = tp + (L - 1) * dp, es[4];
+        row[CC_e_trap] = orc_dni(&Pp->sig_dni, flt, no, (t50_pre * 1000.0 + Pp->trap_pickoff_ns - tf) / dp);
+        orc_extremestats(flt, tf, dp, 0, no - 1, es);
+        row[CC_e_trap_max] = es[1]; row[CC_t_trap_max] = es[3];
+    }
+    /* :417-421 */
+    {
+        int L = Pp->cusp.n_taps;
+        int no = orc_fir_valid(wp, np, Pp->cusp.coeffs, L, flt);
+        double tf = tp + (L - 1) * dp, es[4];
+        row[CC_e_cusp] = orc_dni(&Pp->sig_dni, flt, no, (t50_pre * 1000.0 + Pp->cusp_pickoff_ns - tf) / dp);
+        orc_extremestats(flt, tf, dp, 0, no - 1, es);
+        row[CC_e_cusp_max] = es[1]; row[CC_t_cusp_max] = es[3];
+    }
+    /* :424-428 */
+    {
+        int L = Pp->zac.n_taps;
+        int no = orc_fir_valid(wp, np, Pp->zac.coeffs, L, flt);
+        double tf = tp + (L - 1) * dp, es[4];
+        row[CC_e_zac] = orc_dni(&Pp->sig_dni, flt, no, (t50_pre * 1000.0 + Pp->zac_pickoff_ns - tf) / dp);
+        orc_extremestats(flt, tf, dp, 0, no - 1, es);
+        row[CC_e_zac_max] = es[1]; row[CC_t_zac_max] = es[3];
+    }
+    /* :431-435 currents on the windowed waveform */
+    orc_derivative(ww, nw, 1.0, flt);
+    row[CC_a_raw] = orc_get_wvf_maximum(flt, Pw->cur_from[3], Pw->cur_until[3]);
+    orc_corr_valid(ww, nw, Pw->sg[0].h, Pw->sg[0].n_taps, flt);
+    row[CC_a_sg] = orc_get_wvf_maximum(flt, Pw->cur_from[0], Pw->cur_until[0]);
+    orc_corr_valid(ww, nw, Pw->sg[1].h, Pw->sg[1].n_taps, flt);
+    row[CC_a_60] = orc_get_wvf_maximum(flt, Pw->cur_from[1], Pw->cur_until[1]);
+    orc_corr_valid(ww, nw, Pw->sg[2].h, Pw->sg[2].n_taps, flt);
+    row[CC_a_100] = orc_get_wvf_maximum(flt, Pw->cur_from[2], Pw->cur_until[2]);
+
+    /* :439-445 in-trace pile-up and current rise on SavitzkyGolayFilter(sg_wl * presum_rate / 2) of the presummed
+     * waveform (Pp->sg[0]) */
+    {
+        int n_sg = orc_corr_valid(wp, np, Pp->sg[0].h, Pp->sg[0].n_taps, flt2);
+        double tf = tp + Pp->sg[0].offset * dp, s4[4];
+        orc_signalstats(flt2, tf, dp, Pp->intrace_bl_from, Pp->intrace_bl_until, s4);   /* src/dsp_routines.jl:75 */
+        double thres = s4[1] * Pp->intrace_nsigma;
+        if (thres == 0.0) thres = 1.0;
+        for (int j = 0; j < n_sg; ++j) flt[j] = flt2[n_sg - 1 - j];
+        int64_t mult;
+        double x = orc_intersect(flt, n_sg, tf, dp, thres, Pp->intrace_min_n, &mult, &pos);
+        row[CC_inTrace_intersect] = (tf + (n_sg - 1) * dp) - x;
+        row[CC_inTrace_n] = (double)mult;
+        row[CC_t50_current] = orc_get_threshold(flt2, n_sg, tf, dp, trace_max(flt2, n_sg) * 0.5, Pp->tx_min_n, &pos);
+    }
+    /* :449-450 */
+    for (int i = 0; i < np; ++i) wp[i] = wp[i] * -1.0;
+    for (int i = 0; i < nw; ++i) ww[i] = ww[i] * -1.0;
+    /* :453-455 */
+    {
+        int no = orc_trap(wp, np, Pp->trap_10410.navg, Pp->trap_10410.ngap, Pp->trap_10410.navg2, flt);
+        row[CC_e_10410_inv] = trace_max(flt, no);
+        no = orc_trap(wp, np, Pp->trap_313.navg, Pp->trap_313.ngap, Pp->trap_313.navg2, flt);
+        row[CC_e_313_inv] = trace_max(flt, no);
+    }
+    /* :458 (default flt_pars) */
+    row[CC_t0_inv] = orc_get_t0(ww, nw, tw, dw, &Pw->t0inv_trap, Pw->t0_threshold, Pw->t0_min_n, flt, &pos);
+}
+
+ORC_API int orc_dsp_icpc_compressed(const lgdsp_icpc_params* Pp, const lgdsp_icpc_params* Pw, const void* pre, int pre_bytes,
+                                    int64_t ld_pre, const void* wdw, int wdw_bytes, int64_t ld_wdw, double presum_rate,
+                                    const int32_t aux[8], int64_t n_events, double* out_rows, int n_threads)
+{
+    int used = 1;
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+    used = n_threads;
+#pragma omp parallel num_threads(n_threads)
+#endif
+    {
+        int nmax = Pp->n_samples > Pw->n_samples ? Pp->n_samples : Pw->n_samples;
+        double* ws = (double*)malloc(sizeof(double) * 4 * (size_t)nmax);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+        for (int64_t e = 0; e < n_events; ++e)
+            dsp_icpc_compressed_one(Pp, Pw, (const char*)pre + (size_t)e * ld_pre * pre_bytes, pre_bytes,
+                                    (const char*)wdw + (size_t)e * ld_wdw * wdw_bytes, wdw_bytes, presum_rate, aux,
+                                    out_rows + e * ORC_NCCOL, ws);
         free(ws);
     }
     return used;

@@ -211,6 +211,46 @@ def dsp_icpc(params, wf_u16, n_threads=0, want_idx=False):
     return (rows, idx, used) if want_idx else (rows, used)
 
 
+def signalstats5(y, t0, dt, frm, until):
+    """signalstats incl. slope_residual_sigma (population sigma of the straight-line fit residuals; parity unpinned)"""
+    y, p = _d(y)
+    out = np.zeros(5)
+    L = lib()
+    L.orc_signalstats5.argtypes = [_dp, C.c_double, C.c_double, C.c_int, C.c_int, _dp]
+    L.orc_signalstats5.restype = None
+    L.orc_signalstats5(p, float(t0), float(dt), int(frm), int(until), out.ctypes.data_as(_dp))
+    return out
+
+
+def compressed_columns():
+    L = lib()
+    L.orc_compressed_columns.restype = C.c_char_p
+    return tuple(c for c in L.orc_compressed_columns().decode().split(",") if c)
+
+
+def dsp_icpc_compressed(p_pre, p_wdw, pre, wdw, presum_rate, aux_windows, n_threads=0):
+    """oracle dsp_icpc_compressed (src/dsp_icpc.jl:293-499): dict column -> float64[n_events] of the computed columns.
+    pre / wdw: uint16 or uint32 arrays [n_events, n_samples]; aux_windows: [(from, until)] x 4 (auxbl1, auxbl2, auxpz1,
+    auxpz2), 0-based inclusive on the presummed axis."""
+    def prep(a):
+        a = np.asarray(a)
+        assert a.ndim == 2 and a.dtype in (np.uint16, np.uint32)
+        return np.ascontiguousarray(a)
+    pre, wdw = prep(pre), prep(wdw)
+    assert pre.shape[0] == wdw.shape[0] and pre.shape[1] >= p_pre.n_samples and wdw.shape[1] >= p_wdw.n_samples
+    cols = compressed_columns()
+    n_ev = pre.shape[0]
+    rows = np.zeros((n_ev, len(cols)))
+    aux = (C.c_int32 * 8)(*[int(v) for ab in aux_windows for v in ab])
+    L = lib()
+    L.orc_dsp_icpc_compressed.argtypes = [C.POINTER(_abi.IcpcParams), C.POINTER(_abi.IcpcParams), C.c_void_p, C.c_int, C.c_int64,
+                                          C.c_void_p, C.c_int, C.c_int64, C.c_double, C.POINTER(C.c_int32), C.c_int64, _dp, C.c_int]
+    L.orc_dsp_icpc_compressed(C.byref(p_pre), C.byref(p_wdw), pre.ctypes.data, pre.dtype.itemsize, pre.shape[1],
+                              wdw.ctypes.data, wdw.dtype.itemsize, wdw.shape[1], float(presum_rate), aux, n_ev,
+                              rows.ctypes.data_as(_dp), int(n_threads))
+    return {c: rows[:, i].copy() for i, c in enumerate(cols)}
+
+
 def trap_sweep(sparams, wf_u16, variants, n_threads=0):
     wf = np.ascontiguousarray(wf_u16, dtype=np.uint16)
     n_ev, ld = wf.shape

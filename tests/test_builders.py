@@ -41,6 +41,21 @@ def test_builder_argument_errors(L):
     import ctypes as C
     buf = (C.c_double * 16)()
     assert lib.lgdsp_sg_coeffs(4, 3, 1, buf) != 0      # even length
-    assert lib.lgdsp_sg_coeffs(3, 3, 1, buf) != 0      # degree too high for the window
+    assert lib.lgdsp_sg_coeffs(3, 1, 2, buf) != 0      # derivative above the degree
     assert lib.lgdsp_lsq_fit_matrix(3, 3, buf) != 0
     assert lib.lgdsp_cusp_coeffs(-1.0, 2, 1.0, 16, 1.0, buf) != 0
+
+
+def test_sg_underdetermined_minimum_norm(L, O):
+    """3 taps / degree 3 (the in-trace filter of dsp_icpc_compressed with the example config, src/dsp_icpc.jl:439):
+    minimum-norm solution = pseudo-inverse row, in the library and in the oracle"""
+    x = np.arange(-1, 2, dtype=np.float64)
+    V = np.vander(x, 4, increasing=True)
+    ref = np.linalg.pinv(V)[1]
+    assert np.allclose(L.LibBuilders().sg_coeffs(3, 3, 1), ref, atol=1e-14)
+    assert np.allclose(O.OracleBuilders().sg_coeffs(3, 3, 1), ref, atol=1e-14)
+    assert np.allclose(ref, [-0.25, 0.0, 0.25])
+    x = np.arange(-2, 3, dtype=np.float64)
+    ref5 = np.linalg.pinv(np.vander(x, 7, increasing=True))[1]
+    assert np.allclose(L.LibBuilders().sg_coeffs(5, 6, 1), ref5, atol=1e-12)
+    assert np.allclose(O.OracleBuilders().sg_coeffs(5, 6, 1), ref5, atol=1e-12)
