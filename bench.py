@@ -97,13 +97,26 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+PRESUM, WDW_FROM, WDW_N = 8, 2600, 1400   # the compressed workload: 1024 presummed uint32 + 1400 windowed uint16 samples
+
+
+def compressed_setup(L, cfg, tau, builders=None):
+    return L.resolve_compressed_params(cfg, tau, None, presum_rate=PRESUM, n_pre=8192 // PRESUM, step_pre=L.ns(16.0 * PRESUM),
+                                       n_wdw=WDW_N, t_first_wdw=L.ns(16.0 * WDW_FROM), step_wdw=L.ns(16.0), builders=builders)
+
+
 def cpu_port_throughput(L, O, P, n_events, workload, variants=None, sparams=None, reps=1, threads=0):
     """the CPU port of the reference algorithm (oracle/) on all host cores: waveforms/s"""
     wf = L.synth.generate_host(n_events, first_event=10_000_000)
+    if workload == "compressed":
+        pre, wdw = L.synth.compress(wf, PRESUM, (WDW_FROM, WDW_N))
+        Pp, Pw, aux = P
     best = None
     for _ in range(reps):
         t0 = time.perf_counter()
-        if workload == "trap_sweep":
+        if workload == "compressed":
+            O.dsp_icpc_compressed(Pp, Pw, pre, wdw, PRESUM, aux, n_threads=threads)
+        elif workload == "trap_sweep":
             O.trap_sweep(sparams, wf, variants, n_threads=threads)
         else:
             O.dsp_icpc(P, wf, n_threads=threads)
@@ -118,7 +131,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dsp_icpc", choices=["dsp_icpc", "pz_trap", "trap_sweep"])
+    ap.add_argument("--workload", default="dsp_icpc", choices=["dsp_icpc", "pz_trap", "trap_sweep", "compressed"])
     ap.add_argument("--batch", type=int, default=131072, help="waveforms per step per GPU (131072 = 2.1 GB >> L2)")
     ap.add_argument("--pool", type=int, default=4, help="distinct resident batches cycled by the steps")
     ap.add_argument("--direct", action="store_true", help="CUSP/ZAC as direct 2375-tap FIRs (validation mode)")
@@ -139,15 +152,18 @@ def main():
 
     cfg = L.tiefree_config()
     tau = L.us(500.0)
-    groups = {"dsp_icpc": L._abi.GROUP_ALL, "pz_trap": L._abi.GROUP_PZTRAP, "trap_sweep": 0}[args.workload]
+    groups = {"dsp_icpc": L._abi.GROUP_ALL, "pz_trap": L._abi.GROUP_PZTRAP, "trap_sweep": 0, "compressed": 0}[args.workload]
     wl_name = {"dsp_icpc": "full dsp_icpc, 49 columns incl. CUSP+ZAC (BASELINE configs[2]/[4])",
                "pz_trap": "pole-zero + trapezoid energies/t0 only (BASELINE configs[1])",
-               "trap_sweep": "20x10 trapezoid (rt, ft) sweep, 200 variants (BASELINE configs[3])"}[args.workload]
+               "trap_sweep": "20x10 trapezoid (rt, ft) sweep, 200 variants (BASELINE configs[3])",
+               "compressed": "dsp_icpc_compressed: 1024 presummed uint32 (x8) + 1400 windowed uint16 samples per event "
+                             "(SURVEY 8f rank 1)"}[args.workload]
     if args.groups is not None:
         groups = int(args.groups, 16)
         wl_name += f" [experimental group mask {groups:#x}]"
-    out_bytes = {"dsp_icpc": NCOL * 8, "pz_trap": 5 * 8, "trap_sweep": 200 * 4}[args.workload]
-    bytes_per_wf = BYTES_IN + out_bytes
+    out_bytes = {"dsp_icpc": NCOL * 8, "pz_trap": 5 * 8, "trap_sweep": 200 * 4, "compressed": 65 * 8}[args.workload]
+    bytes_in = BYTES_IN if args.workload != "compressed" else (8192 // PRESUM) * 4 + WDW_N * 2
+    bytes_per_wf = bytes_in + out_bytes
     variants = sparams = None
     if args.workload == "trap_sweep":
         rts = [L.us(1.0 + 0.75 * i) for i in range(20)]
@@ -168,9 +184,14 @@ def main():
         threads = host_threads()
         n_s = args.cpu_sample or (32 * threads if args.workload != "trap_sweep" else 16 * threads)
         wf = L.synth.generate_host(n_s, first_event=10_000_000)
+        if args.workload == "compressed":
+            Pp, Pw, aux = compressed_setup(L, cfg, tau, O.OracleBuilders())
+            pre, wdw = L.synth.compress(wf, PRESUM, (WDW_FROM, WDW_N))
 
         def step():
-            if args.workload == "trap_sweep":
+            if args.workload == "compressed":
+                O.dsp_icpc_compressed(Pp, Pw, pre, wdw, PRESUM, aux, n_threads=threads)
+            elif args.workload == "trap_sweep":
                 O.trap_sweep(sparams, wf, variants, n_threads=threads)
             else:
                 O.dsp_icpc(P, wf, n_threads=threads)
@@ -213,6 +234,8 @@ def main():
     P = L.resolve_icpc_params(cfg, tau, groups=groups or L._abi.GROUP_ALL, cuspzac_direct=args.direct)
     if args.workload == "trap_sweep":
         sparams = L.resolve_sweep_params(cfg, tau)
+    elif args.workload == "compressed":
+        Pp, Pw, aux = compressed_setup(L, cfg, tau)
     else:
         h.icpc_set_params(P)
 
@@ -227,9 +250,26 @@ def main():
     else:
         out = torch.empty((B, NCOL), dtype=torch.float64, device=dev)
     h.synchronize()
+    if args.workload == "compressed":
+        # the DAQ's compressed format made from the full traces (input generation, outside the timed region); only the
+        # compressed buffers stay resident
+        torch.cuda.synchronize()
+        full = pool.view(n_pool, B, 8192).to(torch.int32) & 0xFFFF
+        c_pre = full.view(n_pool, B, 8192 // PRESUM, PRESUM).sum(dim=3, dtype=torch.int32).contiguous()
+        c_wdw = pool[:, :, WDW_FROM:WDW_FROM + WDW_N].contiguous()
+        del full, pool
+        out_w = torch.empty((B, NCOL), dtype=torch.float64, device=dev)
+        out_s = torch.empty((B, 5, 5), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        h.icpc_compressed_run_device(Pp, Pw, c_pre[0].data_ptr(), 4, 8192 // PRESUM, c_wdw[0].data_ptr(), 2, WDW_N, float(PRESUM),
+                                     aux, B, out.data_ptr(), out_w.data_ptr(), out_s.data_ptr())
+        h.synchronize()
 
     def step(k):
-        if args.workload == "trap_sweep":
+        if args.workload == "compressed":
+            h.icpc_compressed_run_device(None, None, c_pre[k % n_pool].data_ptr(), 4, 8192 // PRESUM, c_wdw[k % n_pool].data_ptr(),
+                                         2, WDW_N, float(PRESUM), aux, B, out.data_ptr(), out_w.data_ptr(), out_s.data_ptr())
+        elif args.workload == "trap_sweep":
             h.sweep_run_device(sparams, pool[k % n_pool].data_ptr(), B, 8192, variants, out.data_ptr())
         else:
             h.icpc_run_device(None, pool[k % n_pool].data_ptr(), B, 8192, out.data_ptr())
@@ -262,15 +302,26 @@ def main():
 
     # ---- e2e: pinned host buffers through the host C-ABI call (H2D + kernel + D2H inside the timed region) ----
     Be = min(B, 65536)
-    host_in = torch.empty((Be, 8192), dtype=torch.int16).pin_memory()
-    host_in.copy_(pool[0][:Be])
+    if args.workload == "compressed":
+        host_pre = torch.empty((Be, 8192 // PRESUM), dtype=torch.int32).pin_memory()
+        host_wdw = torch.empty((Be, WDW_N), dtype=torch.int16).pin_memory()
+        host_pre.copy_(c_pre[0][:Be])
+        host_wdw.copy_(c_wdw[0][:Be])
+        host_out_w = torch.empty((Be, NCOL), dtype=torch.float64).pin_memory()
+        host_out_s = torch.empty((Be, 25), dtype=torch.float64).pin_memory()
+    else:
+        host_in = torch.empty((Be, 8192), dtype=torch.int16).pin_memory()
+        host_in.copy_(pool[0][:Be])
     if args.workload == "trap_sweep":
         host_out = torch.empty((Be, 200), dtype=torch.float32).pin_memory()
     else:
         host_out = torch.empty((Be, NCOL), dtype=torch.float64).pin_memory()
 
     def e2e_step():
-        if args.workload == "trap_sweep":
+        if args.workload == "compressed":
+            h.icpc_compressed_run_host(None, None, host_pre.data_ptr(), 4, 8192 // PRESUM, host_wdw.data_ptr(), 2, WDW_N,
+                                       float(PRESUM), aux, Be, host_out.data_ptr(), host_out_w.data_ptr(), host_out_s.data_ptr())
+        elif args.workload == "trap_sweep":
             h.sweep_run_host(sparams, host_in.data_ptr(), Be, 8192, variants, host_out.data_ptr())
         else:
             h.icpc_run_host(None, host_in.data_ptr(), Be, 8192, host_out.data_ptr())
@@ -297,15 +348,16 @@ def main():
             "metric": "waveforms/sec for dsp_icpc (8192-sample)", "value": value, "unit": "waveforms/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_name, "n_samples": 8192, "events_per_step_per_gpu": B, "resident_pool_batches": n_pool,
+            "config": {"workload": wl_name, "n_samples": 8192 if args.workload != "compressed" else [8192 // PRESUM, WDW_N],
+                       "events_per_step_per_gpu": B, "resident_pool_batches": n_pool,
                        "dsp_config": "reference example config (test/test_dsp_icpc.jl:50-161), tie-free windows, tau=500us, default filter pars",
                        "cuspzac": "direct FIR" if args.direct else "structured",
-                       "l2": "inputs larger than L2: each step reads a different 2.1 GB batch",
+                       "l2": f"inputs larger than L2: each step reads a different {B * bytes_in / 1e9:.1f} GB batch",
                        "parallelism": f"event-sharded x{world}, no data-path collective"},
             "clocks": clocks,
             "gpu_launches": int(launches),
-            "e2e": {"value": e2e_val, "unit": "waveforms/s", "h2d_bytes_per_step": Be * BYTES_IN,
-                    "d2h_bytes_per_step": Be * out_bytes, "events_per_step_per_gpu": Be, "checksum": checksum},
+            "e2e": {"value": e2e_val, "unit": "waveforms/s", "h2d_bytes_per_step": Be * bytes_in,
+                    "d2h_bytes_per_step": Be * (out_bytes if args.workload != "compressed" else (2 * NCOL + 25) * 8), "events_per_step_per_gpu": Be, "checksum": checksum},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
                          "traffic": (NCU_DRAM_BYTES_PER_WF[args.workload] * B if args.workload in NCU_DRAM_BYTES_PER_WF
@@ -313,11 +365,14 @@ def main():
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, scaled by events)",
                          "peak_source": peak_kind,
                          "algorithmic_bytes_per_waveform": bytes_per_wf,
-                         "kernel": "sweep_kernel" if args.workload == "trap_sweep" else "icpc_kernel"},
+                         "kernel": "sweep_kernel" if args.workload == "trap_sweep" else "icpc_kernel"
+                                   + (" x2 (presummed + windowed) + window_stats_kernel" if args.workload == "compressed" else "")},
         }
         if not args.no_cpu and world == 1:
             from oracle import oracle as O
             Po = L.resolve_icpc_params(cfg, tau, groups=groups or L._abi.GROUP_ALL, builders=O.OracleBuilders())
+            if args.workload == "compressed":
+                Po = compressed_setup(L, cfg, tau, O.OracleBuilders())
             so = L.resolve_sweep_params(cfg, tau, builders=O.OracleBuilders()) if args.workload == "trap_sweep" else None
             threads = host_threads()
             n_s = args.cpu_sample or 128 * threads

@@ -496,7 +496,11 @@ __device__ __forceinline__ double* cz_tab(double* tabA, double* tabB, int idx)
 // of the anti-causal prefix (P+ at in-chunk offset o is (total - acc[o-1]) * rho^-o; the weights only span one
 // chunk, so nothing cancels).  The running values are stored at the capture events the host sorted by sample index.
 __device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, double* tabA, double* tabB, double* red,
-                        double* pp0)
+                        double* pp0
+#ifdef LGDSP_PROFILE_SECTIONS
+                        , unsigned long long* sect_cnt, unsigned long long* sect_last
+#endif
+                        )
 {
     // SMEM copy of the descriptor, addressed through the dynamic shared memory base so that the loads are LDS
     // (a reference to the kernel parameter or a generic pointer would force generic loads)
@@ -580,6 +584,13 @@ __device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, d
     }
     if (lane == 31) { red[wid] = vpm; red[8 + wid] = vd1; red[16 + wid] = vd2; }
     if (lane == 0) red[24 + wid] = vpp;
+#ifdef LGDSP_PROFILE_SECTIONS
+    if (sect_cnt != nullptr && lane == 0) {   // section 25: cz_scan up to its barrier
+        const unsigned long long now_ = (unsigned long long)clock64();
+        atomicAdd(sect_cnt, now_ - *sect_last);
+        *sect_last = now_;
+    }
+#endif
     __syncthreads();
     double gpm = 0, gd1 = 0, gd2 = 0, gpp = 0;   // carries of the neighbouring warps
     for (int w = 0; w < wid; ++w) { gpm = fma(Z.rho_warp, gpm, red[w]); gd1 += red[8 + w]; gd2 += red[16 + w]; }
@@ -1381,7 +1392,12 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
         }
         SECT(14);
         // CUSP/ZAC prefix tables (first descriptor)
+#ifdef LGDSP_PROFILE_SECTIONS
+        if (cz_structured) cz_scan(npass == 2 ? 1 : 0, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0,
+                                   P.phase_cycles ? &P.phase_cycles[(size_t)gridDim.x * 8 + 25 * 8 + wid] : nullptr, &sect_last);
+#else
         if (cz_structured) cz_scan(npass == 2 ? 1 : 0, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
+#endif
         SECT(15);
         __syncthreads();   // ---- B3 ----
         LGDSP_PHASE(3);
@@ -1784,7 +1800,11 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
             if (rescan) {
                 __syncthreads();   // the previous pass is done with the tables, the coarse values and the output buffer
                 if (tid == 0) ibuf[IB_CZN] = 0;
+#ifdef LGDSP_PROFILE_SECTIONS
+                cz_scan(ps, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0, nullptr, &sect_last);
+#else
                 cz_scan(ps, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
+#endif
                 __syncthreads();
             }
             CzState st;

@@ -30,7 +30,7 @@ if sec and any(any(r) for r in sec):
              6: "tail log", 7: "B2 wait", 8: "resolve t10..", 9: "pz tail stats", 10: "full traps", 11: "coarse traps",
              12: "sg0 chunk pass", 13: "sg1/2+deriv", 14: "sg reductions", 15: "cz_scan", 16: "B3 wait", 17: "t50/pk/stash",
              18: "trap items", 19: "sg masks", 20: "cz_init+coarse", 21: "B4 wait", 22: "cz cand", 23: "cz_run", 24: "final partials",
-             25: "-", 26: "B6 wait", 27: "scalar jobs", 28: "cz jobs/B8 wait", 29: "queue items", 30: "B5 wait"}
+             25: "cz_scan to its barrier", 26: "B6 wait", 27: "scalar jobs", 28: "cz jobs/B8 wait", 29: "queue items", 30: "B5 wait"}
     print("section cycles per event: max over warps | mean over warps | per warp")
     for i in [31] + list(range(31)):
         r = [v / n for v in sec[i]]
