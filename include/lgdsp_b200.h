@@ -191,6 +191,55 @@ typedef struct lgdsp_icpc_params {
     lgdsp_cuspzac cusp, zac;
 } lgdsp_icpc_params;
 
+/* ---- SiPM / PMT trigger chain: dsp_sipm(data, config, pars_optimization)  /root/reference/src/dsp_sipm.jl:47-158 ----
+ * scalar output columns (double rows[n_events][LGDSP_SIPM_NCOL]); t_* in microseconds (:145), the rest in ADC units /
+ * per ns; the four n_trig_* columns are the lengths of the event's trigger lists (exact small integers) */
+enum lgdsp_sipm_col {
+    LGDSP_SIPM_t_max = 0, LGDSP_SIPM_t_min, LGDSP_SIPM_t_max_lar, LGDSP_SIPM_t_min_lar,
+    LGDSP_SIPM_e_max, LGDSP_SIPM_e_min, LGDSP_SIPM_e_max_lar, LGDSP_SIPM_e_min_lar,
+    LGDSP_SIPM_blmean, LGDSP_SIPM_blsigma, LGDSP_SIPM_blslope, LGDSP_SIPM_bloffset,
+    LGDSP_SIPM_wfmean, LGDSP_SIPM_wfsigma, LGDSP_SIPM_wfslope, LGDSP_SIPM_wfoffset,
+    LGDSP_SIPM_threshold, LGDSP_SIPM_threshold_DC, LGDSP_SIPM_threshold_trap, LGDSP_SIPM_threshold_DC_trap,
+    LGDSP_SIPM_n_trig, LGDSP_SIPM_n_trig_DC, LGDSP_SIPM_n_trig_trap, LGDSP_SIPM_n_trig_DC_trap,
+    LGDSP_SIPM_NCOL /* = 24 */
+};
+/* trigger lists (variable length per event, VectorOfVectors in the reference :150-157): list 0 = SG triggers
+ * (trig_pos, trig_max), 1 = SG discharge triggers, 2 = trap triggers (pos, pos_high, pos_tot, max), 3 = trap discharge
+ * triggers; every list entry has the four fields of IntersectMaximum's result (x, x_high, x_tot, max;
+ * src/intersect_maximum.jl:112-118), times in ns.  Padded layout: double trig[n_events][4 lists][4 fields][max_triggers];
+ * entries beyond the event's count are 0.  The count columns hold the TRUE counts: a count > max_triggers means the
+ * lists were cut and the call should be repeated with a larger capacity. */
+#define LGDSP_SIPM_NLIST 4
+#define LGDSP_SIPM_NFIELD 4
+#define LGDSP_SAMPLE_U16 2
+#define LGDSP_SAMPLE_F32 4
+
+typedef struct lgdsp_sipm_params {
+    uint32_t struct_size;      /* sizeof(lgdsp_sipm_params), checked */
+    uint32_t version;          /* LGDSP_PARAMS_VERSION */
+    int32_t n_samples;         /* samples per waveform, <= LGDSP_MAX_SAMPLES (any count, no alignment rule) */
+    int32_t sample_kind;       /* LGDSP_SAMPLE_U16 (raw ADC) or LGDSP_SAMPLE_F32 */
+    double t_first_ns, dt_ns;
+    /* TruncateFilter(t0_hpge_window) [RDDSP] as 0-based inclusive sample range (:94-95) */
+    int32_t trunc_from, trunc_until;
+    /* SavitzkyGolayFilter(pars_optimization.sg.wl, sg_flt_degree, 1)  (:99) */
+    lgdsp_sg sg;
+    /* SG pipeline (:103-105, :120-121): IntersectMaximum(min_tot_intersect, max_tot_intersect) in samples,
+     * thresholdstats_mad bounds and n_sigma factors */
+    int32_t sg_min_n, sg_max_n;
+    double sg_min_thr, sg_max_thr, sg_nsigma;
+    double sg_min_dc, sg_max_dc, sg_nsigma_dc;
+    /* trap pipeline (:125-139): InvCRFilter(pz_tau) as pz_km1 (see lgdsp_icpc_params), TrapezoidalChargeFilter(rt, ft) */
+    lgdsp_trap trap;
+    double pz_km1;
+    int32_t trap_min_n, trap_max_n;
+    double trap_min_thr, trap_max_thr, trap_nsigma;
+    double trap_min_dc, trap_max_dc, trap_nsigma_dc;
+    int32_t max_triggers;      /* capacity of every trigger list, 1 .. LGDSP_SIPM_MAX_TRIGGERS */
+    int32_t reserved0;
+} lgdsp_sipm_params;
+#define LGDSP_SIPM_MAX_TRIGGERS 1024
+
 /* one point of a trapezoidal sweep: filter + pick-off.
  * pickoff_mode 0: fixed time pickoff_ns (dsp_trap_rt_optimization: enc_pickoff_trap);
  * pickoff_mode 1: t50 + pickoff_ns (dsp_trap_ft_optimization: t50 + rt + ft/2), t50 found on the PZ
@@ -342,6 +391,21 @@ int lgdsp_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t
 int lgdsp_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* d_wf, int64_t n_events,
                            int64_t ld_samples, const lgdsp_sweep_variant* variants, int32_t n_variants, void* d_out,
                            double* d_aux);
+
+/* ---- dsp_sipm ---- */
+/* wf: n_events waveforms of `sample_kind` samples, row stride ld_samples (in samples); rows: double[n_events][
+ * LGDSP_SIPM_NCOL]; trig: double[n_events][4][4][max_triggers] (see above).  Host buffers / device buffers. */
+int lgdsp_sipm_run(lgdsp_handle* h, const lgdsp_sipm_params* p, const void* wf, int64_t n_events, int64_t ld_samples,
+                   double* rows, double* trig);
+int lgdsp_sipm_run_device(lgdsp_handle* h, const lgdsp_sipm_params* p, const void* d_wf, int64_t n_events,
+                          int64_t ld_samples, double* d_rows, double* d_trig);
+/* the in-tree primitives of the chain on single traces of doubles (host buffers; one trace per call, for tests and
+ * small jobs): thresholdstats / thresholdstats_mad (src/thresholdstats.jl:19-41, 61-71) and IntersectMaximum
+ * (src/intersect_maximum.jl:24-119; x/x_high/x_tot/max: double[max_triggers], returns the count in *n_found) */
+int lgdsp_thresholdstats(lgdsp_handle* h, const double* y, int32_t n, double min, double max, int32_t mad, double* out);
+int lgdsp_intersect_maximum(lgdsp_handle* h, const double* y, int32_t n, double t_first_ns, double dt_ns, double threshold,
+                            int32_t min_n, int32_t max_n, int32_t max_triggers, double* x, double* x_high, double* x_tot,
+                            double* max, int32_t* n_found);
 
 /* ---- synthetic input ---- */
 /* events [first_event, first_event + n_events) of the stream defined by (seed, mode) */

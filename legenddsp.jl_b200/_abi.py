@@ -141,6 +141,36 @@ class SweepVariant(C.Structure):
     ]
 
 
+# ---- dsp_sipm (include/lgdsp_b200.h: enum lgdsp_sipm_col, lgdsp_sipm_params) ----
+SIPM_COLUMNS = ("t_max", "t_min", "t_max_lar", "t_min_lar", "e_max", "e_min", "e_max_lar", "e_min_lar",
+                "blmean", "blsigma", "blslope", "bloffset", "wfmean", "wfsigma", "wfslope", "wfoffset",
+                "threshold", "threshold_DC", "threshold_trap", "threshold_DC_trap",
+                "n_trig", "n_trig_DC", "n_trig_trap", "n_trig_DC_trap")
+SIPM_COL = {name: i for i, name in enumerate(SIPM_COLUMNS)}
+SIPM_NCOL = len(SIPM_COLUMNS)
+SIPM_NLIST, SIPM_NFIELD = 4, 4
+SIPM_MAX_TRIGGERS = 1024
+SAMPLE_U16, SAMPLE_F32 = 2, 4
+
+
+class SipmParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("version", C.c_uint32),
+        ("n_samples", C.c_int32), ("sample_kind", C.c_int32),
+        ("t_first_ns", C.c_double), ("dt_ns", C.c_double),
+        ("trunc_from", C.c_int32), ("trunc_until", C.c_int32),
+        ("sg", Sg),
+        ("sg_min_n", C.c_int32), ("sg_max_n", C.c_int32),
+        ("sg_min_thr", C.c_double), ("sg_max_thr", C.c_double), ("sg_nsigma", C.c_double),
+        ("sg_min_dc", C.c_double), ("sg_max_dc", C.c_double), ("sg_nsigma_dc", C.c_double),
+        ("trap", Trap), ("pz_km1", C.c_double),
+        ("trap_min_n", C.c_int32), ("trap_max_n", C.c_int32),
+        ("trap_min_thr", C.c_double), ("trap_max_thr", C.c_double), ("trap_nsigma", C.c_double),
+        ("trap_min_dc", C.c_double), ("trap_max_dc", C.c_double), ("trap_nsigma_dc", C.c_double),
+        ("max_triggers", C.c_int32), ("reserved0", C.c_int32),
+    ]
+
+
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_samples", C.c_int32), ("mode", C.c_int32),
                 ("noise_sigma", C.c_double), ("tau_samples", C.c_double)]

@@ -56,6 +56,11 @@ def load_library():
              vp, vp, vp]
     L.lgdsp_icpc_compressed_run.argtypes = _comp
     L.lgdsp_icpc_compressed_run_device.argtypes = _comp
+    L.lgdsp_sipm_run.argtypes = [vp, C.POINTER(_abi.SipmParams), vp, i64, i64, vp, vp]
+    L.lgdsp_sipm_run_device.argtypes = [vp, C.POINTER(_abi.SipmParams), vp, i64, i64, vp, vp]
+    L.lgdsp_thresholdstats.argtypes = [vp, vp, i32, C.c_double, C.c_double, i32, _dp]
+    L.lgdsp_intersect_maximum.argtypes = [vp, vp, i32, C.c_double, C.c_double, C.c_double, i32, i32, i32, vp, vp, vp, vp,
+                                          C.POINTER(i32)]
     L.lgdsp_trap_sweep_run.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64, C.POINTER(_abi.TrapVariant), i32, vp]
     L.lgdsp_trap_sweep_run_device.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64,
                                               C.POINTER(_abi.TrapVariant), i32, vp]
@@ -74,7 +79,8 @@ EXPORTED_SYMBOLS = (
     "lgdsp_version", "lgdsp_last_error", "lgdsp_create", "lgdsp_destroy", "lgdsp_launch_count", "lgdsp_synchronize",
     "lgdsp_lsq_fit_matrix", "lgdsp_sg_coeffs", "lgdsp_cusp_coeffs", "lgdsp_zac_coeffs",
     "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params", "lgdsp_icpc_run_ext", "lgdsp_icpc_run_ext_device",
-    "lgdsp_window_stats_run", "lgdsp_window_stats_run_device", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
+    "lgdsp_window_stats_run", "lgdsp_window_stats_run_device", "lgdsp_sipm_run", "lgdsp_sipm_run_device",
+    "lgdsp_thresholdstats", "lgdsp_intersect_maximum", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
     "lgdsp_trap_sweep_run", "lgdsp_trap_sweep_run_device", "lgdsp_sweep_run", "lgdsp_sweep_run_device",
     "lgdsp_synth_generate_device", "lgdsp_synth_generate_host", "lgdsp_last_kernel_ms", "lgdsp_debug_phase_cycles", "lgdsp_debug_section_cycles",
 )
@@ -191,6 +197,35 @@ class Handle:
 
     def icpc_compressed_run_device(self, *a):
         self._compressed(self._lib.lgdsp_icpc_compressed_run_device, *a)
+
+    # ---- dsp_sipm ----
+    def sipm_run_host(self, params, wf_ptr, n_events, ld, rows_ptr, trig_ptr):
+        self._check(self._lib.lgdsp_sipm_run(self._h, C.byref(params), C.c_void_p(wf_ptr), int(n_events), int(ld),
+                                             C.c_void_p(rows_ptr), C.c_void_p(trig_ptr)))
+
+    def sipm_run_device(self, params, d_wf_ptr, n_events, ld, d_rows_ptr, d_trig_ptr):
+        self._check(self._lib.lgdsp_sipm_run_device(self._h, C.byref(params) if params is not None else None,
+                                                    C.c_void_p(d_wf_ptr), int(n_events), int(ld), C.c_void_p(d_rows_ptr),
+                                                    C.c_void_p(d_trig_ptr)))
+
+    def thresholdstats(self, y, mn, mx, mad):
+        import numpy as np
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        out = C.c_double(0.0)
+        self._check(self._lib.lgdsp_thresholdstats(self._h, C.c_void_p(y.ctypes.data), y.size, float(mn), float(mx),
+                                                   1 if mad else 0, C.byref(out)))
+        return out.value
+
+    def intersect_maximum(self, y, t_first_ns, dt_ns, thr, min_n, max_n, cap):
+        import numpy as np
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        out = [np.zeros(cap) for _ in range(4)]
+        n = C.c_int32(0)
+        self._check(self._lib.lgdsp_intersect_maximum(self._h, C.c_void_p(y.ctypes.data), y.size, float(t_first_ns), float(dt_ns),
+                                                      float(thr), int(min_n), int(max_n), int(cap),
+                                                      *[C.c_void_p(o.ctypes.data) for o in out], C.byref(n)))
+        m = min(n.value, cap)
+        return {"x": out[0][:m], "x_high": out[1][:m], "x_tot": out[2][:m], "max": out[3][:m], "multiplicity": n.value}
 
     # ---- sweeps ----
     def sweep_run_host(self, sparams, wf_ptr, n_events, ld, variants, out_ptr):

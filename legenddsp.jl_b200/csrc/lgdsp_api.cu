@@ -1000,6 +1000,159 @@ int lgdsp_trap_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uin
 }
 
 // ---------------------------------------------------------------------------------------------------
+// dsp_sipm  (/root/reference/src/dsp_sipm.jl:47-158)
+// ---------------------------------------------------------------------------------------------------
+static int sipm_prepare(lgdsp_handle* h, const lgdsp_sipm_params* p, SipmDev& D, int& bps)
+{
+    if (!p) return fail(h, LGDSP_ERR_INVALID_ARG, "params is NULL");
+    if (p->struct_size != sizeof(lgdsp_sipm_params) || p->version != LGDSP_PARAMS_VERSION)
+        return fail(h, LGDSP_ERR_INVALID_ARG, "lgdsp_sipm_params: size/version mismatch (got %u/%u, want %zu/%u)", p->struct_size,
+                    p->version, sizeof(lgdsp_sipm_params), LGDSP_PARAMS_VERSION);
+    const int n = p->n_samples;
+    if (n < 16 || n > LGDSP_MAX_SAMPLES) return fail(h, LGDSP_ERR_UNSUPPORTED, "n_samples = %d: need 16 .. %d", n, LGDSP_MAX_SAMPLES);
+    if (p->sample_kind != LGDSP_SAMPLE_U16 && p->sample_kind != LGDSP_SAMPLE_F32)
+        return fail(h, LGDSP_ERR_UNSUPPORTED, "sample_kind = %d: LGDSP_SAMPLE_U16 or LGDSP_SAMPLE_F32", p->sample_kind);
+    if (!(p->dt_ns > 0) || !std::isfinite(p->t_first_ns)) return fail(h, LGDSP_ERR_INVALID_ARG, "bad time axis");
+    if (!(0 <= p->trunc_from && p->trunc_from <= p->trunc_until && p->trunc_until <= n - 1))
+        return fail(h, LGDSP_ERR_INVALID_ARG, "t0_hpge_window %d:%d outside the waveform", p->trunc_from, p->trunc_until);
+    const lgdsp_sg& sg = p->sg;
+    if (sg.n_taps < 1 || sg.n_taps > LGDSP_MAX_SG || sg.n_taps > n || sg.offset < 0 || sg.offset >= sg.n_taps)
+        return fail(h, LGDSP_ERR_INVALID_ARG, "sg: bad tap count/offset");
+    const int n_sg = n - sg.n_taps + 1;
+    const lgdsp_trap& t = p->trap;
+    if (t.navg < 1 || t.navg2 < 1 || t.ngap < 0 || t.navg + t.ngap + t.navg2 > n_sg)
+        return fail(h, LGDSP_ERR_INVALID_ARG, "trapezoidal filter does not fit the Savitzky-Golay trace");
+    if (p->sg_min_n < 1 || p->sg_max_n < 1 || p->trap_min_n < 1 || p->trap_max_n < 1) return fail(h, LGDSP_ERR_INVALID_ARG, "min_n / max_n must be >= 1");
+    if (p->max_triggers < 1 || p->max_triggers > LGDSP_SIPM_MAX_TRIGGERS) return fail(h, LGDSP_ERR_INVALID_ARG, "max_triggers outside 1..%d", LGDSP_SIPM_MAX_TRIGGERS);
+    D = SipmDev{};
+    D.n = n; D.kind = p->sample_kind; D.t_first = p->t_first_ns; D.dt = p->dt_ns;
+    D.trunc_from = p->trunc_from; D.trunc_until = p->trunc_until;
+    D.sg_taps = sg.n_taps; D.sg_off = sg.offset;
+    for (int k = 0; k < sg.n_taps; ++k) D.sgh[k] = sg.h[k];
+    D.sg_min_n = p->sg_min_n; D.sg_max_n = p->sg_max_n;
+    D.sg_min_thr = p->sg_min_thr; D.sg_max_thr = p->sg_max_thr; D.sg_nsigma = p->sg_nsigma;
+    D.sg_min_dc = p->sg_min_dc; D.sg_max_dc = p->sg_max_dc; D.sg_nsigma_dc = p->sg_nsigma_dc;
+    D.ta = t.navg; D.tg = t.ngap; D.ta2 = t.navg2; D.tL = t.navg + t.ngap + t.navg2;
+    D.inv1 = 1.0 / t.navg; D.inv2 = 1.0 / t.navg2; D.km1 = p->pz_km1;
+    D.trap_min_n = p->trap_min_n; D.trap_max_n = p->trap_max_n;
+    D.trap_min_thr = p->trap_min_thr; D.trap_max_thr = p->trap_max_thr; D.trap_nsigma = p->trap_nsigma;
+    D.trap_min_dc = p->trap_min_dc; D.trap_max_dc = p->trap_max_dc; D.trap_nsigma_dc = p->trap_nsigma_dc;
+    D.cap = p->max_triggers;
+    CK(sipm_configure(n, p->sample_kind, &bps));
+    if (bps < 1) return fail(h, LGDSP_ERR_CUDA, "sipm kernel does not fit on an SM");
+    return LGDSP_OK;
+}
+
+int lgdsp_sipm_run_device(lgdsp_handle* h, const lgdsp_sipm_params* p, const void* d_wf, int64_t n_events, int64_t ld_samples,
+                          double* d_rows, double* d_trig)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    SipmDev D;
+    int bps = 0;
+    int rc = sipm_prepare(h, p, D, bps);
+    if (rc) return rc;
+    if (n_events < 0) return fail(h, LGDSP_ERR_INVALID_ARG, "n_events < 0");
+    if (n_events == 0) return LGDSP_OK;
+    if (!d_wf || !d_rows || !d_trig) return fail(h, LGDSP_ERR_INVALID_ARG, "NULL pointer");
+    if (ld_samples < D.n) return fail(h, LGDSP_ERR_INVALID_ARG, "ld_samples (%lld) < n_samples (%d)", (long long)ld_samples, D.n);
+    const long long cap = (long long)h->sm_count * bps;
+    const int grid = (int)(n_events < cap ? n_events : cap);
+    CK(cudaEventRecord(h->ev0, h->stream));
+    sipm_launch(D, d_wf, n_events, ld_samples, d_rows, d_trig, grid, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->launches += 1;
+    return LGDSP_OK;
+}
+
+int lgdsp_sipm_run(lgdsp_handle* h, const lgdsp_sipm_params* p, const void* wf, int64_t n_events, int64_t ld_samples, double* rows,
+                   double* trig)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    SipmDev D;
+    int bps = 0;
+    int rc = sipm_prepare(h, p, D, bps);
+    if (rc) return rc;
+    if (n_events < 0) return fail(h, LGDSP_ERR_INVALID_ARG, "n_events < 0");
+    if (n_events == 0) return LGDSP_OK;
+    if (!wf || !rows || !trig) return fail(h, LGDSP_ERR_INVALID_ARG, "NULL pointer");
+    if (ld_samples < D.n) return fail(h, LGDSP_ERR_INVALID_ARG, "ld_samples (%lld) < n_samples (%d)", (long long)ld_samples, D.n);
+    const size_t sb = (size_t)D.kind;   // bytes per sample
+    const size_t per_trig = (size_t)LGDSP_SIPM_NLIST * LGDSP_SIPM_NFIELD * D.cap;
+    const int64_t chunk = n_events < 4096 ? n_events : 4096;
+    rc = ensure_staging(h, (size_t)chunk * D.n * sb, (size_t)chunk * (LGDSP_SIPM_NCOL + per_trig) * sizeof(double));
+    if (rc) return rc;
+    const long long gcap = (long long)h->sm_count * bps;
+    const unsigned char* src = static_cast<const unsigned char*>(wf);
+    for (int64_t e0 = 0; e0 < n_events; e0 += chunk) {
+        const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
+        CK(cudaMemcpy2DAsync(h->d_in[0], (size_t)D.n * sb, src + (size_t)e0 * ld_samples * sb, (size_t)ld_samples * sb, (size_t)D.n * sb,
+                             (size_t)ne, cudaMemcpyHostToDevice, h->stream));
+        double* d_rows = h->d_rows;
+        double* d_trig = h->d_rows + (size_t)chunk * LGDSP_SIPM_NCOL;
+        const int grid = (int)(ne < gcap ? ne : gcap);
+        sipm_launch(D, h->d_in[0], ne, D.n, d_rows, d_trig, grid, h->stream);
+        CK(cudaGetLastError());
+        h->launches += 1;
+        CK(cudaMemcpyAsync(rows + e0 * LGDSP_SIPM_NCOL, d_rows, (size_t)ne * LGDSP_SIPM_NCOL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(trig + (size_t)e0 * per_trig, d_trig, (size_t)ne * per_trig * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return LGDSP_OK;
+}
+
+// single-trace primitives (host buffers)
+static int prim_run(lgdsp_handle* h, int mode, const double* y, int n, double a, double b, double t0, double dt, int min_n, int max_n,
+                    int cap, double* out_host, int n_out, int32_t* n_found)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (n < 0 || n > 65536) return fail(h, LGDSP_ERR_UNSUPPORTED, "n = %d: single-trace primitives take 0 .. 65536 samples", n);
+    if (n > 0 && !y) return fail(h, LGDSP_ERR_INVALID_ARG, "trace pointer is NULL");
+    int rc = ensure_staging(h, (size_t)(n > 0 ? n : 1) * sizeof(double), (size_t)(n_out + 2) * sizeof(double));
+    if (rc) return rc;
+    if (n > 0) CK(cudaMemcpyAsync(h->d_in[0], y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int* d_cnt = reinterpret_cast<int*>(h->d_rows + n_out);
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), h->stream));
+    sipm_prim_launch(mode, reinterpret_cast<const double*>(h->d_in[0]), n, a, b, t0, dt, min_n, max_n, cap, h->d_rows, d_cnt, h->stream);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    CK(cudaMemcpyAsync(out_host, h->d_rows, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    int cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n_found) *n_found = cnt;
+    return LGDSP_OK;
+}
+
+int lgdsp_thresholdstats(lgdsp_handle* h, const double* y, int32_t n, double min, double max, int32_t mad, double* out)
+{
+    if (!out) return h ? fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL") : LGDSP_ERR_INVALID_ARG;
+    return prim_run(h, mad ? 1 : 0, y, n, min, max, 0.0, 1.0, 1, 1, 1, out, 1, nullptr);
+}
+
+int lgdsp_intersect_maximum(lgdsp_handle* h, const double* y, int32_t n, double t_first_ns, double dt_ns, double threshold,
+                            int32_t min_n, int32_t max_n, int32_t max_triggers, double* x, double* x_high, double* x_tot,
+                            double* max, int32_t* n_found)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    if (!x || !x_high || !x_tot || !max || !n_found) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
+    if (min_n < 1 || max_n < 1 || max_triggers < 1 || max_triggers > 65536) return fail(h, LGDSP_ERR_INVALID_ARG, "min_n / max_n / max_triggers out of range");
+    std::vector<double> buf((size_t)4 * max_triggers);
+    int rc = prim_run(h, 2, y, n, threshold, 0.0, t_first_ns, dt_ns, min_n, max_n, max_triggers, buf.data(), 4 * max_triggers, n_found);
+    if (rc) return rc;
+    const size_t c = (size_t)max_triggers;
+    memcpy(x, buf.data(), c * sizeof(double));
+    memcpy(x_high, buf.data() + c, c * sizeof(double));
+    memcpy(x_tot, buf.data() + 2 * c, c * sizeof(double));
+    memcpy(max, buf.data() + 3 * c, c * sizeof(double));
+    return LGDSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // synthetic input
 // ---------------------------------------------------------------------------------------------------
 int lgdsp_synth_generate_device(lgdsp_handle* h, const lgdsp_synth_params* sp, int64_t first_event, int64_t n_events,

@@ -46,4 +46,26 @@ void sweep_launch(const SweepDev& P, const uint16_t* d_wf, long long n_events, l
 void synth_launch(const lgdsp_synth_params& sp, long long first_event, long long n_events, long long ld, uint16_t* d_wf,
                   cudaStream_t stream);
 
+// ---- dsp_sipm (lgdsp_sipm.cu) ----
+struct SipmDev {
+    int n, kind;
+    double t_first, dt;
+    int trunc_from, trunc_until;
+    int sg_taps, sg_off;
+    double sgh[LGDSP_MAX_SG];
+    int sg_min_n, sg_max_n;
+    double sg_min_thr, sg_max_thr, sg_nsigma, sg_min_dc, sg_max_dc, sg_nsigma_dc;
+    int ta, tg, ta2, tL;
+    double inv1, inv2, km1;
+    int trap_min_n, trap_max_n;
+    double trap_min_thr, trap_max_thr, trap_nsigma, trap_min_dc, trap_max_dc, trap_nsigma_dc;
+    int cap, pad_;
+};
+cudaError_t sipm_configure(int n, int sample_kind, int* max_blocks_per_sm);
+void sipm_launch(const SipmDev& P, const void* d_wf, long long n_events, long long ld, double* d_rows, double* d_trig, int grid,
+                 cudaStream_t stream);
+// mode 0: thresholdstats, 1: thresholdstats_mad (a, b = bounds), 2: IntersectMaximum (a = threshold)
+void sipm_prim_launch(int mode, const double* d_y, int n, double a, double b, double t0, double dt, int min_n, int max_n, int cap,
+                      double* d_out, int* d_n_found, cudaStream_t stream);
+
 }  // namespace lgdsp

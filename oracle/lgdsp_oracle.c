@@ -950,6 +950,206 @@ ORC_API int orc_dsp_icpc_compressed(const lgdsp_icpc_params* Pp, const lgdsp_icp
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * SiPM / PMT trigger chain  (SURVEY.md 8f rank 3): in-tree primitives + dsp_sipm
+ * ------------------------------------------------------------------------------------------------ */
+
+/* _thresholdstats_impl  src/thresholdstats.jl:19-41: sigma of the samples inside [min, max] */
+ORC_API double orc_thresholdstats(const double* Y, int n, double mn, double mx)
+{
+    double sum_Y = 0, sum_Y_sqr = 0;
+    int64_t cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        double y = Y[i];
+        int inc = (mn <= y) && (y <= mx);
+        y = inc ? y : 0.0 * y;              /* _include * y (:31); 0*y keeps the sign of zero, irrelevant for the sums */
+        sum_Y = y + sum_Y;
+        sum_Y_sqr = fma(y, y, sum_Y_sqr);
+        cnt += inc;
+    }
+    double inv_n = 1.0 / (double)cnt;       /* inv(0) = Inf -> NaN result, as in the reference */
+    double mean_Y = sum_Y * inv_n;
+    double var_Y = sum_Y_sqr * inv_n - mean_Y * mean_Y;
+    if (!(var_Y > 0)) var_Y = (var_Y != var_Y) ? var_Y : 0.0;   /* max(var, 0); NaN propagates */
+    return sqrt(var_Y);
+}
+
+static int cmp_double(const void* a, const void* b)
+{
+    double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
+
+/* Statistics.median!: middle element, or middle(a, b) = a/2 + b/2 of the two middle elements */
+static double median_inplace(double* v, int n)
+{
+    qsort(v, (size_t)n, sizeof(double), cmp_double);
+    if (n & 1) return v[n / 2];
+    return v[n / 2 - 1] / 2 + v[n / 2] / 2;
+}
+
+/* _thresholdstats_mad_impl  src/thresholdstats.jl:61-71 */
+ORC_API double orc_thresholdstats_mad(const double* Y, int n, double mn, double mx)
+{
+    double* f = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if (mn <= Y[i] && Y[i] <= mx) f[m++] = Y[i];
+    if (m == 0) { free(f); return 0.0; }
+    double med = median_inplace(f, m);
+    for (int i = 0; i < m; ++i) f[i] = fabs(f[i] - med);
+    double r = 1.4826 * median_inplace(f, m);
+    free(f);
+    return r;
+}
+
+/* _find_intersect_maximum_impl  src/intersect_maximum.jl:24-119.  X[i] = t0 + i*dt.  Writes at most `cap` entries,
+ * returns the true multiplicity (number of up-crossings found). */
+ORC_API int orc_intersect_maximum(const double* Y, int n, double t0, double dt, double thr, int min_n, int max_n, int cap,
+                                  double* x, double* x_high, double* x_tot, double* mx)
+{
+    if (n <= 0) return 0;                                                           /* :31-39 */
+    int cand_pos = 1;                                                               /* firstindex + 1 (0-based: 1) */
+    int64_t counter = (Y[0] > thr) ? (int64_t)min_n + 1 : 0;                         /* :43 (strict >) */
+    int n_found = 0;
+    int* ups = (int*)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0; i < n; ++i) {                                                   /* :45-56 */
+        int high = Y[i] >= thr;
+        int first_high = counter == 0;
+        if (high && first_high) cand_pos = i;
+        counter = high ? counter + 1 : 0;
+        if (counter == min_n && cand_pos > 0) ups[n_found++] = cand_pos;
+    }
+    for (int k = 0; k < n_found && k < cap; ++k) {
+        int up = ups[k];
+        double x_l = t0 + (up - 1) * dt, x_r = t0 + up * dt, y_l = Y[up - 1], y_r = Y[up];
+        x[k] = (thr - y_l) * (x_r - x_l) / (y_r - y_l) + x_l;                        /* :73 */
+        int from = up - 2 > 0 ? up - 2 : 0, until = up + max_n < n - 1 ? up + max_n : n - 1;   /* :77-78 */
+        int len = until - from + 1, ind = 0;
+        for (int i = 1; i < len; ++i) if (Y[from + i] > Y[from + ind]) ind = i;      /* argmax: first maximum */
+        if (ind > 0 && ind < len - 1) mx[k] = extrema3points(Y[from + ind - 1], Y[from + ind], Y[from + ind + 1]);
+        else mx[k] = Y[from + ind];                                                 /* :81-86 */
+        int down = -1;
+        for (int j = up + min_n; j < n; ++j) if (Y[j] < thr) { down = j; break; }    /* :90-96 */
+        if (down > 0) {
+            double xl = t0 + (down - 1) * dt, xr = t0 + down * dt, yl = Y[down - 1], yr = Y[down];
+            x_high[k] = (thr - yl) * (xr - xl) / (yr - yl) + xl;                     /* :99-104 */
+        } else {
+            x_high[k] = t0 + (n - 1) * dt;                                          /* :107 */
+        }
+        x_tot[k] = x_high[k] - x[k];                                                /* :110 */
+    }
+    free(ups);
+    return n_found;
+}
+
+/* dsp_sipm  src/dsp_sipm.jl:47-158, one event.  w: the waveform as Float64 (:88).  rows: LGDSP_SIPM_NCOL values,
+ * trig: [4 lists][4 fields][cap] */
+static void dsp_sipm_one(const lgdsp_sipm_params* P, const double* w, double* row, double* trig, double* ws)
+{
+    const int n = P->n_samples, cap = P->max_triggers;
+    const double t_first = P->t_first_ns, dt = P->dt_ns;
+    double* sg = ws;
+    double* integ = ws + n;
+    double* flip = ws + 2 * n;
+    double* pz = ws + 3 * n;
+    double* trp = ws + 4 * n;
+    for (int i = 0; i < LGDSP_SIPM_NCOL; ++i) row[i] = 0.0;
+    memset(trig, 0, sizeof(double) * (size_t)LGDSP_SIPM_NLIST * LGDSP_SIPM_NFIELD * cap);
+#define TRIG(list, field) (trig + ((size_t)(list) * LGDSP_SIPM_NFIELD + (field)) * cap)
+    double es[4];
+    /* :91 */
+    orc_extremestats(w, t_first, dt, 0, n - 1, es);
+    row[LGDSP_SIPM_e_min] = es[0]; row[LGDSP_SIPM_e_max] = es[1];
+    row[LGDSP_SIPM_t_min] = es[2] * 0.001; row[LGDSP_SIPM_t_max] = es[3] * 0.001;
+    /* :94-95 TruncateFilter: the samples inside t0_hpge_window keep their times */
+    orc_extremestats(w, t_first, dt, P->trunc_from, P->trunc_until, es);
+    row[LGDSP_SIPM_e_min_lar] = es[0]; row[LGDSP_SIPM_e_max_lar] = es[1];
+    row[LGDSP_SIPM_t_min_lar] = es[2] * 0.001; row[LGDSP_SIPM_t_max_lar] = es[3] * 0.001;
+    /* :99-100 */
+    const int n_sg = orc_corr_valid(w, n, P->sg.h, P->sg.n_taps, sg);
+    const double t_sg = t_first + P->sg.offset * dt;
+    /* :103-105 */
+    double thr = orc_thresholdstats_mad(sg, n_sg, P->sg_min_thr, P->sg_max_thr);
+    row[LGDSP_SIPM_threshold] = thr;
+    int nt = orc_intersect_maximum(sg, n_sg, t_sg, dt, P->sg_nsigma * thr, P->sg_min_n, P->sg_max_n, cap, TRIG(0, 0), TRIG(0, 1),
+                                   TRIG(0, 2), TRIG(0, 3));
+    row[LGDSP_SIPM_n_trig] = (double)nt;
+    /* :108-109 */
+    orc_integrator(sg, n_sg, 1.0, integ);
+    /* :112-115: minimum(inters.x; init = 0) is min(0, x...) */
+    {
+        double time_min = t_sg, d3 = 3 * dt, m = 0.0;
+        for (int k = 0; k < nt && k < cap; ++k) if (TRIG(0, 0)[k] < m) m = TRIG(0, 0)[k];
+        double stop = (m < time_min + d3) ? time_min + d3 : m;
+        int from = (int)rint((time_min - t_sg) / dt), until = (int)rint((stop - t_sg) / dt);
+        if (until > n_sg - 1) until = n_sg - 1;
+        double st[4];
+        orc_signalstats(integ, t_sg, dt, from, until, st);
+        row[LGDSP_SIPM_blmean] = st[0]; row[LGDSP_SIPM_blsigma] = st[1]; row[LGDSP_SIPM_blslope] = st[2]; row[LGDSP_SIPM_bloffset] = st[3];
+        orc_signalstats(integ, t_sg, dt, 0, n_sg - 1, st);
+        row[LGDSP_SIPM_wfmean] = st[0]; row[LGDSP_SIPM_wfsigma] = st[1]; row[LGDSP_SIPM_wfslope] = st[2]; row[LGDSP_SIPM_wfoffset] = st[3];
+    }
+    /* :118-121 */
+    for (int i = 0; i < n_sg; ++i) flip[i] = integ[i] * -1.0;
+    double thr_dc = orc_thresholdstats_mad(flip, n_sg, P->sg_min_dc, P->sg_max_dc);
+    row[LGDSP_SIPM_threshold_DC] = thr_dc;
+    nt = orc_intersect_maximum(flip, n_sg, t_sg, dt, P->sg_nsigma_dc * thr_dc, P->sg_min_n, P->sg_max_n, cap, TRIG(1, 0), TRIG(1, 1),
+                               TRIG(1, 2), TRIG(1, 3));
+    row[LGDSP_SIPM_n_trig_DC] = (double)nt;
+    /* :125-130 */
+    orc_invcr(integ, n_sg, P->pz_km1, pz);
+    const int L = P->trap.navg + P->trap.ngap + P->trap.navg2;
+    const int n_tr = orc_trap(pz, n_sg, P->trap.navg, P->trap.ngap, P->trap.navg2, trp);
+    const double t_tr = t_sg + (L - 1) * dt;
+    /* :133-135 */
+    double thr_tr = orc_thresholdstats_mad(trp, n_tr, P->trap_min_thr, P->trap_max_thr);
+    row[LGDSP_SIPM_threshold_trap] = thr_tr;
+    nt = orc_intersect_maximum(trp, n_tr, t_tr, dt, P->trap_nsigma * thr_tr, P->trap_min_n, P->trap_max_n, cap, TRIG(2, 0),
+                               TRIG(2, 1), TRIG(2, 2), TRIG(2, 3));
+    row[LGDSP_SIPM_n_trig_trap] = (double)nt;
+    /* :138-139 (sic: intflt_sg, the SG pipeline's IntersectMaximum, on the flipped integrated waveform) */
+    double thr_dct = orc_thresholdstats_mad(flip, n_sg, P->trap_min_dc, P->trap_max_dc);
+    row[LGDSP_SIPM_threshold_DC_trap] = thr_dct;
+    nt = orc_intersect_maximum(flip, n_sg, t_sg, dt, P->trap_nsigma_dc * thr_dct, P->sg_min_n, P->sg_max_n, cap, TRIG(3, 0),
+                               TRIG(3, 1), TRIG(3, 2), TRIG(3, 3));
+    row[LGDSP_SIPM_n_trig_DC_trap] = (double)nt;
+#undef TRIG
+}
+
+ORC_API int orc_dsp_sipm(const lgdsp_sipm_params* P, const void* wf, int64_t n_events, int64_t ld, double* rows, double* trig,
+                         int n_threads)
+{
+    int used = 1;
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+    used = n_threads;
+#pragma omp parallel num_threads(n_threads)
+#endif
+    {
+        const int n = P->n_samples;
+        double* ws = (double*)malloc(sizeof(double) * 6 * (size_t)n);
+        double* w = ws + 5 * n;
+        const size_t tsz = (size_t)LGDSP_SIPM_NLIST * LGDSP_SIPM_NFIELD * P->max_triggers;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+        for (int64_t e = 0; e < n_events; ++e) {
+            /* :88 shift_waveform.(wvfs, 0.0): Float64 conversion */
+            if (P->sample_kind == LGDSP_SAMPLE_F32) {
+                const float* r = (const float*)wf + e * ld;
+                for (int i = 0; i < n; ++i) w[i] = (double)r[i] + 0.0;
+            } else {
+                const uint16_t* r = (const uint16_t*)wf + e * ld;
+                for (int i = 0; i < n; ++i) w[i] = (double)r[i] + 0.0;
+            }
+            dsp_sipm_one(P, w, rows + e * LGDSP_SIPM_NCOL, trig + (size_t)e * tsz, ws);
+        }
+        free(ws);
+    }
+    return used;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * trapezoid sweeps  src/dsp_filter_optimization.jl:102-133 (rt, fixed pick-off) and :241-274 (ft, t50-based)
  * out: float[n_events][n_variants] (= column-major Julia matrix n_variants x n_events)
  * ------------------------------------------------------------------------------------------------ */

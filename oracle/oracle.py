@@ -251,6 +251,49 @@ def dsp_icpc_compressed(p_pre, p_wdw, pre, wdw, presum_rate, aux_windows, n_thre
     return {c: rows[:, i].copy() for i, c in enumerate(cols)}
 
 
+def thresholdstats(y, mn=-np.inf, mx=np.inf):
+    y, p = _d(y)
+    L = lib()
+    L.orc_thresholdstats.argtypes = [_dp, C.c_int, C.c_double, C.c_double]
+    L.orc_thresholdstats.restype = C.c_double
+    return L.orc_thresholdstats(p, y.size, float(mn), float(mx))
+
+
+def thresholdstats_mad(y, mn=-np.inf, mx=np.inf):
+    y, p = _d(y)
+    L = lib()
+    L.orc_thresholdstats_mad.argtypes = [_dp, C.c_int, C.c_double, C.c_double]
+    L.orc_thresholdstats_mad.restype = C.c_double
+    return L.orc_thresholdstats_mad(p, y.size, float(mn), float(mx))
+
+
+def intersect_maximum(y, t0, dt, thr, min_n, max_n, cap=256):
+    """IntersectMaximum (src/intersect_maximum.jl:24-119): dict x, x_high, x_tot, max (arrays), multiplicity"""
+    y, p = _d(y)
+    out = [np.zeros(cap) for _ in range(4)]
+    L = lib()
+    L.orc_intersect_maximum.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                        _dp, _dp, _dp, _dp]
+    L.orc_intersect_maximum.restype = C.c_int
+    n = L.orc_intersect_maximum(p, y.size, float(t0), float(dt), float(thr), int(min_n), int(max_n), int(cap),
+                                *[o.ctypes.data_as(_dp) for o in out])
+    m = min(n, cap)
+    return {"x": out[0][:m], "x_high": out[1][:m], "x_tot": out[2][:m], "max": out[3][:m], "multiplicity": n}
+
+
+def dsp_sipm(params, wf, n_threads=0):
+    """oracle dsp_sipm (src/dsp_sipm.jl:47-158): rows[n_events, SIPM_NCOL], trig[n_events, 4, 4, max_triggers]"""
+    wf = np.ascontiguousarray(wf)
+    assert wf.ndim == 2 and wf.dtype == (np.float32 if params.sample_kind == _abi.SAMPLE_F32 else np.uint16)
+    n_ev, ld = wf.shape
+    rows = np.zeros((n_ev, _abi.SIPM_NCOL))
+    trig = np.zeros((n_ev, _abi.SIPM_NLIST, _abi.SIPM_NFIELD, params.max_triggers))
+    L = lib()
+    L.orc_dsp_sipm.argtypes = [C.POINTER(_abi.SipmParams), C.c_void_p, C.c_int64, C.c_int64, _dp, _dp, C.c_int]
+    L.orc_dsp_sipm(C.byref(params), wf.ctypes.data, n_ev, ld, rows.ctypes.data_as(_dp), trig.ctypes.data_as(_dp), int(n_threads))
+    return rows, trig
+
+
 def trap_sweep(sparams, wf_u16, variants, n_threads=0):
     wf = np.ascontiguousarray(wf_u16, dtype=np.uint16)
     n_ev, ld = wf.shape

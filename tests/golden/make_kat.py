@@ -73,6 +73,41 @@ kat = {
             {"name": "two pulses", "ranges": [[99, 104, 0.8], [199, 214, 0.9]], "multiplicity": 2},
         ],
     },
+    "intersect_maximum": {
+        "ref": "test/test_intersect_maximum.jl:6-107: IntersectMaximum(mintot = 2 dt, maxtot = 100 dt) (case 'max at last "
+               "sample': maxtot = 5 dt) on 6200 samples, dt = 16 ns, threshold 0.4; expected values/brackets from the @test lines",
+        "n": 6200, "dt": 16.0, "thr": 0.4, "min_n": 2,
+        "cases": [
+            {"name": "near start (:13-32)", "max_n": 100, "set": {"0": 0.0, "1": 0.5, "2": 0.6, "3": 0.2},
+             "multiplicity": 1, "x_gt": 0.0, "x_lt": 48.0, "max_ge": 0.6, "max_lt": 0.7, "x_high_gt_x": True, "tot_gt": 0.0},
+            {"name": "near end (:35-52)", "max_n": 100, "set": {"6196": 0.0, "6197": 0.5, "6198": 0.6, "6199": 0.2},
+             "multiplicity": 1, "x_gt": 6196 * 16.0, "x_lt": 6199 * 16.0, "max_ge": 0.6, "max_lt": 0.7, "x_high_gt_x": True,
+             "tot_gt": 0.0},
+            {"name": "max at last sample of the window (:56-68)", "max_n": 5,
+             "set": {"6195": 0.3, "6196": 0.5, "6197": 0.6, "6198": 0.8, "6199": 1.0}, "multiplicity": 1, "max_eq": 1.0},
+            {"name": "crossing at the last samples (:71-82)", "max_n": 100, "set": {"6197": 0.3, "6198": 0.5, "6199": 0.6},
+             "multiplicity": 1, "x_gt": 6196 * 16.0, "x_high_eq": 6199 * 16.0},
+            {"name": "two pulses (:96-106)", "max_n": 100, "ranges": [[99, 104, 0.8], [199, 214, 0.9]], "multiplicity": 2,
+             "tot_gt": 0.0, "tot_increasing": True},
+        ],
+        "empty": {"ref": ":85-93", "multiplicity": 0},
+    },
+    "thresholdstats_mad": {
+        "ref": "test/test_thresholdstats.jl:7-65",
+        "cases": [
+            {"name": "constant signal (:11-17)", "signal": [5.0] * 100, "min": -10.0, "max": 10.0, "expect": 0.0, "atol": 1e-10},
+            {"name": "symmetric signal (:20-27)", "signal": [-1.0] * 50 + [1.0] * 50, "min": -5.0, "max": 5.0, "expect": 1.4826,
+             "atol": 1e-10},
+            {"name": "outlier robustness (:30-39)", "signal": [0.0] * 499 + [1000.0] * 11 + [0.0] * 490, "min": "-inf",
+             "max": "inf", "lt": 1.0},
+            {"name": "empty filter (:42-48)", "signal": [5.0] * 100, "min": 10.0, "max": 20.0, "expect": 0.0, "atol": 1e-10},
+        ],
+    },
+    "thresholdstats": {
+        "ref": "test/test_stats.jl:57-110: thresholdstats(wf, min, max) == std(wf[min .<= wf .<= max]) within rtol 0.005 "
+               "(0.001 without bounds) on sigma * randn(10000); the random input is regenerated with a fixed seed",
+        "n": 10000, "seed": 12345, "rtol_bounds": 0.005, "rtol_all": 0.001,
+    },
     "thresholds_fixture": {
         "ref": "test/test_dsp_icpc.jl:189-199 properties on make_fake_waveform: t0 < t50 < t90, drift_time >= 0, "
                "e_10410/e_313/e_trap finite",

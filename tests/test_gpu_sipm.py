@@ -1,0 +1,193 @@
+"""SiPM trigger chain on the GPU: the primitives against the reference's own known-answer tests and
+the oracle, dsp_sipm against the oracle's restatement of src/dsp_sipm.jl:47-158."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from test_sipm_cpu import _signal, check_intersect_maximum_case, sipm_fixture
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def kat():
+    with open(os.path.join(HERE, "golden", "kat_reference_tests.json")) as f:
+        return json.load(f)
+
+
+def test_intersect_maximum_kat_on_gpu(L, handle, kat):
+    """test/test_intersect_maximum.jl:6-107 through lgdsp_intersect_maximum"""
+    k = kat["intersect_maximum"]
+    for c in k["cases"]:
+        y = _signal(k["n"], c)
+        f = L.IntersectMaximum(L.ns(k["min_n"] * k["dt"]), L.ns(c["max_n"] * k["dt"]))
+        r = f(y, k["thr"], step=L.ns(k["dt"]), handle=handle)
+        check_intersect_maximum_case(r, c)
+    r = L.IntersectMaximum(L.ns(32.0), L.ns(1600.0))(np.zeros(0), 0.4, handle=handle)
+    assert r["multiplicity"] == 0 and len(r["x"]) == 0 and len(r["x_high"]) == 0 and len(r["max"]) == 0      # :85-93
+
+
+def test_thresholdstats_kat_on_gpu(L, handle, kat):
+    """test/test_thresholdstats.jl:7-65 and test/test_stats.jl:57-110 through lgdsp_thresholdstats"""
+    for c in kat["thresholdstats_mad"]["cases"]:
+        v = L.thresholdstats_mad(np.array(c["signal"]), float(c["min"]), float(c["max"]), handle=handle)
+        if "expect" in c:
+            assert abs(v - c["expect"]) <= c["atol"], c["name"]
+        else:
+            assert v < c["lt"], c["name"]
+    k = kat["thresholdstats"]
+    rng = np.random.default_rng(k["seed"])
+    sigma = 10.0 * rng.random()
+    y = sigma * rng.standard_normal(k["n"])
+    assert np.isclose(L.thresholdstats(y, handle=handle), sigma, rtol=0.05)
+    assert np.isclose(L.thresholdstats(y, handle=handle), np.std(y, ddof=1), rtol=k["rtol_all"])
+    for _ in range(50):
+        mn, mx = -sigma * rng.random(), sigma * rng.random()
+        sel = y[(y >= mn) & (y <= mx)]
+        if len(sel) > 50:
+            assert np.isclose(L.thresholdstats(y, mn, mx, handle=handle), np.std(sel, ddof=1), rtol=k["rtol_bounds"])
+
+
+def test_primitives_against_oracle(L, O, handle):
+    """random and degenerate traces: medians are exact order statistics, trigger lists identical"""
+    rng = np.random.default_rng(2024)
+    traces = [rng.normal(0, 1.0, 6238), rng.normal(0, 1e-3, 777), np.round(rng.normal(0, 2.0, 5000)),     # heavy ties
+              np.zeros(1000), np.full(333, 2.5), np.concatenate([np.zeros(3000), np.full(3001, 1.0)]),
+              rng.standard_cauchy(4096), np.arange(1000.0), np.array([1.0]), np.array([3.0, -1.0])]
+    for y in traces:
+        for mn, mx in ((-np.inf, np.inf), (-1.0, 1.0), (0.0, 0.5), (5.0, 6.0)):
+            assert L.thresholdstats_mad(y, mn, mx, handle=handle) == O.thresholdstats_mad(y, mn, mx), (len(y), mn, mx)
+    for trial in range(12):
+        n = int(rng.integers(40, 9000))
+        y = rng.normal(0, 1, n)
+        for _ in range(int(rng.integers(0, 30))):
+            a = int(rng.integers(0, n - 5))
+            y[a:a + int(rng.integers(1, 60))] += rng.uniform(1.5, 6)
+        thr, min_n, max_n = float(rng.uniform(1.0, 3.0)), int(rng.integers(1, 6)), int(rng.integers(1, 40))
+        ref = O.intersect_maximum(y, 8.0, 16.0, thr, min_n, max_n, cap=4096)
+        got = handle.intersect_maximum(y, 8.0, 16.0, thr, min_n, max_n, 4096)
+        assert got["multiplicity"] == ref["multiplicity"]
+        assert np.array_equal(got["x"], ref["x"]) and np.array_equal(got["x_high"], ref["x_high"])
+        assert np.array_equal(got["x_tot"], ref["x_tot"])
+        assert np.allclose(got["max"], ref["max"], rtol=1e-13, atol=1e-13)
+    # capacity smaller than the multiplicity: the true count is reported, the first entries are kept
+    y = np.tile(np.array([0.0, 0.0, 3.0, 3.0, 3.0, 0.0]), 100)
+    ref = O.intersect_maximum(y, 0.0, 16.0, 1.0, 2, 5, cap=1024)
+    got = handle.intersect_maximum(y, 0.0, 16.0, 1.0, 2, 5, 7)
+    assert got["multiplicity"] == ref["multiplicity"] == 100 and np.array_equal(got["x"], ref["x"][:7])
+
+
+def sipm_population(n_events, n=6250, seed=7):
+    """raw UInt16 SiPM-like traces: baseline + white noise + 0..6 photo-electron pulses + occasional negative discharge"""
+    rng = np.random.default_rng(seed)
+    k = np.arange(n)
+    wf = np.empty((n_events, n), dtype=np.uint16)
+    for e in range(n_events):
+        y = 2000.0 + rng.normal(0, 2.0, n)
+        for _ in range(int(rng.integers(0, 7))):
+            s0, amp = int(rng.integers(100, n - 400)), rng.uniform(15, 120)
+            d = k - s0
+            y += np.where(d >= 0, amp * (1 - np.exp(-np.maximum(d, 0) / 3.0)) * np.exp(-np.maximum(d, 0) / 30.0), 0.0)
+        if e % 5 == 0:
+            s0 = int(rng.integers(500, n - 600))
+            y -= np.where((k >= s0) & (k < s0 + 40), 60.0, 0.0)
+        wf[e] = np.clip(np.rint(y), 0, 65535).astype(np.uint16)
+    return wf
+
+
+def _compare(L, rows, trig, ref_rows, ref_trig, sg_only=False):
+    c = L._abi.SIPM_COL
+    counts = [c[k] for k in (("n_trig",) if sg_only else ("n_trig", "n_trig_DC", "n_trig_trap", "n_trig_DC_trap"))]
+    assert np.array_equal(rows[:, counts], ref_rows[:, counts])
+    exact = ("t_max", "t_min", "t_max_lar", "t_min_lar", "e_max", "e_min", "e_max_lar", "e_min_lar", "threshold")
+    for name in exact:
+        assert np.array_equal(rows[:, c[name]], ref_rows[:, c[name]]), name
+    for name in ("blmean", "blsigma", "blslope", "bloffset", "wfmean", "wfsigma", "wfslope", "wfoffset", "threshold_DC",
+                 "threshold_trap", "threshold_DC_trap"):
+        a, b = rows[:, c[name]], ref_rows[:, c[name]]
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-9 * (1.0 + np.abs(ref_rows[:, c["wfmean"]]).max())), name
+    # SG trigger list: the SG trace is bit-identical, so positions are too
+    assert np.array_equal(trig[:, 0, :3, :], ref_trig[:, 0, :3, :])
+    assert np.allclose(trig[:, 0, 3, :], ref_trig[:, 0, 3, :], rtol=1e-12, atol=1e-12)
+    # lists on the integrated / trapezoid traces: summation order differs (parallel scans): times to 1e-6 ns
+    for lst in (() if sg_only else (1, 2, 3)):
+        assert np.allclose(trig[:, lst, :3, :], ref_trig[:, lst, :3, :], rtol=0, atol=1e-6), lst
+        assert np.allclose(trig[:, lst, 3, :], ref_trig[:, lst, 3, :], rtol=1e-9, atol=1e-7), lst
+
+
+def test_dsp_sipm_reference_fixture(L, O, handle):
+    """the reference's own test (test/test_dsp_sipm.jl:70-109): 10 identical noise-free events of 6250 samples"""
+    N = 10
+    data = {"waveform": L.RDWaveforms(np.tile(sipm_fixture(), (N, 1))), "baseline": np.zeros(N, np.float32),
+            "timestamp": np.zeros(N, np.uint64), "eventnumber": np.arange(1, N + 1, dtype=np.uint32),
+            "daqenergy": np.zeros(N, np.uint16)}
+    res = L.dsp_sipm(data, L.example_sipm_config(), {"sg": {"wl": L.ns(200.0)}}, handle=handle, builders=O.OracleBuilders())
+    expected = ["blfc", "timestamp", "eventID_fadc", "e_fc", "t_max", "t_min", "t_max_lar", "t_min_lar", "e_max", "e_min",
+                "e_max_lar", "e_min_lar", "blmean", "blsigma", "blslope", "bloffset", "wfmean", "wfsigma", "wfslope", "wfoffset",
+                "threshold", "threshold_DC", "trig_pos", "trig_max", "trig_pos_DC", "trig_max_DC", "threshold_trap",
+                "threshold_DC_trap", "trig_pos_trap", "trig_pos_high_trap", "trig_pos_tot_trap", "trig_max_trap",
+                "trig_pos_DC_trap", "trig_pos_high_DC_trap", "trig_pos_tot_DC_trap", "trig_max_DC_trap"]
+    assert list(res.keys()) == expected                                          # :80-92 (+ the reference's column order)
+    assert all(len(v) == N for v in res.values())                                # :77
+    assert (res["timestamp"] == 0).all() and np.array_equal(res["eventID_fadc"], np.arange(1, N + 1))   # :95-96
+    for k in ("threshold", "threshold_trap"):
+        assert np.isfinite(res[k]).all() and (res[k] >= 0).all()                 # :99-102
+    for k in ("t_max", "t_min"):
+        assert ((res[k] >= 0.0) & (res[k] <= 100.0)).all()                       # :105-106
+    P = L.resolve_sipm_params(L.example_sipm_config(), {"sg": {"wl": L.ns(200.0)}}, n_samples=6250, sample_kind="f32",
+                              builders=O.OracleBuilders())
+    wf = np.tile(sipm_fixture().astype(np.float32), (N, 1))
+    rows, trig = L.sipm_rows(wf, P, handle=handle)
+    ref_rows, ref_trig = O.dsp_sipm(P, wf)
+    # noise-free input: every MAD threshold is exactly 0, so the triggers on the integrated / trapezoid traces compare
+    # rounding noise (+-1e-17 around an exact 0) with 0 -- undefined in the reference as well; the SG list is well defined
+    _compare(L, rows, trig, ref_rows, ref_trig, sg_only=True)
+
+
+@pytest.mark.parametrize("n_samples", [6250, 8192, 2000])
+def test_dsp_sipm_parity(L, O, handle, n_samples):
+    wf = sipm_population(192, n=n_samples, seed=n_samples)
+    cfg = L.example_sipm_config()
+    if n_samples == 2000:
+        cfg["t0_hpge_window"] = (L.us(4.0), L.us(9.0))
+    # raw ADC units: bounds of the threshold estimate scaled to the noise of the population
+    cfg["filters"]["sg"].update(min_threshold=-3.0, max_threshold=3.0, min_dc_threshold=-40.0, max_dc_threshold=40.0)
+    cfg["filters"]["trap"].update(min_threshold=-15.0, max_threshold=15.0, min_dc_threshold=-30.0, max_dc_threshold=30.0)
+    P = L.resolve_sipm_params(cfg, {"sg": {"wl": L.ns(200.0)}}, n_samples=n_samples, builders=O.OracleBuilders(), max_triggers=64)
+    rows, trig = L.sipm_rows(wf, P, handle=handle)
+    ref_rows, ref_trig = O.dsp_sipm(P, wf)
+    _compare(L, rows, trig, ref_rows, ref_trig)
+    c = L._abi.SIPM_COL
+    assert (ref_rows[:, c["n_trig"]] > 0).sum() > 100 and (ref_rows[:, c["n_trig_trap"]] > 0).sum() > 100
+    assert (ref_rows[:, c["n_trig_DC"]] > 0).any()
+    again, trig2 = L.sipm_rows(wf, P, handle=handle)
+    assert np.array_equal(again, rows) and np.array_equal(trig2, trig)            # deterministic
+    # table form: VectorOfVectors with the reference's element pointers
+    tbl = L.sipm_to_table(rows, trig)
+    e = int(np.argmax(ref_rows[:, c["n_trig"]]))
+    assert len(tbl["trig_pos"][e]) == int(ref_rows[e, c["n_trig"]])
+    assert np.array_equal(tbl["trig_pos"][e], ref_trig[e, 0, 0, :len(tbl["trig_pos"][e])])
+
+
+def test_dsp_sipm_capacity_and_errors(L, O, handle):
+    wf = sipm_population(16, seed=3)
+    cfg = L.example_sipm_config()
+    cfg["filters"]["sg"].update(min_threshold=-3.0, max_threshold=3.0, n_σ_threshold=1.0)     # low threshold: many triggers
+    P = L.resolve_sipm_params(cfg, {"sg": {"wl": L.ns(200.0)}}, n_samples=6250, builders=O.OracleBuilders(), max_triggers=4)
+    rows, trig = L.sipm_rows(wf, P, handle=handle)          # grows the capacity until every list fits
+    assert P.max_triggers > 4 and rows[:, L._abi.SIPM_COL["n_trig"]].max() <= P.max_triggers
+    ref_rows, ref_trig = O.dsp_sipm(P, wf)
+    _compare(L, rows, trig, ref_rows, ref_trig)
+    with pytest.raises(AssertionError):
+        c2 = L.example_sipm_config()
+        c2["t0_hpge_window"] = (L.us(200.0), L.us(300.0))
+        L.resolve_sipm_params(c2, {"sg": {"wl": L.ns(200.0)}}, n_samples=6250)
+    bad = L.resolve_sipm_params(cfg, {"sg": {"wl": L.ns(200.0)}}, n_samples=6250)
+    bad.max_triggers = 0
+    with pytest.raises(L.LgdspError):
+        L.sipm_rows(wf, bad, handle=handle)
+    empty = L.dsp_sipm({"waveform": L.RDWaveforms(np.zeros((0, 6250), np.uint16))}, cfg, {"sg": {"wl": L.ns(200.0)}}, handle=handle)
+    assert len(empty["t_max"]) == 0 and len(empty["trig_pos"]) == 0
