@@ -105,8 +105,39 @@ def compressed_setup(L, cfg, tau, builders=None):
                                        n_wdw=WDW_N, t_first_wdw=L.ns(16.0 * WDW_FROM), step_wdw=L.ns(16.0), builders=builders)
 
 
+SIPM_N, SIPM_CAP = 6250, 32
+
+
+def sipm_setup(L, builders=None):
+    cfg = L.example_sipm_config()
+    cfg["filters"]["sg"].update(min_threshold=-3.0, max_threshold=3.0, min_dc_threshold=-40.0, max_dc_threshold=40.0)
+    cfg["filters"]["trap"].update(min_threshold=-15.0, max_threshold=15.0, min_dc_threshold=-30.0, max_dc_threshold=30.0)
+    return L.resolve_sipm_params(cfg, {"sg": {"wl": L.ns(200.0)}}, n_samples=SIPM_N, builders=builders, max_triggers=SIPM_CAP)
+
+
+def sipm_events(torch, n_events, seed, device):
+    """raw UInt16 SiPM-like traces (baseline 2000 ADC, white noise sigma 2, 0..6 photo-electron pulses): int16 bit patterns"""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    k = torch.arange(SIPM_N, device=device, dtype=torch.float32)[None, :]
+    y = 2000.0 + 2.0 * torch.randn((n_events, SIPM_N), generator=g, device=device)
+    for q in range(6):
+        on = (torch.rand((n_events, 1), generator=g, device=device) < 0.5).float()
+        s0 = 100.0 + (SIPM_N - 500.0) * torch.rand((n_events, 1), generator=g, device=device)
+        amp = 15.0 + 105.0 * torch.rand((n_events, 1), generator=g, device=device)
+        d = (k - s0).clamp(min=0.0)
+        y += on * amp * (k >= s0).float() * (1.0 - torch.exp(-d / 3.0)) * torch.exp(-d / 30.0)
+    return y.round().clamp(0, 65535).to(torch.int32).to(torch.int16)
+
+
 def cpu_port_throughput(L, O, P, n_events, workload, variants=None, sparams=None, reps=1, threads=0):
     """the CPU port of the reference algorithm (oracle/) on all host cores: waveforms/s"""
+    if workload == "sipm":
+        import torch
+        wf = sipm_events(torch, n_events, 99, "cpu").numpy().view("uint16")
+        t0 = time.perf_counter()
+        O.dsp_sipm(P, wf, n_threads=threads)
+        return n_events / (time.perf_counter() - t0)
     wf = L.synth.generate_host(n_events, first_event=10_000_000)
     if workload == "compressed":
         pre, wdw = L.synth.compress(wf, PRESUM, (WDW_FROM, WDW_N))
@@ -131,7 +162,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dsp_icpc", choices=["dsp_icpc", "pz_trap", "trap_sweep", "compressed"])
+    ap.add_argument("--workload", default="dsp_icpc", choices=["dsp_icpc", "pz_trap", "trap_sweep", "compressed", "sipm"])
     ap.add_argument("--batch", type=int, default=131072, help="waveforms per step per GPU (131072 = 2.1 GB >> L2)")
     ap.add_argument("--pool", type=int, default=4, help="distinct resident batches cycled by the steps")
     ap.add_argument("--direct", action="store_true", help="CUSP/ZAC as direct 2375-tap FIRs (validation mode)")
@@ -152,17 +183,19 @@ def main():
 
     cfg = L.tiefree_config()
     tau = L.us(500.0)
-    groups = {"dsp_icpc": L._abi.GROUP_ALL, "pz_trap": L._abi.GROUP_PZTRAP, "trap_sweep": 0, "compressed": 0}[args.workload]
+    groups = {"dsp_icpc": L._abi.GROUP_ALL, "pz_trap": L._abi.GROUP_PZTRAP, "trap_sweep": 0, "compressed": 0, "sipm": 0}[args.workload]
     wl_name = {"dsp_icpc": "full dsp_icpc, 49 columns incl. CUSP+ZAC (BASELINE configs[2]/[4])",
                "pz_trap": "pole-zero + trapezoid energies/t0 only (BASELINE configs[1])",
                "trap_sweep": "20x10 trapezoid (rt, ft) sweep, 200 variants (BASELINE configs[3])",
+               "sipm": "dsp_sipm trigger chain on 6250-sample UInt16 SiPM traces (SURVEY 8f rank 3)",
                "compressed": "dsp_icpc_compressed: 1024 presummed uint32 (x8) + 1400 windowed uint16 samples per event "
                              "(SURVEY 8f rank 1)"}[args.workload]
     if args.groups is not None:
         groups = int(args.groups, 16)
         wl_name += f" [experimental group mask {groups:#x}]"
-    out_bytes = {"dsp_icpc": NCOL * 8, "pz_trap": 5 * 8, "trap_sweep": 200 * 4, "compressed": 65 * 8}[args.workload]
-    bytes_in = BYTES_IN if args.workload != "compressed" else (8192 // PRESUM) * 4 + WDW_N * 2
+    out_bytes = {"dsp_icpc": NCOL * 8, "pz_trap": 5 * 8, "trap_sweep": 200 * 4, "compressed": 65 * 8,
+                 "sipm": (24 + 16 * SIPM_CAP) * 8}[args.workload]
+    bytes_in = {"compressed": (8192 // PRESUM) * 4 + WDW_N * 2, "sipm": SIPM_N * 2}.get(args.workload, BYTES_IN)
     bytes_per_wf = bytes_in + out_bytes
     variants = sparams = None
     if args.workload == "trap_sweep":
@@ -187,9 +220,15 @@ def main():
         if args.workload == "compressed":
             Pp, Pw, aux = compressed_setup(L, cfg, tau, O.OracleBuilders())
             pre, wdw = L.synth.compress(wf, PRESUM, (WDW_FROM, WDW_N))
+        if args.workload == "sipm":
+            import torch
+            Ps = sipm_setup(L, O.OracleBuilders())
+            wf = sipm_events(torch, n_s, 99, "cpu").numpy().view("uint16")
 
         def step():
-            if args.workload == "compressed":
+            if args.workload == "sipm":
+                O.dsp_sipm(Ps, wf, n_threads=threads)
+            elif args.workload == "compressed":
                 O.dsp_icpc_compressed(Pp, Pw, pre, wdw, PRESUM, aux, n_threads=threads)
             elif args.workload == "trap_sweep":
                 O.trap_sweep(sparams, wf, variants, n_threads=threads)
@@ -236,15 +275,21 @@ def main():
         sparams = L.resolve_sweep_params(cfg, tau)
     elif args.workload == "compressed":
         Pp, Pw, aux = compressed_setup(L, cfg, tau)
+    elif args.workload == "sipm":
+        Ps = sipm_setup(L)
     else:
         h.icpc_set_params(P)
 
     B = args.batch
     n_pool = max(1, args.pool)
     # resident pool of distinct batches, generated on the device (each rank its own slice of the event stream)
-    pool = torch.empty((n_pool, B, 8192), dtype=torch.int16, device=dev)
-    for k in range(n_pool):
-        L.synth.generate_device(h, pool[k].data_ptr(), B, first_event=(rank * n_pool + k) * B)
+    if args.workload == "sipm":
+        pool = torch.stack([sipm_events(torch, B, 1000 + rank * n_pool + k, dev) for k in range(n_pool)])
+        out_t = torch.empty((B, 4, 4, SIPM_CAP), dtype=torch.float64, device=dev)
+    else:
+        pool = torch.empty((n_pool, B, 8192), dtype=torch.int16, device=dev)
+        for k in range(n_pool):
+            L.synth.generate_device(h, pool[k].data_ptr(), B, first_event=(rank * n_pool + k) * B)
     if args.workload == "trap_sweep":
         out = torch.empty((B, 200), dtype=torch.float32, device=dev)
     else:
@@ -266,7 +311,9 @@ def main():
         h.synchronize()
 
     def step(k):
-        if args.workload == "compressed":
+        if args.workload == "sipm":
+            h.sipm_run_device(Ps, pool[k % n_pool].data_ptr(), B, SIPM_N, out.data_ptr(), out_t.data_ptr())
+        elif args.workload == "compressed":
             h.icpc_compressed_run_device(None, None, c_pre[k % n_pool].data_ptr(), 4, 8192 // PRESUM, c_wdw[k % n_pool].data_ptr(),
                                          2, WDW_N, float(PRESUM), aux, B, out.data_ptr(), out_w.data_ptr(), out_s.data_ptr())
         elif args.workload == "trap_sweep":
@@ -310,15 +357,18 @@ def main():
         host_out_w = torch.empty((Be, NCOL), dtype=torch.float64).pin_memory()
         host_out_s = torch.empty((Be, 25), dtype=torch.float64).pin_memory()
     else:
-        host_in = torch.empty((Be, 8192), dtype=torch.int16).pin_memory()
+        host_in = torch.empty((Be, SIPM_N if args.workload == "sipm" else 8192), dtype=torch.int16).pin_memory()
         host_in.copy_(pool[0][:Be])
+        host_out_t = torch.empty((Be, 16 * SIPM_CAP), dtype=torch.float64).pin_memory() if args.workload == "sipm" else None
     if args.workload == "trap_sweep":
         host_out = torch.empty((Be, 200), dtype=torch.float32).pin_memory()
     else:
         host_out = torch.empty((Be, NCOL), dtype=torch.float64).pin_memory()
 
     def e2e_step():
-        if args.workload == "compressed":
+        if args.workload == "sipm":
+            h.sipm_run_host(Ps, host_in.data_ptr(), Be, SIPM_N, host_out.data_ptr(), host_out_t.data_ptr())
+        elif args.workload == "compressed":
             h.icpc_compressed_run_host(None, None, host_pre.data_ptr(), 4, 8192 // PRESUM, host_wdw.data_ptr(), 2, WDW_N,
                                        float(PRESUM), aux, Be, host_out.data_ptr(), host_out_w.data_ptr(), host_out_s.data_ptr())
         elif args.workload == "trap_sweep":
@@ -348,7 +398,7 @@ def main():
             "metric": "waveforms/sec for dsp_icpc (8192-sample)", "value": value, "unit": "waveforms/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_name, "n_samples": 8192 if args.workload != "compressed" else [8192 // PRESUM, WDW_N],
+            "config": {"workload": wl_name, "n_samples": {"compressed": [8192 // PRESUM, WDW_N], "sipm": SIPM_N}.get(args.workload, 8192),
                        "events_per_step_per_gpu": B, "resident_pool_batches": n_pool,
                        "dsp_config": "reference example config (test/test_dsp_icpc.jl:50-161), tie-free windows, tau=500us, default filter pars",
                        "cuspzac": "direct FIR" if args.direct else "structured",
@@ -365,7 +415,7 @@ def main():
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, scaled by events)",
                          "peak_source": peak_kind,
                          "algorithmic_bytes_per_waveform": bytes_per_wf,
-                         "kernel": "sweep_kernel" if args.workload == "trap_sweep" else "icpc_kernel"
+                         "kernel": "sweep_kernel" if args.workload == "trap_sweep" else "sipm_kernel" if args.workload == "sipm" else "icpc_kernel"
                                    + (" x2 (presummed + windowed) + window_stats_kernel" if args.workload == "compressed" else "")},
         }
         if not args.no_cpu and world == 1:
@@ -373,6 +423,8 @@ def main():
             Po = L.resolve_icpc_params(cfg, tau, groups=groups or L._abi.GROUP_ALL, builders=O.OracleBuilders())
             if args.workload == "compressed":
                 Po = compressed_setup(L, cfg, tau, O.OracleBuilders())
+            if args.workload == "sipm":
+                Po = sipm_setup(L, O.OracleBuilders())
             so = L.resolve_sweep_params(cfg, tau, builders=O.OracleBuilders()) if args.workload == "trap_sweep" else None
             threads = host_threads()
             n_s = args.cpu_sample or 128 * threads
