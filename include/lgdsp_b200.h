@@ -240,6 +240,26 @@ typedef struct lgdsp_sipm_params {
 } lgdsp_sipm_params;
 #define LGDSP_SIPM_MAX_TRIGGERS 1024
 
+/* ---- MultiIntersect(threshold_ratios, mintot, n, d, sampling_rate)(wvf)  /root/reference/src/multi_intersect.jl:10-121 ----
+ * first crossings of the thresholds ratios[j] * maximum(Y) (sequential search: threshold j+1 is looked for from the crossing
+ * of threshold j on, :59-73), each refined by a least-squares polynomial of `degree` over the 2*half_window samples around the
+ * crossing, up-sampled by `rate` (:81-101) */
+#define LGDSP_MI_MAX_THR 128
+#define LGDSP_MI_MAX_HALF 8
+typedef struct lgdsp_multi_intersect_params {
+    uint32_t struct_size;      /* sizeof(lgdsp_multi_intersect_params), checked */
+    uint32_t version;          /* LGDSP_PARAMS_VERSION */
+    int32_t n_samples;         /* samples per trace (doubles), any count >= 2 */
+    int32_t n_thresholds;      /* 1 .. LGDSP_MI_MAX_THR */
+    double t_first_ns, dt_ns;
+    int32_t min_n;             /* max(1, round(mintot/dt)) */
+    int32_t half_window;       /* n: the fit window is pos-n .. pos+n-1; 1 .. LGDSP_MI_MAX_HALF */
+    int32_t degree;            /* d <= LGDSP_MAX_DNI_DEG, d < 2n */
+    int32_t rate;              /* sampling_rate >= 1, 2n*rate <= 256 */
+    double ratios[LGDSP_MI_MAX_THR];
+    double A[2 * LGDSP_MI_MAX_HALF * (LGDSP_MAX_DNI_DEG + 1)];   /* lgdsp_lsq_fit_matrix(2n, degree), row-major */
+} lgdsp_multi_intersect_params;
+
 /* one point of a trapezoidal sweep: filter + pick-off.
  * pickoff_mode 0: fixed time pickoff_ns (dsp_trap_rt_optimization: enc_pickoff_trap);
  * pickoff_mode 1: t50 + pickoff_ns (dsp_trap_ft_optimization: t50 + rt + ft/2), t50 found on the PZ
@@ -406,6 +426,13 @@ int lgdsp_thresholdstats(lgdsp_handle* h, const double* y, int32_t n, double min
 int lgdsp_intersect_maximum(lgdsp_handle* h, const double* y, int32_t n, double t_first_ns, double dt_ns, double threshold,
                             int32_t min_n, int32_t max_n, int32_t max_triggers, double* x, double* x_high, double* x_tot,
                             double* max, int32_t* n_found);
+
+/* MultiIntersect on a batch of traces of doubles: y[e*ld_samples + i]; x: double[n_events][n_thresholds] (ns);
+ * flags: int32[n_events], 1 where the reference's boundary assertion (:85-88) fails (that event's x are NaN) */
+int lgdsp_multi_intersect_run(lgdsp_handle* h, const lgdsp_multi_intersect_params* p, const double* y, int64_t n_events,
+                              int64_t ld_samples, double* x, int32_t* flags);
+int lgdsp_multi_intersect_run_device(lgdsp_handle* h, const lgdsp_multi_intersect_params* p, const double* d_y,
+                                     int64_t n_events, int64_t ld_samples, double* d_x, int32_t* d_flags);
 
 /* ---- synthetic input ---- */
 /* events [first_event, first_event + n_events) of the stream defined by (seed, mode) */

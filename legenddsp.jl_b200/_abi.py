@@ -171,6 +171,20 @@ class SipmParams(C.Structure):
     ]
 
 
+MI_MAX_THR, MI_MAX_HALF = 128, 8
+
+
+class MultiIntersectParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("version", C.c_uint32),
+        ("n_samples", C.c_int32), ("n_thresholds", C.c_int32),
+        ("t_first_ns", C.c_double), ("dt_ns", C.c_double),
+        ("min_n", C.c_int32), ("half_window", C.c_int32), ("degree", C.c_int32), ("rate", C.c_int32),
+        ("ratios", C.c_double * MI_MAX_THR),
+        ("A", C.c_double * (2 * MI_MAX_HALF * (LGDSP_MAX_DNI_DEG + 1))),
+    ]
+
+
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_samples", C.c_int32), ("mode", C.c_int32),
                 ("noise_sigma", C.c_double), ("tau_samples", C.c_double)]

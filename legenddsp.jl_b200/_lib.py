@@ -61,6 +61,8 @@ def load_library():
     L.lgdsp_thresholdstats.argtypes = [vp, vp, i32, C.c_double, C.c_double, i32, _dp]
     L.lgdsp_intersect_maximum.argtypes = [vp, vp, i32, C.c_double, C.c_double, C.c_double, i32, i32, i32, vp, vp, vp, vp,
                                           C.POINTER(i32)]
+    L.lgdsp_multi_intersect_run.argtypes = [vp, C.POINTER(_abi.MultiIntersectParams), vp, i64, i64, vp, vp]
+    L.lgdsp_multi_intersect_run_device.argtypes = [vp, C.POINTER(_abi.MultiIntersectParams), vp, i64, i64, vp, vp]
     L.lgdsp_trap_sweep_run.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64, C.POINTER(_abi.TrapVariant), i32, vp]
     L.lgdsp_trap_sweep_run_device.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64,
                                               C.POINTER(_abi.TrapVariant), i32, vp]
@@ -80,7 +82,7 @@ EXPORTED_SYMBOLS = (
     "lgdsp_lsq_fit_matrix", "lgdsp_sg_coeffs", "lgdsp_cusp_coeffs", "lgdsp_zac_coeffs",
     "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params", "lgdsp_icpc_run_ext", "lgdsp_icpc_run_ext_device",
     "lgdsp_window_stats_run", "lgdsp_window_stats_run_device", "lgdsp_sipm_run", "lgdsp_sipm_run_device",
-    "lgdsp_thresholdstats", "lgdsp_intersect_maximum", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
+    "lgdsp_thresholdstats", "lgdsp_intersect_maximum", "lgdsp_multi_intersect_run", "lgdsp_multi_intersect_run_device", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
     "lgdsp_trap_sweep_run", "lgdsp_trap_sweep_run_device", "lgdsp_sweep_run", "lgdsp_sweep_run_device",
     "lgdsp_synth_generate_device", "lgdsp_synth_generate_host", "lgdsp_last_kernel_ms", "lgdsp_debug_phase_cycles", "lgdsp_debug_section_cycles",
 )
@@ -226,6 +228,14 @@ class Handle:
                                                       *[C.c_void_p(o.ctypes.data) for o in out], C.byref(n)))
         m = min(n.value, cap)
         return {"x": out[0][:m], "x_high": out[1][:m], "x_tot": out[2][:m], "max": out[3][:m], "multiplicity": n.value}
+
+    def multi_intersect_host(self, params, y_ptr, n_events, ld, x_ptr, flags_ptr):
+        self._check(self._lib.lgdsp_multi_intersect_run(self._h, C.byref(params), C.c_void_p(y_ptr), int(n_events), int(ld),
+                                                        C.c_void_p(x_ptr), C.c_void_p(flags_ptr)))
+
+    def multi_intersect_device(self, params, d_y_ptr, n_events, ld, d_x_ptr, d_flags_ptr):
+        self._check(self._lib.lgdsp_multi_intersect_run_device(self._h, C.byref(params), C.c_void_p(d_y_ptr), int(n_events),
+                                                               int(ld), C.c_void_p(d_x_ptr), C.c_void_p(d_flags_ptr)))
 
     # ---- sweeps ----
     def sweep_run_host(self, sparams, wf_ptr, n_events, ld, variants, out_ptr):

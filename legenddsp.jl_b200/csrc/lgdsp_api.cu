@@ -1153,6 +1153,82 @@ int lgdsp_intersect_maximum(lgdsp_handle* h, const double* y, int32_t n, double 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// MultiIntersect  (/root/reference/src/multi_intersect.jl:10-121)
+// ---------------------------------------------------------------------------------------------------
+static int mi_prepare(lgdsp_handle* h, const lgdsp_multi_intersect_params* p, MiDev& D)
+{
+    if (!p) return fail(h, LGDSP_ERR_INVALID_ARG, "params is NULL");
+    if (p->struct_size != sizeof(lgdsp_multi_intersect_params) || p->version != LGDSP_PARAMS_VERSION)
+        return fail(h, LGDSP_ERR_INVALID_ARG, "lgdsp_multi_intersect_params: size/version mismatch");
+    if (p->n_samples < 2) return fail(h, LGDSP_ERR_INVALID_ARG, "n_samples < 2");
+    if (p->n_thresholds < 1 || p->n_thresholds > LGDSP_MI_MAX_THR) return fail(h, LGDSP_ERR_UNSUPPORTED, "n_thresholds outside 1..%d", LGDSP_MI_MAX_THR);
+    if (!(p->dt_ns > 0) || !std::isfinite(p->t_first_ns)) return fail(h, LGDSP_ERR_INVALID_ARG, "bad time axis");
+    if (p->min_n < 1) return fail(h, LGDSP_ERR_INVALID_ARG, "min_n must be >= 1");
+    if (p->half_window < 1 || p->half_window > LGDSP_MI_MAX_HALF || p->degree < 0 || p->degree > LGDSP_MAX_DNI_DEG ||
+        p->degree >= 2 * p->half_window || p->rate < 1 || 2 * p->half_window * p->rate > 256)
+        return fail(h, LGDSP_ERR_UNSUPPORTED, "polynomial window / degree / sampling rate outside the supported range");
+    D = MiDev{};
+    D.len = p->n_samples; D.n_thr = p->n_thresholds; D.t0 = p->t_first_ns; D.dt = p->dt_ns;
+    D.min_n = p->min_n; D.n = p->half_window; D.degree = p->degree; D.rate = p->rate;
+    for (int j = 0; j < p->n_thresholds; ++j) D.ratios[j] = p->ratios[j];
+    for (int i = 0; i < 2 * p->half_window * (p->degree + 1); ++i) D.A[i] = p->A[i];
+    return LGDSP_OK;
+}
+
+int lgdsp_multi_intersect_run_device(lgdsp_handle* h, const lgdsp_multi_intersect_params* p, const double* d_y, int64_t n_events,
+                                     int64_t ld_samples, double* d_x, int32_t* d_flags)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    MiDev D;
+    int rc = mi_prepare(h, p, D);
+    if (rc) return rc;
+    if (n_events < 0) return fail(h, LGDSP_ERR_INVALID_ARG, "n_events < 0");
+    if (n_events == 0) return LGDSP_OK;
+    if (!d_y || !d_x || !d_flags) return fail(h, LGDSP_ERR_INVALID_ARG, "NULL pointer");
+    if (ld_samples < D.len) return fail(h, LGDSP_ERR_INVALID_ARG, "ld_samples < n_samples");
+    CK(cudaEventRecord(h->ev0, h->stream));
+    multi_intersect_launch(D, d_y, n_events, ld_samples, d_x, d_flags, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->launches += 1;
+    return LGDSP_OK;
+}
+
+int lgdsp_multi_intersect_run(lgdsp_handle* h, const lgdsp_multi_intersect_params* p, const double* y, int64_t n_events,
+                              int64_t ld_samples, double* x, int32_t* flags)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    MiDev D;
+    int rc = mi_prepare(h, p, D);
+    if (rc) return rc;
+    if (n_events < 0) return fail(h, LGDSP_ERR_INVALID_ARG, "n_events < 0");
+    if (n_events == 0) return LGDSP_OK;
+    if (!y || !x || !flags) return fail(h, LGDSP_ERR_INVALID_ARG, "NULL pointer");
+    if (ld_samples < D.len) return fail(h, LGDSP_ERR_INVALID_ARG, "ld_samples < n_samples");
+    const int64_t chunk = n_events < 4096 ? n_events : 4096;
+    const size_t out_per = (size_t)D.n_thr * sizeof(double) + sizeof(int32_t);
+    rc = ensure_staging(h, (size_t)chunk * D.len * sizeof(double), (size_t)chunk * out_per + 16);
+    if (rc) return rc;
+    double* d_x = h->d_rows;
+    int* d_f = reinterpret_cast<int*>(h->d_rows + (size_t)chunk * D.n_thr);
+    for (int64_t e0 = 0; e0 < n_events; e0 += chunk) {
+        const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
+        CK(cudaMemcpy2DAsync(h->d_in[0], (size_t)D.len * sizeof(double), y + e0 * ld_samples, (size_t)ld_samples * sizeof(double),
+                             (size_t)D.len * sizeof(double), (size_t)ne, cudaMemcpyHostToDevice, h->stream));
+        multi_intersect_launch(D, reinterpret_cast<const double*>(h->d_in[0]), ne, D.len, d_x, d_f, h->stream);
+        CK(cudaGetLastError());
+        h->launches += 1;
+        CK(cudaMemcpyAsync(x + e0 * D.n_thr, d_x, (size_t)ne * D.n_thr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(flags + e0, d_f, (size_t)ne * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return LGDSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // synthetic input
 // ---------------------------------------------------------------------------------------------------
 int lgdsp_synth_generate_device(lgdsp_handle* h, const lgdsp_synth_params* sp, int64_t first_event, int64_t n_events,

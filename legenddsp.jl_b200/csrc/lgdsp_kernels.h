@@ -68,4 +68,15 @@ void sipm_launch(const SipmDev& P, const void* d_wf, long long n_events, long lo
 void sipm_prim_launch(int mode, const double* d_y, int n, double a, double b, double t0, double dt, int min_n, int max_n, int cap,
                       double* d_out, int* d_n_found, cudaStream_t stream);
 
+// ---- MultiIntersect (lgdsp_sipm.cu): one warp per trace ----
+struct MiDev {
+    int len, n_thr;
+    double t0, dt;
+    int min_n, n, degree, rate;
+    double ratios[LGDSP_MI_MAX_THR];
+    double A[2 * LGDSP_MI_MAX_HALF * (LGDSP_MAX_DNI_DEG + 1)];
+};
+void multi_intersect_launch(const MiDev& P, const double* d_y, long long n_events, long long ld, double* d_x, int* d_flags,
+                            cudaStream_t stream);
+
 }  // namespace lgdsp

@@ -566,6 +566,99 @@ __global__ void __launch_bounds__(SNT) sipm_prim_kernel(int mode, const double* 
     }
 }
 
+// ==================================================================================================
+// MultiIntersect  src/multi_intersect.jl:36-104, one WARP per trace (global memory, coalesced 32-sample steps).
+// The sequential search (:59-73) advances 32 samples per ballot; blocks without a sample above the current threshold are
+// skipped in one step, the others are walked bit by bit in registers (same state machine, no memory traffic).
+// ==================================================================================================
+constexpr int MI_WARPS = 8;
+
+__global__ void __launch_bounds__(MI_WARPS * 32) multi_intersect_kernel(const __grid_constant__ MiDev P, const double* __restrict__ y,
+                                                                        long long n_events, long long ld, double* __restrict__ x_out,
+                                                                        int* __restrict__ flags)
+{
+    __shared__ int pos_s[MI_WARPS][LGDSP_MI_MAX_THR];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int len = P.len, n_thr = P.n_thr, min_n = P.min_n;
+    int* pos = pos_s[wid];
+    for (long long e = (long long)blockIdx.x * MI_WARPS + wid; e < n_events; e += (long long)gridDim.x * MI_WARPS) {
+        const double* Y = y + e * ld;
+        double ymax = -CUDART_INF;
+        for (int i = lane; i < len; i += 32) ymax = fmax(ymax, Y[i]);
+        ymax = wmax(ymax);                                                            // :31 maximum(Y)
+        for (int j = lane; j < n_thr; j += 32) pos[j] = 1;                            // :55
+        __syncwarp();
+        int cand = 1, ic = 0, i = 0;
+        int counter = (Y[0] >= P.ratios[0] * ymax) ? min_n + 1 : 0;                   // :56
+        while (i < len && ic < n_thr) {                                               // :59-73
+            const double thr = P.ratios[ic] * ymax;
+            const int idx = i + lane;
+            const unsigned m = __ballot_sync(FULLM, idx < len && Y[idx] >= thr);
+            const int steps = min(32, len - i);
+            if (m == 0u) { counter = 0; i += steps; continue; }
+            bool found = false;
+            for (int l = 0; l < steps; ++l) {
+                const bool high = (m >> l) & 1u;
+                if (high && counter == 0) cand = i + l;
+                counter = high ? counter + 1 : 0;
+                if (counter == min_n) { found = true; break; }
+            }
+            if (found) {
+                if (lane == 0) pos[ic] = cand;
+                i = cand;                                                             // :69 restart at the crossing
+                ++ic;
+                counter = 0;
+            } else {
+                i += steps;
+            }
+        }
+        __syncwarp();
+        // :76-79 boundary assertion on the first and the last crossing
+        const int n = P.n;
+        const bool bad = !(pos[0] - n >= 0) || !(pos[n_thr - 1] + n - 1 <= len - 1);
+        if (lane == 0) flags[e] = bad ? 1 : 0;
+        const int nw = 2 * n, m_up = 2 * n * P.rate, md = P.degree + 1;
+        for (int j = lane; j < n_thr; j += 32) {
+            double res = CUDART_NAN;
+            const int from = pos[j] - n, to = pos[j] + n - 1;
+            if (!bad && from >= 0 && to <= len - 1) {
+                const double thr = P.ratios[j] * ymax;
+                double c[LGDSP_MAX_DNI_DEG + 1];
+#pragma unroll
+                for (int q = 0; q <= LGDSP_MAX_DNI_DEG; ++q) {
+                    double a = 0.0;
+                    if (q < md)
+                        for (int r = 0; r < nw; ++r) a = fma(P.A[r * md + q], Y[from + r], a);   // :113-116
+                    c[q] = a;
+                }
+                const double xa = time_at(from, P.t0, P.dt), xb = time_at(to, P.t0, P.dt);
+                const double st = (xb - xa) / (double)(m_up - 1);
+                // _find_intersect_impl(axis, y_up, thr, 1): first k with y_up[k] >= thr after a sample below it
+                double prev = 0.0;
+                bool armed = false;
+                for (int k = 0; k < m_up; ++k) {
+                    const double xu = (double)(2 * n - 1) * (double)k / (double)(m_up - 1);        // range(0, 2n-1, m) :83
+                    double v = 0.0, pw = 1.0;
+#pragma unroll
+                    for (int q = 0; q <= LGDSP_MAX_DNI_DEG; ++q) {
+                        if (q < md) { v = fma(c[q], pw, v); pw *= xu; }                           // :117-119
+                    }
+                    const bool high = v >= thr;
+                    if (high && armed) {
+                        const double tl = time_at(k - 1, xa, st), tr = time_at(k, xa, st);
+                        res = (thr - prev) * (tr - tl) / (v - prev) + tl;
+                        break;
+                    }
+                    armed = !high;
+                    prev = v;
+                }
+            }
+            x_out[e * n_thr + j] = res;
+        }
+        __syncwarp();
+    }
+}
+
 size_t sipm_smem_bytes(int n)
 {
     const int npad = (n + 2 + 1) & ~1;
@@ -603,6 +696,15 @@ void sipm_prim_launch(int mode, const double* d_y, int n, double a, double b, do
                       double* d_out, int* d_n_found, cudaStream_t stream)
 {
     sipm_prim_kernel<<<1, SNT, 0, stream>>>(mode, d_y, n, a, b, t0, dt, min_n, max_n, cap, d_out, d_n_found);
+}
+
+void multi_intersect_launch(const MiDev& P, const double* d_y, long long n_events, long long ld, double* d_x, int* d_flags,
+                            cudaStream_t stream)
+{
+    const long long blocks = (n_events + MI_WARPS - 1) / MI_WARPS;
+    const unsigned grid = (unsigned)(blocks < 148 * 8 ? blocks : 148 * 8);
+    if (grid == 0) return;
+    multi_intersect_kernel<<<grid, MI_WARPS * 32, 0, stream>>>(P, d_y, n_events, ld, d_x, d_flags);
 }
 
 }  // namespace lgdsp

@@ -2,7 +2,8 @@
 `dsp_trap_rt_optimization` (:102-133), `dsp_cusp_rt_optimization` (:145-182), `dsp_zac_rt_optimization` (:193-231),
 `dsp_trap_ft_optimization` (:241-274), `dsp_cusp_ft_optimization` (:286-325), `dsp_zac_ft_optimization` (:336-375),
 `dsp_sg_optimization` (:393-441), plus the batched (rt x ft) grid that callers of the reference build by looping over
-the ft sweep (BASELINE.json config 4).  The `_compressed` and QC-classifier variants are out of scope.
+the ft sweep (BASELINE.json config 4), `dsp_qc_flt_optimization` without a classifier (:9-70) and
+`dsp_qdrift_flt_optimization` (:72-91).  The `_compressed` sweeps and the ML classifier are out of scope.
 """
 from __future__ import annotations
 
@@ -150,3 +151,36 @@ def dsp_sg_optimization(wvfs, config: DSPConfig, τ: Q, pars_filter, *, f_evalua
         aoe = out[:, 1:] / energy[:, None]
     return OrderedDict(aoe=np.ascontiguousarray(aoe), energy=energy, blmean=aux[:, 0].copy(), blslope=aux[:, 1].copy(),
                        t50=aux[:, 2].copy(), qc_label=np.full(sig.shape[0], -1, dtype=np.int64))
+
+
+def dsp_qc_flt_optimization(wvfs, config: DSPConfig, τ: Q, f_evaluate_qc=None, *, device: int = 0,
+                            handle: Optional[Handle] = None):
+    """QC DSP for the filter optimisation without a classifier (src/dsp_filter_optimization.jl:12-14, 31-70): table with
+    energy (trap(rt, ft) of the default filter parameters at t50 + rt + ft/2), blmean, blslope [1/ns], t50 [us],
+    qc_label (-1)"""
+    if f_evaluate_qc is not None:
+        raise NotImplementedError("f_evaluate_qc is not supported; qc_label is -1 as in the reference without a model")
+    w = _as_waveforms(wvfs)
+    rt, ft = config.default_flt_param["trap"]["rt"], config.default_flt_param["trap"]["ft"]     # :57-58
+    var = trap_sweep_variants([rt], [ft], w.step, mode="ft")
+    out, aux = _run_general(w, config, τ, var, f64=True, want_aux=True, device=device, handle=handle)
+    return OrderedDict(energy=out[:, 0].copy(), blmean=aux[:, 0].copy(), blslope=aux[:, 1].copy(), t50=aux[:, 2].copy(),
+                       qc_label=np.full(out.shape[0], -1, dtype=np.int64))
+
+
+def dsp_qdrift_flt_optimization(wvfs, blmean, config: DSPConfig, τ: Q, *, device: int = 0, handle: Optional[Handle] = None,
+                                builders=None) -> np.ndarray:
+    """Q-drift for the filter optimisation (src/dsp_filter_optimization.jl:72-90): the waveforms are shifted by the GIVEN
+    baseline means, pole-zero corrected, t0 and get_qdrift as in dsp_icpc.  Returns qdrift[n_events]."""
+    from .config import resolve_icpc_params
+    w = _as_waveforms(wvfs)
+    sig = _signal_u16(w.signal)
+    bl = np.ascontiguousarray(blmean, dtype=np.float64)
+    if bl.shape != (sig.shape[0],):
+        raise ValueError("blmean must hold one value per waveform")
+    P = resolve_icpc_params(config, τ, None, n_samples=sig.shape[1], t_first=w.t_first, step=w.step,
+                            groups=_abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_QDRIFT, builders=builders)
+    h = handle or get_handle(device)
+    rows = np.zeros((sig.shape[0], _abi.NCOL))
+    h.icpc_run_ext_host(P, sig.ctypes.data, 2, bl.ctypes.data, sig.shape[0], sig.strides[0] // 2, rows.ctypes.data)
+    return np.ascontiguousarray(rows[:, _abi.COL["qdrift"]])

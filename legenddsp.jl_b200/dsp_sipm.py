@@ -204,3 +204,51 @@ class IntersectMaximum:
             if r["multiplicity"] <= max_triggers:
                 return r
             max_triggers = r["multiplicity"]
+
+
+class MultiIntersect:
+    """MultiIntersect(threshold_ratios, mintot, n, d, sampling_rate)(waveforms)  (src/multi_intersect.jl:10-34): the
+    times [ns] at which every waveform first exceeds ratio * maximum, x[n_events, n_ratios] (a single trace gives x[n_ratios])"""
+
+    def __init__(self, threshold_ratios=None, mintot: Q = ns(64.0), n: int = 1, d: int = 1, sampling_rate: int = 1):
+        self.threshold_ratios = (np.arange(1, 91) * 0.01 if threshold_ratios is None      # collect(0.01:0.01:0.9)
+                                 else np.asarray(threshold_ratios, dtype=np.float64))
+        self.mintot, self.n, self.d, self.sampling_rate = mintot, int(n), int(d), int(sampling_rate)
+
+    def params(self, n_samples: int, t_first: Q, step: Q, builders=None) -> _abi.MultiIntersectParams:
+        if builders is None:
+            builders = LibBuilders()
+        r = self.threshold_ratios
+        if not (1 <= len(r) <= _abi.MI_MAX_THR):
+            raise ValueError("number of threshold ratios outside 1..%d" % _abi.MI_MAX_THR)
+        if not (1 <= self.n <= _abi.MI_MAX_HALF) or not (0 <= self.d <= _abi.LGDSP_MAX_DNI_DEG) or self.d >= 2 * self.n \
+                or self.sampling_rate < 1 or 2 * self.n * self.sampling_rate > 256:
+            raise ValueError("polynomial window / degree / sampling rate outside the supported range")
+        P = _abi.MultiIntersectParams()
+        P.struct_size, P.version = C.sizeof(_abi.MultiIntersectParams), _abi.LGDSP_PARAMS_VERSION
+        P.n_samples, P.n_thresholds = int(n_samples), len(r)
+        P.t_first_ns, P.dt_ns = t_first.ns(), step.ns()
+        P.min_n = _min_n(self.mintot, step)                       # max(1, round(Int, mintot / step))  :29-30
+        P.half_window, P.degree, P.rate = self.n, self.d, self.sampling_rate
+        for j, v in enumerate(r):
+            P.ratios[j] = float(v)
+        A = builders.lsq_fit_matrix(2 * self.n, self.d)           # _lsq_fit_matrix(0:2n-1, degree)  :80
+        for i, v in enumerate(np.asarray(A).reshape(-1)):
+            P.A[i] = float(v)
+        return P
+
+    def __call__(self, signal, *, t_first: Q = ns(0.0), step: Q = ns(16.0), device: int = 0, handle: Optional[Handle] = None,
+                 builders=None):
+        y = np.asarray(signal, dtype=np.float64)
+        single = y.ndim == 1
+        y = np.ascontiguousarray(y.reshape(1, -1) if single else y)
+        if y.shape[1] == 0:                                       # isempty(Y) && return intersect_x  :50
+            x = np.zeros((y.shape[0], len(self.threshold_ratios)))
+            return x[0] if single else x
+        P = self.params(y.shape[1], t_first, step, builders)
+        x = np.zeros((y.shape[0], P.n_thresholds))
+        flags = np.zeros(y.shape[0], dtype=np.int32)
+        (handle or get_handle(device)).multi_intersect_host(P, y.ctypes.data, y.shape[0], y.shape[1], x.ctypes.data, flags.ctypes.data)
+        if flags.any():
+            raise AssertionError("cannot interpolate intersect on left boundary")       # :85-88
+        return x[0] if single else x

@@ -1149,6 +1149,97 @@ ORC_API int orc_dsp_sipm(const lgdsp_sipm_params* P, const void* wf, int64_t n_e
     return used;
 }
 
+/* dsp_qdrift_flt_optimization  src/dsp_filter_optimization.jl:72-90: external baseline, pole-zero, t0, Q-drift.
+ * out: double[n_events][2] = (qdrift, t0 [us]) */
+ORC_API int orc_qdrift_flt_optimization(const lgdsp_icpc_params* P, const uint16_t* wf, int64_t n_events, int64_t ld,
+                                        const double* blmean, double* out, int n_threads)
+{
+    int used = 1;
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+    used = n_threads;
+#pragma omp parallel num_threads(n_threads)
+#endif
+    {
+        const int n = P->n_samples;
+        double* w = (double*)malloc(sizeof(double) * 2 * (size_t)n);
+        double* flt = w + n;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+        for (int64_t e = 0; e < n_events; ++e) {
+            const uint16_t* raw = wf + e * ld;
+            double shift = -blmean[e];                                                  /* :78 */
+            for (int i = 0; i < n; ++i) w[i] = (double)raw[i] + shift;
+            orc_invcr(w, n, P->pz_km1, flt);                                            /* :82-83 */
+            memcpy(w, flt, sizeof(double) * (size_t)n);
+            int pos;
+            double t0 = orc_get_t0(w, n, P->t_first_ns, P->dt_ns, &P->t0_trap, P->t0_threshold, P->t0_min_n, flt, &pos);  /* :86 */
+            orc_integrator(w, n, 1.0, flt);
+            out[2 * e] = orc_get_qdrift(flt, n, P->t_first_ns, P->dt_ns, &P->int_dni, t0, P->qdrift_first_ns, P->qdrift_last_ns); /* :89 */
+            out[2 * e + 1] = t0;
+        }
+        free(w);
+    }
+    return used;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * MultiIntersect  src/multi_intersect.jl:10-121: first crossings of thresholds ratios[j] * maximum(Y) with local
+ * polynomial up-sampling.  A: _lsq_fit_matrix(0:2n-1, degree), row-major (2n) x (degree+1) [RDDSP].
+ * x: double[n_thr].  Returns 0, or -1 when the reference's boundary assertion (:85-88) fails.
+ * ------------------------------------------------------------------------------------------------ */
+ORC_API int orc_multi_intersect(const double* Y, int len, double t0, double dt, const double* ratios, int n_thr, int min_n,
+                                int n, int degree, int rate, const double* A, double* x)
+{
+    for (int j = 0; j < n_thr; ++j) x[j] = 0.0;
+    if (len <= 0) return 0;                                                          /* :50 */
+    double ymax = Y[0];
+    for (int i = 1; i < len; ++i) if (Y[i] > ymax) ymax = Y[i];
+    double* thr = (double*)malloc(sizeof(double) * (size_t)n_thr);
+    int* pos = (int*)malloc(sizeof(int) * (size_t)n_thr);
+    for (int j = 0; j < n_thr; ++j) { thr[j] = ratios[j] * ymax; pos[j] = 1; }         /* :31, :55 (0-based firstindex+1) */
+    int cand = 1, ic = 0, i = 0;
+    int64_t counter = (Y[0] >= thr[0]) ? (int64_t)min_n + 1 : 0;                       /* :56 */
+    while (i < len && ic < n_thr) {                                                  /* :59-73 */
+        int high = Y[i] >= thr[ic];
+        int first_high = counter == 0;
+        if (high && first_high) cand = i;
+        counter = high ? counter + 1 : 0;
+        int found = counter == min_n;
+        if (found) pos[ic] = cand;
+        i = found ? pos[ic] : i + 1;
+        if (found) { ic += 1; counter = 0; }
+    }
+    int rc = 0;
+    if (!(pos[0] - n >= 0) || !(pos[n_thr - 1] + n - 1 <= len - 1)) rc = -1;            /* :76-79 */
+    if (rc == 0) {
+        int nw = 2 * n, m = 2 * n * rate, md = degree + 1;
+        double* yup = (double*)malloc(sizeof(double) * (size_t)m);
+        for (int j = 0; j < n_thr; ++j) {
+            int from = pos[j] - n, to = pos[j] + n - 1;
+            if (from < 0 || to > len - 1) { x[j] = NAN; continue; }   /* (@inbounds in the reference: undefined; flagged NaN here) */
+            for (int k = 0; k < m; ++k) yup[k] = 0.0;
+            for (int q = 0; q < md; ++q) {                                            /* _lsqfitatwindow! :108-121 */
+                double c = 0.0;
+                for (int r = 0; r < nw; ++r) c = fma(A[r * md + q], Y[from + r], c);
+                for (int k = 0; k < m; ++k) {
+                    double xu = (double)(2 * n - 1) * (double)k / (double)(m - 1);     /* range(0, 2n-1, m) :83 */
+                    yup[k] = fma(c, pow(xu, (double)q), yup[k]);
+                }
+            }
+            /* _find_intersect_impl(_x_axis, y_up, thresholds[j], 1).x on the axis range(X[from], X[to], m) */
+            double xa = t0 + from * dt, xb = t0 + to * dt, st = (xb - xa) / (double)(m - 1);
+            int64_t mult;
+            int p;
+            x[j] = orc_intersect(yup, m, xa, st, thr[j], 1, &mult, &p);
+        }
+        free(yup);
+    }
+    free(thr); free(pos);
+    return rc;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * trapezoid sweeps  src/dsp_filter_optimization.jl:102-133 (rt, fixed pick-off) and :241-274 (ft, t50-based)
  * out: float[n_events][n_variants] (= column-major Julia matrix n_variants x n_events)

@@ -294,6 +294,34 @@ def dsp_sipm(params, wf, n_threads=0):
     return rows, trig
 
 
+def qdrift_flt_optimization(params, wf_u16, blmean, n_threads=0):
+    """oracle dsp_qdrift_flt_optimization (src/dsp_filter_optimization.jl:72-90): (qdrift[n_events], t0_us[n_events])"""
+    wf = np.ascontiguousarray(wf_u16, dtype=np.uint16)
+    bl = np.ascontiguousarray(blmean, dtype=np.float64)
+    out = np.zeros((wf.shape[0], 2))
+    L = lib()
+    L.orc_qdrift_flt_optimization.argtypes = [C.POINTER(_abi.IcpcParams), C.c_void_p, C.c_int64, C.c_int64, _dp, _dp, C.c_int]
+    L.orc_qdrift_flt_optimization(C.byref(params), wf.ctypes.data, wf.shape[0], wf.shape[1], bl.ctypes.data_as(_dp),
+                                  out.ctypes.data_as(_dp), int(n_threads))
+    return out[:, 0].copy(), out[:, 1].copy()
+
+
+def multi_intersect(y, t0, dt, ratios, min_n, n=1, degree=1, rate=1):
+    """MultiIntersect (src/multi_intersect.jl:10-121) on one trace: x[n_thr]; raises AssertionError like the reference (:85-88)"""
+    y, p = _d(y)
+    r = np.ascontiguousarray(ratios, dtype=np.float64)
+    A = OracleBuilders().lsq_fit_matrix(2 * n, degree)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    x = np.zeros(len(r))
+    L = lib()
+    L.orc_multi_intersect.argtypes = [_dp, C.c_int, C.c_double, C.c_double, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]
+    rc = L.orc_multi_intersect(p, y.size, float(t0), float(dt), r.ctypes.data_as(_dp), len(r), int(min_n), int(n), int(degree),
+                               int(rate), A.ctypes.data_as(_dp), x.ctypes.data_as(_dp))
+    if rc != 0:
+        raise AssertionError("cannot interpolate intersect on left boundary")
+    return x
+
+
 def trap_sweep(sparams, wf_u16, variants, n_threads=0):
     wf = np.ascontiguousarray(wf_u16, dtype=np.uint16)
     n_ev, ld = wf.shape

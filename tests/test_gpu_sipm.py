@@ -191,3 +191,39 @@ def test_dsp_sipm_capacity_and_errors(L, O, handle):
         L.sipm_rows(wf, bad, handle=handle)
     empty = L.dsp_sipm({"waveform": L.RDWaveforms(np.zeros((0, 6250), np.uint16))}, cfg, {"sg": {"wl": L.ns(200.0)}}, handle=handle)
     assert len(empty["t_max"]) == 0 and len(empty["trig_pos"]) == 0
+
+
+def test_multi_intersect(L, O, handle, kat):
+    """MultiIntersect: the reference's tests (test/test_multiintersect.jl:8-26: linear ramp, thresholds 10..90 % -> 10..90 s;
+    one ratio == Intersect) and the oracle on noisy pulses with polynomial up-sampling"""
+    k = kat["intersect_ramp"]
+    ramp = np.array(k["signal"], dtype=np.float64)
+    f = L.MultiIntersect(threshold_ratios=[0.1 * q for q in range(1, 10)], mintot=L.ns(1.0))
+    x = f(ramp, t_first=L.ns(k["t0"]), step=L.ns(k["dt"]), handle=handle, builders=O.OracleBuilders())
+    assert np.allclose(x, [c["x"] for c in k["cases"]])                                   # :18-24
+    x1 = L.MultiIntersect(threshold_ratios=[0.5], mintot=L.ns(1.0))(ramp, t_first=L.ns(1.0), step=L.ns(1.0), handle=handle)
+    assert np.isclose(x1[0], O.intersect(ramp, 1.0, 1.0, 50.0, 1)["x"])                    # :9-14
+    # batch of noisy PZ-like pulses, default ratios 0.01:0.01:0.9, several (n, d, rate)
+    rng = np.random.default_rng(8)
+    n_ev, n = 96, 2000
+    kk = np.arange(n)
+    Y = np.empty((n_ev, n))
+    for e in range(n_ev):
+        s0, rise, amp = rng.integers(300, 900), rng.integers(10, 120), rng.uniform(50, 5000)
+        Y[e] = amp * np.clip((kk - s0) / rise, 0, 1) + rng.normal(0, 1.0, n)
+    for (hw, d, rate, mintot) in ((1, 1, 1, 64.0), (2, 2, 4, 32.0), (4, 3, 8, 16.0)):
+        f = L.MultiIntersect(mintot=L.ns(mintot), n=hw, d=d, sampling_rate=rate)
+        got = f(Y, t_first=L.ns(8.0), step=L.ns(16.0), handle=handle, builders=O.OracleBuilders())
+        for e in range(n_ev):
+            ref = O.multi_intersect(Y[e], 8.0, 16.0, f.threshold_ratios, max(1, round(mintot / 16.0)), hw, d, rate)
+            assert np.array_equal(np.isnan(got[e]), np.isnan(ref)), (hw, e)
+            ok = ~np.isnan(ref)
+            assert np.allclose(got[e][ok], ref[ok], rtol=0, atol=1e-6), (hw, e, np.abs(got[e][ok] - ref[ok]).max())
+        assert np.isfinite(got).mean() > 0.9
+    # boundary assertion (:85-88): a trace whose last threshold is never reached keeps the default position 2 -> with n = 2
+    # the left boundary check fails
+    flat = np.zeros((1, 500)); flat[0, 0] = 1.0
+    with pytest.raises(AssertionError):
+        L.MultiIntersect(threshold_ratios=[0.5, 2.0], mintot=L.ns(16.0), n=2, d=1)(flat, handle=handle)
+    with pytest.raises(AssertionError):
+        O.multi_intersect(flat[0], 0.0, 16.0, [0.5, 2.0], 1, 2, 1, 1)

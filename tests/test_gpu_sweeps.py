@@ -139,3 +139,29 @@ def test_dsp_puls_and_decay_times(L, O, handle):
     assert np.allclose(inv(tau), inv(ref_tau), rtol=1e-7, atol=1e-10)
     good = (full[:, L.COL["e_max"]] > 5000) & (full[:, L.COL["n_sat_high"]] == 0) & (full[:, L.COL["inTrace_n"]] == 1)
     assert abs(np.median(tau[good]) - 500.0) < 5.0       # the generator's decay constant
+
+
+def test_qc_and_qdrift_flt_optimization(L, O, handle):
+    """dsp_qc_flt_optimization without a classifier (src/dsp_filter_optimization.jl:12-14, 31-70) and
+    dsp_qdrift_flt_optimization (:72-90, external baseline) against the oracle"""
+    cfg, tau = L.tiefree_config(), L.us(500.0)
+    wf = L.synth.generate_host(300, first_event=4321)
+    W = L.RDWaveforms(wf)
+    tbl = L.dsp_qc_flt_optimization(W, cfg, tau, None, handle=handle)
+    assert list(tbl.keys()) == ["energy", "blmean", "blslope", "t50", "qc_label"] and (tbl["qc_label"] == -1).all()
+    S = L.resolve_sweep_params(cfg, tau, builders=O.OracleBuilders(), out_f64=True)
+    rt, ft = cfg.default_flt_param["trap"]["rt"], cfg.default_flt_param["trap"]["ft"]
+    var = L.trap_sweep_variants([rt], [ft], L.ns(16.0), mode="ft")
+    ref, aux = O.sweep(S, wf, var.array, want_aux=True)
+    assert np.allclose(tbl["energy"], ref[:, 0], rtol=1e-9, atol=1e-7)
+    assert np.array_equal(tbl["blmean"], aux[:, 0]) and np.allclose(tbl["blslope"], aux[:, 1], rtol=1e-9, atol=1e-15)
+    assert np.allclose(tbl["t50"], aux[:, 2], rtol=0, atol=1e-7)
+    # Q-drift with the baseline of a previous pass (here: blmean + an offset, so that the external value matters)
+    bl = tbl["blmean"] + np.linspace(-1.5, 1.5, len(wf))
+    q = L.dsp_qdrift_flt_optimization(W, bl, cfg, tau, handle=handle, builders=O.OracleBuilders())
+    P = L.resolve_icpc_params(cfg, tau, builders=O.OracleBuilders())
+    qref, t0ref = O.qdrift_flt_optimization(P, wf, bl)
+    assert np.allclose(q, qref, rtol=1e-9, atol=1e-3)
+    assert (t0ref > 0).sum() > 200
+    with pytest.raises(ValueError):
+        L.dsp_qdrift_flt_optimization(W, bl[:-1], cfg, tau, handle=handle)
