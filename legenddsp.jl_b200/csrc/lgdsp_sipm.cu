@@ -123,28 +123,59 @@ __device__ __forceinline__ int block_exscan(int v, int& total, Scratch& S)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// exact order statistics: the k-th smallest (0-based) of { v : elem(i, v) } and, if want2, the (k+1)-th.
-// elem(i, v) -> bool: whether sample i takes part, and its value.  [lo, hi]: minimum / maximum of the population.
+// exact order statistics.  The population is described by data, not by a functor, so that ONE copy of the selection code
+// serves all eight medians of the chain (instruction-cache footprint): sample i has the raw value y = sgn * tr[i], takes
+// part if mn <= y <= mx, and enters with the value y (mode 0) or |y - med| (mode 1).
+// SH: the trace lives in shared memory (LDS) or in global memory (single-trace entry).
 // ---------------------------------------------------------------------------------------------------
-template <class Elem>
-__device__ void block_select(Elem elem, int n, long long k, bool want2, double lo, double hi, Scratch& S, double& v1, double& v2)
+struct Sel {
+    const double* tr;
+    double sgn, mn, mx, med;
+    int mode;
+};
+template <bool SH>
+__device__ __forceinline__ bool sel_elem(const Sel& s, int i, double& v)
+{
+    double raw;
+    if (SH) {
+        const unsigned a = (unsigned)__cvta_generic_to_shared(s.tr + i);
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(raw) : "r"(a));
+    } else {
+        raw = s.tr[i];
+    }
+    const double y = raw * s.sgn;
+    v = s.mode ? fabs(y - s.med) : y;
+    return s.mn <= y && y <= s.mx;
+}
+
+// Statistics.median of the population (middle element, or x/2 + y/2 of the two middle ones).
+// [lo, hi]: bounds of the population (every value lies inside; the tighter, the fewer refinement levels).
+// m: size of the population if known, else -1 (taken from the first histogram).  binbuf (optional, n entries of shared
+// memory): the histogram pass leaves every sample's bin there, so that the gather pass is a 16-bit compare per sample.
+// Returns the median; m_out = size of the population (0: empty, the return value is 0).
+template <bool SH>
+__device__ __noinline__ double block_median(const Sel sel, int n, double lo, double hi, long long m, unsigned short* binbuf, Scratch& S,
+                                            long long& m_out)
 {
     const int tid = threadIdx.x;
+    long long k = m >= 0 ? (m - 1) / 2 : 0;
+    bool want2 = m >= 0 ? ((m & 1) == 0) : false;
     bool need_next = false;    // v2 is the smallest element above `above`
-    double above = 0.0;
+    double above = 0.0, v1 = 0.0, v2 = 0.0;
     for (;;) {
         if (lo == hi) {
-            // every remaining candidate has the same value; count them for the second rank
-            v1 = lo;
-            if (!want2) { v2 = lo; break; }
+            // every remaining candidate has the same value; count them (population size / second rank)
             long long c = 0;
             double dmn = 0, dmx = 0;
             for (int i = tid; i < n; i += SNT) {
                 double v;
-                if (elem(i, v) && v == lo) ++c;
+                if (sel_elem<SH>(sel, i, v) && v == lo) ++c;
             }
             block_cnt_min_max(c, dmn, dmx, S);
-            if (k + 1 < c) v2 = lo;
+            if (m < 0) { m = c; k = (m - 1) / 2; want2 = (m & 1) == 0; }
+            if (m == 0) { m_out = 0; return 0.0; }
+            v1 = lo;
+            if (!want2 || k + 1 < c) v2 = lo;
             else { need_next = true; above = lo; }
             break;
         }
@@ -160,7 +191,9 @@ __device__ void block_select(Elem elem, int n, long long k, bool want2, double l
         };
         for (int i = tid; i < n; i += SNT) {
             double v;
-            if (elem(i, v) && v >= lo && v <= hi) atomicAdd(&S.hist[bin_of(v)], 1u);
+            int b = 0xFFFF;
+            if (sel_elem<SH>(sel, i, v) && v >= lo && v <= hi) { b = bin_of(v); atomicAdd(&S.hist[b], 1u); }
+            if (binbuf) binbuf[i] = (unsigned short)b;
         }
         __syncthreads();
         // the bin that holds rank k
@@ -170,6 +203,8 @@ __device__ void block_select(Elem elem, int n, long long k, bool want2, double l
         for (int q = 0; q < BPT; ++q) { local[q] = S.hist[tid * BPT + q]; mine += (int)local[q]; }
         int total;
         const int before = block_exscan(mine, total, S);
+        if (m < 0) { m = total; k = (m - 1) / 2; want2 = (m & 1) == 0; }
+        if (m == 0) { m_out = 0; return 0.0; }
         if ((long long)before <= k && k < (long long)before + mine) {
             int cum = before;
 #pragma unroll
@@ -182,11 +217,15 @@ __device__ void block_select(Elem elem, int n, long long k, bool want2, double l
         __syncthreads();
         const int bsel = S.ibuf[0], cum_before = S.ibuf[1], cnt_b = S.ibuf[2];
         k -= cum_before;
+        auto in_bin = [&](int i, double& v) -> bool {
+            if (binbuf) return binbuf[i] == (unsigned short)bsel && (sel_elem<SH>(sel, i, v), true);
+            return sel_elem<SH>(sel, i, v) && v >= lo && v <= hi && bin_of(v) == bsel;
+        };
         if (cnt_b <= CANDCAP) {
             // gather the bin and rank its elements (ties broken by slot: equal values get consecutive ranks)
             for (int i = tid; i < n; i += SNT) {
                 double v;
-                if (elem(i, v) && v >= lo && v <= hi && bin_of(v) == bsel) S.cand[atomicAdd(&S.ibuf[3], 1)] = v;
+                if (in_bin(i, v)) S.cand[atomicAdd(&S.ibuf[3], 1)] = v;
             }
             __syncthreads();
             if (tid < cnt_b) {
@@ -213,7 +252,7 @@ __device__ void block_select(Elem elem, int n, long long k, bool want2, double l
         double mn = CUDART_INF, mx = -CUDART_INF;
         for (int i = tid; i < n; i += SNT) {
             double v;
-            if (elem(i, v) && v >= lo && v <= hi && bin_of(v) == bsel) { mn = fmin(mn, v); mx = fmax(mx, v); ++c; }
+            if (in_bin(i, v)) { mn = fmin(mn, v); mx = fmax(mx, v); ++c; }
         }
         block_cnt_min_max(c, mn, mx, S);
         lo = mn; hi = mx;
@@ -223,41 +262,43 @@ __device__ void block_select(Elem elem, int n, long long k, bool want2, double l
         double mn = CUDART_INF, mx = 0;
         for (int i = tid; i < n; i += SNT) {
             double v;
-            if (elem(i, v) && v > above) mn = fmin(mn, v);
+            if (sel_elem<SH>(sel, i, v) && v > above) mn = fmin(mn, v);
         }
         block_cnt_min_max(c, mn, mx, S);
         v2 = mn;
     }
+    m_out = m;
+    return want2 ? v1 / 2 + v2 / 2 : v1;
 }
 
-// Statistics.median of { v : elem(i, v) }: middle element or x/2 + y/2 of the two middle ones; `empty` if there is none
-template <class Elem>
-__device__ double block_median(Elem elem, int n, Scratch& S, bool& empty)
+// _thresholdstats_mad_impl  src/thresholdstats.jl:61-71 on the trace y_i = sgn * tr[i], i < n
+template <bool SH>
+__device__ __noinline__ double block_thresholdstats_mad(const double* tr, double sgn, int n, double mn, double mx, unsigned short* binbuf,
+                                                        Scratch& S)
 {
-    long long m = 0;
-    double mn = CUDART_INF, mx = -CUDART_INF;
-    for (int i = threadIdx.x; i < n; i += SNT) {
-        double v;
-        if (elem(i, v)) { ++m; mn = fmin(mn, v); mx = fmax(mx, v); }
+    Sel sel{tr, sgn, mn, mx, 0.0, 0};
+    double lo = mn, hi = mx;
+    long long m = -1;
+    if (!(fabs(mn) < CUDART_INF && fabs(mx) < CUDART_INF)) {
+        // open bounds: one pass for the size, minimum and maximum of the population
+        m = 0;
+        lo = CUDART_INF; hi = -CUDART_INF;
+        for (int i = threadIdx.x; i < n; i += SNT) {
+            double v;
+            if (sel_elem<SH>(sel, i, v)) { ++m; lo = fmin(lo, v); hi = fmax(hi, v); }
+        }
+        block_cnt_min_max(m, lo, hi, S);
+        if (m == 0) return 0.0;
+    } else if (mn > mx) {
+        return 0.0;
     }
-    block_cnt_min_max(m, mn, mx, S);
-    empty = (m == 0);
-    if (empty) return 0.0;
-    const bool even = (m & 1) == 0;
-    double v1, v2;
-    block_select(elem, n, (m - 1) / 2, even, mn, mx, S, v1, v2);
-    return even ? v1 / 2 + v2 / 2 : v1;
-}
-
-// _thresholdstats_mad_impl  src/thresholdstats.jl:61-71 on the trace val(i), i < n
-template <class Val>
-__device__ double block_thresholdstats_mad(Val val, int n, double mn, double mx, Scratch& S)
-{
-    bool empty;
-    const double med = block_median([&](int i, double& v) { v = val(i); return mn <= v && v <= mx; }, n, S, empty);
-    if (empty) return 0.0;                                                                        // :63
-    const double mad = block_median([&](int i, double& v) { const double y = val(i); v = fabs(y - med); return mn <= y && y <= mx; },
-                                    n, S, empty);
+    long long m1, m2;
+    const double med = block_median<SH>(sel, n, lo, hi, m, binbuf, S, m1);
+    if (m1 == 0) return 0.0;                                                                      // :63
+    // the absolute deviations lie in [0, max(med - lo, hi - med)]: no min/max pass
+    sel.med = med;
+    sel.mode = 1;
+    const double mad = block_median<SH>(sel, n, 0.0, fmax(med - lo, hi - med), m1, binbuf, S, m2);
     return 1.4826 * mad;                                                                          // :70
 }
 
@@ -490,7 +531,7 @@ __global__ void __launch_bounds__(SNT, 2) sipm_kernel(const __grid_constant__ Si
         }
         __syncthreads();
         // :103-105
-        const double thr = block_thresholdstats_mad([&](int i) { return bufA[i]; }, n_sg, P.sg_min_thr, P.sg_max_thr, S);
+        const double thr = block_thresholdstats_mad<true>(bufA, 1.0, n_sg, P.sg_min_thr, P.sg_max_thr, reinterpret_cast<unsigned short*>(bufB), S);
         if (tid == 0) S.dbuf[4] = 0.0;
         __syncthreads();
         const int nt0 = block_intersect_maximum([&](int i) { return bufA[i]; }, n_sg, t_sg, P.dt, P.sg_nsigma * thr, P.sg_min_n, P.sg_max_n,
@@ -512,11 +553,11 @@ __global__ void __launch_bounds__(SNT, 2) sipm_kernel(const __grid_constant__ Si
         }
         // :118-121 discharges: flipped integrated waveform
         auto flip = [&](int i) { return bufB[i] * -1.0; };
-        const double thr_dc = block_thresholdstats_mad(flip, n_sg, P.sg_min_dc, P.sg_max_dc, S);
+        const double thr_dc = block_thresholdstats_mad<true>(bufB, -1.0, n_sg, P.sg_min_dc, P.sg_max_dc, reinterpret_cast<unsigned short*>(bufA), S);
         const int nt1 = block_intersect_maximum(flip, n_sg, t_sg, P.dt, P.sg_nsigma_dc * thr_dc, P.sg_min_n, P.sg_max_n, cap,
                                                 tg + (size_t)1 * LGDSP_SIPM_NFIELD * cap, mask, S, nullptr);
         // :138-139 (the SG pipeline's IntersectMaximum with the trap pipeline's discharge bounds)
-        const double thr_dct = block_thresholdstats_mad(flip, n_sg, P.trap_min_dc, P.trap_max_dc, S);
+        const double thr_dct = block_thresholdstats_mad<true>(bufB, -1.0, n_sg, P.trap_min_dc, P.trap_max_dc, reinterpret_cast<unsigned short*>(bufA), S);
         const int nt3 = block_intersect_maximum(flip, n_sg, t_sg, P.dt, P.trap_nsigma_dc * thr_dct, P.sg_min_n, P.sg_max_n, cap,
                                                 tg + (size_t)3 * LGDSP_SIPM_NFIELD * cap, mask, S, nullptr);
         // :125-126 pole-zero: y[i] = x[i] + km1 * cumsum(x)[i]
@@ -533,7 +574,7 @@ __global__ void __launch_bounds__(SNT, 2) sipm_kernel(const __grid_constant__ Si
         }
         __syncthreads();
         // :133-135
-        const double thr_tr = block_thresholdstats_mad([&](int i) { return bufA[i]; }, n_tr, P.trap_min_thr, P.trap_max_thr, S);
+        const double thr_tr = block_thresholdstats_mad<true>(bufA, 1.0, n_tr, P.trap_min_thr, P.trap_max_thr, reinterpret_cast<unsigned short*>(bufB), S);
         const int nt2 = block_intersect_maximum([&](int i) { return bufA[i]; }, n_tr, t_tr, P.dt, P.trap_nsigma * thr_tr, P.trap_min_n,
                                                 P.trap_max_n, cap, tg + (size_t)2 * LGDSP_SIPM_NFIELD * cap, mask, S, nullptr);
         if (tid == 0) {
@@ -558,7 +599,7 @@ __global__ void __launch_bounds__(SNT) sipm_prim_kernel(int mode, const double* 
         const double r = block_thresholdstats(val, n, a, b, S);
         if (threadIdx.x == 0) out[0] = r;
     } else if (mode == 1) {
-        const double r = block_thresholdstats_mad(val, n, a, b, S);
+        const double r = block_thresholdstats_mad<false>(y, 1.0, n, a, b, nullptr, S);
         if (threadIdx.x == 0) out[0] = r;
     } else {
         const int c = block_intersect_maximum(val, n, t0, dt, a, min_n, max_n, cap, out, mask, S, nullptr);
