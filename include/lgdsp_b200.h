@@ -94,8 +94,9 @@ enum lgdsp_col {
 #define LGDSP_GROUP_TRAPS  0x04u  /* e_10410, e_535, e_313, *_inv, e_trap, e_trap_max, t_trap_max */
 #define LGDSP_GROUP_QDRIFT 0x08u  /* qdrift, lq */
 #define LGDSP_GROUP_CUSPZAC 0x10u /* e_cusp, e_zac, e_*_max, t_*_max */
-#define LGDSP_GROUP_CURRENT 0x20u /* a_sg, a_60, a_100, a_raw, inTrace_*, t50_current */
-#define LGDSP_GROUP_ALL    0x3Fu
+#define LGDSP_GROUP_CURRENT 0x20u /* a_sg, a_60, a_100, a_raw */
+#define LGDSP_GROUP_INTRACE 0x40u /* inTrace_intersect, inTrace_n, t50_current (masks on the sg[0] trace) */
+#define LGDSP_GROUP_ALL    0x7Fu
 #define LGDSP_GROUP_PZTRAP (LGDSP_GROUP_BASE | LGDSP_GROUP_TIMING | LGDSP_GROUP_TRAPS)
 
 /* TrapezoidalChargeFilter(avgtime, gaptime, avgtime2) in samples [RDDSP]:

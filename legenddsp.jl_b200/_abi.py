@@ -25,7 +25,8 @@ GROUP_TRAPS = 0x04
 GROUP_QDRIFT = 0x08
 GROUP_CUSPZAC = 0x10
 GROUP_CURRENT = 0x20
-GROUP_ALL = 0x3F
+GROUP_INTRACE = 0x40
+GROUP_ALL = 0x7F
 GROUP_PZTRAP = GROUP_BASE | GROUP_TIMING | GROUP_TRAPS
 
 # computed columns of dsp_icpc in the order of /root/reference/src/dsp_icpc.jl:210-229

@@ -373,7 +373,7 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
     if role not in ("full", "pre", "wdw"):
         raise ValueError(f"unknown role {role!r}")
     if role == "pre":
-        groups = _abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_TRAPS | _abi.GROUP_CUSPZAC | _abi.GROUP_CURRENT
+        groups = _abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_TRAPS | _abi.GROUP_CUSPZAC | _abi.GROUP_INTRACE
     elif role == "wdw":
         groups = _abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_QDRIFT | _abi.GROUP_CURRENT
     dummy_trap = _abi.Trap(1, 0, 1, 0)
@@ -419,7 +419,8 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
     else:
         P.t0_trap = _trap(fp[0], fp[1], step, fp[2])
         P.t0inv_trap = _trap(ns(40.0), ns(100.0), step, ns(2000.0))   # default flt_pars, src/dsp_icpc.jl:207
-    P.t0_threshold = float(cfg.t0_threshold)
+    # the presummed pass has no t0 (its trapezoid is a placeholder): a threshold nothing reaches keeps the crossing search idle
+    P.t0_threshold = 1e300 if role == "pre" else float(cfg.t0_threshold)
     P.t0_min_n = _min_n(kw["t0_mintot"], step)
     P.tx_min_n = _min_n(kw["tx_mintot"], step)
     for i, f in enumerate((0.1, 0.5, 0.8, 0.9, 0.99)):

@@ -1315,18 +1315,20 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
         // argmax, baseline-window sums; the chunk maximum is kept for the mask pass
         double sgcmax = -CUDART_INF;
         const int nsg = P.sg[0].nout;
-        if (G & LGDSP_GROUP_CURRENT) {
+        const bool want_cur = (G & LGDSP_GROUP_CURRENT) != 0, want_intr = (G & LGDSP_GROUP_INTRACE) != 0;
+        if (want_cur || want_intr) {
             double cmax[4] = {-CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF};
             int carg[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
             double sg_S = 0, sg_SS = 0;
             // (a) whole trace, one chunk per thread: only the chunk maximum (uniform cost for every thread)
-            sg_chunk(TT, P.sg[0], i0, min(CH, nsg - i0), [&](int k, double s) { sgcmax = s > sgcmax ? s : sgcmax; });
+            if (want_intr) sg_chunk(TT, P.sg[0], i0, min(CH, nsg - i0), [&](int k, double s) { sgcmax = s > sgcmax ? s : sgcmax; });
             SECT(12);
             // (b) windowed quantities, strided over the block (same operation order as the chunk pass: identical values):
             //     first argmax of sg[0..2] and of the plain derivative inside the current window, baseline-window sums of sg[0]
 #pragma unroll 1
             for (int f = 0; f < 3; ++f) {
                 if (f > 0 && P.sg_alias[f] >= 0) continue;   // identical to an earlier filter: copied after the reduction
+                if (f > 0 && !want_cur) continue;            // only the in-trace statistics of sg[0] are wanted
                 double bm = -CUDART_INF;
                 int ba = 0x7fffffff;
                 if (P.sg[f].n_taps + 1 <= 8) {
@@ -1341,12 +1343,14 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
                         a0 = fma(g[6], p[6], a0); a1 = fma(g[7], p[7], a1);
                         return a0 + a1;
                     };
+                    if (want_cur) {
 #pragma unroll 2
-                    for (int j = P.cur_from[f] + tid; j <= P.cur_until[f]; j += NT) {
-                        const double v = ev(j);
-                        if (v > bm) { bm = v; ba = j; }
+                        for (int j = P.cur_from[f] + tid; j <= P.cur_until[f]; j += NT) {
+                            const double v = ev(j);
+                            if (v > bm) { bm = v; ba = j; }
+                        }
                     }
-                    if (f == 0) {
+                    if (f == 0 && want_intr) {
 #pragma unroll 2
                         for (int j = P.intr_from + tid; j <= P.intr_until; j += NT) {
                             const double v = ev(j);
@@ -1355,12 +1359,14 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
                         }
                     }
                 } else {
+                    if (want_cur) {
 #pragma unroll 1
-                    for (int j = P.cur_from[f] + tid; j <= P.cur_until[f]; j += NT) {
-                        const double v = sg_at(f, j);
-                        if (v > bm) { bm = v; ba = j; }
+                        for (int j = P.cur_from[f] + tid; j <= P.cur_until[f]; j += NT) {
+                            const double v = sg_at(f, j);
+                            if (v > bm) { bm = v; ba = j; }
+                        }
                     }
-                    if (f == 0) {
+                    if (f == 0 && want_intr) {
 #pragma unroll 1
                         for (int j = P.intr_from + tid; j <= P.intr_until; j += NT) {
                             const double v = sg_at(0, j);
@@ -1371,10 +1377,12 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
                 }
                 if (f == 0) { cmax[0] = bm; carg[0] = ba; } else if (f == 1) { cmax[1] = bm; carg[1] = ba; } else { cmax[2] = bm; carg[2] = ba; }
             }
+            if (want_cur) {
 #pragma unroll 2
-            for (int j = P.cur_from[3] + tid; j <= P.cur_until[3]; j += NT) {
-                const double d = deriv_at(TT, j);
-                if (d > cmax[3]) { cmax[3] = d; carg[3] = j; }
+                for (int j = P.cur_from[3] + tid; j <= P.cur_until[3]; j += NT) {
+                    const double d = deriv_at(TT, j);
+                    if (d > cmax[3]) { cmax[3] = d; carg[3] = j; }
+                }
             }
             SECT(13);
             const double wsm = wmax_d(sgcmax);
@@ -1421,7 +1429,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
         // ---- thresholds of the sg[0] masks (t50_current at half the trace maximum; pile-up at n sigma of the baseline
         //      window, sigma exactly as signalstats computes it) ----
         double pile_thr = 0.0, cur_thr = 0.0;
-        if (G & LGDSP_GROUP_CURRENT) {
+        if (G & LGDSP_GROUP_INTRACE) {
             cur_thr = red_max(red, R_SGMAX) * 0.5;
             const double sS = red_sum(red, R_SGS), sSS = red_sum(red, R_SGSS);
             const double mean_Y = mul_rn(sS, P.intr_inv_n);
@@ -1523,7 +1531,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
 
         // ---- masks on the sg[0] trace (t50_current, in-trace pile-up on the REVERSED trace): only chunks whose
         //      maximum reaches the smaller threshold can contribute a bit ----
-        if (G & LGDSP_GROUP_CURRENT) {
+        if (G & LGDSP_GROUP_INTRACE) {
             const bool flag = sgcmax >= fmin(cur_thr, pile_thr);
             const unsigned bf = __ballot_sync(FULL, flag);
             if (__popc(bf) > 10) {
@@ -1725,7 +1733,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
                 const double v = qdrift_warp(tx_us(2), P.lq_first, P.lq_last);       // lq @ t80
                 if (lane == 0) row[LGDSP_COL_lq] = v;
             }
-            if (G & LGDSP_GROUP_CURRENT) {
+            if (G & LGDSP_GROUP_INTRACE) {
                 // crossing resolution of the sg[0] masks (complete since Bq), then t50_current and the in-trace pile-up
                 int posc, posp, multc, multp;
                 resolve_runs(masks + M_CUR * NWORDS, P.tx_min_n, lane, posc, multc);

@@ -214,3 +214,42 @@ def test_full_size_properties(L, O, handle):
     idx = np.sort(rng.choice(n, 1500, replace=False))
     ref, _ = O.dsp_icpc(P, raw[idx])
     assert_parity_with_ties(L, O, P, raw[idx], a[idx], ref)
+
+
+@pytest.mark.parametrize("n_samples", [2048, 1400, 512])
+def test_short_traces(L, O, handle, n_samples):
+    """short traces (the lengths of the compressed format's windowed waveforms): the whole chain, or for lengths the fixed
+    trapezoids do not fit the windowed-waveform pass of dsp_icpc_compressed, against the oracle on full-rate slices"""
+    from importlib import import_module
+    cfgm = import_module("legenddsp.jl_b200.config")
+    us = cfgm.us
+    scale = n_samples / 2048.0
+    d = cfgm.example_config_dict()
+    d["bl_window"] = {"min": us(0.0), "max": us(4.0 * scale)}
+    d["tail_window"] = {"min": us(16.0 * scale), "max": us(30.0 * scale)}
+    d["current_window"] = {"min": us(4.0 * scale), "max": us(12.0 * scale)}
+    d["flt_length_cusp"] = d["flt_length_zac"] = us(6.0 * scale)
+    d["flt_defaults"]["trap"] = d["flt_defaults"]["cusp"] = d["flt_defaults"]["zac"] = {"rt": us(1.0 * scale), "ft": us(0.5 * scale)}
+    d["qdrift_int_length"] = d["lq_int_length"] = (us(1.0 * scale), us(2.0 * scale))
+    cfg = cfgm.DSPConfig.from_dict(d)
+    full = L.synth.generate_host(400, first_event=77)
+    start = 3000 - int(400 * scale)
+    wf = np.ascontiguousarray(full[:, start:start + n_samples])
+    if n_samples < 1600:
+        # the fixed 10/4 us trapezoid (1500 samples) does not fit: the reference's filters would fail the same way
+        with pytest.raises((ValueError, AssertionError)):
+            L.resolve_icpc_params(cfg, L.us(500.0), n_samples=n_samples, builders=O.OracleBuilders())
+        # ... so this length runs the windowed-waveform pass of dsp_icpc_compressed (timing, Q-drift, currents)
+        P = L.resolve_icpc_params(cfg, L.us(500.0), n_samples=n_samples, builders=O.OracleBuilders(), role="wdw")
+    else:
+        P = L.resolve_icpc_params(cfg, L.us(500.0), n_samples=n_samples, builders=O.OracleBuilders())
+    got = L.dsp_icpc_rows(wf, P, handle=handle)
+    ref, _ = O.dsp_icpc(P, wf)
+    if n_samples < 1600:
+        # columns of the groups this pass switches off are 0 on the device; the oracle evaluates the placeholders
+        for name in ("e_10410", "e_535", "e_313", "e_10410_inv", "e_313_inv", "e_trap", "e_trap_max", "t_trap_max", "e_cusp",
+                     "e_zac", "e_cusp_max", "e_zac_max", "t_cusp_max", "t_zac_max", "t50_current", "inTrace_intersect", "inTrace_n"):
+            assert (got[:, L.COL[name]] == 0).all(), name
+            ref[:, L.COL[name]] = 0.0
+    assert_parity_with_ties(L, O, P, wf, got, ref)
+    assert (ref[:, L.COL["t0"]] > 0).sum() > (200 if n_samples >= 1400 else 50)
