@@ -124,9 +124,6 @@ def test_ext_baseline_and_wide_samples(L, O, handle):
     """lgdsp_icpc_run_ext: (a) uint32 samples give the rows of the same values as uint16, (b) an external baseline equal
     to the waveform's own blmean reproduces the plain run bit for bit, (c) a different baseline moves e_max by exactly
     the difference"""
-    P = L.resolve_icpc_params(L.tiefree_config(), L.us(500.0), n_samples=4096, builders=O.OracleBuilders(),
-                              groups=L._abi.GROUP_PZTRAP | L._abi.GROUP_QDRIFT | L._abi.GROUP_CURRENT) \
-        if False else None
     from importlib import import_module
     cfgm = import_module("legenddsp.jl_b200.config")
     d = cfgm.example_config_dict()
