@@ -420,6 +420,15 @@ int lgdsp_sipm_run(lgdsp_handle* h, const lgdsp_sipm_params* p, const void* wf, 
                    double* rows, double* trig);
 int lgdsp_sipm_run_device(lgdsp_handle* h, const lgdsp_sipm_params* p, const void* d_wf, int64_t n_events,
                           int64_t ld_samples, double* d_rows, double* d_trig);
+/* trigger list `list` (0..3) of a finished lgdsp_sipm_run_device call in the reference's VectorOfVectors form, on the
+ * device: d_elem_ptr: int64[n_events + 1] (element pointers, 0-based; d_elem_ptr[n_events] = total number of triggers),
+ * d_flat: double[4 fields][flat_stride] with the entries of event e at [d_elem_ptr[e], d_elem_ptr[e+1]).  Two calls:
+ * lgdsp_sipm_list_pointers_device fills d_elem_ptr and returns the total in *total (synchronises), then the caller
+ * provides d_flat with flat_stride >= total and calls lgdsp_sipm_list_gather_device.  Lists cut at max_triggers stay cut. */
+int lgdsp_sipm_list_pointers_device(lgdsp_handle* h, const double* d_rows, int64_t n_events, int32_t list, int32_t max_triggers,
+                                    int64_t* d_elem_ptr, int64_t* total);
+int lgdsp_sipm_list_gather_device(lgdsp_handle* h, const double* d_trig, int64_t n_events, int32_t list, int32_t max_triggers,
+                                  const int64_t* d_elem_ptr, double* d_flat, int64_t flat_stride);
 /* the in-tree primitives of the chain on single traces of doubles (host buffers; one trace per call, for tests and
  * small jobs): thresholdstats / thresholdstats_mad (src/thresholdstats.jl:19-41, 61-71) and IntersectMaximum
  * (src/intersect_maximum.jl:24-119; x/x_high/x_tot/max: double[max_triggers], returns the count in *n_found) */

@@ -58,6 +58,8 @@ def load_library():
     L.lgdsp_icpc_compressed_run_device.argtypes = _comp
     L.lgdsp_sipm_run.argtypes = [vp, C.POINTER(_abi.SipmParams), vp, i64, i64, vp, vp]
     L.lgdsp_sipm_run_device.argtypes = [vp, C.POINTER(_abi.SipmParams), vp, i64, i64, vp, vp]
+    L.lgdsp_sipm_list_pointers_device.argtypes = [vp, vp, i64, i32, i32, vp, C.POINTER(i64)]
+    L.lgdsp_sipm_list_gather_device.argtypes = [vp, vp, i64, i32, i32, vp, vp, i64]
     L.lgdsp_thresholdstats.argtypes = [vp, vp, i32, C.c_double, C.c_double, i32, _dp]
     L.lgdsp_intersect_maximum.argtypes = [vp, vp, i32, C.c_double, C.c_double, C.c_double, i32, i32, i32, vp, vp, vp, vp,
                                           C.POINTER(i32)]
@@ -82,7 +84,7 @@ EXPORTED_SYMBOLS = (
     "lgdsp_lsq_fit_matrix", "lgdsp_sg_coeffs", "lgdsp_cusp_coeffs", "lgdsp_zac_coeffs",
     "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params", "lgdsp_icpc_run_ext", "lgdsp_icpc_run_ext_device",
     "lgdsp_window_stats_run", "lgdsp_window_stats_run_device", "lgdsp_sipm_run", "lgdsp_sipm_run_device",
-    "lgdsp_thresholdstats", "lgdsp_intersect_maximum", "lgdsp_multi_intersect_run", "lgdsp_multi_intersect_run_device", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
+    "lgdsp_sipm_list_pointers_device", "lgdsp_sipm_list_gather_device", "lgdsp_thresholdstats", "lgdsp_intersect_maximum", "lgdsp_multi_intersect_run", "lgdsp_multi_intersect_run_device", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
     "lgdsp_trap_sweep_run", "lgdsp_trap_sweep_run_device", "lgdsp_sweep_run", "lgdsp_sweep_run_device",
     "lgdsp_synth_generate_device", "lgdsp_synth_generate_host", "lgdsp_last_kernel_ms", "lgdsp_debug_phase_cycles", "lgdsp_debug_section_cycles",
 )
@@ -209,6 +211,17 @@ class Handle:
         self._check(self._lib.lgdsp_sipm_run_device(self._h, C.byref(params) if params is not None else None,
                                                     C.c_void_p(d_wf_ptr), int(n_events), int(ld), C.c_void_p(d_rows_ptr),
                                                     C.c_void_p(d_trig_ptr)))
+
+    def sipm_list_pointers_device(self, d_rows_ptr, n_events, lst, cap, d_elem_ptr):
+        """element pointers of trigger list `lst` (device int64[n_events + 1]); returns the total number of triggers"""
+        tot = C.c_int64(0)
+        self._check(self._lib.lgdsp_sipm_list_pointers_device(self._h, C.c_void_p(d_rows_ptr), int(n_events), int(lst), int(cap),
+                                                              C.c_void_p(d_elem_ptr), C.byref(tot)))
+        return tot.value
+
+    def sipm_list_gather_device(self, d_trig_ptr, n_events, lst, cap, d_elem_ptr, d_flat_ptr, flat_stride):
+        self._check(self._lib.lgdsp_sipm_list_gather_device(self._h, C.c_void_p(d_trig_ptr), int(n_events), int(lst), int(cap),
+                                                            C.c_void_p(d_elem_ptr), C.c_void_p(d_flat_ptr), int(flat_stride)))
 
     def thresholdstats(self, y, mn, mx, mad):
         import numpy as np

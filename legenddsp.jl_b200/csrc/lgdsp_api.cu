@@ -1104,6 +1104,38 @@ int lgdsp_sipm_run(lgdsp_handle* h, const lgdsp_sipm_params* p, const void* wf, 
     return LGDSP_OK;
 }
 
+int lgdsp_sipm_list_pointers_device(lgdsp_handle* h, const double* d_rows, int64_t n_events, int32_t list, int32_t max_triggers,
+                                    int64_t* d_elem_ptr, int64_t* total)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (n_events < 0 || list < 0 || list >= LGDSP_SIPM_NLIST || max_triggers < 1) return fail(h, LGDSP_ERR_INVALID_ARG, "bad n_events / list / max_triggers");
+    if (!d_elem_ptr || (n_events > 0 && !d_rows)) return fail(h, LGDSP_ERR_INVALID_ARG, "NULL pointer");
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    sipm_count_scan_launch(d_rows, n_events, list, max_triggers, reinterpret_cast<long long*>(d_elem_ptr), h->stream);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    long long tot = 0;
+    CK(cudaMemcpyAsync(&tot, d_elem_ptr + n_events, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (total) *total = tot;
+    return LGDSP_OK;
+}
+
+int lgdsp_sipm_list_gather_device(lgdsp_handle* h, const double* d_trig, int64_t n_events, int32_t list, int32_t max_triggers,
+                                  const int64_t* d_elem_ptr, double* d_flat, int64_t flat_stride)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (n_events < 0 || list < 0 || list >= LGDSP_SIPM_NLIST || max_triggers < 1 || flat_stride < 0) return fail(h, LGDSP_ERR_INVALID_ARG, "bad argument");
+    if (n_events == 0) return LGDSP_OK;
+    if (!d_trig || !d_elem_ptr || !d_flat) return fail(h, LGDSP_ERR_INVALID_ARG, "NULL pointer");
+    sipm_compact_launch(d_trig, n_events, list, max_triggers, reinterpret_cast<const long long*>(d_elem_ptr), d_flat, flat_stride, h->stream);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return LGDSP_OK;
+}
+
 // single-trace primitives (host buffers)
 static int prim_run(lgdsp_handle* h, int mode, const double* y, int n, double a, double b, double t0, double dt, int min_n, int max_n,
                     int cap, double* out_host, int n_out, int32_t* n_found)

@@ -68,6 +68,11 @@ void sipm_launch(const SipmDev& P, const void* d_wf, long long n_events, long lo
 void sipm_prim_launch(int mode, const double* d_y, int n, double a, double b, double t0, double dt, int min_n, int max_n, int cap,
                       double* d_out, int* d_n_found, cudaStream_t stream);
 
+// trigger lists -> flat data + element pointers on the device
+void sipm_count_scan_launch(const double* d_rows, long long n_events, int list, int cap, long long* d_elem_ptr, cudaStream_t stream);
+void sipm_compact_launch(const double* d_trig, long long n_events, int list, int cap, const long long* d_elem_ptr, double* d_flat,
+                         long long flat_stride, cudaStream_t stream);
+
 // ---- MultiIntersect (lgdsp_sipm.cu): one warp per trace ----
 struct MiDev {
     int len, n_thr;

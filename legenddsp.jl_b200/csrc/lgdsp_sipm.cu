@@ -700,6 +700,58 @@ __global__ void __launch_bounds__(MI_WARPS * 32) multi_intersect_kernel(const __
     }
 }
 
+// ==================================================================================================
+// trigger lists -> VectorOfVectors form on the device (flat data + element pointers, the reference's
+// VectorOfVectors(inters.x) etc., src/dsp_sipm.jl:150-157).  Step 1: one block scans the per-event counts of one list
+// (min(count, cap)) into elem_ptr[n_events + 1] with a running carry over tiles of 1024 events; step 2: one warp per
+// event copies its entries of the four fields to flat[field][elem_ptr[e] + k].
+// ==================================================================================================
+__global__ void __launch_bounds__(1024) sipm_count_scan_kernel(const double* __restrict__ rows, long long n_events, int list, int cap,
+                                                               long long* __restrict__ elem_ptr)
+{
+    __shared__ long long wsum[32];
+    __shared__ long long carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (long long base = 0; base < n_events; base += 1024) {
+        const long long e = base + tid;
+        long long c = 0;
+        if (e < n_events) {
+            const double cnt = rows[e * LGDSP_SIPM_NCOL + LGDSP_SIPM_n_trig + list];
+            c = (long long)(cnt < (double)cap ? cnt : (double)cap);
+        }
+        long long inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long u = __shfl_up_sync(FULLM, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        long long before = carry_s;
+        for (int w = 0; w < wid; ++w) before += wsum[w];
+        if (e < n_events) elem_ptr[e] = before + inc - c;
+        __syncthreads();
+        if (tid == 1023) carry_s = before + inc;
+        __syncthreads();
+    }
+    if (tid == 0) elem_ptr[n_events] = carry_s;
+}
+
+__global__ void sipm_compact_kernel(const double* __restrict__ trig, long long n_events, int list, int cap,
+                                    const long long* __restrict__ elem_ptr, double* __restrict__ flat, long long flat_stride)
+{
+    const int lane = threadIdx.x & 31;
+    const long long e = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= n_events) return;
+    const long long p0 = elem_ptr[e];
+    const int cnt = (int)(elem_ptr[e + 1] - p0);
+    const double* src = trig + ((size_t)e * LGDSP_SIPM_NLIST + list) * LGDSP_SIPM_NFIELD * cap;
+    for (int f = 0; f < LGDSP_SIPM_NFIELD; ++f)
+        for (int k = lane; k < cnt; k += 32) flat[(size_t)f * flat_stride + p0 + k] = src[(size_t)f * cap + k];
+}
+
 size_t sipm_smem_bytes(int n)
 {
     const int npad = (n + 2 + 1) & ~1;
@@ -737,6 +789,19 @@ void sipm_prim_launch(int mode, const double* d_y, int n, double a, double b, do
                       double* d_out, int* d_n_found, cudaStream_t stream)
 {
     sipm_prim_kernel<<<1, SNT, 0, stream>>>(mode, d_y, n, a, b, t0, dt, min_n, max_n, cap, d_out, d_n_found);
+}
+
+void sipm_count_scan_launch(const double* d_rows, long long n_events, int list, int cap, long long* d_elem_ptr, cudaStream_t stream)
+{
+    sipm_count_scan_kernel<<<1, 1024, 0, stream>>>(d_rows, n_events, list, cap, d_elem_ptr);
+}
+
+void sipm_compact_launch(const double* d_trig, long long n_events, int list, int cap, const long long* d_elem_ptr, double* d_flat,
+                         long long flat_stride, cudaStream_t stream)
+{
+    if (n_events <= 0) return;
+    const unsigned grid = (unsigned)((n_events + 7) / 8);
+    sipm_compact_kernel<<<grid, 256, 0, stream>>>(d_trig, n_events, list, cap, d_elem_ptr, d_flat, flat_stride);
 }
 
 void multi_intersect_launch(const MiDev& P, const double* d_y, long long n_events, long long ld, double* d_x, int* d_flags,

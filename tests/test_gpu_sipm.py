@@ -227,3 +227,35 @@ def test_multi_intersect(L, O, handle, kat):
         L.MultiIntersect(threshold_ratios=[0.5, 2.0], mintot=L.ns(16.0), n=2, d=1)(flat, handle=handle)
     with pytest.raises(AssertionError):
         O.multi_intersect(flat[0], 0.0, 16.0, [0.5, 2.0], 1, 2, 1, 1)
+
+
+def test_trigger_lists_compacted_on_the_device(L, O, handle):
+    """VectorOfVectors form (flat data + element pointers) built on the device == the host packing of the padded lists"""
+    import torch
+    n_ev, cap = 3000, 32
+    wf = sipm_population(48, seed=5)
+    wf = np.tile(wf, (n_ev // 48 + 1, 1))[:n_ev]
+    cfg = L.example_sipm_config()
+    cfg["filters"]["sg"].update(min_threshold=-3.0, max_threshold=3.0, min_dc_threshold=-40.0, max_dc_threshold=40.0)
+    cfg["filters"]["trap"].update(min_threshold=-15.0, max_threshold=15.0, min_dc_threshold=-30.0, max_dc_threshold=30.0)
+    P = L.resolve_sipm_params(cfg, {"sg": {"wl": L.ns(200.0)}}, n_samples=6250, max_triggers=cap)
+    d_wf = torch.from_numpy(wf.view(np.int16)).cuda()
+    d_rows = torch.zeros((n_ev, L._abi.SIPM_NCOL), dtype=torch.float64, device="cuda")
+    d_trig = torch.zeros((n_ev, 4, 4, cap), dtype=torch.float64, device="cuda")
+    handle.sipm_run_device(P, d_wf.data_ptr(), n_ev, 6250, d_rows.data_ptr(), d_trig.data_ptr())
+    handle.synchronize()
+    rows, trig = d_rows.cpu().numpy(), d_trig.cpu().numpy()
+    tbl = L.sipm_to_table(rows, trig)
+    for lst, name in ((0, "trig_pos"), (2, "trig_pos_trap")):
+        d_ptr = torch.zeros(n_ev + 1, dtype=torch.int64, device="cuda")
+        total = handle.sipm_list_pointers_device(d_rows.data_ptr(), n_ev, lst, cap, d_ptr.data_ptr())
+        ref = tbl[name]
+        assert total == len(ref.data) and np.array_equal(d_ptr.cpu().numpy(), ref.elem_ptr)
+        d_flat = torch.zeros((4, max(total, 1)), dtype=torch.float64, device="cuda")
+        handle.sipm_list_gather_device(d_trig.data_ptr(), n_ev, lst, cap, d_ptr.data_ptr(), d_flat.data_ptr(), max(total, 1))
+        handle.synchronize()
+        flat = d_flat.cpu().numpy()
+        assert np.array_equal(flat[0, :total], ref.data)
+        mx_name = "trig_max" if lst == 0 else "trig_max_trap"
+        assert np.array_equal(flat[3, :total], tbl[mx_name].data)
+    assert total > n_ev // 2
