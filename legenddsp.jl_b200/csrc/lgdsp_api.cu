@@ -1082,25 +1082,34 @@ int lgdsp_sipm_run(lgdsp_handle* h, const lgdsp_sipm_params* p, const void* wf, 
     if (ld_samples < D.n) return fail(h, LGDSP_ERR_INVALID_ARG, "ld_samples (%lld) < n_samples (%d)", (long long)ld_samples, D.n);
     const size_t sb = (size_t)D.kind;   // bytes per sample
     const size_t per_trig = (size_t)LGDSP_SIPM_NLIST * LGDSP_SIPM_NFIELD * D.cap;
-    const int64_t chunk = n_events < 4096 ? n_events : 4096;
-    rc = ensure_staging(h, (size_t)chunk * D.n * sb, (size_t)chunk * (LGDSP_SIPM_NCOL + per_trig) * sizeof(double));
+    // double-buffered: the H2D copy of chunk k+1 (copy stream) overlaps the kernel and the D2H copies of chunk k
+    const int64_t chunk = n_events < 8192 ? n_events : 8192;
+    const size_t out_per = LGDSP_SIPM_NCOL + per_trig;
+    rc = ensure_staging(h, (size_t)chunk * D.n * sb, (size_t)2 * chunk * out_per * sizeof(double));
     if (rc) return rc;
     const long long gcap = (long long)h->sm_count * bps;
     const unsigned char* src = static_cast<const unsigned char*>(wf);
-    for (int64_t e0 = 0; e0 < n_events; e0 += chunk) {
+    int c = 0;
+    for (int64_t e0 = 0; e0 < n_events; e0 += chunk, ++c) {
+        const int b = c & 1;
         const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
-        CK(cudaMemcpy2DAsync(h->d_in[0], (size_t)D.n * sb, src + (size_t)e0 * ld_samples * sb, (size_t)ld_samples * sb, (size_t)D.n * sb,
-                             (size_t)ne, cudaMemcpyHostToDevice, h->stream));
-        double* d_rows = h->d_rows;
-        double* d_trig = h->d_rows + (size_t)chunk * LGDSP_SIPM_NCOL;
+        if (c >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
+        CK(cudaMemcpy2DAsync(h->d_in[b], (size_t)D.n * sb, src + (size_t)e0 * ld_samples * sb, (size_t)ld_samples * sb, (size_t)D.n * sb,
+                             (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
+        CK(cudaEventRecord(h->ev_ready[b], h->s_copy));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
+        double* d_rows = h->d_rows + (size_t)b * chunk * out_per;
+        double* d_trig = d_rows + (size_t)chunk * LGDSP_SIPM_NCOL;
         const int grid = (int)(ne < gcap ? ne : gcap);
-        sipm_launch(D, h->d_in[0], ne, D.n, d_rows, d_trig, grid, h->stream);
+        sipm_launch(D, h->d_in[b], ne, D.n, d_rows, d_trig, grid, h->stream);
         CK(cudaGetLastError());
         h->launches += 1;
+        CK(cudaEventRecord(h->ev_free[b], h->stream));
         CK(cudaMemcpyAsync(rows + e0 * LGDSP_SIPM_NCOL, d_rows, (size_t)ne * LGDSP_SIPM_NCOL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(trig + (size_t)e0 * per_trig, d_trig, (size_t)ne * per_trig * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
     }
+    CK(cudaStreamSynchronize(h->s_copy));
+    CK(cudaStreamSynchronize(h->stream));
     return LGDSP_OK;
 }
 
