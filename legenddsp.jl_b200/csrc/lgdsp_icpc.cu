@@ -303,18 +303,18 @@ __device__ __forceinline__ void commit_pair(uint32_t* MA, unsigned long long bit
 // One warp: find runs of >= k consecutive set bits in the NWORDS-word mask M (bits beyond the trace are zero)
 // that do not start at bit 0 -- the Intersect state machine: `pos` = start of the first such
 // run (-1 if none), `mult` = number of such runs.  Every lane looks for run STARTS (set bit after a clear bit) in its
-// 8 words and measures each run forward, word by word; M is left intact.
+// 8 words and measures each run forward, word by word; M is left intact.  Words are dealt round-robin (word w -> lane
+// w % 32): the noisy stretch around a crossing spans a few neighbouring words, which then go to different lanes.
 __device__ __noinline__ int resolve_runs_packed(const uint32_t* M, int k, int lane)
 {
     constexpr int Q = NWORDS / 32;
     int p = 0x7fffffff, cnt = 0;
-    uint32_t prev = lane ? M[lane * Q - 1] : 0u;
 #pragma unroll 1
     for (int q = 0; q < Q; ++q) {
-        const int w0 = lane * Q + q;
+        const int w0 = q * 32 + lane;
         const uint32_t mq = M[w0];
+        const uint32_t prev = w0 ? M[w0 - 1] : 0u;
         uint32_t starts = mq & ~((mq << 1) | (prev >> 31));
-        prev = mq;
         if (w0 == 0) starts &= ~1u;  // a run that starts at the first sample never fires
         while (starts) {
             const int b = __ffs(starts) - 1;
