@@ -1721,18 +1721,6 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
                     row[LGDSP_COL_a_sg + f] = v;
                 }
             }
-        } else if (wid == 7) {
-            if (G & LGDSP_GROUP_QDRIFT) {
-                int pos0, mult_;
-                resolve_runs(masks + M_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
-                const double v = qdrift_warp(t0_us(false, pos0), P.qd_first, P.qd_last);   // qdrift @ t0
-                if (lane == 0) row[LGDSP_COL_qdrift] = v;
-            }
-        } else if (wid == 6) {
-            if (G & LGDSP_GROUP_QDRIFT) {
-                const double v = qdrift_warp(tx_us(2), P.lq_first, P.lq_last);       // lq @ t80
-                if (lane == 0) row[LGDSP_COL_lq] = v;
-            }
             if (G & LGDSP_GROUP_INTRACE) {
                 // crossing resolution of the sg[0] masks (complete since Bq), then t50_current and the in-trace pile-up
                 int posc, posp, multc, multp;
@@ -1760,6 +1748,18 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
                         row[LGDSP_COL_inTrace_n] = (double)multp;
                     }
                 }
+            }
+        } else if (wid == 7) {
+            if (G & LGDSP_GROUP_QDRIFT) {
+                int pos0, mult_;
+                resolve_runs(masks + M_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
+                const double v = qdrift_warp(t0_us(false, pos0), P.qd_first, P.qd_last);   // qdrift @ t0
+                if (lane == 0) row[LGDSP_COL_qdrift] = v;
+            }
+        } else if (wid == 6) {
+            if (G & LGDSP_GROUP_QDRIFT) {
+                const double v = qdrift_warp(tx_us(2), P.lq_first, P.lq_last);       // lq @ t80
+                if (lane == 0) row[LGDSP_COL_lq] = v;
             }
         }
         };
