@@ -732,7 +732,7 @@ __device__ __forceinline__ void cz_out(const CzDev& Z, const double* TT, int n, 
     };
     const bool interior = (m0 - L >= 1) && (m0 + CH + 1 <= n);
     if (interior) {
-#pragma unroll 3
+#pragma unroll 1
         for (int k = 0; k < CH; ++k) {
             emit(k);
             const double a = s0.next_fast(r, k), b = s1.next_fast(r, k), c = s2.next_fast(r, k), d = s3.next_fast(r, k);
