@@ -781,7 +781,7 @@ __device__ __forceinline__ void trap_full2_minmax(const double* TT, const TrapDe
         const double ai1 = A.inv1, ai2 = A.inv2, bi1 = B.inv1, bi2 = B.inv2;
         const int cnt = min(A.nout, B.nout) - tid;
         int off = 0;
-#pragma unroll 2
+#pragma unroll 1
         for (; off < cnt; off += NT) {
             const double t0 = p0[off];
             const double oa = (a3[off] - a2[off]) * ai2 - (a1[off] - t0) * ai1;
@@ -933,7 +933,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
         SECT(31);
         const SAMPLE* xp = xs + i0;
         uint32_t csum = 0, cq = 0, cmn = 0xFFFFFFFFu, cmx = 0;
-#pragma unroll 3
+#pragma unroll 1
         for (int k = 0; k < cvalid; ++k) {
             const uint32_t x = xp[k];
             csum += x;
@@ -947,7 +947,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
             unsigned long long blSS = 0;
             uint32_t blS = 0, blSK = 0;
             const int ka = max(0, P.bl_from - i0), kb = min(cvalid - 1, P.bl_until - i0);
-#pragma unroll 3
+#pragma unroll 1
             for (int k = ka; k <= kb; ++k) {
                 const uint32_t x = xp[k];
                 blS += x;
@@ -1138,7 +1138,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
                     double tprev = TT0;
                     const int c32 = min(cvalid, 32);
                     double tnx = tp[1];                       // software prefetch: the load of sample k+1 overlaps sample k
-#pragma unroll 2
+#pragma unroll 1
                     for (int k = 0; k < c32; ++k) {
                         const double tn = tnx;
                         tnx = tp[k + 2];                      // (<= TT[i0+34]: inside the zero padding for the last chunk)
@@ -1263,7 +1263,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
         // PZ tail statistics (signalstats on the tail window, src/dsp_icpc.jl:123)
         {
             double pz_S = 0, pz_SS = 0, pz_SX = 0;
-#pragma unroll 2
+#pragma unroll 1
             for (int idx = P.tail_from + tid; idx <= P.tail_until; idx += NT) {
                 const double y = TT[idx + 1] - TT[idx];
                 const double X = t_first + (double)idx * dt;
@@ -1344,14 +1344,14 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
                         return a0 + a1;
                     };
                     if (want_cur) {
-#pragma unroll 2
+#pragma unroll 1
                         for (int j = P.cur_from[f] + tid; j <= P.cur_until[f]; j += NT) {
                             const double v = ev(j);
                             if (v > bm) { bm = v; ba = j; }
                         }
                     }
                     if (f == 0 && want_intr) {
-#pragma unroll 2
+#pragma unroll 1
                         for (int j = P.intr_from + tid; j <= P.intr_until; j += NT) {
                             const double v = ev(j);
                             sg_S += v;
@@ -1378,7 +1378,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
                 if (f == 0) { cmax[0] = bm; carg[0] = ba; } else if (f == 1) { cmax[1] = bm; carg[1] = ba; } else { cmax[2] = bm; carg[2] = ba; }
             }
             if (want_cur) {
-#pragma unroll 2
+#pragma unroll 1
                 for (int j = P.cur_from[3] + tid; j <= P.cur_until[3]; j += NT) {
                     const double d = deriv_at(TT, j);
                     if (d > cmax[3]) { cmax[3] = d; carg[3] = j; }
