@@ -321,8 +321,9 @@ typedef struct lgdsp_handle lgdsp_handle;
 const char* lgdsp_version(void);
 /* last error message of the handle (or of the last failed lgdsp_create when handle == NULL) */
 const char* lgdsp_last_error(const lgdsp_handle* h);
-/* create a handle on CUDA device `device`; stream = 0 creates an own stream, otherwise a cudaStream_t
- * to launch on (e.g. torch's current stream) */
+/* create a handle on CUDA device `device`; stream = 0 creates an own NON-BLOCKING stream (it does not synchronise with
+ * the legacy default stream: work the caller enqueued elsewhere on the buffers of a *_device call must be complete, and the
+ * caller reads results after lgdsp_synchronize), otherwise a cudaStream_t to launch on (e.g. torch's current stream) */
 int lgdsp_create(int device, void* stream, lgdsp_handle** out);
 void lgdsp_destroy(lgdsp_handle* h);
 /* number of kernels this handle has launched so far (for bench bookkeeping) */

@@ -106,3 +106,56 @@ def test_pathological_waveforms(L, O, handle):
                     "e_trap_max", "e_cusp_max", "e_zac_max", "t10", "t50", "t90", "qc_label")
     bad = {k: res[k] for k in well_defined if res[k][1] > 0}
     assert not bad, bad
+
+
+def test_full_size_properties(L, O, handle):
+    """BASELINE configs[1]/[2] size (1 M events, 16.4 GB resident): size-independent properties of the fused kernel --
+    the row of an event does not depend on its neighbours or on its position in the batch (reversed input gives the
+    reversed rows, bit for bit), a sub-range run equals the slice of the full run, and a sample of the population agrees
+    with the oracle"""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    n = 1_000_000 if free > 60e9 else 131072
+    P = L.resolve_icpc_params(L.tiefree_config(), L.us(500.0))
+    handle.icpc_set_params(P)
+    wf = torch.empty((n, 8192), dtype=torch.int16, device="cuda")
+    L.synth.generate_device(handle, wf.data_ptr(), n, first_event=50_000_000)
+    rows = torch.empty((n, L.NCOL), dtype=torch.float64, device="cuda")
+    handle.icpc_run_device(None, wf.data_ptr(), n, 8192, rows.data_ptr())
+    handle.synchronize()
+    # (a) position independence: reversed batch
+    wf_r = torch.empty_like(wf)
+    for a0 in range(0, n, 65536):    # reversed copy in blocks (torch.flip mis-indexes tensors of more than 2^31 elements)
+        b0 = min(n, a0 + 65536)
+        wf_r[n - b0:n - a0] = torch.flip(wf[a0:b0], dims=(0,))
+    torch.cuda.synchronize()   # the library launches on the handle's own (non-blocking) stream: torch's copies must be done
+    rows_r = torch.empty_like(rows)
+    handle.icpc_run_device(None, wf_r.data_ptr(), n, 8192, rows_r.data_ptr())
+    handle.synchronize()
+    a, b = rows.view(torch.int64), torch.flip(rows_r, dims=(0,)).view(torch.int64)     # bit patterns (NaN-safe)
+    assert bool((a == b).all())
+    del wf_r, rows_r, b
+    # (b) a sub-range run equals the slice of the full run
+    lo, cnt = n // 3 + 5, 4099
+    sub = torch.empty((cnt, L.NCOL), dtype=torch.float64, device="cuda")
+    handle.icpc_run_device(None, wf[lo:].data_ptr(), cnt, 8192, sub.data_ptr())
+    handle.synchronize()
+    assert bool((sub.view(torch.int64) == a[lo:lo + cnt]).all())
+    # (c) column sanity over the whole population
+    r = rows
+    c = L.COL
+    for name in ("n_sat_low", "n_sat_high", "n_sat_low_cons", "n_sat_high_cons", "inTrace_n"):
+        v = r[:, c[name]]
+        assert bool(((v >= 0) & (v <= 8192) & (v == torch.floor(v))).all()), name
+    assert bool((r[:, c["qc_label"]] == -1).all())
+    ok = r[:, c["t0"]] > 0
+    # (on low-amplitude events the t0 filter crosses its fixed threshold after the half-maximum: a population property, ~5 %)
+    assert float((r[ok, c["t0"]] < r[ok, c["t50"]]).double().mean()) > 0.9
+    assert float((r[ok, c["drift_time"]] > 0).double().mean()) > 0.9
+    assert float(ok.double().mean()) > 0.8
+    assert bool(torch.isfinite(r[:, [c["e_trap"], c["e_cusp"], c["e_zac"], c["e_10410"]]]).all())
+    # (d) a sample against the oracle
+    idx = torch.arange(0, n, max(1, n // 256), device="cuda")[:256]
+    sample = wf[idx].cpu().numpy().view(np.uint16)
+    ref, _ = O.dsp_icpc(L.resolve_icpc_params(L.tiefree_config(), L.us(500.0), builders=O.OracleBuilders()), sample)
+    assert_parity_with_ties(L, O, P, sample, rows[idx].cpu().numpy(), ref)

@@ -242,16 +242,19 @@ def test_trigger_lists_compacted_on_the_device(L, O, handle):
     d_wf = torch.from_numpy(wf.view(np.int16)).cuda()
     d_rows = torch.zeros((n_ev, L._abi.SIPM_NCOL), dtype=torch.float64, device="cuda")
     d_trig = torch.zeros((n_ev, 4, 4, cap), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()   # the handle launches on its own non-blocking stream: torch's fills / copies must be done first
     handle.sipm_run_device(P, d_wf.data_ptr(), n_ev, 6250, d_rows.data_ptr(), d_trig.data_ptr())
     handle.synchronize()
     rows, trig = d_rows.cpu().numpy(), d_trig.cpu().numpy()
     tbl = L.sipm_to_table(rows, trig)
     for lst, name in ((0, "trig_pos"), (2, "trig_pos_trap")):
         d_ptr = torch.zeros(n_ev + 1, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
         total = handle.sipm_list_pointers_device(d_rows.data_ptr(), n_ev, lst, cap, d_ptr.data_ptr())
         ref = tbl[name]
         assert total == len(ref.data) and np.array_equal(d_ptr.cpu().numpy(), ref.elem_ptr)
         d_flat = torch.zeros((4, max(total, 1)), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
         handle.sipm_list_gather_device(d_trig.data_ptr(), n_ev, lst, cap, d_ptr.data_ptr(), d_flat.data_ptr(), max(total, 1))
         handle.synchronize()
         flat = d_flat.cpu().numpy()
