@@ -262,3 +262,39 @@ def test_trigger_lists_compacted_on_the_device(L, O, handle):
         mx_name = "trig_max" if lst == 0 else "trig_max_trap"
         assert np.array_equal(flat[3, :total], tbl[mx_name].data)
     assert total > n_ev // 2
+
+
+def test_sipm_rows_do_not_depend_on_batch_order(L, O, handle):
+    """persistent CTAs process several events each: the result of an event must not depend on what the CTA did before
+    (shuffled batch == shuffled rows, bit for bit), for dsp_sipm and for the two passes of dsp_icpc_compressed"""
+    rng = np.random.default_rng(17)
+    wf = sipm_population(96, seed=23)
+    wf = np.tile(wf, (13, 1))                       # 1248 events > resident CTAs
+    perm = rng.permutation(len(wf))
+    cfg = L.example_sipm_config()
+    cfg["filters"]["sg"].update(min_threshold=-3.0, max_threshold=3.0, min_dc_threshold=-40.0, max_dc_threshold=40.0)
+    cfg["filters"]["trap"].update(min_threshold=-15.0, max_threshold=15.0, min_dc_threshold=-30.0, max_dc_threshold=30.0)
+    P = L.resolve_sipm_params(cfg, {"sg": {"wl": L.ns(200.0)}}, n_samples=6250, max_triggers=48)
+    r1, t1 = L.sipm_rows(wf, P, handle=handle)
+    r2, t2 = L.sipm_rows(np.ascontiguousarray(wf[perm]), P, handle=handle)
+    assert np.array_equal(r1[perm].view(np.int64), r2.view(np.int64)) and np.array_equal(t1[perm].view(np.int64), t2.view(np.int64))
+    # identical input traces (the tiling) give identical rows wherever they sit
+    assert np.array_equal(r1[:96].view(np.int64), r1[96:192].view(np.int64))
+    # compressed dsp_icpc: same property through the host entry
+    full = L.synth.generate_host(700, first_event=31000)
+    pre, wdw = L.synth.compress(full, 8, (2600, 1400))
+    cfgc = L.tiefree_config()
+    Pp, Pw, aux = L.resolve_compressed_params(cfgc, L.us(500.0), None, presum_rate=8, n_pre=1024, step_pre=L.ns(128.0), n_wdw=1400,
+                                              t_first_wdw=L.ns(16.0 * 2600), step_wdw=L.ns(16.0))
+    perm = rng.permutation(len(full))
+
+    def run(p_, w_):
+        n = len(p_)
+        a, b, s = np.zeros((n, L.NCOL)), np.zeros((n, L.NCOL)), np.zeros((n, 5, 5))
+        handle.icpc_compressed_run_host(Pp, Pw, p_.ctypes.data, 4, 1024, w_.ctypes.data, 2, 1400, 8.0, aux, n, a.ctypes.data,
+                                        b.ctypes.data, s.ctypes.data)
+        return a, b, s
+    a1, b1, s1 = run(pre, wdw)
+    a2, b2, s2 = run(np.ascontiguousarray(pre[perm]), np.ascontiguousarray(wdw[perm]))
+    for x, y in ((a1, a2), (b1, b2), (s1, s2)):
+        assert np.array_equal(x[perm].view(np.int64), y.view(np.int64))
