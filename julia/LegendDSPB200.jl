@@ -14,7 +14,7 @@ import LegendDSP: DSPConfig, get_fltpars
 const LIB = get(ENV, "LGDSP_B200_LIB", "liblgdsp_b200.so")
 
 const MAX_DNI, MAX_SG, MAX_FIR, NCOL = 64, 33, 4096, 49
-const PARAMS_VERSION = UInt32(3)
+const PARAMS_VERSION = UInt32(4)      # LGDSP_PARAMS_VERSION
 
 struct Trap; navg::Int32; ngap::Int32; navg2::Int32; reserved::Int32; end
 struct Dni;  n_w::Int32; degree::Int32; A::NTuple{MAX_DNI * 4, Float64}; end
@@ -92,7 +92,7 @@ function resolve_params(wvfs, config::DSPConfig, τ, pars_filter::PropDict)
                   min(n - s.n_taps, _idx(rightendpoint(config.current_window), t1 + s.offset * dt, dt)))
     cw = (curw(sg0, 0), curw(sg1, 1), curw(sg2, 2), (_idx(leftendpoint(config.current_window), t1, dt), _idx(rightendpoint(config.current_window), t1, dt)))
     RC = ustrip(NoUnits, τ / dt)
-    IcpcParams(UInt32(sizeof(IcpcParams)), PARAMS_VERSION, n, 0x3f,
+    IcpcParams(UInt32(sizeof(IcpcParams)), PARAMS_VERSION, n, 0x7f,                      # LGDSP_GROUP_ALL
         ustrip(u"ns", t1), ustrip(u"ns", dt),
         0, 2^kw.fc_bit_depth - kw.fc_bit_depth,                                                  # src/dsp_icpc.jl:93-94
         _idx(leftendpoint(config.bl_window), t1, dt), _idx(rightendpoint(config.bl_window), t1, dt),
