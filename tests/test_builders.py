@@ -59,3 +59,28 @@ def test_sg_underdetermined_minimum_norm(L, O):
     ref5 = np.linalg.pinv(np.vander(x, 7, increasing=True))[1]
     assert np.allclose(L.LibBuilders().sg_coeffs(5, 6, 1), ref5, atol=1e-12)
     assert np.allclose(O.OracleBuilders().sg_coeffs(5, 6, 1), ref5, atol=1e-12)
+
+
+def test_against_independent_library_implementations(L, O):
+    """the published algorithms behind the RadiationDetectorDSP primitives, from independent implementations (scipy / numpy):
+    Savitzky-Golay derivative coefficients, the inverse-CR biquad, the integrator, valid-mode FIR and the trapezoid"""
+    import scipy.signal as sig
+    rng = np.random.default_rng(9)
+    for n_taps, deg in ((5, 3), (7, 3), (13, 3), (7, 2), (21, 4)):
+        ref = sig.savgol_coeffs(n_taps, deg, deriv=1, use="dot")          # s[j] = sum_k h[k] y[j+k], per-sample derivative
+        assert np.allclose(L.LibBuilders().sg_coeffs(n_taps, deg, 1), ref, atol=1e-13), (n_taps, deg)
+        assert np.allclose(O.OracleBuilders().sg_coeffs(n_taps, deg, 1), ref, atol=1e-12), (n_taps, deg)
+    y = rng.normal(0, 1, 500)
+    # InvCRFilter(tau): biquad b = (1/alpha, -1), a = (1, -1), alpha = RC/(RC+1)   (SURVEY.md appendix B)
+    RC = 31250.0
+    alpha = RC / (RC + 1.0)
+    assert np.allclose(O.invcr(y, 1.0 / alpha - 1.0), sig.lfilter([1.0 / alpha, -1.0], [1.0, -1.0], y), rtol=1e-12, atol=1e-12)
+    assert np.allclose(O.integrator(y), np.cumsum(y), rtol=1e-12, atol=1e-12)
+    c = rng.normal(0, 1, 37)
+    assert np.allclose(O.fir_valid(y, c), np.convolve(y, c, mode="valid"), rtol=1e-12, atol=1e-12)
+    h = np.array([0.2, -0.5, 0.1, 0.7, -0.3])
+    assert np.allclose(O.corr_valid(y, h), np.correlate(y, h, mode="valid"), rtol=1e-12, atol=1e-12)
+    # TrapezoidalChargeFilter(avg, gap, avg2) as an FIR: +1/avg2 over the trailing window, -1/avg over the leading one
+    a, g, a2 = 6, 3, 8
+    k = np.concatenate([np.full(a2, 1.0 / a2), np.zeros(g), np.full(a, -1.0 / a)])
+    assert np.allclose(O.trap(y, a, g, a2), np.convolve(y, k, mode="valid"), rtol=1e-12, atol=1e-12)
