@@ -264,6 +264,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (printed to stdout at NCCL_DEBUG=VERSION/INFO) out
+        os.environ["NCCL_DEBUG"] = os.environ.get("LGDSP_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     # a dedicated (non-default) torch stream shared with the library, so torch's CUDA events time our kernels
     stream = torch.cuda.Stream(device=dev)
