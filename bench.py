@@ -264,9 +264,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (printed to stdout at NCCL_DEBUG=VERSION/INFO) out
-        os.environ["NCCL_DEBUG"] = os.environ.get("LGDSP_NCCL_DEBUG", "WARN")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: the communicator initialisation prints "NCCL version ..." to fd 1, so fd 1
+        # points at stderr while the process group and its communicator come up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     # a dedicated (non-default) torch stream shared with the library, so torch's CUDA events time our kernels
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
