@@ -527,7 +527,7 @@ static int icpc_run_host_impl(lgdsp_handle* h, const lgdsp_icpc_params* p, const
     if (n_events == 0) return LGDSP_OK;
     if (!out_rows) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
     const size_t sb = (size_t)sample_bytes;
-    const int64_t chunk = n_events < 8192 ? n_events : 8192;
+    const int64_t chunk = n_events < 2048 ? n_events : 2048;
     rc = ensure_staging(h, (size_t)chunk * n * sb, (size_t)2 * chunk * LGDSP_NCOL * sizeof(double));
     if (rc) return rc;
     if (baseline) {
