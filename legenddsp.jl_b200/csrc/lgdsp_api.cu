@@ -541,8 +541,11 @@ static int icpc_run_host_impl(lgdsp_handle* h, const lgdsp_icpc_params* p, const
         const int b = c & 1;
         const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
         if (c >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
-        CK(cudaMemcpy2DAsync(h->d_in[b], (size_t)n * sb, src + (size_t)e0 * ld_samples * sb, (size_t)ld_samples * sb, (size_t)n * sb,
-                             (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
+        if (ld_samples == n)   // dense rows: one linear copy
+            CK(cudaMemcpyAsync(h->d_in[b], src + (size_t)e0 * n * sb, (size_t)ne * n * sb, cudaMemcpyHostToDevice, h->s_copy));
+        else
+            CK(cudaMemcpy2DAsync(h->d_in[b], (size_t)n * sb, src + (size_t)e0 * ld_samples * sb, (size_t)ld_samples * sb, (size_t)n * sb,
+                                 (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
         double* d_bl = nullptr;
         if (baseline) {
             d_bl = h->d_aux + (size_t)b * chunk;
