@@ -613,6 +613,43 @@ __global__ void __launch_bounds__(SNT) sipm_prim_kernel(int mode, const double* 
 // skipped in one step, the others are walked bit by bit in registers (same state machine, no memory traffic).
 // ==================================================================================================
 constexpr int MI_WARPS = 8;
+#ifndef MI_MAXU
+#define MI_MAXU 8
+#endif
+constexpr int MI_SB = 8;      // 32-sample blocks per fetch while looking for the first crossing
+
+// The state machine of :59-73 on one block of `steps` <= 32 samples, bit-parallel: bit l of m <=> sample i+l is high (bits
+// beyond `steps` are clear).  counter = length of the run of high samples that ends just before the block (a value above
+// k marks a run that may not fire any more, :56), cand = its first sample.  Returns true when a run reaches exactly k
+// samples inside the block (cand = its start); otherwise counter / cand describe the run that touches the block end.
+__device__ __forceinline__ bool mi_block(unsigned m, int steps, int i, int k, int& counter, int& cand)
+{
+    unsigned rest = m;
+    if (counter > 0) {
+        const int t = (m == 0xffffffffu) ? 32 : __ffs(~m) - 1;     // high samples at the start of the block (<= steps)
+        if (counter < k && counter + t >= k) return true;           // the carried run fires here
+        if (t == steps) { counter += t; return false; }             // the whole block is high
+        counter = 0;                                                // the carried run ends at bit t
+        rest = (t >= 31) ? 0u : (m >> (t + 1)) << (t + 1);
+    }
+    if (rest == 0u) { counter = 0; return false; }
+    unsigned r = (k > 32) ? 0u : rest;                              // bit p <=> bits p .. p+k-1 of rest are all set
+    for (int have = 1; have < k && r != 0u;) {
+        const int sh = min(have, k - have);
+        r &= r >> sh;
+        have += sh;
+    }
+    if (r != 0u) {
+        cand = i + __ffs(r) - 1;
+        counter = k;
+        return true;
+    }
+    const unsigned top = rest << (32 - steps);
+    const int tl = (top == 0xffffffffu) ? 32 : __clz(~top);          // high samples at the end of the block
+    counter = tl;
+    if (tl > 0) cand = i + steps - tl;
+    return false;
+}
 
 __global__ void __launch_bounds__(MI_WARPS * 32) multi_intersect_kernel(const __grid_constant__ MiDev P, const double* __restrict__ y,
                                                                         long long n_events, long long ld, double* __restrict__ x_out,
@@ -624,27 +661,59 @@ __global__ void __launch_bounds__(MI_WARPS * 32) multi_intersect_kernel(const __
     int* pos = pos_s[wid];
     for (long long e = (long long)blockIdx.x * MI_WARPS + wid; e < n_events; e += (long long)gridDim.x * MI_WARPS) {
         const double* Y = y + e * ld;
+        // maximum(Y) :31 -- MI_MAXU independent loads per lane in flight (the pass is latency bound otherwise)
         double ymax = -CUDART_INF;
-        for (int i = lane; i < len; i += 32) ymax = fmax(ymax, Y[i]);
-        ymax = wmax(ymax);                                                            // :31 maximum(Y)
+        {
+            double m0 = -CUDART_INF, m1 = -CUDART_INF, m2 = -CUDART_INF, m3 = -CUDART_INF;
+            // from the END of the trace towards its start: the crossing search below begins at sample 0, so the part it
+            // re-reads is the part that was fetched last (L2 / L1 hits instead of a second trip to HBM)
+            const int nfull = len / (MI_MAXU * 32);
+            for (int i = nfull * MI_MAXU * 32 + lane; i < len; i += 32) m0 = fmax(m0, Y[i]);
+            for (int g = nfull - 1; g >= 0; --g) {
+                const double* q = Y + g * (MI_MAXU * 32) + lane;
+                double a[MI_MAXU];
+#pragma unroll
+                for (int u = 0; u < MI_MAXU; ++u) a[u] = q[(MI_MAXU - 1 - u) * 32];
+#pragma unroll
+                for (int u = 0; u < MI_MAXU; u += 4) {
+                    m0 = fmax(m0, a[u]); m1 = fmax(m1, a[u + 1]); m2 = fmax(m2, a[u + 2]); m3 = fmax(m3, a[u + 3]);
+                }
+            }
+            ymax = fmax(fmax(m0, m1), fmax(m2, m3));
+        }
+        ymax = wmax(ymax);
         for (int j = lane; j < n_thr; j += 32) pos[j] = 1;                            // :55
         __syncwarp();
         int cand = 1, ic = 0, i = 0;
         int counter = (Y[0] >= P.ratios[0] * ymax) ? min_n + 1 : 0;                   // :56
         while (i < len && ic < n_thr) {                                               // :59-73
+            if (ic == 0 && i + MI_SB * 32 <= len) {
+                // the search for the FIRST crossing runs through the whole baseline: fetch MI_SB blocks with independent
+                // loads and examine them in order (one block per step would pay the memory latency for every block)
+                const double thr0 = P.ratios[0] * ymax;
+                double v[MI_SB];
+#pragma unroll
+                for (int u = 0; u < MI_SB; ++u) v[u] = Y[i + u * 32 + lane];
+#pragma unroll
+                for (int u = 0; u < MI_SB; ++u) {
+                    if (ic != 0) continue;
+                    const unsigned m = __ballot_sync(FULLM, v[u] >= thr0);
+                    if (mi_block(m, 32, i, min_n, counter, cand)) {
+                        if (lane == 0) pos[0] = cand;
+                        i = cand;
+                        ic = 1;
+                        counter = 0;
+                    } else {
+                        i += 32;
+                    }
+                }
+                continue;
+            }
             const double thr = P.ratios[ic] * ymax;
             const int idx = i + lane;
             const unsigned m = __ballot_sync(FULLM, idx < len && Y[idx] >= thr);
             const int steps = min(32, len - i);
-            if (m == 0u) { counter = 0; i += steps; continue; }
-            bool found = false;
-            for (int l = 0; l < steps; ++l) {
-                const bool high = (m >> l) & 1u;
-                if (high && counter == 0) cand = i + l;
-                counter = high ? counter + 1 : 0;
-                if (counter == min_n) { found = true; break; }
-            }
-            if (found) {
+            if (mi_block(m, steps, i, min_n, counter, cand)) {
                 if (lane == 0) pos[ic] = cand;
                 i = cand;                                                             // :69 restart at the crossing
                 ++ic;

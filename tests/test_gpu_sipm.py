@@ -220,6 +220,25 @@ def test_multi_intersect(L, O, handle, kat):
             ok = ~np.isnan(ref)
             assert np.allclose(got[e][ok], ref[ok], rtol=0, atol=1e-6), (hw, e, np.abs(got[e][ok] - ref[ok]).max())
         assert np.isfinite(got).mean() > 0.9
+    # long time-over-threshold requirements (runs that span several 32-sample blocks), traces that START above the
+    # thresholds (:56: such a run never fires) and a length that is not a multiple of the 32-sample blocks
+    n = 1777
+    kk = np.arange(n)
+    Y = np.empty((n_ev, n))
+    for e in range(n_ev):
+        s0, rise, amp = rng.integers(500, 900), rng.integers(60, 200), rng.uniform(200, 5000)
+        Y[e] = amp * np.clip((kk - s0) / rise, 0, 1) + rng.normal(0, 1.0, n)
+        if e % 2:
+            Y[e, :rng.integers(1, 150)] += 0.6 * amp
+    for (hw, d, rate, mintot) in ((2, 2, 4, 640.0), (1, 1, 2, 192.0), (3, 3, 4, 528.0)):
+        f = L.MultiIntersect(mintot=L.ns(mintot), n=hw, d=d, sampling_rate=rate)
+        got = f(Y, t_first=L.ns(0.0), step=L.ns(16.0), handle=handle, builders=O.OracleBuilders())
+        for e in range(n_ev):
+            ref = O.multi_intersect(Y[e], 0.0, 16.0, f.threshold_ratios, max(1, round(mintot / 16.0)), hw, d, rate)
+            assert np.array_equal(np.isnan(got[e]), np.isnan(ref)), (hw, e)
+            ok = ~np.isnan(ref)
+            assert np.allclose(got[e][ok], ref[ok], rtol=0, atol=1e-6), (hw, e, np.abs(got[e][ok] - ref[ok]).max())
+        assert np.isfinite(got).mean() > 0.9
     # boundary assertion (:85-88): a trace whose last threshold is never reached keeps the default position 2 -> with n = 2
     # the left boundary check fails
     flat = np.zeros((1, 500)); flat[0, 0] = 1.0
