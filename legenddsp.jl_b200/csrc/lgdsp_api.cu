@@ -880,6 +880,8 @@ static int sweep_prepare(lgdsp_handle* h, const lgdsp_sweep_params* p, const lgd
     D.bl_from = p->bl_from; D.bl_until = p->bl_until; D.km1 = p->pz_km1;
     D.sig_dni.n_w = d.n_w; D.sig_dni.m = d.degree + 1;
     D.dni_A = h->d_sweep_dniA; D.vars = h->d_vars; D.nvar = nvar; D.out_f64 = p->out_f64 ? 1 : 0;
+    D.n_other = 0;
+    for (int v = 0; v < nvar; ++v) D.n_other += (sv[v].kind != 0);
     D.bl_inv_n = 1.0 / (double)(p->bl_until - p->bl_from + 1);
     {
         typedef long double ld;

@@ -2096,7 +2096,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
         const double PP_excl = woff2 + incl2 - v2;
         // blmean exactly as signalstats: mean_Y = sum_Y * inv_n
         const double m = mul_rn(blSd, P.bl_inv_n);
-        double ymax = -CUDART_INF;
+        double ymax = -CUDART_INF, ymin = CUDART_INF;   // of this thread's chunk
         {
             uint32_t Pr = P_excl;
             double PPr = PP_excl;
@@ -2117,6 +2117,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
                 const double SS = fma(-tri, m, PPr);
                 tp[k] = fma(km1, SS, Sd);
                 ymax = y > ymax ? y : ymax;
+                ymin = y < ymin ? y : ymin;
             };
             {
                 int k = 0;
@@ -2127,6 +2128,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
             }
         }
         if (tid == 0) TT[0] = 0.0;
+        const double cmax = ymax, cmin = ymin;
         ymax = block_max1(ymax, red, tid);
         if (tid == 0) {
             const long long en = e + gridDim.x;
@@ -2139,9 +2141,19 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
         // t50 on the PZ waveform at 0.5*maximum  (src/dsp_filter_optimization.jl:260)
         const double thr = ymax * 0.5;
         {
+            // the chunk's own extrema decide most chunks: below the threshold everywhere (baseline) or above it everywhere
+            // (flat top after the pole-zero correction).  y from the closed form and y = TT[k+1] - TT[k] differ by
+            // rounding (< 3e-7: |TT| < 2^29, one ulp = 6e-8): chunks within that guard of the threshold are evaluated sample by sample.
             unsigned long long b = 0;
-            const double* p = TT + i0;
-            for (int k = 0; k < cvalid; ++k) b |= ((p[k + 1] - p[k]) >= thr) ? (1ull << k) : 0ull;
+            const double guard = 1e-5 * fmax(1.0, fabs(thr));
+            if (cvalid > 0 && cmax >= thr - guard) {
+                if (cmin >= thr + guard) {
+                    b = (1ull << cvalid) - 1ull;
+                } else {
+                    const double* p = TT + i0;
+                    for (int k = 0; k < cvalid; ++k) b |= ((p[k + 1] - p[k]) >= thr) ? (1ull << k) : 0ull;
+                }
+            }
             mask_commit(mask, tid, b);
         }
         __syncthreads();
@@ -2198,9 +2210,9 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
         }
         // FIR and Savitzky-Golay variants: one warp per variant
 #pragma unroll 1
-        for (int v = wid; v < P.nvar; v += NWARP) {
+        for (int v = wid; v < (P.n_other ? P.nvar : 0); v += NWARP) {
+            if (P.vars[v].kind == 0) continue;
             const SweepVar sv = P.vars[v];
-            if (sv.kind == 0) continue;
             if (sv.kind == 2) {
                 // SavitzkyGolay derivative trace s[j] = sum_k g[k] TT[j+k] (taps folded on the prefix sums); first argmax
                 // inside the window, parabola through its neighbours when strictly inside  (src/interpolation.jl:30-46)

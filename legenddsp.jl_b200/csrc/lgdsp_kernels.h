@@ -36,6 +36,7 @@ struct SweepDev {
     const double* dni_A;     // [LGDSP_MAX_DNI*4]
     const SweepVar* vars;    // device array
     int nvar, out_f64;
+    int n_other, reserved;   // variants of kind != 0 (0: the per-warp FIR / SG pass is skipped)
     double bl_inv_n, bl_sX, bl_sXX;   // baseline regression constants (aux outputs)
 };
 cudaError_t sweep_configure(int* max_blocks_per_sm);
