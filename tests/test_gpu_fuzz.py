@@ -80,3 +80,85 @@ def test_random_configurations(L, O, handle, seed):
     c = L.COL
     # the population is not degenerate (high t0 thresholds leave small pulses without a t0)
     assert np.isfinite(ref[:, c["e_trap"]]).sum() > 100 and (ref[:, c["t0"]] > 0).sum() > 40
+
+
+@pytest.mark.parametrize("seed", list(range(6)))
+def test_random_trap_sweeps(L, O, handle, seed):
+    """dsp_trap_ft-style grids with random (rt, ft) lists under random configurations: the one-thread-per-variant path,
+    the t50 chunk pruning and the pick-off windows near the trace ends (clamped DNI windows) against the oracle"""
+    cfg, tau, _, n, step = _draw(L, 100 + seed)
+    rng = np.random.default_rng(5000 + seed)
+    sc = step.ns() / 16.0
+    rts = [L.ns(float(v) * 1000.0 * sc) for v in np.sort(rng.uniform(0.3, 30.0, int(rng.integers(3, 24))))]
+    fts = [L.ns(float(v) * 1000.0 * sc) for v in np.sort(rng.uniform(0.1, 6.0, int(rng.integers(2, 12))))]
+    wf = np.ascontiguousarray(L.synth.generate_host(96, first_event=300 * (seed + 1))[:, :n])
+    so = L.resolve_sweep_params(cfg, tau, n_samples=n, step=step, builders=O.OracleBuilders())
+    # variants whose trapezoid leaves fewer outputs than the DNI window are rejected by the library: keep the others
+    keep_r = [r for r in rts if 2 * round(r.ns() / step.ns()) + round(fts[-1].ns() / step.ns()) + so.sig_dni.n_w < n]
+    var = L.trap_variants(keep_r, fts, step, mode="ft")
+    got = L.dsp_trap_rtft_grid(L.RDWaveforms(wf, L.ns(0.0), step), cfg, tau, keep_r, fts, handle=handle)
+    ref = O.trap_sweep(so, wf, var)
+    assert got.shape == (len(keep_r), len(fts), 96)
+    assert np.allclose(got.reshape(len(keep_r) * len(fts), 96).T, ref, rtol=1e-6, atol=1e-6, equal_nan=True)
+    assert np.isfinite(ref).mean() > 0.9
+
+
+@pytest.mark.parametrize("seed", list(range(6)))
+def test_random_sipm_configurations(L, O, handle, seed):
+    """dsp_sipm (src/dsp_sipm.jl:47-158) under random filter / threshold / window parameters and trace lengths"""
+    from test_gpu_sipm import _compare, sipm_population
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.choice([6250, 5000, 8192, 3000]))
+    t_end_us = (n - 1) * 0.016
+    lo = float(rng.uniform(2.0, 0.5 * t_end_us))
+    cfg = L.example_sipm_config()
+    cfg["t0_hpge_window"] = (L.us(lo), L.us(float(rng.uniform(lo + 1.0, t_end_us))))
+    cfg["sg_flt_degree"] = int(rng.choice([2, 3]))
+    s = float(rng.uniform(2.5, 6.0))
+    cfg["filters"]["sg"].update({"n_σ_threshold": s, "n_σ_dc_threshold": s + float(rng.uniform(0.5, 4.0))},
+                                min_threshold=-float(rng.uniform(2.0, 6.0)), max_threshold=float(rng.uniform(2.0, 6.0)),
+                                min_dc_threshold=-float(rng.uniform(20.0, 60.0)), max_dc_threshold=float(rng.uniform(20.0, 60.0)),
+                                min_tot_intersect=L.ns(float(rng.uniform(16.0, 120.0))),
+                                max_tot_intersect=L.ns(float(rng.uniform(130.0, 600.0))))
+    s = float(rng.uniform(2.5, 6.0))
+    cfg["filters"]["trap"].update({"n_σ_threshold": s, "n_σ_dc_threshold": s + float(rng.uniform(0.5, 4.0))},
+                                  rt=L.ns(16.0 * int(rng.integers(2, 16))), ft=L.ns(16.0 * int(rng.integers(1, 8))),
+                                  pz_tau=L.us(float(rng.uniform(0.5, 20.0))),
+                                  min_threshold=-float(rng.uniform(8.0, 25.0)), max_threshold=float(rng.uniform(8.0, 25.0)),
+                                  min_dc_threshold=-float(rng.uniform(20.0, 50.0)), max_dc_threshold=float(rng.uniform(20.0, 50.0)),
+                                  min_tot_intersect=L.ns(float(rng.uniform(16.0, 100.0))),
+                                  max_tot_intersect=L.ns(float(rng.uniform(110.0, 500.0))))
+    wl = L.ns(float(rng.uniform(60.0, 500.0)))
+    P = L.resolve_sipm_params(cfg, {"sg": {"wl": wl}}, n_samples=n, builders=O.OracleBuilders(), max_triggers=64)
+    wf = sipm_population(96, n=n, seed=40 + seed)
+    rows, trig = L.sipm_rows(wf, P, handle=handle)
+    ref_rows, ref_trig = O.dsp_sipm(P, wf)          # (sipm_rows grows P.max_triggers in place when a list was cut)
+    _compare(L, rows, trig, ref_rows, ref_trig)
+
+
+@pytest.mark.parametrize("seed", list(range(4)))
+def test_random_compressed_configurations(L, O, handle, seed):
+    """dsp_icpc_compressed (src/dsp_icpc.jl:293-499) with random presum rates, window placements and configurations"""
+    from test_gpu_compressed import _check, _data
+    from parity import TOL
+    rng = np.random.default_rng(300 + seed)
+    presum = int(rng.choice([2, 4, 8]))
+    # the full-rate window must hold the current window (43 .. 62 us = samples 2688 .. 3875) plus the filter lengths
+    w0 = int(rng.integers(2300, 2650))
+    wlen = int((3950 - w0 + rng.integers(0, 300)) // 8 * 8)
+    tau_c = L.us(float(rng.uniform(200.0, 800.0)))
+    cfg = L.tiefree_config() if seed == 0 else L.example_config()
+    n_events = 256
+    data = _data(L, n_events, 11000 * (seed + 1), presum, window=(w0, wlen))
+    res = L.dsp_icpc_compressed(data, cfg, tau_c, None, handle=handle, builders=O.OracleBuilders())
+    wp, ww = data["waveform_presummed"], data["waveform_windowed"]
+    Pp, Pw, aux = L.resolve_compressed_params(cfg, tau_c, None, presum_rate=presum, n_pre=wp.signal.shape[1],
+                                              t_first_pre=wp.t_first, step_pre=wp.step, n_wdw=ww.signal.shape[1],
+                                              t_first_wdw=ww.t_first, step_wdw=ww.step, builders=O.OracleBuilders())
+    ref = O.dsp_icpc_compressed(Pp, Pw, wp.signal, ww.signal, presum, aux)
+    bad = _check(res, ref, skip=("a_sg", "a_60", "a_100", "a_raw"))
+    assert not bad, bad
+    for col in ("a_sg", "a_60", "a_100", "a_raw"):
+        rtol, atol = TOL[col]
+        n_bad = int((np.abs(res[col] - ref[col]) > atol + rtol * np.abs(ref[col])).sum())
+        assert n_bad <= max(2, n_events // 50), (col, n_bad)
