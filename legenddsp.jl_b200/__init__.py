@@ -22,10 +22,10 @@ from .dsp_icpc import (RDWaveforms, TABLE_COLUMNS, COMPRESSED_COLUMNS, dsp_icpc,
 from .dsp_filter_optimization import (dsp_trap_rt_optimization, dsp_trap_ft_optimization, dsp_trap_rtft_grid,
                                       dsp_cusp_rt_optimization, dsp_zac_rt_optimization, dsp_cusp_ft_optimization,
                                       dsp_zac_ft_optimization, dsp_sg_optimization, dsp_qc_flt_optimization,
-                                      dsp_qdrift_flt_optimization)
-from .dsp_sipm import (dsp_sipm, sipm_rows, sipm_to_table, resolve_sipm_params, example_sipm_config, SIPM_TABLE,
+                                      dsp_qc_flt_optimization_compressed, dsp_qdrift_flt_optimization)
+from .dsp_sipm import (dsp_sipm, dsp_sipm_compressed, sipm_rows, sipm_to_table, resolve_sipm_params, example_sipm_config, SIPM_TABLE,
                        VectorOfVectors, IntersectMaximum, MultiIntersect, thresholdstats, thresholdstats_mad)
-from .dsp_puls import dsp_puls, dsp_decay_times, resolve_puls_params, PULS_COLUMNS
+from .dsp_puls import dsp_puls, dsp_puls_compressed, dsp_decay_times, resolve_puls_params, PULS_COLUMNS
 from . import synth, sharding
 
 __all__ = [
@@ -36,7 +36,8 @@ __all__ = [
     "dsp_cusp_rt_optimization", "dsp_zac_rt_optimization", "dsp_cusp_ft_optimization", "dsp_zac_ft_optimization",
     "dsp_sg_optimization", "dsp_puls", "dsp_decay_times", "resolve_puls_params", "PULS_COLUMNS", "trap_sweep_variants", "cuspzac_sweep_variants", "sg_sweep_variants",
     "dsp_icpc_compressed", "compressed_to_table", "COMPRESSED_COLUMNS", "resolve_compressed_params",
-    "dsp_qc_flt_optimization", "dsp_qdrift_flt_optimization",
+    "dsp_qc_flt_optimization", "dsp_qc_flt_optimization_compressed", "dsp_qdrift_flt_optimization",
+    "dsp_puls_compressed", "dsp_sipm_compressed",
     "dsp_sipm", "sipm_rows", "sipm_to_table", "resolve_sipm_params", "example_sipm_config", "SIPM_TABLE", "VectorOfVectors",
     "IntersectMaximum", "MultiIntersect", "thresholdstats", "thresholdstats_mad",
     "synth", "sharding", "COLUMNS", "COL", "INT_COLUMNS", "NCOL", "UNITS",

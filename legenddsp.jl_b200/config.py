@@ -367,15 +367,19 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
     presummed waveform needs (saturation with sat_high * presum_rate :334, windows, energy filters, the in-trace filter
     SavitzkyGolayFilter(sg_wl * presum_rate / 2) :439), "wdw" what the windowed waveform needs (t0, t10..t99, Q-drift,
     currents).  What a pass does not use is filled with the smallest valid placeholder (its groups are switched off or
-    its columns are not read)."""
+    its columns are not read).  "puls" is the pulser chain (`dsp_puls`, src/dsp_puls.jl:29-66): baseline window, t50 and the
+    (10 us, 4 us) trapezoid only -- everything else is a placeholder, so that presummed time axes (64 / 128 ns steps, on
+    which the 60 ns / 100 ns filters of the full chain have no samples) resolve."""
     if builders is None:
         builders = LibBuilders()
-    if role not in ("full", "pre", "wdw"):
+    if role not in ("full", "pre", "wdw", "puls"):
         raise ValueError(f"unknown role {role!r}")
     if role == "pre":
         groups = _abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_TRAPS | _abi.GROUP_CUSPZAC | _abi.GROUP_INTRACE
     elif role == "wdw":
         groups = _abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_QDRIFT | _abi.GROUP_CURRENT
+    elif role == "puls":
+        groups = _abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_TRAPS
     dummy_trap = _abi.Trap(1, 0, 1, 0)
     kw = cfg.kwargs_pars
     P = _abi.IcpcParams()
@@ -405,7 +409,10 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
         P.tail_from, P.tail_until = max(0, n - 16), n - 1
     else:
         P.bl_from, P.bl_until = window(cfg.bl_window, t_first, n, "bl_window")
-        P.tail_from, P.tail_until = window(cfg.tail_window, t_first, n, "tail_window")
+        if role == "puls":      # no tail statistics in dsp_puls
+            P.tail_from, P.tail_until = max(0, n - 16), n - 1
+        else:
+            P.tail_from, P.tail_until = window(cfg.tail_window, t_first, n, "tail_window")
 
     # InvCRFilter(tau) [RDDSP]: RC = tau/dt, alpha = RC/(RC+1), k = 1/alpha
     RC = _ratio(tau, step)
@@ -414,13 +421,13 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
 
     # get_t0: src/dsp_routines.jl:9-25
     fp = kw["t0_flt_pars"]
-    if role == "pre":
+    if role in ("pre", "puls"):
         P.t0_trap = P.t0inv_trap = dummy_trap     # t0 / t0_inv come from the windowed waveform (:378, :458)
     else:
         P.t0_trap = _trap(fp[0], fp[1], step, fp[2])
         P.t0inv_trap = _trap(ns(40.0), ns(100.0), step, ns(2000.0))   # default flt_pars, src/dsp_icpc.jl:207
     # the presummed pass has no t0 (its trapezoid is a placeholder): a threshold nothing reaches keeps the crossing search idle
-    P.t0_threshold = 1e300 if role == "pre" else float(cfg.t0_threshold)
+    P.t0_threshold = 1e300 if role in ("pre", "puls") else float(cfg.t0_threshold)
     P.t0_min_n = _min_n(kw["t0_mintot"], step)
     P.tx_min_n = _min_n(kw["tx_mintot"], step)
     for i, f in enumerate((0.1, 0.5, 0.8, 0.9, 0.99)):
@@ -431,11 +438,11 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
     P.qdrift_last_ns = cfg.qdrift_int_length[2].ns()
     P.lq_first_ns = cfg.lq_int_length[0].ns()
     P.lq_last_ns = cfg.lq_int_length[2].ns()
-    if role == "pre":   # Q-drift is evaluated on the windowed waveform only (:391-394)
+    if role in ("pre", "puls"):   # Q-drift is evaluated on the windowed waveform only (:391-394)
         _fill_dni(P.int_dni, 1, step * 2.0, step, builders)
     else:
         _fill_dni(P.int_dni, int(kw["int_interpolation_order"]), kw["int_interpolation_length"], step, builders)
-    if role == "wdw":   # the SignalEstimator of the energies runs on the presummed waveform only (:407-428)
+    if role in ("wdw", "puls"):   # the SignalEstimator of the energies runs on the presummed waveform only (:407-428)
         _fill_dni(P.sig_dni, 1, step * 2.0, step, builders)
     else:
         _fill_dni(P.sig_dni, int(kw["sig_interpolation_order"]), kw["sig_interpolation_length"], step, builders)
@@ -447,6 +454,9 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
     sg_wl = get_fltpars(pars_filter, "sg", cfg)
     if role == "wdw":
         P.trap_10410 = P.trap_535 = P.trap_313 = P.trap_e = dummy_trap
+    elif role == "puls":
+        P.trap_10410 = _trap(us(10.0), us(4.0), step)          # src/dsp_puls.jl:56
+        P.trap_535 = P.trap_313 = P.trap_e = P.trap_10410      # unused columns: the same smooth trace (cheap pruning)
     else:
         P.trap_10410 = _trap(us(10.0), us(4.0), step)
         P.trap_535 = _trap(us(5.0), us(3.0), step)
@@ -462,7 +472,7 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
 
     # CUSP / ZAC: src/dsp_icpc.jl:87-90,98-99,167,174
     tau_off = us(10000000.0)
-    if role == "wdw":
+    if role in ("wdw", "puls"):
         for cz in (P.cusp, P.zac):
             cz.n_taps, cz.flat, cz.sigma, cz.tau, cz.beta = 4, 0, 1.0, 1.0, 1.0
     else:
@@ -475,7 +485,12 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
 
     # currents: src/dsp_icpc.jl:181-186
     deg = int(cfg.sg_flt_degree)
-    if role == "pre":
+    if role == "puls":
+        for k in range(3):
+            _fill_sg(P.sg[k], step * 5.0, deg, step, policy, builders)
+            P.cur_from[k], P.cur_until[k] = 0, n - P.sg[k].n_taps
+        P.cur_from[3], P.cur_until[3] = 0, n - 1
+    elif role == "pre":
         # :439 the in-trace / current-rise filter of the presummed waveform; the currents themselves (:431-435) are
         # taken from the windowed waveform
         for k in range(3):
@@ -498,7 +513,7 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
     P.intrace_min_n = _min_n(kw["intrace_mintot"], step)
     first_sg = t_first + step * float(P.sg[0].offset)
     n_sg = n - P.sg[0].n_taps + 1
-    if role == "wdw":
+    if role in ("wdw", "puls"):
         a, b = 0, min(n_sg - 1, 15)       # in-trace pile-up is evaluated on the presummed waveform (:440)
     else:
         a = _sub_over_step(cfg.bl_window[0] + first_sg, first_sg, step)   # leftendpoint + first(time), :75

@@ -168,6 +168,12 @@ def dsp_qc_flt_optimization(wvfs, config: DSPConfig, τ: Q, f_evaluate_qc=None, 
                        qc_label=np.full(out.shape[0], -1, dtype=np.int64))
 
 
+def dsp_qc_flt_optimization_compressed(wvfs, config: DSPConfig, τ: Q, f_evaluate_qc=None, **kw):
+    """`dsp_qc_flt_optimization_compressed(wvfs, config, τ, missing)` (src/dsp_filter_optimization.jl:26-28): without a
+    classifier the same `_get_dsp_qc_flt_optimization(wvfs, config, τ, nothing)` as the uncompressed entry"""
+    return dsp_qc_flt_optimization(wvfs, config, τ, f_evaluate_qc, **kw)
+
+
 def dsp_qdrift_flt_optimization(wvfs, blmean, config: DSPConfig, τ: Q, *, device: int = 0, handle: Optional[Handle] = None,
                                 builders=None) -> np.ndarray:
     """Q-drift for the filter optimisation (src/dsp_filter_optimization.jl:72-90): the waveforms are shifted by the GIVEN

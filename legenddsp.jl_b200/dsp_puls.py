@@ -27,7 +27,7 @@ def resolve_puls_params(config: DSPConfig, *, n_samples: int = 8192, t_first: Q 
                         policy: RddspPolicy = DEFAULT_POLICY, builders=None) -> _abi.IcpcParams:
     """dsp_icpc parameters specialised to the pulser chain: no pole-zero correction, default get_threshold mintot"""
     P = resolve_icpc_params(config, us(500.0), None, n_samples=n_samples, t_first=t_first, step=step,
-                            groups=_abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_TRAPS, policy=policy, builders=builders)
+                            role="puls", policy=policy, builders=builders)
     P.pz_km1 = 0.0                               # no InvCRFilter in dsp_puls
     P.tx_min_n = _min_n(ns(1000.0), step)        # get_threshold(wvfs, thr) default mintot  (src/dsp_routines.jl:33)
     return P
@@ -42,6 +42,33 @@ def dsp_puls(data: Mapping[str, Any], config: DSPConfig, *, device: int = 0, han
     h = handle or get_handle(device)
     rows = np.zeros((sig.shape[0], _abi.NCOL), dtype=np.float64)
     h.icpc_run_host(P, sig.ctypes.data, sig.shape[0], sig.strides[0] // 2, rows.ctypes.data)
+    out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    for name in PULS_COLUMNS:
+        if name in _PASS:
+            if _PASS[name] in data:
+                out[name] = np.asarray(data[_PASS[name]])
+        else:
+            out[name] = np.ascontiguousarray(rows[:, _abi.COL[name]])
+    return out
+
+
+def dsp_puls_compressed(data: Mapping[str, Any], config: DSPConfig, *, device: int = 0, handle: Optional[Handle] = None,
+                        policy: RddspPolicy = DEFAULT_POLICY) -> "OrderedDict[str, np.ndarray]":
+    """`dsp_puls_compressed(data, config)` (src/dsp_puls.jl:98-134): `dsp_puls` on `decode_data(data.waveform_presummed)`.
+    The codec (LegendDataTypes.decode_data) is outside the reference tree: `data["waveform_presummed"]` holds the DECODED
+    integer samples (uint16, or uint32 sums of at most 4096 samples per waveform)."""
+    w = _as_waveforms(data["waveform_presummed"])
+    sig = np.asarray(w.signal)
+    if sig.dtype == np.uint32 or (sig.dtype.kind in "iu" and sig.dtype.itemsize > 2 and sig.size and int(sig.max()) > 65535):
+        sig = np.ascontiguousarray(sig, dtype=np.uint32)
+        sample_bytes = 4
+    else:
+        sig = _signal_u16(sig)
+        sample_bytes = 2
+    P = resolve_puls_params(config, n_samples=sig.shape[1], t_first=w.t_first, step=w.step, policy=policy)
+    h = handle or get_handle(device)
+    rows = np.zeros((sig.shape[0], _abi.NCOL), dtype=np.float64)
+    h.icpc_run_ext_host(P, sig.ctypes.data, sample_bytes, None, sig.shape[0], sig.strides[0] // sample_bytes, rows.ctypes.data)
     out: "OrderedDict[str, np.ndarray]" = OrderedDict()
     for name in PULS_COLUMNS:
         if name in _PASS:

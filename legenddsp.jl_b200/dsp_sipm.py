@@ -175,6 +175,15 @@ def dsp_sipm(data: Mapping[str, Any], config: Mapping[str, Any], pars_optimizati
     return sipm_to_table(rows, trig, data)
 
 
+def dsp_sipm_compressed(data: Mapping[str, Any], config: Mapping[str, Any], pars_optimization: Mapping[str, Any], **kw):
+    """`dsp_sipm_compressed(data, config, pars_optimization)` (src/dsp_sipm.jl:207-318): `dsp_sipm` on
+    `decode_data(data.waveform_bit_drop)` -- the two functions differ in that line only.  The codec is outside the
+    reference tree: `data["waveform_bit_drop"]` holds the DECODED samples."""
+    d = dict(data)
+    d["waveform"] = d["waveform_bit_drop"]
+    return dsp_sipm(d, config, pars_optimization, **kw)
+
+
 # ---- the in-tree primitives on single traces (GPU, through the C ABI) ----
 def thresholdstats(signal, min: float = -np.inf, max: float = np.inf, *, device: int = 0, handle: Optional[Handle] = None) -> float:
     """standard deviation of the samples inside [min, max]  (src/thresholdstats.jl:19-41)"""

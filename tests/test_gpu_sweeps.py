@@ -134,7 +134,8 @@ def test_dsp_puls_and_decay_times(L, O, handle):
     cfg = L.example_config()
     tau2 = L.dsp_decay_times(L.RDWaveforms(wf), cfg.bl_window, cfg.tail_window, handle=handle)
     assert np.array_equal(tau, tau2)
-    ref_tau = ref[:, L.COL["tail_tau"]] * 1e-3
+    ref_full, _ = O.dsp_icpc(Pz, wf)            # (the pulser parameter block carries a placeholder tail window)
+    ref_tau = ref_full[:, L.COL["tail_tau"]] * 1e-3
     inv = lambda t: np.where(t == 0, 0.0, 1.0 / np.where(t == 0, 1.0, t))
     assert np.allclose(inv(tau), inv(ref_tau), rtol=1e-7, atol=1e-10)
     good = (full[:, L.COL["e_max"]] > 5000) & (full[:, L.COL["n_sat_high"]] == 0) & (full[:, L.COL["inTrace_n"]] == 1)
@@ -165,3 +166,60 @@ def test_qc_and_qdrift_flt_optimization(L, O, handle):
     assert (t0ref > 0).sum() > 200
     with pytest.raises(ValueError):
         L.dsp_qdrift_flt_optimization(W, bl[:-1], cfg, tau, handle=handle)
+
+
+def test_compressed_entry_points_of_the_subset_chains(L, O, handle):
+    """dsp_puls_compressed (src/dsp_puls.jl:98-134), dsp_sipm_compressed (src/dsp_sipm.jl:207-318) and
+    dsp_qc_flt_optimization_compressed without a classifier (src/dsp_filter_optimization.jl:26-28) differ from their
+    plain counterparts only in the input column / decode_data: same kernels on the decoded samples"""
+    from test_gpu_sipm import sipm_population
+    n = 128
+    wf = L.synth.generate_host(n, first_event=777)
+    # presummed waveform (rate 4) stored as 32-bit sums divided back to the ADC scale: 2048 samples of 64 ns
+    pre = (wf.astype(np.uint32).reshape(n, -1, 4).sum(axis=2) // 4).astype(np.uint32)
+    step = L.ns(64.0)
+    data = {"waveform_presummed": L.RDWaveforms(pre, L.ns(0.0), step), "baseline": np.zeros(n, np.float32),
+            "timestamp": np.arange(n, dtype=np.uint64), "eventnumber": np.arange(n, dtype=np.uint32),
+            "daqenergy": np.zeros(n, np.uint16)}
+    tab = L.dsp_puls_compressed(data, L.example_config(), handle=handle)
+    assert tuple(tab.keys()) == L.PULS_COLUMNS
+    P = L.resolve_puls_params(L.example_config(), n_samples=2048, step=step, builders=O.OracleBuilders())
+    ref, _ = O.dsp_icpc(P, pre.astype(np.uint16))
+    for name, tol in (("blmean", 0), ("blsigma", 1e-9), ("blslope", 1e-15), ("bloffset", 1e-8), ("t50", 1e-7), ("e_max", 0),
+                      ("e_10410", 1e-7)):
+        a, b = tab[name], ref[:, L.COL[name]]
+        assert np.all(np.abs(a - b) <= tol + 1e-9 * np.abs(b)), name
+    # the same samples as uint16 go through the 16-bit instantiation: identical table
+    data16 = dict(data, waveform_presummed=L.RDWaveforms(pre.astype(np.uint16), L.ns(0.0), step))
+    tab16 = L.dsp_puls_compressed(data16, L.example_config(), handle=handle)
+    assert all(np.array_equal(tab[k], tab16[k]) for k in tab)
+    # true 32-bit sums (values above 65535): every linear column scales by the presum rate
+    data32 = dict(data, waveform_presummed=L.RDWaveforms(pre * 4, L.ns(0.0), step))
+    tab32 = L.dsp_puls_compressed(data32, L.example_config(), handle=handle)
+    assert int((pre * 4).max()) > 65535
+    for name in ("blmean", "blsigma", "e_max", "e_10410"):
+        assert np.allclose(tab32[name], 4.0 * tab[name], rtol=1e-12, atol=1e-9), name
+    assert np.allclose(tab32["t50"], tab["t50"], rtol=0, atol=1e-9)
+
+    # dsp_sipm_compressed == dsp_sipm on the decoded bit-drop waveform
+    swf = sipm_population(32, seed=5)
+    cfg = L.example_sipm_config()
+    cfg["filters"]["sg"].update(min_threshold=-3.0, max_threshold=3.0, min_dc_threshold=-40.0, max_dc_threshold=40.0)
+    cfg["filters"]["trap"].update(min_threshold=-15.0, max_threshold=15.0, min_dc_threshold=-30.0, max_dc_threshold=30.0)
+    po = {"sg": {"wl": L.ns(200.0)}}
+    common = {"baseline": np.zeros(32, np.float32), "timestamp": np.zeros(32, np.uint64),
+              "eventnumber": np.arange(32, dtype=np.uint32), "daqenergy": np.zeros(32, np.uint16)}
+    a = L.dsp_sipm(dict(common, waveform=L.RDWaveforms(swf)), cfg, po, handle=handle)
+    b = L.dsp_sipm_compressed(dict(common, waveform_bit_drop=L.RDWaveforms(swf)), cfg, po, handle=handle)
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        if isinstance(a[k], L.VectorOfVectors):
+            assert np.array_equal(a[k].data, b[k].data) and np.array_equal(a[k].elem_ptr, b[k].elem_ptr), k
+        else:
+            assert np.array_equal(a[k], b[k]), k
+
+    # dsp_qc_flt_optimization_compressed(wvfs, config, tau, missing) == dsp_qc_flt_optimization(...)
+    W = L.RDWaveforms(wf)
+    q1 = L.dsp_qc_flt_optimization(W, L.example_config(), L.us(500.0), handle=handle)
+    q2 = L.dsp_qc_flt_optimization_compressed(W, L.example_config(), L.us(500.0), handle=handle)
+    assert all(np.array_equal(q1[k], q2[k], equal_nan=True) for k in q1)
