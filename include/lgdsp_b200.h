@@ -413,6 +413,17 @@ int lgdsp_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t
 int lgdsp_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* d_wf, int64_t n_events,
                            int64_t ld_samples, const lgdsp_sweep_variant* variants, int32_t n_variants, void* d_out,
                            double* d_aux);
+/* dsp_sg_optimization_compressed building block (/root/reference/src/dsp_filter_optimization.jl:460-511): the same sweep on
+ * waveforms of 16-bit (sample_bytes = 2) or 32-bit unsigned samples (4: presummed traces, n_samples <= LGDSP_MAX_SAMPLES/2)
+ * with an optional per-event EXTERNAL baseline: when baseline != NULL the waveform is shifted by -baseline[e] instead of
+ * by its own bl_window mean (:476-477: the windowed waveform is shifted by the presummed baseline / presum_rate).  The aux
+ * outputs keep the statistics of the waveform's own bl_window. */
+int lgdsp_sweep_run_ext(lgdsp_handle* h, const lgdsp_sweep_params* p, const void* wf, int32_t sample_bytes, const double* baseline,
+                        int64_t n_events, int64_t ld_samples, const lgdsp_sweep_variant* variants, int32_t n_variants, void* out,
+                        double* aux);
+int lgdsp_sweep_run_ext_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const void* d_wf, int32_t sample_bytes,
+                               const double* d_baseline, int64_t n_events, int64_t ld_samples,
+                               const lgdsp_sweep_variant* variants, int32_t n_variants, void* d_out, double* d_aux);
 
 /* ---- dsp_sipm ---- */
 /* wf: n_events waveforms of `sample_kind` samples, row stride ld_samples (in samples); rows: double[n_events][

@@ -21,7 +21,7 @@ from .dsp_icpc import (RDWaveforms, TABLE_COLUMNS, COMPRESSED_COLUMNS, dsp_icpc,
                        dsp_icpc_compressed, compressed_to_table)
 from .dsp_filter_optimization import (dsp_trap_rt_optimization, dsp_trap_ft_optimization, dsp_trap_rtft_grid,
                                       dsp_cusp_rt_optimization, dsp_zac_rt_optimization, dsp_cusp_ft_optimization,
-                                      dsp_zac_ft_optimization, dsp_sg_optimization, dsp_qc_flt_optimization,
+                                      dsp_zac_ft_optimization, dsp_sg_optimization, dsp_sg_optimization_compressed, dsp_qc_flt_optimization,
                                       dsp_qc_flt_optimization_compressed, dsp_qdrift_flt_optimization)
 from .dsp_sipm import (dsp_sipm, dsp_sipm_compressed, sipm_rows, sipm_to_table, resolve_sipm_params, example_sipm_config, SIPM_TABLE,
                        VectorOfVectors, IntersectMaximum, MultiIntersect, thresholdstats, thresholdstats_mad)
@@ -37,7 +37,7 @@ __all__ = [
     "dsp_sg_optimization", "dsp_puls", "dsp_decay_times", "resolve_puls_params", "PULS_COLUMNS", "trap_sweep_variants", "cuspzac_sweep_variants", "sg_sweep_variants",
     "dsp_icpc_compressed", "compressed_to_table", "COMPRESSED_COLUMNS", "resolve_compressed_params",
     "dsp_qc_flt_optimization", "dsp_qc_flt_optimization_compressed", "dsp_qdrift_flt_optimization",
-    "dsp_puls_compressed", "dsp_sipm_compressed",
+    "dsp_puls_compressed", "dsp_sipm_compressed", "dsp_sg_optimization_compressed",
     "dsp_sipm", "sipm_rows", "sipm_to_table", "resolve_sipm_params", "example_sipm_config", "SIPM_TABLE", "VectorOfVectors",
     "IntersectMaximum", "MultiIntersect", "thresholdstats", "thresholdstats_mad",
     "synth", "sharding", "COLUMNS", "COL", "INT_COLUMNS", "NCOL", "UNITS",

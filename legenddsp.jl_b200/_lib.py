@@ -70,6 +70,9 @@ def load_library():
                                               C.POINTER(_abi.TrapVariant), i32, vp]
     L.lgdsp_sweep_run.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64, C.POINTER(_abi.SweepVariant), i32, vp, vp]
     L.lgdsp_sweep_run_device.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i64, i64, C.POINTER(_abi.SweepVariant), i32, vp, vp]
+    L.lgdsp_sweep_run_ext.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i32, vp, i64, i64, C.POINTER(_abi.SweepVariant), i32, vp, vp]
+    L.lgdsp_sweep_run_ext_device.argtypes = [vp, C.POINTER(_abi.SweepParams), vp, i32, vp, i64, i64, C.POINTER(_abi.SweepVariant), i32,
+                                             vp, vp]
     L.lgdsp_synth_generate_device.argtypes = [vp, C.POINTER(_abi.SynthParams), i64, i64, i64, vp]
     L.lgdsp_synth_generate_host.argtypes = [C.POINTER(_abi.SynthParams), i64, i64, i64, vp]
     L.lgdsp_debug_phase_cycles.argtypes = [vp, C.c_int, _dp]
@@ -86,6 +89,7 @@ EXPORTED_SYMBOLS = (
     "lgdsp_window_stats_run", "lgdsp_window_stats_run_device", "lgdsp_sipm_run", "lgdsp_sipm_run_device",
     "lgdsp_sipm_list_pointers_device", "lgdsp_sipm_list_gather_device", "lgdsp_thresholdstats", "lgdsp_intersect_maximum", "lgdsp_multi_intersect_run", "lgdsp_multi_intersect_run_device", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
     "lgdsp_trap_sweep_run", "lgdsp_trap_sweep_run_device", "lgdsp_sweep_run", "lgdsp_sweep_run_device",
+    "lgdsp_sweep_run_ext", "lgdsp_sweep_run_ext_device",
     "lgdsp_synth_generate_device", "lgdsp_synth_generate_host", "lgdsp_last_kernel_ms", "lgdsp_debug_phase_cycles", "lgdsp_debug_section_cycles",
 )
 
@@ -269,6 +273,20 @@ class Handle:
         self._check(self._lib.lgdsp_sweep_run_device(self._h, C.byref(sparams), C.c_void_p(d_wf_ptr), int(n_events), int(ld),
                                                      variants, len(variants), C.c_void_p(d_out_ptr),
                                                      C.c_void_p(d_aux_ptr) if d_aux_ptr else None))
+
+    def gsweep_run_ext_host(self, sparams, wf_ptr, sample_bytes, baseline_ptr, n_events, ld, variants, out_ptr, aux_ptr=None):
+        """general sweep on uint16 / uint32 samples with an optional external per-event baseline (lgdsp_sweep_run_ext)"""
+        self._check(self._lib.lgdsp_sweep_run_ext(self._h, C.byref(sparams), C.c_void_p(wf_ptr), int(sample_bytes),
+                                                  C.c_void_p(baseline_ptr) if baseline_ptr else None, int(n_events), int(ld),
+                                                  variants, len(variants), C.c_void_p(out_ptr),
+                                                  C.c_void_p(aux_ptr) if aux_ptr else None))
+
+    def gsweep_run_ext_device(self, sparams, d_wf_ptr, sample_bytes, d_baseline_ptr, n_events, ld, variants, d_out_ptr,
+                              d_aux_ptr=None):
+        self._check(self._lib.lgdsp_sweep_run_ext_device(self._h, C.byref(sparams), C.c_void_p(d_wf_ptr), int(sample_bytes),
+                                                         C.c_void_p(d_baseline_ptr) if d_baseline_ptr else None, int(n_events),
+                                                         int(ld), variants, len(variants), C.c_void_p(d_out_ptr),
+                                                         C.c_void_p(d_aux_ptr) if d_aux_ptr else None))
 
     # ---- synthetic input ----
     def synth_device(self, sp, first_event, n_events, ld, d_wf_ptr):

@@ -549,7 +549,7 @@ def resolve_compressed_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict
 
 
 def resolve_sweep_params(cfg: DSPConfig, tau: Q, *, n_samples: int = 8192, t_first: Q = ns(0.0),
-                         step: Q = ns(16.0), builders=None, out_f64: bool = False) -> _abi.SweepParams:
+                         step: Q = ns(16.0), builders=None, out_f64: bool = False, external_baseline: bool = False) -> _abi.SweepParams:
     """common part of dsp_trap_rt_optimization / dsp_trap_ft_optimization
     (src/dsp_filter_optimization.jl:102-133, 241-274)"""
     if builders is None:
@@ -562,10 +562,15 @@ def resolve_sweep_params(cfg: DSPConfig, tau: Q, *, n_samples: int = 8192, t_fir
     S.tx_min_n = _min_n(kw["tx_mintot"], step)
     S.t_first_ns = t_first.ns()
     S.dt_ns = step.ns()
-    a = _sub_over_step(cfg.bl_window[0], t_first, step)
-    b = _sub_over_step(cfg.bl_window[1], t_first, step)
-    if not (0 <= a <= b <= n_samples - 1):
-        raise AssertionError(f"bl_window: index range {a + 1}:{b + 1} outside 1:{n_samples}")
+    if external_baseline:
+        # the waveform is shifted by a baseline the caller provides (windowed waveform of the compressed format, whose time
+        # axis does not contain bl_window): the kernel's own window is a placeholder, its statistics are not read
+        a, b = 0, min(int(n_samples) - 1, 15)
+    else:
+        a = _sub_over_step(cfg.bl_window[0], t_first, step)
+        b = _sub_over_step(cfg.bl_window[1], t_first, step)
+        if not (0 <= a <= b <= n_samples - 1):
+            raise AssertionError(f"bl_window: index range {a + 1}:{b + 1} outside 1:{n_samples}")
     S.bl_from, S.bl_until = a, b
     RC = _ratio(tau, step)
     alpha = RC / (RC + 1.0)

@@ -895,23 +895,23 @@ static int sweep_prepare(lgdsp_handle* h, const lgdsp_sweep_params* p, const lgd
     return LGDSP_OK;
 }
 
-int lgdsp_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* d_wf, int64_t n_events,
-                           int64_t ld_samples, const lgdsp_sweep_variant* variants, int32_t n_variants, void* d_out,
-                           double* d_aux)
+static int sweep_run_device_impl(lgdsp_handle* h, const lgdsp_sweep_params* p, const void* d_wf, int sample_bytes,
+                                 const double* d_baseline, int64_t n_events, int64_t ld_samples,
+                                 const lgdsp_sweep_variant* variants, int32_t n_variants, void* d_out, double* d_aux)
 {
     if (!h) return LGDSP_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     SweepDev D{};
     int rc = sweep_prepare(h, p, variants, n_variants, D);
     if (rc) return rc;
-    rc = check_wf(h, d_wf, n_events, ld_samples, D.n, true);
+    rc = check_wf(h, d_wf, n_events, ld_samples, D.n, true, sample_bytes);
     if (rc) return rc;
     if (n_events == 0) return LGDSP_OK;
     if (!d_out) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
     const long long cap = (long long)h->sm_count * h->sweep_bps;
     const int grid = (int)(n_events < cap ? n_events : cap);
     CK(cudaEventRecord(h->ev0, h->stream));
-    sweep_launch(D, d_wf, n_events, ld_samples, d_out, d_aux, grid, h->stream);
+    sweep_launch(D, d_wf, sample_bytes, n_events, ld_samples, d_baseline, d_out, d_aux, grid, h->stream);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
@@ -919,8 +919,9 @@ int lgdsp_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const u
     return LGDSP_OK;
 }
 
-int lgdsp_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* wf, int64_t n_events, int64_t ld_samples,
-                    const lgdsp_sweep_variant* variants, int32_t n_variants, void* out, double* aux)
+static int sweep_run_host_impl(lgdsp_handle* h, const lgdsp_sweep_params* p, const void* wf, int sample_bytes,
+                               const double* baseline, int64_t n_events, int64_t ld_samples,
+                               const lgdsp_sweep_variant* variants, int32_t n_variants, void* out, double* aux)
 {
     if (!h) return LGDSP_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
@@ -928,13 +929,18 @@ int lgdsp_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t
     int rc = sweep_prepare(h, p, variants, n_variants, D);
     if (rc) return rc;
     const int n = D.n;
-    rc = check_wf(h, wf, n_events, ld_samples, n, false);
+    rc = check_wf(h, wf, n_events, ld_samples, n, false, sample_bytes);
     if (rc) return rc;
     if (n_events == 0) return LGDSP_OK;
     if (!out) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
+    const size_t sb = (size_t)sample_bytes;
     const int64_t chunk = n_events < 8192 ? n_events : 8192;
-    rc = ensure_staging(h, (size_t)chunk * n * 2, 0);
+    rc = ensure_staging(h, (size_t)chunk * n * sb, 0);
     if (rc) return rc;
+    if (baseline) {
+        rc = ensure_aux(h, (size_t)2 * chunk * sizeof(double));
+        if (rc) return rc;
+    }
     const size_t esz = D.out_f64 ? sizeof(double) : sizeof(float);
     const size_t ob = (size_t)2 * chunk * (n_variants * esz + 4 * sizeof(double));
     if (ob > h->sweep_out_cap) {
@@ -944,20 +950,26 @@ int lgdsp_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t
     }
     const long long cap = (long long)h->sm_count * h->sweep_bps;
     char* base = reinterpret_cast<char*>(h->d_sweep_out);
+    const unsigned char* src = static_cast<const unsigned char*>(wf);
     const size_t out_bytes = (size_t)chunk * n_variants * esz;   // per buffer; the aux buffers follow the two output buffers
     int c = 0;
     for (int64_t e0 = 0; e0 < n_events; e0 += chunk, ++c) {
         const int b = c & 1;
         const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
         if (c >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
-        CK(cudaMemcpy2DAsync(h->d_in[b], (size_t)n * 2, wf + e0 * ld_samples, (size_t)ld_samples * 2, (size_t)n * 2,
+        CK(cudaMemcpy2DAsync(h->d_in[b], (size_t)n * sb, src + (size_t)e0 * ld_samples * sb, (size_t)ld_samples * sb, (size_t)n * sb,
                              (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
+        double* d_bl = nullptr;
+        if (baseline) {
+            d_bl = h->d_aux + (size_t)b * chunk;
+            CK(cudaMemcpyAsync(d_bl, baseline + e0, (size_t)ne * sizeof(double), cudaMemcpyHostToDevice, h->s_copy));
+        }
         CK(cudaEventRecord(h->ev_ready[b], h->s_copy));
         CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
         void* d_o = base + (size_t)b * out_bytes;
         double* d_a = aux ? reinterpret_cast<double*>(base + 2 * out_bytes) + (size_t)b * chunk * 4 : nullptr;
         const int grid = (int)(ne < cap ? ne : cap);
-        sweep_launch(D, h->d_in[b], ne, n, d_o, d_a, grid, h->stream);
+        sweep_launch(D, h->d_in[b], sample_bytes, ne, n, d_bl, d_o, d_a, grid, h->stream);
         CK(cudaGetLastError());
         h->launches += 1;
         CK(cudaEventRecord(h->ev_free[b], h->stream));
@@ -968,6 +980,33 @@ int lgdsp_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t
     CK(cudaStreamSynchronize(h->s_copy));
     CK(cudaStreamSynchronize(h->stream));
     return LGDSP_OK;
+}
+
+int lgdsp_sweep_run_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* d_wf, int64_t n_events,
+                           int64_t ld_samples, const lgdsp_sweep_variant* variants, int32_t n_variants, void* d_out,
+                           double* d_aux)
+{
+    return sweep_run_device_impl(h, p, d_wf, 2, nullptr, n_events, ld_samples, variants, n_variants, d_out, d_aux);
+}
+
+int lgdsp_sweep_run(lgdsp_handle* h, const lgdsp_sweep_params* p, const uint16_t* wf, int64_t n_events, int64_t ld_samples,
+                    const lgdsp_sweep_variant* variants, int32_t n_variants, void* out, double* aux)
+{
+    return sweep_run_host_impl(h, p, wf, 2, nullptr, n_events, ld_samples, variants, n_variants, out, aux);
+}
+
+int lgdsp_sweep_run_ext_device(lgdsp_handle* h, const lgdsp_sweep_params* p, const void* d_wf, int32_t sample_bytes,
+                               const double* d_baseline, int64_t n_events, int64_t ld_samples,
+                               const lgdsp_sweep_variant* variants, int32_t n_variants, void* d_out, double* d_aux)
+{
+    return sweep_run_device_impl(h, p, d_wf, sample_bytes, d_baseline, n_events, ld_samples, variants, n_variants, d_out, d_aux);
+}
+
+int lgdsp_sweep_run_ext(lgdsp_handle* h, const lgdsp_sweep_params* p, const void* wf, int32_t sample_bytes, const double* baseline,
+                        int64_t n_events, int64_t ld_samples, const lgdsp_sweep_variant* variants, int32_t n_variants, void* out,
+                        double* aux)
+{
+    return sweep_run_host_impl(h, p, wf, sample_bytes, baseline, n_events, ld_samples, variants, n_variants, out, aux);
 }
 
 // the trapezoid-only entry points (kept for callers of the first ABI revision): thin wrappers

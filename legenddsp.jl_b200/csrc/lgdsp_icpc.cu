@@ -2015,12 +2015,16 @@ constexpr int SW_DSCAN = SW_IBUF + 64 * 4;
 constexpr int SW_BAR = SW_DSCAN + 8 * 8;
 constexpr int SW_TOTAL = SW_BAR + 16;
 
+// SAMPLE = uint16_t, or uint32_t for presummed waveforms (n <= 4096); bl_ext != NULL: event e is shifted by bl_ext[e] instead
+// of its own bl_window mean (dsp_sg_optimization_compressed shifts the windowed waveform by the presummed baseline /
+// presum_rate, /root/reference/src/dsp_filter_optimization.jl:477); the aux outputs keep the waveform's own statistics
+template <typename SAMPLE>
 __global__ void __launch_bounds__(NT, 2)
-sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf, long long n_events, long long ld,
-             void* __restrict__ out, double* __restrict__ aux)
+sweep_kernel(const __grid_constant__ SweepDev P, const SAMPLE* __restrict__ wf, long long n_events, long long ld,
+             const double* __restrict__ bl_ext, void* __restrict__ out, double* __restrict__ aux)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint16_t* xs = reinterpret_cast<uint16_t*>(smem + SW_XS);
+    SAMPLE* xs = reinterpret_cast<SAMPLE*>(smem + SW_XS);
     double* TT = reinterpret_cast<double*>(smem + SW_TT);
     uint32_t* mask = reinterpret_cast<uint32_t*>(smem + SW_MASK);
     double* red = reinterpret_cast<double*>(smem + SW_RED);
@@ -2032,7 +2036,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = P.n;
-    const uint32_t wf_bytes = (uint32_t)n * 2u;
+    const uint32_t wf_bytes = (uint32_t)n * (uint32_t)sizeof(SAMPLE);
     const double t_first = P.t_first, dt = P.dt;
     for (int i = tid; i < LGDSP_MAX_DNI * 4; i += NT) dniA[i] = P.dni_A[i];
     if (tid == 0) {
@@ -2052,7 +2056,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
     for (; e < n_events; e += gridDim.x) {
         mbar_wait(bar, phase);
         phase ^= 1;
-        const uint16_t* xp = xs + i0;
+        const SAMPLE* xp = xs + i0;
         uint32_t csum = 0, cq = 0, blS = 0, blSK = 0;
         {
             const int ka = P.bl_from - i0, kb = P.bl_until - i0;
@@ -2095,7 +2099,8 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
         for (int w = 0; w < NWARP; ++w) woff2 += (w < wid) ? dscan[w] : 0.0;
         const double PP_excl = woff2 + incl2 - v2;
         // blmean exactly as signalstats: mean_Y = sum_Y * inv_n
-        const double m = mul_rn(blSd, P.bl_inv_n);
+        const double m_own = mul_rn(blSd, P.bl_inv_n);
+        const double m = bl_ext ? bl_ext[e] : m_own;
         double ymax = -CUDART_INF, ymin = CUDART_INF;   // of this thread's chunk
         {
             uint32_t Pr = P_excl;
@@ -2174,7 +2179,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
         if (aux && tid == 0) {
             const Stats st = stats_finalize(P.bl_inv_n, P.bl_sX, P.bl_sXX, blSd, 0.0, t_first * blSd + dt * blSXd);
             double* a = aux + e * 4;
-            a[0] = m; a[1] = st.slope; a[2] = t50_us; a[3] = 0.0;
+            a[0] = m_own; a[1] = st.slope; a[2] = t50_us; a[3] = 0.0;
         }
         const int n_w = P.sig_dni.n_w, mdeg = P.sig_dni.m;
         // trapezoid variants: ONE THREAD per variant walks its pick-off window (4 look-ups in TT per output; the DNI
@@ -2275,15 +2280,20 @@ sweep_kernel(const __grid_constant__ SweepDev P, const uint16_t* __restrict__ wf
 
 cudaError_t sweep_configure(int* max_blocks_per_sm)
 {
-    cudaError_t err = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_TOTAL);
+    cudaError_t err = cudaFuncSetAttribute(sweep_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_TOTAL);
     if (err != cudaSuccess) return err;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, sweep_kernel, NT, SW_TOTAL);
+    err = cudaFuncSetAttribute(sweep_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_TOTAL);
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, sweep_kernel<uint16_t>, NT, SW_TOTAL);
 }
 
-void sweep_launch(const SweepDev& P, const uint16_t* d_wf, long long n_events, long long ld, void* d_out, double* d_aux,
-                  int grid, cudaStream_t stream)
+void sweep_launch(const SweepDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld, const double* d_bl_ext,
+                  void* d_out, double* d_aux, int grid, cudaStream_t stream)
 {
-    sweep_kernel<<<grid, NT, SW_TOTAL, stream>>>(P, d_wf, n_events, ld, d_out, d_aux);
+    if (sample_bytes == 4)
+        sweep_kernel<uint32_t><<<grid, NT, SW_TOTAL, stream>>>(P, static_cast<const uint32_t*>(d_wf), n_events, ld, d_bl_ext, d_out, d_aux);
+    else
+        sweep_kernel<uint16_t><<<grid, NT, SW_TOTAL, stream>>>(P, static_cast<const uint16_t*>(d_wf), n_events, ld, d_bl_ext, d_out, d_aux);
 }
 
 void icpc_launch(const IcpcDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld, const double* d_bl_ext,

@@ -40,8 +40,8 @@ struct SweepDev {
     double bl_inv_n, bl_sX, bl_sXX;   // baseline regression constants (aux outputs)
 };
 cudaError_t sweep_configure(int* max_blocks_per_sm);
-void sweep_launch(const SweepDev& P, const uint16_t* d_wf, long long n_events, long long ld, void* d_out, double* d_aux,
-                  int grid, cudaStream_t stream);
+void sweep_launch(const SweepDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld, const double* d_bl_ext,
+                  void* d_out, double* d_aux, int grid, cudaStream_t stream);
 
 // synthetic generator
 void synth_launch(const lgdsp_synth_params& sp, long long first_event, long long n_events, long long ld, uint16_t* d_wf,

@@ -153,6 +153,52 @@ def dsp_sg_optimization(wvfs, config: DSPConfig, τ: Q, pars_filter, *, f_evalua
                        t50=aux[:, 2].copy(), qc_label=np.full(sig.shape[0], -1, dtype=np.int64))
 
 
+def _int_samples(sig):
+    """decoded integer samples -> (contiguous uint16 | uint32 array, bytes per sample)"""
+    a = np.asarray(sig)
+    if a.dtype == np.uint32 or (a.dtype.kind in "iu" and a.dtype.itemsize > 2 and a.size and int(a.max()) > 65535):
+        return np.ascontiguousarray(a, dtype=np.uint32), 4
+    return _signal_u16(a), 2
+
+
+def dsp_sg_optimization_compressed(wvfs_wdw, wvfs_pre, config: DSPConfig, τ: Q, pars_filter, *, presum_rate: float = 8.0,
+                                   f_evaluate_qc=None, policy: RddspPolicy = DEFAULT_POLICY, device: int = 0,
+                                   handle: Optional[Handle] = None):
+    """Savitzky-Golay window-length sweep on the compressed format (src/dsp_filter_optimization.jl:460-511): baseline,
+    pole-zero correction, t50 and the trap(rt, ft) energy from the PRESUMMED waveform (:469-495), the current maxima from the
+    WINDOWED waveform shifted by blmean / presum_rate (:477, :498-503).  Same table as `dsp_sg_optimization`
+    (aoe, energy, blmean, blslope, t50, qc_label)."""
+    if f_evaluate_qc is not None:
+        raise NotImplementedError("f_evaluate_qc is not supported; qc_label is -1 as in the reference without a model")
+    wp, ww = _as_waveforms(wvfs_pre), _as_waveforms(wvfs_wdw)
+    sp, sbp = _int_samples(wp.signal)
+    sw, sbw = _int_samples(ww.signal)
+    if sp.shape[0] != sw.shape[0]:
+        raise ValueError("presummed and windowed waveforms: different event counts")
+    n_events = sp.shape[0]
+    rt, ft = pars_filter["trap"]["rt"], pars_filter["trap"]["ft"]        # :467-468
+    wls = grid_values(config.a_grid_wl_sg)
+    h = handle or get_handle(device)
+    # presummed waveform: one trapezoid variant at t50 + rt + ft/2 and the aux outputs (blmean, blslope, t50)
+    S_pre = resolve_sweep_params(config, τ, n_samples=sp.shape[1], t_first=wp.t_first, step=wp.step, out_f64=True)
+    ev = trap_sweep_variants([rt], [ft], wp.step, mode="ft")
+    energy = np.zeros((n_events, 1), dtype=np.float64)
+    aux = np.zeros((n_events, 4), dtype=np.float64)
+    h.gsweep_run_ext_host(S_pre, sp.ctypes.data, sbp, None, n_events, sp.strides[0] // sbp, ev.array, energy.ctypes.data,
+                          aux.ctypes.data)
+    # windowed waveform, shifted by the presummed baseline / presum_rate: the window-length grid
+    S_wdw = resolve_sweep_params(config, τ, n_samples=sw.shape[1], t_first=ww.t_first, step=ww.step, out_f64=True,
+                                 external_baseline=True)
+    sgv = sg_sweep_variants(config, wls, n_samples=sw.shape[1], t_first=ww.t_first, step=ww.step, policy=policy)
+    bl = np.ascontiguousarray(aux[:, 0] / float(presum_rate))
+    a = np.zeros((n_events, len(wls)), dtype=np.float64)
+    h.gsweep_run_ext_host(S_wdw, sw.ctypes.data, sbw, bl.ctypes.data, n_events, sw.strides[0] // sbw, sgv.array, a.ctypes.data, None)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        aoe = a / energy
+    return OrderedDict(aoe=np.ascontiguousarray(aoe), energy=energy[:, 0].copy(), blmean=aux[:, 0].copy(),
+                       blslope=aux[:, 1].copy(), t50=aux[:, 2].copy(), qc_label=np.full(n_events, -1, dtype=np.int64))
+
+
 def dsp_qc_flt_optimization(wvfs, config: DSPConfig, τ: Q, f_evaluate_qc=None, *, device: int = 0,
                             handle: Optional[Handle] = None):
     """QC DSP for the filter optimisation without a classifier (src/dsp_filter_optimization.jl:12-14, 31-70): table with

@@ -1297,8 +1297,10 @@ ORC_API int orc_trap_sweep(const lgdsp_sweep_params* P, const uint16_t* wf, int6
  *   kind 2  SavitzkyGolayFilter -> get_wvf_maximum inside current_window                     :432-433
  * out: double[n_events][n_variants]; aux (optional): double[n_events][4] = blmean, blslope, t50 [us], 0   (:436-438)
  * ------------------------------------------------------------------------------------------------ */
-ORC_API int orc_sweep(const lgdsp_sweep_params* P, const uint16_t* wf, int64_t n_events, int64_t ld,
-                      const lgdsp_sweep_variant* var, int n_var, double* out, double* aux, int n_threads)
+/* sample_bytes 2 / 4 (uint16 / uint32 samples); baseline != NULL: event e is shifted by -baseline[e] instead of by its own
+ * bl_window mean (the windowed waveform of dsp_sg_optimization_compressed, src/dsp_filter_optimization.jl:476-477) */
+ORC_API int orc_sweep_ext(const lgdsp_sweep_params* P, const void* wf, int sample_bytes, const double* baseline, int64_t n_events,
+                          int64_t ld, const lgdsp_sweep_variant* var, int n_var, double* out, double* aux, int n_threads)
 {
     int used = 1;
 #ifdef _OPENMP
@@ -1314,11 +1316,16 @@ ORC_API int orc_sweep(const lgdsp_sweep_params* P, const uint16_t* wf, int64_t n
 #pragma omp for schedule(dynamic, 1)
 #endif
         for (int64_t e = 0; e < n_events; ++e) {
-            const uint16_t* raw = wf + e * ld;
-            for (int i = 0; i < n; ++i) w[i] = (double)raw[i];
+            if (sample_bytes == 4) {
+                const uint32_t* raw = (const uint32_t*)wf + e * ld;
+                for (int i = 0; i < n; ++i) w[i] = (double)raw[i];
+            } else {
+                const uint16_t* raw = (const uint16_t*)wf + e * ld;
+                for (int i = 0; i < n; ++i) w[i] = (double)raw[i];
+            }
             double bl[4];
             orc_signalstats(w, P->t_first_ns, P->dt_ns, P->bl_from, P->bl_until, bl);
-            double shift = -bl[0];
+            double shift = baseline ? -baseline[e] : -bl[0];
             for (int i = 0; i < n; ++i) w[i] = w[i] + shift;
             orc_invcr(w, n, P->pz_km1, flt);
             memcpy(w, flt, sizeof(double) * (size_t)n);
@@ -1352,6 +1359,12 @@ ORC_API int orc_sweep(const lgdsp_sweep_params* P, const uint16_t* wf, int64_t n
         free(w);
     }
     return used;
+}
+
+ORC_API int orc_sweep(const lgdsp_sweep_params* P, const uint16_t* wf, int64_t n_events, int64_t ld,
+                      const lgdsp_sweep_variant* var, int n_var, double* out, double* aux, int n_threads)
+{
+    return orc_sweep_ext(P, wf, 2, NULL, n_events, ld, var, n_var, out, aux, n_threads);
 }
 
 ORC_API int orc_num_threads(void)

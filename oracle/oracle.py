@@ -346,5 +346,34 @@ def sweep(sparams, wf_u16, variants, n_threads=0, want_aux=False):
     return (out, aux) if want_aux else out
 
 
+def sweep_ext(sparams, wf, variants, baseline=None, n_threads=0, want_aux=False):
+    """orc_sweep_ext: general sweep on uint16 / uint32 samples with an optional external per-event baseline"""
+    wf = np.ascontiguousarray(wf)
+    if wf.dtype not in (np.uint16, np.uint32):
+        raise TypeError("uint16 or uint32 samples")
+    n_ev, ld = wf.shape
+    nv = len(variants)
+    out = np.zeros((n_ev, nv), dtype=np.float64)
+    aux = np.zeros((n_ev, 4), dtype=np.float64) if want_aux else None
+    bl = None if baseline is None else np.ascontiguousarray(baseline, dtype=np.float64)
+    L = lib()
+    L.orc_sweep_ext.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp, C.c_int64, C.c_int64, C.c_void_p, C.c_int, _dp, _dp, C.c_int]
+    L.orc_sweep_ext(C.byref(sparams), wf.ctypes.data, wf.dtype.itemsize, bl.ctypes.data_as(_dp) if bl is not None else None, n_ev, ld,
+                    C.cast(variants, C.c_void_p), nv, out.ctypes.data_as(_dp), aux.ctypes.data_as(_dp) if want_aux else None,
+                    int(n_threads))
+    return (out, aux) if want_aux else out
+
+
+def dsp_sg_optimization_compressed(S_pre, S_wdw, wf_pre, wf_wdw, energy_variant, sg_variants, presum_rate):
+    """oracle dsp_sg_optimization_compressed (src/dsp_filter_optimization.jl:460-511) on resolved sweep parameters:
+    baseline statistics, pole-zero correction, t50 and the trap(rt, ft) energy on the presummed waveform (:469-495), the
+    Savitzky-Golay window-length sweep on the windowed waveform shifted by blmean / presum_rate (:477, :498-503)"""
+    e, aux = sweep_ext(S_pre, wf_pre, energy_variant, want_aux=True)
+    a = sweep_ext(S_wdw, wf_wdw, sg_variants, baseline=aux[:, 0] / float(presum_rate))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        aoe = a / e[:, :1]
+    return dict(aoe=aoe, energy=e[:, 0].copy(), blmean=aux[:, 0].copy(), blslope=aux[:, 1].copy(), t50=aux[:, 2].copy())
+
+
 def num_threads():
     return lib().orc_num_threads()

@@ -223,3 +223,61 @@ def test_compressed_entry_points_of_the_subset_chains(L, O, handle):
     q1 = L.dsp_qc_flt_optimization(W, L.example_config(), L.us(500.0), handle=handle)
     q2 = L.dsp_qc_flt_optimization_compressed(W, L.example_config(), L.us(500.0), handle=handle)
     assert all(np.array_equal(q1[k], q2[k], equal_nan=True) for k in q1)
+
+
+@pytest.mark.parametrize("presum", [8, 2, 1])
+def test_sg_optimization_compressed(L, O, handle, presum):
+    """dsp_sg_optimization_compressed (src/dsp_filter_optimization.jl:460-511) through lgdsp_sweep_run_ext (32-bit presummed
+    samples; windowed waveform with the external baseline blmean / presum_rate) against the oracle's restatement"""
+    from test_gpu_compressed import _data
+    cfg = L.tiefree_config()
+    tau = L.us(500.0)
+    n = 192
+    data = _data(L, n, 4000, presum)
+    wp, ww = data["waveform_presummed"], data["waveform_windowed"]
+    assert wp.signal.dtype == (np.uint32 if presum > 1 else np.uint16)
+    pf = {"trap": {"rt": L.us(6.0), "ft": L.us(2.0)}}
+    tab = L.dsp_sg_optimization_compressed(ww, wp, cfg, tau, pf, presum_rate=float(presum), handle=handle)
+    assert list(tab.keys()) == ["aoe", "energy", "blmean", "blslope", "t50", "qc_label"] and (tab["qc_label"] == -1).all()
+    wls = L.grid_values(cfg.a_grid_wl_sg)
+    assert tab["aoe"].shape == (n, len(wls))
+    B = O.OracleBuilders()
+    S_pre = L.resolve_sweep_params(cfg, tau, n_samples=wp.signal.shape[1], t_first=wp.t_first, step=wp.step, builders=B, out_f64=True)
+    S_wdw = L.resolve_sweep_params(cfg, tau, n_samples=ww.signal.shape[1], t_first=ww.t_first, step=ww.step, builders=B, out_f64=True,
+                                   external_baseline=True)
+    ev = L.trap_sweep_variants([pf["trap"]["rt"]], [pf["trap"]["ft"]], wp.step, mode="ft")
+    sgv = L.sg_sweep_variants(cfg, wls, n_samples=ww.signal.shape[1], t_first=ww.t_first, step=ww.step, builders=B)
+    ref = O.dsp_sg_optimization_compressed(S_pre, S_wdw, wp.signal, ww.signal, ev.array, sgv.array, presum)
+    assert np.array_equal(tab["blmean"], ref["blmean"])
+    assert np.allclose(tab["blslope"], ref["blslope"], rtol=1e-9, atol=1e-15)
+    assert np.allclose(tab["t50"], ref["t50"], rtol=0, atol=1e-7)
+    assert np.allclose(tab["energy"], ref["energy"], rtol=1e-9, atol=1e-6, equal_nan=True)
+    ok = np.abs(ref["energy"]) > 50.0 * presum            # aoe of empty events is noise / noise
+    bad = ~np.isclose(tab["aoe"][ok], ref["aoe"][ok], rtol=1e-7, atol=1e-9, equal_nan=True)
+    assert bad.sum() <= max(2, ok.sum() // 50), int(bad.sum())       # windowed-argmax ties only (see test_gpu_icpc.py)
+    assert ok.sum() > n // 2
+    if presum == 1:
+        # presum_rate 1 with the full trace as "window": the compressed sweep equals dsp_sg_optimization on that trace
+        wf = L.synth.generate_host(64, first_event=4000)
+        W = L.RDWaveforms(wf)
+        a = L.dsp_sg_optimization(W, cfg, tau, pf, handle=handle)
+        b = L.dsp_sg_optimization_compressed(W, W, cfg, tau, pf, presum_rate=1.0, handle=handle)
+        for k in ("energy", "blmean", "blslope", "t50"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+        assert np.array_equal(a["aoe"], b["aoe"], equal_nan=True)
+    # 32-bit copies of 16-bit samples give the same sweep as the 16-bit kernel
+    if presum == 1:
+        S = L.resolve_sweep_params(cfg, tau, out_f64=True)
+        v = L.trap_sweep_variants([L.us(4.0), L.us(8.0)], [L.us(1.0), L.us(3.0)], L.ns(16.0), mode="ft")
+        o16 = np.zeros((64, 4)); o32 = np.zeros((64, 4))
+        handle.gsweep_run_ext_host(S, wf.ctypes.data, 2, None, 64, 8192, v.array, o16.ctypes.data, None)
+        half = np.ascontiguousarray(wf[:, :4096].astype(np.uint32))
+        S4 = L.resolve_sweep_params(cfg, tau, n_samples=4096, out_f64=True)
+        h16 = np.ascontiguousarray(wf[:, :4096])
+        o16h = np.zeros((64, 4))
+        handle.gsweep_run_ext_host(S4, h16.ctypes.data, 2, None, 64, 4096, v.array, o16h.ctypes.data, None)
+        handle.gsweep_run_ext_host(S4, half.ctypes.data, 4, None, 64, 4096, v.array, o32.ctypes.data, None)
+        assert np.array_equal(o16h, o32, equal_nan=True)
+        with pytest.raises(L.LgdspError):       # 32-bit samples: at most 4096 per waveform
+            big = np.zeros((2, 8192), np.uint32)
+            handle.gsweep_run_ext_host(S, big.ctypes.data, 4, None, 2, 8192, v.array, o32.ctypes.data, None)
