@@ -98,3 +98,47 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".jl")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liblgdsp_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_julia_wrapper_struct_layout_matches_the_ctypes_mirror(L):
+    """julia/LegendDSPB200.jl cannot be run here (no Julia toolchain): at least its `struct` declarations must list the
+    fields of include/lgdsp_b200.h in the same order with the same element types / array lengths as the ctypes mirror
+    (which test_ctypes_mirror_matches_header ties to the header), and its constants must equal the header's."""
+    import ctypes as C
+    import re
+    src = open(os.path.join(ROOT, "julia", "LegendDSPB200.jl"), encoding="utf-8").read()
+    abi = L._abi
+    consts = dict(re.findall(r"const (MAX_DNI|MAX_SG|MAX_FIR|NCOL)\b", src) and
+                  zip(("MAX_DNI", "MAX_SG", "MAX_FIR", "NCOL"),
+                      map(int, re.search(r"const MAX_DNI, MAX_SG, MAX_FIR, NCOL = (\d+), (\d+), (\d+), (\d+)", src).groups())))
+    assert consts == {"MAX_DNI": abi.LGDSP_MAX_DNI, "MAX_SG": abi.LGDSP_MAX_SG, "MAX_FIR": abi.LGDSP_MAX_FIR, "NCOL": abi.NCOL}
+    assert int(re.search(r"PARAMS_VERSION = UInt32\((\d+)\)", src).group(1)) == abi.LGDSP_PARAMS_VERSION
+
+    jl_scalar = {"Int32": C.c_int32, "UInt32": C.c_uint32, "Int64": C.c_int64, "Float64": C.c_double}
+    env = {"MAX_DNI": abi.LGDSP_MAX_DNI, "MAX_SG": abi.LGDSP_MAX_SG, "MAX_FIR": abi.LGDSP_MAX_FIR}
+    structs = {"Trap": abi.Trap, "Dni": abi.Dni, "Sg": abi.Sg, "CuspZac": abi.CuspZac, "IcpcParams": abi.IcpcParams}
+
+    def jl_fields(name):
+        body = re.search(r"struct %s\b(.*?)\bend" % name, src, re.S).group(1)
+        body = re.sub(r"#.*", "", body)
+        return re.findall(r"(\w+)::([\w{}*, ]+?)(?:;|\n|$)", body)
+
+    def ctype_of(jl_type):
+        jl_type = jl_type.strip()
+        m = re.fullmatch(r"NTuple\{(.+),\s*(\w+)\}", jl_type)
+        if m:
+            length = eval(m.group(1), {}, env)
+            return ctype_of(m.group(2)) * length
+        return jl_scalar.get(jl_type) or structs[jl_type]
+
+    for name, cstruct in structs.items():
+        jf = jl_fields(name)
+        cf = list(cstruct._fields_)
+        assert [f for f, _ in jf] == [f for f, _ in cf] or [f for f, _ in jf] == [f.replace("n_window", "n_w") for f, _ in cf], \
+            (name, [f for f, _ in jf], [f for f, _ in cf])
+        for (jn, jt), (cn, ct) in zip(jf, cf):
+            assert C.sizeof(ctype_of(jt)) == C.sizeof(ct), (name, jn, jt, ct)
+    # the column list of the wrapper's output table is the header's column enum
+    cols = re.search(r"const COLS = \((.*?)\)\n", src, re.S).group(1)
+    jl_cols = [c.replace("tail_τ", "tail_tau") for c in re.findall(r":([\wτ]+)", cols)]
+    assert jl_cols == list(abi.COLUMNS)
