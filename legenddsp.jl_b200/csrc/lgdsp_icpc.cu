@@ -942,25 +942,20 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
             cmx = max(cmx, x);
         }
         SECT(0);
-        // baseline regression sums (exact integers): only chunks that intersect the window
+        // baseline regression sums (exact integers), samples of the window strided over ALL threads (the window covers the
+        // first chunks only: summed chunk-wise, three warps would do the whole job while the others wait at B1)
         {
-            unsigned long long blSS = 0;
-            uint32_t blS = 0, blSK = 0;
-            const int ka = max(0, P.bl_from - i0), kb = min(cvalid - 1, P.bl_until - i0);
+            unsigned long long blSS = 0, blSX = 0;
+            uint32_t blS = 0;
 #pragma unroll 1
-            for (int k = ka; k <= kb; ++k) {
-                const uint32_t x = xp[k];
+            for (int idx = P.bl_from + tid; idx <= P.bl_until; idx += NT) {
+                const uint32_t x = xs[idx];
                 blS += x;
-                blSK += x * (uint32_t)k;
+                blSX += (unsigned long long)x * (unsigned long long)idx;
                 blSS += (unsigned long long)x * (unsigned long long)x;
             }
-            double a = 0.0, b = 0.0, c = 0.0;
-            if (__any_sync(FULL, ka <= kb)) {
-                // sum_i i*x = i0*sum x + sum k*x   (all exact in double)
-                a = wsum_d((double)blS);
-                b = wsum_d((double)blSS);
-                c = wsum_d((double)i0 * (double)blS + (double)blSK);
-            }
+            // (all sums < 2^53: exact in double, in any order)
+            const double a = wsum_d((double)blS), b = wsum_d((double)blSS), c = wsum_d((double)blSX);
             if (lane == 0) { red[R_BLS * NWARP + wid] = a; red[R_BLSS * NWARP + wid] = b; red[R_BLSX * NWARP + wid] = c; }
         }
         // saturation counts: a sample can only equal low/high if the chunk's min/max says so
