@@ -1122,12 +1122,12 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
             const double ylo = wmin + km1 * Sd0 - ak * srange, yhi = wmax + km1 * Sd0 + ak * srange;
             const double guard = 1e-9 * (fabs(ylo) + fabs(yhi)) + 1e-6;   // >> rounding of the TT differences
             // t10..t99: a chunk entirely below (above) a threshold contributes zeros (ones) without a compare
-            if ((G & LGDSP_GROUP_TIMING) && cvalid > 0) {
+            if (G & LGDSP_GROUP_TIMING) {
                 uint32_t lo[5] = {0, 0, 0, 0, 0}, hi = 0;   // bits 0..31 of every threshold; bit t of hi = sample 32
                 bool straddle = false;
 #pragma unroll
                 for (int t = 0; t < 5; ++t) straddle |= !(ylo - guard >= thr[t]) && !(yhi + guard < thr[t]);
-                if (straddle) {
+                if (straddle && cvalid > 0) {
                     // one pass over the chunk, the five compares are independent (y from the prefix sums)
                     const double* tp = TT + i0;
                     double tprev = TT0;
@@ -1149,12 +1149,22 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
                         for (int t = 0; t < 5; ++t) hi |= (y >= thr[t]) ? (1u << t) : 0u;
                     }
                 }
+                // The 32 chunks of a warp cover the 33 mask words [33*wid, 33*wid + 32] exactly (chunk of lane l starts at bit l
+                // of word 33*wid + l): every word is assembled from this lane's chunk and its neighbour's top bits and written
+                // with a plain store -- no atomics, no dependence on the zero fill.
 #pragma unroll
                 for (int t = 0; t < 5; ++t) {
                     unsigned long long mbt = (unsigned long long)lo[t] | ((unsigned long long)((hi >> t) & 1u) << 32);
-                    if (ylo - guard >= thr[t]) mbt = chunk_all;
+                    if (cvalid <= 0) mbt = 0ull;
+                    else if (ylo - guard >= thr[t]) mbt = chunk_all;
                     else if (yhi + guard < thr[t]) mbt = 0ull;
-                    mask_commit(masks + (M_T10 + t) * NWORDS, tid, mbt);
+                    const unsigned long long up = __shfl_up_sync(FULL, mbt, 1);
+                    uint32_t word = (uint32_t)(mbt << lane);
+                    if (lane > 0) word |= (uint32_t)(up >> (33 - lane));
+                    uint32_t* M = masks + (M_T10 + t) * NWORDS;
+                    const int w = (CH * wid) + lane;
+                    if (w < NWORDS) M[w] = word;
+                    if (lane == 31 && w + 1 < NWORDS) M[w + 1] = (uint32_t)(mbt >> 1);
                 }
             }
             // bound of max |y| over the block (Lipschitz constants of the pruning)
