@@ -34,7 +34,7 @@ def _argmax_tie_ok(L, O, P, wf_row, got_value, col):
     return False
 
 
-def assert_parity_with_ties(L, O, P, wf, got, ref):
+def assert_parity_with_ties(L, O, P, wf, got, ref, max_ties=None):
     """assert_parity, except that current-amplitude mismatches must be explained by an exact argmax tie"""
     res = compare_rows(got, ref, L.COLUMNS)
     tie_cols = ("a_sg", "a_60", "a_100", "a_raw")
@@ -48,7 +48,8 @@ def assert_parity_with_ties(L, O, P, wf, got, ref):
         from parity import TOL
         rtol, atol = TOL[col]
         rows = np.nonzero(np.abs(got[:, j] - ref[:, j]) > atol + rtol * np.abs(ref[:, j]))[0]
-        assert len(rows) <= max(2, len(got) // 100), f"{col}: too many mismatches to be ties: {len(rows)}"
+        limit = max(2, len(got) // 100) if max_ties is None else max_ties
+        assert len(rows) <= limit, f"{col}: too many mismatches to be ties: {len(rows)}"
         for e in rows:
             assert _argmax_tie_ok(L, O, P, wf[e], got[e, j], col), f"{col}: event {e}: {got[e, j]} vs {ref[e, j]}"
             n_ties += 1
