@@ -165,3 +165,50 @@ def test_random_compressed_configurations(L, O, handle, seed):
         rtol, atol = TOL[col]
         n_bad = int((np.abs(res[col] - ref[col]) > atol + rtol * np.abs(ref[col])).sum())
         assert n_bad <= max(2, n_events // 50), (col, n_bad)
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("LGDSP_FUZZ_SEEDS_MI", "8")))))
+def test_random_multi_intersect(L, O, handle, seed):
+    """MultiIntersect (src/multi_intersect.jl:36-104) with random threshold lists, time-over-threshold requirements (1 .. 70
+    samples: runs inside one 32-sample block, across blocks, longer than a block), polynomial windows and trace lengths;
+    pulses on noise, traces that start above the thresholds, plateaus at a threshold"""
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.integers(700, 8193))
+    n_ev = 48
+    hw, d = int(rng.integers(1, 5)), int(rng.integers(1, 4))
+    d = min(d, 2 * hw - 1)
+    rate = int(rng.choice([1, 2, 4, 8]))
+    min_n = int(rng.choice([1, 2, 3, 5, 9, 17, 31, 32, 33, 40, 70]))
+    nthr = int(rng.integers(1, 100))
+    ratios = np.sort(rng.uniform(0.02, 0.95, nthr))
+    kk = np.arange(n)
+    Y = np.empty((n_ev, n))
+    for e in range(n_ev):
+        s0 = int(rng.integers(100 + min_n, n // 2))
+        rise = int(rng.integers(max(8, 2 * min_n), max(10, 2 * min_n) + 400))
+        amp = rng.uniform(200, 5000)
+        Y[e] = amp * np.clip((kk - s0) / rise, 0, 1) + rng.normal(0, 1.0, n)
+        if e % 3 == 1:
+            Y[e, :int(rng.integers(1, 90))] += rng.uniform(0.1, 0.9) * amp         # starts above some thresholds
+        if e % 3 == 2:
+            Y[e] = np.round(Y[e] / (amp / 16)) * (amp / 16)                          # staircase: exact ties with thresholds
+    f = L.MultiIntersect(threshold_ratios=list(ratios), mintot=L.ns(16.0 * min_n), n=hw, d=d, sampling_rate=rate)
+    n_checked = 0
+    for e0 in range(0, n_ev, 16):
+        batch = Y[e0:e0 + 16]
+        refs, ok_rows = [], []
+        for e in range(len(batch)):
+            try:
+                refs.append(O.multi_intersect(batch[e], 4.0, 16.0, f.threshold_ratios, min_n, hw, d, rate))
+                ok_rows.append(e)
+            except AssertionError:                       # boundary assertion of the reference (:85-88): not part of this test
+                pass
+        if not ok_rows:
+            continue
+        got = f(np.ascontiguousarray(batch[ok_rows]), t_first=L.ns(4.0), step=L.ns(16.0), handle=handle, builders=O.OracleBuilders())
+        for g, r in zip(got, refs):
+            assert np.array_equal(np.isnan(g), np.isnan(r))
+            ok = ~np.isnan(r)
+            assert np.allclose(g[ok], r[ok], rtol=0, atol=1e-6)
+            n_checked += 1
+    assert n_checked >= n_ev // 2
