@@ -395,6 +395,13 @@ int lgdsp_icpc_compressed_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p
 /* upload/validate params once and reuse them for many _device calls (avoids the per-call upload);
  * pass p == NULL to lgdsp_icpc_run_device afterwards */
 int lgdsp_icpc_set_params(lgdsp_handle* h, const lgdsp_icpc_params* p);
+/* execution path of every dsp_icpc pass of this handle (results are the same values):
+ *   1 (default) split pipeline: prefix / extract / CUSP-ZAC kernels coupled through a ring of float64 prefix sums that stays in
+ *     L2; `batch` = events per sub-batch (<= 0: default, 6 per SM), `streams` = side streams the sub-batches alternate on
+ *     (<= 0: default 2, at most 4);
+ *   0 fused: one launch of the single-kernel chain (round-1 path, kept for cross-checks).
+ * Environment overrides at lgdsp_create: LGDSP_ICPC_PATH=fused|split, LGDSP_SPLIT_BATCH, LGDSP_SPLIT_STREAMS. */
+int lgdsp_icpc_set_path(lgdsp_handle* h, int32_t path, int64_t batch, int32_t streams);
 
 /* ---- trapezoidal sweeps ---- */
 /* out: float[n_events][n_variants], i.e. the memory layout of the reference's column-major Julia matrix

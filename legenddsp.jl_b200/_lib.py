@@ -46,6 +46,7 @@ def load_library():
     L.lgdsp_cusp_coeffs.argtypes = [C.c_double, i32, C.c_double, i32, C.c_double, _dp]
     L.lgdsp_zac_coeffs.argtypes = [C.c_double, i32, C.c_double, i32, C.c_double, _dp]
     L.lgdsp_icpc_set_params.argtypes = [vp, C.POINTER(_abi.IcpcParams)]
+    L.lgdsp_icpc_set_path.argtypes = [vp, i32, i64, i32]
     L.lgdsp_icpc_run.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i64, i64, vp]
     L.lgdsp_icpc_run_device.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i64, i64, vp]
     L.lgdsp_icpc_run_ext.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i32, vp, i64, i64, vp]
@@ -85,7 +86,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "lgdsp_version", "lgdsp_last_error", "lgdsp_create", "lgdsp_destroy", "lgdsp_launch_count", "lgdsp_synchronize",
     "lgdsp_lsq_fit_matrix", "lgdsp_sg_coeffs", "lgdsp_cusp_coeffs", "lgdsp_zac_coeffs",
-    "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params", "lgdsp_icpc_run_ext", "lgdsp_icpc_run_ext_device",
+    "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params", "lgdsp_icpc_set_path", "lgdsp_icpc_run_ext", "lgdsp_icpc_run_ext_device",
     "lgdsp_window_stats_run", "lgdsp_window_stats_run_device", "lgdsp_sipm_run", "lgdsp_sipm_run_device",
     "lgdsp_sipm_list_pointers_device", "lgdsp_sipm_list_gather_device", "lgdsp_thresholdstats", "lgdsp_intersect_maximum", "lgdsp_multi_intersect_run", "lgdsp_multi_intersect_run_device", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
     "lgdsp_trap_sweep_run", "lgdsp_trap_sweep_run_device", "lgdsp_sweep_run", "lgdsp_sweep_run_device",
@@ -134,6 +135,11 @@ class Handle:
 
     def synchronize(self):
         self._check(self._lib.lgdsp_synchronize(self._h))
+
+    def set_icpc_path(self, path, batch=0, streams=0):
+        """'split' (default: prefix / extract / CUSP-ZAC kernels coupled through an L2-resident ring) or 'fused' (icpc_kernel)"""
+        code = {"fused": 0, "split": 1}[path] if isinstance(path, str) else int(path)
+        self._check(self._lib.lgdsp_icpc_set_path(self._h, code, int(batch), int(streams)))
 
     def last_kernel_ms(self):
         return float(self._lib.lgdsp_last_kernel_ms(self._h))

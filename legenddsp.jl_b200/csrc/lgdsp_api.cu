@@ -11,6 +11,8 @@
 
 using namespace lgdsp;
 
+#define LGDSP_SPLIT_MAX_STREAMS 4
+
 struct lgdsp_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -56,6 +58,19 @@ struct lgdsp_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int64_t launches = 0;
+    // split dsp_icpc pipeline (lgdsp_icpc_split.cuh): ring of prefix sums + per-event hand-over values, side streams
+    int icpc_path = 1;             // 0: fused icpc_kernel, 1: split pipeline
+    int split_bps[3] = {0, 0, 0};
+    int64_t split_batch = 0;       // events per batch (0: default)
+    int split_streams = 2;
+    double* d_tt = nullptr;
+    double* d_saux = nullptr;
+    int64_t split_cap = 0;         // allocated slots
+    cudaStream_t s_split[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t s_cz[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // CUSP/ZAC kernel next to the extract kernel
+    cudaEvent_t ev_pre[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr}, ev_cz[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    int split_par = 1;             // 1: CUSP/ZAC kernel on its own stream
+    cudaEvent_t ev_fork = nullptr, ev_join[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 static thread_local std::string g_create_err;
@@ -132,6 +147,25 @@ int lgdsp_create(int device, void* stream, lgdsp_handle** out)
         return bail(LGDSP_ERR_CUDA);
     }
     if (h->icpc_bps < 1 || h->sweep_bps < 1) { fail(nullptr, LGDSP_ERR_CUDA, "kernels do not fit on an SM"); return bail(LGDSP_ERR_CUDA); }
+    if ((e = icpc_split_configure(h->split_bps)) != cudaSuccess || h->split_bps[0] < 1 || h->split_bps[1] < 1 || h->split_bps[2] < 1) {
+        fail(nullptr, LGDSP_ERR_CUDA, "split pipeline configuration failed: %s", cudaGetErrorString(e));
+        return bail(LGDSP_ERR_CUDA);
+    }
+    for (int i = 0; i < LGDSP_SPLIT_MAX_STREAMS && ok; ++i) {
+        ok = ok && cudaStreamCreateWithFlags(&h->s_split[i], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&h->s_cz[i], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_cz[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { fail(nullptr, LGDSP_ERR_CUDA, "lgdsp_create: stream allocation failed: %s", cudaGetErrorString(cudaGetLastError())); return bail(LGDSP_ERR_CUDA); }
+    if (const char* env = getenv("LGDSP_ICPC_PATH")) h->icpc_path = (strcmp(env, "fused") == 0) ? 0 : 1;
+    if (const char* env = getenv("LGDSP_SPLIT_BATCH")) h->split_batch = atoll(env);
+    if (const char* env = getenv("LGDSP_SPLIT_STREAMS")) h->split_streams = atoi(env);
+    if (const char* env = getenv("LGDSP_SPLIT_PAR")) h->split_par = atoi(env) != 0;
+    if (h->split_streams < 1) h->split_streams = 1;
+    if (h->split_streams > LGDSP_SPLIT_MAX_STREAMS) h->split_streams = LGDSP_SPLIT_MAX_STREAMS;
     *out = h;
     return LGDSP_OK;
 }
@@ -141,6 +175,15 @@ void lgdsp_destroy(lgdsp_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < LGDSP_SPLIT_MAX_STREAMS; ++i) {
+        if (h->s_split[i]) { cudaStreamSynchronize(h->s_split[i]); cudaStreamDestroy(h->s_split[i]); }
+        if (h->s_cz[i]) { cudaStreamSynchronize(h->s_cz[i]); cudaStreamDestroy(h->s_cz[i]); }
+        if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
+        if (h->ev_cz[i]) cudaEventDestroy(h->ev_cz[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    cudaFree(h->d_tt); cudaFree(h->d_saux);
     cudaFree(h->d_phase);
     cudaFree(h->d_dniA); cudaFree(h->d_cusp_g); cudaFree(h->d_zac_g); cudaFree(h->d_sweep_dniA); cudaFree(h->d_vars); cudaFree(h->d_taps);
     cudaFree(h->d_in[0]); cudaFree(h->d_in[1]); cudaFree(h->d_rows); cudaFree(h->d_sweep_out);
@@ -436,7 +479,78 @@ static int check_wf(lgdsp_handle* h, const void* wf, int64_t n_events, int64_t l
     return LGDSP_OK;
 }
 
+// One dsp_icpc pass over a device batch, in stream order behind h->stream.  Fused path: one launch of icpc_kernel.  Split
+// path: the batch is cut into sub-batches whose prefix sums (65.6 KB per event) fit the L2; sub-batches alternate between
+// side streams (forked from / joined to h->stream with events) so that the tail of one kernel overlaps the next sub-batch.
+static int icpc_dispatch(lgdsp_handle* h, const IcpcDev& D, const void* d_wf, int sample_bytes, int64_t ne, int64_t ld,
+                         const double* d_bl, int64_t bl_stride, double bl_div, double* d_rows)
+{
+    if (h->icpc_path == 0 || D.phase_cycles != nullptr) {
+        const long long cap = (long long)h->sm_count * h->icpc_bps;
+        const int grid = (int)(ne < cap ? ne : cap);
+        icpc_launch(D, d_wf, sample_bytes, ne, ld, d_bl, bl_stride, bl_div, d_rows, grid, h->stream);
+        CK(cudaGetLastError());
+        h->launches += 1;
+        return LGDSP_OK;
+    }
+    const int S = h->split_streams;
+    const int64_t B = h->split_batch > 0 ? h->split_batch : (int64_t)h->sm_count * 6;
+    const int64_t need = B * S;
+    if (need > h->split_cap) {
+        CK(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < LGDSP_SPLIT_MAX_STREAMS; ++i) CK(cudaStreamSynchronize(h->s_split[i]));
+        cudaFree(h->d_tt); cudaFree(h->d_saux);
+        h->d_tt = nullptr; h->d_saux = nullptr; h->split_cap = 0;
+        CK(cudaMalloc(&h->d_tt, sizeof(double) * (size_t)need * (size_t)icpc_split_tt_doubles()));
+        CK(cudaMalloc(&h->d_saux, sizeof(double) * (size_t)need * (size_t)icpc_split_aux_doubles()));
+        h->split_cap = need;
+    }
+    const bool fork = S > 1 && ne > B;
+    if (fork) {
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+        for (int i = 0; i < S; ++i) CK(cudaStreamWaitEvent(h->s_split[i], h->ev_fork, 0));
+    }
+    const unsigned char* wf = static_cast<const unsigned char*>(d_wf);
+    const bool cz = (D.groups & LGDSP_GROUP_CUSPZAC) != 0;
+    int64_t b = 0;
+    for (int64_t e0 = 0; e0 < ne; e0 += B, ++b) {
+        const int64_t nb = (ne - e0) < B ? (ne - e0) : B;
+        const int si = fork ? (int)(b % S) : 0;
+        cudaStream_t st = fork ? h->s_split[si] : h->stream;
+        int grids[3];
+        for (int k = 0; k < 3; ++k) {
+            const long long cap = (long long)h->sm_count * h->split_bps[k];
+            grids[k] = (int)(nb < cap ? nb : cap);
+        }
+        icpc_split_launch_batch(D, wf + (size_t)e0 * (size_t)ld * (size_t)sample_bytes, sample_bytes, nb, ld,
+                                d_bl ? d_bl + e0 * bl_stride : nullptr, bl_stride, bl_div, d_rows + e0 * LGDSP_NCOL,
+                                h->d_tt + (size_t)si * (size_t)B * (size_t)icpc_split_tt_doubles(),
+                                h->d_saux + (size_t)si * (size_t)B * (size_t)icpc_split_aux_doubles(), grids, st,
+                                h->split_par ? h->s_cz[si] : nullptr, h->ev_pre[si], h->ev_cz[si]);
+        CK(cudaGetLastError());
+        h->launches += cz ? 3 : 2;
+    }
+    if (fork) {
+        for (int i = 0; i < S; ++i) {
+            CK(cudaEventRecord(h->ev_join[i], h->s_split[i]));
+            CK(cudaStreamWaitEvent(h->stream, h->ev_join[i], 0));
+        }
+    }
+    return LGDSP_OK;
+}
+
 extern "C" {
+
+/* path: 0 = fused icpc_kernel, 1 = split pipeline (default); batch <= 0 / streams <= 0: keep the defaults */
+int lgdsp_icpc_set_path(lgdsp_handle* h, int32_t path, int64_t batch, int32_t streams)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    if (path != 0 && path != 1) return fail(h, LGDSP_ERR_INVALID_ARG, "lgdsp_icpc_set_path: path %d (0 fused, 1 split)", path);
+    h->icpc_path = path;
+    if (batch > 0) h->split_batch = batch;
+    if (streams > 0) h->split_streams = streams > LGDSP_SPLIT_MAX_STREAMS ? LGDSP_SPLIT_MAX_STREAMS : streams;
+    return LGDSP_OK;
+}
 
 int lgdsp_icpc_set_params(lgdsp_handle* h, const lgdsp_icpc_params* p)
 {
@@ -467,11 +581,10 @@ static int icpc_run_device_impl(lgdsp_handle* h, const lgdsp_icpc_params* p, con
         h->phase_grid = grid;
     }
     CK(cudaEventRecord(h->ev0, h->stream));
-    icpc_launch(D, d_wf, sample_bytes, n_events, ld_samples, d_baseline, 1, 1.0, d_out_rows, grid, h->stream);
-    CK(cudaGetLastError());
+    rc = icpc_dispatch(h, D, d_wf, sample_bytes, n_events, ld_samples, d_baseline, 1, 1.0, d_out_rows);
+    if (rc) return rc;
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
-    h->launches += 1;
     return LGDSP_OK;
 }
 
@@ -534,7 +647,6 @@ static int icpc_run_host_impl(lgdsp_handle* h, const lgdsp_icpc_params* p, const
         rc = ensure_aux(h, (size_t)2 * chunk * sizeof(double));
         if (rc) return rc;
     }
-    const long long cap = (long long)h->sm_count * h->icpc_bps;
     const unsigned char* src = static_cast<const unsigned char*>(wf);
     int c = 0;
     for (int64_t e0 = 0; e0 < n_events; e0 += chunk, ++c) {
@@ -554,10 +666,8 @@ static int icpc_run_host_impl(lgdsp_handle* h, const lgdsp_icpc_params* p, const
         CK(cudaEventRecord(h->ev_ready[b], h->s_copy));
         CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
         double* d_rows = h->d_rows + (size_t)b * chunk * LGDSP_NCOL;
-        const int grid = (int)(ne < cap ? ne : cap);
-        icpc_launch(h->icpc, h->d_in[b], sample_bytes, ne, n, d_bl, 1, 1.0, d_rows, grid, h->stream);
-        CK(cudaGetLastError());
-        h->launches += 1;
+        rc = icpc_dispatch(h, h->icpc, h->d_in[b], sample_bytes, ne, n, d_bl, 1, 1.0, d_rows);
+        if (rc) return rc;
         CK(cudaEventRecord(h->ev_free[b], h->stream));
         CK(cudaMemcpyAsync(out_rows + e0 * LGDSP_NCOL, d_rows, (size_t)ne * LGDSP_NCOL * sizeof(double),
                            cudaMemcpyDeviceToHost, h->stream));
@@ -667,20 +777,20 @@ static int compressed_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, c
 }
 
 // the three launches of one batch, in stream order
-static void compressed_launch(lgdsp_handle* h, const void* d_pre, int pre_bytes, int64_t ld_pre, const void* d_wdw, int wdw_bytes,
+static int compressed_launch(lgdsp_handle* h, const void* d_pre, int pre_bytes, int64_t ld_pre, const void* d_wdw, int wdw_bytes,
                               int64_t ld_wdw, double presum_rate, int64_t ne, double* d_rows_pre, double* d_rows_wdw, double* d_stats)
 {
-    const long long cap = (long long)h->sm_count * h->icpc_bps;
-    const int grid = (int)(ne < cap ? ne : cap);
     // :332-346, :356-375, :383, :397-428, :439-455 on the presummed waveform
-    icpc_launch(h->icpc, d_pre, pre_bytes, ne, ld_pre, nullptr, 1, 1.0, d_rows_pre, grid, h->stream);
+    int rc = icpc_dispatch(h, h->icpc, d_pre, pre_bytes, ne, ld_pre, nullptr, 1, 1.0, d_rows_pre);
+    if (rc) return rc;
     // :338-339, :346 (slope_residual_sigma), :365-366: windows 3, 4 are shifted by the baseline mean of the first launch
     window_stats_launch(d_pre, pre_bytes, ne, ld_pre, h->icpc.t_first, h->icpc.dt, d_rows_pre + LGDSP_COL_blmean, LGDSP_NCOL, 0x18u,
                         h->d_win, 5, d_stats, h->stream);
     // :350 the windowed waveform is shifted by -blmean / presum_rate; :378-394, :431-435, :458
-    icpc_launch(h->icpc_w, d_wdw, wdw_bytes, ne, ld_wdw, d_rows_pre + LGDSP_COL_blmean, LGDSP_NCOL, presum_rate, d_rows_wdw, grid,
-                h->stream);
-    h->launches += 3;
+    rc = icpc_dispatch(h, h->icpc_w, d_wdw, wdw_bytes, ne, ld_wdw, d_rows_pre + LGDSP_COL_blmean, LGDSP_NCOL, presum_rate, d_rows_wdw);
+    if (rc) return rc;
+    h->launches += 1;
+    return LGDSP_OK;
 }
 
 int lgdsp_icpc_compressed_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, const lgdsp_icpc_params* p_wdw,
@@ -699,8 +809,9 @@ int lgdsp_icpc_compressed_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p
     if (n_events == 0) return LGDSP_OK;
     if (!d_rows_pre || !d_rows_wdw || !d_stats) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
     CK(cudaEventRecord(h->ev0, h->stream));
-    compressed_launch(h, d_wf_pre, pre_sample_bytes, ld_pre, d_wf_wdw, wdw_sample_bytes, ld_wdw, presum_rate, n_events, d_rows_pre,
-                      d_rows_wdw, d_stats);
+    rc = compressed_launch(h, d_wf_pre, pre_sample_bytes, ld_pre, d_wf_wdw, wdw_sample_bytes, ld_wdw, presum_rate, n_events, d_rows_pre,
+                           d_rows_wdw, d_stats);
+    if (rc) return rc;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
@@ -755,7 +866,8 @@ int lgdsp_icpc_compressed_run(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, c
         double* d_rp = h->d_crows + (size_t)b * chunk * per_event;
         double* d_rw = d_rp + (size_t)chunk * LGDSP_NCOL;
         double* d_st = d_rw + (size_t)chunk * LGDSP_NCOL;
-        compressed_launch(h, h->d_cin[b][0], pre_sample_bytes, np, h->d_cin[b][1], wdw_sample_bytes, nw, presum_rate, ne, d_rp, d_rw, d_st);
+        rc = compressed_launch(h, h->d_cin[b][0], pre_sample_bytes, np, h->d_cin[b][1], wdw_sample_bytes, nw, presum_rate, ne, d_rp, d_rw, d_st);
+        if (rc) return rc;
         CK(cudaGetLastError());
         CK(cudaEventRecord(h->ev_free[b], h->stream));
         CK(cudaMemcpyAsync(rows_pre + e0 * LGDSP_NCOL, d_rp, (size_t)ne * LGDSP_NCOL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -495,6 +495,7 @@ __device__ __forceinline__ double* cz_tab(double* tabA, double* tabB, int idx)
 // One forward loop per chunk: P- (decayed prefix), D1, D2 (moments) and the partial sums acc = sum_{k'<=k} rho^k' d
 // of the anti-causal prefix (P+ at in-chunk offset o is (total - acc[o-1]) * rho^-o; the weights only span one
 // chunk, so nothing cancels).  The running values are stored at the capture events the host sorted by sample index.
+template <int PAR_OFF>
 __device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, double* tabA, double* tabB, double* red,
                         double* pp0
 #ifdef LGDSP_PROFILE_SECTIONS
@@ -505,7 +506,7 @@ __device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, d
     // SMEM copy of the descriptor, addressed through the dynamic shared memory base so that the loads are LDS
     // (a reference to the kernel parameter or a generic pointer would force generic loads)
     extern __shared__ __align__(128) unsigned char smem_dyn[];
-    const CzDev& Z = reinterpret_cast<const SmemPar*>(smem_dyn + SM_PAR)->cz[ps];
+    const CzDev& Z = reinterpret_cast<const SmemPar*>(smem_dyn + PAR_OFF)->cz[ps];
     const int lane = tid & 31, wid = tid >> 5;
     const int i0 = tid * CH;
     const double r = Z.r, rho = Z.rho;
@@ -1406,10 +1407,10 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
         SECT(14);
         // CUSP/ZAC prefix tables (first descriptor)
 #ifdef LGDSP_PROFILE_SECTIONS
-        if (cz_structured) cz_scan(npass == 2 ? 1 : 0, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0,
+        if (cz_structured) cz_scan<SM_PAR>(npass == 2 ? 1 : 0, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0,
                                    P.phase_cycles ? &P.phase_cycles[(size_t)gridDim.x * 8 + 25 * 8 + wid] : nullptr, &sect_last);
 #else
-        if (cz_structured) cz_scan(npass == 2 ? 1 : 0, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
+        if (cz_structured) cz_scan<SM_PAR>(npass == 2 ? 1 : 0, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
 #endif
         SECT(15);
         __syncthreads();   // ---- B3 ----
@@ -1814,9 +1815,9 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
                 __syncthreads();   // the previous pass is done with the tables, the coarse values and the output buffer
                 if (tid == 0) ibuf[IB_CZN] = 0;
 #ifdef LGDSP_PROFILE_SECTIONS
-                cz_scan(ps, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0, nullptr, &sect_last);
+                cz_scan<SM_PAR>(ps, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0, nullptr, &sect_last);
 #else
-                cz_scan(ps, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
+                cz_scan<SM_PAR>(ps, TT, n, tid, tabA, tabB, red + R_CZSCR * NWARP, scr + SC_PP0);
 #endif
                 __syncthreads();
             }
@@ -2387,6 +2388,49 @@ void window_stats_launch(const void* d_wf, int sample_bytes, long long n_events,
     else
         window_stats_kernel<uint16_t><<<grid, wpb * 32, 0, stream>>>(static_cast<const uint16_t*>(d_wf), n_events, ld, t_first, dt,
                                                                       d_shift, shift_stride, shift_mask, d_win, n_windows, d_out);
+}
+
+#include "lgdsp_icpc_split.cuh"
+
+// ---- split pipeline: host side ----
+cudaError_t icpc_split_configure(int* bps3)
+{
+    cudaError_t err;
+    if ((err = cudaFuncSetAttribute(icpc_prefix_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(icpc_prefix_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(icpc_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(icpc_cuspzac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3[0], icpc_prefix_kernel<uint16_t>, NT, K1_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3[1], icpc_extract_kernel, NT2, K2_TOTAL)) != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3[2], icpc_cuspzac_kernel, NT, K3_TOTAL);
+}
+long long icpc_split_tt_doubles() { return TTG_LEN; }
+long long icpc_split_aux_doubles() { return AUX_LEN; }
+
+// one event batch: prefix -> extract -> CUSP/ZAC on `stream`; d_tt / d_aux hold n_events slots
+void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld,
+                             const double* d_bl_ext, long long bl_stride, double bl_div, double* d_rows, double* d_tt, double* d_aux,
+                             const int* grids3, cudaStream_t stream, cudaStream_t stream_cz, cudaEvent_t ev_prefix, cudaEvent_t ev_cz)
+{
+    const bool cz = (P.groups & LGDSP_GROUP_CUSPZAC) != 0;
+    if (sample_bytes == 4)
+        icpc_prefix_kernel<uint32_t><<<grids3[0], NT, K1_TOTAL, stream>>>(P, static_cast<const uint32_t*>(d_wf), n_events, ld, d_bl_ext,
+                                                                          bl_stride, bl_div, d_tt, d_aux, d_rows);
+    else
+        icpc_prefix_kernel<uint16_t><<<grids3[0], NT, K1_TOTAL, stream>>>(P, static_cast<const uint16_t*>(d_wf), n_events, ld, d_bl_ext,
+                                                                          bl_stride, bl_div, d_tt, d_aux, d_rows);
+    // the two consumers only depend on the prefix kernel: with a second stream they share the SMs (the extract kernel is issue
+    // bound, the CUSP/ZAC kernel waits on its serial recurrences)
+    const bool par = cz && stream_cz != nullptr && stream_cz != stream;
+    if (par) {
+        cudaEventRecord(ev_prefix, stream);
+        cudaStreamWaitEvent(stream_cz, ev_prefix, 0);
+        icpc_cuspzac_kernel<<<grids3[2], NT, K3_TOTAL, stream_cz>>>(P, d_tt, d_aux, n_events, d_rows);
+        cudaEventRecord(ev_cz, stream_cz);
+    }
+    icpc_extract_kernel<<<grids3[1], NT2, K2_TOTAL, stream>>>(P, d_tt, d_aux, n_events, cz ? 0 : 1, d_rows);
+    if (cz && !par) icpc_cuspzac_kernel<<<grids3[2], NT, K3_TOTAL, stream>>>(P, d_tt, d_aux, n_events, d_rows);
+    if (par) cudaStreamWaitEvent(stream, ev_cz, 0);   // the ring slot is reused behind both consumers
 }
 
 cudaError_t icpc_configure(int* max_blocks_per_sm)
