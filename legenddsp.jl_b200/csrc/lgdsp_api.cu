@@ -65,6 +65,7 @@ struct lgdsp_handle {
     int split_streams = 2;
     double* d_tt = nullptr;
     double* d_saux = nullptr;
+    double* d_scz = nullptr;       // candidate records of the CUSP/ZAC kernels
     int64_t split_cap = 0;         // allocated slots
     cudaStream_t s_split[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t s_cz[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // CUSP/ZAC kernel next to the extract kernel
@@ -183,7 +184,7 @@ void lgdsp_destroy(lgdsp_handle* h)
         if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    cudaFree(h->d_tt); cudaFree(h->d_saux);
+    cudaFree(h->d_tt); cudaFree(h->d_saux); cudaFree(h->d_scz);
     cudaFree(h->d_phase);
     cudaFree(h->d_dniA); cudaFree(h->d_cusp_g); cudaFree(h->d_zac_g); cudaFree(h->d_sweep_dniA); cudaFree(h->d_vars); cudaFree(h->d_taps);
     cudaFree(h->d_in[0]); cudaFree(h->d_in[1]); cudaFree(h->d_rows); cudaFree(h->d_sweep_out);
@@ -499,10 +500,11 @@ static int icpc_dispatch(lgdsp_handle* h, const IcpcDev& D, const void* d_wf, in
     if (need > h->split_cap) {
         CK(cudaStreamSynchronize(h->stream));
         for (int i = 0; i < LGDSP_SPLIT_MAX_STREAMS; ++i) CK(cudaStreamSynchronize(h->s_split[i]));
-        cudaFree(h->d_tt); cudaFree(h->d_saux);
-        h->d_tt = nullptr; h->d_saux = nullptr; h->split_cap = 0;
+        cudaFree(h->d_tt); cudaFree(h->d_saux); cudaFree(h->d_scz);
+        h->d_tt = nullptr; h->d_saux = nullptr; h->d_scz = nullptr; h->split_cap = 0;
         CK(cudaMalloc(&h->d_tt, sizeof(double) * (size_t)need * (size_t)icpc_split_tt_doubles()));
         CK(cudaMalloc(&h->d_saux, sizeof(double) * (size_t)need * (size_t)icpc_split_aux_doubles()));
+        CK(cudaMalloc(&h->d_scz, sizeof(double) * (size_t)need * (size_t)icpc_split_cz_doubles()));
         h->split_cap = need;
     }
     const bool fork = S > 1 && ne > B;
@@ -525,10 +527,11 @@ static int icpc_dispatch(lgdsp_handle* h, const IcpcDev& D, const void* d_wf, in
         icpc_split_launch_batch(D, wf + (size_t)e0 * (size_t)ld * (size_t)sample_bytes, sample_bytes, nb, ld,
                                 d_bl ? d_bl + e0 * bl_stride : nullptr, bl_stride, bl_div, d_rows + e0 * LGDSP_NCOL,
                                 h->d_tt + (size_t)si * (size_t)B * (size_t)icpc_split_tt_doubles(),
-                                h->d_saux + (size_t)si * (size_t)B * (size_t)icpc_split_aux_doubles(), grids, st,
+                                h->d_saux + (size_t)si * (size_t)B * (size_t)icpc_split_aux_doubles(),
+                                h->d_scz + (size_t)si * (size_t)B * (size_t)icpc_split_cz_doubles(), grids, st,
                                 h->split_par ? h->s_cz[si] : nullptr, h->ev_pre[si], h->ev_cz[si]);
         CK(cudaGetLastError());
-        h->launches += cz ? 3 : 2;
+        h->launches += cz ? (D.direct ? 3 : 4) : 2;
     }
     if (fork) {
         for (int i = 0; i < S; ++i) {

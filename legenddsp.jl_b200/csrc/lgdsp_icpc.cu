@@ -701,22 +701,22 @@ struct CzStream {
 // CH recurrence steps of one candidate chunk: the CUSP and ZAC outputs go to obuf[k][0..1] (-inf where m0+k is not a
 // valid output); maxima, argmaxima and the pick-off windows are taken from there by a block-parallel pass.  No
 // compares or branches in the loop: the only loop-carried dependency is the state update.
-__device__ __forceinline__ void cz_out(const CzDev& Z, const double* TT, int n, int tid, CzState& S, double* obuf)
+template <typename F>
+__device__ __forceinline__ void cz_out_each(const CzDev& Z, const double* TT, int n, int tid, CzState& S, F&& f)
 {
     const int m0 = tid * CH;
-    const int L = Z.L, lt = Z.lt, F = Z.F;
+    const int L = Z.L, lt = Z.lt, F_ = Z.F;
     const double r = Z.r;
     CzStream s0, s1, s2, s3;
     s0.init(TT, m0 + 1);
     s1.init(TT, m0 + 1 - lt);
-    s2.init(TT, m0 - lt - F);
+    s2.init(TT, m0 - lt - F_);
     s3.init(TT, m0 + 1 - L);
     auto emit = [&](int k) {
         const double ylast = s3.yprev;   // y[m-L]
         const double Dc = (S.EpL - S.EmL + S.EpR - S.EmR) + S.W0F;
         const double poly = (S.W2L - Z.h2 * S.W1L) + (S.V2 - Z.h2 * S.V1);
-        obuf[2 * k] = fma(Z.g, Dc, Z.gclast_cusp * ylast);
-        obuf[2 * k + 1] = fma(Z.g, fma(Z.B, poly, Dc), Z.gclast_zac * ylast);
+        f(k, fma(Z.g, Dc, Z.gclast_cusp * ylast), fma(Z.g, fma(Z.B, poly, Dc), Z.gclast_zac * ylast));
     };
     auto update = [&](double a, double b, double c, double d) {
         S.EmL = fma(Z.rho, S.EmL, fma(Z.cA, a, -Z.cA_rho_lt * b));
@@ -744,12 +744,16 @@ __device__ __forceinline__ void cz_out(const CzDev& Z, const double* TT, int n, 
         for (int k = 0; k < CH; ++k) {
             const int m = m0 + k;
             if (m >= L - 1 && m < n) emit(k);
-            else { obuf[2 * k] = -CUDART_INF; obuf[2 * k + 1] = -CUDART_INF; }
+            else f(k, -CUDART_INF, -CUDART_INF);
             const double a = s0.next_safe(TT, r, n), b = s1.next_safe(TT, r, n), c = s2.next_safe(TT, r, n),
                          d = s3.next_safe(TT, r, n);
             update(a, b, c, d);
         }
     }
+}
+__device__ __forceinline__ void cz_out(const CzDev& Z, const double* TT, int n, int tid, CzState& S, double* obuf)
+{
+    cz_out_each(Z, TT, n, tid, S, [&](int k, double oc, double oz) { obuf[2 * k] = oc; obuf[2 * k + 1] = oz; });
 }
 
 // CUSP / ZAC outputs at the chunk start m0 = CH*tid from the closed-form state (the coarse grid of the pruning);
@@ -2406,11 +2410,13 @@ cudaError_t icpc_split_configure(int* bps3)
 }
 long long icpc_split_tt_doubles() { return TTG_LEN; }
 long long icpc_split_aux_doubles() { return AUX_LEN; }
+long long icpc_split_cz_doubles() { return CZG_LEN; }
 
 // one event batch: prefix -> extract -> CUSP/ZAC on `stream`; d_tt / d_aux hold n_events slots
 void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld,
                              const double* d_bl_ext, long long bl_stride, double bl_div, double* d_rows, double* d_tt, double* d_aux,
-                             const int* grids3, cudaStream_t stream, cudaStream_t stream_cz, cudaEvent_t ev_prefix, cudaEvent_t ev_cz)
+                             double* d_cz, const int* grids3, cudaStream_t stream, cudaStream_t stream_cz, cudaEvent_t ev_prefix,
+                             cudaEvent_t ev_cz)
 {
     const bool cz = (P.groups & LGDSP_GROUP_CUSPZAC) != 0;
     if (sample_bytes == 4)
@@ -2422,14 +2428,19 @@ void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_byte
     // the two consumers only depend on the prefix kernel: with a second stream they share the SMs (the extract kernel is issue
     // bound, the CUSP/ZAC kernel waits on its serial recurrences)
     const bool par = cz && stream_cz != nullptr && stream_cz != stream;
+    const int fin_grid = (int)((n_events + K4_WARPS - 1) / K4_WARPS);
     if (par) {
         cudaEventRecord(ev_prefix, stream);
         cudaStreamWaitEvent(stream_cz, ev_prefix, 0);
-        icpc_cuspzac_kernel<<<grids3[2], NT, K3_TOTAL, stream_cz>>>(P, d_tt, d_aux, n_events, d_rows);
+        icpc_cuspzac_kernel<<<grids3[2], NT, K3_TOTAL, stream_cz>>>(P, d_tt, d_aux, n_events, d_cz, d_rows);
+        if (!P.direct) icpc_cuspzac_finish_kernel<<<fin_grid, K4_WARPS * 32, 0, stream_cz>>>(P, d_tt, d_cz, n_events, d_rows);
         cudaEventRecord(ev_cz, stream_cz);
     }
     icpc_extract_kernel<<<grids3[1], NT2, K2_TOTAL, stream>>>(P, d_tt, d_aux, n_events, cz ? 0 : 1, d_rows);
-    if (cz && !par) icpc_cuspzac_kernel<<<grids3[2], NT, K3_TOTAL, stream>>>(P, d_tt, d_aux, n_events, d_rows);
+    if (cz && !par) {
+        icpc_cuspzac_kernel<<<grids3[2], NT, K3_TOTAL, stream>>>(P, d_tt, d_aux, n_events, d_cz, d_rows);
+        if (!P.direct) icpc_cuspzac_finish_kernel<<<fin_grid, K4_WARPS * 32, 0, stream>>>(P, d_tt, d_cz, n_events, d_rows);
+    }
     if (par) cudaStreamWaitEvent(stream, ev_cz, 0);   // the ring slot is reused behind both consumers
 }
 

@@ -916,16 +916,28 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
 }
 
 // ==================================================================================================
-// CUSP / ZAC kernel
+// CUSP / ZAC: select kernel (prefix tables, coarse grid, candidate chunks) + finish kernel (recurrences, one lane per
+// candidate chunk, one warp per event)
 // ==================================================================================================
+// In icpc_kernel the 33-step recurrences of the ~25 candidate chunks of an event run in the two or three warps that own
+// them while the rest of the block waits at a barrier (a fifth of the samples of that kernel).  Here the block only selects
+// the candidates and hands their closed-form window states over; a second kernel steps the recurrences with one LANE per
+// candidate chunk and one warp per event, so the serial part is 33 full-width steps per event and nobody waits for it.
+constexpr int CZ_REC = 12;                    // doubles per candidate record: the 11 window states + the chunk index
+constexpr int CZ_MAXC = NT;                   // candidate capacity per (event, pass): every chunk
+constexpr int CZ_HDR = 16;                    // doubles per (event, pass) header
+enum { CZH_N = 0, CZH_MAXC, CZH_ARGC, CZH_MAXZ, CZH_ARGZ, CZH_PKP0, CZH_PKF0, CZH_PKP1, CZH_PKF1 };
+constexpr int CZP_LEN = CZ_HDR + CZ_MAXC * CZ_REC;   // doubles per (event, pass)
+constexpr int CZG_LEN = 2 * CZP_LEN;                 // doubles per event slot
+
 enum { K3R_CZC0 = 0, K3R_CZC1, K3R_CZMAX0, K3R_CZARG0, K3R_CZMAX1, K3R_CZARG1, K3R_CZSCR, K3R_CZSCR1, K3R_CZSCR2, K3R_CZSCR3, K3R_N };
-enum { K3I_CZN = 0, K3I_PKFROM = 1 /* 2 */, K3I_CZT = 4 /* CZCAP chunk ids */, K3I_N = 4 + 32 };
+enum { K3I_CZN = 0, K3I_PKFROM = 1 /* 2 */, K3I_N = 4 };
 constexpr int K3_TT = 0;
 constexpr int K3_TABA = K3_TT + TT_LEN * 8;                 // double tabA[8][NT]
-constexpr int K3_TABB = K3_TABA + 8 * NT * 8;               // double tabB[8][NT]: tables 8..15, then the output buffer
+constexpr int K3_TABB = K3_TABA + 8 * NT * 8;               // double tabB[8][NT]: tables 8..15
 constexpr int K3_CZCO = K3_TABB + 8 * NT * 8;               // double czco[2][NT]: coarse CUSP / ZAC values
 constexpr int K3_RED = K3_CZCO + 2 * NT * 8;
-constexpr int K3_STASH = K3_RED + K3R_N * NWARP * 8;        // double stash[2][LGDSP_MAX_DNI]
+constexpr int K3_STASH = K3_RED + K3R_N * NWARP * 8;        // double stash[2][LGDSP_MAX_DNI] (direct mode)
 constexpr int K3_SCR = K3_STASH + 2 * LGDSP_MAX_DNI * 8;    // double scr[8]: pk_p[2], pp0, Ymax
 constexpr int K3_IBUF = K3_SCR + 8 * 8;                     // int ibuf[K3I_N]
 constexpr int K3_BAR = K3_IBUF + K3I_N * 4;
@@ -936,7 +948,7 @@ enum { K3S_PKP = 0 /* 2 */, K3S_PP0 = 2, K3S_YMAX = 3 };
 
 __global__ void __launch_bounds__(NT, 2)
 icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict__ ttg, const double* __restrict__ auxg,
-                    long long n_events, double* __restrict__ rows)
+                    long long n_events, double* __restrict__ czg, double* __restrict__ rows)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     double* TT = reinterpret_cast<double*>(smem + K3_TT);
@@ -999,15 +1011,12 @@ icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             ibuf[K3I_PKFROM + lane] = pf;
             if (lane == 0) scr[K3S_YMAX] = ax[AX_YMAX];
         }
-        double czmax[2] = {-CUDART_INF, -CUDART_INF};
-        int czarg[2] = {0x7fffffff, 0x7fffffff};
-        double pk_p[2];
-        int pk_from[2];
-
         if (npass == 0) {
-            // direct form (validation mode only)
+            // direct form (validation mode only): the whole evaluation in this kernel
+            double czmax[2] = {-CUDART_INF, -CUDART_INF};
+            int czarg[2] = {0x7fffffff, 0x7fffffff};
             __syncthreads();
-            pk_from[0] = ibuf[K3I_PKFROM]; pk_from[1] = ibuf[K3I_PKFROM + 1];
+            const int pk_from[2] = {ibuf[K3I_PKFROM], ibuf[K3I_PKFROM + 1]};
 #pragma unroll 1
             for (int f = 0; f < 2; ++f) {
                 const int L = f ? P.zac_L : P.cusp_L;
@@ -1024,18 +1033,44 @@ icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                 }
                 if (f == 0) { czmax[0] = bm; czarg[0] = ba; } else { czmax[1] = bm; czarg[1] = ba; }
             }
+            czmax[0] = wargmax_d(czmax[0], czarg[0]);
+            czmax[1] = wargmax_d(czmax[1], czarg[1]);
+            if (lane == 0) {
+                red[K3R_CZMAX0 * NWARP + wid] = czmax[0]; red[K3R_CZARG0 * NWARP + wid] = (double)czarg[0];
+                red[K3R_CZMAX1 * NWARP + wid] = czmax[1]; red[K3R_CZARG1 * NWARP + wid] = (double)czarg[1];
+            }
+            __syncthreads();
+            if (wid < 2) {
+                const int f = wid;
+                const double v = dni_eval_warp(A_sig, nw, P.sig_dni.m, stash + f * LGDSP_MAX_DNI,
+                                               scr[K3S_PKP + f] - (double)ibuf[K3I_PKFROM + f], lane);
+                double cm;
+                int ca;
+                red_argmax(red, f ? K3R_CZMAX1 : K3R_CZMAX0, f ? K3R_CZARG1 : K3R_CZARG0, cm, ca);
+                if (lane == 0) {
+                    const int L = f ? P.zac_L : P.cusp_L;
+                    double* ro = rows + e * LGDSP_NCOL;
+                    ro[f ? LGDSP_COL_e_zac_max : LGDSP_COL_e_cusp_max] = cm;
+                    ro[f ? LGDSP_COL_t_zac_max : LGDSP_COL_t_cusp_max] = t_first + (double)(ca + L - 1) * dt;
+                    ro[f ? LGDSP_COL_e_zac : LGDSP_COL_e_cusp] = v;
+                }
+            }
+            __syncthreads();
+            continue;
         }
+        // One pass of the structured evaluation up to the candidate selection.  The descriptor index is a compile-time
+        // constant so that its fields are immediate constant-bank operands.
         auto cz_pass = [&](auto psc, const bool want_cusp, const bool want_zac, const bool rescan) {
             constexpr int ps = decltype(psc)::value;
             const CzDev& Z = P.cz[ps];
+            double* cg = czg + e * CZG_LEN + ps * CZP_LEN;
             if (rescan) {
-                __syncthreads();   // the previous pass is done with the tables, the coarse values and the output buffer
+                __syncthreads();   // the previous pass is done with the tables, the coarse values and the counters
                 if (tid == 0) ibuf[K3I_CZN] = 0;
             }
             cz_scan<K3_PAR>(ps, TT, n, tid, tabA, tabB, red + K3R_CZSCR * NWARP, scr + K3S_PP0);
             __syncthreads();   // tables (and the pick-off windows) are complete
-            pk_p[0] = scr[K3S_PKP]; pk_p[1] = scr[K3S_PKP + 1];
-            pk_from[0] = ibuf[K3I_PKFROM]; pk_from[1] = ibuf[K3I_PKFROM + 1];
+            const int pk_from[2] = {ibuf[K3I_PKFROM], ibuf[K3I_PKFROM + 1]};
             const double Ymax = scr[K3S_YMAX];
             CzState st;
             st.active = false;
@@ -1044,16 +1079,25 @@ icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             cz_coarse(Z, TT, n, tid, st, oc, oz);
             if (!want_cusp) oc = -CUDART_INF;
             if (!want_zac) oz = -CUDART_INF;
+            // the coarse points are outputs themselves
             const int j0 = i0 - Z.L + 1;
-            if (oc > czmax[0]) { czmax[0] = oc; czarg[0] = j0; }
-            if (oz > czmax[1]) { czmax[1] = oz; czarg[1] = j0; }
             czco[tid] = oc;
             czco[NT + tid] = oz;
-            const double wc = wmax_d(oc), wz = wmax_d(oz);
-            red_put(red, K3R_CZC0, wid, lane, wc);
-            red_put(red, K3R_CZC1, wid, lane, wz);
+            {
+                int ac = oc > -CUDART_INF ? j0 : 0x7fffffff, az = oz > -CUDART_INF ? j0 : 0x7fffffff;
+                const double wc = wargmax_d(oc, ac), wz = wargmax_d(oz, az);
+                if (lane == 0) {
+                    red[K3R_CZMAX0 * NWARP + wid] = wc; red[K3R_CZARG0 * NWARP + wid] = (double)ac;
+                    red[K3R_CZMAX1 * NWARP + wid] = wz; red[K3R_CZARG1 * NWARP + wid] = (double)az;
+                }
+            }
             __syncthreads();   // tables are dead, coarse values complete
-            const double Mc = red_max(red, K3R_CZC0), Mz = red_max(red, K3R_CZC1);
+            double Mc, Mz;
+            int Ac, Az;
+            red_argmax(red, K3R_CZMAX0, K3R_CZARG0, Mc, Ac);
+            red_argmax(red, K3R_CZMAX1, K3R_CZARG1, Mz, Az);
+            // candidate chunks: Lipschitz bound on (33 tid, 33 tid + 33) against the best coarse value; chunks that
+            // hold part of a pick-off window are always evaluated
             bool cand = false;
             if (st.active) {
                 const int t1 = min(tid + 1, NT - 1);
@@ -1080,72 +1124,113 @@ icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                     cand |= (jhi >= pk_from[1] && jlo < pk_from[1] + nw);
                 }
             }
-            int slot = -1;
+            // candidate records: the window states at the chunk start + the chunk index
             {
                 const unsigned bc = __ballot_sync(FULL, cand);
                 int base = 0;
                 if (lane == 0 && bc) base = atomicAdd(&ibuf[K3I_CZN], __popc(bc));
                 base = __shfl_sync(FULL, base, 0);
-                if (cand) slot = base + __popc(bc & ((1u << lane) - 1u));
+                if (cand) {
+                    double* r = cg + CZ_HDR + (size_t)(base + __popc(bc & ((1u << lane) - 1u))) * CZ_REC;
+                    r[0] = st.EmL; r[1] = st.EpL; r[2] = st.W0L; r[3] = st.W1L; r[4] = st.W2L; r[5] = st.W0F;
+                    r[6] = st.V0; r[7] = st.V1; r[8] = st.V2; r[9] = st.EpR; r[10] = st.EmR; r[11] = (double)tid;
+                }
             }
-            double* czbuf = tabB;
-#pragma unroll 1
-            for (int r0 = 0;; r0 += CZCAP) {
-                if (cand && slot >= r0 && slot < r0 + CZCAP) {
-                    ibuf[K3I_CZT + slot - r0] = tid;
-                    cz_out(Z, TT, n, tid, st, czbuf + (size_t)(slot - r0) * (CH * 2));
-                }
-                __syncthreads();
-                const int ncz = ibuf[K3I_CZN];
-                const int nslot = min(ncz - r0, CZCAP);
-#pragma unroll 1
-                for (int i = tid; i < nslot * CH; i += NT) {
-                    const int sl = i / CH, k = i - sl * CH;
-                    const int j = ibuf[K3I_CZT + sl] * CH + k - Z.L + 1;
-                    const double o_c = czbuf[2 * i], o_z = czbuf[2 * i + 1];
-                    if (want_cusp) {
-                        if (o_c > czmax[0] || (o_c == czmax[0] && j < czarg[0])) { czmax[0] = o_c; czarg[0] = j; }
-                        const int q = j - pk_from[0];
-                        if (q >= 0 && q < nw && o_c > -CUDART_INF) stash[q] = o_c;
-                    }
-                    if (want_zac) {
-                        if (o_z > czmax[1] || (o_z == czmax[1] && j < czarg[1])) { czmax[1] = o_z; czarg[1] = j; }
-                        const int q = j - pk_from[1];
-                        if (q >= 0 && q < nw && o_z > -CUDART_INF) stash[LGDSP_MAX_DNI + q] = o_z;
-                    }
-                }
-                if (r0 + CZCAP >= ncz) break;
-                __syncthreads();   // the buffer is reused by the next round
+            __syncthreads();   // candidate count complete
+            if (tid == 0) {
+                cg[CZH_N] = (double)ibuf[K3I_CZN];
+                cg[CZH_MAXC] = Mc; cg[CZH_ARGC] = (double)Ac; cg[CZH_MAXZ] = Mz; cg[CZH_ARGZ] = (double)Az;
+                cg[CZH_PKP0] = scr[K3S_PKP]; cg[CZH_PKF0] = (double)pk_from[0];
+                cg[CZH_PKP1] = scr[K3S_PKP + 1]; cg[CZH_PKF1] = (double)pk_from[1];
             }
         };
         if (npass == 2) {
             cz_pass(std::integral_constant<int, 1>{}, false, true, false);
             cz_pass(std::integral_constant<int, 0>{}, true, false, true);
-        } else if (npass == 1) {
+        } else {
             cz_pass(std::integral_constant<int, 0>{}, true, true, false);
         }
+        __syncthreads();   // TT, scr, ibuf may be overwritten by the next event
+    }
+}
+
+// finish: one warp per event, one lane per candidate chunk
+constexpr int K4_WARPS = 4;
+__global__ void __launch_bounds__(K4_WARPS * 32)
+icpc_cuspzac_finish_kernel(const __grid_constant__ IcpcDev P, const double* __restrict__ ttg, const double* __restrict__ czg,
+                           long long n_events, double* __restrict__ rows)
+{
+    __shared__ double stash_s[K4_WARPS][2][LGDSP_MAX_DNI];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n = P.n;
+    const int nw = P.sig_dni.n_w;
+    const double* A_sig = P.dni_A + LGDSP_MAX_DNI * 4;
+    double* stash = &stash_s[wid][0][0];
+    const int npass = P.cz_shared ? 1 : 2;
+    for (long long e = (long long)blockIdx.x * K4_WARPS + wid; e < n_events; e += (long long)gridDim.x * K4_WARPS) {
+        const double* TT = ttg + e * TTG_LEN;
+        double czmax[2] = {-CUDART_INF, -CUDART_INF};
+        int czarg[2] = {0x7fffffff, 0x7fffffff};
+        double pk_p[2] = {0.0, 0.0};
+        int pk_from[2] = {0, 0};
+        auto pass = [&](auto psc, const bool want_cusp, const bool want_zac) {
+            constexpr int ps = decltype(psc)::value;
+            const CzDev& Z = P.cz[ps];
+            const double* cg = czg + e * CZG_LEN + ps * CZP_LEN;
+            const int ncand = (int)cg[CZH_N];
+            pk_p[0] = cg[CZH_PKP0]; pk_p[1] = cg[CZH_PKP1];
+            pk_from[0] = (int)cg[CZH_PKF0]; pk_from[1] = (int)cg[CZH_PKF1];
+            if (lane == 0) {
+                // the coarse points are outputs themselves
+                if (want_cusp) { czmax[0] = cg[CZH_MAXC]; czarg[0] = (int)cg[CZH_ARGC]; }
+                if (want_zac) { czmax[1] = cg[CZH_MAXZ]; czarg[1] = (int)cg[CZH_ARGZ]; }
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < ncand; c0 += 32) {
+                if (c0 + lane < ncand) {
+                    const double* r = cg + CZ_HDR + (size_t)(c0 + lane) * CZ_REC;
+                    CzState st;
+                    st.EmL = r[0]; st.EpL = r[1]; st.W0L = r[2]; st.W1L = r[3]; st.W2L = r[4]; st.W0F = r[5];
+                    st.V0 = r[6]; st.V1 = r[7]; st.V2 = r[8]; st.EpR = r[9]; st.EmR = r[10];
+                    st.active = true;
+                    const int chunk = (int)r[11];
+                    const int jb = chunk * CH - Z.L + 1;
+                    cz_out_each(Z, TT, n, chunk, st, [&](int k, double o_c, double o_z) {
+                        const int j = jb + k;
+                        if (want_cusp) {
+                            if (o_c > czmax[0] || (o_c == czmax[0] && j < czarg[0])) { czmax[0] = o_c; czarg[0] = j; }
+                            const int q = j - pk_from[0];
+                            if (q >= 0 && q < nw && o_c > -CUDART_INF) stash[q] = o_c;
+                        }
+                        if (want_zac) {
+                            if (o_z > czmax[1] || (o_z == czmax[1] && j < czarg[1])) { czmax[1] = o_z; czarg[1] = j; }
+                            const int q = j - pk_from[1];
+                            if (q >= 0 && q < nw && o_z > -CUDART_INF) stash[LGDSP_MAX_DNI + q] = o_z;
+                        }
+                    });
+                }
+            }
+        };
+        if (npass == 2) {
+            pass(std::integral_constant<int, 1>{}, false, true);
+            pass(std::integral_constant<int, 0>{}, true, false);
+        } else {
+            pass(std::integral_constant<int, 0>{}, true, true);
+        }
+        __syncwarp();
         czmax[0] = wargmax_d(czmax[0], czarg[0]);
         czmax[1] = wargmax_d(czmax[1], czarg[1]);
+        const double vc = dni_eval_warp(A_sig, nw, P.sig_dni.m, stash, pk_p[0] - (double)pk_from[0], lane);
+        const double vz = dni_eval_warp(A_sig, nw, P.sig_dni.m, stash + LGDSP_MAX_DNI, pk_p[1] - (double)pk_from[1], lane);
         if (lane == 0) {
-            red[K3R_CZMAX0 * NWARP + wid] = czmax[0]; red[K3R_CZARG0 * NWARP + wid] = (double)czarg[0];
-            red[K3R_CZMAX1 * NWARP + wid] = czmax[1]; red[K3R_CZARG1 * NWARP + wid] = (double)czarg[1];
+            double* ro = rows + e * LGDSP_NCOL;
+            ro[LGDSP_COL_e_cusp_max] = czmax[0];
+            ro[LGDSP_COL_t_cusp_max] = P.t_first + (double)(czarg[0] + P.cusp_L - 1) * P.dt;
+            ro[LGDSP_COL_e_cusp] = vc;
+            ro[LGDSP_COL_e_zac_max] = czmax[1];
+            ro[LGDSP_COL_t_zac_max] = P.t_first + (double)(czarg[1] + P.zac_L - 1) * P.dt;
+            ro[LGDSP_COL_e_zac] = vz;
         }
-        __syncthreads();
-        if (wid < 2) {
-            const int f = wid;
-            const double v = dni_eval_warp(A_sig, nw, P.sig_dni.m, stash + f * LGDSP_MAX_DNI,
-                                           scr[K3S_PKP + f] - (double)ibuf[K3I_PKFROM + f], lane);
-            double cm;
-            int ca;
-            red_argmax(red, f ? K3R_CZMAX1 : K3R_CZMAX0, f ? K3R_CZARG1 : K3R_CZARG0, cm, ca);
-            if (lane == 0) {
-                const int L = f ? P.zac_L : P.cusp_L;
-                double* ro = rows + e * LGDSP_NCOL;
-                ro[f ? LGDSP_COL_e_zac_max : LGDSP_COL_e_cusp_max] = cm;
-                ro[f ? LGDSP_COL_t_zac_max : LGDSP_COL_t_cusp_max] = t_first + (double)(ca + L - 1) * dt;
-                ro[f ? LGDSP_COL_e_zac : LGDSP_COL_e_cusp] = v;
-            }
-        }
-        __syncthreads();   // TT, stash, scr, ibuf may be overwritten by the next event
+        __syncwarp();   // the stash is reused by this warp's next event
     }
 }
