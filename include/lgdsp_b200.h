@@ -59,6 +59,10 @@ extern "C" {
 #define LGDSP_MAX_SG 33          /* Savitzky-Golay taps */
 #define LGDSP_MAX_FIR 4096       /* CUSP/ZAC taps */
 
+/* waveform codecs of `decode_data` (LegendDataTypes.jl; call sites /root/reference/src/dsp_icpc.jl:313-314) */
+#define LGDSP_CODEC_RADWARE 1     /* RadwareSigcompress(shift): radware-sigcompress v1.0, 16-bit samples, big-endian words */
+#define LGDSP_CODEC_ULEB128ZZD 2  /* ULEB128 zig-zag difference codec (VarlenDiffArrayCodec): 16- or 32-bit samples */
+
 /* ---- output schema: computed columns of dsp_icpc, order of src/dsp_icpc.jl:210-229.
  * The four pass-through columns (blfc, timestamp, eventID_fadc, e_fc) never touch the GPU.
  * Device rows are double[LGDSP_NCOL]; integer columns (qc_label, inTrace_n, n_sat_*) hold exact small

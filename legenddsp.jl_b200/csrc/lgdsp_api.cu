@@ -519,16 +519,12 @@ static int icpc_dispatch(lgdsp_handle* h, const IcpcDev& D, const void* d_wf, in
         const int64_t nb = (ne - e0) < B ? (ne - e0) : B;
         const int si = fork ? (int)(b % S) : 0;
         cudaStream_t st = fork ? h->s_split[si] : h->stream;
-        int grids[3];
-        for (int k = 0; k < 3; ++k) {
-            const long long cap = (long long)h->sm_count * h->split_bps[k];
-            grids[k] = (int)(nb < cap ? nb : cap);
-        }
         icpc_split_launch_batch(D, wf + (size_t)e0 * (size_t)ld * (size_t)sample_bytes, sample_bytes, nb, ld,
                                 d_bl ? d_bl + e0 * bl_stride : nullptr, bl_stride, bl_div, d_rows + e0 * LGDSP_NCOL,
                                 h->d_tt + (size_t)si * (size_t)B * (size_t)icpc_split_tt_doubles(),
                                 h->d_saux + (size_t)si * (size_t)B * (size_t)icpc_split_aux_doubles(),
-                                h->d_scz + (size_t)si * (size_t)B * (size_t)icpc_split_cz_doubles(), grids, st,
+                                h->d_scz + (size_t)si * (size_t)B * (size_t)icpc_split_cz_doubles(),
+                                h->split_bps, h->sm_count, st,
                                 h->split_par ? h->s_cz[si] : nullptr, h->ev_pre[si], h->ev_cz[si]);
         CK(cudaGetLastError());
         h->launches += cz ? (D.direct ? 3 : 4) : 2;

@@ -626,19 +626,21 @@ __device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, d
 }
 
 // window states at m = CH*tid in closed form from the tables
-__device__ __forceinline__ void cz_init(const CzDev& Z, const double* TT, int n, int tid, double* tabA, double* tabB, double pp0,
-                        CzState& S)
+// tab_c(q, kind, chunk) / tab_a(q, chunk): the decimated prefix tables (causal P-, D1, D2 / anti-causal P+) at a chunk
+template <typename TC, typename TA>
+__device__ __forceinline__ void cz_init_with(const CzDev& Z, const double* TT, int n, int tid, double pp0, CzState& S, TC&& tab_c,
+                                             TA&& tab_a)
 {
     const int m = tid * CH;
     S.active = (m < n) && (m + CH - 1 >= Z.L - 1);
     if (!S.active) return;
     auto lc = [&](int q, int kind, int pos) -> double {   // causal prefixes (P-, D1, D2): zero before the trace
-        return pos < 0 ? 0.0 : cz_tab(tabA, tabB, q * 3 + kind)[pos / CH];
+        return pos < 0 ? 0.0 : tab_c(q, kind, pos / CH);
     };
     auto la = [&](int q, int pos) -> double {             // anti-causal prefix P+
         if (pos >= n) return 0.0;
         if (pos < 0) return exp_d((double)pos * Z.inv_sigma) * pp0;   // rho^(-pos) * P+[0]
-        return cz_tab(tabA, tabB, 12 + q)[pos / CH];
+        return tab_a(q, pos / CH);
     };
     auto d0 = [&](int j) -> double {                      // D0[j] = sum_{i<=j} d[i] = TT[j+1] - r*TT[j]
         return j < 0 ? 0.0 : fma(-Z.r, TT[j], TT[j + 1]);
@@ -660,6 +662,13 @@ __device__ __forceinline__ void cz_init(const CzDev& Z, const double* TT, int n,
     S.V0 = b0;
     S.V1 = b1 - qq * b0;
     S.V2 = b2 - 2.0 * qq * b1 + qq * qq * b0;
+}
+__device__ __forceinline__ void cz_init(const CzDev& Z, const double* TT, int n, int tid, double* tabA, double* tabB, double pp0,
+                        CzState& S)
+{
+    cz_init_with(Z, TT, n, tid, pp0, S,
+                 [&](int q, int kind, int c) -> double { return cz_tab(tabA, tabB, q * 3 + kind)[c]; },
+                 [&](int q, int c) -> double { return cz_tab(tabA, tabB, 12 + q)[c]; });
 }
 
 // one input stream d[j], j advancing by one per step
@@ -684,6 +693,19 @@ struct CzStream {
         t = tn;
         return d;
     }
+    // the same with the load of the following step issued one step ahead (tpre = p[k] on entry; reads p[k + 1] <= TT[n + 1])
+    double tpre;
+    __device__ __forceinline__ void prime() { tpre = p[0]; }
+    __device__ __forceinline__ double next_fast_pf(double r, int k)
+    {
+        const double tn = tpre;
+        tpre = p[k + 1];
+        const double y = tn - t;
+        const double d = fma(-r, yprev, y);
+        yprev = y;
+        t = tn;
+        return d;
+    }
     // indices before the trace read as zero, beyond the end clamp
     __device__ __forceinline__ double next_safe(const double* TT, double r, int n)
     {
@@ -701,7 +723,7 @@ struct CzStream {
 // CH recurrence steps of one candidate chunk: the CUSP and ZAC outputs go to obuf[k][0..1] (-inf where m0+k is not a
 // valid output); maxima, argmaxima and the pick-off windows are taken from there by a block-parallel pass.  No
 // compares or branches in the loop: the only loop-carried dependency is the state update.
-template <typename F>
+template <bool PF = false, typename F>
 __device__ __forceinline__ void cz_out_each(const CzDev& Z, const double* TT, int n, int tid, CzState& S, F&& f)
 {
     const int m0 = tid * CH;
@@ -732,7 +754,16 @@ __device__ __forceinline__ void cz_out_each(const CzDev& Z, const double* TT, in
         S.EmR = fma(Z.rho_inv, S.EmR, fma(Z.cA_rho_Rn, c, -Z.cA * d));
     };
     const bool interior = (m0 - L >= 1) && (m0 + CH + 1 <= n);
-    if (interior) {
+    if (interior && PF) {
+        // loads one step ahead (global-memory prefix sums: the finish kernel of the split pipeline)
+        s0.prime(); s1.prime(); s2.prime(); s3.prime();
+#pragma unroll 1
+        for (int k = 0; k < CH; ++k) {
+            emit(k);
+            const double a = s0.next_fast_pf(r, k), b = s1.next_fast_pf(r, k), c = s2.next_fast_pf(r, k), d = s3.next_fast_pf(r, k);
+            update(a, b, c, d);
+        }
+    } else if (interior) {
 #pragma unroll 1
         for (int k = 0; k < CH; ++k) {
             emit(k);
@@ -2412,35 +2443,36 @@ long long icpc_split_tt_doubles() { return TTG_LEN; }
 long long icpc_split_aux_doubles() { return AUX_LEN; }
 long long icpc_split_cz_doubles() { return CZG_LEN; }
 
-// one event batch: prefix -> extract -> CUSP/ZAC on `stream`; d_tt / d_aux hold n_events slots
+// one event batch: prefix -> extract || CUSP/ZAC (select + finish) on `stream` (and `stream_cz`); the d_* scratch buffers hold
+// n_events slots.  bps3: resident blocks per SM of {prefix, extract, CUSP/ZAC select}
 void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld,
                              const double* d_bl_ext, long long bl_stride, double bl_div, double* d_rows, double* d_tt, double* d_aux,
-                             double* d_cz, const int* grids3, cudaStream_t stream, cudaStream_t stream_cz, cudaEvent_t ev_prefix,
-                             cudaEvent_t ev_cz)
+                             double* d_cz, const int* bps3, int sm_count, cudaStream_t stream, cudaStream_t stream_cz,
+                             cudaEvent_t ev_prefix, cudaEvent_t ev_cz)
 {
     const bool cz = (P.groups & LGDSP_GROUP_CUSPZAC) != 0;
+    auto grid = [&](int k) { const long long cap = (long long)sm_count * bps3[k]; return (int)(n_events < cap ? n_events : cap); };
     if (sample_bytes == 4)
-        icpc_prefix_kernel<uint32_t><<<grids3[0], NT, K1_TOTAL, stream>>>(P, static_cast<const uint32_t*>(d_wf), n_events, ld, d_bl_ext,
-                                                                          bl_stride, bl_div, d_tt, d_aux, d_rows);
+        icpc_prefix_kernel<uint32_t><<<grid(0), NT, K1_TOTAL, stream>>>(P, static_cast<const uint32_t*>(d_wf), n_events, ld, d_bl_ext,
+                                                                        bl_stride, bl_div, d_tt, d_aux, d_rows);
     else
-        icpc_prefix_kernel<uint16_t><<<grids3[0], NT, K1_TOTAL, stream>>>(P, static_cast<const uint16_t*>(d_wf), n_events, ld, d_bl_ext,
-                                                                          bl_stride, bl_div, d_tt, d_aux, d_rows);
-    // the two consumers only depend on the prefix kernel: with a second stream they share the SMs (the extract kernel is issue
-    // bound, the CUSP/ZAC kernel waits on its serial recurrences)
-    const bool par = cz && stream_cz != nullptr && stream_cz != stream;
+        icpc_prefix_kernel<uint16_t><<<grid(0), NT, K1_TOTAL, stream>>>(P, static_cast<const uint16_t*>(d_wf), n_events, ld, d_bl_ext,
+                                                                        bl_stride, bl_div, d_tt, d_aux, d_rows);
     const int fin_grid = (int)((n_events + K4_WARPS - 1) / K4_WARPS);
+    auto launch_cz = [&](cudaStream_t st) {
+        icpc_cuspzac_kernel<<<grid(2), NT, K3_TOTAL, st>>>(P, d_tt, d_aux, n_events, d_cz, d_rows);
+        if (!P.direct) icpc_cuspzac_finish_kernel<<<fin_grid, K4_WARPS * 32, 0, st>>>(P, d_tt, d_cz, n_events, d_rows);
+    };
+    // the two consumers only depend on the prefix kernel: with a second stream their tails overlap
+    const bool par = cz && stream_cz != nullptr && stream_cz != stream;
     if (par) {
         cudaEventRecord(ev_prefix, stream);
         cudaStreamWaitEvent(stream_cz, ev_prefix, 0);
-        icpc_cuspzac_kernel<<<grids3[2], NT, K3_TOTAL, stream_cz>>>(P, d_tt, d_aux, n_events, d_cz, d_rows);
-        if (!P.direct) icpc_cuspzac_finish_kernel<<<fin_grid, K4_WARPS * 32, 0, stream_cz>>>(P, d_tt, d_cz, n_events, d_rows);
+        launch_cz(stream_cz);
         cudaEventRecord(ev_cz, stream_cz);
     }
-    icpc_extract_kernel<<<grids3[1], NT2, K2_TOTAL, stream>>>(P, d_tt, d_aux, n_events, cz ? 0 : 1, d_rows);
-    if (cz && !par) {
-        icpc_cuspzac_kernel<<<grids3[2], NT, K3_TOTAL, stream>>>(P, d_tt, d_aux, n_events, d_cz, d_rows);
-        if (!P.direct) icpc_cuspzac_finish_kernel<<<fin_grid, K4_WARPS * 32, 0, stream>>>(P, d_tt, d_cz, n_events, d_rows);
-    }
+    icpc_extract_kernel<<<grid(1), NT2, K2_TOTAL, stream>>>(P, d_tt, d_aux, n_events, cz ? 0 : 1, d_rows);
+    if (cz && !par) launch_cz(stream);
     if (par) cudaStreamWaitEvent(stream, ev_cz, 0);   // the ring slot is reused behind both consumers
 }
 

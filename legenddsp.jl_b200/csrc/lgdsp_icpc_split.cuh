@@ -23,6 +23,7 @@ enum { AX_M = 0, AX_EMAX = 1, AX_YMAX = 2, AX_THR = 3 /* 5 */, AX_POS = 8 /* 5 *
 // ---- prefix kernel: shared memory ----
 enum { K1R_BLS = 0, K1R_BLSS, K1R_BLSX, K1R_MX /* + K1R_MN: 4 x NWARP uint32 */, K1R_MN, K1R_SLEN, K1R_SS, K1R_SQ,
        K1R_TLS, K1R_TLSS, K1R_TLSX, K1R_TLBAD, K1R_YMAX, K1R_N };
+
 constexpr int K1_XS = 0;                                   // 2 x (MAXN * 2) bytes: double-buffered raw samples
 constexpr int K1_MASK = K1_XS + 2 * MAXN * 2;              // uint32 masks[5][NWORDS]: t10..t99
 constexpr int K1_RED = K1_MASK + 5 * NWORDS * 4;
@@ -257,41 +258,53 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
                 double* tile = reinterpret_cast<double*>(smem + K1_TILE) + wid * (32 * TILE_LD);
                 double tprev = TT0;
                 const int cbase = wid * 32;   // first chunk of this warp
+                // store pass: lane -> (chunk 4r + lane/8, sample kb + lane%8); everything but r and kb is loop invariant
+                const double* trd = tile + (lane >> 3) * TILE_LD + (lane & 7);
+                double* gwr = tg + (cbase + (lane >> 3)) * CH + (lane & 7) + 1;
+                const int glim = n - ((cbase + (lane >> 3)) * CH + (lane & 7));   // sample kb of chunk 4r is valid iff kb + 4r*CH < glim
+                const bool wfull = (cbase + 32) * CH <= n;                        // every chunk of this warp is complete
+                // sample k of the chunk: prefix sum, threshold bits, scan step
+                auto sample = [&](int k, bool with_thr) -> double {
+                    const double tn = body(k);
+                    if (with_thr) {
+                        const double y = tn - tprev;     // = TT[i+1] - TT[i] as every consumer forms it
+                        if (k < 32) {
+                            const uint32_t bit = 1u << k;
+#pragma unroll
+                            for (int t = 0; t < 5; ++t) lo[t] |= (y >= thr[t]) ? bit : 0u;
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 5; ++t) hi |= (y >= thr[t]) ? (1u << t) : 0u;
+                        }
+                    }
+                    tprev = tn;
+                    return tn;
+                };
 #pragma unroll 1
                 for (int kb = 0; kb < 32; kb += 8) {
+                    if (wfull && !wstr) {
+                        // common case: complete chunks, no threshold inside this warp's samples
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const int k = kb + kk;
-                        if (k < cvalid) {
-                            const double tn = body(k);
-                            if (wstr) {
-                                const double y = tn - tprev;     // = TT[i+1] - TT[i] as every consumer forms it
-                                const uint32_t bit = 1u << k;
+                        for (int kk = 0; kk < 8; ++kk) tile[lane * TILE_LD + kk] = sample(kb + kk, false);
+                    } else {
 #pragma unroll
-                                for (int t = 0; t < 5; ++t) lo[t] |= (y >= thr[t]) ? bit : 0u;
-                            }
-                            tprev = tn;
-                            tile[lane * TILE_LD + kk] = tn;
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const int k = kb + kk;
+                            if (k < cvalid) tile[lane * TILE_LD + kk] = sample(k, wstr);
                         }
                     }
                     __syncwarp();
+                    if (wfull) {
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const int c = 4 * r + (lane >> 3), kk = lane & 7;
-                        const int ci0 = (cbase + c) * CH;
-                        if (ci0 + kb + kk < n) tg[ci0 + kb + kk + 1] = tile[c * TILE_LD + kk];
+                        for (int r = 0; r < 8; ++r) gwr[kb + r * (4 * CH)] = trd[r * (4 * TILE_LD)];
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            if (kb + r * (4 * CH) < glim) gwr[kb + r * (4 * CH)] = trd[r * (4 * TILE_LD)];
                     }
                     __syncwarp();
                 }
-                if (cvalid > 32) {
-                    const double tn = body(32);
-                    if (wstr) {
-                        const double y = tn - tprev;
-#pragma unroll
-                        for (int t = 0; t < 5; ++t) hi |= (y >= thr[t]) ? (1u << t) : 0u;
-                    }
-                    tg[i0 + 33] = tn;
-                }
+                if (cvalid > 32) tg[i0 + 33] = sample(32, wstr);
                 if (tid == 0) tg[0] = 0.0;
                 if (i0 <= n && n < i0 + CH) tg[n + 1] = 0.0;   // the consumers load (n + 2) doubles (16-byte granularity)
             }
@@ -314,41 +327,55 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
             const double ya = wmax_d(cvalid > 0 ? fmax(fabs(ylo), fabs(yhi)) : 0.0);
             red_put(red, K1R_YMAX, wid, lane, ya);
         }
-        // tailstats: log-regression on the PRE-PZ waveform (src/tailstats.jl:22-72), samples strided over the block
+        // tailstats: log-regression on the PRE-PZ waveform (src/tailstats.jl:22-72).  Every thread takes a run of CONSECUTIVE
+        // tail samples: log(w) = log(c) + log1p((w - c)/c) around the thread's first sample c, and inside such a run (w - c)/c
+        // is noise over amplitude, so a short Taylor polynomial reaches 1e-16 (the warp picks the degree its largest |u| needs;
+        // a sample further than 1/8 away takes the full logarithm and becomes the new reference).
         {
             double tl_S = 0, tl_SS = 0, tl_SX = 0;
             bool bad = false;
             double cref = 0.0, cinv = 0.0, clog = 0.0;
-            auto one = [&](int idx, double w, double u) {
-                if (w <= 0.0) { bad = true; return; }
+            const int ntail = P.tail_until - P.tail_from + 1;
+            const int q = (ntail + NT - 1) / NT;
+            const int ia = P.tail_from + tid * q, ib = min(ia + q - 1, P.tail_until);
+#pragma unroll 1
+            for (int i = 0; i < q; ++i) {
+                const int idx = ia + i;
+                const bool act = idx <= ib;
+                const double w = act ? u2d(xs[idx]) - m : cref;
+                const bool pos = w > 0.0;
+                if (act && !pos) bad = true;
+                const double u = (w - cref) * cinv, au = fabs(u);
+                const bool use = act && pos;
+                int cat = 0;
+                if (use) cat = !(cref > 0.0) || au > 0.125 ? 3 : (au > 0.015625 ? 2 : (au > 0.0009765625 ? 1 : 0));
+                const int wcat = __reduce_max_sync(FULL, cat);
                 double lg;
-                if (cref > 0.0 && fabs(u) <= 0.125) {
+                if (wcat == 0) {
+                    // |u| <= 2^-10: terms to u^5 (truncation u^5/6 < 2e-16 relative)
+                    double pl = fma(u, 1.0 / 5.0, -1.0 / 4.0);
+                    pl = fma(u, pl, 1.0 / 3.0); pl = fma(u, pl, -1.0 / 2.0); pl = fma(u, pl, 1.0);
+                    lg = fma(u, pl, clog);
+                } else if (wcat == 1) {
+                    // |u| <= 2^-6: terms to u^9
+                    const double u2 = u * u, u4 = u2 * u2;
+                    const double a0 = fma(-1.0 / 2.0, u, 1.0), a1 = fma(-1.0 / 4.0, u, 1.0 / 3.0), a2 = fma(-1.0 / 6.0, u, 1.0 / 5.0),
+                                 a3 = fma(-1.0 / 8.0, u, 1.0 / 7.0);
+                    const double b0 = fma(a1, u2, a0), b1 = fma(a3, u2, a2);
+                    const double c0 = fma(b1, u4, b0);
+                    lg = fma(u, fma(u4 * u4, 1.0 / 9.0, c0), clog);
+                } else {
                     lg = clog + log1p_small(u);
-                } else {
-                    lg = log_d(w);
-                    cref = w; cinv = 1.0 / w; clog = lg;
-                }
-                const double X = t_first + (double)idx * dt;
-                tl_S += lg;
-                tl_SS = fma(lg, lg, tl_SS);
-                tl_SX = fma(X, lg, tl_SX);
-            };
-#pragma unroll 1
-            for (int idx = P.tail_from + tid; idx <= P.tail_until; idx += 2 * NT) {
-                const bool two = idx + NT <= P.tail_until;
-                const double w0 = u2d(xs[idx]) - m, w1 = two ? u2d(xs[idx + NT]) - m : cref;
-                const double u0 = (w0 - cref) * cinv, u1 = (w1 - cref) * cinv;
-                if (two && cref > 0.0 && w0 > 0.0 && w1 > 0.0 && fabs(u0) <= 0.125 && fabs(u1) <= 0.125) {
-                    const double l0 = clog + log1p_small(u0), l1 = clog + log1p_small(u1);
-                    const double X0 = t_first + (double)idx * dt, X1 = t_first + (double)(idx + NT) * dt;
-                    tl_S += l0; tl_SS = fma(l0, l0, tl_SS); tl_SX = fma(X0, l0, tl_SX);
-                    tl_S += l1; tl_SS = fma(l1, l1, tl_SS); tl_SX = fma(X1, l1, tl_SX);
-                } else {
-#pragma unroll 1
-                    for (int q = 0; q < (two ? 2 : 1); ++q) {
-                        const double w = q ? w1 : w0;
-                        one(idx + q * NT, w, (w - cref) * cinv);
+                    if (cat == 3) {
+                        lg = log_d(w);
+                        cref = w; cinv = 1.0 / w; clog = lg;
                     }
+                }
+                if (use) {
+                    const double X = t_first + (double)idx * dt;
+                    tl_S += lg;
+                    tl_SS = fma(lg, lg, tl_SS);
+                    tl_SX = fma(X, lg, tl_SX);
                 }
             }
             tl_S = wsum_d(tl_S); tl_SS = wsum_d(tl_SS); tl_SX = wsum_d(tl_SX);
@@ -934,7 +961,7 @@ enum { K3R_CZC0 = 0, K3R_CZC1, K3R_CZMAX0, K3R_CZARG0, K3R_CZMAX1, K3R_CZARG1, K
 enum { K3I_CZN = 0, K3I_PKFROM = 1 /* 2 */, K3I_N = 4 };
 constexpr int K3_TT = 0;
 constexpr int K3_TABA = K3_TT + TT_LEN * 8;                 // double tabA[8][NT]
-constexpr int K3_TABB = K3_TABA + 8 * NT * 8;               // double tabB[8][NT]: tables 8..15
+constexpr int K3_TABB = K3_TABA + 8 * NT * 8;               // double tabB[8][NT]: tables 8..15 (contiguous with tabA)
 constexpr int K3_CZCO = K3_TABB + 8 * NT * 8;               // double czco[2][NT]: coarse CUSP / ZAC values
 constexpr int K3_RED = K3_CZCO + 2 * NT * 8;
 constexpr int K3_STASH = K3_RED + K3R_N * NWARP * 8;        // double stash[2][LGDSP_MAX_DNI] (direct mode)
@@ -945,6 +972,89 @@ constexpr int K3_PAR = K3_BAR + 16;                         // SmemPar (CzDev co
 constexpr int K3_TOTAL = K3_PAR + (int)sizeof(SmemPar);
 static_assert(2 * (K3_TOTAL + 1024) <= 233472, "two CTAs per SM");
 enum { K3S_PKP = 0 /* 2 */, K3S_PP0 = 2, K3S_YMAX = 3 };
+
+// Candidate selection of one structured pass: closed-form window states at every chunk
+// start (tab_c / tab_a read the prefix tables), coarse CUSP / ZAC values, Lipschitz bound against the best coarse value,
+// candidate records + header -> cg.  Contains two block barriers; every thread of the block must call it.
+template <typename TC, typename TA>
+__device__ __forceinline__ void cz_select(const CzDev& Z, const double* TT, int n, int nw, double pp0, double Ymax, const int* pk_from,
+                                          const double* pk_p, bool want_cusp, bool want_zac, double* czco, double* red, int* czn,
+                                          double* cg, TC&& tab_c, TA&& tab_a)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int i0 = tid * CH;
+    CzState st;
+    st.active = false;
+    double oc = -CUDART_INF, oz = -CUDART_INF;
+    cz_init_with(Z, TT, n, tid, pp0, st, tab_c, tab_a);
+    cz_coarse(Z, TT, n, tid, st, oc, oz);
+    if (!want_cusp) oc = -CUDART_INF;
+    if (!want_zac) oz = -CUDART_INF;
+    // the coarse points are outputs themselves
+    const int j0 = i0 - Z.L + 1;
+    czco[tid] = oc;
+    czco[NT + tid] = oz;
+    {
+        int ac = oc > -CUDART_INF ? j0 : 0x7fffffff, az = oz > -CUDART_INF ? j0 : 0x7fffffff;
+        const double wc = wargmax_d(oc, ac), wz = wargmax_d(oz, az);
+        if (lane == 0) {
+            red[K3R_CZMAX0 * NWARP + wid] = wc; red[K3R_CZARG0 * NWARP + wid] = (double)ac;
+            red[K3R_CZMAX1 * NWARP + wid] = wz; red[K3R_CZARG1 * NWARP + wid] = (double)az;
+        }
+    }
+    __syncthreads();   // tables are dead, coarse values complete
+    double Mc, Mz;
+    int Ac, Az;
+    red_argmax(red, K3R_CZMAX0, K3R_CZARG0, Mc, Ac);
+    red_argmax(red, K3R_CZMAX1, K3R_CZARG1, Mz, Az);
+    // candidate chunks: Lipschitz bound on (33 tid, 33 tid + 33) against the best coarse value; chunks that
+    // hold part of a pick-off window are always evaluated
+    bool cand = false;
+    if (st.active) {
+        const int t1 = min(tid + 1, NT - 1);
+        const double kap = Ymax * 1.000001;
+        const int jlo = i0 - Z.L + 1, jhi = jlo + CH - 1;
+        if (want_cusp) {
+            const double a = oc, b = (tid + 1 < NT) ? czco[t1] : -CUDART_INF;
+            const double kc = kap * Z.lip_cusp;
+            double bound;
+            if (a > -CUDART_INF) bound = interval_bound(a, b, b > -CUDART_INF, kc);
+            else if (b > -CUDART_INF) bound = fma((double)CH, kc, b);
+            else bound = CUDART_INF;
+            cand |= bound + 1e-6 * (fabs(Mc) + Ymax * fabs(Z.g)) >= Mc;
+            cand |= (jhi >= pk_from[0] && jlo < pk_from[0] + nw);
+        }
+        if (want_zac) {
+            const double a = oz, b = (tid + 1 < NT) ? czco[NT + t1] : -CUDART_INF;
+            const double kz = kap * Z.lip_zac;
+            double bound;
+            if (a > -CUDART_INF) bound = interval_bound(a, b, b > -CUDART_INF, kz);
+            else if (b > -CUDART_INF) bound = fma((double)CH, kz, b);
+            else bound = CUDART_INF;
+            cand |= bound + 1e-6 * (fabs(Mz) + Ymax * fabs(Z.g)) >= Mz;
+            cand |= (jhi >= pk_from[1] && jlo < pk_from[1] + nw);
+        }
+    }
+    // candidate records: the window states at the chunk start + the chunk index
+    {
+        const unsigned bc = __ballot_sync(FULL, cand);
+        int base = 0;
+        if (lane == 0 && bc) base = atomicAdd(czn, __popc(bc));
+        base = __shfl_sync(FULL, base, 0);
+        if (cand) {
+            double* r = cg + CZ_HDR + (size_t)(base + __popc(bc & ((1u << lane) - 1u))) * CZ_REC;
+            r[0] = st.EmL; r[1] = st.EpL; r[2] = st.W0L; r[3] = st.W1L; r[4] = st.W2L; r[5] = st.W0F;
+            r[6] = st.V0; r[7] = st.V1; r[8] = st.V2; r[9] = st.EpR; r[10] = st.EmR; r[11] = (double)tid;
+        }
+    }
+    __syncthreads();   // candidate count complete
+    if (tid == 0) {
+        cg[CZH_N] = (double)*czn;
+        cg[CZH_MAXC] = Mc; cg[CZH_ARGC] = (double)Ac; cg[CZH_MAXZ] = Mz; cg[CZH_ARGZ] = (double)Az;
+        cg[CZH_PKP0] = pk_p[0]; cg[CZH_PKF0] = (double)pk_from[0];
+        cg[CZH_PKP1] = pk_p[1]; cg[CZH_PKF1] = (double)pk_from[1];
+    }
+}
 
 __global__ void __launch_bounds__(NT, 2)
 icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict__ ttg, const double* __restrict__ auxg,
@@ -1071,78 +1181,10 @@ icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             cz_scan<K3_PAR>(ps, TT, n, tid, tabA, tabB, red + K3R_CZSCR * NWARP, scr + K3S_PP0);
             __syncthreads();   // tables (and the pick-off windows) are complete
             const int pk_from[2] = {ibuf[K3I_PKFROM], ibuf[K3I_PKFROM + 1]};
-            const double Ymax = scr[K3S_YMAX];
-            CzState st;
-            st.active = false;
-            double oc = -CUDART_INF, oz = -CUDART_INF;
-            cz_init(Z, TT, n, tid, tabA, tabB, scr[K3S_PP0], st);
-            cz_coarse(Z, TT, n, tid, st, oc, oz);
-            if (!want_cusp) oc = -CUDART_INF;
-            if (!want_zac) oz = -CUDART_INF;
-            // the coarse points are outputs themselves
-            const int j0 = i0 - Z.L + 1;
-            czco[tid] = oc;
-            czco[NT + tid] = oz;
-            {
-                int ac = oc > -CUDART_INF ? j0 : 0x7fffffff, az = oz > -CUDART_INF ? j0 : 0x7fffffff;
-                const double wc = wargmax_d(oc, ac), wz = wargmax_d(oz, az);
-                if (lane == 0) {
-                    red[K3R_CZMAX0 * NWARP + wid] = wc; red[K3R_CZARG0 * NWARP + wid] = (double)ac;
-                    red[K3R_CZMAX1 * NWARP + wid] = wz; red[K3R_CZARG1 * NWARP + wid] = (double)az;
-                }
-            }
-            __syncthreads();   // tables are dead, coarse values complete
-            double Mc, Mz;
-            int Ac, Az;
-            red_argmax(red, K3R_CZMAX0, K3R_CZARG0, Mc, Ac);
-            red_argmax(red, K3R_CZMAX1, K3R_CZARG1, Mz, Az);
-            // candidate chunks: Lipschitz bound on (33 tid, 33 tid + 33) against the best coarse value; chunks that
-            // hold part of a pick-off window are always evaluated
-            bool cand = false;
-            if (st.active) {
-                const int t1 = min(tid + 1, NT - 1);
-                const double kap = Ymax * 1.000001;
-                const int jlo = i0 - Z.L + 1, jhi = jlo + CH - 1;
-                if (want_cusp) {
-                    const double a = oc, b = (tid + 1 < NT) ? czco[t1] : -CUDART_INF;
-                    const double kc = kap * Z.lip_cusp;
-                    double bound;
-                    if (a > -CUDART_INF) bound = interval_bound(a, b, b > -CUDART_INF, kc);
-                    else if (b > -CUDART_INF) bound = fma((double)CH, kc, b);
-                    else bound = CUDART_INF;
-                    cand |= bound + 1e-6 * (fabs(Mc) + Ymax * fabs(Z.g)) >= Mc;
-                    cand |= (jhi >= pk_from[0] && jlo < pk_from[0] + nw);
-                }
-                if (want_zac) {
-                    const double a = oz, b = (tid + 1 < NT) ? czco[NT + t1] : -CUDART_INF;
-                    const double kz = kap * Z.lip_zac;
-                    double bound;
-                    if (a > -CUDART_INF) bound = interval_bound(a, b, b > -CUDART_INF, kz);
-                    else if (b > -CUDART_INF) bound = fma((double)CH, kz, b);
-                    else bound = CUDART_INF;
-                    cand |= bound + 1e-6 * (fabs(Mz) + Ymax * fabs(Z.g)) >= Mz;
-                    cand |= (jhi >= pk_from[1] && jlo < pk_from[1] + nw);
-                }
-            }
-            // candidate records: the window states at the chunk start + the chunk index
-            {
-                const unsigned bc = __ballot_sync(FULL, cand);
-                int base = 0;
-                if (lane == 0 && bc) base = atomicAdd(&ibuf[K3I_CZN], __popc(bc));
-                base = __shfl_sync(FULL, base, 0);
-                if (cand) {
-                    double* r = cg + CZ_HDR + (size_t)(base + __popc(bc & ((1u << lane) - 1u))) * CZ_REC;
-                    r[0] = st.EmL; r[1] = st.EpL; r[2] = st.W0L; r[3] = st.W1L; r[4] = st.W2L; r[5] = st.W0F;
-                    r[6] = st.V0; r[7] = st.V1; r[8] = st.V2; r[9] = st.EpR; r[10] = st.EmR; r[11] = (double)tid;
-                }
-            }
-            __syncthreads();   // candidate count complete
-            if (tid == 0) {
-                cg[CZH_N] = (double)ibuf[K3I_CZN];
-                cg[CZH_MAXC] = Mc; cg[CZH_ARGC] = (double)Ac; cg[CZH_MAXZ] = Mz; cg[CZH_ARGZ] = (double)Az;
-                cg[CZH_PKP0] = scr[K3S_PKP]; cg[CZH_PKF0] = (double)pk_from[0];
-                cg[CZH_PKP1] = scr[K3S_PKP + 1]; cg[CZH_PKF1] = (double)pk_from[1];
-            }
+            cz_select(Z, TT, n, nw, scr[K3S_PP0], scr[K3S_YMAX], pk_from, scr + K3S_PKP, want_cusp, want_zac, czco, red,
+                      &ibuf[K3I_CZN], cg,
+                      [&](int q, int kind, int c) -> double { return tabA[(q * 3 + kind) * NT + c]; },
+                      [&](int q, int c) -> double { return tabA[(12 + q) * NT + c]; });
         };
         if (npass == 2) {
             cz_pass(std::integral_constant<int, 1>{}, false, true, false);
@@ -1195,7 +1237,7 @@ icpc_cuspzac_finish_kernel(const __grid_constant__ IcpcDev P, const double* __re
                     st.active = true;
                     const int chunk = (int)r[11];
                     const int jb = chunk * CH - Z.L + 1;
-                    cz_out_each(Z, TT, n, chunk, st, [&](int k, double o_c, double o_z) {
+                    cz_out_each<true>(Z, TT, n, chunk, st, [&](int k, double o_c, double o_z) {
                         const int j = jb + k;
                         if (want_cusp) {
                             if (o_c > czmax[0] || (o_c == czmax[0] && j < czarg[0])) { czmax[0] = o_c; czarg[0] = j; }

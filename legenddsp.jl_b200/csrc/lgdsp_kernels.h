@@ -13,14 +13,15 @@ cudaError_t icpc_configure(int* max_blocks_per_sm);
 // d_bl_ext != NULL: event e is shifted by -(d_bl_ext[e * bl_stride] / bl_div) instead of by its own baseline mean
 void icpc_launch(const IcpcDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld, const double* d_bl_ext,
                  long long bl_stride, double bl_div, double* d_rows, int grid, cudaStream_t stream);
-// split pipeline (lgdsp_icpc_split.cuh): resident blocks per SM of the prefix / extract / CUSP-ZAC kernels; ring sizes per event
+// split pipeline (lgdsp_icpc_split.cuh): resident blocks per SM of {prefix, extract, CUSP/ZAC select}; scratch sizes per event
 cudaError_t icpc_split_configure(int* bps3);
 long long icpc_split_tt_doubles();
 long long icpc_split_aux_doubles();
 long long icpc_split_cz_doubles();
 void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld,
                              const double* d_bl_ext, long long bl_stride, double bl_div, double* d_rows, double* d_tt, double* d_aux,
-                             double* d_cz, const int* grids3, cudaStream_t stream, cudaStream_t stream_cz, cudaEvent_t ev_prefix, cudaEvent_t ev_cz);
+                             double* d_cz, const int* bps3, int sm_count, cudaStream_t stream, cudaStream_t stream_cz,
+                             cudaEvent_t ev_prefix, cudaEvent_t ev_cz);
 // window w is shifted by -d_shift[e * shift_stride] when d_shift != NULL and bit w of shift_mask is set
 void window_stats_launch(const void* d_wf, int sample_bytes, long long n_events, long long ld, double t_first, double dt,
                          const double* d_shift, long long shift_stride, unsigned shift_mask, const int* d_win, int n_windows,
@@ -50,6 +51,14 @@ struct SweepDev {
 cudaError_t sweep_configure(int* max_blocks_per_sm);
 void sweep_launch(const SweepDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld, const double* d_bl_ext,
                   void* d_out, double* d_aux, int grid, cudaStream_t stream);
+
+// ---- waveform codecs of decode_data (lgdsp_codec.cu) ----
+long long codec_max_encoded_bytes(int codec, int n_samples, int sample_bytes);
+int codec_encode_host(int codec, const void* wf, int sample_bytes, long long n_events, int n_samples, long long ld, int shift,
+                      uint8_t* enc, long long cap, long long* offsets);
+cudaError_t codec_decode_launch(int codec, const uint8_t* d_enc, const long long* d_off, long long off_base, long long n_events,
+                                int n_samples, int shift, void* d_out, int sample_bytes, long long ld, int* d_status, int sm_count,
+                                cudaStream_t stream);
 
 // synthetic generator
 void synth_launch(const lgdsp_synth_params& sp, long long first_event, long long n_events, long long ld, uint16_t* d_wf,

@@ -1,6 +1,8 @@
 """The split dsp_icpc pipeline (prefix / extract / CUSP-ZAC kernels coupled through the prefix-sum ring) against the
 single-kernel path of round 1, through the C ABI: both evaluate the same expressions in the same order, so the rows
-must be IDENTICAL (bit for bit, NaNs in the same places), for every batch / stream setting and column-group mask."""
+must be IDENTICAL (bit for bit, NaNs in the same places), for every batch / stream setting and column-group mask.
+Exception: the three tailstats columns -- the split path sums the tail logarithms in a different order and with shorter
+log1p polynomials, so they are compared with the oracle tolerances of tests/parity.py."""
 import numpy as np
 import pytest
 
@@ -15,9 +17,15 @@ def _rows(L, h, wf, P, path, batch=0, streams=0):
         h.set_icpc_path("split")
 
 
+_TAIL = ("tail_mean", "tail_sigma", "tail_tau")
+
+
 def _identical(a, b, columns):
-    bad = {}
+    from parity import compare_rows
+    bad = {k: v for k, v in compare_rows(a, b, columns).items() if k in _TAIL and v[1] > 0}
     for j, name in enumerate(columns):
+        if name in _TAIL:
+            continue
         x, y = a[:, j], b[:, j]
         same = (x == y) | (np.isnan(x) & np.isnan(y))
         if not same.all():
