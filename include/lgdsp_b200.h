@@ -343,13 +343,36 @@ int lgdsp_zac_coeffs(double sigma, int32_t flat, double tau, int32_t n_taps, dou
 
 /* ---- dsp_icpc ---- */
 /* waveforms on the HOST: wf[e*ld_samples + i], i < n_samples; out_rows: host double[n_events][LGDSP_NCOL].
- * Copies in chunks (pinned staging, overlapped with compute), blocks until the result is in out_rows. */
+ * Copies in chunks overlapped with compute and blocks until the result is in out_rows.  Page-locked caller memory
+ * (cudaHostAlloc / cudaHostRegister) is copied directly; pageable memory is packed into the handle's pinned double buffers by
+ * LGDSP_COPY_THREADS host threads (default: half the cores, at most 8) so that the copies stay asynchronous. */
 int lgdsp_icpc_run(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* wf, int64_t n_events,
                    int64_t ld_samples, double* out_rows);
 /* waveforms and output rows in DEVICE memory (wf 16-byte aligned, ld_samples multiple of 8); asynchronous
  * on the handle's stream */
 int lgdsp_icpc_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* d_wf, int64_t n_events,
                           int64_t ld_samples, double* d_out_rows);
+/* ---- decode_data: LegendDataTypes.jl `decode_data(encoded_waveforms)`, called at /root/reference/src/dsp_icpc.jl:313-314,
+ * src/dsp_puls.jl:103, src/dsp_sipm.jl:241 ----
+ * Encoded waveform sets are a byte buffer `enc` plus `offsets[n_events + 1]` (the element pointers of the reference's
+ * VectorOfEncodedArrays): event e occupies enc[offsets[e] .. offsets[e+1]).  codec = LGDSP_CODEC_RADWARE (RadwareSigcompress(shift),
+ * 16-bit samples; the reference uses shift = -32768 for UInt16 waveforms) or LGDSP_CODEC_ULEB128ZZD (16- / 32-bit samples).
+ * A malformed stream makes the call return LGDSP_ERR_INVALID_ARG (device entry: status[e] = 1, zero-filled waveform). */
+int64_t lgdsp_codec_max_encoded_bytes(int32_t codec, int32_t n_samples, int32_t sample_bytes);
+/* host-side encoder (tests, benchmarks, round trips): fills enc and offsets; LGDSP_ERR_OOM when enc_capacity is too small */
+int lgdsp_codec_encode_host(int32_t codec, const void* wf, int32_t sample_bytes, int64_t n_events, int32_t n_samples, int64_t ld_samples,
+                            int32_t shift, uint8_t* enc, int64_t enc_capacity, int64_t* offsets);
+/* device buffers, asynchronous on the handle's stream; d_status (int32[n_events], may be NULL) */
+int lgdsp_decode_data_device(lgdsp_handle* h, int32_t codec, const uint8_t* d_enc, const int64_t* d_offsets, int64_t n_events,
+                             int32_t n_samples, int32_t shift, void* d_wf, int32_t sample_bytes, int64_t ld_samples, int32_t* d_status);
+/* host buffers: encoded bytes in, decoded samples out (chunked; blocks until wf is filled) */
+int lgdsp_decode_data(lgdsp_handle* h, int32_t codec, const uint8_t* enc, const int64_t* offsets, int64_t n_events, int32_t n_samples,
+                      int32_t shift, void* wf, int32_t sample_bytes, int64_t ld_samples);
+/* dsp_icpc on encoded waveforms in HOST memory: only the codec's bytes cross the host link, decode_data runs on the device in front
+ * of the chain (n_samples from the parameters; baseline as lgdsp_icpc_run_ext, may be NULL) */
+int lgdsp_icpc_run_encoded(lgdsp_handle* h, const lgdsp_icpc_params* p, int32_t codec, const uint8_t* enc, const int64_t* offsets,
+                           int32_t shift, int32_t sample_bytes, const double* baseline, int64_t n_events, double* out_rows);
+
 /* dsp_icpc_compressed building block (/root/reference/src/dsp_icpc.jl:293-499): the same chain on waveforms of
  * 16-bit (sample_bytes = 2) or 32-bit unsigned samples (sample_bytes = 4: presummed traces, n_samples <=
  * LGDSP_MAX_SAMPLES/2), with an optional per-event EXTERNAL baseline: when baseline != NULL the waveform is shifted by

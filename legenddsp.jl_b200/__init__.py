@@ -26,7 +26,8 @@ from .dsp_filter_optimization import (dsp_trap_rt_optimization, dsp_trap_ft_opti
 from .dsp_sipm import (dsp_sipm, dsp_sipm_compressed, sipm_rows, sipm_to_table, resolve_sipm_params, example_sipm_config, SIPM_TABLE,
                        VectorOfVectors, IntersectMaximum, MultiIntersect, thresholdstats, thresholdstats_mad)
 from .dsp_puls import dsp_puls, dsp_puls_compressed, dsp_decay_times, resolve_puls_params, PULS_COLUMNS
-from . import synth, sharding
+from .codec import EncodedWaveforms, encode_waveforms, decode_data, RADWARE_SIGCOMPRESS, ULEB128_ZIGZAG_DIFF
+from . import synth, sharding, codec
 
 __all__ = [
     "DSPConfig", "Q", "ns", "us", "RddspPolicy", "example_config", "tiefree_config", "get_fltpars", "grid_values",
@@ -40,5 +41,6 @@ __all__ = [
     "dsp_puls_compressed", "dsp_sipm_compressed", "dsp_sg_optimization_compressed",
     "dsp_sipm", "sipm_rows", "sipm_to_table", "resolve_sipm_params", "example_sipm_config", "SIPM_TABLE", "VectorOfVectors",
     "IntersectMaximum", "MultiIntersect", "thresholdstats", "thresholdstats_mad",
+    "EncodedWaveforms", "encode_waveforms", "decode_data", "RADWARE_SIGCOMPRESS", "ULEB128_ZIGZAG_DIFF", "codec",
     "synth", "sharding", "COLUMNS", "COL", "INT_COLUMNS", "NCOL", "UNITS",
 ]

@@ -51,6 +51,12 @@ def load_library():
     L.lgdsp_icpc_run_device.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i64, i64, vp]
     L.lgdsp_icpc_run_ext.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i32, vp, i64, i64, vp]
     L.lgdsp_icpc_run_ext_device.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i32, vp, i64, i64, vp]
+    L.lgdsp_codec_max_encoded_bytes.argtypes = [i32, i32, i32]
+    L.lgdsp_codec_max_encoded_bytes.restype = i64
+    L.lgdsp_codec_encode_host.argtypes = [i32, vp, i32, i64, i32, i64, i32, vp, i64, vp]
+    L.lgdsp_decode_data_device.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp, i32, i64, vp]
+    L.lgdsp_decode_data.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp, i32, i64]
+    L.lgdsp_icpc_run_encoded.argtypes = [vp, C.POINTER(_abi.IcpcParams), i32, vp, vp, i32, i32, vp, i64, vp]
     L.lgdsp_window_stats_run.argtypes = [vp, vp, i32, i64, i32, i64, C.c_double, C.c_double, vp, vp, i32, vp]
     L.lgdsp_window_stats_run_device.argtypes = [vp, vp, i32, i64, i32, i64, C.c_double, C.c_double, vp, vp, i32, vp]
     _comp = [vp, C.POINTER(_abi.IcpcParams), C.POINTER(_abi.IcpcParams), vp, i32, i64, vp, i32, i64, C.c_double, vp, i64,
@@ -87,6 +93,7 @@ EXPORTED_SYMBOLS = (
     "lgdsp_version", "lgdsp_last_error", "lgdsp_create", "lgdsp_destroy", "lgdsp_launch_count", "lgdsp_synchronize",
     "lgdsp_lsq_fit_matrix", "lgdsp_sg_coeffs", "lgdsp_cusp_coeffs", "lgdsp_zac_coeffs",
     "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params", "lgdsp_icpc_set_path", "lgdsp_icpc_run_ext", "lgdsp_icpc_run_ext_device",
+    "lgdsp_codec_max_encoded_bytes", "lgdsp_codec_encode_host", "lgdsp_decode_data", "lgdsp_decode_data_device", "lgdsp_icpc_run_encoded",
     "lgdsp_window_stats_run", "lgdsp_window_stats_run_device", "lgdsp_sipm_run", "lgdsp_sipm_run_device",
     "lgdsp_sipm_list_pointers_device", "lgdsp_sipm_list_gather_device", "lgdsp_thresholdstats", "lgdsp_intersect_maximum", "lgdsp_multi_intersect_run", "lgdsp_multi_intersect_run_device", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
     "lgdsp_trap_sweep_run", "lgdsp_trap_sweep_run_device", "lgdsp_sweep_run", "lgdsp_sweep_run_device",
@@ -180,6 +187,25 @@ class Handle:
                                                         C.c_void_p(d_wf_ptr), int(sample_bytes),
                                                         C.c_void_p(d_baseline_ptr) if d_baseline_ptr else None,
                                                         int(n_events), int(ld), C.c_void_p(d_out_ptr)))
+
+    # ---- decode_data ----
+    def decode_data_host(self, codec, enc_ptr, offsets_ptr, n_events, n_samples, shift, wf_ptr, sample_bytes, ld):
+        self._check(self._lib.lgdsp_decode_data(self._h, int(codec), C.c_void_p(enc_ptr), C.c_void_p(offsets_ptr), int(n_events),
+                                                int(n_samples), int(shift), C.c_void_p(wf_ptr), int(sample_bytes), int(ld)))
+
+    def decode_data_device(self, codec, d_enc_ptr, d_offsets_ptr, n_events, n_samples, shift, d_wf_ptr, sample_bytes, ld,
+                           d_status_ptr=None):
+        self._check(self._lib.lgdsp_decode_data_device(self._h, int(codec), C.c_void_p(d_enc_ptr), C.c_void_p(d_offsets_ptr),
+                                                       int(n_events), int(n_samples), int(shift), C.c_void_p(d_wf_ptr),
+                                                       int(sample_bytes), int(ld),
+                                                       C.c_void_p(d_status_ptr) if d_status_ptr else None))
+
+    def icpc_run_encoded_host(self, params, codec, enc_ptr, offsets_ptr, shift, sample_bytes, baseline_ptr, n_events, out_ptr):
+        """dsp_icpc on encoded waveforms in host memory (decode_data on the device)"""
+        self._check(self._lib.lgdsp_icpc_run_encoded(self._h, C.byref(params) if params is not None else None, int(codec),
+                                                     C.c_void_p(enc_ptr), C.c_void_p(offsets_ptr), int(shift), int(sample_bytes),
+                                                     C.c_void_p(baseline_ptr) if baseline_ptr else None, int(n_events),
+                                                     C.c_void_p(out_ptr)))
 
     def window_stats_host(self, wf_ptr, sample_bytes, n_events, n_samples, ld, t_first_ns, dt_ns, shift_ptr, windows, out_ptr):
         """signalstats on `windows` ([(from, until), ...] 0-based inclusive) of every waveform; out double[n][nw][5]"""

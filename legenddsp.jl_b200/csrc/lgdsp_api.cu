@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 #include "lgdsp_kernels.h"
 
@@ -54,6 +55,23 @@ struct lgdsp_handle {
     size_t in_cap = 0, rows_cap = 0, sweep_out_cap = 0;
     cudaStream_t s_copy = nullptr;
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    // pinned staging of the host paths (HostIO below): pageable caller memory goes through these double buffers
+    void* h_pin[2] = {nullptr, nullptr};
+    size_t pin_cap = 0;
+    void* h_out[2] = {nullptr, nullptr};
+    size_t out_cap = 0;
+    cudaEvent_t ev_pin[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    int copy_threads = 4;
+    int64_t host_chunk = 8192;     // events per chunk of the host paths
+    // encoded-waveform staging (decode_data on the device)
+    uint8_t* d_enc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][stream]
+    size_t enc_cap[2] = {0, 0};
+    long long* d_off[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    size_t off_cap = 0;
+    void* d_dec[2] = {nullptr, nullptr};                               // decoded waveforms of the current chunk
+    size_t dec_cap[2] = {0, 0};
+    int* d_dstat = nullptr;
+    size_t dstat_cap = 0;
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
@@ -62,7 +80,7 @@ struct lgdsp_handle {
     int icpc_path = 1;             // 0: fused icpc_kernel, 1: split pipeline
     int split_bps[3] = {0, 0, 0};
     int64_t split_batch = 0;       // events per batch (0: default)
-    int split_streams = 2;
+    int split_streams = 3;
     double* d_tt = nullptr;
     double* d_saux = nullptr;
     double* d_scz = nullptr;       // candidate records of the CUSP/ZAC kernels
@@ -137,6 +155,16 @@ int lgdsp_create(int device, void* stream, lgdsp_handle** out)
         ok = ok && cudaEventCreateWithFlags(&h->ev_ready[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
     }
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = ok && cudaEventCreateWithFlags(&h->ev_pin[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        h->copy_threads = hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1);
+        if (const char* env = getenv("LGDSP_COPY_THREADS")) h->copy_threads = atoi(env) > 0 ? atoi(env) : 1;
+        if (const char* env = getenv("LGDSP_HOST_CHUNK")) h->host_chunk = atoll(env) > 0 ? atoll(env) : 8192;
+    }
     ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_dniA, sizeof(double) * 2 * LGDSP_MAX_DNI * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_cusp_g, sizeof(double) * (LGDSP_MAX_FIR + 1)) == cudaSuccess;
@@ -194,7 +222,14 @@ void lgdsp_destroy(lgdsp_handle* h)
     for (int i = 0; i < 2; ++i) {
         if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]);
         if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
+        if (h->ev_pin[i]) cudaEventDestroy(h->ev_pin[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+        if (h->h_pin[i]) cudaFreeHost(h->h_pin[i]);
+        if (h->h_out[i]) cudaFreeHost(h->h_out[i]);
+        for (int k = 0; k < 2; ++k) { cudaFree(h->d_enc[i][k]); cudaFree(h->d_off[i][k]); }
+        cudaFree(h->d_dec[i]);
     }
+    cudaFree(h->d_dstat);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
@@ -495,7 +530,7 @@ static int icpc_dispatch(lgdsp_handle* h, const IcpcDev& D, const void* d_wf, in
         return LGDSP_OK;
     }
     const int S = h->split_streams;
-    const int64_t B = h->split_batch > 0 ? h->split_batch : (int64_t)h->sm_count * 6;
+    const int64_t B = h->split_batch > 0 ? h->split_batch : 4096;
     const int64_t need = B * S;
     if (need > h->split_cap) {
         CK(cudaStreamSynchronize(h->stream));
@@ -625,23 +660,285 @@ static int ensure_aux(lgdsp_handle* h, size_t bytes)
     return LGDSP_OK;
 }
 
-// host buffers in, host rows out: chunked, H2D of chunk k+1 overlaps the kernel of chunk k
+// ---------------------------------------------------------------------------------------------------
+// Host <-> device traffic of the chunked host paths.  Caller memory that is already page-locked (cudaHostAlloc /
+// cudaHostRegister / torch pin_memory) is copied directly; PAGEABLE caller memory (a Julia `flatview(wvfs.signal)`, a numpy
+// array) is first packed into the handle's pinned double buffers by a few threads, so that the H2D copy of chunk k+1 and the
+// D2H copy of chunk k-1 still run asynchronously beside the kernels of chunk k.  (A cudaMemcpyAsync straight from pageable
+// memory is a blocking staged copy: the overlap the pipeline depends on would be gone.)
+// ---------------------------------------------------------------------------------------------------
+static bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// dst[r*dpitch .. +width) = src[r*spitch .. +width), rows split over a few threads
+static void pack_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, int threads)
+{
+    const size_t total = width * rows;
+    if (threads > 1 && total < ((size_t)4 << 20)) threads = 1;
+    if (rows < (size_t)threads && !(dpitch == width && spitch == width)) threads = rows ? (int)rows : 1;
+    auto work = [=](int t) {
+        if (dpitch == width && spitch == width) {   // dense: split the bytes
+            const size_t a0 = total * t / threads, a1 = total * (t + 1) / threads;
+            memcpy(static_cast<char*>(dst) + a0, static_cast<const char*>(src) + a0, a1 - a0);
+        } else {
+            const size_t r0 = rows * t / threads, r1 = rows * (t + 1) / threads;
+            for (size_t r = r0; r < r1; ++r)
+                memcpy(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width);
+        }
+    };
+    if (threads <= 1) { work(0); return; }
+    std::vector<std::thread> th;
+    th.reserve(threads - 1);
+    for (int t = 1; t < threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+
+struct HostIO {
+    lgdsp_handle* h;
+    int b = 0;                 // double-buffer index of the current chunk
+    size_t in_used = 0, out_used = 0;
+    struct Pending { void* dst; const void* src; size_t bytes; };
+    std::vector<Pending> pending[2];   // pinned -> caller copies that wait for ev_out[b]
+    bool used_pin[2] = {false, false}, used_out[2] = {false, false};
+
+    explicit HostIO(lgdsp_handle* hh) : h(hh) {}
+
+    // capacity of the two pinned staging areas per chunk (grown on demand; growing synchronises)
+    int reserve(size_t in_bytes, size_t out_bytes)
+    {
+        if (in_bytes > h->pin_cap) {
+            CK(cudaStreamSynchronize(h->s_copy));
+            for (int i = 0; i < 2; ++i) { if (h->h_pin[i]) cudaFreeHost(h->h_pin[i]); h->h_pin[i] = nullptr; }
+            h->pin_cap = 0;
+            for (int i = 0; i < 2; ++i) CK(cudaHostAlloc(&h->h_pin[i], in_bytes, cudaHostAllocDefault));
+            h->pin_cap = in_bytes;
+        }
+        if (out_bytes > h->out_cap) {
+            CK(cudaStreamSynchronize(h->stream));
+            for (int i = 0; i < 2; ++i) { if (h->h_out[i]) cudaFreeHost(h->h_out[i]); h->h_out[i] = nullptr; }
+            h->out_cap = 0;
+            for (int i = 0; i < 2; ++i) CK(cudaHostAlloc(&h->h_out[i], out_bytes, cudaHostAllocDefault));
+            h->out_cap = out_bytes;
+        }
+        return LGDSP_OK;
+    }
+    int flush(int bb)
+    {
+        if (used_out[bb]) { CK(cudaEventSynchronize(h->ev_out[bb])); used_out[bb] = false; }
+        for (const Pending& q : pending[bb]) memcpy(q.dst, q.src, q.bytes);
+        pending[bb].clear();
+        return LGDSP_OK;
+    }
+    // chunk c starts: its staging buffers must be free again (the copies of chunk c-2 that used them are done)
+    int begin_chunk(int c)
+    {
+        b = c & 1;
+        in_used = out_used = 0;
+        if (used_pin[b]) { CK(cudaEventSynchronize(h->ev_pin[b])); used_pin[b] = false; }
+        return flush(b);
+    }
+    static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+    // rows of `width` bytes (source pitch `spitch`) -> dense device rows, on the copy stream
+    int h2d(void* d_dst, const void* src, size_t spitch, size_t width, size_t rows, bool src_pinned)
+    {
+        if (width == 0 || rows == 0) return LGDSP_OK;
+        if (src_pinned) {
+            if (spitch == width) CK(cudaMemcpyAsync(d_dst, src, width * rows, cudaMemcpyHostToDevice, h->s_copy));
+            else CK(cudaMemcpy2DAsync(d_dst, width, src, spitch, width, rows, cudaMemcpyHostToDevice, h->s_copy));
+            return LGDSP_OK;
+        }
+        const size_t bytes = width * rows;
+        if (in_used + bytes > h->pin_cap) return fail(h, LGDSP_ERR_CUDA, "internal: pinned input staging too small");
+        char* stage = static_cast<char*>(h->h_pin[b]) + in_used;
+        pack_rows(stage, width, src, spitch, width, rows, h->copy_threads);
+        in_used = up256(in_used + bytes);
+        CK(cudaMemcpyAsync(d_dst, stage, bytes, cudaMemcpyHostToDevice, h->s_copy));
+        used_pin[b] = true;
+        return LGDSP_OK;
+    }
+    // every H2D copy of the chunk is issued: the compute stream waits for them
+    int inputs_ready()
+    {
+        CK(cudaEventRecord(h->ev_ready[b], h->s_copy));
+        if (used_pin[b]) CK(cudaEventRecord(h->ev_pin[b], h->s_copy));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
+        return LGDSP_OK;
+    }
+    // device -> caller, in stream order behind the kernels of this chunk
+    int d2h(void* dst, const void* d_src, size_t bytes, bool dst_pinned)
+    {
+        if (bytes == 0) return LGDSP_OK;
+        if (dst_pinned) { CK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, h->stream)); return LGDSP_OK; }
+        if (out_used + bytes > h->out_cap) return fail(h, LGDSP_ERR_CUDA, "internal: pinned output staging too small");
+        char* stage = static_cast<char*>(h->h_out[b]) + out_used;
+        out_used = up256(out_used + bytes);
+        CK(cudaMemcpyAsync(stage, d_src, bytes, cudaMemcpyDeviceToHost, h->stream));
+        pending[b].push_back({dst, stage, bytes});
+        used_out[b] = true;
+        return LGDSP_OK;
+    }
+    int end_chunk()
+    {
+        if (used_out[b]) CK(cudaEventRecord(h->ev_out[b], h->stream));
+        return LGDSP_OK;
+    }
+    int finish()
+    {
+        CK(cudaStreamSynchronize(h->s_copy));
+        CK(cudaStreamSynchronize(h->stream));
+        used_pin[0] = used_pin[1] = false;
+        int rc = flush(0);
+        return rc ? rc : flush(1);
+    }
+};
+
+static int ensure_bytes(lgdsp_handle* h, void** p, size_t* cap, size_t bytes)
+{
+    if (bytes > *cap) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaStreamSynchronize(h->s_copy));
+        cudaFree(*p); *p = nullptr; *cap = 0;
+        CK(cudaMalloc(p, bytes));
+        *cap = bytes;
+    }
+    return LGDSP_OK;
+}
+
+// One encoded stream set of a chunk -> decoded device rows: upload of the byte range and of the offsets slice (copy stream),
+// decode kernel (compute stream, behind inputs_ready).  `slot` = 0 / 1: the two waveforms of dsp_icpc_compressed.
+struct EncodedInput {
+    int codec, sample_bytes, n_samples, shift;
+    const uint8_t* enc;
+    const int64_t* offsets;
+    bool enc_pinned, off_pinned;
+};
+static int encoded_reserve(lgdsp_handle* h, const EncodedInput& in, int slot, int64_t chunk, int64_t n_events)
+{
+    size_t max_bytes = 0;
+    for (int64_t e0 = 0; e0 < n_events; e0 += chunk) {
+        const int64_t e1 = e0 + chunk < n_events ? e0 + chunk : n_events;
+        const size_t nb = (size_t)(in.offsets[e1] - in.offsets[e0]);
+        max_bytes = nb > max_bytes ? nb : max_bytes;
+    }
+    for (int bb = 0; bb < 2; ++bb) {
+        size_t cap = h->enc_cap[slot];
+        int rc = ensure_bytes(h, reinterpret_cast<void**>(&h->d_enc[bb][slot]), &cap, max_bytes + 16);
+        if (rc) return rc;
+        if (bb == 1) h->enc_cap[slot] = cap;
+    }
+    if ((size_t)(chunk + 1) * sizeof(long long) > h->off_cap) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaStreamSynchronize(h->s_copy));
+        for (int bb = 0; bb < 2; ++bb)
+            for (int k = 0; k < 2; ++k) {
+                cudaFree(h->d_off[bb][k]); h->d_off[bb][k] = nullptr;
+                CK(cudaMalloc(&h->d_off[bb][k], (size_t)(chunk + 1) * sizeof(long long)));
+            }
+        h->off_cap = (size_t)(chunk + 1) * sizeof(long long);
+    }
+    int rc = ensure_bytes(h, &h->d_dec[slot], &h->dec_cap[slot], (size_t)chunk * in.n_samples * in.sample_bytes);
+    if (rc) return rc;
+    return ensure_bytes(h, reinterpret_cast<void**>(&h->d_dstat), &h->dstat_cap, 2 * sizeof(int));
+}
+// d_dstat = {number of malformed streams, smallest event index among them} of the running call
+static int decode_err_reset(lgdsp_handle* h)
+{
+    const int init[2] = {0, 0x7fffffff};
+    CK(cudaMemcpyAsync(h->d_dstat, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LGDSP_OK;
+}
+static int decode_err_check(lgdsp_handle* h)
+{
+    int st[2] = {0, 0};
+    CK(cudaMemcpy(st, h->d_dstat, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st[0]) return fail(h, LGDSP_ERR_INVALID_ARG, "%d malformed encoded waveform(s), first at event %d", st[0], st[1]);
+    return LGDSP_OK;
+}
+static size_t encoded_stage_bytes(const EncodedInput& in, int64_t chunk, int64_t n_events)
+{
+    size_t m = 0;
+    for (int64_t e0 = 0; e0 < n_events; e0 += chunk) {
+        const int64_t e1 = e0 + chunk < n_events ? e0 + chunk : n_events;
+        const size_t nb = (size_t)(in.offsets[e1] - in.offsets[e0]) + (size_t)(e1 - e0 + 1) * sizeof(int64_t) + 512;
+        m = nb > m ? nb : m;
+    }
+    return m;
+}
+static int encoded_upload(lgdsp_handle* h, HostIO& io, const EncodedInput& in, int slot, int64_t e0, int64_t ne)
+{
+    const size_t nb = (size_t)(in.offsets[e0 + ne] - in.offsets[e0]);
+    int rc = io.h2d(h->d_enc[io.b][slot], in.enc + in.offsets[e0], nb, nb, nb ? 1 : 0, in.enc_pinned);
+    if (rc) return rc;
+    return io.h2d(h->d_off[io.b][slot], in.offsets + e0, (size_t)(ne + 1) * sizeof(int64_t), (size_t)(ne + 1) * sizeof(int64_t), 1,
+                  in.off_pinned);
+}
+static int encoded_decode(lgdsp_handle* h, HostIO& io, const EncodedInput& in, int slot, int64_t e0, int64_t ne)
+{
+    cudaError_t e = codec_decode_launch(in.codec, h->d_enc[io.b][slot], h->d_off[io.b][slot], (long long)in.offsets[e0], ne, in.n_samples,
+                                        in.shift, h->d_dec[slot], in.sample_bytes, in.n_samples, nullptr, h->d_dstat, (int)e0, h->sm_count,
+                                        h->stream);
+    if (e != cudaSuccess) return fail(h, LGDSP_ERR_CUDA, "decode kernel: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    return LGDSP_OK;
+}
+static int check_encoded(lgdsp_handle* h, int codec, const void* enc, const int64_t* offsets, int64_t n_events, int sample_bytes)
+{
+    if (codec != LGDSP_CODEC_RADWARE && codec != LGDSP_CODEC_ULEB128ZZD) return fail(h, LGDSP_ERR_UNSUPPORTED, "unknown codec %d", codec);
+    if (codec == LGDSP_CODEC_RADWARE && sample_bytes != 2) return fail(h, LGDSP_ERR_UNSUPPORTED, "RadwareSigcompress holds 16-bit samples");
+    if (sample_bytes != 2 && sample_bytes != 4) return fail(h, LGDSP_ERR_UNSUPPORTED, "sample_bytes = %d", sample_bytes);
+    if (n_events > 0 && (!enc || !offsets)) return fail(h, LGDSP_ERR_INVALID_ARG, "encoded data / offsets pointer is NULL");
+    for (int64_t e = 0; e < n_events; ++e)
+        if (offsets[e + 1] < offsets[e]) return fail(h, LGDSP_ERR_INVALID_ARG, "offsets must be non-decreasing (event %lld)", (long long)e);
+    return LGDSP_OK;
+}
+// host buffers in, host rows out: chunked, H2D of chunk k+1 overlaps the kernels of chunk k.  `encin` != NULL: the input
+// is an encoded waveform set (decode_data on the device), else raw samples `wf`.
 static int icpc_run_host_impl(lgdsp_handle* h, const lgdsp_icpc_params* p, const void* wf, int sample_bytes,
-                              const double* baseline, int64_t n_events, int64_t ld_samples, double* out_rows)
+                              const double* baseline, int64_t n_events, int64_t ld_samples, double* out_rows,
+                              const EncodedInput* encin = nullptr)
 {
     if (!h) return LGDSP_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     if (p) { int rc = icpc_prepare(h, p); if (rc) return rc; }
     if (!h->have_icpc) return fail(h, LGDSP_ERR_INVALID_ARG, "no parameters set");
     const int n = h->icpc.n;
-    int rc = check_wf(h, wf, n_events, ld_samples, n, false, sample_bytes);
+    int rc;
+    if (encin) {
+        if (n_events < 0) return fail(h, LGDSP_ERR_INVALID_ARG, "n_events < 0");
+        if (sample_bytes == 4 && n > LGDSP_MAX_SAMPLES / 2) return fail(h, LGDSP_ERR_UNSUPPORTED, "32-bit samples: n_samples = %d > %d", n, LGDSP_MAX_SAMPLES / 2);
+        rc = check_encoded(h, encin->codec, encin->enc, encin->offsets, n_events, sample_bytes);
+    } else {
+        rc = check_wf(h, wf, n_events, ld_samples, n, false, sample_bytes);
+    }
     if (rc) return rc;
     if (n_events == 0) return LGDSP_OK;
     if (!out_rows) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
     const size_t sb = (size_t)sample_bytes;
-    const int64_t chunk = n_events < 2048 ? n_events : 2048;
-    rc = ensure_staging(h, (size_t)chunk * n * sb, (size_t)2 * chunk * LGDSP_NCOL * sizeof(double));
+    const int64_t chunk = n_events < h->host_chunk ? n_events : h->host_chunk;
+    const bool in_pinned = encin ? false : is_pinned(wf);
+    const bool out_pinned = is_pinned(out_rows);
+    const bool bl_pinned = baseline ? is_pinned(baseline) : true;
+    HostIO io(h);
+    size_t stage_in = 0;
+    if (encin) stage_in = (encin->enc_pinned && encin->off_pinned) ? 0 : encoded_stage_bytes(*encin, chunk, n_events);
+    else if (!in_pinned) stage_in = (size_t)chunk * n * sb + 256;
+    if (baseline && !bl_pinned) stage_in += (size_t)chunk * sizeof(double) + 256;
+    rc = io.reserve(stage_in, out_pinned ? 0 : (size_t)chunk * LGDSP_NCOL * sizeof(double) + 256);
     if (rc) return rc;
+    rc = ensure_staging(h, encin ? 16 : (size_t)chunk * n * sb, (size_t)2 * chunk * LGDSP_NCOL * sizeof(double));
+    if (rc) return rc;
+    if (encin) {
+        rc = encoded_reserve(h, *encin, 0, chunk, n_events);
+        if (rc) return rc;
+        rc = decode_err_reset(h);
+        if (rc) return rc;
+    }
     if (baseline) {
         rc = ensure_aux(h, (size_t)2 * chunk * sizeof(double));
         if (rc) return rc;
@@ -649,31 +946,40 @@ static int icpc_run_host_impl(lgdsp_handle* h, const lgdsp_icpc_params* p, const
     const unsigned char* src = static_cast<const unsigned char*>(wf);
     int c = 0;
     for (int64_t e0 = 0; e0 < n_events; e0 += chunk, ++c) {
-        const int b = c & 1;
         const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
-        if (c >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
-        if (ld_samples == n)   // dense rows: one linear copy
-            CK(cudaMemcpyAsync(h->d_in[b], src + (size_t)e0 * n * sb, (size_t)ne * n * sb, cudaMemcpyHostToDevice, h->s_copy));
-        else
-            CK(cudaMemcpy2DAsync(h->d_in[b], (size_t)n * sb, src + (size_t)e0 * ld_samples * sb, (size_t)ld_samples * sb, (size_t)n * sb,
-                                 (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
+        rc = io.begin_chunk(c);
+        if (rc) return rc;
+        const int b = io.b;
+        if (c >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));   // the device buffers of chunk c-2 are consumed
+        if (encin) rc = encoded_upload(h, io, *encin, 0, e0, ne);
+        else rc = io.h2d(h->d_in[b], src + (size_t)e0 * ld_samples * sb, (size_t)ld_samples * sb, (size_t)n * sb, (size_t)ne, in_pinned);
+        if (rc) return rc;
         double* d_bl = nullptr;
         if (baseline) {
             d_bl = h->d_aux + (size_t)b * chunk;
-            CK(cudaMemcpyAsync(d_bl, baseline + e0, (size_t)ne * sizeof(double), cudaMemcpyHostToDevice, h->s_copy));
+            rc = io.h2d(d_bl, baseline + e0, (size_t)ne * sizeof(double), (size_t)ne * sizeof(double), 1, bl_pinned);
+            if (rc) return rc;
         }
-        CK(cudaEventRecord(h->ev_ready[b], h->s_copy));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
+        rc = io.inputs_ready();
+        if (rc) return rc;
+        const void* d_wf = h->d_in[b];
+        if (encin) {
+            rc = encoded_decode(h, io, *encin, 0, e0, ne);
+            if (rc) return rc;
+            d_wf = h->d_dec[0];
+        }
         double* d_rows = h->d_rows + (size_t)b * chunk * LGDSP_NCOL;
-        rc = icpc_dispatch(h, h->icpc, h->d_in[b], sample_bytes, ne, n, d_bl, 1, 1.0, d_rows);
+        rc = icpc_dispatch(h, h->icpc, d_wf, sample_bytes, ne, n, d_bl, 1, 1.0, d_rows);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev_free[b], h->stream));
-        CK(cudaMemcpyAsync(out_rows + e0 * LGDSP_NCOL, d_rows, (size_t)ne * LGDSP_NCOL * sizeof(double),
-                           cudaMemcpyDeviceToHost, h->stream));
+        rc = io.d2h(out_rows + e0 * LGDSP_NCOL, d_rows, (size_t)ne * LGDSP_NCOL * sizeof(double), out_pinned);
+        if (rc) return rc;
+        rc = io.end_chunk();
+        if (rc) return rc;
     }
-    CK(cudaStreamSynchronize(h->s_copy));
-    CK(cudaStreamSynchronize(h->stream));
-    return LGDSP_OK;
+    rc = io.finish();
+    if (rc) return rc;
+    return encin ? decode_err_check(h) : LGDSP_OK;
 }
 
 int lgdsp_icpc_run(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* wf, int64_t n_events,
@@ -686,6 +992,110 @@ int lgdsp_icpc_run_ext(lgdsp_handle* h, const lgdsp_icpc_params* p, const void* 
                        const double* baseline, int64_t n_events, int64_t ld_samples, double* out_rows)
 {
     return icpc_run_host_impl(h, p, wf, sample_bytes, baseline, n_events, ld_samples, out_rows);
+}
+
+// ---- decode_data (LegendDataTypes.jl codecs; /root/reference/src/dsp_icpc.jl:313-314) ----
+int64_t lgdsp_codec_max_encoded_bytes(int32_t codec, int32_t n_samples, int32_t sample_bytes)
+{
+    if ((codec != LGDSP_CODEC_RADWARE && codec != LGDSP_CODEC_ULEB128ZZD) || n_samples < 0) return -1;
+    return codec_max_encoded_bytes(codec, n_samples, sample_bytes);
+}
+
+int lgdsp_codec_encode_host(int32_t codec, const void* wf, int32_t sample_bytes, int64_t n_events, int32_t n_samples, int64_t ld_samples,
+                            int32_t shift, uint8_t* enc, int64_t enc_capacity, int64_t* offsets)
+{
+    if ((codec != LGDSP_CODEC_RADWARE && codec != LGDSP_CODEC_ULEB128ZZD) || !offsets || n_events < 0 || n_samples < 0 ||
+        (n_events > 0 && (!wf || !enc)) || ld_samples < n_samples || (sample_bytes != 2 && sample_bytes != 4) ||
+        (codec == LGDSP_CODEC_RADWARE && (sample_bytes != 2 || n_samples > 65535)))
+        return LGDSP_ERR_INVALID_ARG;
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset type");
+    const int rc = codec_encode_host(codec, wf, sample_bytes, n_events, n_samples, ld_samples, shift, enc, enc_capacity,
+                                     reinterpret_cast<long long*>(offsets));
+    return rc == 0 ? LGDSP_OK : (rc == -1 ? LGDSP_ERR_OOM : LGDSP_ERR_INVALID_ARG);
+}
+
+int lgdsp_decode_data_device(lgdsp_handle* h, int32_t codec, const uint8_t* d_enc, const int64_t* d_offsets, int64_t n_events,
+                             int32_t n_samples, int32_t shift, void* d_wf, int32_t sample_bytes, int64_t ld_samples, int32_t* d_status)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (codec != LGDSP_CODEC_RADWARE && codec != LGDSP_CODEC_ULEB128ZZD) return fail(h, LGDSP_ERR_UNSUPPORTED, "unknown codec %d", codec);
+    if ((codec == LGDSP_CODEC_RADWARE && sample_bytes != 2) || (sample_bytes != 2 && sample_bytes != 4))
+        return fail(h, LGDSP_ERR_UNSUPPORTED, "codec %d with %d-byte samples", codec, sample_bytes);
+    if (n_events < 0 || n_samples < 1 || n_samples > LGDSP_MAX_SAMPLES || ld_samples < n_samples) return fail(h, LGDSP_ERR_INVALID_ARG, "bad sizes");
+    if (n_events == 0) return LGDSP_OK;
+    if (!d_enc || !d_offsets || !d_wf) return fail(h, LGDSP_ERR_INVALID_ARG, "NULL pointer");
+    CK(cudaEventRecord(h->ev0, h->stream));
+    cudaError_t e = codec_decode_launch(codec, d_enc, reinterpret_cast<const long long*>(d_offsets), 0, n_events, n_samples, shift, d_wf,
+                                        sample_bytes, ld_samples, d_status, nullptr, 0, h->sm_count, h->stream);
+    if (e != cudaSuccess) return fail(h, LGDSP_ERR_CUDA, "decode kernel: %s", cudaGetErrorString(e));
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->launches += 1;
+    return LGDSP_OK;
+}
+
+int lgdsp_decode_data(lgdsp_handle* h, int32_t codec, const uint8_t* enc, const int64_t* offsets, int64_t n_events, int32_t n_samples,
+                      int32_t shift, void* wf, int32_t sample_bytes, int64_t ld_samples)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = check_encoded(h, codec, enc, offsets, n_events, sample_bytes);
+    if (rc) return rc;
+    if (n_events < 0 || n_samples < 1 || n_samples > LGDSP_MAX_SAMPLES || ld_samples < n_samples) return fail(h, LGDSP_ERR_INVALID_ARG, "bad sizes");
+    if (n_events == 0) return LGDSP_OK;
+    if (!wf) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
+    EncodedInput in{codec, sample_bytes, n_samples, shift, enc, offsets, is_pinned(enc), is_pinned(offsets)};
+    const int64_t chunk = n_events < 8192 ? n_events : 8192;
+    const bool out_pinned = is_pinned(wf);
+    const size_t row = (size_t)n_samples * sample_bytes;
+    HostIO io(h);
+    rc = io.reserve((in.enc_pinned && in.off_pinned) ? 0 : encoded_stage_bytes(in, chunk, n_events), out_pinned ? 0 : (size_t)chunk * row + 256);
+    if (rc) return rc;
+    rc = encoded_reserve(h, in, 0, chunk, n_events);
+    if (rc) return rc;
+    rc = decode_err_reset(h);
+    if (rc) return rc;
+    int c = 0;
+    for (int64_t e0 = 0; e0 < n_events; e0 += chunk, ++c) {
+        const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
+        rc = io.begin_chunk(c);
+        if (rc) return rc;
+        if (c >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_free[io.b], 0));
+        rc = encoded_upload(h, io, in, 0, e0, ne);
+        if (rc) return rc;
+        rc = io.inputs_ready();
+        if (rc) return rc;
+        rc = encoded_decode(h, io, in, 0, e0, ne);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev_free[io.b], h->stream));
+        // (d_dec is single-buffered: the D2H below is in stream order in front of the next chunk's decode kernel)
+        if (ld_samples == n_samples) {
+            rc = io.d2h(static_cast<char*>(wf) + (size_t)e0 * row, h->d_dec[0], (size_t)ne * row, out_pinned);
+        } else {
+            for (int64_t e = 0; e < ne && !rc; ++e)
+                rc = io.d2h(static_cast<char*>(wf) + (size_t)(e0 + e) * ld_samples * sample_bytes, static_cast<char*>(h->d_dec[0]) + (size_t)e * row,
+                            row, out_pinned);
+        }
+        if (rc) return rc;
+        rc = io.end_chunk();
+        if (rc) return rc;
+    }
+    rc = io.finish();
+    if (rc) return rc;
+    return decode_err_check(h);
+}
+
+// dsp_icpc on ENCODED waveforms: the host link carries the codec's bytes, decode_data runs on the device in front of the chain
+int lgdsp_icpc_run_encoded(lgdsp_handle* h, const lgdsp_icpc_params* p, int32_t codec, const uint8_t* enc, const int64_t* offsets,
+                           int32_t shift, int32_t sample_bytes, const double* baseline, int64_t n_events, double* out_rows)
+{
+    if (!h) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (p) { int rc = icpc_prepare(h, p); if (rc) return rc; }
+    if (!h->have_icpc) return fail(h, LGDSP_ERR_INVALID_ARG, "no parameters set");
+    EncodedInput in{codec, sample_bytes, h->icpc.n, shift, enc, offsets, enc ? is_pinned(enc) : false, offsets ? is_pinned(offsets) : false};
+    return icpc_run_host_impl(h, nullptr, nullptr, sample_bytes, baseline, n_events, h->icpc.n, out_rows, &in);
 }
 
 // signalstats on n_windows windows of every waveform (optionally shifted by -shift[e]): out double[n_events][n_windows][5]

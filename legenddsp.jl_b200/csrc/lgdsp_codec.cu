@@ -208,10 +208,12 @@ __device__ __forceinline__ int load_stream(const uint8_t* __restrict__ enc, long
     return skew;
 }
 
-// out[e][i] = sample i of event e (uint16); status[e] = 0 ok, 1 malformed stream (the waveform is zero-filled)
+// out[e][i] = sample i of event e (uint16); status[e] = 0 ok, 1 malformed stream (the waveform is zero-filled); err[0] counts
+// the malformed streams, err[1] keeps the smallest err_base + e among them (both optional)
 __global__ void __launch_bounds__(DEC_NT)
 radware_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restrict__ off, long long off_base, long long n_events,
-                      int n_samples, int shift, uint16_t* __restrict__ out, long long ld, int* __restrict__ status, int cap_bytes)
+                      int n_samples, int shift, uint16_t* __restrict__ out, long long ld, int* __restrict__ status, int* __restrict__ err,
+                      int err_base, int cap_bytes)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     unsigned char* bytes = dsm;                                                   // cap_bytes + 8
@@ -312,7 +314,10 @@ radware_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restri
                 }
             }
         }
-        if (tid == 0 && status) status[e] = s_err;
+        if (tid == 0) {
+            if (status) status[e] = s_err;
+            if (s_err && err) { atomicAdd(&err[0], 1); atomicMin(&err[1], err_base + (int)e); }
+        }
         __syncthreads();   // the byte buffer and the section table are reused by the next event
     }
 }
@@ -321,7 +326,8 @@ radware_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restri
 template <typename OUT>
 __global__ void __launch_bounds__(DEC_NT)
 uleb_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restrict__ off, long long off_base, long long n_events,
-                   int n_samples, OUT* __restrict__ out, long long ld, int* __restrict__ status, int cap_bytes)
+                   int n_samples, OUT* __restrict__ out, long long ld, int* __restrict__ status, int* __restrict__ err, int err_base,
+                   int cap_bytes)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     unsigned char* bytes = dsm;                                                             // cap_bytes + 16
@@ -396,7 +402,10 @@ uleb_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restrict_
                 o[i] = (OUT)acc;
             }
         }
-        if (tid == 0 && status) status[e] = s_err;
+        if (tid == 0) {
+            if (status) status[e] = s_err;
+            if (s_err && err) { atomicAdd(&err[0], 1); atomicMin(&err[1], err_base + (int)e); }
+        }
         __syncthreads();
     }
 }
@@ -411,8 +420,8 @@ static int dec_smem(int codec, int n_samples, int sample_bytes, int* cap_bytes)
 
 // d_off[e] - off_base = first byte of event e inside d_enc (off_base = d_off[0] when only a slice of the bytes was uploaded)
 cudaError_t codec_decode_launch(int codec, const uint8_t* d_enc, const long long* d_off, long long off_base, long long n_events,
-                                int n_samples, int shift, void* d_out, int sample_bytes, long long ld, int* d_status, int sm_count,
-                                cudaStream_t stream)
+                                int n_samples, int shift, void* d_out, int sample_bytes, long long ld, int* d_status, int* d_err,
+                                int err_base, int sm_count, cudaStream_t stream)
 {
     if (n_events <= 0) return cudaSuccess;
     int cap = 0;
@@ -423,15 +432,15 @@ cudaError_t codec_decode_launch(int codec, const uint8_t* d_enc, const long long
     if (codec == LGDSP_CODEC_RADWARE) {
         if ((err = cudaFuncSetAttribute(radware_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return err;
         radware_decode_kernel<<<grid, DEC_NT, smem, stream>>>(d_enc, d_off, off_base, n_events, n_samples, shift, static_cast<uint16_t*>(d_out), ld,
-                                                               d_status, cap);
+                                                               d_status, d_err, err_base, cap);
     } else if (sample_bytes == 4) {
         if ((err = cudaFuncSetAttribute(uleb_decode_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return err;
         uleb_decode_kernel<uint32_t><<<grid, DEC_NT, smem, stream>>>(d_enc, d_off, off_base, n_events, n_samples, static_cast<uint32_t*>(d_out), ld,
-                                                                     d_status, cap);
+                                                                     d_status, d_err, err_base, cap);
     } else {
         if ((err = cudaFuncSetAttribute(uleb_decode_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return err;
         uleb_decode_kernel<uint16_t><<<grid, DEC_NT, smem, stream>>>(d_enc, d_off, off_base, n_events, n_samples, static_cast<uint16_t*>(d_out), ld,
-                                                                     d_status, cap);
+                                                                     d_status, d_err, err_base, cap);
     }
     return cudaGetLastError();
 }

@@ -24,8 +24,9 @@ _dp = C.POINTER(C.c_double)
 
 def build(force=False):
     src = os.path.join(_HERE, "lgdsp_oracle.c")
+    src2 = os.path.join(_HERE, "lgdsp_codec_oracle.c")
     hdr = os.path.join(_HERE, "..", "include", "lgdsp_b200.h")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(src2), os.path.getmtime(hdr)):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return _SO
 
@@ -377,3 +378,52 @@ def dsp_sg_optimization_compressed(S_pre, S_wdw, wf_pre, wf_wdw, energy_variant,
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+# ---- waveform codecs of decode_data (lgdsp_codec_oracle.c) ----
+def radware_encode(x_u16, shift=-32768, big_endian=True):
+    """one waveform -> bytes (radware-sigcompress v1.0 restatement)"""
+    L = lib()
+    L.orc_radware_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]
+    L.orc_radware_encode.restype = C.c_int64
+    x = np.ascontiguousarray(x_u16, dtype=np.uint16)
+    out = np.empty(2 * x.size + 8 * (x.size // 48 + 2) + 16, dtype=np.uint8)
+    nb = L.orc_radware_encode(x.ctypes.data, x.size, int(shift), 1 if big_endian else 0, out.ctypes.data, out.size)
+    if nb < 0:
+        raise ValueError(f"orc_radware_encode: {nb}")
+    return out[:nb].copy()
+
+
+def radware_decode(b_u8, n_max=65535, shift=-32768, big_endian=True):
+    L = lib()
+    L.orc_radware_decode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    b = np.ascontiguousarray(b_u8, dtype=np.uint8)
+    out = np.zeros(n_max, dtype=np.uint16)
+    n = L.orc_radware_decode(b.ctypes.data, b.size, int(shift), 1 if big_endian else 0, out.ctypes.data, n_max)
+    if n < 0:
+        raise ValueError("orc_radware_decode: malformed stream")
+    return out[:n].copy()
+
+
+def uleb128zzd_encode(x):
+    L = lib()
+    L.orc_uleb128zzd_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]
+    L.orc_uleb128zzd_encode.restype = C.c_int64
+    x = np.ascontiguousarray(x)
+    assert x.dtype in (np.uint16, np.uint32)
+    out = np.empty(10 * x.size + 16, dtype=np.uint8)
+    nb = L.orc_uleb128zzd_encode(x.ctypes.data, x.dtype.itemsize, x.size, out.ctypes.data, out.size)
+    if nb < 0:
+        raise ValueError("orc_uleb128zzd_encode")
+    return out[:nb].copy()
+
+
+def uleb128zzd_decode(b_u8, dtype=np.uint32, n_max=65536):
+    L = lib()
+    L.orc_uleb128zzd_decode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int]
+    b = np.ascontiguousarray(b_u8, dtype=np.uint8)
+    out = np.zeros(n_max, dtype=dtype)
+    n = L.orc_uleb128zzd_decode(b.ctypes.data, b.size, np.dtype(dtype).itemsize, out.ctypes.data, n_max)
+    if n < 0:
+        raise ValueError("orc_uleb128zzd_decode: malformed stream")
+    return out[:n].copy()
