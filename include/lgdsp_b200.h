@@ -102,6 +102,11 @@ enum lgdsp_col {
 #define LGDSP_GROUP_INTRACE 0x40u /* inTrace_intersect, inTrace_n, t50_current (masks on the sg[0] trace) */
 #define LGDSP_GROUP_ALL    0x7Fu
 #define LGDSP_GROUP_PZTRAP (LGDSP_GROUP_BASE | LGDSP_GROUP_TIMING | LGDSP_GROUP_TRAPS)
+/* modifier of LGDSP_GROUP_PZTRAP (split pipeline only): compute nothing but {blmean, t0, t50, e_trap, e_10410} -- no tail
+ * statistics, no t10/t80/t90/t99, no e_535/e_313/inverted traces, no trapezoid maxima; every other column is 0 or unspecified
+ * (BASELINE.json configs[1]: "pole-zero + trapezoidal energy/t0 only") */
+#define LGDSP_GROUP_LEAN   0x80u
+#define LGDSP_GROUP_PZTRAP_LEAN (LGDSP_GROUP_PZTRAP | LGDSP_GROUP_LEAN)
 
 /* TrapezoidalChargeFilter(avgtime, gaptime, avgtime2) in samples [RDDSP]:
  * out[j] = mean(y[j+navg+ngap .. j+navg+ngap+navg2-1]) - mean(y[j .. j+navg-1]), j = 0 .. n-L, L = navg+ngap+navg2;
@@ -372,6 +377,15 @@ int lgdsp_decode_data(lgdsp_handle* h, int32_t codec, const uint8_t* enc, const 
  * of the chain (n_samples from the parameters; baseline as lgdsp_icpc_run_ext, may be NULL) */
 int lgdsp_icpc_run_encoded(lgdsp_handle* h, const lgdsp_icpc_params* p, int32_t codec, const uint8_t* enc, const int64_t* offsets,
                            int32_t shift, int32_t sample_bytes, const double* baseline, int64_t n_events, double* out_rows);
+
+/* dsp_icpc_compressed with both `decode_data` calls of /root/reference/src/dsp_icpc.jl:313-314 on the device: the presummed
+ * and the windowed waveforms arrive as encoded streams in host memory (in LEGEND data: ULEB128ZZD for the 32-bit presummed
+ * samples, RadwareSigcompress(-32768) for the windowed UInt16 samples); everything else as lgdsp_icpc_compressed_run */
+int lgdsp_icpc_compressed_run_encoded(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, const lgdsp_icpc_params* p_wdw,
+                                      int32_t pre_codec, const uint8_t* enc_pre, const int64_t* off_pre, int32_t pre_shift,
+                                      int32_t pre_sample_bytes, int32_t wdw_codec, const uint8_t* enc_wdw, const int64_t* off_wdw,
+                                      int32_t wdw_shift, int32_t wdw_sample_bytes, double presum_rate, const int32_t* aux_windows,
+                                      int64_t n_events, double* rows_pre, double* rows_wdw, double* stats);
 
 /* dsp_icpc_compressed building block (/root/reference/src/dsp_icpc.jl:293-499): the same chain on waveforms of
  * 16-bit (sample_bytes = 2) or 32-bit unsigned samples (sample_bytes = 4: presummed traces, n_samples <=

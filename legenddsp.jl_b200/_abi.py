@@ -28,6 +28,8 @@ GROUP_CURRENT = 0x20
 GROUP_INTRACE = 0x40
 GROUP_ALL = 0x7F
 GROUP_PZTRAP = GROUP_BASE | GROUP_TIMING | GROUP_TRAPS
+GROUP_LEAN = 0x80
+GROUP_PZTRAP_LEAN = GROUP_PZTRAP | GROUP_LEAN
 
 # computed columns of dsp_icpc in the order of /root/reference/src/dsp_icpc.jl:210-229
 COLUMNS = (

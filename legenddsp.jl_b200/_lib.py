@@ -57,6 +57,8 @@ def load_library():
     L.lgdsp_decode_data_device.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp, i32, i64, vp]
     L.lgdsp_decode_data.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp, i32, i64]
     L.lgdsp_icpc_run_encoded.argtypes = [vp, C.POINTER(_abi.IcpcParams), i32, vp, vp, i32, i32, vp, i64, vp]
+    L.lgdsp_icpc_compressed_run_encoded.argtypes = [vp, C.POINTER(_abi.IcpcParams), C.POINTER(_abi.IcpcParams), i32, vp, vp, i32, i32,
+                                                    i32, vp, vp, i32, i32, C.c_double, vp, i64, vp, vp, vp]
     L.lgdsp_window_stats_run.argtypes = [vp, vp, i32, i64, i32, i64, C.c_double, C.c_double, vp, vp, i32, vp]
     L.lgdsp_window_stats_run_device.argtypes = [vp, vp, i32, i64, i32, i64, C.c_double, C.c_double, vp, vp, i32, vp]
     _comp = [vp, C.POINTER(_abi.IcpcParams), C.POINTER(_abi.IcpcParams), vp, i32, i64, vp, i32, i64, C.c_double, vp, i64,
@@ -93,7 +95,7 @@ EXPORTED_SYMBOLS = (
     "lgdsp_version", "lgdsp_last_error", "lgdsp_create", "lgdsp_destroy", "lgdsp_launch_count", "lgdsp_synchronize",
     "lgdsp_lsq_fit_matrix", "lgdsp_sg_coeffs", "lgdsp_cusp_coeffs", "lgdsp_zac_coeffs",
     "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params", "lgdsp_icpc_set_path", "lgdsp_icpc_run_ext", "lgdsp_icpc_run_ext_device",
-    "lgdsp_codec_max_encoded_bytes", "lgdsp_codec_encode_host", "lgdsp_decode_data", "lgdsp_decode_data_device", "lgdsp_icpc_run_encoded",
+    "lgdsp_codec_max_encoded_bytes", "lgdsp_codec_encode_host", "lgdsp_decode_data", "lgdsp_decode_data_device", "lgdsp_icpc_run_encoded", "lgdsp_icpc_compressed_run_encoded",
     "lgdsp_window_stats_run", "lgdsp_window_stats_run_device", "lgdsp_sipm_run", "lgdsp_sipm_run_device",
     "lgdsp_sipm_list_pointers_device", "lgdsp_sipm_list_gather_device", "lgdsp_thresholdstats", "lgdsp_intersect_maximum", "lgdsp_multi_intersect_run", "lgdsp_multi_intersect_run_device", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
     "lgdsp_trap_sweep_run", "lgdsp_trap_sweep_run_device", "lgdsp_sweep_run", "lgdsp_sweep_run_device",
@@ -206,6 +208,19 @@ class Handle:
                                                      C.c_void_p(enc_ptr), C.c_void_p(offsets_ptr), int(shift), int(sample_bytes),
                                                      C.c_void_p(baseline_ptr) if baseline_ptr else None, int(n_events),
                                                      C.c_void_p(out_ptr)))
+
+    def icpc_compressed_run_encoded_host(self, p_pre, p_wdw, enc_pre, enc_wdw, presum_rate, aux_windows, rows_pre_ptr, rows_wdw_ptr,
+                                         stats_ptr):
+        """dsp_icpc_compressed on two codec.EncodedWaveforms sets in host memory (decode_data on the device)"""
+        import numpy as np
+        w = (C.c_int32 * 8)(*[int(v) for ab in aux_windows for v in ab])
+        keep = [np.ascontiguousarray(x) for x in (enc_pre.data, enc_pre.offsets, enc_wdw.data, enc_wdw.offsets)]
+        self._check(self._lib.lgdsp_icpc_compressed_run_encoded(
+            self._h, C.byref(p_pre) if p_pre is not None else None, C.byref(p_wdw) if p_wdw is not None else None,
+            int(enc_pre.codec), C.c_void_p(keep[0].ctypes.data), C.c_void_p(keep[1].ctypes.data), int(enc_pre.shift),
+            int(enc_pre.sample_bytes), int(enc_wdw.codec), C.c_void_p(keep[2].ctypes.data), C.c_void_p(keep[3].ctypes.data),
+            int(enc_wdw.shift), int(enc_wdw.sample_bytes), float(presum_rate), w, len(enc_pre), C.c_void_p(rows_pre_ptr),
+            C.c_void_p(rows_wdw_ptr), C.c_void_p(stats_ptr)))
 
     def window_stats_host(self, wf_ptr, sample_bytes, n_events, n_samples, ld, t_first_ns, dt_ns, shift_ptr, windows, out_ptr):
         """signalstats on `windows` ([(from, until), ...] 0-based inclusive) of every waveform; out double[n][nw][5]"""

@@ -1227,27 +1227,34 @@ int lgdsp_icpc_compressed_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p
     return LGDSP_OK;
 }
 
-int lgdsp_icpc_compressed_run(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, const lgdsp_icpc_params* p_wdw, const void* wf_pre,
-                              int32_t pre_sample_bytes, int64_t ld_pre, const void* wf_wdw, int32_t wdw_sample_bytes,
-                              int64_t ld_wdw, double presum_rate, const int32_t* aux_windows, int64_t n_events, double* rows_pre,
-                              double* rows_wdw, double* stats)
+// host buffers: raw samples (wf_* != NULL) or encoded waveform sets (enc_* != NULL) per waveform kind
+static int compressed_run_host_impl(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, const lgdsp_icpc_params* p_wdw, const void* wf_pre,
+                                    int pre_sample_bytes, int64_t ld_pre, const void* wf_wdw, int wdw_sample_bytes, int64_t ld_wdw,
+                                    const EncodedInput* enc_pre, const EncodedInput* enc_wdw, double presum_rate,
+                                    const int32_t* aux_windows, int64_t n_events, double* rows_pre, double* rows_wdw, double* stats)
 {
     if (!h) return LGDSP_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     int rc = compressed_prepare(h, p_pre, p_wdw, pre_sample_bytes, wdw_sample_bytes, presum_rate, aux_windows);
     if (rc) return rc;
     const int np = h->icpc.n, nw = h->icpc_w.n;
-    rc = check_wf(h, wf_pre, n_events, ld_pre, np, false, pre_sample_bytes);
+    EncodedInput ep{}, ew{};
+    if (enc_pre) { ep = *enc_pre; ep.n_samples = np; rc = check_encoded(h, ep.codec, ep.enc, ep.offsets, n_events, pre_sample_bytes); }
+    else rc = check_wf(h, wf_pre, n_events, ld_pre, np, false, pre_sample_bytes);
     if (rc) return rc;
-    rc = check_wf(h, wf_wdw, n_events, ld_wdw, nw, false, wdw_sample_bytes);
+    if (enc_wdw) { ew = *enc_wdw; ew.n_samples = nw; rc = check_encoded(h, ew.codec, ew.enc, ew.offsets, n_events, wdw_sample_bytes); }
+    else rc = check_wf(h, wf_wdw, n_events, ld_wdw, nw, false, wdw_sample_bytes);
     if (rc) return rc;
+    if (n_events < 0) return fail(h, LGDSP_ERR_INVALID_ARG, "n_events < 0");
     if (n_events == 0) return LGDSP_OK;
     if (!rows_pre || !rows_wdw || !stats) return fail(h, LGDSP_ERR_INVALID_ARG, "output pointer is NULL");
-    const int64_t chunk = n_events < 8192 ? n_events : 8192;
+    const int64_t chunk = n_events < h->host_chunk ? n_events : h->host_chunk;
     const size_t sbp = (size_t)pre_sample_bytes, sbw = (size_t)wdw_sample_bytes;
-    const size_t need[2] = {(size_t)chunk * np * sbp, (size_t)chunk * nw * sbw};
+    const size_t need[2] = {enc_pre ? 16 : (size_t)chunk * np * sbp, enc_wdw ? 16 : (size_t)chunk * nw * sbw};
     for (int k = 0; k < 2; ++k)
         if (need[k] > h->cin_cap[k]) {
+            CK(cudaStreamSynchronize(h->stream));
+            CK(cudaStreamSynchronize(h->s_copy));
             for (int b = 0; b < 2; ++b) { cudaFree(h->d_cin[b][k]); h->d_cin[b][k] = nullptr; }
             h->cin_cap[k] = 0;
             for (int b = 0; b < 2; ++b) CK(cudaMalloc(&h->d_cin[b][k], need[k]));
@@ -1255,37 +1262,86 @@ int lgdsp_icpc_compressed_run(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, c
         }
     const size_t per_event = 2 * LGDSP_NCOL + 5 * LGDSP_NSTAT;
     if ((size_t)2 * chunk * per_event * sizeof(double) > h->crows_cap) {
+        CK(cudaStreamSynchronize(h->stream));
         cudaFree(h->d_crows); h->d_crows = nullptr; h->crows_cap = 0;
         CK(cudaMalloc(&h->d_crows, (size_t)2 * chunk * per_event * sizeof(double)));
         h->crows_cap = (size_t)2 * chunk * per_event * sizeof(double);
     }
+    const bool pin_pre = enc_pre ? (ep.enc_pinned && ep.off_pinned) : is_pinned(wf_pre);
+    const bool pin_wdw = enc_wdw ? (ew.enc_pinned && ew.off_pinned) : is_pinned(wf_wdw);
+    const bool pin_out = is_pinned(rows_pre) && is_pinned(rows_wdw) && is_pinned(stats);
+    HostIO io(h);
+    size_t stage_in = 0;
+    if (!pin_pre) stage_in += (enc_pre ? encoded_stage_bytes(ep, chunk, n_events) : (size_t)chunk * np * sbp) + 512;
+    if (!pin_wdw) stage_in += (enc_wdw ? encoded_stage_bytes(ew, chunk, n_events) : (size_t)chunk * nw * sbw) + 512;
+    rc = io.reserve(stage_in, pin_out ? 0 : (size_t)chunk * per_event * sizeof(double) + 1024);
+    if (rc) return rc;
+    if (enc_pre) { rc = encoded_reserve(h, ep, 0, chunk, n_events); if (rc) return rc; }
+    if (enc_wdw) { rc = encoded_reserve(h, ew, 1, chunk, n_events); if (rc) return rc; }
+    if (enc_pre || enc_wdw) { rc = decode_err_reset(h); if (rc) return rc; }
     const unsigned char* sp = static_cast<const unsigned char*>(wf_pre);
     const unsigned char* sw = static_cast<const unsigned char*>(wf_wdw);
     int c = 0;
     for (int64_t e0 = 0; e0 < n_events; e0 += chunk, ++c) {
-        const int b = c & 1;
         const int64_t ne = (n_events - e0) < chunk ? (n_events - e0) : chunk;
+        rc = io.begin_chunk(c);
+        if (rc) return rc;
+        const int b = io.b;
         if (c >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
-        CK(cudaMemcpy2DAsync(h->d_cin[b][0], (size_t)np * sbp, sp + (size_t)e0 * ld_pre * sbp, (size_t)ld_pre * sbp, (size_t)np * sbp,
-                             (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
-        CK(cudaMemcpy2DAsync(h->d_cin[b][1], (size_t)nw * sbw, sw + (size_t)e0 * ld_wdw * sbw, (size_t)ld_wdw * sbw, (size_t)nw * sbw,
-                             (size_t)ne, cudaMemcpyHostToDevice, h->s_copy));
-        CK(cudaEventRecord(h->ev_ready[b], h->s_copy));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_ready[b], 0));
+        if (enc_pre) rc = encoded_upload(h, io, ep, 0, e0, ne);
+        else rc = io.h2d(h->d_cin[b][0], sp + (size_t)e0 * ld_pre * sbp, (size_t)ld_pre * sbp, (size_t)np * sbp, (size_t)ne, pin_pre);
+        if (rc) return rc;
+        if (enc_wdw) rc = encoded_upload(h, io, ew, 1, e0, ne);
+        else rc = io.h2d(h->d_cin[b][1], sw + (size_t)e0 * ld_wdw * sbw, (size_t)ld_wdw * sbw, (size_t)nw * sbw, (size_t)ne, pin_wdw);
+        if (rc) return rc;
+        rc = io.inputs_ready();
+        if (rc) return rc;
+        const void* d_pre = h->d_cin[b][0];
+        const void* d_wdw = h->d_cin[b][1];
+        if (enc_pre) { rc = encoded_decode(h, io, ep, 0, e0, ne); if (rc) return rc; d_pre = h->d_dec[0]; }
+        if (enc_wdw) { rc = encoded_decode(h, io, ew, 1, e0, ne); if (rc) return rc; d_wdw = h->d_dec[1]; }
         double* d_rp = h->d_crows + (size_t)b * chunk * per_event;
         double* d_rw = d_rp + (size_t)chunk * LGDSP_NCOL;
         double* d_st = d_rw + (size_t)chunk * LGDSP_NCOL;
-        rc = compressed_launch(h, h->d_cin[b][0], pre_sample_bytes, np, h->d_cin[b][1], wdw_sample_bytes, nw, presum_rate, ne, d_rp, d_rw, d_st);
+        rc = compressed_launch(h, d_pre, pre_sample_bytes, np, d_wdw, wdw_sample_bytes, nw, presum_rate, ne, d_rp, d_rw, d_st);
         if (rc) return rc;
         CK(cudaGetLastError());
         CK(cudaEventRecord(h->ev_free[b], h->stream));
-        CK(cudaMemcpyAsync(rows_pre + e0 * LGDSP_NCOL, d_rp, (size_t)ne * LGDSP_NCOL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(rows_wdw + e0 * LGDSP_NCOL, d_rw, (size_t)ne * LGDSP_NCOL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(stats + e0 * 5 * LGDSP_NSTAT, d_st, (size_t)ne * 5 * LGDSP_NSTAT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        rc = io.d2h(rows_pre + e0 * LGDSP_NCOL, d_rp, (size_t)ne * LGDSP_NCOL * sizeof(double), pin_out);
+        if (!rc) rc = io.d2h(rows_wdw + e0 * LGDSP_NCOL, d_rw, (size_t)ne * LGDSP_NCOL * sizeof(double), pin_out);
+        if (!rc) rc = io.d2h(stats + e0 * 5 * LGDSP_NSTAT, d_st, (size_t)ne * 5 * LGDSP_NSTAT * sizeof(double), pin_out);
+        if (rc) return rc;
+        rc = io.end_chunk();
+        if (rc) return rc;
     }
-    CK(cudaStreamSynchronize(h->s_copy));
-    CK(cudaStreamSynchronize(h->stream));
-    return LGDSP_OK;
+    rc = io.finish();
+    if (rc) return rc;
+    return (enc_pre || enc_wdw) ? decode_err_check(h) : LGDSP_OK;
+}
+
+int lgdsp_icpc_compressed_run(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, const lgdsp_icpc_params* p_wdw, const void* wf_pre,
+                              int32_t pre_sample_bytes, int64_t ld_pre, const void* wf_wdw, int32_t wdw_sample_bytes,
+                              int64_t ld_wdw, double presum_rate, const int32_t* aux_windows, int64_t n_events, double* rows_pre,
+                              double* rows_wdw, double* stats)
+{
+    return compressed_run_host_impl(h, p_pre, p_wdw, wf_pre, pre_sample_bytes, ld_pre, wf_wdw, wdw_sample_bytes, ld_wdw, nullptr, nullptr,
+                                    presum_rate, aux_windows, n_events, rows_pre, rows_wdw, stats);
+}
+
+// dsp_icpc_compressed with decode_data on the device (/root/reference/src/dsp_icpc.jl:313-314): both waveform kinds arrive
+// as encoded byte streams in host memory
+int lgdsp_icpc_compressed_run_encoded(lgdsp_handle* h, const lgdsp_icpc_params* p_pre, const lgdsp_icpc_params* p_wdw,
+                                      int32_t pre_codec, const uint8_t* enc_pre, const int64_t* off_pre, int32_t pre_shift,
+                                      int32_t pre_sample_bytes, int32_t wdw_codec, const uint8_t* enc_wdw, const int64_t* off_wdw,
+                                      int32_t wdw_shift, int32_t wdw_sample_bytes, double presum_rate, const int32_t* aux_windows,
+                                      int64_t n_events, double* rows_pre, double* rows_wdw, double* stats)
+{
+    EncodedInput ep{pre_codec, pre_sample_bytes, 0, pre_shift, enc_pre, off_pre, enc_pre ? is_pinned(enc_pre) : false,
+                    off_pre ? is_pinned(off_pre) : false};
+    EncodedInput ew{wdw_codec, wdw_sample_bytes, 0, wdw_shift, enc_wdw, off_wdw, enc_wdw ? is_pinned(enc_wdw) : false,
+                    off_wdw ? is_pinned(off_wdw) : false};
+    return compressed_run_host_impl(h, p_pre, p_wdw, nullptr, pre_sample_bytes, 0, nullptr, wdw_sample_bytes, 0, &ep, &ew, presum_rate,
+                                    aux_windows, n_events, rows_pre, rows_wdw, stats);
 }
 
 // debug: per-phase cycle counters of the last lgdsp_icpc_run_device call (sum over CTAs; index 0: TMA wait,

@@ -214,6 +214,8 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
         double thr[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) thr[k] = e_max * P.tx_frac[k];
+        const bool lean = (G & LGDSP_GROUP_LEAN) != 0;   // only {blmean, t0, t50, e_trap, e_10410} are wanted
+        if (lean) { thr[0] = CUDART_INF; thr[2] = CUDART_INF; thr[3] = CUDART_INF; thr[4] = CUDART_INF; }
 
         // ==========================================================================================
         // prefix sums of the pole-zero waveform -> global ring; t10..t99 masks from the values in flight
@@ -333,10 +335,10 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
         // a sample further than 1/8 away takes the full logarithm and becomes the new reference).
         {
             double tl_S = 0, tl_SS = 0, tl_SX = 0;
-            bool bad = false;
+            bool bad = lean;
             double cref = 0.0, cinv = 0.0, clog = 0.0;
             const int ntail = P.tail_until - P.tail_from + 1;
-            const int q = (ntail + NT - 1) / NT;
+            const int q = lean ? 0 : (ntail + NT - 1) / NT;
             const int ia = P.tail_from + tid * q, ib = min(ia + q - 1, P.tail_until);
 #pragma unroll 1
             for (int i = 0; i < q; ++i) {
@@ -501,7 +503,8 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
         // ==========================================================================================
         // phase A: window passes over TT that depend on nothing else
         // ==========================================================================================
-        {
+        const bool lean = (G & LGDSP_GROUP_LEAN) != 0;   // BASELINE configs[1]: only {blmean, t0, t50, e_trap, e_10410}
+        if (!lean) {
             double pz_S = 0, pz_SS = 0, pz_SX = 0;
 #pragma unroll 2
             for (int idx = P.tail_from + tid; idx <= P.tail_until; idx += NT2) {
@@ -516,7 +519,19 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                 red[K2R_PZS * NW2 + wid] = pz_S; red[K2R_PZSS * NW2 + wid] = pz_SS; red[K2R_PZSX * NW2 + wid] = pz_SX;
             }
         }
-        if (G & LGDSP_GROUP_TRAPS) {
+        if (lean) {
+            // the maximum of the (10 us, 4 us) trapezoid trace only
+            double mx = -CUDART_INF;
+            const TrapDev& A = P.e10410;
+            const double* p0 = TT + tid;
+#pragma unroll 2
+            for (int off = 0; off < A.nout - tid; off += NT2) {
+                const double o = (p0[off + A.L] - p0[off + A.a + A.g]) * A.inv2 - (p0[off + A.a] - p0[off]) * A.inv1;
+                mx = o > mx ? o : mx;
+            }
+            const double a = wmax_d(mx);
+            if (lane == 0) red[K2R_E104 * NW2 + wid] = a;
+        } else if (G & LGDSP_GROUP_TRAPS) {
             double o4[4];
             trap_full2_minmax(TT, P.e10410, P.e313, tid, o4);
             const double a = wmax_d(o4[0]), b = wmax_d(o4[1]), c = wmax_d(o4[2]), d = wmax_d(o4[3]);
@@ -532,12 +547,12 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             if (G & LGDSP_GROUP_TIMING) {
                 if (ja < P.t0.nout) c0a = trap_at(TT, P.t0, ja);
                 if (jb < P.t0.nout) c0b = trap_at(TT, P.t0, jb);
-                if (!P.t0inv_same) {
+                if (!P.t0inv_same && !lean) {
                     if (ja < P.t0inv.nout) cia = trap_at(TT, P.t0inv, ja);
                     if (jb < P.t0inv.nout) cib = trap_at(TT, P.t0inv, jb);
                 }
             }
-            if (G & LGDSP_GROUP_TRAPS) {
+            if ((G & LGDSP_GROUP_TRAPS) && !lean) {
                 if (ja < P.e535.nout) c5a = trap_at(TT, P.e535, ja);
                 if (jb < P.e535.nout) c5b = trap_at(TT, P.e535, jb);
                 if (ja < P.etrap.nout) cea = trap_at(TT, P.etrap, ja);
@@ -680,7 +695,7 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                 const unsigned mp = __ballot_sync(FULL, v && (o >= th));
                 const unsigned mn_ = __ballot_sync(FULL, v && (-o >= th));
                 commit_pair(type == 0 ? masks + MK_T0 * NWORDS : nullptr, (unsigned long long)mp << 1,
-                            (type == 1 || P.t0inv_same) ? masks + MK_T0INV * NWORDS : nullptr, (unsigned long long)mn_ << 1,
+                            ((type == 1 || P.t0inv_same) && !lean) ? masks + MK_T0INV * NWORDS : nullptr, (unsigned long long)mn_ << 1,
                             false, 0, q, lane);
             } else if (type == 2) {
                 const int j = q * CH + 1 + lane;
@@ -725,18 +740,18 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                     const bool pa = va && (c0a >= th), pb = vb && (c0b >= th);
                     const bool na = va && (-c0a >= th), nb = vb && (-c0b >= th);
                     const bool fp = need(pa, pb, va), fn = need(na, nb, va);
-                    f0 = P.t0inv_same ? (fp || fn) : fp;
+                    f0 = (P.t0inv_same && !lean) ? (fp || fn) : fp;
                     if (pa) mask_commit(masks + MK_T0 * NWORDS, tid, 1ull);
-                    if (P.t0inv_same && na) mask_commit(masks + MK_T0INV * NWORDS, tid, 1ull);
+                    if (P.t0inv_same && na && !lean) mask_commit(masks + MK_T0INV * NWORDS, tid, 1ull);
                 }
-                if (!P.t0inv_same) {
+                if (!P.t0inv_same && !lean) {
                     const bool wa = i0 < P.t0inv.nout, wb = i0 + CH < P.t0inv.nout;
                     const bool na = wa && (-cia >= th), nb = wb && (-cib >= th);
                     fi = need(na, nb, wa);
                     if (na) mask_commit(masks + MK_T0INV * NWORDS, tid, 1ull);
                 }
             }
-            if (G & LGDSP_GROUP_TRAPS) {
+            if ((G & LGDSP_GROUP_TRAPS) && !lean) {
                 const double M5 = red_max(red, K2R_C535), Me = red_max(red, K2R_CET);
                 const double k5 = Ymax * 2.0 * (P.e535.inv1 + P.e535.inv2) * 1.000001;
                 const double ke = Ymax * 2.0 * (P.etrap.inv1 + P.etrap.inv2) * 1.000001;
@@ -824,7 +839,7 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             const double area1 = a[1] - a[0], area2 = a[2] - a[1];
             return area2 - area1;
         };
-        if (wid == 0) {
+        if (wid == 0 && !lean) {
             // PZ tail statistics (signalstats on the tail window, src/dsp_icpc.jl:123)
             const double pzS = red_sum(red, K2R_PZS), pzSS = red_sum(red, K2R_PZSS), pzSX = red_sum(red, K2R_PZSX);
             if (lane == 0) {
@@ -833,9 +848,9 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                 row[LGDSP_COL_tailslope] = st.slope; row[LGDSP_COL_tailoffset] = st.offset;
             }
         } else if (wid == 1) {
-            int pos0, pos0i, mult_;
+            int pos0, pos0i = -1, mult_;
             resolve_runs(masks + MK_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
-            resolve_runs(masks + MK_T0INV * NWORDS, P.t0_min_n, lane, pos0i, mult_);
+            if (!lean) resolve_runs(masks + MK_T0INV * NWORDS, P.t0_min_n, lane, pos0i, mult_);
             double t = 0.0;
             if (lane < 5) {
                 t = tx_us(lane);
@@ -849,12 +864,16 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
         } else if (wid == 2) {
             if (G & LGDSP_GROUP_TRAPS) {
                 const double v = dni_eval_warp(A_sig, P.sig_dni.n_w, P.sig_dni.m, stash, pk_p - (double)pk_from, lane);
-                double em;
-                int ea;
-                red_argmax(red, K2R_ETMAX, K2R_ETARG, em, ea);
-                const double a = red_max(red, K2R_E104), b = red_max(red, K2R_E535), c = red_max(red, K2R_E313);
-                const double d = red_max(red, K2R_E104N), f = red_max(red, K2R_E313N);
-                if (lane == 0) {
+                if (lean) {
+                    const double a = red_max(red, K2R_E104);
+                    if (lane == 0) { row[LGDSP_COL_e_10410] = a; row[LGDSP_COL_e_trap] = v; }
+                }
+                double em = 0;
+                int ea = 0;
+                if (!lean) red_argmax(red, K2R_ETMAX, K2R_ETARG, em, ea);
+                const double a = lean ? 0.0 : red_max(red, K2R_E104), b = lean ? 0.0 : red_max(red, K2R_E535), c = lean ? 0.0 : red_max(red, K2R_E313);
+                const double d = lean ? 0.0 : red_max(red, K2R_E104N), f = lean ? 0.0 : red_max(red, K2R_E313N);
+                if (lane == 0 && !lean) {
                     row[LGDSP_COL_e_10410] = a; row[LGDSP_COL_e_535] = b; row[LGDSP_COL_e_313] = c;
                     row[LGDSP_COL_e_10410_inv] = d; row[LGDSP_COL_e_313_inv] = f;
                     row[LGDSP_COL_e_trap_max] = em;
@@ -1079,7 +1098,6 @@ icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
     const double* A_sig = P.dni_A + LGDSP_MAX_DNI * 4;
     const int npass = P.direct ? 0 : (P.cz_shared ? 1 : 2);
     const int nw = P.sig_dni.n_w;
-    const int i0 = tid * CH;
 
     if (tid == 0) {
         mbar_init(bar, 1);

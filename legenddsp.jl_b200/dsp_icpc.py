@@ -209,18 +209,49 @@ def compressed_to_table(rows_pre: np.ndarray, rows_wdw: np.ndarray, stats: np.nd
     return out
 
 
+def _dsp_icpc_compressed_encoded(data, wp, ww, config, τ, pars_filter, device, handle, policy, builders):
+    ep, ew = wp.signal, ww.signal
+    if len(ep) != len(ew):
+        raise ValueError("waveform_presummed and waveform_windowed differ in length")
+    rates = np.unique(np.asarray(data["presum_rate"]))
+    if rates.size != 1:
+        raise ValueError("presum_rate must be the same for all events")
+    presum = int(rates[0])
+    n_events = len(ep)
+    P_pre, P_wdw, aux = resolve_compressed_params(config, τ, pars_filter, presum_rate=presum, n_pre=ep.n_samples,
+                                                  t_first_pre=wp.t_first, step_pre=wp.step, n_wdw=ew.n_samples,
+                                                  t_first_wdw=ww.t_first, step_wdw=ww.step, policy=policy, builders=builders)
+    h = handle or get_handle(device)
+    rows_pre = np.zeros((n_events, _abi.NCOL), dtype=np.float64)
+    rows_wdw = np.zeros((n_events, _abi.NCOL), dtype=np.float64)
+    stats = np.zeros((n_events, 5, 5), dtype=np.float64)
+    h.icpc_compressed_run_encoded_host(P_pre, P_wdw, ep, ew, float(presum), aux, rows_pre.ctypes.data, rows_wdw.ctypes.data,
+                                       stats.ctypes.data)
+    return compressed_to_table(rows_pre, rows_wdw, stats, data)
+
+
 def dsp_icpc_compressed(data: Mapping[str, Any], config: DSPConfig, τ: Q, pars_filter: Optional[Dict[str, Any]] = None, *,
                         f_evaluate_qc=None, device: int = 0, handle: Optional[Handle] = None,
                         policy: RddspPolicy = DEFAULT_POLICY, builders=None) -> "OrderedDict[str, np.ndarray]":
     """DSP routine for ICPC detectors on the compressed format: the reference's
     `dsp_icpc_compressed(data, config, τ, pars_filter)` (src/dsp_icpc.jl:293-499).
 
-    `data` needs `waveform_presummed`, `waveform_windowed` (RDWaveforms of raw integer samples, each with its own time
-    axis) and `presum_rate` (one value for all events, `only(unique(presum_rate))` :324); the pass-through columns
+    `data` needs `waveform_presummed`, `waveform_windowed` (RDWaveforms of raw integer samples -- or of
+    `codec.EncodedWaveforms`, which are decoded on the device like the reference's `decode_data` calls :313-314 -- each with
+    its own time axis) and `presum_rate` (one value for all events, `only(unique(presum_rate))` :324); the pass-through columns
     `baseline, timestamp, eventnumber, daqenergy, t_sat_lo, t_sat_hi, deadtime` are copied when present."""
     if f_evaluate_qc is not None:
         raise NotImplementedError("f_evaluate_qc is not supported; qc_label is -1 as in the reference without a model")
+    from .codec import EncodedWaveforms
     wp, ww = _as_waveforms(data["waveform_presummed"]), _as_waveforms(data["waveform_windowed"])
+    encoded = isinstance(wp.signal, EncodedWaveforms) and isinstance(ww.signal, EncodedWaveforms)
+    if encoded:
+        # decode_data(data.waveform_presummed), decode_data(data.waveform_windowed)  src/dsp_icpc.jl:313-314 -- on the device
+        return _dsp_icpc_compressed_encoded(data, wp, ww, config, τ, pars_filter, device, handle, policy, builders)
+    if isinstance(wp.signal, EncodedWaveforms) or isinstance(ww.signal, EncodedWaveforms):
+        from .codec import decode_data
+        wp = RDWaveforms(decode_data(wp.signal, handle or get_handle(device)), wp.t_first, wp.step) if isinstance(wp.signal, EncodedWaveforms) else wp
+        ww = RDWaveforms(decode_data(ww.signal, handle or get_handle(device)), ww.t_first, ww.step) if isinstance(ww.signal, EncodedWaveforms) else ww
     pre, wdw = _signal_uint(wp.signal), _signal_uint(ww.signal)
     if pre.shape[0] != wdw.shape[0]:
         raise ValueError("waveform_presummed and waveform_windowed differ in length")

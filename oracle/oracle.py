@@ -12,6 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liblgdsp_oracle.so")
+_SO_FAST = os.path.join(_HERE, "liblgdsp_oracle_fast.so")   # -O3 -march=native build of the same sources: the TIMED CPU arm
 
 _abi = importlib.import_module("legenddsp.jl_b200._abi")
 
@@ -23,22 +24,31 @@ _dp = C.POINTER(C.c_double)
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "lgdsp_oracle.c")
-    src2 = os.path.join(_HERE, "lgdsp_codec_oracle.c")
-    hdr = os.path.join(_HERE, "..", "include", "lgdsp_b200.h")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(src2), os.path.getmtime(hdr)):
+    deps = [os.path.join(_HERE, f) for f in ("lgdsp_oracle.c", "lgdsp_codec_oracle.c", "lgdsp_synth_oracle.c", "Makefile")]
+    deps.append(os.path.join(_HERE, "..", "include", "lgdsp_b200.h"))
+    newest = max(os.path.getmtime(d) for d in deps)
+    if force or not all(os.path.exists(f) and os.path.getmtime(f) >= newest for f in (_SO, _SO_FAST)):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return _SO
 
 
 _lib = None
+_fast = False
+
+
+def use_fast_build(on=True):
+    """switch this module to the -O3 -march=native build (bench.py's CPU arms); the tests stay on the strict build"""
+    global _lib, _fast
+    if on != _fast:
+        _lib = None
+        _fast = on
 
 
 def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(_SO)
+        L = C.CDLL(_SO_FAST if _fast else _SO)
         L.orc_lsq_fit_matrix.argtypes = [C.c_int, C.c_int, _dp]
         L.orc_sg_coeffs.argtypes = [C.c_int, C.c_int, C.c_int, _dp]
         L.orc_cusp_coeffs.argtypes = [C.c_double, C.c_int, C.c_double, C.c_int, C.c_double, _dp]
@@ -427,3 +437,25 @@ def uleb128zzd_decode(b_u8, dtype=np.uint32, n_max=65536):
     if n < 0:
         raise ValueError("orc_uleb128zzd_decode: malformed stream")
     return out[:n].copy()
+
+
+def synth_generate(n_events, first_event=0, n_samples=8192, seed=20260101, mode=0, noise_sigma=3.0, tau_samples=31250.0):
+    """the synthetic event stream (lgdsp_synth_oracle.c): the CPU arms' own generator, no product library involved"""
+    L = lib()
+    L.orc_synth_generate.argtypes = [C.POINTER(_abi.SynthParams), C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
+    sp = _abi.SynthParams(seed, n_samples, mode, noise_sigma, tau_samples)
+    out = np.zeros((int(n_events), n_samples), dtype=np.uint16)
+    rc = L.orc_synth_generate(C.byref(sp), int(first_event), int(n_events), n_samples, out.ctypes.data)
+    if rc != 0:
+        raise ValueError("orc_synth_generate failed")
+    return out
+
+
+def pz_trap(params, wf_u16, n_threads=0):
+    """BASELINE configs[1] on the CPU: columns blmean, t0, t50, e_trap, e_10410"""
+    L = lib()
+    L.orc_pz_trap.argtypes = [C.POINTER(_abi.IcpcParams), C.c_void_p, C.c_int64, C.c_int64, _dp, C.c_int]
+    wf = np.ascontiguousarray(wf_u16, dtype=np.uint16)
+    out = np.zeros((wf.shape[0], 5), dtype=np.float64)
+    L.orc_pz_trap(C.byref(params), wf.ctypes.data, wf.shape[0], wf.shape[1], out.ctypes.data_as(_dp), int(n_threads))
+    return out

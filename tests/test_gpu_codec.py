@@ -72,3 +72,27 @@ def test_dsp_icpc_on_encoded_waveforms(L, O, handle):
     same = (got == want) | (np.isnan(got) & np.isnan(want))
     assert same.all()
     print("bytes per event over the host link:", enc.nbytes / len(enc) + 8, "instead of", wf.shape[1] * 2)
+
+
+def test_dsp_icpc_compressed_with_decode_data_on_the_device(L, O, handle):
+    """`dsp_icpc_compressed` fed with encoded waveform sets (the reference's decode_data calls, src/dsp_icpc.jl:313-314)
+    gives the same table as fed with the decoded samples"""
+    n_events, presum, window = 3000, 8, (2600, 1400)
+    wf = L.synth.generate_host(n_events, first_event=31)
+    pre, wdw = L.synth.compress(wf, presum, window)
+    step = L.ns(16.0)
+    base = {"presum_rate": np.full(n_events, presum, dtype=np.uint16)}
+    plain = dict(base, waveform_presummed=L.RDWaveforms(pre, L.ns(0.0), step * float(presum)),
+                 waveform_windowed=L.RDWaveforms(wdw, step * float(window[0]), step))
+    enc_pre = L.encode_waveforms(pre.astype(np.uint32), L.ULEB128_ZIGZAG_DIFF)
+    enc_wdw = L.encode_waveforms(wdw.astype(np.uint16), L.RADWARE_SIGCOMPRESS)
+    coded = dict(base, waveform_presummed=L.RDWaveforms(enc_pre, L.ns(0.0), step * float(presum)),
+                 waveform_windowed=L.RDWaveforms(enc_wdw, step * float(window[0]), step))
+    cfg = L.example_config()
+    want = L.dsp_icpc_compressed(plain, cfg, L.us(500.0), handle=handle)
+    got = L.dsp_icpc_compressed(coded, cfg, L.us(500.0), handle=handle)
+    assert list(want) == list(got)
+    for k in want:
+        a, b = np.asarray(want[k], dtype=np.float64), np.asarray(got[k], dtype=np.float64)
+        assert ((a == b) | (np.isnan(a) & np.isnan(b))).all(), k
+    print("encoded bytes per event:", (enc_pre.nbytes + enc_wdw.nbytes) / n_events, "raw:", pre.shape[1] * 4 + wdw.shape[1] * 2)

@@ -67,3 +67,14 @@ def test_split_separate_cusp_zac_and_short_traces(L, O, handle):
     split = _rows(L, handle, wf, P, "split", 128, 2)
     bad = _identical(split, fused, L.COLUMNS)
     assert not bad, bad
+
+
+def test_lean_pz_trap_columns(L, O, handle):
+    """LGDSP_GROUP_PZTRAP_LEAN (BASELINE configs[1]): the five columns it keeps are the full chain's values, bit for bit"""
+    cfg = L.tiefree_config()
+    wf = L.synth.generate_host(1500, first_event=99)
+    full = L.dsp_icpc_rows(wf, L.resolve_icpc_params(cfg, L.us(500.0)), handle=handle)
+    lean = L.dsp_icpc_rows(wf, L.resolve_icpc_params(cfg, L.us(500.0), groups=L._abi.GROUP_PZTRAP_LEAN), handle=handle)
+    for name in ("blmean", "t0", "t50", "e_trap", "e_10410", "e_max", "e_min", "n_sat_high"):
+        j = L.COL[name]
+        assert np.array_equal(lean[:, j], full[:, j]), name
