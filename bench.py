@@ -3,16 +3,24 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload W] [--batch B]
 
-One "step" = one pass of the fused kernel over one batch of synthetic waveforms that is already resident in
-HBM (`value`), and the same through the reference-facing C-ABI call with pinned HOST buffers (`e2e`).
-Workloads: dsp_icpc (default; full 49-column chain incl. CUSP/ZAC = BASELINE.json configs[2]/[4]),
-pz_trap (configs[1]), trap_sweep (configs[3], 200 trapezoid variants).
-Multi-GPU: one process per GPU under torchrun, events sharded, no collective on the data path ("weak" scaling:
-per-GPU batch fixed).  `--impl reference` times the CPU port of the reference algorithm (oracle/) on rank 0.
-Prints ONE JSON line on rank 0.
+One "step" = one pass of the chain over one batch of synthetic waveforms.
+  value            the batch is already resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e              the same through the reference-facing host C-ABI call with PINNED host buffers: H2D of the raw UInt16
+                   samples + kernels + D2H of the 49-column rows inside the timed region
+  e2e_pageable     the same from pageable numpy memory (what a Julia `flatview(wvfs.signal)` is): staged through the library's
+                   pinned ring by LGDSP_COPY_THREADS host threads
+  e2e_encoded      the same with radware-sigcompress ENCODED waveforms in pinned host memory (the on-disk form of LEGEND
+                   waveforms): only the encoded bytes cross the host link, decode_data runs on the GPU
+  value_with_gather  (config 5 of BASELINE.json) the device-resident step plus the gather of every rank's output table on rank 0
+                   (NCCL gather over NVLink, then one D2H into pinned host memory) inside the timed region
+  extra_workloads  BASELINE configs[1] (PZ + trapezoid energy / t0 only) and configs[3] (20 x 10 trapezoid sweep), a few steps each
+Workloads: dsp_icpc (default; full 49-column chain incl. CUSP/ZAC = BASELINE.json configs[2]/[4]), pz_trap (configs[1]),
+trap_sweep (configs[3]), compressed (dsp_icpc_compressed; e2e on ENCODED bytes), sipm.
+Multi-GPU: one process per GPU under torchrun, events sharded, no collective on the data path ("weak" scaling: per-GPU
+batch fixed).  `--impl reference` times the CPU port of the reference algorithm (oracle/, -O3 build) on rank 0; it does
+not load the product library.  Prints ONE JSON line on rank 0.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -25,10 +33,11 @@ sys.path.insert(0, ROOT)
 
 BYTES_IN = 8192 * 2
 NCOL = 49
-# DRAM traffic per waveform of icpc_kernel from the committed ncu --set full capture (profiles/r01_icpc_kernel_ncu_full.txt:
-# dram__bytes_read.sum + dram__bytes_write.sum = 269.97 MB + 11.56 MB for 16 384 events); roofline.traffic scales it to
-# the events of one launch.  Algorithmic bytes are 16 776 B/waveform: no re-reads.
-NCU_DRAM_BYTES_PER_WF = {"dsp_icpc": (269.97e6 + 11.56e6) / 16384.0}
+# DRAM traffic per waveform from the committed ncu capture of the split pipeline (profiles/r02_ncu_launches_split.txt:
+# dram__bytes_read.sum + dram__bytes_write.sum of prefix + extract + CUSP/ZAC select + finish, per event).  The prefix sums
+# (65.6 KB per event) are written once and read by the two consumers through L2/HBM: that is the price of running the chain
+# as kernels with their own occupancy; algorithmic bytes are 16 776 B per waveform.
+NCU_DRAM_BYTES_PER_WF = {"dsp_icpc": 231.1e3}
 
 
 def _peaks():
@@ -130,30 +139,82 @@ def sipm_events(torch, n_events, seed, device):
     return y.round().clamp(0, 65535).to(torch.int32).to(torch.int16)
 
 
-def cpu_port_throughput(L, O, P, n_events, workload, variants=None, sparams=None, reps=1, threads=0):
-    """the CPU port of the reference algorithm (oracle/) on all host cores: waveforms/s"""
-    if workload == "sipm":
-        import torch
-        wf = sipm_events(torch, n_events, 99, "cpu").numpy().view("uint16")
-        t0 = time.perf_counter()
-        O.dsp_sipm(P, wf, n_threads=threads)
-        return n_events / (time.perf_counter() - t0)
-    wf = L.synth.generate_host(n_events, first_event=10_000_000)
-    if workload == "compressed":
-        pre, wdw = L.synth.compress(wf, PRESUM, (WDW_FROM, WDW_N))
-        Pp, Pw, aux = P
-    best = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
+def sweep_variants(L):
+    rts = [L.us(1.0 + 0.75 * i) for i in range(20)]
+    fts = [L.us(1.0 + 0.3 * i) for i in range(10)]
+    return L.trap_variants(rts, fts, L.ns(16.0), mode="ft")
+
+
+class CpuArm:
+    """the CPU port of the reference algorithm (oracle/, the -O3 -march=native build that also pays for the reference's
+    second ZAC pass) on all host cores; its own event generator -- nothing of the product library is loaded"""
+
+    def __init__(self, L, workload, cfg, tau, groups, threads):
+        from oracle import oracle as O
+        O.use_fast_build(True)
+        self.O, self.L, self.workload, self.threads = O, L, workload, threads
+        self.kind = "port"
+        b = O.OracleBuilders()
         if workload == "compressed":
-            O.dsp_icpc_compressed(Pp, Pw, pre, wdw, PRESUM, aux, n_threads=threads)
-        elif workload == "trap_sweep":
-            O.trap_sweep(sparams, wf, variants, n_threads=threads)
+            self.P = compressed_setup(L, cfg, tau, b)
+        elif workload == "sipm":
+            self.P = sipm_setup(L, b)
         else:
-            O.dsp_icpc(P, wf, n_threads=threads)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n_events / best
+            self.P = L.resolve_icpc_params(cfg, tau, groups=groups or L._abi.GROUP_ALL, builders=b)
+        if workload == "trap_sweep":
+            self.sp = L.resolve_sweep_params(cfg, tau, builders=b)
+            self.variants = sweep_variants(L)
+
+    def events(self, n):
+        if self.workload == "sipm":
+            import torch
+            return sipm_events(torch, n, 99, "cpu").numpy().view("uint16")
+        wf = self.O.synth_generate(n, first_event=10_000_000)
+        if self.workload == "compressed":
+            import numpy as np
+            pre = wf.reshape(n, 8192 // PRESUM, PRESUM).sum(axis=2, dtype=np.uint32)
+            return pre, np.ascontiguousarray(wf[:, WDW_FROM:WDW_FROM + WDW_N])
+        return wf
+
+    def step(self, ev):
+        O, t = self.O, self.threads
+        if self.workload == "sipm":
+            O.dsp_sipm(self.P, ev, n_threads=t)
+        elif self.workload == "compressed":
+            Pp, Pw, aux = self.P
+            O.dsp_icpc_compressed(Pp, Pw, ev[0], ev[1], PRESUM, aux, n_threads=t)
+        elif self.workload == "trap_sweep":
+            O.trap_sweep(self.sp, ev, self.variants, n_threads=t)
+        elif self.workload == "pz_trap":
+            O.pz_trap(self.P, ev, n_threads=t)
+        else:
+            O.dsp_icpc(self.P, ev, n_threads=t)
+
+    def throughput(self, n, reps=1):
+        ev = self.events(n)
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            self.step(ev)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return n / best
+
+    def describe(self, n):
+        what = {"pz_trap": "only the steps that produce blmean, t0, t50, e_trap, e_10410 (src/dsp_icpc.jl:102-163)",
+                "trap_sweep": "one full trapezoid pass per (rt, ft) variant as the reference does"}.get(
+                    self.workload, "float64, one materialised intermediate per step, direct-form CUSP/ZAC FIRs, ZAC applied twice as "
+                                   "src/dsp_icpc.jl:175,177")
+        return (f"{n} waveforms of the same synthetic stream; CPU restatement of the reference algorithm (oracle/, gcc -O3 "
+                f"-march=native -fopenmp, OpenMP over events): {what}; not Julia")
+
+
+WL_NAME = {"dsp_icpc": "full dsp_icpc, 49 columns incl. CUSP+ZAC (BASELINE configs[2]/[4])",
+           "pz_trap": "pole-zero + trapezoid energy / t0 only: blmean, t0, t50, e_trap, e_10410 (BASELINE configs[1])",
+           "trap_sweep": "20x10 trapezoid (rt, ft) sweep, 200 variants (BASELINE configs[3])",
+           "sipm": "dsp_sipm trigger chain on 6250-sample UInt16 SiPM traces (SURVEY 8f rank 3)",
+           "compressed": "dsp_icpc_compressed: 1024 presummed uint32 (x8) + 1400 windowed uint16 samples per event "
+                         "(SURVEY 8f rank 1)"}
 
 
 def main():
@@ -164,11 +225,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dsp_icpc", choices=["dsp_icpc", "pz_trap", "trap_sweep", "compressed", "sipm"])
     ap.add_argument("--batch", type=int, default=131072, help="waveforms per step per GPU (131072 = 2.1 GB >> L2)")
-    ap.add_argument("--pool", type=int, default=4, help="distinct resident batches cycled by the steps")
+    ap.add_argument("--pool", type=int, default=8, help="distinct resident batches cycled by the steps")
     ap.add_argument("--direct", action="store_true", help="CUSP/ZAC as direct 2375-tap FIRs (validation mode)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--path", default="split", choices=["split", "fused"], help="dsp_icpc execution path")
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-sample", type=int, default=0, help="events of the cpu_baseline sample (0: auto)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads / e2e variants / value_with_gather")
     ap.add_argument("--groups", default=None, help="override the column-group mask (hex), for per-stage timing experiments")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -183,13 +246,8 @@ def main():
 
     cfg = L.tiefree_config()
     tau = L.us(500.0)
-    groups = {"dsp_icpc": L._abi.GROUP_ALL, "pz_trap": L._abi.GROUP_PZTRAP, "trap_sweep": 0, "compressed": 0, "sipm": 0}[args.workload]
-    wl_name = {"dsp_icpc": "full dsp_icpc, 49 columns incl. CUSP+ZAC (BASELINE configs[2]/[4])",
-               "pz_trap": "pole-zero + trapezoid energies/t0 only (BASELINE configs[1])",
-               "trap_sweep": "20x10 trapezoid (rt, ft) sweep, 200 variants (BASELINE configs[3])",
-               "sipm": "dsp_sipm trigger chain on 6250-sample UInt16 SiPM traces (SURVEY 8f rank 3)",
-               "compressed": "dsp_icpc_compressed: 1024 presummed uint32 (x8) + 1400 windowed uint16 samples per event "
-                             "(SURVEY 8f rank 1)"}[args.workload]
+    groups = {"dsp_icpc": L._abi.GROUP_ALL, "pz_trap": L._abi.GROUP_PZTRAP_LEAN, "trap_sweep": 0, "compressed": 0, "sipm": 0}[args.workload]
+    wl_name = WL_NAME[args.workload]
     if args.groups is not None:
         groups = int(args.groups, 16)
         wl_name += f" [experimental group mask {groups:#x}]"
@@ -197,51 +255,25 @@ def main():
                  "sipm": (24 + 16 * SIPM_CAP) * 8}[args.workload]
     bytes_in = {"compressed": (8192 // PRESUM) * 4 + WDW_N * 2, "sipm": SIPM_N * 2}.get(args.workload, BYTES_IN)
     bytes_per_wf = bytes_in + out_bytes
-    variants = sparams = None
-    if args.workload == "trap_sweep":
-        rts = [L.us(1.0 + 0.75 * i) for i in range(20)]
-        fts = [L.us(1.0 + 0.3 * i) for i in range(10)]
-        variants = L.trap_variants(rts, fts, L.ns(16.0), mode="ft")
 
     # ------------------------------------------------------------------------------------------
     # reference arm: the CPU port of the reference algorithm (the reference itself is Julia and cannot be
-    # installed here -- DESIGN.md section 3), all host threads, bounded sample per step
+    # installed here -- DESIGN.md section 2), all host threads, bounded sample per step
     # ------------------------------------------------------------------------------------------
     if args.impl == "reference":
         if rank != 0:
             return 0
-        from oracle import oracle as O
-        P = L.resolve_icpc_params(cfg, tau, groups=groups or L._abi.GROUP_ALL, builders=O.OracleBuilders())
-        if args.workload == "trap_sweep":
-            sparams = L.resolve_sweep_params(cfg, tau, builders=O.OracleBuilders())
         threads = host_threads()
-        n_s = args.cpu_sample or (32 * threads if args.workload != "trap_sweep" else 16 * threads)
-        wf = L.synth.generate_host(n_s, first_event=10_000_000)
-        if args.workload == "compressed":
-            Pp, Pw, aux = compressed_setup(L, cfg, tau, O.OracleBuilders())
-            pre, wdw = L.synth.compress(wf, PRESUM, (WDW_FROM, WDW_N))
-        if args.workload == "sipm":
-            import torch
-            Ps = sipm_setup(L, O.OracleBuilders())
-            wf = sipm_events(torch, n_s, 99, "cpu").numpy().view("uint16")
-
-        def step():
-            if args.workload == "sipm":
-                O.dsp_sipm(Ps, wf, n_threads=threads)
-            elif args.workload == "compressed":
-                O.dsp_icpc_compressed(Pp, Pw, pre, wdw, PRESUM, aux, n_threads=threads)
-            elif args.workload == "trap_sweep":
-                O.trap_sweep(sparams, wf, variants, n_threads=threads)
-            else:
-                O.dsp_icpc(P, wf, n_threads=threads)
+        arm = CpuArm(L, args.workload, cfg, tau, groups, threads)
+        n_s = args.cpu_sample or {"pz_trap": 512 * threads, "trap_sweep": 16 * threads}.get(args.workload, 32 * threads)
+        ev = arm.events(n_s)
         for _ in range(args.warmup):
-            step()
+            arm.step(ev)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            step()
+            arm.step(ev)
         dt = time.perf_counter() - t0
         val = n_s * args.steps / dt
-        sample = f"{n_s} synthetic waveforms per step (same generator/config as the GPU arm), float64, OpenMP over events"
         print(json.dumps({
             "impl": "reference", "metric": "waveforms/sec for dsp_icpc (8192-sample)", "value": val,
             "unit": "waveforms/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
@@ -249,7 +281,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name, "n_samples": 8192, "events_per_step": n_s,
                        "note": "CPU restatement of the reference algorithm (oracle/), not Julia: no Julia toolchain in this image"},
-            "cpu_baseline": {"value": val, "unit": "waveforms/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "waveforms/s", "cores": threads, "kind": arm.kind, "sample": arm.describe(n_s)},
             "e2e": {"value": val, "unit": "waveforms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return 0
@@ -257,6 +289,7 @@ def main():
     # ------------------------------------------------------------------------------------------
     # our arm
     # ------------------------------------------------------------------------------------------
+    import numpy as np
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -281,10 +314,13 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     h = L.Handle(local_rank, stream=stream.cuda_stream)
+    h.set_icpc_path(args.path)
 
     P = L.resolve_icpc_params(cfg, tau, groups=groups or L._abi.GROUP_ALL, cuspzac_direct=args.direct)
+    variants = sparams = None
     if args.workload == "trap_sweep":
         sparams = L.resolve_sweep_params(cfg, tau)
+        variants = sweep_variants(L)
     elif args.workload == "compressed":
         Pp, Pw, aux = compressed_setup(L, cfg, tau)
     elif args.workload == "sipm":
@@ -333,117 +369,227 @@ def main():
         else:
             h.icpc_run_device(None, pool[k % n_pool].data_ptr(), B, 8192, out.data_ptr())
 
+    def timed(fn, steps, warmup):
+        """device ms (CUDA events on the launching stream, max over ranks) and kernel launches of `steps` calls"""
+        for k in range(warmup):
+            fn(k)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0 = h.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for k in range(steps):
+            fn(k)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), h.launch_count - l0
+
+    sampler = ClockSampler(local_rank)
     for k in range(args.warmup):
         step(k)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = h.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record(stream)
-    for k in range(args.steps):
-        step(k)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    launches = h.launch_count - launches0
+    ms_max, launches = timed(step, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
     value = world * B * args.steps / (ms_max * 1e-3)
 
-    # ---- e2e: pinned host buffers through the host C-ABI call (H2D + kernel + D2H inside the timed region) ----
-    Be = min(B, 65536)
+    # ---- e2e through the host C-ABI call (H2D + kernels + D2H inside the timed region) ----
+    Be = min(B, 131072)
+
+    def wall(fn, steps):
+        fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item())
+
+    e2e_extra = {}
     if args.workload == "compressed":
-        host_pre = torch.empty((Be, 8192 // PRESUM), dtype=torch.int32).pin_memory()
-        host_wdw = torch.empty((Be, WDW_N), dtype=torch.int16).pin_memory()
-        host_pre.copy_(c_pre[0][:Be])
-        host_wdw.copy_(c_wdw[0][:Be])
+        # the reference-facing call takes the ENCODED waveform sets (decode_data, src/dsp_icpc.jl:313-314, runs on the device)
+        pre_h = (c_pre[0][:Be].cpu().numpy().view(np.uint32))
+        wdw_h = (c_wdw[0][:Be].cpu().numpy().view(np.uint16))
+        enc_p = L.encode_waveforms(pre_h, L.ULEB128_ZIGZAG_DIFF)
+        enc_w = L.encode_waveforms(wdw_h, L.RADWARE_SIGCOMPRESS)
+        pins = [torch.from_numpy(a).pin_memory() for a in (enc_p.data, enc_p.offsets, enc_w.data, enc_w.offsets)]
+        enc_p.data, enc_p.offsets, enc_w.data, enc_w.offsets = [p.numpy() for p in pins]
+        host_out = torch.empty((Be, NCOL), dtype=torch.float64).pin_memory()
         host_out_w = torch.empty((Be, NCOL), dtype=torch.float64).pin_memory()
         host_out_s = torch.empty((Be, 25), dtype=torch.float64).pin_memory()
+        h.icpc_compressed_run_encoded_host(Pp, Pw, enc_p, enc_w, float(PRESUM), aux, host_out.data_ptr(), host_out_w.data_ptr(),
+                                           host_out_s.data_ptr())
+
+        def e2e_step():
+            h.icpc_compressed_run_encoded_host(None, None, enc_p, enc_w, float(PRESUM), aux, host_out.data_ptr(), host_out_w.data_ptr(),
+                                               host_out_s.data_ptr())
+        h2d_bytes = enc_p.nbytes + enc_w.nbytes + 2 * (Be + 1) * 8
+        e2e_note = (f"ENCODED host input: ULEB128 zig-zag diff (presummed) + radware-sigcompress (windowed), "
+                    f"{(enc_p.nbytes + enc_w.nbytes) / Be:.0f} B/event instead of {bytes_in} B decoded; decode_data on the device")
+        # the decoded-input variant for comparison
+        hp = torch.from_numpy(pre_h.view(np.int32)).pin_memory()
+        hw = torch.from_numpy(wdw_h.view(np.int16)).pin_memory()
+
+        def e2e_raw():
+            h.icpc_compressed_run_host(None, None, hp.data_ptr(), 4, 8192 // PRESUM, hw.data_ptr(), 2, WDW_N, float(PRESUM), aux, Be,
+                                       host_out.data_ptr(), host_out_w.data_ptr(), host_out_s.data_ptr())
+        if not args.no_extra:
+            s = wall(e2e_raw, args.e2e_steps)
+            e2e_extra["e2e_decoded_input"] = {"value": world * Be * args.e2e_steps / s, "unit": "waveforms/s",
+                                              "h2d_bytes_per_step": Be * bytes_in}
     else:
         host_in = torch.empty((Be, SIPM_N if args.workload == "sipm" else 8192), dtype=torch.int16).pin_memory()
         host_in.copy_(pool[0][:Be])
         host_out_t = torch.empty((Be, 16 * SIPM_CAP), dtype=torch.float64).pin_memory() if args.workload == "sipm" else None
-    if args.workload == "trap_sweep":
-        host_out = torch.empty((Be, 200), dtype=torch.float32).pin_memory()
-    else:
-        host_out = torch.empty((Be, NCOL), dtype=torch.float64).pin_memory()
+        host_out = (torch.empty((Be, 200), dtype=torch.float32) if args.workload == "trap_sweep"
+                    else torch.empty((Be, NCOL), dtype=torch.float64)).pin_memory()
 
-    def e2e_step():
-        if args.workload == "sipm":
-            h.sipm_run_host(Ps, host_in.data_ptr(), Be, SIPM_N, host_out.data_ptr(), host_out_t.data_ptr())
-        elif args.workload == "compressed":
-            h.icpc_compressed_run_host(None, None, host_pre.data_ptr(), 4, 8192 // PRESUM, host_wdw.data_ptr(), 2, WDW_N,
-                                       float(PRESUM), aux, Be, host_out.data_ptr(), host_out_w.data_ptr(), host_out_s.data_ptr())
-        elif args.workload == "trap_sweep":
-            h.sweep_run_host(sparams, host_in.data_ptr(), Be, 8192, variants, host_out.data_ptr())
-        else:
-            h.icpc_run_host(None, host_in.data_ptr(), Be, 8192, host_out.data_ptr())
-    e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * Be * args.e2e_steps / float(te.item())
+        def e2e_step():
+            if args.workload == "sipm":
+                h.sipm_run_host(Ps, host_in.data_ptr(), Be, SIPM_N, host_out.data_ptr(), host_out_t.data_ptr())
+            elif args.workload == "trap_sweep":
+                h.sweep_run_host(sparams, host_in.data_ptr(), Be, 8192, variants, host_out.data_ptr())
+            else:
+                h.icpc_run_host(None, host_in.data_ptr(), Be, 8192, host_out.data_ptr())
+        h2d_bytes = Be * bytes_in
+        e2e_note = "pinned host buffers, raw UInt16 samples"
+    e2e_s = wall(e2e_step, args.e2e_steps)
+    e2e_val = world * Be * args.e2e_steps / e2e_s
     ho = host_out.double()
     checksum = float(ho[torch.isfinite(ho)].sum().item())  # the result is really read on the host
 
+    if args.workload == "dsp_icpc" and not args.no_extra:
+        # (a) pageable caller memory (numpy): staged through the library's pinned ring
+        pg_in = host_in.numpy().copy()
+        pg_out = np.empty((Be, NCOL))
+        s = wall(lambda: h.icpc_run_host(None, pg_in.ctypes.data, Be, 8192, pg_out.ctypes.data), args.e2e_steps)
+        e2e_extra["e2e_pageable"] = {"value": world * Be * args.e2e_steps / s, "unit": "waveforms/s", "h2d_bytes_per_step": Be * bytes_in,
+                                     "note": "pageable numpy buffers packed into the pinned staging ring by host threads; bound by the "
+                                             "host's memcpy bandwidth (tools/h2d_peak.py)"}
+        same = np.array_equal(np.nan_to_num(pg_out), np.nan_to_num(host_out.numpy()))
+        # (b) radware-sigcompress encoded waveforms in pinned memory: decode_data on the device
+        enc = L.encode_waveforms(pg_in.view(np.uint16), L.RADWARE_SIGCOMPRESS)
+        pe, po = torch.from_numpy(enc.data).pin_memory(), torch.from_numpy(enc.offsets).pin_memory()
+        s = wall(lambda: h.icpc_run_encoded_host(None, enc.codec, pe.data_ptr(), po.data_ptr(), enc.shift, 2, None, Be,
+                                                 host_out.data_ptr()), args.e2e_steps)
+        same = same and np.array_equal(np.nan_to_num(pg_out), np.nan_to_num(host_out.numpy()))
+        e2e_extra["e2e_encoded"] = {"value": world * Be * args.e2e_steps / s, "unit": "waveforms/s",
+                                    "h2d_bytes_per_step": enc.nbytes + (Be + 1) * 8, "bytes_per_event": enc.nbytes / Be,
+                                    "note": "RadwareSigcompress(-32768) encoded UInt16 waveforms in pinned host memory (the on-disk form "
+                                            "of LEGEND waveforms); decode_data (src/dsp_icpc.jl:313-314) on the device",
+                                    "rows_identical_to_e2e": bool(same)}
+
+    # ---- config 5: device-resident step + gather of every rank's output table on rank 0 inside the timed region ----
+    gather = None
+    if args.workload == "dsp_icpc" and not args.no_extra:
+        gsteps = min(args.steps, 10)
+        table = torch.empty((world, B, NCOL), dtype=torch.float64, device=dev) if rank == 0 else None
+        host_tab = [torch.empty((world * B, NCOL), dtype=torch.float64).pin_memory() for _ in range(2)] if rank == 0 else None
+
+        def gstep(k, compute=True):
+            if compute:
+                step(k)
+            if world > 1:
+                dist.gather(out, list(table.unbind(0)) if rank == 0 else None, dst=0)
+                src = table
+            else:
+                src = out
+            if rank == 0:
+                host_tab[k & 1].copy_(src.view(-1, NCOL), non_blocking=True)
+        ms_g, _ = timed(gstep, gsteps, 1)
+        ms_only, _ = timed(lambda k: gstep(k, False), gsteps, 1)
+        gather = {"value_with_gather": world * B * gsteps / (ms_g * 1e-3), "unit": "waveforms/s", "steps": gsteps,
+                  "gather_ms_per_step": ms_only / gsteps, "d2h_bytes_per_step_rank0": world * B * NCOL * 8,
+                  "how": "per step: kernels, NCCL gather of the 392-byte rows to rank 0 (NVLink; no-op at N=1), one D2H of the "
+                         "gathered table into pinned host memory; gather_ms_per_step is the gather + D2H timed alone"}
+
+    # ---- the other two single-GPU configurations of BASELINE.json, a few steps each ----
+    extra = []
+    peaks, peak_kind = _peaks()
+    if args.workload == "dsp_icpc" and not args.no_extra and args.groups is None:
+        xs = min(args.steps, 8)
+        P2 = L.resolve_icpc_params(cfg, tau, groups=L._abi.GROUP_PZTRAP_LEAN)
+        h.icpc_set_params(P2)
+        ms2, _ = timed(step, xs, 2)
+        h.icpc_set_params(P)
+        b2 = BYTES_IN + 5 * 8
+        extra.append({"workload": WL_NAME["pz_trap"], "value": world * B * xs / (ms2 * 1e-3), "unit": "waveforms/s", "ms_per_step": ms2 / xs,
+                      "roofline": {"frac": B * b2 / (ms2 * 1e-3 / xs) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_waveform": b2},
+                      "kernel": "icpc_prefix_kernel + icpc_extract_kernel (LGDSP_GROUP_PZTRAP_LEAN)"})
+        sp3, v3 = L.resolve_sweep_params(cfg, tau), sweep_variants(L)
+        out3 = torch.empty((B, 200), dtype=torch.float32, device=dev)
+        ms3, _ = timed(lambda k: h.sweep_run_device(sp3, pool[k % n_pool].data_ptr(), B, 8192, v3, out3.data_ptr()), xs, 2)
+        b3 = BYTES_IN + 200 * 4
+        extra.append({"workload": WL_NAME["trap_sweep"], "value": world * B * xs / (ms3 * 1e-3), "unit": "waveforms/s", "ms_per_step": ms3 / xs,
+                      "roofline": {"frac": B * b3 / (ms3 * 1e-3 / xs) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_waveform": b3},
+                      "kernel": "sweep_kernel"})
+
+    kernel_ms = None
+    if args.workload == "dsp_icpc" and args.path == "split" and not args.no_extra and rank == 0:
+        nprof = min(B, 16384)
+        ms4 = h.icpc_profile_device(pool[0].data_ptr(), nprof, 8192, out.data_ptr())
+        kernel_ms = {"events": nprof, "icpc_prefix_kernel": ms4[0], "icpc_extract_kernel": ms4[1], "icpc_cuspzac_kernel": ms4[2],
+                     "icpc_cuspzac_finish_kernel": ms4[3],
+                     "note": "one batch run serially with CUDA events between the kernels; in the timed steps the batches of "
+                             "three streams overlap"}
+
     if rank == 0:
-        peaks, peak_kind = _peaks()
         achieved = B * bytes_per_wf / (ms_max * 1e-3 / args.steps) / 1e9
+        kern = {"trap_sweep": "sweep_kernel", "sipm": "sipm_kernel"}.get(
+            args.workload, ("icpc_kernel (fused)" if args.path == "fused" else
+                            "split pipeline: icpc_prefix_kernel -> icpc_extract_kernel || icpc_cuspzac_kernel -> icpc_cuspzac_finish_kernel")
+            + (" x2 (presummed + windowed) + window_stats_kernel" if args.workload == "compressed" else ""))
         line = {
             "metric": "waveforms/sec for dsp_icpc (8192-sample)", "value": value, "unit": "waveforms/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name, "n_samples": {"compressed": [8192 // PRESUM, WDW_N], "sipm": SIPM_N}.get(args.workload, 8192),
                        "events_per_step_per_gpu": B, "resident_pool_batches": n_pool,
+                       "events_timed_per_gpu": B * args.steps, "resident_pool_events_per_gpu": B * n_pool,
+                       "size_note": "BASELINE configs[2] names 10 M events from a 4 M-event pool: the timed region here is "
+                                    f"{B * args.steps / 1e6:.1f} M events cycling a {B * n_pool / 1e6:.2f} M-event resident pool (same workload, "
+                                    "sample count and dtype; --steps 80 --pool 32 gives the named size)",
                        "dsp_config": "reference example config (test/test_dsp_icpc.jl:50-161), tie-free windows, tau=500us, default filter pars",
-                       "cuspzac": "direct FIR" if args.direct else "structured",
+                       "cuspzac": "direct FIR" if args.direct else "structured", "path": args.path,
                        "l2": f"inputs larger than L2: each step reads a different {B * bytes_in / 1e9:.1f} GB batch",
                        "parallelism": f"event-sharded x{world}, no data-path collective"},
             "clocks": clocks,
             "gpu_launches": int(launches),
-            "e2e": {"value": e2e_val, "unit": "waveforms/s", "h2d_bytes_per_step": Be * bytes_in,
-                    "d2h_bytes_per_step": Be * (out_bytes if args.workload != "compressed" else (2 * NCOL + 25) * 8), "events_per_step_per_gpu": Be, "checksum": checksum},
+            "e2e": {"value": e2e_val, "unit": "waveforms/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": Be * (out_bytes if args.workload != "compressed" else (2 * NCOL + 25) * 8),
+                    "events_per_step_per_gpu": Be, "steps": args.e2e_steps, "input": e2e_note, "checksum": checksum},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
                          "traffic": (NCU_DRAM_BYTES_PER_WF[args.workload] * B if args.workload in NCU_DRAM_BYTES_PER_WF
-                                     and args.groups is None else None),
-                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, scaled by events)",
-                         "peak_source": peak_kind,
-                         "algorithmic_bytes_per_waveform": bytes_per_wf,
-                         "kernel": "sweep_kernel" if args.workload == "trap_sweep" else "sipm_kernel" if args.workload == "sipm" else "icpc_kernel"
-                                   + (" x2 (presummed + windowed) + window_stats_kernel" if args.workload == "compressed" else "")},
+                                     and args.groups is None and args.path == "split" else None),
+                         "traffic_unit": "bytes per step (ncu dram__bytes_read.sum + dram__bytes_write.sum of the pipeline's kernels, "
+                                         "scaled by events)",
+                         "peak_source": peak_kind, "algorithmic_bytes_per_waveform": bytes_per_wf, "kernel": kern,
+                         "kernel_ms": kernel_ms},
         }
+        line.update(e2e_extra)
+        if gather:
+            line["value_with_gather"] = gather
+        if extra:
+            line["extra_workloads"] = extra
         if not args.no_cpu and world == 1:
-            from oracle import oracle as O
-            Po = L.resolve_icpc_params(cfg, tau, groups=groups or L._abi.GROUP_ALL, builders=O.OracleBuilders())
-            if args.workload == "compressed":
-                Po = compressed_setup(L, cfg, tau, O.OracleBuilders())
-            if args.workload == "sipm":
-                Po = sipm_setup(L, O.OracleBuilders())
-            so = L.resolve_sweep_params(cfg, tau, builders=O.OracleBuilders()) if args.workload == "trap_sweep" else None
             threads = host_threads()
-            n_s = args.cpu_sample or 128 * threads
-            v = cpu_port_throughput(L, O, Po, n_s, args.workload, variants, so, threads=threads)
-            line["cpu_baseline"] = {"value": v, "unit": "waveforms/s", "cores": threads, "kind": "port",
-                                    "sample": f"{n_s} waveforms of the same synthetic stream, CPU restatement of the reference "
-                                              "algorithm (oracle/, float64, direct-form CUSP/ZAC FIRs), OpenMP over events; not Julia"}
+            arm = CpuArm(L, args.workload, cfg, tau, groups, threads)
+            n_s = args.cpu_sample or {"pz_trap": 8192 * threads, "trap_sweep": 64 * threads}.get(args.workload, 512 * threads)
+            v = arm.throughput(n_s)
+            line["cpu_baseline"] = {"value": v, "unit": "waveforms/s", "cores": threads, "kind": arm.kind, "sample": arm.describe(n_s)}
         print(json.dumps(line))
     h.close()
     if world > 1:

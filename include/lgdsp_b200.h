@@ -511,6 +511,18 @@ int lgdsp_synth_generate_device(lgdsp_handle* h, const lgdsp_synth_params* sp, i
 int lgdsp_synth_generate_host(const lgdsp_synth_params* sp, int64_t first_event, int64_t n_events,
                               int64_t ld_samples, uint16_t* wf);
 
+/* ---- page-locked host memory: buffers allocated / registered here take the direct copy path of the host entry points (no
+ * staging through the handle's pinned ring); register once, reuse across calls, unregister before the memory is freed ---- */
+int lgdsp_host_alloc(void** p, int64_t bytes);
+int lgdsp_host_free(void* p);
+int lgdsp_host_register(void* p, int64_t bytes);
+int lgdsp_host_unregister(void* p);
+
+/* ---- measurement: device times [ms] of the four kernels of the split dsp_icpc pipeline on one batch run serially on the
+ * handle's stream: ms4 = prefix, extract, CUSP/ZAC select, CUSP/ZAC finish (bench.py's roofline shares) ---- */
+int lgdsp_icpc_profile_device(lgdsp_handle* h, const uint16_t* d_wf, int64_t n_events, int64_t ld_samples, double* d_out_rows,
+                              double* ms4);
+
 /* ---- timing helper: elapsed milliseconds of the last *_device call measured with CUDA events on the
  * handle's stream (valid after lgdsp_synchronize) ---- */
 double lgdsp_last_kernel_ms(const lgdsp_handle* h);

@@ -47,6 +47,11 @@ def load_library():
     L.lgdsp_zac_coeffs.argtypes = [C.c_double, i32, C.c_double, i32, C.c_double, _dp]
     L.lgdsp_icpc_set_params.argtypes = [vp, C.POINTER(_abi.IcpcParams)]
     L.lgdsp_icpc_set_path.argtypes = [vp, i32, i64, i32]
+    L.lgdsp_icpc_profile_device.argtypes = [vp, vp, i64, i64, vp, _dp]
+    L.lgdsp_host_alloc.argtypes = [C.POINTER(vp), i64]
+    L.lgdsp_host_free.argtypes = [vp]
+    L.lgdsp_host_register.argtypes = [vp, i64]
+    L.lgdsp_host_unregister.argtypes = [vp]
     L.lgdsp_icpc_run.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i64, i64, vp]
     L.lgdsp_icpc_run_device.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i64, i64, vp]
     L.lgdsp_icpc_run_ext.argtypes = [vp, C.POINTER(_abi.IcpcParams), vp, i32, vp, i64, i64, vp]
@@ -94,7 +99,8 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "lgdsp_version", "lgdsp_last_error", "lgdsp_create", "lgdsp_destroy", "lgdsp_launch_count", "lgdsp_synchronize",
     "lgdsp_lsq_fit_matrix", "lgdsp_sg_coeffs", "lgdsp_cusp_coeffs", "lgdsp_zac_coeffs",
-    "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params", "lgdsp_icpc_set_path", "lgdsp_icpc_run_ext", "lgdsp_icpc_run_ext_device",
+    "lgdsp_icpc_run", "lgdsp_icpc_run_device", "lgdsp_icpc_set_params", "lgdsp_icpc_set_path", "lgdsp_icpc_profile_device", "lgdsp_host_alloc", "lgdsp_host_free", "lgdsp_host_register",
+    "lgdsp_host_unregister", "lgdsp_icpc_run_ext", "lgdsp_icpc_run_ext_device",
     "lgdsp_codec_max_encoded_bytes", "lgdsp_codec_encode_host", "lgdsp_decode_data", "lgdsp_decode_data_device", "lgdsp_icpc_run_encoded", "lgdsp_icpc_compressed_run_encoded",
     "lgdsp_window_stats_run", "lgdsp_window_stats_run_device", "lgdsp_sipm_run", "lgdsp_sipm_run_device",
     "lgdsp_sipm_list_pointers_device", "lgdsp_sipm_list_gather_device", "lgdsp_thresholdstats", "lgdsp_intersect_maximum", "lgdsp_multi_intersect_run", "lgdsp_multi_intersect_run_device", "lgdsp_icpc_compressed_run", "lgdsp_icpc_compressed_run_device",
@@ -144,6 +150,12 @@ class Handle:
 
     def synchronize(self):
         self._check(self._lib.lgdsp_synchronize(self._h))
+
+    def icpc_profile_device(self, d_wf_ptr, n_events, ld, d_out_ptr):
+        """device ms of (prefix, extract, CUSP/ZAC select, CUSP/ZAC finish) on one batch run serially"""
+        ms = (C.c_double * 4)()
+        self._check(self._lib.lgdsp_icpc_profile_device(self._h, C.c_void_p(d_wf_ptr), int(n_events), int(ld), C.c_void_p(d_out_ptr), ms))
+        return list(ms)
 
     def set_icpc_path(self, path, batch=0, streams=0):
         """'split' (default: prefix / extract / CUSP-ZAC kernels coupled through an L2-resident ring) or 'fused' (icpc_kernel)"""

@@ -560,7 +560,7 @@ static int icpc_dispatch(lgdsp_handle* h, const IcpcDev& D, const void* d_wf, in
                                 h->d_saux + (size_t)si * (size_t)B * (size_t)icpc_split_aux_doubles(),
                                 h->d_scz + (size_t)si * (size_t)B * (size_t)icpc_split_cz_doubles(),
                                 h->split_bps, h->sm_count, st,
-                                h->split_par ? h->s_cz[si] : nullptr, h->ev_pre[si], h->ev_cz[si]);
+                                h->split_par ? h->s_cz[si] : nullptr, h->ev_pre[si], h->ev_cz[si], nullptr);
         CK(cudaGetLastError());
         h->launches += cz ? (D.direct ? 3 : 4) : 2;
     }
@@ -621,6 +621,59 @@ static int icpc_run_device_impl(lgdsp_handle* h, const lgdsp_icpc_params* p, con
     h->timed = true;
     return LGDSP_OK;
 }
+
+// per-kernel device times of the split pipeline on ONE batch run serially (prefix, extract, CUSP/ZAC select, CUSP/ZAC finish)
+int lgdsp_icpc_profile_device(lgdsp_handle* h, const uint16_t* d_wf, int64_t n_events, int64_t ld_samples, double* d_out_rows,
+                              double* ms4)
+{
+    if (!h || !ms4) return LGDSP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (!h->have_icpc) return fail(h, LGDSP_ERR_INVALID_ARG, "no parameters set");
+    int rc = check_wf(h, d_wf, n_events, ld_samples, h->icpc.n, true, 2);
+    if (rc) return rc;
+    if (n_events <= 0 || !d_out_rows) return fail(h, LGDSP_ERR_INVALID_ARG, "nothing to profile");
+    // scratch for the whole batch in one piece
+    const int64_t keepB = h->split_batch;
+    const int keepS = h->split_streams;
+    h->split_batch = n_events; h->split_streams = 1;
+    IcpcDev D = h->icpc;
+    D.phase_cycles = nullptr;
+    rc = icpc_dispatch(h, D, d_wf, 2, n_events, ld_samples, nullptr, 1, 1.0, d_out_rows);   // sizes the scratch, warms up
+    h->split_batch = keepB; h->split_streams = keepS;
+    if (rc) return rc;
+    cudaEvent_t marks[5];
+    for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&marks[i]));
+    icpc_split_launch_batch(D, d_wf, 2, n_events, ld_samples, nullptr, 1, 1.0, d_out_rows, h->d_tt, h->d_saux, h->d_scz, h->split_bps,
+                            h->sm_count, h->stream, nullptr, h->ev_pre[0], h->ev_cz[0], marks);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    const bool cz = (D.groups & LGDSP_GROUP_CUSPZAC) != 0;
+    float t;
+    CK(cudaEventElapsedTime(&t, marks[0], marks[1])); ms4[0] = t;
+    CK(cudaEventElapsedTime(&t, marks[1], marks[2])); ms4[1] = t;
+    ms4[2] = ms4[3] = 0.0;
+    if (cz) {
+        CK(cudaEventElapsedTime(&t, marks[2], marks[3])); ms4[2] = t;
+        if (!D.direct) { CK(cudaEventElapsedTime(&t, marks[3], marks[4])); ms4[3] = t; }
+    }
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(marks[i]);
+    h->launches += cz ? 4 : 2;
+    return LGDSP_OK;
+}
+
+/* pinned host memory for callers that want the direct (unstaged) copy path of the host entry points */
+int lgdsp_host_alloc(void** p, int64_t bytes)
+{
+    if (!p || bytes < 0) return LGDSP_ERR_INVALID_ARG;
+    return cudaHostAlloc(p, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? LGDSP_OK : LGDSP_ERR_OOM;
+}
+int lgdsp_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? LGDSP_OK : LGDSP_ERR_CUDA; }
+int lgdsp_host_register(void* p, int64_t bytes)
+{
+    if (!p || bytes <= 0) return LGDSP_ERR_INVALID_ARG;
+    return cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault) == cudaSuccess ? LGDSP_OK : LGDSP_ERR_CUDA;
+}
+int lgdsp_host_unregister(void* p) { return cudaHostUnregister(p) == cudaSuccess ? LGDSP_OK : LGDSP_ERR_CUDA; }
 
 int lgdsp_icpc_run_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const uint16_t* d_wf, int64_t n_events,
                           int64_t ld_samples, double* d_out_rows)

@@ -2448,8 +2448,10 @@ long long icpc_split_cz_doubles() { return CZG_LEN; }
 void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld,
                              const double* d_bl_ext, long long bl_stride, double bl_div, double* d_rows, double* d_tt, double* d_aux,
                              double* d_cz, const int* bps3, int sm_count, cudaStream_t stream, cudaStream_t stream_cz,
-                             cudaEvent_t ev_prefix, cudaEvent_t ev_cz)
+                             cudaEvent_t ev_prefix, cudaEvent_t ev_cz, cudaEvent_t* marks)
 {
+    // marks != NULL (profiling): everything on `stream`, an event after every kernel (marks[0] in front of the first)
+    if (marks) { stream_cz = nullptr; cudaEventRecord(marks[0], stream); }
     const bool cz = (P.groups & LGDSP_GROUP_CUSPZAC) != 0;
     auto grid = [&](int k) { const long long cap = (long long)sm_count * bps3[k]; return (int)(n_events < cap ? n_events : cap); };
     if (sample_bytes == 4)
@@ -2458,10 +2460,13 @@ void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_byte
     else
         icpc_prefix_kernel<uint16_t><<<grid(0), NT, K1_TOTAL, stream>>>(P, static_cast<const uint16_t*>(d_wf), n_events, ld, d_bl_ext,
                                                                         bl_stride, bl_div, d_tt, d_aux, d_rows);
+    if (marks) cudaEventRecord(marks[1], stream);
     const int fin_grid = (int)((n_events + K4_WARPS - 1) / K4_WARPS);
     auto launch_cz = [&](cudaStream_t st) {
         icpc_cuspzac_kernel<<<grid(2), NT, K3_TOTAL, st>>>(P, d_tt, d_aux, n_events, d_cz, d_rows);
+        if (marks) cudaEventRecord(marks[3], st);
         if (!P.direct) icpc_cuspzac_finish_kernel<<<fin_grid, K4_WARPS * 32, 0, st>>>(P, d_tt, d_cz, n_events, d_rows);
+        if (marks) cudaEventRecord(marks[4], st);
     };
     // the two consumers only depend on the prefix kernel: with a second stream their tails overlap
     const bool par = cz && stream_cz != nullptr && stream_cz != stream;
@@ -2472,6 +2477,7 @@ void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_byte
         cudaEventRecord(ev_cz, stream_cz);
     }
     icpc_extract_kernel<<<grid(1), NT2, K2_TOTAL, stream>>>(P, d_tt, d_aux, n_events, cz ? 0 : 1, d_rows);
+    if (marks) cudaEventRecord(marks[2], stream);
     if (cz && !par) launch_cz(stream);
     if (par) cudaStreamWaitEvent(stream, ev_cz, 0);   // the ring slot is reused behind both consumers
 }

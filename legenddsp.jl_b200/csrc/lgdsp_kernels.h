@@ -21,7 +21,7 @@ long long icpc_split_cz_doubles();
 void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld,
                              const double* d_bl_ext, long long bl_stride, double bl_div, double* d_rows, double* d_tt, double* d_aux,
                              double* d_cz, const int* bps3, int sm_count, cudaStream_t stream, cudaStream_t stream_cz,
-                             cudaEvent_t ev_prefix, cudaEvent_t ev_cz);
+                             cudaEvent_t ev_prefix, cudaEvent_t ev_cz, cudaEvent_t* marks);
 // window w is shifted by -d_shift[e * shift_stride] when d_shift != NULL and bit w of shift_mask is set
 void window_stats_launch(const void* d_wf, int sample_bytes, long long n_events, long long ld, double t_first, double dt,
                          const double* d_shift, long long shift_stride, unsigned shift_mask, const int* d_win, int n_windows,
