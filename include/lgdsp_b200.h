@@ -392,7 +392,10 @@ int lgdsp_icpc_compressed_run_encoded(lgdsp_handle* h, const lgdsp_icpc_params* 
  * LGDSP_MAX_SAMPLES/2), with an optional per-event EXTERNAL baseline: when baseline != NULL the waveform is shifted by
  * -baseline[e] instead of by its own bl_window mean -- the windowed waveform of the compressed format is shifted by the
  * presummed waveform's baseline / presum_rate (:349-350).  blmean..bloffset still report the statistics of the
- * waveform's own bl_window. */
+ * waveform's own bl_window.
+ * Range of 32-bit samples: the prefix sums are exact uint32 arithmetic, so a waveform must sum to < 2^32 (presummed 16-bit
+ * traces of <= 4096 samples do up to a mean of 2^20, i.e. any presum rate <= 16).  An event beyond that gets a row of NaN
+ * (all 49 columns; sweep outputs likewise) instead of wrapped sums. */
 int lgdsp_icpc_run_ext(lgdsp_handle* h, const lgdsp_icpc_params* p, const void* wf, int32_t sample_bytes,
                        const double* baseline, int64_t n_events, int64_t ld_samples, double* out_rows);
 int lgdsp_icpc_run_ext_device(lgdsp_handle* h, const lgdsp_icpc_params* p, const void* d_wf, int32_t sample_bytes,

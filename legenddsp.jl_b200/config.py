@@ -372,7 +372,7 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
     which the 60 ns / 100 ns filters of the full chain have no samples) resolve."""
     if builders is None:
         builders = LibBuilders()
-    if role not in ("full", "pre", "wdw", "puls"):
+    if role not in ("full", "pre", "wdw", "puls", "decay"):
         raise ValueError(f"unknown role {role!r}")
     if role == "pre":
         groups = _abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_TRAPS | _abi.GROUP_CUSPZAC | _abi.GROUP_INTRACE
@@ -380,6 +380,9 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
         groups = _abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_QDRIFT | _abi.GROUP_CURRENT
     elif role == "puls":
         groups = _abi.GROUP_BASE | _abi.GROUP_TIMING | _abi.GROUP_TRAPS
+    elif role == "decay":    # dsp_decay_times (src/dsp_decaytime.jl:11-25): baseline and tail windows only
+        groups = _abi.GROUP_BASE
+    lite = role in ("puls", "decay")    # everything the full chain adds is a placeholder
     dummy_trap = _abi.Trap(1, 0, 1, 0)
     kw = cfg.kwargs_pars
     P = _abi.IcpcParams()
@@ -421,13 +424,13 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
 
     # get_t0: src/dsp_routines.jl:9-25
     fp = kw["t0_flt_pars"]
-    if role in ("pre", "puls"):
+    if role == "pre" or lite:
         P.t0_trap = P.t0inv_trap = dummy_trap     # t0 / t0_inv come from the windowed waveform (:378, :458)
     else:
         P.t0_trap = _trap(fp[0], fp[1], step, fp[2])
         P.t0inv_trap = _trap(ns(40.0), ns(100.0), step, ns(2000.0))   # default flt_pars, src/dsp_icpc.jl:207
     # the presummed pass has no t0 (its trapezoid is a placeholder): a threshold nothing reaches keeps the crossing search idle
-    P.t0_threshold = 1e300 if role in ("pre", "puls") else float(cfg.t0_threshold)
+    P.t0_threshold = 1e300 if (role == "pre" or lite) else float(cfg.t0_threshold)
     P.t0_min_n = _min_n(kw["t0_mintot"], step)
     P.tx_min_n = _min_n(kw["tx_mintot"], step)
     for i, f in enumerate((0.1, 0.5, 0.8, 0.9, 0.99)):
@@ -438,11 +441,11 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
     P.qdrift_last_ns = cfg.qdrift_int_length[2].ns()
     P.lq_first_ns = cfg.lq_int_length[0].ns()
     P.lq_last_ns = cfg.lq_int_length[2].ns()
-    if role in ("pre", "puls"):   # Q-drift is evaluated on the windowed waveform only (:391-394)
+    if role == "pre" or lite:   # Q-drift is evaluated on the windowed waveform only (:391-394)
         _fill_dni(P.int_dni, 1, step * 2.0, step, builders)
     else:
         _fill_dni(P.int_dni, int(kw["int_interpolation_order"]), kw["int_interpolation_length"], step, builders)
-    if role in ("wdw", "puls"):   # the SignalEstimator of the energies runs on the presummed waveform only (:407-428)
+    if role == "wdw" or lite:   # the SignalEstimator of the energies runs on the presummed waveform only (:407-428)
         _fill_dni(P.sig_dni, 1, step * 2.0, step, builders)
     else:
         _fill_dni(P.sig_dni, int(kw["sig_interpolation_order"]), kw["sig_interpolation_length"], step, builders)
@@ -452,7 +455,7 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
     cusp_rt, cusp_ft = get_fltpars(pars_filter, "cusp", cfg)
     zac_rt, zac_ft = get_fltpars(pars_filter, "zac", cfg)
     sg_wl = get_fltpars(pars_filter, "sg", cfg)
-    if role == "wdw":
+    if role in ("wdw", "decay"):
         P.trap_10410 = P.trap_535 = P.trap_313 = P.trap_e = dummy_trap
     elif role == "puls":
         P.trap_10410 = _trap(us(10.0), us(4.0), step)          # src/dsp_puls.jl:56
@@ -472,7 +475,7 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
 
     # CUSP / ZAC: src/dsp_icpc.jl:87-90,98-99,167,174
     tau_off = us(10000000.0)
-    if role in ("wdw", "puls"):
+    if role == "wdw" or lite:
         for cz in (P.cusp, P.zac):
             cz.n_taps, cz.flat, cz.sigma, cz.tau, cz.beta = 4, 0, 1.0, 1.0, 1.0
     else:
@@ -485,7 +488,7 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
 
     # currents: src/dsp_icpc.jl:181-186
     deg = int(cfg.sg_flt_degree)
-    if role == "puls":
+    if lite:
         for k in range(3):
             _fill_sg(P.sg[k], step * 5.0, deg, step, policy, builders)
             P.cur_from[k], P.cur_until[k] = 0, n - P.sg[k].n_taps
@@ -513,7 +516,7 @@ def resolve_icpc_params(cfg: DSPConfig, tau: Q, pars_filter: Optional[Dict[str, 
     P.intrace_min_n = _min_n(kw["intrace_mintot"], step)
     first_sg = t_first + step * float(P.sg[0].offset)
     n_sg = n - P.sg[0].n_taps + 1
-    if role in ("wdw", "puls"):
+    if role == "wdw" or lite:
         a, b = 0, min(n_sg - 1, 15)       # in-trace pile-up is evaluated on the presummed waveform (:440)
     else:
         a = _sub_over_step(cfg.bl_window[0] + first_sg, first_sg, step)   # leftendpoint + first(time), :75
@@ -682,7 +685,7 @@ def params_summary(P: _abi.IcpcParams) -> Dict[str, Any]:
     return {
         "n_samples": P.n_samples, "dt_ns": P.dt_ns, "sat": (P.sat_low, P.sat_high),
         "bl": (P.bl_from, P.bl_until), "tail": (P.tail_from, P.tail_until),
-        "RC": 1.0 / P.pz_km1, "t0_trap": P.t0_trap.as_tuple(), "t0_min_n": P.t0_min_n,
+        "RC": (1.0 / P.pz_km1) if P.pz_km1 != 0 else float("inf"), "t0_trap": P.t0_trap.as_tuple(), "t0_min_n": P.t0_min_n,
         "tx_min_n": P.tx_min_n, "intrace_min_n": P.intrace_min_n,
         "trap_10410": P.trap_10410.as_tuple(), "trap_535": P.trap_535.as_tuple(),
         "trap_313": P.trap_313.as_tuple(), "trap_e": P.trap_e.as_tuple(),

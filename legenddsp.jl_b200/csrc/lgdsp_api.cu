@@ -461,20 +461,21 @@ static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p, int slot = 
     D.intr_from = p->intrace_bl_from; D.intr_until = p->intrace_bl_until;
     D.intr_inv_n = 1.0 / (double)(p->intrace_bl_until - p->intrace_bl_from + 1);
     // CUSP / ZAC
+    // (all validation first: the device tables of the handle are only touched once the whole parameter set is accepted, so
+    // a rejected set leaves the previous one -- descriptors AND tables -- intact)
     const lgdsp_cuspzac* cz[2] = {&p->cusp, &p->zac};
     double* dst[2] = {t_cusp, t_zac};
-    std::vector<double> g(LGDSP_MAX_FIR + 1);
+    std::vector<double> g[2];
     for (int f = 0; f < 2; ++f) {
         const int L = cz[f]->n_taps;
         if (L < 4 || L > LGDSP_MAX_FIR || n - L + 1 < nw_sig)
             return fail(h, LGDSP_ERR_INVALID_ARG, "%s: %d taps do not fit (need >= %d outputs)", f ? "zac" : "cusp", L, nw_sig);
         // differenced taps on the prefix sum TT: out[j] = sum_{k=0}^{L} g[k] TT[j+L-k]
         const double* c = cz[f]->coeffs;
-        g[0] = c[0];
-        for (int k = 1; k < L; ++k) g[k] = c[k] - c[k - 1];
-        g[L] = -c[L - 1];
-        CK(cudaMemcpyAsync(dst[f], g.data(), sizeof(double) * (L + 1), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        g[f].resize(L + 1);
+        g[f][0] = c[0];
+        for (int k = 1; k < L; ++k) g[f][k] = c[k] - c[k - 1];
+        g[f][L] = -c[L - 1];
     }
     D.cusp_L = p->cusp.n_taps; D.zac_L = p->zac.n_taps;
     if (!D.direct && (D.groups & LGDSP_GROUP_CUSPZAC)) {
@@ -490,6 +491,7 @@ static int icpc_prepare(lgdsp_handle* h, const lgdsp_icpc_params* p, int slot = 
         }
         if (!ok) return fail(h, LGDSP_ERR_UNSUPPORTED, "CUSP/ZAC structured evaluation: %s (set cuspzac_direct = 1)", why.c_str());
     }
+    for (int f = 0; f < 2; ++f) CK(cudaMemcpyAsync(dst[f], g[f].data(), sizeof(double) * g[f].size(), cudaMemcpyHostToDevice, h->stream));
     std::vector<double> A(2 * LGDSP_MAX_DNI * 4, 0.0);
     memcpy(A.data(), p->int_dni.A, sizeof(double) * LGDSP_MAX_DNI * 4);
     memcpy(A.data() + LGDSP_MAX_DNI * 4, p->sig_dni.A, sizeof(double) * LGDSP_MAX_DNI * 4);

@@ -881,6 +881,23 @@ __device__ __noinline__ unsigned long long mask_chunk(const double* tp, double t
     return m;
 }
 
+// 32-bit samples: does the waveform sum to more than 32 bits (the uint32 prefix sums P would wrap)?  Block-uniform result.
+// mx = block-wide maximum sample: the exact 64-bit sum is only formed when mx * n could reach 2^32; scratch = NWARP doubles
+// (the sums are integers < 2^53: exact in double, in any order).  Contains two barriers on the slow path.
+template <typename SAMPLE>
+__device__ __forceinline__ bool sum_exceeds_u32(const SAMPLE* xp, int cvalid, uint32_t mx, int n, double* scratch)
+{
+    if (sizeof(SAMPLE) != 4 || (unsigned long long)mx * (unsigned long long)n <= 0xFFFFFFFFull) return false;
+    unsigned long long c64 = 0;
+    for (int k = 0; k < cvalid; ++k) c64 += (unsigned long long)xp[k];
+    const double w = wsum_d((double)c64);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = w;
+    __syncthreads();
+    const double total = red_sum(scratch, 0);
+    __syncthreads();
+    return total > 4294967295.0;
+}
+
 // SAMPLE = uint16_t (raw FADC samples) or uint32_t (presummed waveforms of dsp_icpc_compressed, n <= 4096).
 // bl_ext != NULL: the baseline mean of event e is bl_ext[e] instead of the bl_window mean (windowed waveforms of
 // dsp_icpc_compressed are shifted by blmean_presummed / presum_rate, src/dsp_icpc.jl:350).
@@ -1110,6 +1127,8 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
             __syncthreads();
         }
 
+        // (32-bit samples whose sum leaves 32 bits: the row is NaN instead of silently wrong)
+        const bool wrapped = sum_exceeds_u32<SAMPLE>(xp, cvalid, mx, n, red + R_TLS * NWARP);
         // blmean = mean_Y = sum_Y * inv_n exactly as signalstats computes it (the other baseline statistics: P5)
         const double m = bl_ext ? div_rn(bl_ext[e * bl_stride], bl_div) : mul_rn(red_sum(red, R_BLS), P.bl_inv_n);
         const double e_max = (double)mx - m, e_min = (double)mn - m;
@@ -2000,7 +2019,7 @@ icpc_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, lo
         __syncthreads();   // ---- B8 ----
         LGDSP_PHASE(6);
         SECT(28);
-        if (tid < LGDSP_NCOL) rows[e * LGDSP_NCOL + tid] = row[tid];
+        if (tid < LGDSP_NCOL) rows[e * LGDSP_NCOL + tid] = wrapped ? CUDART_NAN : row[tid];
         // (the next iteration's first barrier orders the reuse of row/stash/masks/scr/red)
     }
     if (pc_on) {
@@ -2119,6 +2138,14 @@ sweep_kernel(const __grid_constant__ SweepDev P, const SAMPLE* __restrict__ wf, 
         uint32_t* ured = reinterpret_cast<uint32_t*>(ibuf + 32);
         if (lane == 31) ured[wid] = incl;
         mask[tid] = 0u;
+        // 32-bit samples: the uint32 prefix sums are exact only while the waveform sums to < 2^32; beyond that the event's
+        // outputs are NaN (the sum of the chunk sums is exact in double)
+        bool wrapped = false;
+        if (sizeof(SAMPLE) == 4) {
+            unsigned long long c64 = 0;
+            for (int k = 0; k < cvalid; ++k) c64 += (unsigned long long)xp[k];
+            wrapped = block_sum1((double)c64, red, tid) > 4294967295.0;
+        }
         const double blSd = block_sum1((double)blS, red, tid);
         // sum_i i*x over the baseline window (for blslope of the aux outputs; exact in double)
         const double blSXd = aux ? block_sum1((double)i0 * (double)blS + (double)blSK, red, tid) : 0.0;
@@ -2310,10 +2337,10 @@ sweep_kernel(const __grid_constant__ SweepDev P, const SAMPLE* __restrict__ wf, 
         __syncthreads();
         if (P.out_f64) {
             double* o = reinterpret_cast<double*>(out);
-            for (int v = tid; v < P.nvar; v += NT) o[e * (long long)P.nvar + v] = obuf[v];
+            for (int v = tid; v < P.nvar; v += NT) o[e * (long long)P.nvar + v] = wrapped ? CUDART_NAN : obuf[v];
         } else {
             float* o = reinterpret_cast<float*>(out);
-            for (int v = tid; v < P.nvar; v += NT) o[e * (long long)P.nvar + v] = (float)obuf[v];
+            for (int v = tid; v < P.nvar; v += NT) o[e * (long long)P.nvar + v] = wrapped ? CUDART_NAN_F : (float)obuf[v];
         }
         __syncthreads();
     }
@@ -2465,7 +2492,7 @@ void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_byte
     auto launch_cz = [&](cudaStream_t st) {
         icpc_cuspzac_kernel<<<grid(2), NT, K3_TOTAL, st>>>(P, d_tt, d_aux, n_events, d_cz, d_rows);
         if (marks) cudaEventRecord(marks[3], st);
-        if (!P.direct) icpc_cuspzac_finish_kernel<<<fin_grid, K4_WARPS * 32, 0, st>>>(P, d_tt, d_cz, n_events, d_rows);
+        if (!P.direct) icpc_cuspzac_finish_kernel<<<fin_grid, K4_WARPS * 32, 0, st>>>(P, d_tt, d_aux, d_cz, n_events, d_rows);
         if (marks) cudaEventRecord(marks[4], st);
     };
     // the two consumers only depend on the prefix kernel: with a second stream their tails overlap

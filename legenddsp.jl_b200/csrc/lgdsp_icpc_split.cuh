@@ -18,7 +18,7 @@
 
 constexpr int TTG_LEN = TT_LEN;     // doubles per event slot of the global prefix-sum ring
 constexpr int AUX_LEN = 16;         // doubles per event: values handed from the prefix kernel to the consumers
-enum { AX_M = 0, AX_EMAX = 1, AX_YMAX = 2, AX_THR = 3 /* 5 */, AX_POS = 8 /* 5 */ };
+enum { AX_M = 0, AX_EMAX = 1, AX_YMAX = 2, AX_THR = 3 /* 5 */, AX_POS = 8 /* 5 */, AX_BAD = 13 /* 1: sample sum beyond 32 bits */ };
 
 // ---- prefix kernel: shared memory ----
 enum { K1R_BLS = 0, K1R_BLSS, K1R_BLSX, K1R_MX /* + K1R_MN: 4 x NWARP uint32 */, K1R_MN, K1R_SLEN, K1R_SS, K1R_SQ,
@@ -209,6 +209,9 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
             __syncthreads();   // the partials share their storage with the threshold masks written below
         }
 
+        // 32-bit samples: the prefix sums are exact uint32 only while the waveform sums to < 2^32 (any 16-bit trace does; a
+        // presummed trace does up to a mean of 2^20).  Beyond that the event's row is NaN instead of silently wrong.
+        const bool wrapped = sum_exceeds_u32<SAMPLE>(xp, cvalid, mx, n, red + K1R_TLS * NWARP);
         const double m = bl_ext ? div_rn(bl_ext[e * bl_stride], bl_div) : mul_rn(red_sum(red, K1R_BLS), P.bl_inv_n);
         const double e_max = (double)mx - m, e_min = (double)mn - m;
         double thr[5];
@@ -407,22 +410,23 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
                 const double sXY = lane == 0 ? t_first * blS + dt * blSX : tlSX;
                 const Stats st = stats_finalize(lane == 0 ? P.bl_inv_n : P.tail_inv_n, lane == 0 ? P.bl_sX : P.tail_sX,
                                                 lane == 0 ? P.bl_sXX : P.tail_sXX, sY, sYY, sXY);
+                const double bad = wrapped ? CUDART_NAN : 0.0;   // (x + NaN = NaN)
                 if (lane == 0) {
-                    ro[LGDSP_COL_blmean] = st.mean; ro[LGDSP_COL_blsigma] = st.sigma;
-                    ro[LGDSP_COL_blslope] = st.slope; ro[LGDSP_COL_bloffset] = st.offset;
-                    ro[LGDSP_COL_qc_label] = -1.0;
-                    ro[LGDSP_COL_e_max] = e_max; ro[LGDSP_COL_e_min] = e_min;
-                    ro[LGDSP_COL_n_sat_low] = (double)nlow; ro[LGDSP_COL_n_sat_high] = (double)nhigh;
-                    ro[LGDSP_COL_n_sat_low_cons] = (double)cons_low; ro[LGDSP_COL_n_sat_high_cons] = (double)cons_high;
+                    ro[LGDSP_COL_blmean] = st.mean + bad; ro[LGDSP_COL_blsigma] = st.sigma + bad;
+                    ro[LGDSP_COL_blslope] = st.slope + bad; ro[LGDSP_COL_bloffset] = st.offset + bad;
+                    ro[LGDSP_COL_qc_label] = -1.0 + bad;
+                    ro[LGDSP_COL_e_max] = e_max + bad; ro[LGDSP_COL_e_min] = e_min + bad;
+                    ro[LGDSP_COL_n_sat_low] = (double)nlow + bad; ro[LGDSP_COL_n_sat_high] = (double)nhigh + bad;
+                    ro[LGDSP_COL_n_sat_low_cons] = (double)cons_low + bad; ro[LGDSP_COL_n_sat_high_cons] = (double)cons_high + bad;
                 } else {
                     const bool ok = tlbad == 0.0;
-                    ro[LGDSP_COL_tail_mean] = ok ? st.mean : 0.0; ro[LGDSP_COL_tail_sigma] = ok ? st.sigma : 0.0;
-                    ro[LGDSP_COL_tail_tau] = ok ? div_rn(-1.0, st.slope) : 0.0;
+                    ro[LGDSP_COL_tail_mean] = (ok ? st.mean : 0.0) + bad; ro[LGDSP_COL_tail_sigma] = (ok ? st.sigma : 0.0) + bad;
+                    ro[LGDSP_COL_tail_tau] = (ok ? div_rn(-1.0, st.slope) : 0.0) + bad;
                 }
             }
         } else if (wid == 6) {
             const double Ymax = red_max(red, K1R_YMAX);
-            if (lane == 0) { ax[AX_M] = m; ax[AX_EMAX] = e_max; ax[AX_YMAX] = Ymax; }
+            if (lane == 0) { ax[AX_M] = m; ax[AX_EMAX] = e_max; ax[AX_YMAX] = Ymax; ax[AX_BAD] = wrapped ? 1.0 : 0.0; }
         }
         __syncthreads();   // ---- B3: reduction slots / masks may be reused ----
     }
@@ -955,7 +959,7 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                                (tid >= LGDSP_COL_tail_tau && tid <= LGDSP_COL_e_min) || tid >= LGDSP_COL_n_sat_low;
             const bool k3col = tid == LGDSP_COL_e_cusp || tid == LGDSP_COL_e_zac || tid == LGDSP_COL_e_cusp_max ||
                                tid == LGDSP_COL_e_zac_max || tid == LGDSP_COL_t_cusp_max || tid == LGDSP_COL_t_zac_max;
-            if (!k1col && (!k3col || write_cz_zeros)) rows[e * LGDSP_NCOL + tid] = row[tid];
+            if (!k1col && (!k3col || write_cz_zeros)) rows[e * LGDSP_NCOL + tid] = aux[AX_BAD] != 0.0 ? CUDART_NAN : row[tid];
         }
         // (phase B of the next event zeroes `row` behind its first barrier: every thread has stored its column by then)
     }
@@ -1177,10 +1181,11 @@ icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                 red_argmax(red, f ? K3R_CZMAX1 : K3R_CZMAX0, f ? K3R_CZARG1 : K3R_CZARG0, cm, ca);
                 if (lane == 0) {
                     const int L = f ? P.zac_L : P.cusp_L;
+                    const double bad = auxg[e * AUX_LEN + AX_BAD] != 0.0 ? CUDART_NAN : 0.0;
                     double* ro = rows + e * LGDSP_NCOL;
-                    ro[f ? LGDSP_COL_e_zac_max : LGDSP_COL_e_cusp_max] = cm;
-                    ro[f ? LGDSP_COL_t_zac_max : LGDSP_COL_t_cusp_max] = t_first + (double)(ca + L - 1) * dt;
-                    ro[f ? LGDSP_COL_e_zac : LGDSP_COL_e_cusp] = v;
+                    ro[f ? LGDSP_COL_e_zac_max : LGDSP_COL_e_cusp_max] = cm + bad;
+                    ro[f ? LGDSP_COL_t_zac_max : LGDSP_COL_t_cusp_max] = t_first + (double)(ca + L - 1) * dt + bad;
+                    ro[f ? LGDSP_COL_e_zac : LGDSP_COL_e_cusp] = v + bad;
                 }
             }
             __syncthreads();
@@ -1217,8 +1222,8 @@ icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
 // finish: one warp per event, one lane per candidate chunk
 constexpr int K4_WARPS = 4;
 __global__ void __launch_bounds__(K4_WARPS * 32)
-icpc_cuspzac_finish_kernel(const __grid_constant__ IcpcDev P, const double* __restrict__ ttg, const double* __restrict__ czg,
-                           long long n_events, double* __restrict__ rows)
+icpc_cuspzac_finish_kernel(const __grid_constant__ IcpcDev P, const double* __restrict__ ttg, const double* __restrict__ auxg,
+                           const double* __restrict__ czg, long long n_events, double* __restrict__ rows)
 {
     __shared__ double stash_s[K4_WARPS][2][LGDSP_MAX_DNI];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1282,7 +1287,11 @@ icpc_cuspzac_finish_kernel(const __grid_constant__ IcpcDev P, const double* __re
         czmax[1] = wargmax_d(czmax[1], czarg[1]);
         const double vc = dni_eval_warp(A_sig, nw, P.sig_dni.m, stash, pk_p[0] - (double)pk_from[0], lane);
         const double vz = dni_eval_warp(A_sig, nw, P.sig_dni.m, stash + LGDSP_MAX_DNI, pk_p[1] - (double)pk_from[1], lane);
-        if (lane == 0) {
+        if (lane == 0 && auxg[e * AUX_LEN + AX_BAD] != 0.0) {
+            double* ro = rows + e * LGDSP_NCOL;
+            ro[LGDSP_COL_e_cusp_max] = ro[LGDSP_COL_t_cusp_max] = ro[LGDSP_COL_e_cusp] = CUDART_NAN;
+            ro[LGDSP_COL_e_zac_max] = ro[LGDSP_COL_t_zac_max] = ro[LGDSP_COL_e_zac] = CUDART_NAN;
+        } else if (lane == 0) {
             double* ro = rows + e * LGDSP_NCOL;
             ro[LGDSP_COL_e_cusp_max] = czmax[0];
             ro[LGDSP_COL_t_cusp_max] = P.t_first + (double)(czarg[0] + P.cusp_L - 1) * P.dt;

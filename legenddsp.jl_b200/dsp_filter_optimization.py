@@ -37,9 +37,10 @@ def dsp_trap_rt_optimization(wvfs, config: DSPConfig, τ: Q, *, ft: Q = us(2.0),
     Returns Float64[n_rt, n_events] like the reference (src/dsp_filter_optimization.jl:122)."""
     w = _as_waveforms(wvfs)
     rts = grid_values(config.e_grid_rt_trap)
-    var = trap_variants(rts, [ft], w.step, mode="rt", pickoff=config.enc_pickoff_trap)
-    out = _run(w, config, τ, var, device, handle)
-    return np.ascontiguousarray(out.T).astype(np.float64)
+    # (the general sweep entry in float64: the reference's grid is a Matrix{Float64}, :122)
+    var = trap_sweep_variants(rts, [ft], w.step, mode="rt", pickoff=config.enc_pickoff_trap)
+    out = _run_general(w, config, τ, var, f64=True, device=device, handle=handle)
+    return np.ascontiguousarray(out.T)
 
 
 def dsp_trap_ft_optimization(wvfs, config: DSPConfig, τ: Q, rt: Q, *, device: int = 0,

@@ -93,8 +93,10 @@ def dsp_decay_times(wvfs, config_or_bl_window, tail_window=None, *, device: int 
         cfg = DSPConfig.from_dict(d)
     w = _as_waveforms(wvfs)
     sig = _signal_u16(w.signal)
+    # role "decay": only the baseline and tail windows have to fit the trace (the reference's
+    # dsp_decay_times(wvfs, bl_window, tail_window) takes nothing else)
     P = resolve_icpc_params(cfg, us(500.0), None, n_samples=sig.shape[1], t_first=w.t_first, step=w.step,
-                            groups=_abi.GROUP_BASE, policy=policy)
+                            role="decay", policy=policy)
     h = handle or get_handle(device)
     rows = np.zeros((sig.shape[0], _abi.NCOL), dtype=np.float64)
     h.icpc_run_host(P, sig.ctypes.data, sig.shape[0], sig.strides[0] // 2, rows.ctypes.data)

@@ -203,3 +203,27 @@ def test_compressed_errors_and_empty(L, O, handle):
     Pp, Pw, aux = L.resolve_compressed_params(cfg, L.us(500.0), None, presum_rate=8, n_pre=1024, step_pre=L.ns(128.0),
                                               n_wdw=1400, t_first_wdw=L.ns(41600.0), step_wdw=L.ns(16.0))
     handle.icpc_compressed_run_host(Pp, Pw, 0, 4, 1024, 0, 2, 1400, 8.0, aux, 0, 0, 0, 0)
+
+
+def test_wide_samples_beyond_32_bit_sums_give_nan_rows(L, O, handle):
+    """32-bit samples whose sum leaves 32 bits (mean >= 2^20 over 4096 samples) cannot be processed with exact uint32 prefix
+    sums: the row is NaN, the neighbouring events are untouched (both execution paths)"""
+    cfg = L.example_config()
+    cfg.bl_window = (L.us(0.0), L.us(20.0))
+    cfg.tail_window = (L.us(52.0), L.us(62.0))
+    cfg.current_window = (L.us(30.0), L.us(55.0))
+    P = L.resolve_icpc_params(cfg, L.us(500.0), n_samples=4096, groups=0x07)
+    wf = L.synth.generate_host(6, first_event=5)[:, :4096].astype(np.uint32)
+    big = wf.copy()
+    big[2] = big[2] * 64 + (1 << 20)          # sums to ~ 2^33
+    rows, ref = [], None
+    for path in ("split", "fused"):
+        handle.set_icpc_path(path)
+        out = np.zeros((6, L.NCOL))
+        ok = np.zeros((6, L.NCOL))
+        handle.icpc_run_ext_host(P, big.ctypes.data, 4, None, 6, 4096, out.ctypes.data)
+        handle.icpc_run_ext_host(P, wf.ctypes.data, 4, None, 6, 4096, ok.ctypes.data)
+        assert np.isnan(out[2]).all(), path
+        keep = [0, 1, 3, 4, 5]
+        assert np.array_equal(np.nan_to_num(out[keep]), np.nan_to_num(ok[keep])), path
+    handle.set_icpc_path("split")

@@ -179,3 +179,32 @@ def test_oracle_rows_golden(L, O, example_params):
     assert rows.shape == ref.shape
     both_nan = np.isnan(rows) & np.isnan(ref)
     assert np.allclose(np.where(both_nan, 0, rows), np.where(both_nan, 0, ref), rtol=1e-9, atol=1e-9)
+
+
+def test_timed_oracle_build_agrees_with_the_strict_one(L, O):
+    """bench.py's CPU arms run the -O3 -march=native build of the oracle sources (contraction allowed, the
+    reference's second ZAC pass paid for); it must agree with the strict checker build to 1e-9 on every column"""
+    from parity import compare_rows
+    P = L.resolve_icpc_params(L.example_config(), L.us(500.0), builders=O.OracleBuilders())
+    wf = O.synth_generate(96, first_event=77)
+    strict, _ = O.dsp_icpc(P, wf)
+    O.use_fast_build(True)
+    try:
+        fast, _ = O.dsp_icpc(P, wf)
+        lean = O.pz_trap(P, wf)
+    finally:
+        O.use_fast_build(False)
+    tie_cols = {"a_sg", "a_60", "a_100", "a_raw"}
+    bad = {k: v for k, v in compare_rows(fast, strict, L.COLUMNS).items() if v[1] > 0 and k not in tie_cols}
+    assert not bad, bad
+    for i, k in enumerate(("blmean", "t0", "t50", "e_trap", "e_10410")):
+        ref = strict[:, L.COL[k]]
+        assert np.allclose(lean[:, i], ref, rtol=1e-9, atol=1e-7), k
+
+
+def test_oracle_event_generator_matches_the_product_host_generator(L, O):
+    """the CPU arms' own statement of the synthetic stream (oracle/lgdsp_synth_oracle.c) == lgdsp_synth_generate_host"""
+    for kw in (dict(first_event=0), dict(first_event=123456789), dict(mode=1), dict(n_samples=1024, first_event=5)):
+        a = O.synth_generate(40, **kw)
+        b = L.synth.generate_host(40, **kw)
+        assert np.array_equal(a, b), kw
