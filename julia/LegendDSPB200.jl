@@ -160,13 +160,14 @@ function sweep_params(t::AbstractRange, config::DSPConfig, τ; out_f64::Bool)
     put!(buf, O.out_f64, Int32(out_f64))
     buf
 end
-"""array of `lgdsp_trap_variant` for (rt, ft) pairs; mode 0: fixed pick-off, 1: t50 + pick-off"""
+"""array of `lgdsp_sweep_variant` (kind 0: trapezoid) for (rt, ft) pairs; mode 0: fixed pick-off, 1: t50 + pick-off"""
 function trap_variants(pairs, dt, pickoffs, mode::Integer)
-    buf = zeros(UInt8, SIZEOF_LGDSP_TRAP_VARIANT * length(pairs)); O = OFF_LGDSP_TRAP_VARIANT
+    buf = zeros(UInt8, SIZEOF_LGDSP_SWEEP_VARIANT * length(pairs)); O = OFF_LGDSP_SWEEP_VARIANT
     for (i, ((rt, ft), pk)) in enumerate(zip(pairs, pickoffs))
-        off = (i - 1) * SIZEOF_LGDSP_TRAP_VARIANT
+        off = (i - 1) * SIZEOF_LGDSP_SWEEP_VARIANT
+        put!(buf, off + O.kind, Int32(0)); put!(buf, off + O.pickoff_mode, Int32(mode))
+        put!(buf, off + O.pickoff_ns, Float64(ustrip(u"ns", pk)))
         put_trap!(buf, off + O.trap, rt, ft, rt, dt)
-        put!(buf, off + O.pickoff_ns, Float64(ustrip(u"ns", pk))); put!(buf, off + O.pickoff_mode, Int32(mode))
     end
     buf
 end
@@ -292,32 +293,33 @@ function _compressed_table(data, rp, rw, st)
 end
 
 # ---- trapezoid sweeps: src/dsp_filter_optimization.jl:102-133, 241-274 ----
-function _trap_sweep(wvfs, config, τ, pairs, pickoffs, mode; out_f64::Bool)
+function _trap_sweep(wvfs, config, τ, pairs, pickoffs, mode, ::Type{T}) where {T <: Union{Float32, Float64}}
     flat = _flat(wvfs.signal, UInt16); n_samples, n_events = size(flat)
     t = wvfs[1].time
-    sp = sweep_params(t, config, τ; out_f64 = false)
+    sp = sweep_params(t, config, τ; out_f64 = T === Float64)
     var = trap_variants(pairs, step(t), pickoffs, mode)
-    out = Matrix{Float32}(undef, length(pairs), n_events)               # == the reference's (n_grid x n_events) column-major matrix
+    out = Matrix{T}(undef, length(pairs), n_events)                     # == the reference's (n_grid x n_events) column-major matrix
     h = handle()
     GC.@preserve flat sp var out begin
-        rc = ccall((:lgdsp_trap_sweep_run, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{UInt16}, Int64, Int64, Ptr{UInt8}, Int32, Ptr{Float32}),
-                   h.ptr, sp, flat, n_events, stride(flat, 2), var, Int32(length(pairs)), out)
+        rc = ccall((:lgdsp_sweep_run, LIB), Cint,
+                   (Ptr{Cvoid}, Ptr{UInt8}, Ptr{UInt16}, Int64, Int64, Ptr{UInt8}, Int32, Ptr{Cvoid}, Ptr{Float64}),
+                   h.ptr, sp, flat, n_events, stride(flat, 2), var, Int32(length(pairs)), out, C_NULL)
     end
-    _check(h, rc, "lgdsp_trap_sweep_run")
-    out_f64 ? Float64.(out) : out
+    _check(h, rc, "lgdsp_sweep_run")
+    out
 end
 
 """`dsp_trap_rt_optimization(wvfs, config, τ; ft)` -> Matrix{Float64}(n_rt, n_events): ENC grid at the fixed pick-off
 `config.enc_pickoff_trap` (src/dsp_filter_optimization.jl:102-133)"""
 function dsp_trap_rt_optimization(wvfs, config::DSPConfig, τ::Quantity; ft = 2.0u"μs")
     rts = collect(config.e_grid_rt_trap)
-    _trap_sweep(wvfs, config, τ, [(rt, ft) for rt in rts], fill(config.enc_pickoff_trap, length(rts)), 0; out_f64 = true)
+    _trap_sweep(wvfs, config, τ, [(rt, ft) for rt in rts], fill(config.enc_pickoff_trap, length(rts)), 0, Float64)
 end
 """`dsp_trap_ft_optimization(wvfs, config, τ, rt)` -> Matrix{Float32}(n_ft, n_events): energy grid at t50 + rt + ft/2
 (src/dsp_filter_optimization.jl:241-274)"""
 function dsp_trap_ft_optimization(wvfs, config::DSPConfig, τ::Quantity, rt)
     fts = collect(config.e_grid_ft_trap)
-    _trap_sweep(wvfs, config, τ, [(rt, ft) for ft in fts], [rt + ft / 2 for ft in fts], 1; out_f64 = false)
+    _trap_sweep(wvfs, config, τ, [(rt, ft) for ft in fts], [rt + ft / 2 for ft in fts], 1, Float32)
 end
 
 end # module

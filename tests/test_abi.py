@@ -100,44 +100,47 @@ def test_product_never_imports_the_oracle():
                 assert "liblgdsp_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
 
 
-def test_julia_wrapper_struct_layout_matches_the_ctypes_mirror(L):
-    """julia/LegendDSPB200.jl cannot be run here (no Julia toolchain): at least its `struct` declarations must list the
-    fields of include/lgdsp_b200.h in the same order with the same element types / array lengths as the ctypes mirror
-    (which test_ctypes_mirror_matches_header ties to the header), and its constants must equal the header's."""
+def test_julia_wrapper_stays_in_sync_with_the_header(L):
+    """julia/LegendDSPB200.jl cannot be run here (no Julia toolchain).  What can be checked: (1) julia/lgdsp_offsets.jl -- the
+    struct layouts the wrapper writes its parameter blocks at -- is exactly what the C compiler measures on the header today
+    and equals the ctypes mirror; (2) every offset / constant the wrapper uses exists in that file; (3) every C symbol it
+    ccalls is exported; (4) its column list is the header's column enum."""
     import ctypes as C
+    import importlib.util
     import re
-    src = open(os.path.join(ROOT, "julia", "LegendDSPB200.jl"), encoding="utf-8").read()
+    spec = importlib.util.spec_from_file_location("gen_julia_offsets", os.path.join(ROOT, "tools", "gen_julia_offsets.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    committed = open(os.path.join(ROOT, "julia", "lgdsp_offsets.jl")).read()
+    assert committed == gen.generate(), "julia/lgdsp_offsets.jl is stale: run python tools/gen_julia_offsets.py"
     abi = L._abi
-    consts = dict(re.findall(r"const (MAX_DNI|MAX_SG|MAX_FIR|NCOL)\b", src) and
-                  zip(("MAX_DNI", "MAX_SG", "MAX_FIR", "NCOL"),
-                      map(int, re.search(r"const MAX_DNI, MAX_SG, MAX_FIR, NCOL = (\d+), (\d+), (\d+), (\d+)", src).groups())))
-    assert consts == {"MAX_DNI": abi.LGDSP_MAX_DNI, "MAX_SG": abi.LGDSP_MAX_SG, "MAX_FIR": abi.LGDSP_MAX_FIR, "NCOL": abi.NCOL}
-    assert int(re.search(r"PARAMS_VERSION = UInt32\((\d+)\)", src).group(1)) == abi.LGDSP_PARAMS_VERSION
+    mirror = {"LGDSP_TRAP": abi.Trap, "LGDSP_DNI": abi.Dni, "LGDSP_SG": abi.Sg, "LGDSP_CUSPZAC": abi.CuspZac,
+              "LGDSP_ICPC_PARAMS": abi.IcpcParams, "LGDSP_SWEEP_PARAMS": abi.SweepParams, "LGDSP_TRAP_VARIANT": abi.TrapVariant,
+              "LGDSP_SWEEP_VARIANT": abi.SweepVariant}
+    offs = {}
+    for name, body in re.findall(r"const OFF_(\w+) = \((.*?)\)\n", committed):
+        offs[name] = dict((k, int(v)) for k, v in re.findall(r"(\w+) = (\d+)", body))
+        for f, o in offs[name].items():
+            assert getattr(mirror[name], f).offset == o, (name, f)
+    for name, size in re.findall(r"const SIZEOF_(\w+) = (\d+)", committed):
+        assert C.sizeof(mirror[name]) == int(size), name
+    consts = dict((k, int(v)) for k, v in re.findall(r"const (LGDSP_\w+) = (\d+)", committed))
+    assert consts["LGDSP_NCOL"] == abi.NCOL and consts["LGDSP_PARAMS_VERSION"] == abi.LGDSP_PARAMS_VERSION
+    assert consts["LGDSP_GROUP_ALL"] == abi.GROUP_ALL and consts["LGDSP_MAX_FIR"] == abi.LGDSP_MAX_FIR
 
-    jl_scalar = {"Int32": C.c_int32, "UInt32": C.c_uint32, "Int64": C.c_int64, "Float64": C.c_double}
-    env = {"MAX_DNI": abi.LGDSP_MAX_DNI, "MAX_SG": abi.LGDSP_MAX_SG, "MAX_FIR": abi.LGDSP_MAX_FIR}
-    structs = {"Trap": abi.Trap, "Dni": abi.Dni, "Sg": abi.Sg, "CuspZac": abi.CuspZac, "IcpcParams": abi.IcpcParams}
-
-    def jl_fields(name):
-        body = re.search(r"struct %s\b(.*?)\bend" % name, src, re.S).group(1)
-        body = re.sub(r"#.*", "", body)
-        return re.findall(r"(\w+)::([\w{}*, ]+?)(?:;|\n|$)", body)
-
-    def ctype_of(jl_type):
-        jl_type = jl_type.strip()
-        m = re.fullmatch(r"NTuple\{(.+),\s*(\w+)\}", jl_type)
-        if m:
-            length = eval(m.group(1), {}, env)
-            return ctype_of(m.group(2)) * length
-        return jl_scalar.get(jl_type) or structs[jl_type]
-
-    for name, cstruct in structs.items():
-        jf = jl_fields(name)
-        cf = list(cstruct._fields_)
-        assert [f for f, _ in jf] == [f for f, _ in cf] or [f for f, _ in jf] == [f.replace("n_window", "n_w") for f, _ in cf], \
-            (name, [f for f, _ in jf], [f for f, _ in cf])
-        for (jn, jt), (cn, ct) in zip(jf, cf):
-            assert C.sizeof(ctype_of(jt)) == C.sizeof(ct), (name, jn, jt, ct)
+    src = open(os.path.join(ROOT, "julia", "LegendDSPB200.jl"), encoding="utf-8").read()
+    for name, field in re.findall(r"\bOFF_(LGDSP_\w+)\.(\w+)", src):
+        assert field in offs[name], f"OFF_{name}.{field} is not a field of the header's struct"
+    aliases = dict(re.findall(r"\b(\w+) = OFF_(LGDSP_\w+)\b", src))        # e.g. `O = OFF_LGDSP_ICPC_PARAMS`
+    assert aliases, "the wrapper is expected to alias the offset tables"
+    aliased_fields = set().union(*(offs[v] for v in aliases.values()))
+    for field in set(re.findall(r"\bO\.(\w+)", src)):
+        assert field in aliased_fields, f"O.{field} is not a field of any aliased struct"
+    for ident in set(re.findall(r"\b(LGDSP_[A-Z0-9_]+|SIZEOF_LGDSP_[A-Z_]+)\b", src)):
+        assert ident in consts or ident in ("SIZEOF_" + k for k in mirror) or ident.startswith("LGDSP_B200"), ident
+    lib = L.load_library()
+    for sym in set(re.findall(r"ccall\(\(:(\w+), LIB\)", src)) | set(re.findall(r":(lgdsp_(?:cusp|zac)_coeffs)", src)):
+        assert hasattr(lib, sym), f"{sym} is not exported by liblgdsp_b200.so"
     # the column list of the wrapper's output table is the header's column enum
     cols = re.search(r"const COLS = \((.*?)\)\n", src, re.S).group(1)
     jl_cols = [c.replace("tail_τ", "tail_tau") for c in re.findall(r":([\wτ]+)", cols)]
