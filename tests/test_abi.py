@@ -131,9 +131,9 @@ def test_julia_wrapper_stays_in_sync_with_the_header(L):
     src = open(os.path.join(ROOT, "julia", "LegendDSPB200.jl"), encoding="utf-8").read()
     for name, field in re.findall(r"\bOFF_(LGDSP_\w+)\.(\w+)", src):
         assert field in offs[name], f"OFF_{name}.{field} is not a field of the header's struct"
-    aliases = dict(re.findall(r"\b(\w+) = OFF_(LGDSP_\w+)\b", src))        # e.g. `O = OFF_LGDSP_ICPC_PARAMS`
+    aliases = set(v for _, v in re.findall(r"\b(\w+) = OFF_(LGDSP_\w+)\b", src))        # e.g. `O = OFF_LGDSP_ICPC_PARAMS`
     assert aliases, "the wrapper is expected to alias the offset tables"
-    aliased_fields = set().union(*(offs[v] for v in aliases.values()))
+    aliased_fields = set().union(*(offs[v] for v in aliases))
     for field in set(re.findall(r"\bO\.(\w+)", src)):
         assert field in aliased_fields, f"O.{field} is not a field of any aliased struct"
     for ident in set(re.findall(r"\b(LGDSP_[A-Z0-9_]+|SIZEOF_LGDSP_[A-Z_]+)\b", src)):
