@@ -193,6 +193,12 @@ int lgdsp_create(int device, void* stream, lgdsp_handle** out)
     if (const char* env = getenv("LGDSP_SPLIT_BATCH")) h->split_batch = atoll(env);
     if (const char* env = getenv("LGDSP_SPLIT_STREAMS")) h->split_streams = atoi(env);
     if (const char* env = getenv("LGDSP_SPLIT_PAR")) h->split_par = atoi(env) != 0;
+    if (const char* env = getenv("LGDSP_SPLIT_BPS")) {   // experiment knob: resident blocks per SM of {prefix, extract, cuspzac}, e.g. "2,3,1"
+        int v[3] = {0, 0, 0};
+        if (sscanf(env, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3)
+            for (int k = 0; k < 3; ++k)
+                if (v[k] >= 1 && v[k] < h->split_bps[k]) h->split_bps[k] = v[k];
+    }
     if (h->split_streams < 1) h->split_streams = 1;
     if (h->split_streams > LGDSP_SPLIT_MAX_STREAMS) h->split_streams = LGDSP_SPLIT_MAX_STREAMS;
     *out = h;
