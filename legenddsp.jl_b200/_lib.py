@@ -8,7 +8,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblgdsp_b200.so")
+LIB_PATH = os.environ.get("LGDSP_B200_LIB") or os.path.join(_HERE, "liblgdsp_b200.so")   # (override: A/B builds of tools/)
 
 _dp = C.POINTER(C.c_double)
 _lib = None

@@ -138,13 +138,13 @@ __device__ __forceinline__ double warp_sum(double v)
 __device__ __forceinline__ double warp_max(double v)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(FULL, v, o); v = w > v ? w : v; }   // (fmax() costs 2x: NaN handling)
     return v;
 }
 __device__ __forceinline__ double warp_min(double v)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+    for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(FULL, v, o); v = w < v ? w : v; }
     return v;
 }
 // (value, index) maximum with FIRST index on ties

@@ -211,11 +211,20 @@ __device__ __noinline__ double trap_eval(const double* TT, int a, int ag, int L,
 {
     const double s1 = TT[j + a] - TT[j];
     const double s2 = TT[j + L] - TT[j + ag];
-    return s2 * inv2 - s1 * inv1;
+    return __fma_rn(s2, inv2, -__dmul_rn(s1, inv1));
 }
 __device__ __forceinline__ double trap_at(const double* TT, const TrapDev& t, int j)
 {
     return trap_eval(TT, t.a, t.a + t.g, t.L, t.inv1, t.inv2, j);
+}
+// the same arithmetic inlined at the call site (the split pipeline's extract kernel: no call frame, the trapezoid's
+// constants stay in uniform registers)
+__device__ __forceinline__ double trap_at_i(const double* TT, const TrapDev& t, int j)
+{
+    const double* p = TT + j;
+    const double s1 = p[t.a] - p[0];
+    const double s2 = p[t.L] - p[t.a + t.g];
+    return __fma_rn(s2, t.inv2, -__dmul_rn(s1, t.inv1));
 }
 __device__ __forceinline__ double y_at(const double* TT, int i) { return TT[i + 1] - TT[i]; }
 __device__ __noinline__ double sg_eval(const double* TT, const double* gg, int n_taps, int j)
@@ -811,35 +820,35 @@ __device__ __forceinline__ void trap_full2_minmax(const double* TT, const TrapDe
 {
     double mxa = -CUDART_INF, mna = CUDART_INF, mxb = -CUDART_INF, mnb = CUDART_INF;
     const double* p0 = TT + tid;
-    {
-        const double* a1 = p0 + A.a; const double* a2 = a1 + A.g; const double* a3 = p0 + A.L;
-        const double* b1 = p0 + B.a; const double* b2 = b1 + B.g; const double* b3 = p0 + B.L;
-        const double ai1 = A.inv1, ai2 = A.inv2, bi1 = B.inv1, bi2 = B.inv2;
-        const int cnt = min(A.nout, B.nout) - tid;
-        int off = 0;
+    const double* a1 = p0 + A.a; const double* a2 = a1 + A.g; const double* a3 = p0 + A.L;
+    const double* b1 = p0 + B.a; const double* b2 = b1 + B.g; const double* b3 = p0 + B.L;
+    const double ai1 = A.inv1, ai2 = A.inv2, bi1 = B.inv1, bi2 = B.inv2;
+    const int cnt = min(A.nout, B.nout) - tid;
+    int off = 0;
+    // (ternaries, not fmax/fmin: the NaN handling of those doubles the instruction count; an LDS-bound loop -- scaling
+    //  the extrema once instead of every output was measured and changes nothing)
 #pragma unroll 1
-        for (; off < cnt; off += NT) {
-            const double t0 = p0[off];
-            const double oa = (a3[off] - a2[off]) * ai2 - (a1[off] - t0) * ai1;
-            const double ob = (b3[off] - b2[off]) * bi2 - (b1[off] - t0) * bi1;
-            mxa = oa > mxa ? oa : mxa; mna = oa < mna ? oa : mna;
-            mxb = ob > mxb ? ob : mxb; mnb = ob < mnb ? ob : mnb;
-        }
-        // remainder of the longer trace
-        const bool a_longer = A.nout > B.nout;
-        const TrapDev& R = a_longer ? A : B;
-        const double* r1 = p0 + R.a; const double* r2 = r1 + R.g; const double* r3 = p0 + R.L;
-        const double ri1 = R.inv1, ri2 = R.inv2;
-        double mx = -CUDART_INF, mn = CUDART_INF;
-        const int cntr = R.nout - tid;
-#pragma unroll 1
-        for (; off < cntr; off += NT) {
-            const double o = (r3[off] - r2[off]) * ri2 - (r1[off] - p0[off]) * ri1;
-            mx = o > mx ? o : mx; mn = o < mn ? o : mn;
-        }
-        if (a_longer) { mxa = mx > mxa ? mx : mxa; mna = mn < mna ? mn : mna; }
-        else { mxb = mx > mxb ? mx : mxb; mnb = mn < mnb ? mn : mnb; }
+    for (; off < cnt; off += NT) {
+        const double t0 = p0[off];
+        const double oa = __fma_rn(a3[off] - a2[off], ai2, -__dmul_rn(a1[off] - t0, ai1));
+        const double ob = __fma_rn(b3[off] - b2[off], bi2, -__dmul_rn(b1[off] - t0, bi1));
+        mxa = oa > mxa ? oa : mxa; mna = oa < mna ? oa : mna;
+        mxb = ob > mxb ? ob : mxb; mnb = ob < mnb ? ob : mnb;
     }
+    // remainder of the longer trace
+    const bool a_longer = A.nout > B.nout;
+    const TrapDev& R = a_longer ? A : B;
+    const double* r1 = p0 + R.a; const double* r2 = r1 + R.g; const double* r3 = p0 + R.L;
+    const double ri1 = R.inv1, ri2 = R.inv2;
+    double mx = -CUDART_INF, mn = CUDART_INF;
+    const int cntr = R.nout - tid;
+#pragma unroll 1
+    for (; off < cntr; off += NT) {
+        const double o = __fma_rn(r3[off] - r2[off], ri2, -__dmul_rn(r1[off] - p0[off], ri1));
+        mx = o > mx ? o : mx; mn = o < mn ? o : mn;
+    }
+    if (a_longer) { mxa = mx > mxa ? mx : mxa; mna = mn < mna ? mn : mna; }
+    else { mxb = mx > mxb ? mx : mxb; mnb = mn < mnb ? mn : mnb; }
     out[0] = mxa; out[1] = -mna; out[2] = mxb; out[3] = -mnb;
 }
 
@@ -2059,7 +2068,7 @@ __device__ __forceinline__ double block_max1(double v, double* red, int tid)
     __syncthreads();
     double s = red[0];
 #pragma unroll
-    for (int w = 1; w < NWARP; ++w) s = fmax(s, red[w]);
+    for (int w = 1; w < NWARP; ++w) s = red[w] > s ? red[w] : s;
     __syncthreads();
     return s;
 }

@@ -530,7 +530,7 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             const double* p0 = TT + tid;
 #pragma unroll 2
             for (int off = 0; off < A.nout - tid; off += NT2) {
-                const double o = (p0[off + A.L] - p0[off + A.a + A.g]) * A.inv2 - (p0[off + A.a] - p0[off]) * A.inv1;
+                const double o = __fma_rn(p0[off + A.L] - p0[off + A.a + A.g], A.inv2, -__dmul_rn(p0[off + A.a] - p0[off], A.inv1));
                 mx = o > mx ? o : mx;
             }
             const double a = wmax_d(mx);
@@ -549,18 +549,18 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
         {
             const int ja = i0, jb = i0 + CH;
             if (G & LGDSP_GROUP_TIMING) {
-                if (ja < P.t0.nout) c0a = trap_at(TT, P.t0, ja);
-                if (jb < P.t0.nout) c0b = trap_at(TT, P.t0, jb);
+                if (ja < P.t0.nout) c0a = trap_at_i(TT, P.t0, ja);
+                if (jb < P.t0.nout) c0b = trap_at_i(TT, P.t0, jb);
                 if (!P.t0inv_same && !lean) {
-                    if (ja < P.t0inv.nout) cia = trap_at(TT, P.t0inv, ja);
-                    if (jb < P.t0inv.nout) cib = trap_at(TT, P.t0inv, jb);
+                    if (ja < P.t0inv.nout) cia = trap_at_i(TT, P.t0inv, ja);
+                    if (jb < P.t0inv.nout) cib = trap_at_i(TT, P.t0inv, jb);
                 }
             }
             if ((G & LGDSP_GROUP_TRAPS) && !lean) {
-                if (ja < P.e535.nout) c5a = trap_at(TT, P.e535, ja);
-                if (jb < P.e535.nout) c5b = trap_at(TT, P.e535, jb);
-                if (ja < P.etrap.nout) cea = trap_at(TT, P.etrap, ja);
-                if (jb < P.etrap.nout) ceb = trap_at(TT, P.etrap, jb);
+                if (ja < P.e535.nout) c5a = trap_at_i(TT, P.e535, ja);
+                if (jb < P.e535.nout) c5b = trap_at_i(TT, P.e535, jb);
+                if (ja < P.etrap.nout) cea = trap_at_i(TT, P.etrap, ja);
+                if (jb < P.etrap.nout) ceb = trap_at_i(TT, P.etrap, jb);
                 const double w5 = wmax_d(c5a), we = wmax_d(cea);
                 red_put(red, K2R_C535, wid, lane, w5);
                 red_put(red, K2R_CET, wid, lane, we);
@@ -674,7 +674,7 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             const double tf = t_first + (double)(P.etrap.L - 1) * dt;
             dni_window(P.sig_dni.n_w, n - P.etrap.L + 1, (t50_us * 1000.0 + P.trap_pick - tf) / dt, pk_p, pk_from);
         }
-        if ((G & LGDSP_GROUP_TRAPS) && tid < P.sig_dni.n_w) stash[tid] = trap_at(TT, P.etrap, pk_from + tid);
+        if ((G & LGDSP_GROUP_TRAPS) && tid < P.sig_dni.n_w) stash[tid] = trap_at_i(TT, P.etrap, pk_from + tid);
 
         double pile_thr = 0.0, cur_thr = 0.0;
         if (G & LGDSP_GROUP_INTRACE) {
@@ -695,7 +695,7 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                 const double th = P.t0_thr;
                 const int j = q * CH + 1 + lane;
                 const bool v = j < tr.nout;
-                const double o = v ? trap_at(TT, tr, j) : 0.0;
+                const double o = v ? trap_at_i(TT, tr, j) : 0.0;
                 const unsigned mp = __ballot_sync(FULL, v && (o >= th));
                 const unsigned mn_ = __ballot_sync(FULL, v && (-o >= th));
                 commit_pair(type == 0 ? masks + MK_T0 * NWORDS : nullptr, (unsigned long long)mp << 1,
@@ -704,13 +704,13 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             } else if (type == 2) {
                 const int j = q * CH + 1 + lane;
                 if (j < P.e535.nout) {
-                    const double o = trap_at(TT, P.e535, j);
+                    const double o = trap_at_i(TT, P.e535, j);
                     e535 = o > e535 ? o : e535;
                 }
             } else if (type == 3) {
                 const int j = q * CH + 1 + lane;
                 if (j < P.etrap.nout) {
-                    const double o = trap_at(TT, P.etrap, j);
+                    const double o = trap_at_i(TT, P.etrap, j);
                     if (o > etmax || (o == etmax && j < etarg)) { etmax = o; etarg = j; }
                 }
             } else {
@@ -815,7 +815,7 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             if (pos >= 1) {
                 const double tl = t_first + (double)(pos - 1 + tr.L - 1) * dt;
                 const double sgn = inv ? -1.0 : 1.0;
-                t = cross_x(P.t0_thr, sgn * trap_at(TT, tr, pos - 1), sgn * trap_at(TT, tr, pos), tl, dt) * 0.001;
+                t = cross_x(P.t0_thr, sgn * trap_at_i(TT, tr, pos - 1), sgn * trap_at_i(TT, tr, pos), tl, dt) * 0.001;
             }
             return t != t ? 0.0 : t;
         };

@@ -27,6 +27,15 @@ res = []
 for s in settings:
     f = s.split(":")
     path = f[0]
+    if path == "prof":   # prof:<events>: serial per-kernel device times of the split pipeline on one batch
+        m = int(f[1]) if len(f) > 1 else 16384
+        best = None
+        for k in range(4):
+            ms = h.icpc_profile_device(pool[0].data_ptr(), m, 8192, out.data_ptr())
+            best = ms if best is None else [min(a, b) for a, b in zip(best, ms)]
+        print(json.dumps({"setting": s, "events": m, "ms_prefix_extract_select_finish": best, "sum_ms": sum(best),
+                          "Mwf_s_serial": m / sum(best) / 1e3}), flush=True)
+        continue
     batch = int(f[1]) if len(f) > 1 else 0
     streams = int(f[2]) if len(f) > 2 else 0
     h.set_icpc_path(path, batch, streams)
