@@ -185,12 +185,6 @@ int codec_encode_host(int codec, const void* wf, int sample_bytes, long long n_e
 // device decoders
 // ---------------------------------------------------------------------------------------------------
 constexpr int DEC_NT = 128;
-constexpr int RW_MAXSEC = 512;   // sections per waveform the table holds (the encoder makes >= 48-sample sections: <= 171)
-
-struct RwSec {
-    int iso, nw, nb, diff, mn, start, payload;   // payload: first payload word of the section
-};
-
 // bytes of one stream -> shared memory; returns the index of stream byte 0 inside `sm` (the copy is word aligned: whole
 // 32-bit words where they lie inside the stream, single bytes at its two ends -- nothing outside the stream is read)
 __device__ __forceinline__ int load_stream(const uint8_t* __restrict__ enc, long long off, long long nbytes, unsigned char* sm, int tid)
@@ -208,94 +202,120 @@ __device__ __forceinline__ int load_stream(const uint8_t* __restrict__ enc, long
     return skew;
 }
 
+// One stream -> the warp's shared-memory buffer with stream byte 0 on a 4-byte boundary, 16 zero bytes behind it.  Whole
+// aligned 32-bit words where they lie inside the stream (funnel shift when the stream starts between word boundaries),
+// single bytes at the ends: nothing outside the stream is read.
+__device__ __forceinline__ void load_stream_warp(const uint8_t* __restrict__ p, int nbytes, uint32_t* dst, int lane)
+{
+    const int skew = (int)(reinterpret_cast<uintptr_t>(p) & 3);
+    const int nfull = nbytes >> 2, tail = nbytes & 3;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(p - skew);   // a[i], a[i+1] cover destination word i
+    if (skew == 0) {
+        int i = lane;
+        for (; i + 96 < nfull; i += 128) {   // four loads in flight
+            const uint32_t v0 = __ldg(a + i), v1 = __ldg(a + i + 32), v2 = __ldg(a + i + 64), v3 = __ldg(a + i + 96);
+            dst[i] = v0; dst[i + 32] = v1; dst[i + 64] = v2; dst[i + 96] = v3;
+        }
+        for (; i < nfull; i += 32) dst[i] = __ldg(a + i);
+    } else {
+        for (int i = lane; i < nfull; i += 32) {
+            uint32_t v;
+            if (i >= 1 && 4 * (i + 2) - skew <= nbytes) v = __funnelshift_r(__ldg(a + i), __ldg(a + i + 1), 8 * skew);
+            else {
+                const uint8_t* q = p + 4 * i;
+                v = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) | ((uint32_t)__ldg(q + 3) << 24);
+            }
+            dst[i] = v;
+        }
+    }
+    if (lane < 4) {
+        uint32_t v = 0;
+        if (lane == 0) for (int t = 0; t < tail; ++t) v |= (uint32_t)__ldg(p + 4 * nfull + t) << (8 * t);
+        dst[nfull + lane] = v;
+    }
+}
+
 // out[e][i] = sample i of event e (uint16); status[e] = 0 ok, 1 malformed stream (the waveform is zero-filled); err[0] counts
-// the malformed streams, err[1] keeps the smallest err_base + e among them (both optional)
+// the malformed streams, err[1] keeps the smallest err_base + e among them (both optional).
+// One WARP per waveform: it walks the sections in order (the header fields are read by every lane: shared-memory
+// broadcasts, no divergence, no block barrier) and unpacks a section's <= 128 values four per lane.  `cap_w` = bytes of
+// one warp's stream buffer (>= longest stream + 16).
+constexpr int DEC_WARPS = DEC_NT / 32;
 __global__ void __launch_bounds__(DEC_NT)
 radware_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restrict__ off, long long off_base, long long n_events,
                       int n_samples, int shift, uint16_t* __restrict__ out, long long ld, int* __restrict__ status, int* __restrict__ err,
-                      int err_base, int cap_bytes)
+                      int err_base, int cap_w)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
-    unsigned char* bytes = dsm;                                                   // cap_bytes + 8
-    RwSec* sec = reinterpret_cast<RwSec*>(dsm + ((cap_bytes + 8 + 15) & ~15));    // RW_MAXSEC
-    __shared__ int s_nsec, s_err;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (long long e = blockIdx.x; e < n_events; e += gridDim.x) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* w32 = reinterpret_cast<uint32_t*>(dsm + (size_t)wid * cap_w);
+    const uint16_t* h16 = reinterpret_cast<const uint16_t*>(w32);
+    auto word = [&](int k) -> int { return (int)__byte_perm((unsigned)h16[k], 0u, 0x4401); };   // big-endian 16-bit word k
+    auto bswap = [](uint32_t v) -> uint32_t { return __byte_perm(v, 0u, 0x0123); };
+    for (long long e = (long long)blockIdx.x * DEC_WARPS + wid; e < n_events; e += (long long)gridDim.x * DEC_WARPS) {
         const long long o0 = off[e] - off_base, nbytes = off[e + 1] - off[e];
-        const bool fits = nbytes >= 2 && nbytes + 4 <= cap_bytes;
-        int skew = 0;
-        if (fits) skew = load_stream(enc, o0, nbytes, bytes, tid);
-        __syncthreads();
-        const unsigned char* b = bytes + skew;
-        auto word = [&](int k) -> unsigned { return ((unsigned)b[2 * k] << 8) | b[2 * k + 1]; };
-        if (tid == 0) {
-            // the section headers are the only sequential part
-            int err = fits ? 0 : 1, ns = 0;
-            if (!err) {
-                const int nwords = (int)(nbytes >> 1);
-                const int siglen = (int)word(0);
-                if (siglen != n_samples) err = 1;
-                int pos = 1, iso = 0;
-                while (!err && pos < nwords && iso < siglen) {
-                    if (ns >= RW_MAXSEC || pos + 3 > nwords) { err = 1; break; }
-                    RwSec s;
-                    s.iso = iso;
-                    s.nw = (int)word(pos);
-                    int nb = (int)word(pos + 1);
-                    s.diff = nb >= 32;
-                    if (s.diff) {
-                        nb -= 32;
-                        if (pos + 4 > nwords) { err = 1; break; }
-                        s.start = (short)word(pos + 2);
-                        s.mn = (short)word(pos + 3);
-                        s.payload = pos + 4;
-                    } else {
-                        s.start = 0;
-                        s.mn = (short)word(pos + 2);
-                        s.payload = pos + 3;
-                    }
-                    s.nb = nb;
-                    if (nb > 16 || s.nw < 1) { err = 1; break; }
-                    const int nvals = s.diff ? s.nw - 1 : s.nw;
-                    const int pw = (nvals * nb + 15) >> 4;
-                    if (s.payload + pw > nwords) { err = 1; break; }
-                    if (s.nw > siglen - iso) s.nw = siglen - iso;   // the original stops at the stored length
-                    sec[ns++] = s;
-                    iso += s.nw;
-                    pos = s.payload + pw;
-                }
-                if (!err && iso != siglen) err = 1;
-            }
-            s_nsec = ns;
-            s_err = err;
-        }
-        __syncthreads();
+        int bad = (nbytes >= 2 && nbytes + 16 <= cap_w) ? 0 : 1;
         uint16_t* o = out + e * ld;
-        if (s_err) {
-            for (int i = tid; i < n_samples; i += DEC_NT) o[i] = 0;
-        } else {
-            // one warp per section; a lane unpacks four consecutive values per round of 128
-            for (int si = wid; si < s_nsec; si += DEC_NT / 32) {
-                const RwSec s = sec[si];
-                const unsigned mask = s.nb ? (0xffffffffu >> (32 - s.nb)) : 0u;
-                auto val = [&](int k) -> int {   // payload value k
-                    const int p = k * s.nb, wq = s.payload + (p >> 4), sh = p & 15;
-                    const unsigned x = (word(wq) << 16) | word(wq + 1);   // (one word of slack behind the stream is zero padded)
-                    return s.nb ? (int)((x >> (32 - sh - s.nb)) & mask) + s.mn : s.mn;
-                };
-                if (!s.diff) {
-                    for (int k = lane; k < s.nw; k += 32) o[s.iso + k] = (uint16_t)((val(k) - shift) & 0xffff);
+        __syncwarp();   // every lane is done with the previous stream
+        if (!bad) {
+            load_stream_warp(enc + o0, (int)nbytes, w32, lane);
+            __syncwarp();
+            const int nwords = (int)(nbytes >> 1);
+            const int siglen = word(0);
+            if (siglen != n_samples) bad = 1;
+            int pos = 1, iso = 0;
+            while (!bad && pos < nwords && iso < siglen) {
+                if (pos + 3 > nwords) { bad = 1; break; }
+                int nw = word(pos), nb = word(pos + 1), start = 0, mn, payload;
+                const bool diff = nb >= 32;
+                if (diff) {
+                    nb -= 32;
+                    if (pos + 4 > nwords) { bad = 1; break; }
+                    start = (short)word(pos + 2);
+                    mn = (short)word(pos + 3);
+                    payload = pos + 4;
                 } else {
-                    int carry = s.start;   // running value in front of this round (16-bit wrap-around is applied at the store)
-                    if (lane == 0) o[s.iso] = (uint16_t)((carry - shift) & 0xffff);
-                    for (int k0 = 0; k0 < s.nw - 1; k0 += 128) {
-                        int v[4], sum = 0;
+                    mn = (short)word(pos + 2);
+                    payload = pos + 3;
+                }
+                if (nb > 16 || nw < 1) { bad = 1; break; }
+                const int nvals = diff ? nw - 1 : nw;
+                const int pw = (nvals * nb + 15) >> 4;
+                if (payload + pw > nwords) { bad = 1; break; }
+                if (nw > siglen - iso) nw = siglen - iso;   // the original stops at the stored length
+                const int nv = diff ? nw - 1 : nw;          // values to unpack
+                uint16_t* os = o + iso + (diff ? 1 : 0);
+                int carry = start;                           // running value in front of this round (16-bit wrap-around at the store)
+                if (diff && lane == 0) o[iso] = (uint16_t)((carry - shift) & 0xffff);
+                const int rsh = 32 - nb;
+                for (int k0 = 0; k0 < nv; k0 += 128) {
+                    // this lane's four values start at bit (k0 + 4 lane) nb of the payload: at most 16 + 15 + 64 bits = three words
+                    const int kb = k0 + 4 * lane;
+                    int v[4] = {0, 0, 0, 0};
+                    if (kb < nv && nb > 0) {
+                        const int p0 = kb * nb;
+                        const int hw = payload + (p0 >> 4);
+                        const uint32_t* q = w32 + (hw >> 1);
+                        const uint32_t B0 = bswap(q[0]), B1 = bswap(q[1]), B2 = bswap(q[2]);
+                        int t = ((hw & 1) << 4) + (p0 & 15);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int k = k0 + 4 * lane + q;
-                            v[q] = k < s.nw - 1 ? val(k) : 0;
-                            sum += v[q];
-                            v[q] = sum;
+                        for (int r = 0; r < 4; ++r) {
+                            const int j = t >> 5;
+                            const uint32_t hi = j == 0 ? B0 : (j == 1 ? B1 : B2), lo = j == 0 ? B1 : (j == 1 ? B2 : 0u);
+                            v[r] = (int)(__funnelshift_l(lo, hi, t & 31) >> rsh);
+                            t += nb;
+                        }
+                    }
+                    if (!diff) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            if (kb + r < nv) os[kb + r] = (uint16_t)((v[r] + mn - shift) & 0xffff);
+                    } else {
+                        int sum = 0;
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            sum += (kb + r < nv) ? v[r] + mn : 0;
+                            v[r] = sum;
                         }
                         int incl = sum;
 #pragma unroll
@@ -305,24 +325,29 @@ radware_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restri
                         }
                         const int base = carry + incl - sum;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int k = k0 + 4 * lane + q;
-                            if (k < s.nw - 1) o[s.iso + 1 + k] = (uint16_t)((base + v[q] - shift) & 0xffff);
-                        }
+                        for (int r = 0; r < 4; ++r)
+                            if (kb + r < nv) os[kb + r] = (uint16_t)((base + v[r] - shift) & 0xffff);
                         carry += __shfl_sync(FULL, incl, 31);
                     }
                 }
+                iso += nw;
+                pos = payload + pw;
             }
+            if (!bad && iso != siglen) bad = 1;
         }
-        if (tid == 0) {
-            if (status) status[e] = s_err;
-            if (s_err && err) { atomicAdd(&err[0], 1); atomicMin(&err[1], err_base + (int)e); }
+        if (bad) {
+            __syncwarp();
+            for (int i = lane; i < n_samples; i += 32) o[i] = 0;
         }
-        __syncthreads();   // the byte buffer and the section table are reused by the next event
+        if (lane == 0) {
+            if (status) status[e] = bad;
+            if (bad && err) { atomicAdd(&err[0], 1); atomicMin(&err[1], err_base + (int)e); }
+        }
     }
 }
 
 // ULEB128 zig-zag differences -> uint16 / uint32 samples
+#define VPAD(i) ((i) + ((i) >> 5))   // table index with one pad word per 32: the per-thread runs start in different banks
 template <typename OUT>
 __global__ void __launch_bounds__(DEC_NT)
 uleb_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restrict__ off, long long off_base, long long n_events,
@@ -373,7 +398,8 @@ uleb_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restrict_
                     sh += 7;
                     if (c < 0x80 || q >= nb || sh > 63) break;
                 }
-                vals[idx++] = (uint32_t)((z >> 1) ^ (0ull - (z & 1ull)));   // zig-zag decode; the sums wrap in 32 bits
+                vals[VPAD(idx)] = (uint32_t)((z >> 1) ^ (0ull - (z & 1ull)));   // zig-zag decode; the sums wrap in 32 bits
+                ++idx;
             }
         }
         __syncthreads();
@@ -381,11 +407,12 @@ uleb_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restrict_
         if (s_err) {
             for (int i = tid; i < n_samples; i += DEC_NT) o[i] = 0;
         } else {
-            // prefix sum of the differences: every thread sums a contiguous run, block scan of the run totals
+            // prefix sum of the differences: every thread sums a contiguous run, block scan of the run totals; the sums go
+            // back into the table and leave through a coalesced copy
             const int run = (n_samples + DEC_NT - 1) / DEC_NT;
             const int a = tid * run, z = min(a + run, n_samples);
             uint32_t sum = 0;
-            for (int i = a; i < z; ++i) sum += vals[i];
+            for (int i = a; i < z; ++i) sum += vals[VPAD(i)];
             uint32_t inc = sum;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -398,8 +425,17 @@ uleb_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restrict_
             for (int w = 0; w < wid; ++w) wb += s_tot[w];
             uint32_t acc = wb + inc - sum;
             for (int i = a; i < z; ++i) {
-                acc += vals[i];
-                o[i] = (OUT)acc;
+                acc += vals[VPAD(i)];
+                vals[VPAD(i)] = acc;
+            }
+            __syncthreads();
+            if (sizeof(OUT) == 2 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+                uint32_t* o2 = reinterpret_cast<uint32_t*>(o);
+                for (int i = tid; 2 * i + 1 < n_samples; i += DEC_NT)
+                    o2[i] = (vals[VPAD(2 * i)] & 0xffffu) | (vals[VPAD(2 * i + 1)] << 16);
+                if ((n_samples & 1) && tid == 0) o[n_samples - 1] = (OUT)vals[VPAD(n_samples - 1)];
+            } else {
+                for (int i = tid; i < n_samples; i += DEC_NT) o[i] = (OUT)vals[VPAD(i)];
             }
         }
         if (tid == 0) {
@@ -410,30 +446,42 @@ uleb_decode_kernel(const uint8_t* __restrict__ enc, const long long* __restrict_
     }
 }
 
-static int dec_smem(int codec, int n_samples, int sample_bytes, int* cap_bytes)
+static int dec_smem(int codec, int n_samples, int sample_bytes, long long max_stream_bytes, int* cap_bytes)
 {
-    const int cap = (int)codec_max_encoded_bytes(codec, n_samples, sample_bytes) + 8;
+    const long long worst = codec_max_encoded_bytes(codec, n_samples, sample_bytes);
+    if (codec == LGDSP_CODEC_RADWARE) {
+        // per-warp stream buffers sized for the longest stream of the batch when the caller knows it (host offsets)
+        const long long m = (max_stream_bytes > 0 && max_stream_bytes < worst) ? max_stream_bytes : worst;
+        const int cap = (int)((m + 16 + 15) & ~15LL);
+        *cap_bytes = cap;
+        return cap * DEC_WARPS;
+    }
+    const int cap = (int)worst + 8;
     *cap_bytes = cap;
-    if (codec == LGDSP_CODEC_RADWARE) return ((cap + 8 + 15) & ~15) + RW_MAXSEC * (int)sizeof(RwSec);
-    return ((cap + 16 + 15) & ~15) + n_samples * 4;
+    return ((cap + 16 + 15) & ~15) + (n_samples + (n_samples >> 5) + 1) * 4;
 }
 
-// d_off[e] - off_base = first byte of event e inside d_enc (off_base = d_off[0] when only a slice of the bytes was uploaded)
+// d_off[e] - off_base = first byte of event e inside d_enc (off_base = d_off[0] when only a slice of the bytes was uploaded);
+// max_stream_bytes = longest single stream of the batch if known (0: the codec's worst case)
 cudaError_t codec_decode_launch(int codec, const uint8_t* d_enc, const long long* d_off, long long off_base, long long n_events,
                                 int n_samples, int shift, void* d_out, int sample_bytes, long long ld, int* d_status, int* d_err,
-                                int err_base, int sm_count, cudaStream_t stream)
+                                int err_base, long long max_stream_bytes, int sm_count, cudaStream_t stream)
 {
     if (n_events <= 0) return cudaSuccess;
     int cap = 0;
-    const int smem = dec_smem(codec, n_samples, sample_bytes, &cap);
+    const int smem = dec_smem(codec, n_samples, sample_bytes, max_stream_bytes, &cap);
     const long long maxg = (long long)sm_count * 16;
-    const int grid = (int)(n_events < maxg ? n_events : maxg);
     cudaError_t err;
     if (codec == LGDSP_CODEC_RADWARE) {
+        const long long want = (n_events + DEC_WARPS - 1) / DEC_WARPS;
+        const int grid = (int)(want < maxg ? want : maxg);
         if ((err = cudaFuncSetAttribute(radware_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return err;
         radware_decode_kernel<<<grid, DEC_NT, smem, stream>>>(d_enc, d_off, off_base, n_events, n_samples, shift, static_cast<uint16_t*>(d_out), ld,
                                                                d_status, d_err, err_base, cap);
-    } else if (sample_bytes == 4) {
+        return cudaGetLastError();
+    }
+    const int grid = (int)(n_events < maxg ? n_events : maxg);
+    if (sample_bytes == 4) {
         if ((err = cudaFuncSetAttribute(uleb_decode_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return err;
         uleb_decode_kernel<uint32_t><<<grid, DEC_NT, smem, stream>>>(d_enc, d_off, off_base, n_events, n_samples, static_cast<uint32_t*>(d_out), ld,
                                                                      d_status, d_err, err_base, cap);

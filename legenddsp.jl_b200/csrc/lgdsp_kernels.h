@@ -58,7 +58,7 @@ int codec_encode_host(int codec, const void* wf, int sample_bytes, long long n_e
                       uint8_t* enc, long long cap, long long* offsets);
 cudaError_t codec_decode_launch(int codec, const uint8_t* d_enc, const long long* d_off, long long off_base, long long n_events,
                                 int n_samples, int shift, void* d_out, int sample_bytes, long long ld, int* d_status, int* d_err,
-                                int err_base, int sm_count, cudaStream_t stream);
+                                int err_base, long long max_stream_bytes, int sm_count, cudaStream_t stream);
 
 // synthetic generator
 void synth_launch(const lgdsp_synth_params& sp, long long first_event, long long n_events, long long ld, uint16_t* d_wf,
