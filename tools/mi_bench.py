@@ -33,3 +33,6 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 print(f"MultiIntersect: {n} traces x {ns} f64 samples, {P.n_thresholds} thresholds: {ms:.3f} ms per launch, {n / ms / 1e3:.2f} M traces/s, "
       f"{n * ns * 8 / ms / 1e6:.0f} GB/s of trace bytes; flagged {int(fl.sum())}, finite {float(torch.isfinite(x).double().mean()):.3f}")
+import json
+print(json.dumps({"kernel": "multi_intersect_kernel", "traces": n, "n_samples": ns, "thresholds": int(P.n_thresholds), "ms_per_launch": ms,
+                  "Mtraces_s": n / ms / 1e3, "trace_GB_s": n * ns * 8 / ms / 1e6, "flagged": int(fl.sum())}))
