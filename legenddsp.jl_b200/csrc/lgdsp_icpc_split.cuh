@@ -263,7 +263,10 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
                 double* tile = reinterpret_cast<double*>(smem + K1_TILE) + wid * (32 * TILE_LD);
                 double tprev = TT0;
                 const int cbase = wid * 32;   // first chunk of this warp
-                // store pass: lane -> (chunk 4r + lane/8, sample kb + lane%8); everything but r and kb is loop invariant
+                // store pass: lane -> (chunk 4r + lane/8, sample kb + lane%8); everything but r and kb is loop invariant.
+                // (tile rows 1 apart share one bank pair per half warp: 17 % of this kernel's SMEM wavefronts are that 2-way
+                //  conflict.  Pairing chunks 8 apart removes it -- rows 72 = 8 mod 16 doubles apart -- but spreads each store
+                //  instruction over 2 KB instead of 1 KB of the ring and was 2.3 % SLOWER, 0.7375 vs 0.7210 ms per 16 384 events)
                 const double* trd = tile + (lane >> 3) * TILE_LD + (lane & 7);
                 double* gwr = tg + (cbase + (lane >> 3)) * CH + (lane & 7) + 1;
                 const int glim = n - ((cbase + (lane >> 3)) * CH + (lane & 7));   // sample kb of chunk 4r is valid iff kb + 4r*CH < glim
