@@ -23,12 +23,28 @@ IDX_NAMES = ("t0", "t10", "t50", "t80", "t90", "t99", "t50_current", "t0_inv", "
 _dp = C.POINTER(C.c_double)
 
 
+def _cpu_signature():
+    """model + ISA flags of this host: the fast build uses -march=native, so it has to be compiled where it runs"""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        keep = sorted({l.split(":", 1)[1].strip() for l in txt.splitlines() if l.startswith(("flags", "model name"))})
+        return hashlib.md5("|".join(keep).encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
 def build(force=False):
     deps = [os.path.join(_HERE, f) for f in ("lgdsp_oracle.c", "lgdsp_codec_oracle.c", "lgdsp_synth_oracle.c", "Makefile")]
     deps.append(os.path.join(_HERE, "..", "include", "lgdsp_b200.h"))
     newest = max(os.path.getmtime(d) for d in deps)
-    if force or not all(os.path.exists(f) and os.path.getmtime(f) >= newest for f in (_SO, _SO_FAST)):
+    stamp = os.path.join(_HERE, ".build_host")
+    sig = _cpu_signature()
+    same_host = os.path.exists(stamp) and open(stamp).read().strip() == sig
+    if force or not same_host or not all(os.path.exists(f) and os.path.getmtime(f) >= newest for f in (_SO, _SO_FAST)):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+        with open(stamp, "w") as f:
+            f.write(sig + "\n")
     return _SO
 
 
