@@ -107,6 +107,11 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// hint: bring `bytes` (multiple of 16, 16-byte aligned source) into L2 ahead of a later bulk copy
+__device__ __forceinline__ void tma_prefetch_l2(const void* src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase)
 {
     uint32_t ok;

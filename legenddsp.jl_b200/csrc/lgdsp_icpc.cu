@@ -504,7 +504,8 @@ __device__ __forceinline__ double* cz_tab(double* tabA, double* tabB, int idx)
 // One forward loop per chunk: P- (decayed prefix), D1, D2 (moments) and the partial sums acc = sum_{k'<=k} rho^k' d
 // of the anti-causal prefix (P+ at in-chunk offset o is (total - acc[o-1]) * rho^-o; the weights only span one
 // chunk, so nothing cancels).  The running values are stored at the capture events the host sorted by sample index.
-template <int PAR_OFF>
+// CONTIG: tables 8..15 follow tables 0..7 in memory (the split pipeline's layout): no per-access choice of the half
+template <int PAR_OFF, bool CONTIG = false>
 __device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, double* tabA, double* tabB, double* red,
                         double* pp0
 #ifdef LGDSP_PROFILE_SECTIONS
@@ -516,6 +517,7 @@ __device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, d
     // (a reference to the kernel parameter or a generic pointer would force generic loads)
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     const CzDev& Z = reinterpret_cast<const SmemPar*>(smem_dyn + PAR_OFF)->cz[ps];
+    auto tabp = [&](int idx) -> double* { return CONTIG ? tabA + idx * NT : cz_tab(tabA, tabB, idx); };
     const int lane = tid & 31, wid = tid >> 5;
     const int i0 = tid * CH;
     const double r = Z.r, rho = Z.rho;
@@ -573,11 +575,11 @@ __device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, d
             if (last) break;
             const int tb = Z.ev_tab[ev];
             if (Z.ev_kind[ev] == 0) {
-                cz_tab(tabA, tabB, tb * 3 + 0)[tid] = pm;
-                cz_tab(tabA, tabB, tb * 3 + 1)[tid] = d1;
-                cz_tab(tabA, tabB, tb * 3 + 2)[tid] = d2;
+                tabp(tb * 3 + 0)[tid] = pm;
+                tabp(tb * 3 + 1)[tid] = d1;
+                tabp(tb * 3 + 2)[tid] = d2;
             } else {
-                cz_tab(tabA, tabB, 12 + tb)[tid] = acc;
+                tabp(12 + tb)[tid] = acc;
             }
         }
     }
@@ -619,14 +621,14 @@ __device__ __noinline__ void cz_scan(int ps, const double* TT, int n, int tid, d
             const int tb = Z.ev_tab[ev];
             const double pw = Z.ev_pw[ev];
             if (Z.ev_kind[ev] == 0) {
-                double* t0 = cz_tab(tabA, tabB, tb * 3 + 0) + tid;
-                double* t1 = cz_tab(tabA, tabB, tb * 3 + 1) + tid;
-                double* t2 = cz_tab(tabA, tabB, tb * 3 + 2) + tid;
+                double* t0 = tabp(tb * 3 + 0) + tid;
+                double* t1 = tabp(tb * 3 + 1) + tid;
+                double* t2 = tabp(tb * 3 + 2) + tid;
                 *t0 = fma(pw, c_pm, *t0);
                 *t1 += c_d1;
                 *t2 += c_d2;
             } else {
-                double* t = cz_tab(tabA, tabB, 12 + tb) + tid;
+                double* t = tabp(12 + tb) + tid;
                 *t = fma(pw, c_pp, (pp - *t) * Z.ev_rinv[ev]);
             }
         }
@@ -709,6 +711,9 @@ struct CzStream {
     {
         const double tn = tpre;
         tpre = p[k + 1];
+        // every fourth step: the sector three ahead of this lane's stream into L1 (the finish kernel's lanes walk 32 different
+        // chunks, 32 sectors per load; measured in the pipeline: 6.32 -> 6.47 M wf/s, distances 8 / 12 / 20 within 0.5 %)
+        if ((k & 3) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + min(k + 12, CH)));
         const double y = tn - t;
         const double d = fma(-r, yprev, y);
         yprev = y;

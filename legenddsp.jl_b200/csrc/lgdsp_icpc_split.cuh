@@ -501,6 +501,8 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             fence_proxy_async();
             mbar_expect_tx(bar, tt_bytes);
             tma_load_1d(TT, ttg + e * TTG_LEN, tt_bytes, bar);
+            // the next event of this CTA into L2 while this one computes: its bulk copy then runs at L2 speed (+2 %)
+            if (e + gridDim.x < n_events) tma_prefetch_l2(ttg + (e + gridDim.x) * TTG_LEN, tt_bytes);
         }
 #pragma unroll
         for (int q = 0; q < MK_N; ++q) masks[q * NWORDS + tid] = 0u;
@@ -987,7 +989,7 @@ enum { K3R_CZC0 = 0, K3R_CZC1, K3R_CZMAX0, K3R_CZARG0, K3R_CZMAX1, K3R_CZARG1, K
 enum { K3I_CZN = 0, K3I_PKFROM = 1 /* 2 */, K3I_N = 4 };
 constexpr int K3_TT = 0;
 constexpr int K3_TABA = K3_TT + TT_LEN * 8;                 // double tabA[8][NT]
-constexpr int K3_TABB = K3_TABA + 8 * NT * 8;               // double tabB[8][NT]: tables 8..15 (contiguous with tabA)
+constexpr int K3_TABB = K3_TABA + 8 * NT * 8;               // double tabB[8][NT]: tables 8..15 (contiguous with tabA: cz_scan<.., true>)
 constexpr int K3_CZCO = K3_TABB + 8 * NT * 8;               // double czco[2][NT]: coarse CUSP / ZAC values
 constexpr int K3_RED = K3_CZCO + 2 * NT * 8;
 constexpr int K3_STASH = K3_RED + K3R_N * NWARP * 8;        // double stash[2][LGDSP_MAX_DNI] (direct mode)
@@ -1124,6 +1126,8 @@ icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             fence_proxy_async();
             mbar_expect_tx(bar, tt_bytes);
             tma_load_1d(TT, ttg + e * TTG_LEN, tt_bytes, bar);
+            // the next event of this CTA into L2 while this one computes: its bulk copy then runs at L2 speed (+2 %)
+            if (e + gridDim.x < n_events) tma_prefetch_l2(ttg + (e + gridDim.x) * TTG_LEN, tt_bytes);
             ibuf[K3I_CZN] = 0;
         }
         mbar_wait(bar, it & 1u);
@@ -1204,7 +1208,7 @@ icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                 __syncthreads();   // the previous pass is done with the tables, the coarse values and the counters
                 if (tid == 0) ibuf[K3I_CZN] = 0;
             }
-            cz_scan<K3_PAR>(ps, TT, n, tid, tabA, tabB, red + K3R_CZSCR * NWARP, scr + K3S_PP0);
+            cz_scan<K3_PAR, true>(ps, TT, n, tid, tabA, tabB, red + K3R_CZSCR * NWARP, scr + K3S_PP0);
             __syncthreads();   // tables (and the pick-off windows) are complete
             const int pk_from[2] = {ibuf[K3I_PKFROM], ibuf[K3I_PKFROM + 1]};
             cz_select(Z, TT, n, nw, scr[K3S_PP0], scr[K3S_YMAX], pk_from, scr + K3S_PKP, want_cusp, want_zac, czco, red,
