@@ -12,7 +12,7 @@
 
 using namespace lgdsp;
 
-#define LGDSP_SPLIT_MAX_STREAMS 4
+#define LGDSP_SPLIT_MAX_STREAMS 6
 
 struct lgdsp_handle {
     int device = 0;
@@ -81,14 +81,14 @@ struct lgdsp_handle {
     int icpc_path = 1;             // 0: fused icpc_kernel, 1: split pipeline
     int split_bps[3] = {0, 0, 0};
     int64_t split_batch = 0;       // events per batch (0: default)
-    int split_streams = 3;
+    int split_streams = 4;         // stream pairs the sub-batches go round (2 / 3 / 4: 6.35 / 6.56 / 6.67 M wf/s)
     double* d_tt = nullptr;
     double* d_saux = nullptr;
     double* d_scz = nullptr;       // candidate records of the CUSP/ZAC kernels
     int64_t split_cap = 0;         // allocated slots
-    cudaStream_t s_split[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t s_cz[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // CUSP/ZAC kernel next to the extract kernel
-    cudaEvent_t ev_pre[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr}, ev_cz[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t s_split[LGDSP_SPLIT_MAX_STREAMS] = {};
+    cudaStream_t s_cz[LGDSP_SPLIT_MAX_STREAMS] = {};   // CUSP/ZAC kernel next to the extract kernel
+    cudaEvent_t ev_pre[LGDSP_SPLIT_MAX_STREAMS] = {}, ev_cz[LGDSP_SPLIT_MAX_STREAMS] = {};
     int split_par = 1;             // 1: CUSP/ZAC kernel on its own stream
     cudaEvent_t ev_fork = nullptr, ev_join[LGDSP_SPLIT_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
 };
