@@ -325,6 +325,20 @@ __device__ __noinline__ int resolve_runs_packed(const uint32_t* M, int k, int la
         const uint32_t prev = w0 ? M[w0 - 1] : 0u;
         uint32_t starts = mq & ~((mq << 1) | (prev >> 31));
         if (w0 == 0) starts &= ~1u;  // a run that starts at the first sample never fires
+        if (k <= 32) {
+            // short runs (t10..t99, current and pile-up masks): bit-parallel test "k set bits from here on" on the 64-bit window
+            // of this word and the next (AND-doubling) -- no loop over the starts, whose number explodes on noise-only events
+            unsigned long long r = (unsigned long long)mq | ((unsigned long long)(w0 + 1 < NWORDS ? M[w0 + 1] : 0u) << 32);
+            for (int len = 1; len < k;) {
+                const int sft = min(len, k - len);
+                r &= r >> sft;
+                len += sft;
+            }
+            starts &= (uint32_t)r;
+            cnt += __popc(starts);
+            if (starts) p = min(p, w0 * 32 + __ffs(starts) - 1);
+            continue;
+        }
         while (starts) {
             const int b = __ffs(starts) - 1;
             starts &= starts - 1;
