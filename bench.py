@@ -37,7 +37,7 @@ NCOL = 49
 # dram__bytes_read.sum + dram__bytes_write.sum of prefix + extract + CUSP/ZAC select + finish, per event).  The prefix sums
 # (65.6 KB per event) are written once and read by the two consumers through L2/HBM: that is the price of running the chain
 # as kernels with their own occupancy; algorithmic bytes are 16 776 B per waveform.
-NCU_DRAM_BYTES_PER_WF = {"dsp_icpc": 223.1e3}
+NCU_DRAM_BYTES_PER_WF = {"dsp_icpc": 223.9e3}
 
 
 def _peaks():
@@ -369,8 +369,9 @@ def main():
         else:
             h.icpc_run_device(None, pool[k % n_pool].data_ptr(), B, 8192, out.data_ptr())
 
-    def timed(fn, steps, warmup):
-        """device ms (CUDA events on the launching stream, max over ranks) and kernel launches of `steps` calls"""
+    def timed(fn, steps, warmup, finish=None):
+        """device ms (CUDA events on the launching stream, max over ranks) and kernel launches of `steps` calls;
+        finish() (optional) makes the launching stream wait for side-stream work before the end event"""
         for k in range(warmup):
             fn(k)
         torch.cuda.synchronize()
@@ -382,6 +383,8 @@ def main():
         e0.record(stream)
         for k in range(steps):
             fn(k)
+        if finish is not None:
+            finish()
         e1.record(stream)
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -498,22 +501,45 @@ def main():
         table = torch.empty((world, B, NCOL), dtype=torch.float64, device=dev) if rank == 0 else None
         host_tab = [torch.empty((world * B, NCOL), dtype=torch.float64).pin_memory() for _ in range(2)] if rank == 0 else None
 
+        # double-buffered: the gather + D2H of step k run on a side stream under the kernels of step k+1
+        outs2 = [out, torch.empty_like(out)]
+        gs = torch.cuda.Stream(device=dev)
+        ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        used = [False, False]
+
         def gstep(k, compute=True):
+            b = k & 1
             if compute:
-                step(k)
-            if world > 1:
-                dist.gather(out, list(table.unbind(0)) if rank == 0 else None, dst=0)
-                src = table
-            else:
-                src = out
-            if rank == 0:
-                host_tab[k & 1].copy_(src.view(-1, NCOL), non_blocking=True)
-        ms_g, _ = timed(gstep, gsteps, 1)
-        ms_only, _ = timed(lambda k: gstep(k, False), gsteps, 1)
+                if used[b]:
+                    stream.wait_event(ev_free[b])   # the previous gather out of this buffer is done
+                h.icpc_run_device(None, pool[k % n_pool].data_ptr(), B, 8192, outs2[b].data_ptr())
+            ev_done[b].record(stream)
+            with torch.cuda.stream(gs):
+                gs.wait_event(ev_done[b])
+                if world > 1:
+                    dist.gather(outs2[b], list(table.unbind(0)) if rank == 0 else None, dst=0)
+                    src = table
+                else:
+                    src = outs2[b]
+                if rank == 0:
+                    host_tab[b].copy_(src.view(-1, NCOL), non_blocking=True)
+                ev_free[b].record(gs)
+            used[b] = True
+
+        def gfinish():
+            for b in range(2):
+                if used[b]:
+                    stream.wait_event(ev_free[b])
+
+        ms_g, _ = timed(gstep, gsteps, 1, gfinish)
+        ms_only, _ = timed(lambda k: gstep(k, False), gsteps, 1, gfinish)
         gather = {"value_with_gather": world * B * gsteps / (ms_g * 1e-3), "unit": "waveforms/s", "steps": gsteps,
                   "gather_ms_per_step": ms_only / gsteps, "d2h_bytes_per_step_rank0": world * B * NCOL * 8,
                   "how": "per step: kernels, NCCL gather of the 392-byte rows to rank 0 (NVLink; no-op at N=1), one D2H of the "
-                         "gathered table into pinned host memory; gather_ms_per_step is the gather + D2H timed alone"}
+                         "gathered table into pinned host memory; two output buffers: the gather + D2H of step k run on a side "
+                         "stream under the kernels of step k+1, the timed region ends when the last table is in host memory; "
+                         "gather_ms_per_step is the gather + D2H timed alone"}
 
     # ---- the other two single-GPU configurations of BASELINE.json, a few steps each ----
     extra = []
@@ -543,7 +569,7 @@ def main():
         kernel_ms = {"events": nprof, "icpc_prefix_kernel": ms4[0], "icpc_extract_kernel": ms4[1], "icpc_cuspzac_kernel": ms4[2],
                      "icpc_cuspzac_finish_kernel": ms4[3],
                      "note": "one batch run serially with CUDA events between the kernels; in the timed steps the batches of "
-                             "three streams overlap"}
+                             "four stream pairs overlap"}
         tot4 = sum(ms4) or 1.0
         names4 = ("icpc_prefix_kernel", "icpc_extract_kernel", "icpc_cuspzac_kernel", "icpc_cuspzac_finish_kernel")
         top = max(range(4), key=lambda i: ms4[i])
