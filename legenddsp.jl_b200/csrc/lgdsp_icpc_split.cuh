@@ -513,6 +513,7 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
         // phase A: window passes over TT that depend on nothing else
         // ==========================================================================================
         const bool lean = (G & LGDSP_GROUP_LEAN) != 0;   // BASELINE configs[1]: only {blmean, t0, t50, e_trap, e_10410}
+        const TrapDev& T5 = lean ? P.e10410 : P.e535;    // the trapezoid whose maximum alone is wanted (coarse-to-fine)
         if (!lean) {
             double pz_S = 0, pz_SS = 0, pz_SX = 0;
 #pragma unroll 2
@@ -528,19 +529,8 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                 red[K2R_PZS * NW2 + wid] = pz_S; red[K2R_PZSS * NW2 + wid] = pz_SS; red[K2R_PZSX * NW2 + wid] = pz_SX;
             }
         }
-        if (lean) {
-            // the maximum of the (10 us, 4 us) trapezoid trace only
-            double mx = -CUDART_INF;
-            const TrapDev& A = P.e10410;
-            const double* p0 = TT + tid;
-#pragma unroll 2
-            for (int off = 0; off < A.nout - tid; off += NT2) {
-                const double o = __fma_rn(p0[off + A.L] - p0[off + A.a + A.g], A.inv2, -__dmul_rn(p0[off + A.a] - p0[off], A.inv1));
-                mx = o > mx ? o : mx;
-            }
-            const double a = wmax_d(mx);
-            if (lane == 0) red[K2R_E104 * NW2 + wid] = a;
-        } else if (G & LGDSP_GROUP_TRAPS) {
+        // (lean: only the MAXIMUM of the (10 us, 4 us) trapezoid is wanted, so it is pruned coarse-to-fine like e_535 below -- T5)
+        if (!lean && (G & LGDSP_GROUP_TRAPS)) {
             double o4[4];
             trap_full2_minmax(TT, P.e10410, P.e313, tid, o4);
             const double a = wmax_d(o4[0]), b = wmax_d(o4[1]), c = wmax_d(o4[2]), d = wmax_d(o4[3]);
@@ -561,14 +551,17 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                     if (jb < P.t0inv.nout) cib = trap_at_i(TT, P.t0inv, jb);
                 }
             }
-            if ((G & LGDSP_GROUP_TRAPS) && !lean) {
-                if (ja < P.e535.nout) c5a = trap_at_i(TT, P.e535, ja);
-                if (jb < P.e535.nout) c5b = trap_at_i(TT, P.e535, jb);
-                if (ja < P.etrap.nout) cea = trap_at_i(TT, P.etrap, ja);
-                if (jb < P.etrap.nout) ceb = trap_at_i(TT, P.etrap, jb);
-                const double w5 = wmax_d(c5a), we = wmax_d(cea);
+            if (G & LGDSP_GROUP_TRAPS) {
+                if (ja < T5.nout) c5a = trap_at_i(TT, T5, ja);
+                if (jb < T5.nout) c5b = trap_at_i(TT, T5, jb);
+                const double w5 = wmax_d(c5a);
                 red_put(red, K2R_C535, wid, lane, w5);
-                red_put(red, K2R_CET, wid, lane, we);
+                if (!lean) {
+                    if (ja < P.etrap.nout) cea = trap_at_i(TT, P.etrap, ja);
+                    if (jb < P.etrap.nout) ceb = trap_at_i(TT, P.etrap, jb);
+                    const double we = wmax_d(cea);
+                    red_put(red, K2R_CET, wid, lane, we);
+                }
             }
         }
         double sgcmax = -CUDART_INF;
@@ -708,8 +701,8 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                             false, 0, q, lane);
             } else if (type == 2) {
                 const int j = q * CH + 1 + lane;
-                if (j < P.e535.nout) {
-                    const double o = trap_at_i(TT, P.e535, j);
+                if (j < T5.nout) {
+                    const double o = trap_at_i(TT, T5, j);
                     e535 = o > e535 ? o : e535;
                 }
             } else if (type == 3) {
@@ -760,12 +753,15 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                     if (na) mask_commit(masks + MK_T0INV * NWORDS, tid, 1ull);
                 }
             }
-            if ((G & LGDSP_GROUP_TRAPS) && !lean) {
-                const double M5 = red_max(red, K2R_C535), Me = red_max(red, K2R_CET);
-                const double k5 = Ymax * 2.0 * (P.e535.inv1 + P.e535.inv2) * 1.000001;
-                const double ke = Ymax * 2.0 * (P.etrap.inv1 + P.etrap.inv2) * 1.000001;
-                if (i0 + 1 < P.e535.nout) f5 = interval_bound(c5a, c5b, i0 + CH < P.e535.nout, k5) + kslack >= M5;
-                if (i0 + 1 < P.etrap.nout) fe = interval_bound(cea, ceb, i0 + CH < P.etrap.nout, ke) + kslack >= Me;
+            if (G & LGDSP_GROUP_TRAPS) {
+                const double M5 = red_max(red, K2R_C535);
+                const double k5 = Ymax * 2.0 * (T5.inv1 + T5.inv2) * 1.000001;
+                if (i0 + 1 < T5.nout) f5 = interval_bound(c5a, c5b, i0 + CH < T5.nout, k5) + kslack >= M5;
+                if (!lean) {
+                    const double Me = red_max(red, K2R_CET);
+                    const double ke = Ymax * 2.0 * (P.etrap.inv1 + P.etrap.inv2) * 1.000001;
+                    if (i0 + 1 < P.etrap.nout) fe = interval_bound(cea, ceb, i0 + CH < P.etrap.nout, ke) + kslack >= Me;
+                }
             }
             flags = (f0 ? 1u : 0u) | (fi ? 2u : 0u) | (f5 ? 4u : 0u) | (fe ? 8u : 0u);
         }
@@ -874,7 +870,7 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
             if (G & LGDSP_GROUP_TRAPS) {
                 const double v = dni_eval_warp(A_sig, P.sig_dni.n_w, P.sig_dni.m, stash, pk_p - (double)pk_from, lane);
                 if (lean) {
-                    const double a = red_max(red, K2R_E104);
+                    const double a = red_max(red, K2R_E535);   // (the pruned maximum of T5 = e_10410)
                     if (lane == 0) { row[LGDSP_COL_e_10410] = a; row[LGDSP_COL_e_trap] = v; }
                 }
                 double em = 0;
