@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "liblgdsp_b200.so")
 SOURCES = ("lgdsp_api.cu", "lgdsp_icpc.cu", "lgdsp_sipm.cu", "lgdsp_codec.cu", "lgdsp_synth.cu", "lgdsp_host_filters.cpp")
-HEADERS = ("lgdsp_device.cuh", "lgdsp_kernels.h", "lgdsp_synth.cuh", "lgdsp_icpc_split.cuh", os.path.join("..", "..", "include", "lgdsp_b200.h"))
+HEADERS = ("lgdsp_device.cuh", "lgdsp_kernels.h", "lgdsp_synth.cuh", "lgdsp_icpc_split.cuh", "lgdsp_sweep_warp.cuh", os.path.join("..", "..", "include", "lgdsp_b200.h"))
 NVCC_FLAGS = ["-O3", "-std=c++17", "--threads", "4", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -1,6 +1,7 @@
 // C ABI of liblgdsp_b200 (include/lgdsp_b200.h): handle management, parameter validation/upload, launches.
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1531,6 +1532,33 @@ static int sweep_prepare(lgdsp_handle* h, const lgdsp_sweep_params* p, const lgd
     D.dni_A = h->d_sweep_dniA; D.vars = h->d_vars; D.nvar = nvar; D.out_f64 = p->out_f64 ? 1 : 0;
     D.n_other = 0;
     for (int v = 0; v < nvar; ++v) D.n_other += (sv[v].kind != 0);
+    // Reach of the variant set around the crossing sample `pos` of t50 (t50 lies in [pos-1, pos]):
+    // from = rint(pc) - n_w/2, pc = (t50 - t_first)/dt + pick/dt - (L-1)  (dni_window), look-ups in [from, from + L + n_w)
+    D.warp_ok = 0;
+    if (D.n_other == 0) {
+        bool all1 = true, all0 = true;
+        double lo = 1e300, hi = -1e300;
+        for (int v = 0; v < nvar; ++v) {
+            all1 = all1 && sv[v].mode != 0;
+            all0 = all0 && sv[v].mode == 0;
+            const double rel = sv[v].pick_ns / p->dt_ns - (double)(sv[v].L - 1) - (double)(d.n_w / 2);
+            const double base = sv[v].mode ? rel : rel - p->t_first_ns / p->dt_ns;
+            lo = std::min(lo, std::floor(base - 1.5) - 2.0);
+            hi = std::max(hi, std::ceil(base + 0.5) + (double)(sv[v].L + d.n_w) + 2.0);
+        }
+        if (all1) { lo = std::min(lo, -3.0); hi = std::max(hi, 3.0); }
+        const int wmax = sweep_warp_max_window();
+        int longest = 0;
+        for (int v = 0; v < nvar; ++v) longest = std::max(longest, sv[v].L + d.n_w + 2);
+        if ((all1 || all0) && wmax > 0 && hi - lo <= (double)wmax && longest <= wmax && std::fabs(lo) < 1e9) {
+            const int need = std::max((int)(hi - lo), longest);
+            D.win_steps = std::max(6, (need + 287) / 288);
+            D.win_mode = all1 ? 1 : 0;
+            D.win_rel_lo = all1 ? (int)lo : 0;
+            D.win_abs_lo = all1 ? 0 : std::max(0, (int)lo);
+            D.warp_ok = D.win_steps * 288 <= wmax ? 1 : 0;
+        }
+    }
     D.bl_inv_n = 1.0 / (double)(p->bl_until - p->bl_from + 1);
     {
         typedef long double ld;
@@ -1560,7 +1588,8 @@ static int sweep_run_device_impl(lgdsp_handle* h, const lgdsp_sweep_params* p, c
     const long long cap = (long long)h->sm_count * h->sweep_bps;
     const int grid = (int)(n_events < cap ? n_events : cap);
     CK(cudaEventRecord(h->ev0, h->stream));
-    sweep_launch(D, d_wf, sample_bytes, n_events, ld_samples, d_baseline, d_out, d_aux, grid, h->stream);
+    if (sweep_launch(D, p->sig_dni.A, d_wf, sample_bytes, n_events, ld_samples, d_baseline, d_out, d_aux, grid, h->sm_count, h->stream) < 0)
+        return fail(h, LGDSP_ERR_UNSUPPORTED, "LGDSP_SWEEP_PATH=warp: this variant set / sample type runs on the one-CTA-per-waveform kernel");
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
@@ -1618,7 +1647,8 @@ static int sweep_run_host_impl(lgdsp_handle* h, const lgdsp_sweep_params* p, con
         void* d_o = base + (size_t)b * out_bytes;
         double* d_a = aux ? reinterpret_cast<double*>(base + 2 * out_bytes) + (size_t)b * chunk * 4 : nullptr;
         const int grid = (int)(ne < cap ? ne : cap);
-        sweep_launch(D, h->d_in[b], sample_bytes, ne, n, d_bl, d_o, d_a, grid, h->stream);
+        if (sweep_launch(D, p->sig_dni.A, h->d_in[b], sample_bytes, ne, n, d_bl, d_o, d_a, grid, h->sm_count, h->stream) < 0)
+            return fail(h, LGDSP_ERR_UNSUPPORTED, "LGDSP_SWEEP_PATH=warp: this variant set / sample type runs on the one-CTA-per-waveform kernel");
         CK(cudaGetLastError());
         h->launches += 1;
         CK(cudaEventRecord(h->ev_free[b], h->stream));

@@ -29,6 +29,8 @@
 // The waveform is read from HBM exactly once (16 KB) and 392 B are written.
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include "lgdsp_device.cuh"
 #include "lgdsp_kernels.h"
@@ -2287,8 +2289,8 @@ sweep_kernel(const __grid_constant__ SweepDev P, const SAMPLE* __restrict__ wf, 
             const double pick = P.vars[v].pick_ns;
             const int mode = P.vars[v].mode;
             const int nout = n - t.L + 1;
-            const double tf = t_first + (double)(t.L - 1) * dt;
-            const double t_ns = mode ? t50_us * 1000.0 + pick : pick;
+            const double tf = __fma_rn((double)(t.L - 1), dt, t_first);
+            const double t_ns = mode ? __fma_rn(t50_us, 1000.0, pick) : pick;
             double pc;
             int from;
             dni_window(n_w, nout, (t_ns - tf) / dt, pc, from);
@@ -2299,7 +2301,7 @@ sweep_kernel(const __grid_constant__ SweepDev P, const SAMPLE* __restrict__ wf, 
             double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll 2
             for (int i = 0; i < n_w; ++i) {
-                const double val = (p3[i] - p2[i]) * t.inv2 - (p1[i] - p0[i]) * t.inv1;
+                const double val = __fma_rn(p3[i] - p2[i], t.inv2, -__dmul_rn(p1[i] - p0[i], t.inv1));
                 const double* a = dniA + i * mdeg;
                 c0 = fma(a[0], val, c0);
                 if (mdeg > 1) c1 = fma(a[1], val, c1);
@@ -2383,13 +2385,34 @@ cudaError_t sweep_configure(int* max_blocks_per_sm)
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, sweep_kernel<uint16_t>, NT, SW_TOTAL);
 }
 
-void sweep_launch(const SweepDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld, const double* d_bl_ext,
-                  void* d_out, double* d_aux, int grid, cudaStream_t stream)
+#include "lgdsp_sweep_warp.cuh"
+
+int sweep_warp_max_window() { return SWW_MAX_STEPS * SWW_STEP; }
+
+int sweep_launch(const SweepDev& P, const double* dni_A_host, const void* d_wf, int sample_bytes, long long n_events, long long ld,
+                 const double* d_bl_ext, void* d_out, double* d_aux, int grid, int sm_count, cudaStream_t stream)
 {
+    // LGDSP_SWEEP_PATH=cta forces the one-CTA-per-waveform kernel (A/B tests)
+    const char* env = getenv("LGDSP_SWEEP_PATH");
+    if (P.warp_ok && sample_bytes == 2 && dni_A_host && !(env && strcmp(env, "cta") == 0)) {
+        const SwwGeom g = sww_geometry(P.win_steps);
+        if (g.warps_per_cta > 0) {
+            SweepDni D;
+            memcpy(D.A, dni_A_host, sizeof(D.A));
+            const long long ctas_needed = (n_events + g.warps_per_cta - 1) / g.warps_per_cta;
+            const long long cap = (long long)sm_count * g.ctas_per_sm;
+            const int wgrid = (int)(ctas_needed < cap ? ctas_needed : cap);
+            sweep_warp_kernel<<<wgrid, g.warps_per_cta * 32, (size_t)g.warps_per_cta * sww_warp_bytes(P.win_steps), stream>>>(
+                P, D, static_cast<const uint16_t*>(d_wf), n_events, ld, d_bl_ext, d_out, d_aux);
+            return 1;
+        }
+    }
+    if (env && strcmp(env, "warp") == 0) return -1;   // the test suite demands the warp path
     if (sample_bytes == 4)
         sweep_kernel<uint32_t><<<grid, NT, SW_TOTAL, stream>>>(P, static_cast<const uint32_t*>(d_wf), n_events, ld, d_bl_ext, d_out, d_aux);
     else
         sweep_kernel<uint16_t><<<grid, NT, SW_TOTAL, stream>>>(P, static_cast<const uint16_t*>(d_wf), n_events, ld, d_bl_ext, d_out, d_aux);
+    return 0;
 }
 
 void icpc_launch(const IcpcDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld, const double* d_bl_ext,

@@ -47,10 +47,19 @@ struct SweepDev {
     int nvar, out_f64;
     int n_other, reserved;   // variants of kind != 0 (0: the per-warp FIR / SG pass is skipped)
     double bl_inv_n, bl_sX, bl_sXX;   // baseline regression constants (aux outputs)
+    // one-warp-per-waveform path (lgdsp_sweep_warp.cuh): warp_ok = 1 when every variant is a trapezoid of one pick-off mode
+    // and the prefix-sum window the set can reach fits win_steps * 288 samples.  win_mode 1: the first window starts at
+    // (crossing sample + win_rel_lo); 0: at win_abs_lo
+    int warp_ok, win_steps, win_mode, win_rel_lo, win_abs_lo, reserved2;
 };
 cudaError_t sweep_configure(int* max_blocks_per_sm);
-void sweep_launch(const SweepDev& P, const void* d_wf, int sample_bytes, long long n_events, long long ld, const double* d_bl_ext,
-                  void* d_out, double* d_aux, int grid, cudaStream_t stream);
+// dni_A_host: the fit matrix on the host (the warp path passes it in the constant bank); sm_count sizes the warp path's grid.
+// Returns 1: one-warp-per-waveform kernel launched, 0: one-CTA-per-waveform kernel launched, -1: nothing launched
+// (LGDSP_SWEEP_PATH=warp demands the warp path and the variant set is not eligible)
+int sweep_launch(const SweepDev& P, const double* dni_A_host, const void* d_wf, int sample_bytes, long long n_events, long long ld,
+                 const double* d_bl_ext, void* d_out, double* d_aux, int grid, int sm_count, cudaStream_t stream);
+// window capacity of the warp path in samples (0: path unavailable on this device)
+int sweep_warp_max_window();
 
 // ---- waveform codecs of decode_data (lgdsp_codec.cu) ----
 long long codec_max_encoded_bytes(int codec, int n_samples, int sample_bytes);
