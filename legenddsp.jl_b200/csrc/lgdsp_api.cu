@@ -1552,7 +1552,7 @@ static int sweep_prepare(lgdsp_handle* h, const lgdsp_sweep_params* p, const lgd
         for (int v = 0; v < nvar; ++v) longest = std::max(longest, sv[v].L + d.n_w + 2);
         if ((all1 || all0) && wmax > 0 && hi - lo <= (double)wmax && longest <= wmax && std::fabs(lo) < 1e9) {
             const int need = std::max((int)(hi - lo), longest);
-            D.win_steps = std::max(6, (need + 287) / 288);
+            D.win_steps = std::max(4, (need + 287) / 288);   // (>= 4: the window area also holds pass 1's group table)
             D.win_mode = all1 ? 1 : 0;
             D.win_rel_lo = all1 ? (int)lo : 0;
             D.win_abs_lo = all1 ? 0 : std::max(0, (int)lo);

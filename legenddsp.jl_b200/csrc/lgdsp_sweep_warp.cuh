@@ -5,13 +5,16 @@
 // to amortise them, and builds the prefix sums of the WHOLE pole-zero waveform although a trapezoid sweep only reads
 // them in a window of ~2 200 samples around t50.  Here a warp owns a waveform from the first load to the last store:
 //
-//   baseline   sum x, sum i*x over bl_window (128-bit loads, exact integers)                                     [:250-253]
-//   pass 1     whole waveform, 8 consecutive samples per lane and step (one 128-bit load, two steps ahead):
-//              exact integer prefix sums P (warp scan), y = w + km1*cumsum(w) in closed form -> max(y);
-//              per 8-sample group its [min y, max y] (float, rounded outwards) and P at its start -> SMEM;
-//              P and PP = cumsum(P) at every 256-sample boundary -> SMEM                                          [:255-256]
-//   pass 1b    threshold 0.5*max(y) [:260]: a group entirely below / above the threshold gives a 0x00 / 0xff mask byte,
-//              the others (the rising edge; every group of a noise-only event) are re-evaluated sample by sample;
+//   pass 1     whole waveform, INTEGERS only, 16 consecutive samples per lane and step (two 128-bit loads, two steps ahead):
+//              exact prefix sums P (warp scan); per 16-sample group P at its start and its largest / smallest sample -> SMEM;
+//              P and PP = cumsum(P) at every 512-sample boundary -> SMEM
+//   baseline   sum x, sum i*x over bl_window as differences of P / PP (two or three look-ups)                      [:250-253]
+//   pass 1a    y = w + km1*cumsum(w) [:255-256] is NOT evaluated everywhere: from a group's extreme samples and P follow rigorous
+//              bounds of y over the group (float, rounded outwards -> SMEM); every lane evaluates its most promising group in
+//              float64, and only groups whose upper bound reaches the best value found are evaluated too (a few per cent of
+//              a flat top) -> max(y), exactly the float64 value a full evaluation gives
+//   pass 1b    threshold 0.5*max(y) [:260]: a group whose bounds lie below / above the threshold gives a 0x00 / 0xff mask byte,
+//              the others (the rising edge; every group of a noise-only event) are evaluated sample by sample;
 //              bit-parallel Intersect run detection (resolve_runs) -> first crossing sample
 //   pass 2     prefix sums TT of the pole-zero waveform ONLY in a window [lo, lo + W) around the crossing (W from the host:
 //              what the variant set can reach), 9 consecutive samples per lane and step (odd stride: conflict-free 64-bit
@@ -27,10 +30,10 @@
 // variant sets whose reach exceeds the window capacity.
 
 constexpr int SWW_STEP = 288;        // samples per window-build step (9 per lane)
-constexpr int SWW_MIN_STEPS = 6;     // the window area also holds pass 1's group table (12 KB)
+constexpr int SWW_MIN_STEPS = 4;     // the window area also holds pass 1's group table (8 KB)
 constexpr int SWW_MAX_STEPS = 10;
 constexpr int SWW_MAX_WARPS = 12;    // warps per CTA (launch bound)
-constexpr int SWW_EXT_BYTES = 8192;  // float2 per 8-sample group
+constexpr int SWW_EXT_BYTES = 4096;  // float2 per 16-sample group
 __host__ __device__ constexpr int sww_win_bytes(int steps) { return (steps * SWW_STEP + 8) * 8; }
 __host__ __device__ constexpr int sww_warp_bytes(int steps) { return sww_win_bytes(steps) + NWORDS * 4 + 36 * 4 + 34 * 8; }
 
@@ -48,6 +51,108 @@ __device__ __forceinline__ double sww_y(uint32_t x, uint32_t Pincl, double ip1, 
     return fma(km1, Sd, w);
 }
 
+// the 16 consecutive samples of lane-group i0 (multiple of 16; the trace length is a multiple of 8: the second half may lie
+// beyond the trace and reads as zeros)
+__device__ __forceinline__ void sww_ld16(const uint16_t* __restrict__ x, int i0, int n, uint32_t (&v)[16])
+{
+    const uint4 r0 = (i0 < n) ? sww_ld8(x + i0) : make_uint4(0u, 0u, 0u, 0u);
+    const uint4 r1 = (i0 + 8 < n) ? sww_ld8(x + i0 + 8) : make_uint4(0u, 0u, 0u, 0u);
+    v[0] = r0.x & 0xffffu; v[1] = r0.x >> 16; v[2] = r0.y & 0xffffu; v[3] = r0.y >> 16;
+    v[4] = r0.z & 0xffffu; v[5] = r0.z >> 16; v[6] = r0.w & 0xffffu; v[7] = r0.w >> 16;
+    v[8] = r1.x & 0xffffu; v[9] = r1.x >> 16; v[10] = r1.y & 0xffffu; v[11] = r1.y >> 16;
+    v[12] = r1.z & 0xffffu; v[13] = r1.z >> 16; v[14] = r1.w & 0xffffu; v[15] = r1.w >> 16;
+}
+
+// P_excl(i) = sum_{j<i} x_j and PP_excl(i) = sum_{j<i} P_incl(j) for 0 <= i <= n from the 512-sample boundary carries plus the
+// partial step before i (warp-cooperative, i warp-uniform; every lane gets the result)
+__device__ __forceinline__ void sww_prefix_at(const uint16_t* __restrict__ x, int n, const uint32_t* cP, const double* cPP, int i,
+                                              int lane, uint32_t& Pq, double& PPq)
+{
+    const int bq = i >> 9, rem = i & 511;
+    Pq = cP[bq];
+    PPq = cPP[bq];
+    if (rem) {
+        const int j0 = 16 * lane;
+        uint32_t v[16];
+        sww_ld16(x, bq * 512 + j0, n, v);
+        uint32_t dP = 0, dPP = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int j = j0 + k;
+            dP += (j < rem) ? v[k] : 0u;
+            dPP += (j < rem) ? v[k] * (uint32_t)(rem - j) : 0u;
+        }
+        PPq += (double)rem * u2d(Pq) + warp_sum((double)dPP);
+        Pq += __reduce_add_sync(FULL, dP);
+    }
+}
+
+// exact maximum of y over the 16-sample group that starts at sample i0 (P_excl(i0) = Pst); samples beyond the trace excluded
+__device__ __forceinline__ double sww_group_max(const uint16_t* __restrict__ x, int i0, int n, uint32_t Pst, double m, double km1)
+{
+    uint32_t v[16];
+    sww_ld16(x, i0, n, v);
+    const double ib = (double)(i0 + 1);
+    double gmax = -CUDART_INF;
+    uint32_t Pr = Pst;
+    const int kn = (i0 + 8 < n) ? 16 : 8;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        Pr += v[k];
+        const double y = sww_y(v[k], Pr, ib + (double)k, m, km1);
+        gmax = (y > gmax && k < kn) ? y : gmax;
+    }
+    return gmax;
+}
+// bit k: y(i0 + k) >= thr
+__device__ __forceinline__ uint32_t sww_group_bits(const uint16_t* __restrict__ x, int i0, int n, uint32_t Pst, double m, double km1,
+                                                   double thr)
+{
+    uint32_t v[16];
+    sww_ld16(x, i0, n, v);
+    const double ib = (double)(i0 + 1);
+    uint32_t Pr = Pst, b = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        Pr += v[k];
+        b |= (sww_y(v[k], Pr, ib + (double)k, m, km1) >= thr) ? (1u << k) : 0u;
+    }
+    return (i0 + 8 < n) ? b : (b & 0xffu);
+}
+
+// sum_i A[i][j] * trap(from + i), j < mdeg: the PolynomialDNI coefficient sums of one variant.  NW/MD > 0: the window length and
+// degree+1 are compile-time constants, the loop is unrolled completely and the fit matrix enters the FMAs as constant-bank
+// operands (no load instruction, no index arithmetic); NW = 0: run-time sizes
+template <int NW, int MD>
+__device__ __forceinline__ void sww_dni_sums(const SweepDni& D, const double* p0, const TrapDev& t, int n_w, int mdeg, double& c0,
+                                             double& c1, double& c2, double& c3)
+{
+    const double* p1 = p0 + t.a;
+    const double* p2 = p1 + t.g;
+    const double* p3 = p0 + t.L;
+    c0 = 0; c1 = 0; c2 = 0; c3 = 0;
+    if (NW > 0) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const double val = __fma_rn(p3[i] - p2[i], t.inv2, -__dmul_rn(p1[i] - p0[i], t.inv1));
+            c0 = fma(D.A[i * MD], val, c0);
+            if (MD > 1) c1 = fma(D.A[i * MD + 1], val, c1);
+            if (MD > 2) c2 = fma(D.A[i * MD + 2], val, c2);
+            if (MD > 3) c3 = fma(D.A[i * MD + 3], val, c3);
+        }
+    } else {
+#pragma unroll 4
+        for (int i = 0; i < n_w; ++i) {
+            const double val = __fma_rn(p3[i] - p2[i], t.inv2, -__dmul_rn(p1[i] - p0[i], t.inv1));
+            const double* a = D.A + i * mdeg;
+            c0 = fma(a[0], val, c0);
+            if (mdeg > 1) c1 = fma(a[1], val, c1);
+            if (mdeg > 2) c2 = fma(a[2], val, c2);
+            if (mdeg > 3) c3 = fma(a[3], val, c3);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SWW_MAX_WARPS * 32, 1)
 sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ SweepDni D, const uint16_t* __restrict__ wf,
                   long long n_events, long long ld, const double* __restrict__ bl_ext, void* __restrict__ out,
@@ -61,87 +166,121 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
     double* win = reinterpret_cast<double*>(base);
     float2* ext = reinterpret_cast<float2*>(base);
     uint32_t* pst = reinterpret_cast<uint32_t*>(base + SWW_EXT_BYTES);
+    uint32_t* xmm = pst + MAXN / 16;
     uint32_t* mask = reinterpret_cast<uint32_t*>(base + sww_win_bytes(steps));
     uint32_t* cP = mask + NWORDS;
     double* cPP = reinterpret_cast<double*>(cP + 36);
 
-    const int n = P.n, n_it = (n + 255) >> 8;
+    const int n = P.n, n_it = (n + 511) >> 9;
     const double t_first = P.t_first, dt = P.dt, km1 = P.km1;
     const int n_w = P.sig_dni.n_w, mdeg = P.sig_dni.m;
     const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
     for (long long e = (long long)blockIdx.x * (blockDim.x >> 5) + wib; e < n_events; e += wstride) {
         const uint16_t* __restrict__ x = wf + e * ld;
         if (lane == 0 && e + wstride < n_events) tma_prefetch_l2(wf + (e + wstride) * ld, (uint32_t)n * 2u);
 
-        // ---- baseline window: sum x, sum i*x (exact) ----
-        uint32_t blS = 0;
-        unsigned long long blSX = 0;
-        for (int g = (P.bl_from >> 3) + lane; g <= (P.bl_until >> 3); g += 32) {
-            const uint4 r = sww_ld8(x + 8 * g);
-            const uint32_t v[8] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16, r.z & 0xffffu, r.z >> 16, r.w & 0xffffu, r.w >> 16};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = 8 * g + k;
-                const bool in = (i >= P.bl_from && i <= P.bl_until);
-                blS += in ? v[k] : 0u;
-                if (aux) blSX += in ? (unsigned long long)v[k] * (unsigned)i : 0ull;
-            }
-        }
-        blS = __reduce_add_sync(FULL, blS);
-        const double blSd = (double)blS;
-        const double blSXd = aux ? warp_sum((double)blSX) : 0.0;
-        const double m_own = mul_rn(blSd, P.bl_inv_n);
-        const double m = bl_ext ? bl_ext[e] : m_own;
-
-        // ---- pass 1: max(y), group table, boundary carries ----
+        // ---- pass 1 (integers only): prefix sums, group table (P at the group start, max / min sample), boundary carries ----
         uint32_t carryP = 0;
         unsigned long long carryPP = 0;
-        double ymax = -CUDART_INF;
-        uint4 nx1 = (8 * lane < n) ? sww_ld8(x + 8 * lane) : zero4;
-        uint4 nx2 = (256 + 8 * lane < n) ? sww_ld8(x + 256 + 8 * lane) : zero4;
+        uint32_t v[16], vn[16];
+        sww_ld16(x, 16 * lane, n, v);
+        sww_ld16(x, 512 + 16 * lane, n, vn);
 #pragma unroll 1
         for (int it = 0; it < n_it; ++it) {
-            const uint4 r = nx1;
-            nx1 = nx2;
-            {
-                const int i2 = (it + 2) * 256 + 8 * lane;
-                nx2 = (i2 < n) ? sww_ld8(x + i2) : zero4;
-            }
-            const int i0 = it * 256 + 8 * lane;
-            const bool act = i0 < n;
+            uint32_t vf[16];
+            sww_ld16(x, (it + 2) * 512 + 16 * lane, n, vf);    // two steps ahead
             if (lane == 0) { cP[it] = carryP; cPP[it] = (double)carryPP; }
-            const uint32_t v[8] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16, r.z & 0xffffu, r.z >> 16, r.w & 0xffffu, r.w >> 16};
-            uint32_t s[8];
+            uint32_t s[16];
             s[0] = v[0];
 #pragma unroll
-            for (int k = 1; k < 8; ++k) s[k] = s[k - 1] + v[k];
-            uint32_t incl = s[7];
+            for (int k = 1; k < 16; ++k) s[k] = s[k - 1] + v[k];
+            const int i0 = it * 512 + 16 * lane;
+            uint32_t xmax = __vimax3_u32(__vimax3_u32(v[0], v[1], v[2]), __vimax3_u32(v[3], v[4], v[5]), __vimax3_u32(v[6], v[7], v[7]));
+            uint32_t xmin = __vimin3_u32(__vimin3_u32(v[0], v[1], v[2]), __vimin3_u32(v[3], v[4], v[5]), __vimin3_u32(v[6], v[7], v[7]));
+            if (i0 + 8 < n) {
+                xmax = __vimax3_u32(__vimax3_u32(v[8], v[9], v[10]), __vimax3_u32(v[11], v[12], v[13]), __vimax3_u32(v[14], v[15], xmax));
+                xmin = __vimin3_u32(__vimin3_u32(v[8], v[9], v[10]), __vimin3_u32(v[11], v[12], v[13]), __vimin3_u32(v[14], v[15], xmin));
+            }
+            uint32_t incl = s[15];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(FULL, incl, o);
                 if (lane >= o) incl += t;
             }
-            const uint32_t Pst = carryP + incl - s[7];
-            // sum over the 256 samples of the step of P(i): 256*carryP + 8*sum_l excl_l + sum_l sum_k s_l[k]
-            const uint32_t tl = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-            const uint32_t sum_t = __reduce_add_sync(FULL, tl);
-            const uint32_t sum_ex = __reduce_add_sync(FULL, (uint32_t)(31 - lane) * s[7]);
-            carryPP += 256ull * carryP + 8ull * sum_ex + sum_t;
-            carryP += __shfl_sync(FULL, incl, 31);
-            double gmax = -CUDART_INF, gmin = CUDART_INF;
-            const double ib = (double)(i0 + 1);
+            const uint32_t Pst = carryP + incl - s[15];
+            // sum over the 512 samples of the step of P(i): 512*carryP + 16*sum_l excl_l + sum_l sum_k s_l[k]
+            uint32_t tl = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const double y = sww_y(v[k], Pst + s[k], ib + (double)k, m, km1);
-                gmax = y > gmax ? y : gmax;
-                gmin = y < gmin ? y : gmin;
-            }
-            if (act) {
-                ymax = gmax > ymax ? gmax : ymax;
-                ext[it * 32 + lane] = make_float2(__double2float_ru(gmax), __double2float_rd(gmin));
+            for (int k = 0; k < 16; k += 4) tl += (s[k] + s[k + 1]) + (s[k + 2] + s[k + 3]);
+            const uint32_t sum_t = __reduce_add_sync(FULL, tl);
+            const uint32_t sum_ex = __reduce_add_sync(FULL, (uint32_t)(31 - lane) * s[15]);
+            carryPP += 512ull * carryP + 16ull * sum_ex + sum_t;
+            carryP += __shfl_sync(FULL, incl, 31);
+            if (i0 < n) {
                 pst[it * 32 + lane] = Pst;
+                xmm[it * 32 + lane] = (xmax << 16) | xmin;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { v[k] = vn[k]; vn[k] = vf[k]; }
+        }
+        if (lane == 0) { cP[n_it] = carryP; cPP[n_it] = (double)carryPP; }
+        __syncwarp();
+
+        // ---- baseline window from the prefix sums: sum x = P(b+1) - P(a), sum i*x = b*P(b+1) - a*P(a) - (PP(b) - PP(a)) ----
+        double blSd, blSXd = 0.0;
+        {
+            uint32_t Qa, Qb1;
+            double PPa, PPb, PPb1;
+            sww_prefix_at(x, n, cP, cPP, P.bl_from, lane, Qa, PPa);
+            sww_prefix_at(x, n, cP, cPP, P.bl_until + 1, lane, Qb1, PPb1);
+            blSd = u2d(Qb1 - Qa);
+            if (aux) {
+                uint32_t Qb;
+                sww_prefix_at(x, n, cP, cPP, P.bl_until, lane, Qb, PPb);
+                blSXd = ((double)P.bl_until * u2d(Qb1) - (double)P.bl_from * u2d(Qa)) - (PPb - PPa);
+            }
+        }
+        const double m_own = mul_rn(blSd, P.bl_inv_n);
+        const double m = bl_ext ? bl_ext[e] : m_own;
+
+        // ---- pass 1a: rigorous bounds of y over every group -> table; max(y) from the few groups that can hold it ----
+        // y_k = d_k + km1*Sd_k, d_k = x_k - m, Sd_k = Sd_0 + sum_{j<=k} d_j with Sd_0 = P(group start) - i0*m, so within a group
+        //   Sd_0 + 16*min(0, d_min) <= Sd_k <= Sd_0 + 16*max(0, d_max);  the sample that attains d_max has y >= d_max + km1*Sd_lo.
+        // G covers the rounding of the float64 evaluation (|terms| < 2^17 + |km1| n 2^16, one ulp each).
+        const double G = 1e-9 * (65536.0 + fabs(m) + fabs(km1) * (double)n * 65536.0);
+        double lbmax = -CUDART_INF;
+        float best_ub = -CUDART_INF_F;
+        int best_it = 0;
+#pragma unroll 1
+        for (int it = 0; it < n_it; ++it) {
+            const int i0 = it * 512 + 16 * lane;
+            if (i0 >= n) break;
+            const uint32_t xm = xmm[it * 32 + lane];
+            const double dmax = u2d(xm >> 16) - m, dmin = u2d(xm & 0xffffu) - m;
+            const double Sd0 = fma(-(double)i0, m, u2d(pst[it * 32 + lane]));
+            const double Sd_hi = fma(16.0, dmax > 0.0 ? dmax : 0.0, Sd0), Sd_lo = fma(16.0, dmin < 0.0 ? dmin : 0.0, Sd0);
+            const double k_hi = km1 >= 0.0 ? Sd_hi : Sd_lo, k_lo = km1 >= 0.0 ? Sd_lo : Sd_hi;
+            const double ub = fma(km1, k_hi, dmax) + G;
+            const double lb_all = fma(km1, k_lo, dmin) - G;
+            const double lb_top = fma(km1, k_lo, dmax) - G;
+            lbmax = lb_top > lbmax ? lb_top : lbmax;
+            const float ubf = __double2float_ru(ub);
+            ext[it * 32 + lane] = make_float2(ubf, __double2float_rd(lb_all));
+            if (ubf > best_ub) { best_ub = ubf; best_it = it; }
+        }
+        // every lane evaluates the group with its largest upper bound exactly: a lower bound close to the maximum ...
+        double ymax = -CUDART_INF;
+        if (16 * lane < n) ymax = sww_group_max(x, best_it * 512 + 16 * lane, n, pst[best_it * 32 + lane], m, km1);
+        const double LB = fmax(warp_max(ymax), warp_max(lbmax));
+        // ... and only groups whose upper bound reaches it can hold a larger sample
+#pragma unroll 1
+        for (int it = 0; it < n_it; ++it) {
+            const int i0 = it * 512 + 16 * lane;
+            if (i0 >= n) break;
+            if ((double)ext[it * 32 + lane].x >= LB && it != best_it) {
+                const double gm = sww_group_max(x, i0, n, pst[it * 32 + lane], m, km1);
+                ymax = gm > ymax ? gm : ymax;
             }
         }
         ymax = warp_max(ymax);
@@ -149,31 +288,19 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
 
         // ---- pass 1b: threshold mask of y >= thr, first run of >= tx_min_n samples ----
 #pragma unroll 1
-        for (int it = 0; it < NWORDS / 8; ++it) {
+        for (int it = 0; it < NWORDS / 16; ++it) {
             uint32_t b = 0;
-            const int i0 = it * 256 + 8 * lane;
+            const int i0 = it * 512 + 16 * lane;
             if (i0 < n) {
                 const float2 ex = ext[it * 32 + lane];
                 if ((double)ex.x >= thr) {
-                    if ((double)ex.y >= thr) {
-                        b = 0xffu;
-                    } else {
-                        const uint4 r = sww_ld8(x + i0);
-                        const uint32_t v[8] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16, r.z & 0xffffu, r.z >> 16, r.w & 0xffffu, r.w >> 16};
-                        uint32_t Pr = pst[it * 32 + lane];
-                        const double ib = (double)(i0 + 1);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            Pr += v[k];
-                            b |= (sww_y(v[k], Pr, ib + (double)k, m, km1) >= thr) ? (1u << k) : 0u;
-                        }
-                    }
+                    if ((double)ex.y >= thr) b = (i0 + 8 < n) ? 0xffffu : 0xffu;
+                    else b = sww_group_bits(x, i0, n, pst[it * 32 + lane], m, km1, thr);
                 }
             }
-            b <<= 8 * (lane & 3);
+            b <<= 16 * (lane & 1);
             b |= __shfl_xor_sync(FULL, b, 1);
-            b |= __shfl_xor_sync(FULL, b, 2);
-            if ((lane & 3) == 0) mask[it * 8 + (lane >> 2)] = b;
+            if ((lane & 1) == 0) mask[it * 16 + (lane >> 1)] = b;
         }
         __syncwarp();
         int pos, mult;
@@ -192,28 +319,10 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
 #pragma unroll 1
         while (true) {
             __syncwarp();
-            // prefix sums at the window start from the boundary carries + the partial 256-sample step before lo
+            // prefix sums at the window start
             uint32_t cp;
             double cpp;
-            {
-                const int bq = lo >> 8, rem = lo & 255;
-                cp = cP[bq];
-                cpp = cPP[bq];
-                if (rem) {
-                    const int j0 = 8 * lane;
-                    const uint4 r = (bq * 256 + j0 < n) ? sww_ld8(x + bq * 256 + j0) : zero4;
-                    const uint32_t v[8] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16, r.z & 0xffffu, r.z >> 16, r.w & 0xffffu, r.w >> 16};
-                    uint32_t dP = 0, dPP = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int j = j0 + k;
-                        dP += (j < rem) ? v[k] : 0u;
-                        dPP += (j < rem) ? v[k] * (uint32_t)(rem - j) : 0u;
-                    }
-                    cpp += (double)rem * (double)cp + warp_sum((double)dPP);
-                    cp += __reduce_add_sync(FULL, dP);
-                }
-            }
+            sww_prefix_at(x, n, cP, cPP, lo, lane, cp, cpp);
             if (lane == 0) {
                 const double lod = (double)lo;
                 const double tri = 0.5 * lod * (lod + 1.0);
@@ -309,20 +418,9 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
                     continue;
                 }
                 done |= 1u << rnd;
-                const double* p0 = TTw + from;
-                const double* p1 = p0 + t.a;
-                const double* p2 = p1 + t.g;
-                const double* p3 = p0 + t.L;
-                double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-#pragma unroll 4
-                for (int i = 0; i < n_w; ++i) {
-                    const double val = __fma_rn(p3[i] - p2[i], t.inv2, -__dmul_rn(p1[i] - p0[i], t.inv1));
-                    const double* a = D.A + i * mdeg;
-                    c0 = fma(a[0], val, c0);
-                    if (mdeg > 1) c1 = fma(a[1], val, c1);
-                    if (mdeg > 2) c2 = fma(a[2], val, c2);
-                    if (mdeg > 3) c3 = fma(a[3], val, c3);
-                }
+                double c0, c1, c2, c3;
+                if (n_w == 44 && mdeg == 4) sww_dni_sums<44, 4>(D, TTw + from, t, n_w, mdeg, c0, c1, c2, c3);
+                else sww_dni_sums<0, 0>(D, TTw + from, t, n_w, mdeg, c0, c1, c2, c3);
                 const double u = pc - (double)from;
                 const double res = (nout >= n_w) ? fma(fma(fma(c3, u, c2), u, c1), u, c0) : CUDART_NAN;
                 if (P.out_f64) reinterpret_cast<double*>(out)[e * (long long)P.nvar + v] = res;
