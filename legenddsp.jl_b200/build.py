@@ -26,7 +26,8 @@ def build_library(force=False, verbose=False, profile=False):
     if not force and not needs_build():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DLGDSP_PROFILE_SECTIONS"] if profile else [])
+    extra = os.environ.get("LGDSP_NVCC_EXTRA", "").split()   # experiment knobs (-D...), never set for a release build
+    cmd = ([nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + (["-DLGDSP_PROFILE_SECTIONS"] if profile else [])
            + ["-o", OUT] + list(SOURCES))
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:

@@ -1535,6 +1535,11 @@ static int sweep_prepare(lgdsp_handle* h, const lgdsp_sweep_params* p, const lgd
     // Reach of the variant set around the crossing sample `pos` of t50 (t50 lies in [pos-1, pos]):
     // from = rint(pc) - n_w/2, pc = (t50 - t_first)/dt + pick/dt - (L-1)  (dni_window), look-ups in [from, from + L + n_w)
     D.warp_ok = 0;
+    {
+        int ex = 0;
+        D.dt_pow2 = (p->dt_ns > 0 && std::frexp(p->dt_ns, &ex) == 0.5) ? 1 : 0;
+        D.rdt = 1.0 / p->dt_ns;
+    }
     if (D.n_other == 0) {
         bool all1 = true, all0 = true;
         double lo = 1e300, hi = -1e300;

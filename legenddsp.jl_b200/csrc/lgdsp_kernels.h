@@ -50,7 +50,9 @@ struct SweepDev {
     // one-warp-per-waveform path (lgdsp_sweep_warp.cuh): warp_ok = 1 when every variant is a trapezoid of one pick-off mode
     // and the prefix-sum window the set can reach fits win_steps * 288 samples.  win_mode 1: the first window starts at
     // (crossing sample + win_rel_lo); 0: at win_abs_lo
-    int warp_ok, win_steps, win_mode, win_rel_lo, win_abs_lo, reserved2;
+    int warp_ok, win_steps, win_mode, win_rel_lo, win_abs_lo;
+    int dt_pow2;             // dt is a power of two: x / dt == x * rdt bit for bit
+    double rdt;
 };
 cudaError_t sweep_configure(int* max_blocks_per_sm);
 // dni_A_host: the fit matrix on the host (the warp path passes it in the constant bank); sm_count sizes the warp path's grid.

@@ -29,6 +29,9 @@
 // arithmetic on the same exact integers), which stays the path of FIR / Savitzky-Golay variants, 32-bit samples and
 // variant sets whose reach exceeds the window capacity.
 
+#ifndef SWW_UNR
+#define SWW_UNR 11   // outputs per iteration of the pick-off window loop (measured: 2 / 4 / 11 / 44 -> 37.3 / 38.9 / 39.9 / 33.6 M wf/s)
+#endif
 constexpr int SWW_STEP = 288;        // samples per window-build step (9 per lane)
 constexpr int SWW_MIN_STEPS = 4;     // the window area also holds pass 1's group table (8 KB)
 constexpr int SWW_MAX_STEPS = 10;
@@ -42,6 +45,14 @@ struct SweepDni {
 };
 
 __device__ __forceinline__ uint4 sww_ld8(const uint16_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// the same for the single pass over the whole waveform: no L1 allocation (the small L1 left beside 220 KB of shared memory keeps
+// the variant table and the window's samples instead)
+__device__ __forceinline__ uint4 sww_ld8_stream(const uint16_t* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
 
 // closed-form pole-zero sample (the arithmetic of sweep_kernel's P2 body)
 __device__ __forceinline__ double sww_y(uint32_t x, uint32_t Pincl, double ip1, double m, double km1)
@@ -53,10 +64,12 @@ __device__ __forceinline__ double sww_y(uint32_t x, uint32_t Pincl, double ip1, 
 
 // the 16 consecutive samples of lane-group i0 (multiple of 16; the trace length is a multiple of 8: the second half may lie
 // beyond the trace and reads as zeros)
+template <bool STREAM = false>
 __device__ __forceinline__ void sww_ld16(const uint16_t* __restrict__ x, int i0, int n, uint32_t (&v)[16])
 {
-    const uint4 r0 = (i0 < n) ? sww_ld8(x + i0) : make_uint4(0u, 0u, 0u, 0u);
-    const uint4 r1 = (i0 + 8 < n) ? sww_ld8(x + i0 + 8) : make_uint4(0u, 0u, 0u, 0u);
+    uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+    if (i0 < n) r0 = STREAM ? sww_ld8_stream(x + i0) : sww_ld8(x + i0);
+    if (i0 + 8 < n) r1 = STREAM ? sww_ld8_stream(x + i0 + 8) : sww_ld8(x + i0 + 8);
     v[0] = r0.x & 0xffffu; v[1] = r0.x >> 16; v[2] = r0.y & 0xffffu; v[3] = r0.y >> 16;
     v[4] = r0.z & 0xffffu; v[5] = r0.z >> 16; v[6] = r0.w & 0xffffu; v[7] = r0.w >> 16;
     v[8] = r1.x & 0xffffu; v[9] = r1.x >> 16; v[10] = r1.y & 0xffffu; v[11] = r1.y >> 16;
@@ -65,7 +78,7 @@ __device__ __forceinline__ void sww_ld16(const uint16_t* __restrict__ x, int i0,
 
 // P_excl(i) = sum_{j<i} x_j and PP_excl(i) = sum_{j<i} P_incl(j) for 0 <= i <= n from the 512-sample boundary carries plus the
 // partial step before i (warp-cooperative, i warp-uniform; every lane gets the result)
-__device__ __forceinline__ void sww_prefix_at(const uint16_t* __restrict__ x, int n, const uint32_t* cP, const double* cPP, int i,
+__device__ __noinline__ void sww_prefix_at(const uint16_t* __restrict__ x, int n, const uint32_t* cP, const double* cPP, int i,
                                               int lane, uint32_t& Pq, double& PPq)
 {
     const int bq = i >> 9, rem = i & 511;
@@ -88,7 +101,7 @@ __device__ __forceinline__ void sww_prefix_at(const uint16_t* __restrict__ x, in
 }
 
 // exact maximum of y over the 16-sample group that starts at sample i0 (P_excl(i0) = Pst); samples beyond the trace excluded
-__device__ __forceinline__ double sww_group_max(const uint16_t* __restrict__ x, int i0, int n, uint32_t Pst, double m, double km1)
+__device__ __noinline__ double sww_group_max(const uint16_t* __restrict__ x, int i0, int n, uint32_t Pst, double m, double km1)
 {
     uint32_t v[16];
     sww_ld16(x, i0, n, v);
@@ -105,7 +118,7 @@ __device__ __forceinline__ double sww_group_max(const uint16_t* __restrict__ x, 
     return gmax;
 }
 // bit k: y(i0 + k) >= thr
-__device__ __forceinline__ uint32_t sww_group_bits(const uint16_t* __restrict__ x, int i0, int n, uint32_t Pst, double m, double km1,
+__device__ __noinline__ uint32_t sww_group_bits(const uint16_t* __restrict__ x, int i0, int n, uint32_t Pst, double m, double km1,
                                                    double thr)
 {
     uint32_t v[16];
@@ -132,13 +145,21 @@ __device__ __forceinline__ void sww_dni_sums(const SweepDni& D, const double* p0
     const double* p3 = p0 + t.L;
     c0 = 0; c1 = 0; c2 = 0; c3 = 0;
     if (NW > 0) {
+        // blocks of 4 outputs: the loop body (about 60 instructions) stays inside the instruction cache of a scheduler; a
+        // complete unroll (44 x 12 instructions) ran fetch-bound
+        constexpr int UNR = SWW_UNR;
+        static_assert(NW % UNR == 0, "window length must be a multiple of the unroll factor");
+#pragma unroll 1
+        for (int ib = 0; ib < NW; ib += UNR) {
 #pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            const double val = __fma_rn(p3[i] - p2[i], t.inv2, -__dmul_rn(p1[i] - p0[i], t.inv1));
-            c0 = fma(D.A[i * MD], val, c0);
-            if (MD > 1) c1 = fma(D.A[i * MD + 1], val, c1);
-            if (MD > 2) c2 = fma(D.A[i * MD + 2], val, c2);
-            if (MD > 3) c3 = fma(D.A[i * MD + 3], val, c3);
+            for (int u = 0; u < UNR; ++u) {
+                const int i = ib + u;
+                const double val = __fma_rn(p3[i] - p2[i], t.inv2, -__dmul_rn(p1[i] - p0[i], t.inv1));
+                c0 = fma(D.A[i * MD], val, c0);
+                if (MD > 1) c1 = fma(D.A[i * MD + 1], val, c1);
+                if (MD > 2) c2 = fma(D.A[i * MD + 2], val, c2);
+                if (MD > 3) c3 = fma(D.A[i * MD + 3], val, c3);
+            }
         }
     } else {
 #pragma unroll 4
@@ -184,12 +205,12 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
         uint32_t carryP = 0;
         unsigned long long carryPP = 0;
         uint32_t v[16], vn[16];
-        sww_ld16(x, 16 * lane, n, v);
-        sww_ld16(x, 512 + 16 * lane, n, vn);
+        sww_ld16<true>(x, 16 * lane, n, v);
+        sww_ld16<true>(x, 512 + 16 * lane, n, vn);
 #pragma unroll 1
         for (int it = 0; it < n_it; ++it) {
             uint32_t vf[16];
-            sww_ld16(x, (it + 2) * 512 + 16 * lane, n, vf);    // two steps ahead
+            sww_ld16<true>(x, (it + 2) * 512 + 16 * lane, n, vf);    // two steps ahead
             if (lane == 0) { cP[it] = carryP; cPP[it] = (double)carryPP; }
             uint32_t s[16];
             s[0] = v[0];
@@ -400,31 +421,54 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
                 }
             }
             int minfrom = 0x7fffffff;
-            int rnd = 0;
+            // Warp-uniform loop over rounds of 32 variants: every lane runs the arithmetic (a lane without work reads the start of
+            // the window), so the inner loop sits in convergent code and the fit matrix is read through the uniform datapath
+            const int n_rounds = (P.nvar + 31) >> 5;
+            int rnd;
+            // this lane's variant of the next round is loaded one round ahead (the table comes from L2 / L1)
+            TrapDev tn = P.vars[min(lane, P.nvar - 1)].t;
+            double pickn = P.vars[min(lane, P.nvar - 1)].pick_ns;
+            int moden = P.vars[min(lane, P.nvar - 1)].mode;
 #pragma unroll 1
-            for (int v = lane; v < P.nvar; v += 32, ++rnd) {
-                if ((done >> rnd) & 1u) continue;
-                const SweepVar& sv = P.vars[v];
-                const TrapDev t = sv.t;
-                const double pick = sv.pick_ns;
-                const int nout = n - t.L + 1;
-                const double tf = __fma_rn((double)(t.L - 1), dt, t_first);
-                const double t_ns = sv.mode ? __fma_rn(t50_us, 1000.0, pick) : pick;
-                double pc;
-                int from;
-                dni_window(n_w, nout, (t_ns - tf) / dt, pc, from);
-                if (from < lo || from + t.L + n_w - 1 > lo + W) {   // look-ups TT[from .. from + L + n_w - 1]
-                    minfrom = min(minfrom, from);
-                    continue;
+            for (rnd = 0; rnd < n_rounds; ++rnd) {
+                const int v = rnd * 32 + lane;
+                const TrapDev tv = tn;
+                const double pick = pickn;
+                const int mode = moden;
+                {
+                    const SweepVar& nx = P.vars[min(v + 32, P.nvar - 1)];
+                    tn = nx.t; pickn = nx.pick_ns; moden = nx.mode;
                 }
-                done |= 1u << rnd;
+                bool eval = false;
+                TrapDev t;
+                t.a = 0; t.g = 0; t.L = 0; t.inv1 = 0.0; t.inv2 = 0.0;
+                double pc = 0.0;
+                int from = lo, nout = 0;
+                if (v < P.nvar && !((done >> rnd) & 1u)) {
+                    nout = n - tv.L + 1;
+                    const double tf = __fma_rn((double)(tv.L - 1), dt, t_first);
+                    const double t_ns = mode ? __fma_rn(t50_us, 1000.0, pick) : pick;
+                    int fr;
+                    dni_window(n_w, nout, P.dt_pow2 ? (t_ns - tf) * P.rdt : (t_ns - tf) / dt, pc, fr);
+                    if (fr < lo || fr + tv.L + n_w - 1 > lo + W) {   // look-ups TT[from .. from + L + n_w - 1]
+                        minfrom = min(minfrom, fr);
+                    } else {
+                        eval = true;
+                        done |= 1u << rnd;
+                        from = fr;
+                        t = tv;
+                    }
+                }
+                if (__ballot_sync(FULL, eval) == 0u) continue;
                 double c0, c1, c2, c3;
                 if (n_w == 44 && mdeg == 4) sww_dni_sums<44, 4>(D, TTw + from, t, n_w, mdeg, c0, c1, c2, c3);
                 else sww_dni_sums<0, 0>(D, TTw + from, t, n_w, mdeg, c0, c1, c2, c3);
-                const double u = pc - (double)from;
-                const double res = (nout >= n_w) ? fma(fma(fma(c3, u, c2), u, c1), u, c0) : CUDART_NAN;
-                if (P.out_f64) reinterpret_cast<double*>(out)[e * (long long)P.nvar + v] = res;
-                else reinterpret_cast<float*>(out)[e * (long long)P.nvar + v] = (float)res;
+                if (eval) {
+                    const double u = pc - (double)from;
+                    const double res = (nout >= n_w) ? fma(fma(fma(c3, u, c2), u, c1), u, c0) : CUDART_NAN;
+                    if (P.out_f64) reinterpret_cast<double*>(out)[e * (long long)P.nvar + v] = res;
+                    else reinterpret_cast<float*>(out)[e * (long long)P.nvar + v] = (float)res;
+                }
             }
             minfrom = __reduce_min_sync(FULL, minfrom);
             if (minfrom == 0x7fffffff) break;
