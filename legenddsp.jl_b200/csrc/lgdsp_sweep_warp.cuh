@@ -32,6 +32,13 @@
 #ifndef SWW_UNR
 #define SWW_UNR 11   // outputs per iteration of the pick-off window loop (measured: 2 / 4 / 11 / 44 -> 37.3 / 38.9 / 39.9 / 33.6 M wf/s)
 #endif
+#ifndef SWW_U1A
+#define SWW_U1A 1
+#endif
+#ifndef SWW_U1B
+#define SWW_U1B 1
+#endif
+constexpr int kU1A = SWW_U1A, kU1B = SWW_U1B;   // unroll factors of the group loops (pragma arguments are not macro-expanded)
 constexpr int SWW_STEP = 288;        // samples per window-build step (9 per lane)
 constexpr int SWW_MIN_STEPS = 4;     // the window area also holds pass 1's group table (8 KB)
 constexpr int SWW_MAX_STEPS = 10;
@@ -64,6 +71,21 @@ __device__ __forceinline__ double sww_y(uint32_t x, uint32_t Pincl, double ip1, 
 
 // the 16 consecutive samples of lane-group i0 (multiple of 16; the trace length is a multiple of 8: the second half may lie
 // beyond the trace and reads as zeros)
+__device__ __forceinline__ void sww_unpack16(const uint4& r0, const uint4& r1, uint32_t (&v)[16])
+{
+    v[0] = r0.x & 0xffffu; v[1] = r0.x >> 16; v[2] = r0.y & 0xffffu; v[3] = r0.y >> 16;
+    v[4] = r0.z & 0xffffu; v[5] = r0.z >> 16; v[6] = r0.w & 0xffffu; v[7] = r0.w >> 16;
+    v[8] = r1.x & 0xffffu; v[9] = r1.x >> 16; v[10] = r1.y & 0xffffu; v[11] = r1.y >> 16;
+    v[12] = r1.z & 0xffffu; v[13] = r1.z >> 16; v[14] = r1.w & 0xffffu; v[15] = r1.w >> 16;
+}
+// streaming load of a lane group, left packed (the stream pass keeps three steps in flight)
+__device__ __forceinline__ void sww_ld16_raw(const uint16_t* __restrict__ x, int i0, int n, uint4& r0, uint4& r1)
+{
+    r0 = make_uint4(0u, 0u, 0u, 0u);
+    r1 = r0;
+    if (i0 < n) r0 = sww_ld8_stream(x + i0);
+    if (i0 + 8 < n) r1 = sww_ld8_stream(x + i0 + 8);
+}
 template <bool STREAM = false>
 __device__ __forceinline__ void sww_ld16(const uint16_t* __restrict__ x, int i0, int n, uint32_t (&v)[16])
 {
@@ -204,13 +226,15 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
         // ---- pass 1 (integers only): prefix sums, group table (P at the group start, max / min sample), boundary carries ----
         uint32_t carryP = 0;
         unsigned long long carryPP = 0;
-        uint32_t v[16], vn[16];
-        sww_ld16<true>(x, 16 * lane, n, v);
-        sww_ld16<true>(x, 512 + 16 * lane, n, vn);
+        uint4 ra[3], rb[3];   // raw samples of the next three steps
+#pragma unroll
+        for (int q = 0; q < 3; ++q) sww_ld16_raw(x, q * 512 + 16 * lane, n, ra[q], rb[q]);
 #pragma unroll 1
         for (int it = 0; it < n_it; ++it) {
-            uint32_t vf[16];
-            sww_ld16<true>(x, (it + 2) * 512 + 16 * lane, n, vf);    // two steps ahead
+            uint32_t v[16];
+            sww_unpack16(ra[0], rb[0], v);
+            ra[0] = ra[1]; rb[0] = rb[1]; ra[1] = ra[2]; rb[1] = rb[2];
+            sww_ld16_raw(x, (it + 3) * 512 + 16 * lane, n, ra[2], rb[2]);    // three steps ahead
             if (lane == 0) { cP[it] = carryP; cPP[it] = (double)carryPP; }
             uint32_t s[16];
             s[0] = v[0];
@@ -242,8 +266,6 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
                 pst[it * 32 + lane] = Pst;
                 xmm[it * 32 + lane] = (xmax << 16) | xmin;
             }
-#pragma unroll
-            for (int k = 0; k < 16; ++k) { v[k] = vn[k]; vn[k] = vf[k]; }
         }
         if (lane == 0) { cP[n_it] = carryP; cPP[n_it] = (double)carryPP; }
         __syncwarp();
@@ -273,10 +295,10 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
         double lbmax = -CUDART_INF;
         float best_ub = -CUDART_INF_F;
         int best_it = 0;
-#pragma unroll 1
-        for (int it = 0; it < n_it; ++it) {
+        const int my_groups = (n - 16 * lane + 511) >> 9;   // groups of this lane (<= 0: none)
+#pragma unroll (kU1A)
+        for (int it = 0; it < my_groups; ++it) {
             const int i0 = it * 512 + 16 * lane;
-            if (i0 >= n) break;
             const uint32_t xm = xmm[it * 32 + lane];
             const double dmax = u2d(xm >> 16) - m, dmin = u2d(xm & 0xffffu) - m;
             const double Sd0 = fma(-(double)i0, m, u2d(pst[it * 32 + lane]));
@@ -296,9 +318,8 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
         const double LB = fmax(warp_max(ymax), warp_max(lbmax));
         // ... and only groups whose upper bound reaches it can hold a larger sample
 #pragma unroll 1
-        for (int it = 0; it < n_it; ++it) {
+        for (int it = 0; it < my_groups; ++it) {
             const int i0 = it * 512 + 16 * lane;
-            if (i0 >= n) break;
             if ((double)ext[it * 32 + lane].x >= LB && it != best_it) {
                 const double gm = sww_group_max(x, i0, n, pst[it * 32 + lane], m, km1);
                 ymax = gm > ymax ? gm : ymax;
@@ -308,7 +329,7 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
         const double thr = ymax * 0.5;
 
         // ---- pass 1b: threshold mask of y >= thr, first run of >= tx_min_n samples ----
-#pragma unroll 1
+#pragma unroll (kU1B)
         for (int it = 0; it < NWORDS / 16; ++it) {
             uint32_t b = 0;
             const int i0 = it * 512 + 16 * lane;
@@ -336,6 +357,10 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
         unsigned done = 0;
         double t50_us = 0.0;
         bool first = true;
+        // (the first round's variant parameters travel while the window is built)
+        const TrapDev t_first_round = P.vars[min(lane, P.nvar - 1)].t;
+        const double pick_first_round = P.vars[min(lane, P.nvar - 1)].pick_ns;
+        const int mode_first_round = P.vars[min(lane, P.nvar - 1)].mode;
         int rounds = 0;
 #pragma unroll 1
         while (true) {
@@ -426,9 +451,9 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
             const int n_rounds = (P.nvar + 31) >> 5;
             int rnd;
             // this lane's variant of the next round is loaded one round ahead (the table comes from L2 / L1)
-            TrapDev tn = P.vars[min(lane, P.nvar - 1)].t;
-            double pickn = P.vars[min(lane, P.nvar - 1)].pick_ns;
-            int moden = P.vars[min(lane, P.nvar - 1)].mode;
+            TrapDev tn = t_first_round;
+            double pickn = pick_first_round;
+            int moden = mode_first_round;
 #pragma unroll 1
             for (rnd = 0; rnd < n_rounds; ++rnd) {
                 const int v = rnd * 32 + lane;
