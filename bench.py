@@ -560,7 +560,7 @@ def main():
         b3 = BYTES_IN + 200 * 4
         extra.append({"workload": WL_NAME["trap_sweep"], "value": world * B * xs / (ms3 * 1e-3), "unit": "waveforms/s", "ms_per_step": ms3 / xs,
                       "roofline": {"frac": B * b3 / (ms3 * 1e-3 / xs) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_waveform": b3},
-                      "kernel": "sweep_kernel"})
+                      "kernel": "sweep_warp_kernel (one warp per waveform; LGDSP_SWEEP_PATH=cta: sweep_kernel)"})
 
     kernel_ms = None
     if args.workload == "dsp_icpc" and args.path == "split" and not args.no_extra and rank == 0:
@@ -578,7 +578,7 @@ def main():
 
     if rank == 0:
         achieved = B * bytes_per_wf / (ms_max * 1e-3 / args.steps) / 1e9
-        kern = {"trap_sweep": "sweep_kernel", "sipm": "sipm_kernel"}.get(
+        kern = {"trap_sweep": "sweep_warp_kernel", "sipm": "sipm_kernel"}.get(
             args.workload, ("icpc_kernel (fused)" if args.path == "fused" else
                             "split pipeline: icpc_prefix_kernel -> icpc_extract_kernel || icpc_cuspzac_kernel -> icpc_cuspzac_finish_kernel")
             + (" x2 (presummed + windowed) + window_stats_kernel" if args.workload == "compressed" else ""))

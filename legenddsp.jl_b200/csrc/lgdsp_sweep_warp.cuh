@@ -45,7 +45,11 @@ constexpr int SWW_MAX_STEPS = 10;
 constexpr int SWW_MAX_WARPS = 12;    // warps per CTA (launch bound)
 constexpr int SWW_EXT_BYTES = 4096;  // float2 per 16-sample group
 __host__ __device__ constexpr int sww_win_bytes(int steps) { return (steps * SWW_STEP + 8) * 8; }
-__host__ __device__ constexpr int sww_warp_bytes(int steps) { return sww_win_bytes(steps) + NWORDS * 4 + 36 * 4 + 34 * 8; }
+// per waveform: window | mask | cP[20] | cPP[18] | locPP[16] | xch[8] | stepP[16] | xchi[4]   (11 CTAs per SM at 8 window steps)
+__host__ __device__ constexpr int sww_warp_bytes(int steps)
+{
+    return sww_win_bytes(steps) + NWORDS * 4 + 20 * 4 + 18 * 8 + 16 * 8 + 8 * 8 + 16 * 4 + 4 * 4;
+}
 
 struct SweepDni {
     double A[LGDSP_MAX_DNI * (LGDSP_MAX_DNI_DEG + 1)];
@@ -196,79 +200,125 @@ __device__ __forceinline__ void sww_dni_sums(const SweepDni& D, const double* p0
     }
 }
 
-__global__ void __launch_bounds__(SWW_MAX_WARPS * 32, 1)
+// WPE warps (a CTA) own one waveform: WPE = 1 needs no block barrier at all; WPE = 2 halves every phase and doubles the warps an
+// SM holds (the float64 window, not the thread count, limits residency) for ~8 CTA-wide barriers of 64 threads per waveform.
+template <int WPE>
+__device__ __forceinline__ void sww_team_sync()
+{
+    if (WPE == 1) __syncwarp();
+    else __syncthreads();
+}
+// maximum over the team of a warp-uniform value (slot: a distinct exchange slot per use inside one waveform)
+template <int WPE>
+__device__ __forceinline__ double sww_team_max(double v, double* xch, int slot, int we, int lane)
+{
+    if (WPE == 1) return v;
+    if (lane == 0) xch[slot * WPE + we] = v;
+    __syncthreads();
+    double r = xch[slot * WPE];
+#pragma unroll
+    for (int w = 1; w < WPE; ++w) r = xch[slot * WPE + w] > r ? xch[slot * WPE + w] : r;
+    return r;
+}
+
+template <int WPE>
+__global__ void __launch_bounds__(32 * WPE, 11)
 sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ SweepDni D, const uint16_t* __restrict__ wf,
                   long long n_events, long long ld, const double* __restrict__ bl_ext, void* __restrict__ out,
                   double* __restrict__ aux)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, we = threadIdx.x >> 5;
     const int steps = P.win_steps;
     const int W = steps * SWW_STEP;
-    unsigned char* base = smem + (size_t)wib * sww_warp_bytes(steps);
+    unsigned char* base = smem;
     double* win = reinterpret_cast<double*>(base);
     float2* ext = reinterpret_cast<float2*>(base);
+    // P at the group start: absolute (WPE == 1) / relative to its 512-sample step, whose carry is known after the team's barrier
     uint32_t* pst = reinterpret_cast<uint32_t*>(base + SWW_EXT_BYTES);
     uint32_t* xmm = pst + MAXN / 16;
     uint32_t* mask = reinterpret_cast<uint32_t*>(base + sww_win_bytes(steps));
     uint32_t* cP = mask + NWORDS;
-    double* cPP = reinterpret_cast<double*>(cP + 36);
+    double* cPP = reinterpret_cast<double*>(cP + 20);
+    double* locPP = cPP + 18;                                           // [16] sum over a step of (P(i) - P(step start))
+    double* xch = locPP + 16;                                           // [2][WPE <= 4] team exchange slots
+    uint32_t* stepP = reinterpret_cast<uint32_t*>(xch + 8);            // [16] sum of the samples of a step
+    int* xchi = reinterpret_cast<int*>(stepP + 16);                     // [4]
 
     const int n = P.n, n_it = (n + 511) >> 9;
     const double t_first = P.t_first, dt = P.dt, km1 = P.km1;
     const int n_w = P.sig_dni.n_w, mdeg = P.sig_dni.m;
-    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    auto pbase = [&](int it) -> uint32_t { return WPE == 1 ? 0u : cP[it]; };
 
-    for (long long e = (long long)blockIdx.x * (blockDim.x >> 5) + wib; e < n_events; e += wstride) {
+    for (long long e = blockIdx.x; e < n_events; e += gridDim.x) {
         const uint16_t* __restrict__ x = wf + e * ld;
-        if (lane == 0 && e + wstride < n_events) tma_prefetch_l2(wf + (e + wstride) * ld, (uint32_t)n * 2u);
+        if (threadIdx.x == 0 && e + gridDim.x < n_events) tma_prefetch_l2(wf + (e + gridDim.x) * ld, (uint32_t)n * 2u);
 
-        // ---- pass 1 (integers only): prefix sums, group table (P at the group start, max / min sample), boundary carries ----
-        uint32_t carryP = 0;
-        unsigned long long carryPP = 0;
-        uint4 ra[3], rb[3];   // raw samples of the next three steps
+        // ---- pass 1 (integers only): the steps it = we, we + WPE, ...; prefix sums inside the step, group table, step sums ----
+        {
+            uint32_t carryP = 0;             // (WPE == 1: the steps follow each other, the carries run along)
+            unsigned long long carryPP = 0;
+            uint4 ra[3], rb[3];   // raw samples of this warp's next three steps
 #pragma unroll
-        for (int q = 0; q < 3; ++q) sww_ld16_raw(x, q * 512 + 16 * lane, n, ra[q], rb[q]);
+            for (int q = 0; q < 3; ++q) sww_ld16_raw(x, (we + q * WPE) * 512 + 16 * lane, n, ra[q], rb[q]);
 #pragma unroll 1
-        for (int it = 0; it < n_it; ++it) {
-            uint32_t v[16];
-            sww_unpack16(ra[0], rb[0], v);
-            ra[0] = ra[1]; rb[0] = rb[1]; ra[1] = ra[2]; rb[1] = rb[2];
-            sww_ld16_raw(x, (it + 3) * 512 + 16 * lane, n, ra[2], rb[2]);    // three steps ahead
-            if (lane == 0) { cP[it] = carryP; cPP[it] = (double)carryPP; }
-            uint32_t s[16];
-            s[0] = v[0];
+            for (int it = we; it < n_it; it += WPE) {
+                uint32_t v[16];
+                sww_unpack16(ra[0], rb[0], v);
+                ra[0] = ra[1]; rb[0] = rb[1]; ra[1] = ra[2]; rb[1] = rb[2];
+                sww_ld16_raw(x, (it + 3 * WPE) * 512 + 16 * lane, n, ra[2], rb[2]);    // three steps ahead
+                uint32_t s[16];
+                s[0] = v[0];
 #pragma unroll
-            for (int k = 1; k < 16; ++k) s[k] = s[k - 1] + v[k];
-            const int i0 = it * 512 + 16 * lane;
-            uint32_t xmax = __vimax3_u32(__vimax3_u32(v[0], v[1], v[2]), __vimax3_u32(v[3], v[4], v[5]), __vimax3_u32(v[6], v[7], v[7]));
-            uint32_t xmin = __vimin3_u32(__vimin3_u32(v[0], v[1], v[2]), __vimin3_u32(v[3], v[4], v[5]), __vimin3_u32(v[6], v[7], v[7]));
-            if (i0 + 8 < n) {
-                xmax = __vimax3_u32(__vimax3_u32(v[8], v[9], v[10]), __vimax3_u32(v[11], v[12], v[13]), __vimax3_u32(v[14], v[15], xmax));
-                xmin = __vimin3_u32(__vimin3_u32(v[8], v[9], v[10]), __vimin3_u32(v[11], v[12], v[13]), __vimin3_u32(v[14], v[15], xmin));
-            }
-            uint32_t incl = s[15];
+                for (int k = 1; k < 16; ++k) s[k] = s[k - 1] + v[k];
+                const int i0 = it * 512 + 16 * lane;
+                uint32_t xmax = __vimax3_u32(__vimax3_u32(v[0], v[1], v[2]), __vimax3_u32(v[3], v[4], v[5]), __vimax3_u32(v[6], v[7], v[7]));
+                uint32_t xmin = __vimin3_u32(__vimin3_u32(v[0], v[1], v[2]), __vimin3_u32(v[3], v[4], v[5]), __vimin3_u32(v[6], v[7], v[7]));
+                if (i0 + 8 < n) {
+                    xmax = __vimax3_u32(__vimax3_u32(v[8], v[9], v[10]), __vimax3_u32(v[11], v[12], v[13]), __vimax3_u32(v[14], v[15], xmax));
+                    xmin = __vimin3_u32(__vimin3_u32(v[8], v[9], v[10]), __vimin3_u32(v[11], v[12], v[13]), __vimin3_u32(v[14], v[15], xmin));
+                }
+                uint32_t incl = s[15];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const uint32_t Pst = carryP + incl - s[15];
-            // sum over the 512 samples of the step of P(i): 512*carryP + 16*sum_l excl_l + sum_l sum_k s_l[k]
-            uint32_t tl = 0;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                // sum over the 512 samples of the step of (P(i) - P(step start)): 16*sum_l excl_l + sum_l sum_k s_l[k]
+                uint32_t tl = 0;
 #pragma unroll
-            for (int k = 0; k < 16; k += 4) tl += (s[k] + s[k + 1]) + (s[k + 2] + s[k + 3]);
-            const uint32_t sum_t = __reduce_add_sync(FULL, tl);
-            const uint32_t sum_ex = __reduce_add_sync(FULL, (uint32_t)(31 - lane) * s[15]);
-            carryPP += 512ull * carryP + 16ull * sum_ex + sum_t;
-            carryP += __shfl_sync(FULL, incl, 31);
-            if (i0 < n) {
-                pst[it * 32 + lane] = Pst;
-                xmm[it * 32 + lane] = (xmax << 16) | xmin;
+                for (int k = 0; k < 16; k += 4) tl += (s[k] + s[k + 1]) + (s[k + 2] + s[k + 3]);
+                const uint32_t sum_t = __reduce_add_sync(FULL, tl);
+                const uint32_t sum_ex = __reduce_add_sync(FULL, (uint32_t)(31 - lane) * s[15]);
+                if (WPE == 1) {
+                    if (lane == 0) { cP[it] = carryP; cPP[it] = (double)carryPP; }
+                    if (i0 < n) pst[it * 32 + lane] = carryP + incl - s[15];
+                    carryPP += 512ull * carryP + 16ull * sum_ex + sum_t;
+                    carryP += __shfl_sync(FULL, incl, 31);
+                } else {
+                    if (lane == 31) {
+                        stepP[it] = incl;
+                        locPP[it] = (double)(16ull * sum_ex + sum_t);
+                    }
+                    if (i0 < n) pst[it * 32 + lane] = incl - s[15];
+                }
+                if (i0 < n) xmm[it * 32 + lane] = (xmax << 16) | xmin;
             }
+            if (WPE == 1 && lane == 0) { cP[n_it] = carryP; cPP[n_it] = (double)carryPP; }
         }
-        if (lane == 0) { cP[n_it] = carryP; cPP[n_it] = (double)carryPP; }
-        __syncwarp();
+        sww_team_sync<WPE>();
+        // P and PP = cumsum(P) at every 512-sample boundary (exact integers; PP < 2^43 in float64)
+        if (WPE > 1 && we == 0 && lane <= n_it) {
+            uint32_t cp = 0;
+            double cpp = 0.0;
+            for (int i = 0; i < lane; ++i) {
+                cpp += fma(512.0, u2d(cp), locPP[i]);
+                cp += stepP[i];
+            }
+            cP[lane] = cp;
+            cPP[lane] = cpp;
+        }
+        sww_team_sync<WPE>();
 
         // ---- baseline window from the prefix sums: sum x = P(b+1) - P(a), sum i*x = b*P(b+1) - a*P(a) - (PP(b) - PP(a)) ----
         double blSd, blSXd = 0.0;
@@ -294,14 +344,14 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
         const double G = 1e-9 * (65536.0 + fabs(m) + fabs(km1) * (double)n * 65536.0);
         double lbmax = -CUDART_INF;
         float best_ub = -CUDART_INF_F;
-        int best_it = 0;
-        const int my_groups = (n - 16 * lane + 511) >> 9;   // groups of this lane (<= 0: none)
+        int best_it = -1;
+        const int my_groups = (n - 16 * lane + 511) >> 9;   // groups of this lane's column (<= 0: none)
 #pragma unroll (kU1A)
-        for (int it = 0; it < my_groups; ++it) {
+        for (int it = we; it < my_groups; it += WPE) {
             const int i0 = it * 512 + 16 * lane;
             const uint32_t xm = xmm[it * 32 + lane];
             const double dmax = u2d(xm >> 16) - m, dmin = u2d(xm & 0xffffu) - m;
-            const double Sd0 = fma(-(double)i0, m, u2d(pst[it * 32 + lane]));
+            const double Sd0 = fma(-(double)i0, m, u2d(pst[it * 32 + lane] + pbase(it)));
             const double Sd_hi = fma(16.0, dmax > 0.0 ? dmax : 0.0, Sd0), Sd_lo = fma(16.0, dmin < 0.0 ? dmin : 0.0, Sd0);
             const double k_hi = km1 >= 0.0 ? Sd_hi : Sd_lo, k_lo = km1 >= 0.0 ? Sd_lo : Sd_hi;
             const double ub = fma(km1, k_hi, dmax) + G;
@@ -314,37 +364,37 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
         }
         // every lane evaluates the group with its largest upper bound exactly: a lower bound close to the maximum ...
         double ymax = -CUDART_INF;
-        if (16 * lane < n) ymax = sww_group_max(x, best_it * 512 + 16 * lane, n, pst[best_it * 32 + lane], m, km1);
-        const double LB = fmax(warp_max(ymax), warp_max(lbmax));
+        if (best_it >= 0) ymax = sww_group_max(x, best_it * 512 + 16 * lane, n, pst[best_it * 32 + lane] + pbase(best_it), m, km1);
+        const double LB = sww_team_max<WPE>(fmax(warp_max(ymax), warp_max(lbmax)), xch, 0, we, lane);
         // ... and only groups whose upper bound reaches it can hold a larger sample
 #pragma unroll 1
-        for (int it = 0; it < my_groups; ++it) {
+        for (int it = we; it < my_groups; it += WPE) {
             const int i0 = it * 512 + 16 * lane;
             if ((double)ext[it * 32 + lane].x >= LB && it != best_it) {
-                const double gm = sww_group_max(x, i0, n, pst[it * 32 + lane], m, km1);
+                const double gm = sww_group_max(x, i0, n, pst[it * 32 + lane] + pbase(it), m, km1);
                 ymax = gm > ymax ? gm : ymax;
             }
         }
-        ymax = warp_max(ymax);
+        ymax = sww_team_max<WPE>(warp_max(ymax), xch, 1, we, lane);
         const double thr = ymax * 0.5;
 
         // ---- pass 1b: threshold mask of y >= thr, first run of >= tx_min_n samples ----
 #pragma unroll (kU1B)
-        for (int it = 0; it < NWORDS / 16; ++it) {
+        for (int it = we; it < NWORDS / 16; it += WPE) {
             uint32_t b = 0;
             const int i0 = it * 512 + 16 * lane;
             if (i0 < n) {
                 const float2 ex = ext[it * 32 + lane];
                 if ((double)ex.x >= thr) {
                     if ((double)ex.y >= thr) b = (i0 + 8 < n) ? 0xffffu : 0xffu;
-                    else b = sww_group_bits(x, i0, n, pst[it * 32 + lane], m, km1, thr);
+                    else b = sww_group_bits(x, i0, n, pst[it * 32 + lane] + pbase(it), m, km1, thr);
                 }
             }
             b <<= 16 * (lane & 1);
             b |= __shfl_xor_sync(FULL, b, 1);
             if ((lane & 1) == 0) mask[it * 16 + (lane >> 1)] = b;
         }
-        __syncwarp();
+        sww_team_sync<WPE>();
         int pos, mult;
         resolve_runs(mask, P.tx_min_n, lane, pos, mult);
 
@@ -357,81 +407,88 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
         unsigned done = 0;
         double t50_us = 0.0;
         bool first = true;
+        constexpr int VSTRIDE = 32 * WPE;                  // variants per round of the team
+        const int vlane = we * 32 + lane;
         // (the first round's variant parameters travel while the window is built)
-        const TrapDev t_first_round = P.vars[min(lane, P.nvar - 1)].t;
-        const double pick_first_round = P.vars[min(lane, P.nvar - 1)].pick_ns;
-        const int mode_first_round = P.vars[min(lane, P.nvar - 1)].mode;
+        const TrapDev t_first_round = P.vars[min(vlane, P.nvar - 1)].t;
+        const double pick_first_round = P.vars[min(vlane, P.nvar - 1)].pick_ns;
+        const int mode_first_round = P.vars[min(vlane, P.nvar - 1)].mode;
         int rounds = 0;
+        const int steps_w = (steps + WPE - 1) / WPE;       // window steps per warp: warp `we` builds [we*steps_w, (we+1)*steps_w)
 #pragma unroll 1
         while (true) {
-            __syncwarp();
-            // prefix sums at the window start
-            uint32_t cp;
-            double cpp;
-            sww_prefix_at(x, n, cP, cPP, lo, lane, cp, cpp);
-            if (lane == 0) {
-                const double lod = (double)lo;
-                const double tri = 0.5 * lod * (lod + 1.0);
-                win[0] = fma(km1, fma(-tri, m, cpp), fma(-lod, m, u2d(cp)));
-            }
-            uint32_t q[9];
-            {
-                const int i0 = lo + 9 * lane;
+            sww_team_sync<WPE>();   // every read of the group table / the previous window is over
+            const int j_from = we * steps_w, j_until = min(steps, j_from + steps_w);
+            if (j_from < j_until) {
+                // prefix sums at this warp's first sample
+                const int start = lo + SWW_STEP * j_from;
+                uint32_t cp;
+                double cpp;
+                sww_prefix_at(x, n, cP, cPP, min(start, n), lane, cp, cpp);
+                if (we == 0 && lane == 0) {
+                    const double lod = (double)lo;
+                    const double tri = 0.5 * lod * (lod + 1.0);
+                    win[0] = fma(km1, fma(-tri, m, cpp), fma(-lod, m, u2d(cp)));
+                }
+                uint32_t q[9];
+                {
+                    const int i0 = start + 9 * lane;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) q[k] = (i0 + k < n) ? (uint32_t)__ldg(x + i0 + k) : 0u;
-            }
+                    for (int k = 0; k < 9; ++k) q[k] = (i0 + k < n) ? (uint32_t)__ldg(x + i0 + k) : 0u;
+                }
 #pragma unroll 1
-            for (int j = 0; j < steps; ++j) {
-                uint32_t v[9];
+                for (int j = j_from; j < j_until; ++j) {
+                    uint32_t v[9];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) v[k] = q[k];
-                const int i0 = lo + SWW_STEP * j + 9 * lane;
-                if (j + 1 < steps) {
+                    for (int k = 0; k < 9; ++k) v[k] = q[k];
+                    const int i0 = lo + SWW_STEP * j + 9 * lane;
+                    if (j + 1 < j_until) {
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) q[k] = (i0 + SWW_STEP + k < n) ? (uint32_t)__ldg(x + i0 + SWW_STEP + k) : 0u;
+                        for (int k = 0; k < 9; ++k) q[k] = (i0 + SWW_STEP + k < n) ? (uint32_t)__ldg(x + i0 + SWW_STEP + k) : 0u;
+                    }
+                    uint32_t s[9];
+                    s[0] = v[0];
+#pragma unroll
+                    for (int k = 1; k < 9; ++k) s[k] = s[k - 1] + v[k];
+                    uint32_t incl = s[8];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const uint32_t Pst = cp + incl - s[8];
+                    uint32_t tl = s[0];
+#pragma unroll
+                    for (int k = 1; k < 9; ++k) tl += s[k];
+                    const double qd = fma(9.0, u2d(incl - s[8]), u2d(tl));   // lane sum of (P(i) - cp): exact (< 2^37)
+                    double inclq = qd;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double t = __shfl_up_sync(FULL, inclq, o);
+                        if (lane >= o) inclq += t;
+                    }
+                    // PP before this lane's first sample: cpp + 9*lane*cp + (scan of the lane sums)
+                    double PPr = cpp + (double)(9 * lane) * u2d(cp) + (inclq - qd);
+                    uint32_t Pr = Pst;
+                    double ip1 = (double)i0;
+                    double tri = 0.5 * ip1 * (ip1 + 1.0);
+                    double* tp = win + SWW_STEP * j + 9 * lane + 1;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        Pr += v[k];
+                        const double Pd = u2d(Pr);
+                        PPr += Pd;
+                        ip1 += 1.0;
+                        tri += ip1;
+                        const double Sd = fma(-ip1, m, Pd);
+                        const double SS = fma(-tri, m, PPr);
+                        tp[k] = (i0 + k < n) ? fma(km1, SS, Sd) : 0.0;
+                    }
+                    cpp += (double)SWW_STEP * u2d(cp) + __shfl_sync(FULL, inclq, 31);
+                    cp += __shfl_sync(FULL, incl, 31);
                 }
-                uint32_t s[9];
-                s[0] = v[0];
-#pragma unroll
-                for (int k = 1; k < 9; ++k) s[k] = s[k - 1] + v[k];
-                uint32_t incl = s[8];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const uint32_t Pst = cp + incl - s[8];
-                uint32_t tl = s[0];
-#pragma unroll
-                for (int k = 1; k < 9; ++k) tl += s[k];
-                const double qd = fma(9.0, u2d(incl - s[8]), u2d(tl));   // lane sum of (P(i) - cp): exact (< 2^37)
-                double inclq = qd;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double t = __shfl_up_sync(FULL, inclq, o);
-                    if (lane >= o) inclq += t;
-                }
-                // PP before this lane's first sample: cpp + 9*lane*cp + (scan of the lane sums)
-                double PPr = cpp + (double)(9 * lane) * u2d(cp) + (inclq - qd);
-                uint32_t Pr = Pst;
-                double ip1 = (double)i0;
-                double tri = 0.5 * ip1 * (ip1 + 1.0);
-                double* tp = win + SWW_STEP * j + 9 * lane + 1;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    Pr += v[k];
-                    const double Pd = u2d(Pr);
-                    PPr += Pd;
-                    ip1 += 1.0;
-                    tri += ip1;
-                    const double Sd = fma(-ip1, m, Pd);
-                    const double SS = fma(-tri, m, PPr);
-                    tp[k] = (i0 + k < n) ? fma(km1, SS, Sd) : 0.0;
-                }
-                cpp += (double)SWW_STEP * u2d(cp) + __shfl_sync(FULL, inclq, 31);
-                cp += __shfl_sync(FULL, incl, 31);
             }
-            __syncwarp();
+            sww_team_sync<WPE>();
             const double* TTw = win - lo;   // TTw[i] = TT[i] for lo <= i <= lo + W
             if (first) {
                 first = false;
@@ -439,16 +496,16 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
                     t50_us = cross_x(thr, y_at(TTw, pos - 1), y_at(TTw, pos), t_first + (double)(pos - 1) * dt, dt) * 0.001;
                     if (t50_us != t50_us) t50_us = 0.0;
                 }
-                if (aux && lane == 0) {
+                if (aux && threadIdx.x == 0) {
                     const Stats st = stats_finalize(P.bl_inv_n, P.bl_sX, P.bl_sXX, blSd, 0.0, t_first * blSd + dt * blSXd);
                     double* a = aux + e * 4;
                     a[0] = m_own; a[1] = st.slope; a[2] = t50_us; a[3] = 0.0;
                 }
             }
             int minfrom = 0x7fffffff;
-            // Warp-uniform loop over rounds of 32 variants: every lane runs the arithmetic (a lane without work reads the start of
+            // Warp-uniform loop over rounds of 32*WPE variants: every lane runs the arithmetic (a lane without work reads the start of
             // the window), so the inner loop sits in convergent code and the fit matrix is read through the uniform datapath
-            const int n_rounds = (P.nvar + 31) >> 5;
+            const int n_rounds = (P.nvar + VSTRIDE - 1) / VSTRIDE;
             int rnd;
             // this lane's variant of the next round is loaded one round ahead (the table comes from L2 / L1)
             TrapDev tn = t_first_round;
@@ -456,12 +513,12 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
             int moden = mode_first_round;
 #pragma unroll 1
             for (rnd = 0; rnd < n_rounds; ++rnd) {
-                const int v = rnd * 32 + lane;
+                const int v = rnd * VSTRIDE + vlane;
                 const TrapDev tv = tn;
                 const double pick = pickn;
                 const int mode = moden;
                 {
-                    const SweepVar& nx = P.vars[min(v + 32, P.nvar - 1)];
+                    const SweepVar& nx = P.vars[min(v + VSTRIDE, P.nvar - 1)];
                     tn = nx.t; pickn = nx.pick_ns; moden = nx.mode;
                 }
                 bool eval = false;
@@ -496,11 +553,18 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
                 }
             }
             minfrom = __reduce_min_sync(FULL, minfrom);
+            if (WPE > 1) {   // the decision to build another window belongs to the team
+                if (lane == 0) xchi[we] = minfrom;
+                __syncthreads();
+#pragma unroll
+                for (int w = 0; w < WPE; ++w) minfrom = min(minfrom, xchi[w]);
+                __syncthreads();
+            }
             if (minfrom == 0x7fffffff) break;
             if (++rounds > 2 * 1024 / 32 + 2) {
                 // cannot happen (every variant fits a window that starts at its own `from`); never spin on the device
                 rnd = 0;
-                for (int v = lane; v < P.nvar; v += 32, ++rnd) {
+                for (int v = vlane; v < P.nvar; v += VSTRIDE, ++rnd) {
                     if ((done >> rnd) & 1u) continue;
                     if (P.out_f64) reinterpret_cast<double*>(out)[e * (long long)P.nvar + v] = CUDART_NAN;
                     else reinterpret_cast<float*>(out)[e * (long long)P.nvar + v] = CUDART_NAN_F;
@@ -509,15 +573,16 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
             }
             lo = max(0, min(minfrom, lo_max));
         }
-        __syncwarp();   // the window area becomes the next event's group table
+        sww_team_sync<WPE>();   // the window area becomes the next event's group table
     }
 }
 
-// launch geometry for a window of `steps` steps: warps per CTA and CTAs per SM that keep the most warps resident
+// launch geometry for a window of `steps` steps: warps per waveform (CTA) and CTAs per SM
 struct SwwGeom {
     int warps_per_cta = 0, ctas_per_sm = 0;
 };
-inline SwwGeom sww_geometry(int steps)
+template <int WPE>
+inline SwwGeom sww_geometry_t(int steps)
 {
     static SwwGeom cache[SWW_MAX_STEPS + 1];
     static bool attr_set = false;
@@ -527,19 +592,17 @@ inline SwwGeom sww_geometry(int steps)
         int dev = 0, optin = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (cudaFuncSetAttribute(sweep_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) return SwwGeom{};
+        if (cudaFuncSetAttribute(sweep_warp_kernel<WPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) return SwwGeom{};
         attr_set = true;
     }
-    SwwGeom best;
-    int best_warps = 0;
-    for (int w = 1; w <= SWW_MAX_WARPS; ++w) {
-        int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sweep_warp_kernel, w * 32, (size_t)w * sww_warp_bytes(steps)) != cudaSuccess) {
-            cudaGetLastError();
-            continue;
-        }
-        if (nb * w > best_warps) { best_warps = nb * w; best.warps_per_cta = w; best.ctas_per_sm = nb; }
+    SwwGeom g;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sweep_warp_kernel<WPE>, WPE * 32, (size_t)sww_warp_bytes(steps)) != cudaSuccess) {
+        cudaGetLastError();
+        return SwwGeom{};
     }
-    cache[steps] = best;
-    return best;
+    g.warps_per_cta = WPE;
+    g.ctas_per_sm = nb;
+    if (nb > 0) cache[steps] = g;
+    return g;
 }

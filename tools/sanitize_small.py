@@ -35,4 +35,14 @@ if "sweep" in which:
     wf = L.synth.generate_host(4, first_event=3)
     g = L.dsp_trap_ft_optimization(L.RDWaveforms(wf), L.tiefree_config(), L.us(500.0), L.us(5.0), handle=h)
     print("sweep", g.shape)
+    # the 20x10 grid on the one-warp-per-waveform kernel: generator events plus steps at the trace ends (second window)
+    ends = np.full((3, 8192), 10000, np.uint16)
+    ends[0, 40:] = 50000; ends[1, 8192 - 20:] = 50000; ends[2, :] = 0
+    wf2 = np.concatenate([L.synth.generate_host(40, first_event=11), L.synth.generate_host(8, mode=1), ends])
+    rts = [L.us(1.0 + 0.75 * i) for i in range(20)]
+    fts = [L.us(1.0 + 0.3 * i) for i in range(10)]
+    os.environ["LGDSP_SWEEP_PATH"] = "warp"
+    g2 = L.dsp_trap_rtft_grid(L.RDWaveforms(wf2), L.tiefree_config(), L.us(500.0), rts, fts, handle=h)
+    os.environ.pop("LGDSP_SWEEP_PATH")
+    print("sweep warp", g2.shape, float(np.nanmean(g2)))
 h.close()
