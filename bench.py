@@ -37,7 +37,9 @@ NCOL = 49
 # dram__bytes_read.sum + dram__bytes_write.sum of prefix + extract + CUSP/ZAC select + finish, per event).  The prefix sums
 # (65.6 KB per event) are written once and read by the two consumers through L2/HBM: that is the price of running the chain
 # as kernels with their own occupancy; algorithmic bytes are 16 776 B per waveform.
-NCU_DRAM_BYTES_PER_WF = {"dsp_icpc": 223.9e3}
+NCU_DRAM_BYTES_PER_WF = {"dsp_icpc": 223.9e3,
+                         # sweep_warp_kernel (profiles/r02_sweep_warp_kernel_ncu_full.txt): 309.0 MB read + 9.9 MB written per 16 384 events
+                         "trap_sweep": 19.46e3}
 
 
 def _peaks():
