@@ -150,3 +150,29 @@ def test_warp_path_large_batch_determinism(L, handle):
         outs.append(o.cpu().numpy())
     assert np.array_equal(outs[0], outs[1], equal_nan=True)
     assert np.array_equal(outs[0], outs[2], equal_nan=True)
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("LGDSP_FUZZ_SEEDS_SWEEP", "6")))))
+def test_warp_path_fuzz_against_cta_path(L, O, handle, seed):
+    """random configurations (sampling step 16 / 8 / 12.5 ns -> both forms of the division by dt, PolynomialDNI windows of 8 .. 60
+    samples and degree 1 .. 3 -> the run-time-sized pick-off loop, trace lengths 6144 .. 8192, random baseline windows and decay
+    times) and random (rt, ft) lists that fit the warp path's window: every output and the aux columns bit for bit"""
+    from test_gpu_fuzz import _draw
+    from legenddsp.jl_b200.dsp_filter_optimization import _run_general
+    cfg, tau, _, n, step = _draw(L, 300 + seed)
+    rng = np.random.default_rng(9000 + seed)
+    sc = step.ns() / 16.0
+    rts = [L.ns(float(v) * 1000.0 * sc) for v in np.sort(rng.uniform(0.3, 14.0, int(rng.integers(3, 24))))]
+    fts = [L.ns(float(v) * 1000.0 * sc) for v in np.sort(rng.uniform(0.1, 4.0, int(rng.integers(2, 12))))]
+    wf = np.ascontiguousarray(np.concatenate([L.synth.generate_host(150, first_event=900 * (seed + 1)),
+                                              L.synth.generate_host(10, mode=1), _pathological(8192)])[:, :n])
+    W = L.RDWaveforms(wf, L.ns(0.0), step)
+    var = L.trap_sweep_variants(rts, fts, step, mode="ft")
+    f64 = bool(seed % 2)
+    with sweep_path("warp"):
+        a, aa = _run_general(W, cfg, tau, var, f64=f64, want_aux=True, handle=handle)
+    with sweep_path("cta"):
+        b, ba = _run_general(W, cfg, tau, var, f64=f64, want_aux=True, handle=handle)
+    assert np.array_equal(a, b, equal_nan=True), np.nanmax(np.abs(a.astype(np.float64) - b))
+    assert np.array_equal(aa, ba, equal_nan=True)
+    assert np.isfinite(a).mean() > 0.9
