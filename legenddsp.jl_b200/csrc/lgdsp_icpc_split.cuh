@@ -346,44 +346,99 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
             const int ntail = P.tail_until - P.tail_from + 1;
             const int q = lean ? 0 : (ntail + NT - 1) / NT;
             const int ia = P.tail_from + tid * q, ib = min(ia + q - 1, P.tail_until);
-#pragma unroll 1
-            for (int i = 0; i < q; ++i) {
-                const int idx = ia + i;
-                const bool act = idx <= ib;
-                const double w = act ? u2d(xs[idx]) - m : cref;
-                const bool pos = w > 0.0;
-                if (act && !pos) bad = true;
-                const double u = (w - cref) * cinv, au = fabs(u);
-                const bool use = act && pos;
-                int cat = 0;
-                if (use) cat = !(cref > 0.0) || au > 0.125 ? 3 : (au > 0.015625 ? 2 : (au > 0.0009765625 ? 1 : 0));
-                const int wcat = __reduce_max_sync(FULL, cat);
-                double lg;
-                if (wcat == 0) {
-                    // |u| <= 2^-10: terms to u^5 (truncation u^5/6 < 2e-16 relative)
-                    double pl = fma(u, 1.0 / 5.0, -1.0 / 4.0);
-                    pl = fma(u, pl, 1.0 / 3.0); pl = fma(u, pl, -1.0 / 2.0); pl = fma(u, pl, 1.0);
-                    lg = fma(u, pl, clog);
-                } else if (wcat == 1) {
-                    // |u| <= 2^-6: terms to u^9
-                    const double u2 = u * u, u4 = u2 * u2;
-                    const double a0 = fma(-1.0 / 2.0, u, 1.0), a1 = fma(-1.0 / 4.0, u, 1.0 / 3.0), a2 = fma(-1.0 / 6.0, u, 1.0 / 5.0),
-                                 a3 = fma(-1.0 / 8.0, u, 1.0 / 7.0);
-                    const double b0 = fma(a1, u2, a0), b1 = fma(a3, u2, a2);
-                    const double c0 = fma(b1, u4, b0);
-                    lg = fma(u, fma(u4 * u4, 1.0 / 9.0, c0), clog);
-                } else {
-                    lg = clog + log1p_small(u);
-                    if (cat == 3) {
-                        lg = log_d(w);
-                        cref = w; cinv = 1.0 / w; clog = lg;
-                    }
+            // Integer pre-pass over the thread's run: the samples are integers, so w - c is the exact integer x - x_ref and the
+            // largest |u| = |x - x_ref| / c of the run is known before any logarithm; the warp picks ONE series for the whole run
+            // (no per-sample category, vote or branch on data), and a non-positive sample is an integer compare with floor(m).
+            int wcat = 3;
+            double c_run = 0.0, cinv_run = 0.0;
+            int xref = 0;
+            if (q > 0) {
+                const int mfl = (int)floor(fmin(fmax(m, -2.0e9), 2.0e9));   // x <= m  <=>  x <= floor(m) for integer x
+                int dmx = 0;
+                bool nonpos = false;
+                xref = ia <= ib ? (int)xs[ia] : 0;
+#pragma unroll 2
+                for (int idx = ia; idx <= ib; ++idx) {
+                    const int xv = (int)xs[idx];
+                    nonpos |= xv <= mfl;
+                    dmx = max(dmx, abs(xv - xref));
                 }
-                if (use) {
+                int cat = 0;
+                if (ia <= ib) {
+                    c_run = u2d((uint32_t)xref) - m;
+                    cinv_run = 1.0 / c_run;
+                    const double au = (double)dmx * cinv_run;
+                    cat = (nonpos || !(c_run > 0.0) || au > 0.125) ? 3 : (au > 0.015625 ? 2 : (au > 0.0009765625 ? 1 : 0));
+                }
+                wcat = __reduce_max_sync(FULL, cat);
+            }
+            if (wcat < 3) {
+                const double clog_run = ia <= ib ? log_d(c_run) : 0.0;
+#pragma unroll 1
+                for (int idx = ia; idx <= ib; ++idx) {
+                    const double u = (double)((int)xs[idx] - xref) * cinv_run;
+                    double lg;
+                    if (wcat == 0) {
+                        double pl = fma(u, 1.0 / 5.0, -1.0 / 4.0);
+                        pl = fma(u, pl, 1.0 / 3.0); pl = fma(u, pl, -1.0 / 2.0); pl = fma(u, pl, 1.0);
+                        lg = fma(u, pl, clog_run);
+                    } else if (wcat == 1) {
+                        const double u2 = u * u, u4 = u2 * u2;
+                        const double a0 = fma(-1.0 / 2.0, u, 1.0), a1 = fma(-1.0 / 4.0, u, 1.0 / 3.0), a2 = fma(-1.0 / 6.0, u, 1.0 / 5.0),
+                                     a3 = fma(-1.0 / 8.0, u, 1.0 / 7.0);
+                        const double b0 = fma(a1, u2, a0), b1 = fma(a3, u2, a2);
+                        const double c0 = fma(b1, u4, b0);
+                        lg = fma(u, fma(u4 * u4, 1.0 / 9.0, c0), clog_run);
+                    } else {
+                        lg = clog_run + log1p_small(u);
+                    }
                     const double X = t_first + (double)idx * dt;
                     tl_S += lg;
                     tl_SS = fma(lg, lg, tl_SS);
                     tl_SX = fma(X, lg, tl_SX);
+                }
+            } else {
+                // a run with a sample more than 1/8 away from its first one (small or noisy tails), or with a non-positive sample:
+                // the sample-by-sample form with re-referencing
+#pragma unroll 1
+                for (int i = 0; i < q; ++i) {
+                    const int idx = ia + i;
+                    const bool act = idx <= ib;
+                    const double w = act ? u2d(xs[idx]) - m : cref;
+                    const bool pos = w > 0.0;
+                    if (act && !pos) bad = true;
+                    const double u = (w - cref) * cinv, au = fabs(u);
+                    const bool use = act && pos;
+                    int cat = 0;
+                    if (use) cat = !(cref > 0.0) || au > 0.125 ? 3 : (au > 0.015625 ? 2 : (au > 0.0009765625 ? 1 : 0));
+                    const int wcat = __reduce_max_sync(FULL, cat);
+                    double lg;
+                    if (wcat == 0) {
+                        // |u| <= 2^-10: terms to u^5 (truncation u^5/6 < 2e-16 relative)
+                        double pl = fma(u, 1.0 / 5.0, -1.0 / 4.0);
+                        pl = fma(u, pl, 1.0 / 3.0); pl = fma(u, pl, -1.0 / 2.0); pl = fma(u, pl, 1.0);
+                        lg = fma(u, pl, clog);
+                    } else if (wcat == 1) {
+                        // |u| <= 2^-6: terms to u^9
+                        const double u2 = u * u, u4 = u2 * u2;
+                        const double a0 = fma(-1.0 / 2.0, u, 1.0), a1 = fma(-1.0 / 4.0, u, 1.0 / 3.0), a2 = fma(-1.0 / 6.0, u, 1.0 / 5.0),
+                                     a3 = fma(-1.0 / 8.0, u, 1.0 / 7.0);
+                        const double b0 = fma(a1, u2, a0), b1 = fma(a3, u2, a2);
+                        const double c0 = fma(b1, u4, b0);
+                        lg = fma(u, fma(u4 * u4, 1.0 / 9.0, c0), clog);
+                    } else {
+                        lg = clog + log1p_small(u);
+                        if (cat == 3) {
+                            lg = log_d(w);
+                            cref = w; cinv = 1.0 / w; clog = lg;
+                        }
+                    }
+                    if (use) {
+                        const double X = t_first + (double)idx * dt;
+                        tl_S += lg;
+                        tl_SS = fma(lg, lg, tl_SS);
+                        tl_SX = fma(X, lg, tl_SX);
+                    }
                 }
             }
             tl_S = wsum_d(tl_S); tl_SS = wsum_d(tl_SS); tl_SX = wsum_d(tl_SX);
