@@ -2543,7 +2543,7 @@ void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_byte
         icpc_prefix_kernel<uint16_t><<<grid(0), NT, K1_TOTAL, stream>>>(P, static_cast<const uint16_t*>(d_wf), n_events, ld, d_bl_ext,
                                                                         bl_stride, bl_div, d_tt, d_aux, d_rows);
     if (marks) cudaEventRecord(marks[1], stream);
-    const int fin_grid = (int)((n_events + K4_WARPS - 1) / K4_WARPS);
+    const int fin_grid = (int)((n_events * K4_NBLK + K4_WARPS - 1) / K4_WARPS);   // warps: one per event + K4_NBLK - 1 helpers
     auto launch_cz = [&](cudaStream_t st) {
         icpc_cuspzac_kernel<<<grid(2), NT, K3_TOTAL, st>>>(P, d_tt, d_aux, n_events, d_cz, d_rows);
         if (marks) cudaEventRecord(marks[3], st);

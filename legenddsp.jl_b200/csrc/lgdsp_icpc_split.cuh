@@ -1032,9 +1032,15 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
 constexpr int CZ_REC = 12;                    // doubles per candidate record: the 11 window states + the chunk index
 constexpr int CZ_MAXC = NT;                   // candidate capacity per (event, pass): every chunk
 constexpr int CZ_HDR = 16;                    // doubles per (event, pass) header
-enum { CZH_N = 0, CZH_MAXC, CZH_ARGC, CZH_MAXZ, CZH_ARGZ, CZH_PKP0, CZH_PKF0, CZH_PKP1, CZH_PKF1 };
+enum { CZH_N = 0, CZH_MAXC, CZH_ARGC, CZH_MAXZ, CZH_ARGZ, CZH_PKP0, CZH_PKF0, CZH_PKP1, CZH_PKF1,
+       CZH_CNT };                                    // (pass 0 only) arrival counter of the finish kernel's warps, zeroed here
 constexpr int CZP_LEN = CZ_HDR + CZ_MAXC * CZ_REC;   // doubles per (event, pass)
-constexpr int CZG_LEN = 2 * CZP_LEN;                 // doubles per event slot
+#ifndef LGDSP_K4_NBLK
+#define LGDSP_K4_NBLK 4
+#endif
+constexpr int K4_NBLK = LGDSP_K4_NBLK;               // warps of the finish kernel that may share one event
+constexpr int CZ_SCR = K4_NBLK * 4 + 2 * LGDSP_MAX_DNI;   // their exchange area: partial (max, argmax) x 2 + the two pick-off windows
+constexpr int CZG_LEN = 2 * CZP_LEN + CZ_SCR;        // doubles per event slot
 
 enum { K3R_CZC0 = 0, K3R_CZC1, K3R_CZMAX0, K3R_CZARG0, K3R_CZMAX1, K3R_CZARG1, K3R_CZSCR, K3R_CZSCR1, K3R_CZSCR2, K3R_CZSCR3, K3R_N };
 enum { K3I_CZN = 0, K3I_PKFROM = 1 /* 2 */, K3I_N = 4 };
@@ -1132,6 +1138,7 @@ __device__ __forceinline__ void cz_select(const CzDev& Z, const double* TT, int 
         cg[CZH_MAXC] = Mc; cg[CZH_ARGC] = (double)Ac; cg[CZH_MAXZ] = Mz; cg[CZH_ARGZ] = (double)Az;
         cg[CZH_PKP0] = pk_p[0]; cg[CZH_PKF0] = (double)pk_from[0];
         cg[CZH_PKP1] = pk_p[1]; cg[CZH_PKF1] = (double)pk_from[1];
+        cg[CZH_CNT] = 0.0;
     }
 }
 
@@ -1277,20 +1284,42 @@ icpc_cuspzac_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
     }
 }
 
-// finish: one warp per event, one lane per candidate chunk
+// finish: one lane per candidate chunk, one warp per event -- and up to K4_NBLK warps for an event with more than 32
+// candidates.  The kernel is bound by the latency of a round (33 dependent recurrence steps on prefix sums in L2 / HBM), and
+// 93 % of the events need one round (median 11 candidates) while the 3 % noise-only events, where all 248 chunks are
+// candidates, needed eight rounds on one warp: they set the duration of every launch.  Warp w < n_events takes the first 32
+// candidates of event w; the warps behind take the further blocks of the few events that have them (and exit at once
+// otherwise).  Warps that share an event leave their partial maxima and pick-off windows in the event's slot of the ring;
+// the last one to arrive (counter in the header) combines them.  Maxima / first indices do not depend on the order and the
+// pick-off estimate is dni_eval_warp on the same values: bit-identical to one warp per event.
 constexpr int K4_WARPS = 4;
-__global__ void __launch_bounds__(K4_WARPS * 32)
+__global__ void __launch_bounds__(K4_WARPS * 32, 5)
 icpc_cuspzac_finish_kernel(const __grid_constant__ IcpcDev P, const double* __restrict__ ttg, const double* __restrict__ auxg,
-                           const double* __restrict__ czg, long long n_events, double* __restrict__ rows)
+                           double* __restrict__ czg, long long n_events, double* __restrict__ rows)
 {
     __shared__ double stash_s[K4_WARPS][2][LGDSP_MAX_DNI];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = P.n;
     const int nw = P.sig_dni.n_w;
     const double* A_sig = P.dni_A + LGDSP_MAX_DNI * 4;
-    double* stash = &stash_s[wid][0][0];
     const int npass = P.cz_shared ? 1 : 2;
-    for (long long e = (long long)blockIdx.x * K4_WARPS + wid; e < n_events; e += (long long)gridDim.x * K4_WARPS) {
+    const long long w = (long long)blockIdx.x * K4_WARPS + wid;
+    long long e;
+    int kb;
+    if (w < n_events) { e = w; kb = 0; }
+    else { e = (w - n_events) / (K4_NBLK - 1); kb = 1 + (int)((w - n_events) % (K4_NBLK - 1)); }
+    if (e >= n_events) return;
+    double* ce = czg + e * CZG_LEN;
+    int nwork = 1;
+    {
+        const int n0 = (int)ce[CZH_N], n1 = npass == 2 ? (int)ce[CZP_LEN + CZH_N] : 0;
+        nwork = min(K4_NBLK, max(1, (max(n0, n1) + 31) >> 5));
+    }
+    if (kb >= nwork) return;
+    const bool shared_event = nwork > 1;
+    double* scr = ce + 2 * CZP_LEN;                       // [K4_NBLK][4] partials, then the two pick-off windows
+    double* stash = shared_event ? scr + K4_NBLK * 4 : &stash_s[wid][0][0];
+    {
         const double* TT = ttg + e * TTG_LEN;
         double czmax[2] = {-CUDART_INF, -CUDART_INF};
         int czarg[2] = {0x7fffffff, 0x7fffffff};
@@ -1299,17 +1328,17 @@ icpc_cuspzac_finish_kernel(const __grid_constant__ IcpcDev P, const double* __re
         auto pass = [&](auto psc, const bool want_cusp, const bool want_zac) {
             constexpr int ps = decltype(psc)::value;
             const CzDev& Z = P.cz[ps];
-            const double* cg = czg + e * CZG_LEN + ps * CZP_LEN;
+            const double* cg = ce + ps * CZP_LEN;
             const int ncand = (int)cg[CZH_N];
             pk_p[0] = cg[CZH_PKP0]; pk_p[1] = cg[CZH_PKP1];
             pk_from[0] = (int)cg[CZH_PKF0]; pk_from[1] = (int)cg[CZH_PKF1];
-            if (lane == 0) {
+            if (lane == 0 && kb == 0) {
                 // the coarse points are outputs themselves
                 if (want_cusp) { czmax[0] = cg[CZH_MAXC]; czarg[0] = (int)cg[CZH_ARGC]; }
                 if (want_zac) { czmax[1] = cg[CZH_MAXZ]; czarg[1] = (int)cg[CZH_ARGZ]; }
             }
 #pragma unroll 1
-            for (int c0 = 0; c0 < ncand; c0 += 32) {
+            for (int c0 = 32 * kb; c0 < ncand; c0 += 32 * nwork) {
                 if (c0 + lane < ncand) {
                     const double* r = cg + CZ_HDR + (size_t)(c0 + lane) * CZ_REC;
                     CzState st;
@@ -1343,8 +1372,34 @@ icpc_cuspzac_finish_kernel(const __grid_constant__ IcpcDev P, const double* __re
         __syncwarp();
         czmax[0] = wargmax_d(czmax[0], czarg[0]);
         czmax[1] = wargmax_d(czmax[1], czarg[1]);
-        const double vc = dni_eval_warp(A_sig, nw, P.sig_dni.m, stash, pk_p[0] - (double)pk_from[0], lane);
-        const double vz = dni_eval_warp(A_sig, nw, P.sig_dni.m, stash + LGDSP_MAX_DNI, pk_p[1] - (double)pk_from[1], lane);
+        const double* win = stash;
+        if (shared_event) {
+            if (lane == 0) {
+                double* pr = scr + kb * 4;
+                pr[0] = czmax[0]; pr[1] = (double)czarg[0]; pr[2] = czmax[1]; pr[3] = (double)czarg[1];
+            }
+            __threadfence();    // this warp's partials and pick-off samples are visible before it counts itself in
+            __syncwarp();
+            unsigned prev = 0;
+            if (lane == 0) prev = atomicAdd(reinterpret_cast<unsigned*>(ce + CZH_CNT), 1u);
+            prev = __shfl_sync(FULL, prev, 0);
+            if (prev != (unsigned)(nwork - 1)) return;   // a later warp finishes the event
+            __threadfence();
+            double pm0 = -CUDART_INF, pm1 = -CUDART_INF;
+            int pa0 = 0x7fffffff, pa1 = 0x7fffffff;
+            if (lane < nwork) {
+                const double* pr = scr + lane * 4;
+                pm0 = __ldcg(pr); pa0 = (int)__ldcg(pr + 1); pm1 = __ldcg(pr + 2); pa1 = (int)__ldcg(pr + 3);
+            }
+            czmax[0] = wargmax_d(pm0, pa0); czarg[0] = pa0;
+            czmax[1] = wargmax_d(pm1, pa1); czarg[1] = pa1;
+            double* sm = &stash_s[wid][0][0];
+            for (int i = lane; i < 2 * LGDSP_MAX_DNI; i += 32) sm[i] = __ldcg(stash + i);
+            __syncwarp();
+            win = sm;
+        }
+        const double vc = dni_eval_warp(A_sig, nw, P.sig_dni.m, win, pk_p[0] - (double)pk_from[0], lane);
+        const double vz = dni_eval_warp(A_sig, nw, P.sig_dni.m, win + LGDSP_MAX_DNI, pk_p[1] - (double)pk_from[1], lane);
         if (lane == 0 && auxg[e * AUX_LEN + AX_BAD] != 0.0) {
             double* ro = rows + e * LGDSP_NCOL;
             ro[LGDSP_COL_e_cusp_max] = ro[LGDSP_COL_t_cusp_max] = ro[LGDSP_COL_e_cusp] = CUDART_NAN;
@@ -1358,6 +1413,5 @@ icpc_cuspzac_finish_kernel(const __grid_constant__ IcpcDev P, const double* __re
             ro[LGDSP_COL_t_zac_max] = P.t_first + (double)(czarg[1] + P.zac_L - 1) * P.dt;
             ro[LGDSP_COL_e_zac] = vz;
         }
-        __syncwarp();   // the stash is reused by this warp's next event
     }
 }
