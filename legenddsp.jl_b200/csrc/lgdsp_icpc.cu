@@ -2513,12 +2513,16 @@ void window_stats_launch(const void* d_wf, int sample_bytes, long long n_events,
 cudaError_t icpc_split_configure(int* bps3)
 {
     cudaError_t err;
-    if ((err = cudaFuncSetAttribute(icpc_prefix_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_TOTAL)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(icpc_prefix_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_TOTAL)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(icpc_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(icpc_prefix_kernel<uint16_t, 0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(icpc_prefix_kernel<uint32_t, 0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(icpc_prefix_kernel<uint16_t, LGDSP_GROUP_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(icpc_prefix_kernel<uint16_t, LGDSP_GROUP_PZTRAP_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(icpc_extract_kernel<0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(icpc_extract_kernel<LGDSP_GROUP_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(icpc_extract_kernel<LGDSP_GROUP_PZTRAP_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_TOTAL)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(icpc_cuspzac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_TOTAL)) != cudaSuccess) return err;
-    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3[0], icpc_prefix_kernel<uint16_t>, NT, K1_TOTAL)) != cudaSuccess) return err;
-    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3[1], icpc_extract_kernel, NT2, K2_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3[0], icpc_prefix_kernel<uint16_t, 0u>, NT, K1_TOTAL)) != cudaSuccess) return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3[1], icpc_extract_kernel<0u>, NT2, K2_TOTAL)) != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3[2], icpc_cuspzac_kernel, NT, K3_TOTAL);
 }
 long long icpc_split_tt_doubles() { return TTG_LEN; }
@@ -2536,12 +2540,18 @@ void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_byte
     if (marks) { stream_cz = nullptr; cudaEventRecord(marks[0], stream); }
     const bool cz = (P.groups & LGDSP_GROUP_CUSPZAC) != 0;
     auto grid = [&](int k) { const long long cap = (long long)sm_count * bps3[k]; return (int)(n_events < cap ? n_events : cap); };
+    // (16-bit samples with the full chain or the lean configs[1] group run instantiations with a compile-time group mask)
+#define LGDSP_PREFIX_ARGS P, static_cast<const uint16_t*>(d_wf), n_events, ld, d_bl_ext, bl_stride, bl_div, d_tt, d_aux, d_rows
     if (sample_bytes == 4)
-        icpc_prefix_kernel<uint32_t><<<grid(0), NT, K1_TOTAL, stream>>>(P, static_cast<const uint32_t*>(d_wf), n_events, ld, d_bl_ext,
-                                                                        bl_stride, bl_div, d_tt, d_aux, d_rows);
+        icpc_prefix_kernel<uint32_t, 0u><<<grid(0), NT, K1_TOTAL, stream>>>(P, static_cast<const uint32_t*>(d_wf), n_events, ld, d_bl_ext,
+                                                                            bl_stride, bl_div, d_tt, d_aux, d_rows);
+    else if (P.groups == LGDSP_GROUP_ALL)
+        icpc_prefix_kernel<uint16_t, LGDSP_GROUP_ALL><<<grid(0), NT, K1_TOTAL, stream>>>(LGDSP_PREFIX_ARGS);
+    else if (P.groups == LGDSP_GROUP_PZTRAP_LEAN)
+        icpc_prefix_kernel<uint16_t, LGDSP_GROUP_PZTRAP_LEAN><<<grid(0), NT, K1_TOTAL, stream>>>(LGDSP_PREFIX_ARGS);
     else
-        icpc_prefix_kernel<uint16_t><<<grid(0), NT, K1_TOTAL, stream>>>(P, static_cast<const uint16_t*>(d_wf), n_events, ld, d_bl_ext,
-                                                                        bl_stride, bl_div, d_tt, d_aux, d_rows);
+        icpc_prefix_kernel<uint16_t, 0u><<<grid(0), NT, K1_TOTAL, stream>>>(LGDSP_PREFIX_ARGS);
+#undef LGDSP_PREFIX_ARGS
     if (marks) cudaEventRecord(marks[1], stream);
     const int fin_grid = (int)((n_events * K4_NBLK + K4_WARPS - 1) / K4_WARPS);   // warps: one per event + K4_NBLK - 1 helpers
     auto launch_cz = [&](cudaStream_t st) {
@@ -2558,7 +2568,12 @@ void icpc_split_launch_batch(const IcpcDev& P, const void* d_wf, int sample_byte
         launch_cz(stream_cz);
         cudaEventRecord(ev_cz, stream_cz);
     }
-    icpc_extract_kernel<<<grid(1), NT2, K2_TOTAL, stream>>>(P, d_tt, d_aux, n_events, cz ? 0 : 1, d_rows);
+    if (P.groups == LGDSP_GROUP_ALL)
+        icpc_extract_kernel<LGDSP_GROUP_ALL><<<grid(1), NT2, K2_TOTAL, stream>>>(P, d_tt, d_aux, n_events, cz ? 0 : 1, d_rows);
+    else if (P.groups == LGDSP_GROUP_PZTRAP_LEAN)
+        icpc_extract_kernel<LGDSP_GROUP_PZTRAP_LEAN><<<grid(1), NT2, K2_TOTAL, stream>>>(P, d_tt, d_aux, n_events, cz ? 0 : 1, d_rows);
+    else
+        icpc_extract_kernel<0u><<<grid(1), NT2, K2_TOTAL, stream>>>(P, d_tt, d_aux, n_events, cz ? 0 : 1, d_rows);
     if (marks) cudaEventRecord(marks[2], stream);
     if (cz && !par) launch_cz(stream);
     if (par) cudaStreamWaitEvent(stream, ev_cz, 0);   // the ring slot is reused behind both consumers

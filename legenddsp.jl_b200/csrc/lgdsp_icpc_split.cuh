@@ -34,7 +34,8 @@ constexpr int K1_TILE = K1_BAR + 16;                       // double tile[NWARP]
 constexpr int K1_TOTAL = K1_TILE + NWARP * 32 * TILE_LD * 8;
 static_assert(4 * (K1_TOTAL + 1024) <= 233472, "four CTAs per SM");
 
-template <typename SAMPLE>
+// GMASK: compile-time column-group mask (0: from the parameter block), see icpc_extract_kernel
+template <typename SAMPLE, unsigned GMASK>
 __global__ void __launch_bounds__(NT, 4)
 icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__ wf, long long n_events, long long ld,
                    const double* __restrict__ bl_ext, long long bl_stride, double bl_div, double* __restrict__ ttg,
@@ -50,7 +51,7 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
     const int n = P.n;
     const uint32_t wf_bytes = (uint32_t)n * (uint32_t)sizeof(SAMPLE);
     const double t_first = P.t_first, dt = P.dt;
-    const unsigned G = P.groups;
+    const unsigned G = GMASK ? GMASK : P.groups;
 
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -512,6 +513,9 @@ constexpr int K2_BAR = K2_FLAG + NT2;
 constexpr int K2_TOTAL = K2_BAR + 16;
 static_assert(3 * (K2_TOTAL + 1024) <= 233472, "three CTAs per SM");
 
+// GMASK != 0: the column-group mask is a compile-time constant (the full chain and the lean configs[1] group get their own
+// instantiation without the other's branches: smaller hot code for the instruction cache); 0: mask from the parameter block
+template <unsigned GMASK>
 __global__ void __launch_bounds__(NT2, 3)
 icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict__ ttg, const double* __restrict__ auxg,
                     long long n_events, int write_cz_zeros, double* __restrict__ rows)
@@ -531,7 +535,7 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
     const int n = P.n;
     const uint32_t tt_bytes = (uint32_t)(n + 2) * 8u;
     const double t_first = P.t_first, dt = P.dt;
-    const unsigned G = P.groups;
+    const unsigned G = GMASK ? GMASK : P.groups;
     const double* A_int = P.dni_A;
     const double* A_sig = P.dni_A + LGDSP_MAX_DNI * 4;
 
