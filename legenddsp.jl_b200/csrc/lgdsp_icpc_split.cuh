@@ -52,6 +52,7 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
     const uint32_t wf_bytes = (uint32_t)n * (uint32_t)sizeof(SAMPLE);
     const double t_first = P.t_first, dt = P.dt;
     const unsigned G = GMASK ? GMASK : P.groups;
+    const bool lean = (G & LGDSP_GROUP_LEAN) != 0;   // only {blmean, t0, t50, e_trap, e_10410} are wanted (+ e_max / e_min / saturation counts)
 
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -102,8 +103,10 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
             for (int idx = P.bl_from + tid; idx <= P.bl_until; idx += NT) {
                 const uint32_t x = xs[idx];
                 blS += x;
-                blSX += (unsigned long long)x * (unsigned long long)idx;
-                blSS += (unsigned long long)x * (unsigned long long)x;
+                if (!lean) {   // (slope / sigma of the baseline are not among the lean columns)
+                    blSX += (unsigned long long)x * (unsigned long long)idx;
+                    blSS += (unsigned long long)x * (unsigned long long)x;
+                }
             }
             const double a = wsum_d((double)blS), bq = wsum_d((double)blSS), c = wsum_d((double)blSX);
             if (lane == 0) { red[K1R_BLS * NWARP + wid] = a; red[K1R_BLSS * NWARP + wid] = bq; red[K1R_BLSX * NWARP + wid] = c; }
@@ -218,8 +221,7 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
         double thr[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) thr[k] = e_max * P.tx_frac[k];
-        const bool lean = (G & LGDSP_GROUP_LEAN) != 0;   // only {blmean, t0, t50, e_trap, e_10410} are wanted
-        if (lean) { thr[0] = CUDART_INF; thr[2] = CUDART_INF; thr[3] = CUDART_INF; thr[4] = CUDART_INF; }
+        if (lean) { thr[0] = CUDART_INF; thr[2] = CUDART_INF; thr[3] = CUDART_INF; thr[4] = CUDART_INF; }   // only t50
 
         // ==========================================================================================
         // prefix sums of the pole-zero waveform -> global ring; t10..t99 masks from the values in flight
@@ -238,7 +240,8 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
             bool straddle = false;
             if (G & LGDSP_GROUP_TIMING) {
 #pragma unroll
-                for (int t = 0; t < 5; ++t) straddle |= !(ylo - guard >= thr[t]) && !(yhi + guard < thr[t]);
+                for (int t = 0; t < 5; ++t)
+                    if (!(lean && t != 1)) straddle |= !(ylo - guard >= thr[t]) && !(yhi + guard < thr[t]);
                 straddle = straddle && cvalid > 0;
             }
             const bool wstr = __any_sync(FULL, straddle);   // warp-uniform: compare inside the loop or not
@@ -280,10 +283,12 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
                         if (k < 32) {
                             const uint32_t bit = 1u << k;
 #pragma unroll
-                            for (int t = 0; t < 5; ++t) lo[t] |= (y >= thr[t]) ? bit : 0u;
+                            for (int t = 0; t < 5; ++t)
+                                if (!(lean && t != 1)) lo[t] |= (y >= thr[t]) ? bit : 0u;
                         } else {
 #pragma unroll
-                            for (int t = 0; t < 5; ++t) hi |= (y >= thr[t]) ? (1u << t) : 0u;
+                            for (int t = 0; t < 5; ++t)
+                                if (!(lean && t != 1)) hi |= (y >= thr[t]) ? (1u << t) : 0u;
                         }
                     }
                     tprev = tn;
@@ -320,6 +325,7 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
             if (G & LGDSP_GROUP_TIMING) {
 #pragma unroll
                 for (int t = 0; t < 5; ++t) {
+                    if (lean && t != 1) continue;
                     unsigned long long mbt = (unsigned long long)lo[t] | ((unsigned long long)((hi >> t) & 1u) << 32);
                     if (cvalid <= 0) mbt = 0ull;
                     else if (ylo - guard >= thr[t]) mbt = chunk_all;
@@ -456,7 +462,7 @@ icpc_prefix_kernel(const __grid_constant__ IcpcDev P, const SAMPLE* __restrict__
         if (wid < 5) {
             // crossing resolution of t10..t99 (positions; the consumers interpolate on TT)
             int pos = -1, mult = 0;
-            if (G & LGDSP_GROUP_TIMING) resolve_runs(masks + wid * NWORDS, P.tx_min_n, lane, pos, mult);
+            if ((G & LGDSP_GROUP_TIMING) && !(lean && wid != 1)) resolve_runs(masks + wid * NWORDS, P.tx_min_n, lane, pos, mult);
             if (lane == 0) { ax[AX_POS + wid] = (double)pos; ax[AX_THR + wid] = thr[wid == 0 ? 0 : wid == 1 ? 1 : wid == 2 ? 2 : wid == 3 ? 3 : 4]; }
         } else if (wid == 5) {
             // baseline [:102] and tailstats [:115] (lane 0 / lane 1, same code path)
