@@ -5,7 +5,7 @@
 // to amortise them, and builds the prefix sums of the WHOLE pole-zero waveform although a trapezoid sweep only reads
 // them in a window of ~2 200 samples around t50.  Here a warp owns a waveform from the first load to the last store:
 //
-//   pass 1     whole waveform, INTEGERS only, 16 consecutive samples per lane and step (two 128-bit loads, two steps ahead):
+//   pass 1     whole waveform, INTEGERS only, 16 consecutive samples per lane and step (two 128-bit streaming loads, three steps ahead):
 //              exact prefix sums P (warp scan); per 16-sample group P at its start and its largest / smallest sample -> SMEM;
 //              P and PP = cumsum(P) at every 512-sample boundary -> SMEM
 //   baseline   sum x, sum i*x over bl_window as differences of P / PP (two or three look-ups)                      [:250-253]
@@ -13,20 +13,23 @@
 //              bounds of y over the group (float, rounded outwards -> SMEM); every lane evaluates its most promising group in
 //              float64, and only groups whose upper bound reaches the best value found are evaluated too (a few per cent of
 //              a flat top) -> max(y), exactly the float64 value a full evaluation gives
-//   pass 1b    threshold 0.5*max(y) [:260]: a group whose bounds lie below / above the threshold gives a 0x00 / 0xff mask byte,
+//   pass 1b    threshold 0.5*max(y) [:260]: a group whose bounds lie below / above the threshold gives 16 mask bits 0x0000 / 0xffff,
 //              the others (the rising edge; every group of a noise-only event) are evaluated sample by sample;
 //              bit-parallel Intersect run detection (resolve_runs) -> first crossing sample
 //   pass 2     prefix sums TT of the pole-zero waveform ONLY in a window [lo, lo + W) around the crossing (W from the host:
 //              what the variant set can reach), 9 consecutive samples per lane and step (odd stride: conflict-free 64-bit
 //              shared-memory stores), closed form from P / PP exactly as sweep_kernel -> identical TT values
 //   t50        linear interpolation of the crossing [:260]
-//   variants   one LANE per (rt, ft) point walks the n_w outputs of its PolynomialDNI pick-off window [:262-268]
-//              (4 look-ups in TT per output, fit matrix from the constant bank); results straight to global memory.
+//   variants   warp-uniform rounds of 32 variants, one LANE per (rt, ft) point, which walks the n_w outputs of its PolynomialDNI
+//              pick-off window [:262-268] (4 look-ups in TT per output; fit matrix from the constant bank through the uniform
+//              datapath, blocks of 11 outputs: a complete unroll ran instruction-fetch bound); results straight to global memory.
 //              A variant whose window leaves [lo, lo + W) -- clamped pick-offs of events with t50 at the trace ends -- waits
 //              for a second window built where it needs it (rare; the loop ends because every variant fits W on its own).
 //
-// No block barrier, no atomics; the warps of a CTA share nothing.  Outputs are bit-identical to sweep_kernel's (same
-// arithmetic on the same exact integers), which stays the path of FIR / Savitzky-Golay variants, 32-bit samples and
+// No block barrier, no atomics (sweep_warp_kernel<1>, the default: one warp = one CTA).  sweep_warp_kernel<2> splits every phase
+// over a team of two warps (same shared memory per waveform, twice the resident warps, ~8 barriers of 64 threads): measured
+// slower (37.0 vs 40.4 M wf/s, instruction fetch), kept behind LGDSP_SWEEP_WPE=2.  Outputs are bit-identical to sweep_kernel's
+// (same arithmetic on the same exact integers), which stays the path of FIR / Savitzky-Golay variants, 32-bit samples and
 // variant sets whose reach exceeds the window capacity.
 
 #ifndef SWW_UNR
@@ -42,7 +45,6 @@ constexpr int kU1A = SWW_U1A, kU1B = SWW_U1B;   // unroll factors of the group l
 constexpr int SWW_STEP = 288;        // samples per window-build step (9 per lane)
 constexpr int SWW_MIN_STEPS = 4;     // the window area also holds pass 1's group table (8 KB)
 constexpr int SWW_MAX_STEPS = 10;
-constexpr int SWW_MAX_WARPS = 12;    // warps per CTA (launch bound)
 constexpr int SWW_EXT_BYTES = 4096;  // float2 per 16-sample group
 __host__ __device__ constexpr int sww_win_bytes(int steps) { return (steps * SWW_STEP + 8) * 8; }
 // per waveform: window | mask | cP[20] | cPP[18] | locPP[16] | xch[8] | stepP[16] | xchi[4]   (11 CTAs per SM at 8 window steps)
