@@ -28,7 +28,9 @@ SHOW = ("UBLKCP", "SYNCS", "UTMA", "REDUX", "BAR.", "DFMA", "DADD", "DMUL", "DSE
 index = []
 for name, lines in funcs.items():
     pretty = demangle(name)
-    short = re.sub(r"^void ", "", pretty).split("(")[0].replace("lgdsp::", "")
+    # (template arguments carry casts such as "(unsigned int)127": drop them before cutting at the argument list, so that every
+    #  instantiation gets its own file)
+    short = re.sub(r"\((?:unsigned )?(?:int|long|short|char|bool)\)", "", re.sub(r"^void ", "", pretty)).split("(")[0].replace("lgdsp::", "")
     short = re.sub(r"[^A-Za-z0-9]+", "_", short.replace("(anonymous namespace)::", "")).strip("_").replace("unnamed_", "")
     hist = collections.Counter()
     base = collections.Counter()
