@@ -563,6 +563,18 @@ def main():
         extra.append({"workload": WL_NAME["trap_sweep"], "value": world * B * xs / (ms3 * 1e-3), "unit": "waveforms/s", "ms_per_step": ms3 / xs,
                       "roofline": {"frac": B * b3 / (ms3 * 1e-3 / xs) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_waveform": b3},
                       "kernel": "sweep_warp_kernel (one warp per waveform; LGDSP_SWEEP_PATH=cta: sweep_kernel)"})
+        # the reference's own rise-time sweep: e_grid_rt_trap (31 rise times at ft = 2 us), fixed pick-off enc_pickoff_trap, Float64 grid
+        # (src/dsp_filter_optimization.jl:102-133); nothing in it depends on t50, so the warp kernel skips max(y) and the crossing
+        sp4 = L.resolve_sweep_params(cfg, tau, out_f64=True)
+        v4 = L.trap_sweep_variants(L.grid_values(cfg.e_grid_rt_trap), [L.us(2.0)], L.ns(16.0), mode="rt", pickoff=cfg.enc_pickoff_trap)
+        nv4 = len(v4.array)
+        out4 = torch.empty((B, nv4), dtype=torch.float64, device=dev)
+        ms_rt, _ = timed(lambda k: h.gsweep_run_device(sp4, pool[k % n_pool].data_ptr(), B, 8192, v4.array, out4.data_ptr()), xs, 2)
+        b4 = BYTES_IN + nv4 * 8
+        extra.append({"workload": f"dsp_trap_rt_optimization: {nv4} rise times, fixed pick-off (src/dsp_filter_optimization.jl:102-133)",
+                      "value": world * B * xs / (ms_rt * 1e-3), "unit": "waveforms/s", "ms_per_step": ms_rt / xs,
+                      "roofline": {"frac": B * b4 / (ms_rt * 1e-3 / xs) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_waveform": b4},
+                      "kernel": "sweep_warp_kernel"})
 
     kernel_ms = None
     if args.workload == "dsp_icpc" and args.path == "split" and not args.no_extra and rank == 0:

@@ -256,6 +256,9 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
         const uint16_t* __restrict__ x = wf + e * ld;
         if (threadIdx.x == 0 && e + gridDim.x < n_events) tma_prefetch_l2(wf + (e + gridDim.x) * ld, (uint32_t)n * 2u);
 
+        // Fixed pick-offs (win_mode 0) without the aux outputs read nothing that depends on t50: max(y), the threshold mask and the
+        // crossing are skipped (dsp_trap_rt_optimization, src/dsp_filter_optimization.jl:102-133)
+        const bool need_t50 = P.win_mode == 1 || aux != nullptr;
         // ---- pass 1 (integers only): the steps it = we, we + WPE, ...; prefix sums inside the step, group table, step sums ----
         {
             uint32_t carryP = 0;             // (WPE == 1: the steps follow each other, the carries run along)
@@ -274,9 +277,12 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
 #pragma unroll
                 for (int k = 1; k < 16; ++k) s[k] = s[k - 1] + v[k];
                 const int i0 = it * 512 + 16 * lane;
-                uint32_t xmax = __vimax3_u32(__vimax3_u32(v[0], v[1], v[2]), __vimax3_u32(v[3], v[4], v[5]), __vimax3_u32(v[6], v[7], v[7]));
-                uint32_t xmin = __vimin3_u32(__vimin3_u32(v[0], v[1], v[2]), __vimin3_u32(v[3], v[4], v[5]), __vimin3_u32(v[6], v[7], v[7]));
-                if (i0 + 8 < n) {
+                uint32_t xmax = 0, xmin = 0;
+                if (need_t50) {
+                    xmax = __vimax3_u32(__vimax3_u32(v[0], v[1], v[2]), __vimax3_u32(v[3], v[4], v[5]), __vimax3_u32(v[6], v[7], v[7]));
+                    xmin = __vimin3_u32(__vimin3_u32(v[0], v[1], v[2]), __vimin3_u32(v[3], v[4], v[5]), __vimin3_u32(v[6], v[7], v[7]));
+                }
+                if (need_t50 && i0 + 8 < n) {
                     xmax = __vimax3_u32(__vimax3_u32(v[8], v[9], v[10]), __vimax3_u32(v[11], v[12], v[13]), __vimax3_u32(v[14], v[15], xmax));
                     xmin = __vimin3_u32(__vimin3_u32(v[8], v[9], v[10]), __vimin3_u32(v[11], v[12], v[13]), __vimin3_u32(v[14], v[15], xmin));
                 }
@@ -294,7 +300,7 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
                 const uint32_t sum_ex = __reduce_add_sync(FULL, (uint32_t)(31 - lane) * s[15]);
                 if (WPE == 1) {
                     if (lane == 0) { cP[it] = carryP; cPP[it] = (double)carryPP; }
-                    if (i0 < n) pst[it * 32 + lane] = carryP + incl - s[15];
+                    if (need_t50 && i0 < n) pst[it * 32 + lane] = carryP + incl - s[15];
                     carryPP += 512ull * carryP + 16ull * sum_ex + sum_t;
                     carryP += __shfl_sync(FULL, incl, 31);
                 } else {
@@ -302,9 +308,9 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
                         stepP[it] = incl;
                         locPP[it] = (double)(16ull * sum_ex + sum_t);
                     }
-                    if (i0 < n) pst[it * 32 + lane] = incl - s[15];
+                    if (need_t50 && i0 < n) pst[it * 32 + lane] = incl - s[15];
                 }
-                if (i0 < n) xmm[it * 32 + lane] = (xmax << 16) | xmin;
+                if (need_t50 && i0 < n) xmm[it * 32 + lane] = (xmax << 16) | xmin;
             }
             if (WPE == 1 && lane == 0) { cP[n_it] = carryP; cPP[n_it] = (double)carryPP; }
         }
@@ -339,67 +345,71 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
         const double m_own = mul_rn(blSd, P.bl_inv_n);
         const double m = bl_ext ? bl_ext[e] : m_own;
 
-        // ---- pass 1a: rigorous bounds of y over every group -> table; max(y) from the few groups that can hold it ----
-        // y_k = d_k + km1*Sd_k, d_k = x_k - m, Sd_k = Sd_0 + sum_{j<=k} d_j with Sd_0 = P(group start) - i0*m, so within a group
-        //   Sd_0 + 16*min(0, d_min) <= Sd_k <= Sd_0 + 16*max(0, d_max);  the sample that attains d_max has y >= d_max + km1*Sd_lo.
-        // G covers the rounding of the float64 evaluation (|terms| < 2^17 + |km1| n 2^16, one ulp each).
-        const double G = 1e-9 * (65536.0 + fabs(m) + fabs(km1) * (double)n * 65536.0);
-        double lbmax = -CUDART_INF;
-        float best_ub = -CUDART_INF_F;
-        int best_it = -1;
-        const int my_groups = (n - 16 * lane + 511) >> 9;   // groups of this lane's column (<= 0: none)
+        int pos = -1;
+        double thr = 0.0;
+        if (need_t50) {
+            // ---- pass 1a: rigorous bounds of y over every group -> table; max(y) from the few groups that can hold it ----
+            // y_k = d_k + km1*Sd_k, d_k = x_k - m, Sd_k = Sd_0 + sum_{j<=k} d_j with Sd_0 = P(group start) - i0*m, so within a group
+            //   Sd_0 + 16*min(0, d_min) <= Sd_k <= Sd_0 + 16*max(0, d_max);  the sample that attains d_max has y >= d_max + km1*Sd_lo.
+            // G covers the rounding of the float64 evaluation (|terms| < 2^17 + |km1| n 2^16, one ulp each).
+            const double G = 1e-9 * (65536.0 + fabs(m) + fabs(km1) * (double)n * 65536.0);
+            double lbmax = -CUDART_INF;
+            float best_ub = -CUDART_INF_F;
+            int best_it = -1;
+            const int my_groups = (n - 16 * lane + 511) >> 9;   // groups of this lane's column (<= 0: none)
 #pragma unroll (kU1A)
-        for (int it = we; it < my_groups; it += WPE) {
-            const int i0 = it * 512 + 16 * lane;
-            const uint32_t xm = xmm[it * 32 + lane];
-            const double dmax = u2d(xm >> 16) - m, dmin = u2d(xm & 0xffffu) - m;
-            const double Sd0 = fma(-(double)i0, m, u2d(pst[it * 32 + lane] + pbase(it)));
-            const double Sd_hi = fma(16.0, dmax > 0.0 ? dmax : 0.0, Sd0), Sd_lo = fma(16.0, dmin < 0.0 ? dmin : 0.0, Sd0);
-            const double k_hi = km1 >= 0.0 ? Sd_hi : Sd_lo, k_lo = km1 >= 0.0 ? Sd_lo : Sd_hi;
-            const double ub = fma(km1, k_hi, dmax) + G;
-            const double lb_all = fma(km1, k_lo, dmin) - G;
-            const double lb_top = fma(km1, k_lo, dmax) - G;
-            lbmax = lb_top > lbmax ? lb_top : lbmax;
-            const float ubf = __double2float_ru(ub);
-            ext[it * 32 + lane] = make_float2(ubf, __double2float_rd(lb_all));
-            if (ubf > best_ub) { best_ub = ubf; best_it = it; }
-        }
-        // every lane evaluates the group with its largest upper bound exactly: a lower bound close to the maximum ...
-        double ymax = -CUDART_INF;
-        if (best_it >= 0) ymax = sww_group_max(x, best_it * 512 + 16 * lane, n, pst[best_it * 32 + lane] + pbase(best_it), m, km1);
-        const double LB = sww_team_max<WPE>(fmax(warp_max(ymax), warp_max(lbmax)), xch, 0, we, lane);
-        // ... and only groups whose upper bound reaches it can hold a larger sample
-#pragma unroll 1
-        for (int it = we; it < my_groups; it += WPE) {
-            const int i0 = it * 512 + 16 * lane;
-            if ((double)ext[it * 32 + lane].x >= LB && it != best_it) {
-                const double gm = sww_group_max(x, i0, n, pst[it * 32 + lane] + pbase(it), m, km1);
-                ymax = gm > ymax ? gm : ymax;
+            for (int it = we; it < my_groups; it += WPE) {
+                const int i0 = it * 512 + 16 * lane;
+                const uint32_t xm = xmm[it * 32 + lane];
+                const double dmax = u2d(xm >> 16) - m, dmin = u2d(xm & 0xffffu) - m;
+                const double Sd0 = fma(-(double)i0, m, u2d(pst[it * 32 + lane] + pbase(it)));
+                const double Sd_hi = fma(16.0, dmax > 0.0 ? dmax : 0.0, Sd0), Sd_lo = fma(16.0, dmin < 0.0 ? dmin : 0.0, Sd0);
+                const double k_hi = km1 >= 0.0 ? Sd_hi : Sd_lo, k_lo = km1 >= 0.0 ? Sd_lo : Sd_hi;
+                const double ub = fma(km1, k_hi, dmax) + G;
+                const double lb_all = fma(km1, k_lo, dmin) - G;
+                const double lb_top = fma(km1, k_lo, dmax) - G;
+                lbmax = lb_top > lbmax ? lb_top : lbmax;
+                const float ubf = __double2float_ru(ub);
+                ext[it * 32 + lane] = make_float2(ubf, __double2float_rd(lb_all));
+                if (ubf > best_ub) { best_ub = ubf; best_it = it; }
             }
-        }
-        ymax = sww_team_max<WPE>(warp_max(ymax), xch, 1, we, lane);
-        const double thr = ymax * 0.5;
-
-        // ---- pass 1b: threshold mask of y >= thr, first run of >= tx_min_n samples ----
-#pragma unroll (kU1B)
-        for (int it = we; it < NWORDS / 16; it += WPE) {
-            uint32_t b = 0;
-            const int i0 = it * 512 + 16 * lane;
-            if (i0 < n) {
-                const float2 ex = ext[it * 32 + lane];
-                if ((double)ex.x >= thr) {
-                    if ((double)ex.y >= thr) b = (i0 + 8 < n) ? 0xffffu : 0xffu;
-                    else b = sww_group_bits(x, i0, n, pst[it * 32 + lane] + pbase(it), m, km1, thr);
+            // every lane evaluates the group with its largest upper bound exactly: a lower bound close to the maximum ...
+            double ymax = -CUDART_INF;
+            if (best_it >= 0) ymax = sww_group_max(x, best_it * 512 + 16 * lane, n, pst[best_it * 32 + lane] + pbase(best_it), m, km1);
+            const double LB = sww_team_max<WPE>(fmax(warp_max(ymax), warp_max(lbmax)), xch, 0, we, lane);
+            // ... and only groups whose upper bound reaches it can hold a larger sample
+#pragma unroll 1
+            for (int it = we; it < my_groups; it += WPE) {
+                const int i0 = it * 512 + 16 * lane;
+                if ((double)ext[it * 32 + lane].x >= LB && it != best_it) {
+                    const double gm = sww_group_max(x, i0, n, pst[it * 32 + lane] + pbase(it), m, km1);
+                    ymax = gm > ymax ? gm : ymax;
                 }
             }
-            b <<= 16 * (lane & 1);
-            b |= __shfl_xor_sync(FULL, b, 1);
-            if ((lane & 1) == 0) mask[it * 16 + (lane >> 1)] = b;
-        }
-        sww_team_sync<WPE>();
-        int pos, mult;
-        resolve_runs(mask, P.tx_min_n, lane, pos, mult);
+            ymax = sww_team_max<WPE>(warp_max(ymax), xch, 1, we, lane);
+            thr = ymax * 0.5;
 
+            // ---- pass 1b: threshold mask of y >= thr, first run of >= tx_min_n samples ----
+#pragma unroll (kU1B)
+            for (int it = we; it < NWORDS / 16; it += WPE) {
+                uint32_t b = 0;
+                const int i0 = it * 512 + 16 * lane;
+                if (i0 < n) {
+                    const float2 ex = ext[it * 32 + lane];
+                    if ((double)ex.x >= thr) {
+                        if ((double)ex.y >= thr) b = (i0 + 8 < n) ? 0xffffu : 0xffu;
+                        else b = sww_group_bits(x, i0, n, pst[it * 32 + lane] + pbase(it), m, km1, thr);
+                    }
+                }
+                b <<= 16 * (lane & 1);
+                b |= __shfl_xor_sync(FULL, b, 1);
+                if ((lane & 1) == 0) mask[it * 16 + (lane >> 1)] = b;
+            }
+            sww_team_sync<WPE>();
+            int mult;
+            resolve_runs(mask, P.tx_min_n, lane, pos, mult);
+
+        }
         // ---- pass 2 + variants ----
         const int lo_max = n > W ? n - W : 0;
         int lo = (pos >= 1 && P.win_mode == 1) ? pos + P.win_rel_lo : P.win_abs_lo;

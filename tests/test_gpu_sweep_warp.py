@@ -124,6 +124,9 @@ def test_rt_sweep_with_fixed_pickoff_and_ineligible_sets(L, O, handle):
         assert "LGDSP_SWEEP_PATH=warp" in str(e)
     a = _run_general(W, cfg, tau, var, f64=True, handle=handle)   # default dispatch: whichever path, same numbers
     assert np.array_equal(a, b, equal_nan=True)
+    # with the aux outputs the fixed pick-off set needs t50 after all (without them the warp path skips max(y) / the crossing)
+    (a2, aa2), (b2, ba2) = _both(L, handle, W, cfg, tau, var, True)
+    assert np.array_equal(a2, b2, equal_nan=True) and np.array_equal(aa2, ba2, equal_nan=True) and np.array_equal(a2, b, equal_nan=True)
     # CUSP variants are never eligible: demanding the warp path is an error, the default dispatch runs them
     cvar = L.cuspzac_sweep_variants(cfg, "cusp", [L.us(6.0)], [L.us(2.0)], L.ns(16.0), mode="ft")
     with sweep_path("warp"):
