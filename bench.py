@@ -570,10 +570,23 @@ def main():
         nv4 = len(v4.array)
         out4 = torch.empty((B, nv4), dtype=torch.float64, device=dev)
         ms_rt, _ = timed(lambda k: h.gsweep_run_device(sp4, pool[k % n_pool].data_ptr(), B, 8192, v4.array, out4.data_ptr()), xs, 2)
-        b4 = BYTES_IN + nv4 * 8
+        # bytes the computation needs: the samples up to the last look-up of the set (fixed windows: the same for every event; the
+        # kernel reads no sample behind it) + the outputs.  frac_whole_waveform counts all 16 384 input bytes as the other workloads do
+        n_w4 = sp4.sig_dni.n_w
+        last4 = sp4.bl_until + 1
+        for i in range(nv4):
+            t4 = v4.array[i].trap
+            L4 = t4.navg + t4.ngap + t4.navg2
+            nout4 = 8192 - L4 + 1
+            pc4 = min(max((v4.array[i].pickoff_ns - (sp4.t_first_ns + (L4 - 1) * sp4.dt_ns)) / sp4.dt_ns, 0.0), nout4 - 1.0)
+            f4 = min(max(int(round(pc4)) - n_w4 // 2, 0), nout4 - n_w4)
+            last4 = max(last4, f4 + L4 + n_w4)
+        b4 = 2 * min(8192, last4 + 8) + nv4 * 8
+        rate4 = B / (ms_rt * 1e-3 / xs) / 1e9 / peaks["hbm_gbs"]
         extra.append({"workload": f"dsp_trap_rt_optimization: {nv4} rise times, fixed pick-off (src/dsp_filter_optimization.jl:102-133)",
                       "value": world * B * xs / (ms_rt * 1e-3), "unit": "waveforms/s", "ms_per_step": ms_rt / xs,
-                      "roofline": {"frac": B * b4 / (ms_rt * 1e-3 / xs) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_waveform": b4},
+                      "roofline": {"frac": rate4 * b4, "algorithmic_bytes_per_waveform": b4,
+                                   "frac_whole_waveform": rate4 * (BYTES_IN + nv4 * 8)},
                       "kernel": "sweep_warp_kernel"})
 
     kernel_ms = None

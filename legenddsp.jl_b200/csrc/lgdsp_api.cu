@@ -1563,6 +1563,23 @@ static int sweep_prepare(lgdsp_handle* h, const lgdsp_sweep_params* p, const lgd
             D.win_abs_lo = all1 ? 0 : std::max(0, (int)lo);
             D.warp_ok = D.win_steps * 288 <= wmax ? 1 : 0;
         }
+        // fixed pick-offs: the windows are the same for every event -- the exact last look-up of the set (dni_window's arithmetic)
+        D.stream_n = n;
+        if (all0) {
+            long long last = p->bl_until + 1;
+            for (int v = 0; v < nvar; ++v) {
+                const int Lf = sv[v].L, nout = n - Lf + 1;
+                const double tf = std::fma((double)(Lf - 1), p->dt_ns, p->t_first_ns);
+                double pc = (sv[v].pick_ns - tf) / p->dt_ns;
+                if (!(pc >= 0)) pc = 0;
+                if (pc > nout - 1) pc = nout - 1;
+                long long f = (long long)std::nearbyint(pc) - d.n_w / 2;
+                if (f < 0) f = 0;
+                if (f > nout - d.n_w) f = nout - d.n_w;
+                last = std::max(last, f + Lf + d.n_w);
+            }
+            D.stream_n = (int)std::min<long long>(n, last + 8);
+        }
     }
     D.bl_inv_n = 1.0 / (double)(p->bl_until - p->bl_from + 1);
     {

@@ -52,6 +52,7 @@ struct SweepDev {
     // (crossing sample + win_rel_lo); 0: at win_abs_lo
     int warp_ok, win_steps, win_mode, win_rel_lo, win_abs_lo;
     int dt_pow2;             // dt is a power of two: x / dt == x * rdt bit for bit
+    int stream_n, reserved3; // win_mode 0: samples [0, stream_n) cover the baseline window and every look-up of the set
     double rdt;
 };
 cudaError_t sweep_configure(int* max_blocks_per_sm);

@@ -254,24 +254,26 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
 
     for (long long e = blockIdx.x; e < n_events; e += gridDim.x) {
         const uint16_t* __restrict__ x = wf + e * ld;
-        if (threadIdx.x == 0 && e + gridDim.x < n_events) tma_prefetch_l2(wf + (e + gridDim.x) * ld, (uint32_t)n * 2u);
-
         // Fixed pick-offs (win_mode 0) without the aux outputs read nothing that depends on t50: max(y), the threshold mask and the
-        // crossing are skipped (dsp_trap_rt_optimization, src/dsp_filter_optimization.jl:102-133)
+        // crossing are skipped (dsp_trap_rt_optimization, src/dsp_filter_optimization.jl:102-133), and no sample behind the last
+        // look-up of the set (stream_n, exact on the host: the windows do not depend on the event) is read at all
         const bool need_t50 = P.win_mode == 1 || aux != nullptr;
+        const int n_s = need_t50 ? n : min(n, (P.stream_n + 15) & ~15);   // samples of the integer pass (multiple of 8: n is)
+        const int n_it_s = (n_s + 511) >> 9;
+        if (threadIdx.x == 0 && e + gridDim.x < n_events) tma_prefetch_l2(wf + (e + gridDim.x) * ld, (uint32_t)n_s * 2u);
         // ---- pass 1 (integers only): the steps it = we, we + WPE, ...; prefix sums inside the step, group table, step sums ----
         {
             uint32_t carryP = 0;             // (WPE == 1: the steps follow each other, the carries run along)
             unsigned long long carryPP = 0;
             uint4 ra[3], rb[3];   // raw samples of this warp's next three steps
 #pragma unroll
-            for (int q = 0; q < 3; ++q) sww_ld16_raw(x, (we + q * WPE) * 512 + 16 * lane, n, ra[q], rb[q]);
+            for (int q = 0; q < 3; ++q) sww_ld16_raw(x, (we + q * WPE) * 512 + 16 * lane, n_s, ra[q], rb[q]);
 #pragma unroll 1
-            for (int it = we; it < n_it; it += WPE) {
+            for (int it = we; it < n_it_s; it += WPE) {
                 uint32_t v[16];
                 sww_unpack16(ra[0], rb[0], v);
                 ra[0] = ra[1]; rb[0] = rb[1]; ra[1] = ra[2]; rb[1] = rb[2];
-                sww_ld16_raw(x, (it + 3 * WPE) * 512 + 16 * lane, n, ra[2], rb[2]);    // three steps ahead
+                sww_ld16_raw(x, (it + 3 * WPE) * 512 + 16 * lane, n_s, ra[2], rb[2]);    // three steps ahead
                 uint32_t s[16];
                 s[0] = v[0];
 #pragma unroll
@@ -312,11 +314,11 @@ sweep_warp_kernel(const __grid_constant__ SweepDev P, const __grid_constant__ Sw
                 }
                 if (need_t50 && i0 < n) xmm[it * 32 + lane] = (xmax << 16) | xmin;
             }
-            if (WPE == 1 && lane == 0) { cP[n_it] = carryP; cPP[n_it] = (double)carryPP; }
+            if (WPE == 1 && lane == 0) { cP[n_it_s] = carryP; cPP[n_it_s] = (double)carryPP; }
         }
         sww_team_sync<WPE>();
         // P and PP = cumsum(P) at every 512-sample boundary (exact integers; PP < 2^43 in float64)
-        if (WPE > 1 && we == 0 && lane <= n_it) {
+        if (WPE > 1 && we == 0 && lane <= n_it_s) {
             uint32_t cp = 0;
             double cpp = 0.0;
             for (int i = 0; i < lane; ++i) {
