@@ -112,16 +112,15 @@ def test_rt_sweep_with_fixed_pickoff_and_ineligible_sets(L, O, handle):
     wf = L.synth.generate_host(200, first_event=9)
     W = L.RDWaveforms(wf)
     from legenddsp.jl_b200.dsp_filter_optimization import _run_general
-    # fixed pick-off (mode 0): eligible when the absolute reach of the set fits the window, otherwise the CTA kernel serves it
+    # fixed pick-off (mode 0): the warp path skips max(y) / the crossing and reads only the samples up to the last look-up
     var = L.trap_sweep_variants(L.grid_values(cfg.e_grid_rt_trap), [L.us(2.0)], L.ns(16.0), mode="rt", pickoff=cfg.enc_pickoff_trap)
     with sweep_path("cta"):
         b = _run_general(W, cfg, tau, var, f64=True, handle=handle)
-    try:
-        with sweep_path("warp"):
-            a = _run_general(W, cfg, tau, var, f64=True, handle=handle)
-        assert np.array_equal(a, b, equal_nan=True)
-    except Exception as e:
-        assert "LGDSP_SWEEP_PATH=warp" in str(e)
+    with sweep_path("warp"):   # the example grid (1 .. 16 us at ft = 2 us, pick-off 40 us) reaches 2 176 samples: eligible
+        a = _run_general(W, cfg, tau, var, f64=True, handle=handle)
+    assert np.array_equal(a, b, equal_nan=True)
+    ref = O.sweep(L.resolve_sweep_params(cfg, tau, builders=O.OracleBuilders(), out_f64=True), wf, var.array)
+    assert np.allclose(a, ref, rtol=1e-8, atol=1e-6, equal_nan=True)
     a = _run_general(W, cfg, tau, var, f64=True, handle=handle)   # default dispatch: whichever path, same numbers
     assert np.array_equal(a, b, equal_nan=True)
     # with the aux outputs the fixed pick-off set needs t50 after all (without them the warp path skips max(y) / the crossing)
