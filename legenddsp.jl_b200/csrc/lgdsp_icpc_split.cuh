@@ -917,17 +917,23 @@ icpc_extract_kernel(const __grid_constant__ IcpcDev P, const double* __restrict_
                 row[LGDSP_COL_tailmean] = st.mean; row[LGDSP_COL_tailsigma] = st.sigma;
                 row[LGDSP_COL_tailslope] = st.slope; row[LGDSP_COL_tailoffset] = st.offset;
             }
+            // t0 of the inverted waveform (src/dsp_icpc.jl:207) here: warp 1 then resolves one mask, not two (the two long-run
+            // resolutions in a row made it the slowest job of the phase)
+            if (G & LGDSP_GROUP_TIMING) {
+                int pos0i, mult_;
+                resolve_runs(masks + MK_T0INV * NWORDS, P.t0_min_n, lane, pos0i, mult_);
+                if (lane == 0) row[LGDSP_COL_t0_inv] = t0_us(true, pos0i);
+            }
         } else if (wid == 1) {
-            int pos0, pos0i = -1, mult_;
+            int pos0, mult_;
             resolve_runs(masks + MK_T0 * NWORDS, P.t0_min_n, lane, pos0, mult_);
-            if (!lean) resolve_runs(masks + MK_T0INV * NWORDS, P.t0_min_n, lane, pos0i, mult_);
             double t = 0.0;
             if (lane < 5) {
                 t = tx_us(lane);
                 if (G & LGDSP_GROUP_TIMING) row[LGDSP_COL_t10 + lane] = t;
-            } else if (lane == 5 || lane == 6) {
-                t = t0_us(lane == 6, lane == 6 ? pos0i : pos0);
-                if (G & LGDSP_GROUP_TIMING) row[lane == 6 ? LGDSP_COL_t0_inv : LGDSP_COL_t0] = t;
+            } else if (lane == 5) {
+                t = t0_us(false, pos0);
+                if (G & LGDSP_GROUP_TIMING) row[LGDSP_COL_t0] = t;
             }
             const double t90 = __shfl_sync(FULL, t, 3), t0v = __shfl_sync(FULL, t, 5);
             if (lane == 0 && (G & LGDSP_GROUP_TIMING)) row[LGDSP_COL_drift_time] = (t90 - t0v) * 1000.0;
